@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors by running the LIVE reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+Inputs are the deterministic synthetic configs of ``pyxrd_b200.synthetic``
+(rebuilt identically by the tests); outputs are what the unmodified reference
+``pyxrd.calculations`` (v0.8.4, behind the 4-alias compatibility shim of
+``_live_reference.py``) returns for them with the numpy / scipy of this image.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import scipy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+
+import _live_reference  # noqa: E402
+from pyxrd_b200 import synthetic as syn  # noqa: E402
+
+N_CANDIDATES = {"c1": 3, "c2": 3, "c3": 1, "c4": 3, "c5": 2}
+SEED = 2024
+
+
+def fingerprint(mix):
+    """A few numbers that change if the synthetic builders drift."""
+    acc = []
+    for spec in mix.specimens:
+        acc += [float(np.sum(spec.range_theta)), float(spec.goniometer.wavelength)]
+        for phase in spec.phases[0]:
+            acc += [float(np.sum(phase.P)), float(np.trace(phase.W)), float(phase.sigma_star),
+                    float(phase.CSDS.average), float(phase.CSDS.maximum)]
+            for comp in phase.components:
+                acc += [comp.d001, comp.weight, comp.volume, comp.delta_c]
+                acc += [a.pn for a in comp.layer_atoms + comp.interlayer_atoms]
+                acc += [a.default_z for a in comp.layer_atoms + comp.interlayer_atoms]
+    return np.array(acc, dtype=float)
+
+
+def kats(ref, out):
+    """The reference's own known-answer vectors, re-evaluated live."""
+    theta = np.asanyarray([2.2551711385, 2.478038901, 2.7001518288, 2.9214422642, 3.1418428,
+                           3.3612863, 3.5797059197, 3.7970351263])
+    out["kat_theta"] = theta
+    out["kat_lpf"] = ref.goniometer.get_lorentz_polarisation_factor(theta, 12, 2.3, 2.3, 0)
+    out["kat_ads"] = ref.goniometer.get_fixed_to_ads_correction_range(theta, None)
+    out["kat_S"] = np.array(ref.goniometer.get_S(2.5, 2.5))
+    # test_atom_type.py:58-75 goes through AtomType.get_atomic_scattering_factors, which squares
+    # (stl * 0.05); here the calculation-layer function is called on the same abscissa
+    from pyxrd_b200.data_objects import AtomTypeData, AtomData, ComponentData, CSDSData
+    at = AtomTypeData(par_a=np.full(5, 10.2), par_b=np.full(5, 10.2), par_c=20.2, debye=0.0)
+    stl = np.array([0.1152, 0.5756, 1.1469])
+    out["kat_asf_stl"] = stl
+    out["kat_asf"] = ref.atoms.get_atomic_scattering_factor((stl * 0.05) ** 2, at)
+    # test_components.py:24-62 component (H atoms) -- values unpinned upstream, pinned here
+    h = AtomTypeData(par_a=np.asanyarray([0.413048, 0.294953, 0.187491, 0.080701, 0.023736]),
+                     par_b=np.asanyarray([15.569946, 32.398468, 5.711404, 61.889874, 1.334118]),
+                     par_c=0.000049, debye=0)
+    comp = ComponentData(layer_atoms=[AtomData(atom_type=h, pn=1, default_z=0, z=0)],
+                         interlayer_atoms=[AtomData(atom_type=h, pn=1, default_z=0.55, z=0.55)],
+                         volume=1.0, weight=1.0, d001=0.55, default_c=0.6, delta_c=0.02, lattice_d=0.45)
+    sf, phi = ref.components.get_factors(theta, comp)
+    out["kat_comp_sf"], out["kat_comp_phi"] = sf, phi
+    # test_CSDS.py:26-35 distribution
+    csds = CSDSData(average=10, maximum=50, minimum=1, alpha_scale=0.9485, alpha_offset=0.017,
+                    beta_scale=0.1032, beta_offset=0.0034)
+    arr, mean = ref.CSDS.calculate_distribution(csds)
+    out["kat_csds_arr"], out["kat_csds_mean"] = arr, np.array(mean)
+
+
+def run_config(ref, name, out):
+    cfg = syn.CONFIGS[name]
+    truth = cfg.truth()
+    cands = cfg.population(SEED, N_CANDIDATES[name])
+
+    def calc_total(mix):
+        ref.mixture.calculate_mixture(mix)
+        return [np.array(s.total_intensity) for s in mix.specimens]
+
+    t0 = time.time()
+    syn.attach_observed(cands, truth, calc_total)
+    for s, spec in enumerate(truth.specimens):
+        out["%s_observed_s%d" % (name, s)] = spec.observed_intensity
+    allmix = [("truth", truth)] + [("k%d" % i, m) for i, m in enumerate(cands)]
+    rng = np.random.default_rng(77)
+    for tag, mix in allmix:
+        out["%s_%s_fp" % (name, tag)] = fingerprint(mix)
+        mix.parsed = mix.calculated = mix.optimized = False
+        ref.mixture.calculate_mixture(mix)
+        for s, spec in enumerate(mix.specimens):
+            out["%s_%s_corr_s%d" % (name, tag, s)] = np.array(spec.correction)
+            out["%s_%s_pi_s%d" % (name, tag, s)] = np.array(spec.phase_intensities)
+            out["%s_%s_total_s%d" % (name, tag, s)] = np.array(spec.total_intensity)
+        out["%s_%s_residuals" % (name, tag)] = np.array(mix.residuals, dtype=float)
+        # a second, random solution vector through the reference's own unpack path
+        x = np.concatenate([rng.uniform(0.05, 1.0, mix.m), rng.uniform(0.2, 3.0, mix.n),
+                            rng.uniform(0.0, 5.0, mix.o)])
+        out["%s_%s_x" % (name, tag)] = x
+        mix.calculated = False
+        res = ref.mixture._get_residuals(x.copy(), mix)
+        out["%s_%s_x_residuals" % (name, tag)] = np.array(res, dtype=float)
+        for s, spec in enumerate(mix.specimens):
+            out["%s_%s_x_total_s%d" % (name, tag, s)] = np.array(spec.total_intensity)
+        # the optimiser (fresh flags, as get_optimized_residual is called per trial)
+        if name != "c3" or tag == "truth":
+            mix.calculated = mix.optimized = False
+            r = ref.mixture.get_optimized_residual(mix)
+            out["%s_%s_opt_residual" % (name, tag)] = np.array(r, dtype=float)
+            out["%s_%s_opt_fractions" % (name, tag)] = np.array(mix.fractions, dtype=float)
+            out["%s_%s_opt_scales" % (name, tag)] = np.array(mix.scales, dtype=float)
+            out["%s_%s_opt_bgshifts" % (name, tag)] = np.array(mix.bgshifts, dtype=float)
+            out["%s_%s_opt_residuals" % (name, tag)] = np.array(mix.residuals, dtype=float)
+        print("  %s %s done (%.1f s)" % (name, tag, time.time() - t0), flush=True)
+
+
+def main():
+    ref = _live_reference.load()
+    names = sys.argv[1:] or ["kat", "c1", "c2", "c4", "c5", "c3"]
+    for name in names:
+        out = {"versions": np.array("numpy %s scipy %s python %s reference 0.8.4"
+                                    % (np.__version__, scipy.__version__, sys.version.split()[0]))}
+        if name == "kat":
+            kats(ref, out)
+        else:
+            run_config(ref, name, out)
+        path = os.path.join(HERE, "%s.npz" % name)
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes", flush=True)
+
+
+if __name__ == "__main__":
+    main()
