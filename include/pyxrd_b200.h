@@ -1,0 +1,188 @@
+/*
+ * pyxrd_b200 -- C-ABI of the B200 (sm_100a) implementation of PyXRD's matrix-method
+ * hot path (pyxrd.calculations: phase -> diffracted intensity -> specimen pattern ->
+ * mixture residual).
+ *
+ * The reference has no FFI of its own: its boundary is a set of Python module-level
+ * functions taking DataObject graphs.  The Python host layer in
+ * pyxrd_b200/ flattens those graphs ("packing") into the plain arrays below and calls
+ * these entry points through ctypes; INTEGRATION.md shows the binding.  Each entry
+ * point names the reference function(s) (path:line under the reference tree) whose
+ * arithmetic it replaces.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure with a
+ * message available from pyxrd_last_error(); all pointers are HOST pointers unless a
+ * parameter name ends in _dev; all floating point is IEEE double; all work is queued
+ * on the context's CUDA stream and the pyxrd_read_* calls synchronise that stream.
+ * There is no CPU fallback: without a CUDA device pyxrd_create() fails.
+ */
+#ifndef PYXRD_B200_H
+#define PYXRD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pyxrd_ctx pyxrd_ctx;
+
+/* layout strides of the packed parameter tables */
+#define PYXRD_GONIO_STRIDE 12 /* wavelength, soller1, soller2, mcr_2theta, divergence_mode (0 FIXED, 1 AUTOMATIC, 2 other), divergence, has_absorption_correction, absorption, sample_surf_density, sample_length, radius, reserved */
+#define PYXRD_ATYPE_STRIDE 12 /* par_a[5], par_b[5], par_c, debye */
+#define PYXRD_PHASE_I_STRIDE 8 /* G, rank, csds_minimum, csds_maximum, flags, comp_list_begin, matrix_offset, reserved */
+#define PYXRD_PHASE_D_STRIDE 8 /* sigma_star, csds_average, alpha_scale, alpha_offset, beta_scale, beta_offset, reserved x2 */
+#define PYXRD_COMP_D_STRIDE 8  /* d001, default_c, delta_c, lattice_d, volume, weight, reserved x2 */
+#define PYXRD_COMP_I_STRIDE 4  /* atom_begin, n_layer_atoms, n_interlayer_atoms, reserved */
+#define PYXRD_ATOM_D_STRIDE 2  /* pn, default_z */
+
+#define PYXRD_FLAG_VALID_PROBS 1      /* PhaseData.valid_probs (phases.py:109-111) */
+#define PYXRD_FLAG_APPLY_LPF 2        /* PhaseData.apply_lpf (phases.py:88) */
+#define PYXRD_FLAG_APPLY_CORRECTION 4 /* PhaseData.apply_correction (specimen.py:57) */
+
+#define PYXRD_MAX_RANK 64
+#define PYXRD_MAX_COMPONENTS 8
+
+/* Candidate-invariant tables: what SpecimenData / GonioData / AtomTypeData carry
+ * (data_objects.py:35-47,118-172,214-239).  Ragged per-specimen arrays are
+ * concatenated in specimen order. */
+typedef struct {
+    int32_t n_specimens;      /* S */
+    int32_t n_atom_types;     /* T */
+    int32_t n_patterns;       /* Z = len(specimen.z_list) (mixture.py:133-138) */
+    int32_t reserved;
+    const int32_t *spec_npts; /* [S] X_s = len(range_theta) */
+    const double *theta;      /* [sum X_s] SpecimenData.range_theta (radians) */
+    const double *spec_gonio; /* [S][PYXRD_GONIO_STRIDE] */
+    const int32_t *spec_nwl;  /* [S] len(goniometer.wavelength_distribution) */
+    const double *wl_fraction;/* [sum nwl] the f_j of the list, in list order */
+    /* per (specimen, wavelength j, point x), concatenated: the abscissa part of
+     * interp1d(asin(stl*lambda_j/2), ., fill 0)(theta) (specimen.py:66-69): index of the
+     * upper neighbour (or -1 when theta_x lies outside) and the two lerp weights */
+    const int32_t *wl_index;
+    const double *wl_w_hi;
+    const double *wl_w_lo;
+    const double *observed;   /* [S][Z][X_s] = observed_intensity.T */
+    const uint8_t *selected;  /* [sum X_s] SpecimenData.selected_range */
+    const double *atom_types; /* [T][PYXRD_ATYPE_STRIDE] */
+    /* optional [sum X_s]: use these 2 sin(theta)/lambda values instead of deriving them from
+     * theta and the wavelength (get_diffracted_intensity / get_intensity take range_stl as an
+     * argument of their own, phases.py:68,81); NULL otherwise */
+    const double *stl_override;
+} pyxrd_static_desc;
+
+/* Per-candidate parameters: what PhaseData / ComponentData / AtomData / CSDSData /
+ * MixtureData carry (data_objects.py:49-116,174-271). */
+typedef struct {
+    int32_t n_candidates;     /* K trials */
+    int32_t n_phase_slots;    /* M = mixture.m (columns of the phase matrix) */
+    int32_t n_phases;         /* NP parameter blocks */
+    int32_t n_components;     /* NC */
+    int32_t n_atoms;          /* NA */
+    int32_t n_phase_comp;     /* length of phase_comp */
+    int64_t n_matrix;         /* length of matrices */
+    const int32_t *phase_i;   /* [NP][PYXRD_PHASE_I_STRIDE] */
+    const double *phase_d;    /* [NP][PYXRD_PHASE_D_STRIDE] */
+    const int32_t *phase_comp;/* component index lists */
+    const double *matrices;   /* per phase at matrix_offset: W[r*r] then P[r*r], row major */
+    const double *comp_d;     /* [NC][PYXRD_COMP_D_STRIDE] */
+    const int32_t *comp_i;    /* [NC][PYXRD_COMP_I_STRIDE] */
+    const double *atom_d;     /* [NA][PYXRD_ATOM_D_STRIDE] */
+    const int32_t *atom_type; /* [NA] index into atom_types, -1 = None */
+    const int32_t *job_phase; /* [K][S][Z][M] parameter-block index, -1 = None phase */
+    const double *fractions;  /* [K][M]  MixtureData.fractions */
+    const double *scales;     /* [K][S]  MixtureData.scales */
+    const double *bgshifts;   /* [K][S]  MixtureData.bgshifts (already 0 when settings.BGSHIFT is off) */
+} pyxrd_batch_desc;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int pyxrd_create(int device, pyxrd_ctx **out);
+void pyxrd_destroy(pyxrd_ctx *ctx);
+const char *pyxrd_last_error(const pyxrd_ctx *ctx);
+/* use an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+int pyxrd_set_stream(pyxrd_ctx *ctx, void *cuda_stream);
+int pyxrd_synchronize(pyxrd_ctx *ctx);
+/* number of kernels this context has launched so far */
+int64_t pyxrd_launch_count(const pyxrd_ctx *ctx);
+
+/* ---- upload -------------------------------------------------------------------- */
+/* Uploads the tables and runs the table kernels: sin(theta), stl = 2 sin(theta)/lambda
+ * (specimen.py:50), cos^2(2 theta), machine correction (specimen.py:21-43,
+ * goniometer.py:36-37) and the atomic scattering factors (atoms.py:13-38) per
+ * (atom type, point). */
+int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *desc);
+/* Uploads K candidates and runs the per-phase prologue: CSDS distribution + mean
+ * (CSDS.py:13-46, math_tools.py:36-37), progression factors (phases.py:147-151),
+ * absolute scale (phases.py:48-66), interlayer z-stretch (components.py:15-16,42-50). */
+int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc);
+/* Replace only the mixture solution of the resident batch ([K][M], [K][S], [K][S]). */
+int pyxrd_set_solution(pyxrd_ctx *ctx, const double *fractions, const double *scales,
+                       const double *bgshifts);
+
+/* Load phase intensities computed earlier (SpecimenData.phase_intensities, [K][S][M][Z][X_s])
+ * into the resident batch instead of computing them (calculate_scaled_intensities on a
+ * specimen whose patterns already exist, specimen.py:84-88). */
+int pyxrd_set_intensities(pyxrd_ctx *ctx, const double *intensities, int64_t count);
+
+/* ---- compute (asynchronous on the stream) ---------------------------------------- */
+/* All phase patterns of the resident batch: structure factors (atoms.py:40-67,
+ * components.py:18-54, phases.py:20-39), the CSDS-weighted series Re Tr(F W S)*scale
+ * (phases.py:106-158, math_tools.py:16-17), Lorentz-polarisation (goniometer.py:15-34,
+ * phases.py:81-95), machine correction and the wavelength distribution
+ * (specimen.py:45-82).  Result: f64 [K][S][M][Z][X_s] on the device. */
+int pyxrd_compute_intensities(pyxrd_ctx *ctx);
+/* Scale / sum / background and Rp per specimen (specimen.py:84-88,16-19,
+ * statistics.py:22-27, mixture.py:222-257).  Result: residuals f64 [K][1+S]
+ * ([k][0] = mean over specimens), totals f64 [K][S][Z][X_s]; with want_scaled != 0
+ * also scaled_phase_intensities f64 [K][S][M][Z][X_s]. */
+int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled);
+
+/* ---- results (synchronise, device -> host) ---------------------------------------- */
+int64_t pyxrd_intensity_count(const pyxrd_ctx *ctx); /* doubles in the intensity buffer */
+int64_t pyxrd_total_count(const pyxrd_ctx *ctx);     /* doubles in the totals buffer */
+int pyxrd_read_intensities(pyxrd_ctx *ctx, double *out, int64_t count);
+int pyxrd_read_scaled(pyxrd_ctx *ctx, double *out, int64_t count);
+int pyxrd_read_totals(pyxrd_ctx *ctx, double *out, int64_t count);
+int pyxrd_read_residuals(pyxrd_ctx *ctx, double *out, int64_t count);
+int pyxrd_read_correction(pyxrd_ctx *ctx, double *out, int64_t count); /* [sum X_s] */
+/* device addresses of the result buffers, for zero-copy consumers (NCCL gather) */
+int pyxrd_device_buffers(pyxrd_ctx *ctx, double **intensities_dev, double **totals_dev,
+                         double **residuals_dev);
+
+/* ---- one call, host buffers in and out (what a per-generation plugin call does) ---- */
+/* set_batch + compute_intensities + compute_residuals + read residuals [K][1+S];
+ * intensities_out may be NULL (a refinement trial only needs the residuals). */
+int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *residuals_out,
+                        double *intensities_out);
+
+/* ---- leaf helpers (GUI previews; also the unit-level parity hooks) ---------------- */
+/* get_atomic_scattering_factor (atoms.py:13-38): s -> asf, n points, one atom type */
+int pyxrd_leaf_asf(pyxrd_ctx *ctx, const double *s, int64_t n, const double *atom_type, double *out);
+/* get_lorentz_polarisation_factor (goniometer.py:15-34) */
+int pyxrd_leaf_lpf(pyxrd_ctx *ctx, const double *theta, int64_t n, double sigma_star,
+                   double soller1, double soller2, double mcr_2theta, double *out);
+/* calculate_distribution (CSDS.py:13-46): out_arr[maximum+1], out_mean[1];
+ * progression factors (phases.py:147-151) into out_coef[maximum+2] (index = power of Q) */
+int pyxrd_leaf_csds(pyxrd_ctx *ctx, const double *csds6, int minimum, int maximum,
+                    double *out_arr, double *out_mean, double *out_coef);
+/* get_factors (components.py:18-54) / get_structure_factor (atoms.py:40-67) of ONE component on
+ * an arbitrary stl axis: SF and phi as interleaved complex [n]; z_out[NA] = the stretched atom
+ * positions the reference writes back into atom.z (components.py:42-44).  atom_type_rows holds
+ * one PYXRD_ATYPE_STRIDE row per atom; atom_has_type[a] == 0 marks a None atom / atom type. */
+int pyxrd_leaf_component(pyxrd_ctx *ctx, const double *stl, int64_t n, const double *comp_d,
+                         int n_layer, int n_interlayer, const double *atom_d,
+                         const double *atom_type_rows, const uint8_t *atom_has_type,
+                         double *sf_out, double *phi_out, double *z_out);
+
+/* ---- measurement helpers ----------------------------------------------------------- */
+/* CUDA-event durations (ms) of the most recent compute calls, on the context's stream:
+ * ms_out[0] = phase-intensity kernels, [1] = wavelength kernel, [2] = mixture residual kernels,
+ * [3] = per-candidate prologue (set_batch).  Synchronises the stream. */
+int pyxrd_stage_times(pyxrd_ctx *ctx, double *ms_out);
+/* dependent-chain-free DFMA microbenchmark; returns achieved FP64 TFLOP/s (FMA = 2 flop) */
+int pyxrd_dfma_peak(pyxrd_ctx *ctx, int iterations, double *tflops_out, double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYXRD_B200_H */

@@ -1,0 +1,259 @@
+"""Device versions of ``pyxrd/calculations/mixture.py``: same names, same arguments,
+same in-place mutation of the MixtureData / SpecimenData objects.
+
+Phase intensities, scaling / summing and the Rp residual run on the device.  The bounded
+minimisation of ``optimize_mixture`` is driven by the very same scipy L-BFGS-B call as the
+reference (mixture.py:178-184) with the device evaluating the objective; the batched,
+fully device-resident optimiser for whole populations lives in ``pyxrd_b200.batched``.
+"""
+import logging
+import time
+
+import numpy as np
+
+from .. import settings
+from ..packing import BatchPack, StaticPack, collect_atom_types
+from ..runtime import default_context
+from .exceptions import wrap_exceptions
+
+logger = logging.getLogger(__name__)
+
+_epoch = [0]
+
+
+def _inspect_signature_has(func, name):
+    import inspect
+    try:
+        return name in inspect.signature(func).parameters
+    except (TypeError, ValueError):
+        return False
+
+
+# ---- solution vector handling (mixture.py:32-77): host bookkeeping on tiny vectors ------------
+def parse_solution(x, mixture):
+    fractions, scales, bgshifts = mixture.fractions, mixture.scales, mixture.bgshifts
+    scaled = x[:mixture.m] * (1.0 - mixture.sum_static_fractions) / np.sum(x[:mixture.m])
+    np.put(fractions, mixture.selected_fractions, scaled)
+    np.put(scales, mixture.selected_scales, x[mixture.m:mixture.m + mixture.n])
+    np.put(bgshifts, mixture.selected_bgshifts, x[-mixture.o:])
+    return fractions, scales, bgshifts
+
+
+def get_solution(mixture):
+    return np.concatenate((np.take(mixture.fractions, mixture.selected_fractions),
+                           np.take(mixture.scales, mixture.selected_scales),
+                           np.take(mixture.bgshifts, mixture.selected_bgshifts)))
+
+
+def set_solution(x, mixture):
+    mixture.fractions, mixture.scales, mixture.bgshifts = parse_solution(x, mixture)
+
+
+def get_zero_solution(mixture):
+    x0 = np.ones(shape=(mixture.m + mixture.n + mixture.o,))
+    x0[-mixture.o:] = 0.0       # NB: with o == 0 this zeroes everything first, as in the reference
+    x0[:mixture.m] = 1.0 / (1.0 - mixture.sum_static_fractions)
+    return x0
+
+
+def get_bounds(mixture):
+    return ([(0., 1.)] * mixture.m) + ([(1e-3, None)] * mixture.n) + ([(0., None)] * mixture.o)
+
+
+# ---- device residency -------------------------------------------------------------------
+def _make_resident(mixture, ctx, download):
+    """Pack + upload the mixture and compute its phase intensities on ``ctx``.
+
+    ``mixture._b200_epoch`` (a plain int: survives pickling, is no device handle) remembers
+    which upload the context holds, so that later calls on the same parsed mixture reuse the
+    device-resident intensities instead of recomputing them."""
+    specimens = mixture.specimens
+    static = StaticPack(specimens, collect_atom_types(specimens), n_patterns=mixture.z)
+    ctx.set_static(static)
+    batch = BatchPack([mixture], static, bgshift_enabled=bool(settings.get("BGSHIFT")))
+    ctx.set_batch(batch)
+    ctx.compute_intensities()
+    _epoch[0] += 1
+    mixture._b200_epoch = _epoch[0]
+    ctx._resident_epoch = _epoch[0]
+    if download:
+        corr = ctx.read_correction_flat()
+        per_spec = ctx.split_per_specimen(ctx.read_intensities_flat(), (batch.M, static.Z))[0]
+        for s, specimen in enumerate(specimens):
+            if specimen is not None:
+                lo, hi = int(static.offsets[s]), int(static.offsets[s + 1])
+                specimen.correction = corr[lo:hi].copy()
+                specimen.phase_intensities = per_spec[s].copy()
+
+
+def _ensure_resident(mixture, ctx):
+    if getattr(ctx, "_resident_epoch", None) != getattr(mixture, "_b200_epoch", -1):
+        _make_resident(mixture, ctx, download=False)
+
+
+def _device_residuals(mixture, ctx, want_patterns):
+    """residuals [1+S] of the mixture's current fractions / scales / bgshifts"""
+    _ensure_resident(mixture, ctx)
+    S = len(mixture.specimens)
+    bg = np.asarray(mixture.bgshifts, dtype=float) if settings.get("BGSHIFT") else np.zeros(S)
+    ctx.set_solution(np.asarray(mixture.fractions, dtype=float), np.asarray(mixture.scales, dtype=float)[:S], bg[:S])
+    ctx.compute_residuals(want_scaled=want_patterns)
+    return ctx.read_residuals()[0]
+
+
+# ---- the public functions ----------------------------------------------------------------
+def parse_mixture(mixture, force=False):
+    """mixture.py:103-148: bookkeeping of the selected variables + all phase intensities."""
+    if mixture.parsed and not force:
+        return
+    mixture.parsed = False
+    assert mixture.n > 0, "Need at least 1 specimen to optimize phase fractions, scales and background."
+    assert mixture.n == len(mixture.specimens), "Invalid specimen count on mixture data object."
+    assert mixture.m > 0, "Need at least 1 phase in one of the specimen to optimize phase fractions, scales and background."
+    mixture.selected_fractions = np.asanyarray(np.nonzero(mixture.fractions_mask)).flatten()
+    mixture.selected_scales = np.asanyarray(np.nonzero(mixture.scales_mask)).flatten()
+    mixture.selected_bgshifts = np.asanyarray(np.nonzero(mixture.bgshifts_mask)).flatten()
+    mixture.real_m, mixture.real_n, mixture.real_o = mixture.m, mixture.n, mixture.n
+    mixture.m = len(mixture.selected_fractions)
+    mixture.n = len(mixture.selected_scales)
+    mixture.o = len(mixture.selected_bgshifts)
+    sm = np.sum(mixture.fractions)
+    mixture.sum_static_fractions = sm - np.sum(np.take(mixture.fractions, mixture.selected_fractions))
+    if sm != 1.0 and mixture.sum_static_fractions < 0.0 or mixture.sum_static_fractions > 1.0:
+        mixture.fractions = mixture.fractions / sm
+        sm = 1.0
+    mixture.sum_static_fractions = sm - np.sum(np.take(mixture.fractions, mixture.selected_fractions))
+    mixture.z = 0
+    for specimen in mixture.specimens:
+        if specimen is not None:
+            mixture.z = len(specimen.z_list)
+            break
+    assert mixture.z > 0, "Need at least 1 pattern in one of the specimens to optimize phase fractions, scales and background."
+    for specimen in mixture.specimens:
+        if specimen is None:
+            logger.warning("parse_mixture reports: 'None found!'")
+    ctx = default_context()
+    with ctx.lock:
+        _make_resident(mixture, ctx, download=True)
+    mixture.parsed = True
+
+
+@wrap_exceptions
+def calculate_mixture(mixture, force=False):
+    """mixture.py:221-257."""
+    if mixture.calculated and not force:
+        return mixture
+    try:
+        parse_mixture(mixture)
+    except AssertionError:
+        for specimen in mixture.specimens:
+            if specimen is not None:
+                specimen.total_intensity = None
+                specimen.scaled_phase_intensities = None
+        return mixture
+    ctx = default_context()
+    with ctx.lock:
+        res = _device_residuals(mixture, ctx, want_patterns=True)
+        static, batch = ctx._static, ctx._batch
+        totals = ctx.split_per_specimen(ctx.read_totals_flat(), (static.Z,))[0]
+        scaled = ctx.split_per_specimen(ctx.read_scaled_flat(), (batch.M, static.Z))[0]
+    bgs = np.asarray(mixture.bgshifts, dtype=float)
+    residuals = [0.0]
+    for s, specimen in enumerate(mixture.specimens):
+        value = 0.0
+        if specimen is not None:
+            bg = float(bgs[s]) if settings.get("BGSHIFT") else 0.0
+            specimen.background_intensity = bg * specimen.correction
+            specimen.scaled_phase_intensities = scaled[s].copy()
+            specimen.total_intensity = totals[s].copy()
+            if np.size(specimen.observed_intensity) > 0:
+                if settings.get("RESIDUAL_METHOD") != "Rp":
+                    raise NotImplementedError("only the default residual 'Rp' is on the device path "
+                                              "(settings.RESIDUAL_METHOD = %r)" % (settings.get("RESIDUAL_METHOD"),))
+                value = float(res[1 + s])
+            else:
+                logger.warning("calculate_mixture reports: 'Zero observations found!'")
+        residuals.append(value)
+    residuals[0] = np.average(residuals[1:])
+    mixture.residuals = residuals
+    mixture.calculated = True
+    return mixture
+
+
+def _get_residuals(x, mixture):
+    """mixture.py:91-94."""
+    set_solution(x, mixture)
+    mixture = calculate_mixture(mixture)
+    return mixture.residuals
+
+
+def get_residual(mixture):
+    """mixture.py:96-97."""
+    return _get_residuals(get_solution(mixture), mixture)
+
+
+@wrap_exceptions
+def optimize_mixture(mixture, force=False):
+    """mixture.py:150-219: scipy L-BFGS-B (finite-difference gradient, bounds) over
+    [fractions | scales | bgshifts]; the objective is evaluated on the device."""
+    from scipy.optimize import fmin_l_bfgs_b
+    if mixture.optimized and not force:
+        return mixture
+    try:
+        parse_mixture(mixture)
+    except AssertionError:
+        if settings.get("DEBUG"):
+            raise
+        return mixture
+    x0 = get_zero_solution(mixture)
+    bounds = get_bounds(mixture)
+    ctx = default_context()
+    no_obs = [s for s, sp in enumerate(mixture.specimens) if sp is None or np.size(sp.observed_intensity) == 0]
+
+    def objective(x):
+        mixture.calculated = False
+        set_solution(x, mixture)
+        with ctx.lock:
+            res = _device_residuals(mixture, ctx, want_patterns=False)
+        if no_obs:
+            per = [0.0 if s in no_obs else res[1 + s] for s in range(len(mixture.specimens))]
+            return np.average(per)
+        return res[0]
+
+    t1 = time.time()
+    kwargs = dict(approx_grad=True, bounds=bounds)
+    if _inspect_signature_has(fmin_l_bfgs_b, "iprint"):
+        kwargs["iprint"] = -1
+    lastx, residual, info = fmin_l_bfgs_b(objective, x0, **kwargs)
+    if np.isscalar(residual):
+        residual = np.array([residual])
+    logger.debug('%s took %0.3f ms' % ("optimize_mixture", (time.time() - t1) * 1000.0))
+    fractions, scales, bgshifts = parse_solution(lastx, mixture)
+    fractions = fractions.flatten()
+    sum_frac = np.sum(fractions)
+    if sum_frac == 0.0 and len(fractions) > 0:
+        fractions[0] = 1.0
+        sum_frac = 1.0
+    fractions = np.around((fractions / sum_frac), 6)
+    scales *= sum_frac
+    scales = scales.round(6)
+    mixture.fractions = fractions
+    mixture.scales = scales
+    mixture.bgshifts = bgshifts
+    mixture.residual = residual
+    mixture.calculated = False
+    mixture.optimized = True
+    return mixture
+
+
+@wrap_exceptions
+def calculate_and_optimize_mixture(mixture):
+    """mixture.py:259-266."""
+    return calculate_mixture(optimize_mixture(mixture))
+
+
+@wrap_exceptions
+def get_optimized_residual(mixture):
+    """mixture.py:268-276: the optimiser's final objective value (1-element array)."""
+    mixture = calculate_and_optimize_mixture(mixture)
+    return mixture.residual

@@ -1,0 +1,61 @@
+"""Device versions of ``pyxrd/calculations/phases.py``."""
+import logging
+
+import numpy as np
+
+from ..data_objects import GonioData, SpecimenData
+from ..packing import BatchPack, StaticPack, collect_atom_types
+from ..runtime import default_context
+
+logger = logging.getLogger(__name__)
+
+
+class _Mix(object):
+    pass
+
+
+def _single_phase_pattern(range_theta, range_stl, soller1, soller2, mcr_2theta, phase, with_lpf):
+    theta = np.ascontiguousarray(range_theta, dtype=float).ravel()
+    stl = np.ascontiguousarray(range_stl, dtype=float).ravel()
+    if theta.size != stl.size:
+        raise ValueError("range_theta and range_stl differ in length")
+    # divergence_mode "NONE": no machine correction is part of get_intensity (phases.py:81-95)
+    gon = GonioData(wavelength=1.0, soller1=soller1, soller2=soller2, mcr_2theta=mcr_2theta, divergence_mode="NONE",
+                    divergence=0.0, has_absorption_correction=False, absorption=0.0, sample_surf_density=0.0,
+                    sample_length=0.0, radius=1.0, wavelength_distribution=[])
+    spec = SpecimenData(goniometer=gon, range_theta=theta, selected_range=None, z_list=[0.0], phases=[[phase]],
+                        observed_intensity=np.zeros((theta.size, 1)))
+    mix = _Mix()
+    mix.specimens, mix.fractions, mix.scales, mix.bgshifts = [spec], np.ones(1), np.ones(1), np.zeros(1)
+    saved = phase.apply_lpf
+    ctx = default_context()
+    with ctx.lock:
+        try:
+            phase.apply_lpf = bool(with_lpf and saved)
+            static = StaticPack([spec], collect_atom_types([spec]), n_patterns=1, stl_override=stl)
+            batch = BatchPack([mix], static)
+        finally:
+            phase.apply_lpf = saved
+        ctx.set_static(static)
+        ctx.set_batch(batch)
+        ctx.compute_intensities()
+        return ctx.read_intensities_flat().reshape(np.shape(range_stl))
+
+
+def get_diffracted_intensity(range_theta, range_stl, phase):
+    """phases.py:68-79,106-158: one phase, no LPF.  Invalid probabilities -> zeros."""
+    if phase.type == "AbtractPhase":
+        raise NotImplementedError
+    if phase.type == "Phase" and not phase.valid_probs:
+        logger.debug("- calc: get_diffracted_intensity reports: 'Invalid probability found!'")
+        return np.zeros_like(np.asarray(range_stl, dtype=float))
+    return _single_phase_pattern(range_theta, range_stl, 1.0, 1.0, 0.0, phase, with_lpf=False)
+
+
+def get_intensity(range_theta, range_stl, soller1, soller2, mcr_2theta, phase):
+    """phases.py:81-95: one phase with the Lorentz-polarisation factor (if ``apply_lpf``)."""
+    if phase.type == "AbtractPhase":
+        raise NotImplementedError
+    if phase.type == "Phase" and not phase.valid_probs:
+        return np.zeros_like(np.asarray(range_stl, dtype=float))
+    return _single_phase_pattern(range_theta, range_stl, soller1, soller2, mcr_2theta, phase, with_lpf=True)

@@ -1,0 +1,803 @@
+// Device code of the pyxrd_b200 hot path (sm_100a, fp64).
+//
+// Kernel map (reference = pyxrd/calculations/*, v0.8.4):
+//   k_specimen_tables   specimen.py:21-43,50  goniometer.py:36-37      per-point static tables
+//   k_asf_table         atoms.py:13-38                                   ASF per (atom type, point)
+//   k_phase_prologue    CSDS.py:13-46 math_tools.py:36-37 phases.py:48-66,147-151
+//   k_component_z       components.py:15-16,40-50                        interlayer z-stretch
+//   k_phase_small<R,G>  atoms.py:40-67 components.py:18-54 phases.py:20-39,106-158
+//   k_phase_staged<R,G> goniometer.py:15-34 phases.py:81-95 specimen.py:45-62   (ranks 16, 27)
+//   k_phase_generic     same, any rank <= 64
+//   k_wavelength        specimen.py:64-74
+//   k_mixture_residual  specimen.py:84-88,16-19 statistics.py:22-27 mixture.py:242-253
+//
+// The series: with u_I = SF_comp(I), F = conj(u) u^T, W, S = mean*Id + sum_n coef_n Q^n,
+// Q = P diag(phi), the reference's Re Tr(F W S) equals Re( a^T (S b) ) with a = W^T u,
+// b = conj(u); S b is evaluated by the vector Horner recurrence y <- P (phi o (y + coef_n b)),
+// O(N r^2) real x complex MACs per point instead of the reference's O(N r^3) matrix powers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PX_TPB 128          // threads (= 2-theta points) per block in the phase kernels
+#define PX_GEN_TPB 64       // generic-rank fallback
+#define PX_TWO_PI 6.283185307179586        // python: 2 * math.pi
+#define PX_PI 3.141592653589793
+#define PX_SQRT2PI 2.5066282746310002      // math.sqrt(2 * pi)
+#define PX_SQRT8 2.8284271247461903        // math.sqrt(8)
+
+struct StaticDev {
+    int S, T, Z, maxX;
+    long long sumX;
+    const int *spec_npts;        // [S]
+    const long long *spec_off;   // [S+1]
+    const double *gonio;         // [S][12]
+    const double *derived;       // [S][8]: pol, S_soller, S_soller^2, obs_den
+    const double *theta, *sin_t, *stl, *c2t2, *corr;   // [sumX]
+    const double *asf;           // [T][sumX]
+    const int *spec_nwl;         // [S]
+    const int *wl_first;         // [S] first entry in wl_fraction
+    const long long *wl_off;     // [S] offset of (s, j=0, x=0) in wl_index / weights
+    const double *wl_fraction;
+    const int *wl_index;
+    const double *wl_w_hi, *wl_w_lo;
+    const double *observed;      // [S][Z][X_s] at Z*spec_off[s]
+    const unsigned char *selected;
+    const double *atypes;        // [T][12]
+};
+
+struct BatchDev {
+    int K, M, NP, NC, NA, ncap;      // ncap = stride of coef
+    long long cand_stride;           // doubles per candidate in the intensity buffer = M*Z*sumX
+    const int *phase_i;              // [NP][8]
+    const double *phase_d;           // [NP][8]
+    const int *phase_comp;
+    const double *matrices;
+    const double *comp_d;            // [NC][8]
+    const int *comp_i;               // [NC][4]
+    const double *atom_d;            // [NA][2]
+    const int *atom_type;            // [NA]
+    double *atom_z;                  // [NA]   derived
+    double *phase_x;                 // [NP][4] derived: mean, abs_scale, ntop
+    double *coef;                    // [NP][ncap] derived, index = power of Q
+    const int *job_pb, *job_spec;    // [NJ]
+    const long long *job_out;        // [NJ]
+    const double *fractions, *scales, *bgshifts;   // [K][M], [K][S], [K][S]
+    double *intensities;             // [K][S][M][Z][X_s]
+    double *scaled;                  // same shape (optional)
+    double *totals;                  // [K][S][Z][X_s]
+    double *residuals;               // [K][1+S]
+};
+
+// ---------------------------------------------------------------------------------
+// static tables
+// ---------------------------------------------------------------------------------
+__global__ void k_specimen_derived(int S, const double *gonio, double *derived) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const double *g = gonio + s * 12;
+    double mcr = g[3];
+    double c = cos(mcr * (PX_PI / 180.0));                 // np.cos(np.radians(mcr)) ** 2
+    double h1 = g[1] * 0.5, h2 = g[2] * 0.5;
+    double Ss = sqrt(__dadd_rn(__dmul_rn(h1, h1), __dmul_rn(h2, h2)));   // goniometer.py:15-18
+    derived[s * 8 + 0] = __dmul_rn(c, c);
+    derived[s * 8 + 1] = Ss;
+    derived[s * 8 + 2] = __dmul_rn(Ss, Ss);
+    // sample-length factor L/(R tan(div)) (specimen.py:41)
+    double div = g[5];
+    derived[s * 8 + 4] = g[9] / __dmul_rn(g[10], tan(div * (PX_PI / 180.0)));
+}
+
+__global__ void k_specimen_tables(StaticDev st, double *sin_t, double *stl, double *c2t2, double *corr,
+                                  const double *stl_override) {
+    const int s = blockIdx.y;
+    const int X = st.spec_npts[s];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= X) return;
+    const long long gx = st.spec_off[s] + x;
+    const double *g = st.gonio + s * 12;
+    const double th = st.theta[gx];
+    const double sn = sin(th);
+    sin_t[gx] = sn;
+    stl[gx] = stl_override ? stl_override[gx] : __ddiv_rn(__dmul_rn(2.0, sn), g[0]);   // 2 * sin(theta) / wavelength
+    const double c2 = cos(__dmul_rn(2.0, th));
+    c2t2[gx] = __dmul_rn(c2, c2);
+    // machine correction, specimen.py:21-43
+    double c = 1.0;
+    const int mode = (int)g[4];
+    if (mode == 1) c = __dmul_rn(c, sn);                    // AUTOMATIC: * sin(theta)
+    if (g[6] > 0.0) {
+        const double mu = __dmul_rn(__dmul_rn(g[7], g[8]), 1e-3);
+        if (mu > 0.0) c = __dmul_rn(c, fmin(1.0 - exp(__ddiv_rn(__dmul_rn(-2.0, mu), sn)), 1.0));
+    }
+    if (mode == 0 && g[5] > 0.0) c = __dmul_rn(c, fmin(__dmul_rn(sn, st.derived[s * 8 + 4]), 1.0));
+    corr[gx] = c;
+}
+
+__device__ __forceinline__ double asf_value(const double *__restrict__ at, double s) {
+    // (((a1 e1 + a2 e2) + a3 e3) + a4 e4) + a5 e5, + c, * exp(-B s)   (atoms.py:33-34)
+    double acc = __dmul_rn(at[0], exp(__dmul_rn(-at[5], s)));
+#pragma unroll
+    for (int i = 1; i < 5; ++i) acc = __dadd_rn(acc, __dmul_rn(at[i], exp(__dmul_rn(-at[5 + i], s))));
+    acc = __dadd_rn(acc, at[10]);
+    return __dmul_rn(acc, exp(__dmul_rn(-at[11], s)));
+}
+
+__global__ void k_asf_table(StaticDev st, double *asf) {
+    const long long gx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (gx >= st.sumX) return;
+    const double v = __dmul_rn(st.stl[gx], 0.05);
+    asf[(long long)t * st.sumX + gx] = asf_value(st.atypes + t * 12, __dmul_rn(v, v));
+}
+
+__global__ void k_leaf_asf(const double *s, long long n, const double *at, double *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = asf_value(at, s[i]);
+}
+
+// sum |observed| over the selected points of all Z patterns of one specimen (statistics.py:27 denominator)
+__global__ void k_observed_norm(StaticDev st, double *derived) {
+    const int s = blockIdx.x;
+    const int X = st.spec_npts[s];
+    const double *obs = st.observed + (long long)st.Z * st.spec_off[s];
+    const unsigned char *sel = st.selected + st.spec_off[s];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < st.Z * X; i += blockDim.x)
+        if (sel[i % X]) acc += fabs(obs[i]);
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) derived[s * 8 + 3] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// per-candidate prologue
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double lognormal_dev(double T, double a, double b) {
+    // exp(-(log(T) - a) ** 2 / (2.0 * b ** 2)) / (sqrt2pi * abs(b) * T)     math_tools.py:36-37
+    const double d = log(T) - a;
+    return exp(-(d * d) / (2.0 * (b * b))) / (PX_SQRT2PI * fabs(b) * T);
+}
+
+// q_T (normalised) into arr[0..maximum], mean, and coefficient-by-power table cpow[0..maximum+1]
+__device__ void csds_series(const double *pd, int nmin, int nmax, double *arr, double *mean_out,
+                            double *cpow, int *ntop_out) {
+    const double lavg = log(pd[1]);
+    const double a = pd[2] * lavg + pd[3];
+    const double b = sqrt(pd[4] * lavg + pd[5]);
+    double total = 0.0, mean = 0.0;
+    for (int T = nmin; T <= nmax; ++T) {                   // CSDS.py:29-36,40-44: key int(T), T = max(min+i, 1e-50)
+        const double q = lognormal_dev(fmax((double)T, 1e-50), a, b);
+        total += q;
+        mean += (double)T * q;
+    }
+    *mean_out = mean / total;
+    if (arr) {
+        for (int T = 0; T <= nmax; ++T) arr[T] = 0.0;
+        for (int T = (nmin > 0 ? nmin : 0); T <= nmax; ++T) arr[T] = lognormal_dev(fmax((double)T, 1e-50), a, b) / total;
+    }
+    // coef_n = 2 sum_{m>n} (m-n) q_m (phases.py:147-151) by the two running sums
+    //   tail(n) = sum_{m>n} q_m,  c(n-1) = c(n) + tail(n-1)     (all terms positive: no cancellation)
+    for (int n = 0; n <= nmax + 1; ++n) cpow[n] = 0.0;
+    double tail = 0.0, c = 0.0;
+    int ntop = 0;
+    for (int n = nmax; n >= 0; --n) {
+        // here: tail = sum_{m>n} q_m, c = sum_{m>n} (m-n) q_m
+        if (n >= nmin) {
+            const int power = (n >= 1) ? n : nmax + 1;     // Qn[n-1] with python wrap-around for n = 0
+            cpow[power] += 2.0 * c;
+            if (c != 0.0 && power > ntop) ntop = power;
+        }
+        const double qn = (n >= nmin && n >= 1) ? lognormal_dev((double)n, a, b) / total : 0.0;
+        tail += qn;
+        c += tail;
+    }
+    *ntop_out = ntop;
+}
+
+__global__ void k_phase_prologue(BatchDev bt) {
+    const int pb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pb >= bt.NP) return;
+    const int *pi = bt.phase_i + pb * 8;
+    const double *pd = bt.phase_d + pb * 8;
+    double *px = bt.phase_x + pb * 4;
+    if (!(pi[4] & 1)) { px[0] = 0.0; px[1] = 0.0; px[2] = 0.0; return; }
+    const int G = pi[0], r = pi[1];
+    double mean;
+    int ntop;
+    csds_series(pd, pi[2], pi[3], nullptr, &mean, bt.coef + (long long)pb * bt.ncap, &ntop);
+    // absolute scale, phases.py:48-66 (first G diagonal entries of W)
+    const double *W = bt.matrices + pi[6];
+    double vol = 0.0, d001 = 0.0, dens = 0.0;
+    for (int i = 0; i < G; ++i) {
+        const double *cd = bt.comp_d + bt.phase_comp[pi[5] + i] * 8;
+        const double w = W[i * r + i];
+        vol += cd[4] * w;
+        d001 += cd[0] * w;
+        dens += cd[5] * w / cd[4];
+    }
+    const double mass = mean * (vol * vol) * dens;
+    px[0] = mean;
+    px[1] = (mass != 0.0) ? d001 / mass : 0.0;
+    px[2] = (double)ntop;
+}
+
+__global__ void k_component_z(BatchDev bt) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= bt.NC) return;
+    const double *cd = bt.comp_d + ci * 8;
+    const int *cc = bt.comp_i + ci * 4;
+    const double lattice_d = cd[3];
+    const double zf = __ddiv_rn(cd[0] - lattice_d, cd[1] - lattice_d);   // components.py:36
+    for (int a = 0; a < cc[1] + cc[2]; ++a) {
+        const double z0 = bt.atom_d[(cc[0] + a) * 2 + 1];
+        bt.atom_z[cc[0] + a] = (a < cc[1]) ? z0 : __dadd_rn(lattice_d, __dmul_rn(zf, z0 - lattice_d));
+    }
+}
+
+__global__ void k_leaf_csds(const double *pd, int nmin, int nmax, double *arr, double *mean, double *cpow) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int ntop;
+        csds_series(pd, nmin, nmax, arr, mean, cpow, &ntop);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// phase kernels: shared-memory staging of one phase parameter block
+// ---------------------------------------------------------------------------------
+#define PX_MAX_ATOMS 256     // atoms per phase (all components)
+
+struct PhaseSmem {          // header living at the start of dynamic shared memory
+    int comp_first[8];      // first atom (local index) of component c
+    int comp_count[8];
+    double comp_d001[8];
+    double comp_delta[8];
+    double atom_arg[PX_MAX_ATOMS];   // (2 pi) * z
+    double atom_pn[PX_MAX_ATOMS];
+    int atom_type[PX_MAX_ATOMS];
+};
+
+// Lorentz-polarisation factor for one point (goniometer.py:20-34)
+__device__ __forceinline__ double lpf_value(double st, double c2t2, double sigma_star, double Ss, double Ss2, double pol) {
+    const double sig = fmax(sigma_star, 1e-18);
+    const double Q = Ss / ((PX_SQRT8 * st) * sig);
+    const double T = erf(Q) * PX_SQRT2PI / ((2.0 * sig) * Ss) - (2.0 * st) * (1.0 - exp(-(Q * Q))) / Ss2;
+    return T * (1.0 + pol * c2t2) / st;
+}
+
+__global__ void k_leaf_lpf(const double *theta, long long n, double sigma_star, double s1, double s2,
+                           double mcr, double *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double c = cos(mcr * (PX_PI / 180.0));
+    const double h1 = s1 * 0.5, h2 = s2 * 0.5;
+    const double Ss = sqrt(__dadd_rn(__dmul_rn(h1, h1), __dmul_rn(h2, h2)));
+    const double th = theta[i];
+    const double c2 = cos(2.0 * th);
+    out[i] = lpf_value(sin(th), __dmul_rn(c2, c2), sigma_star, Ss, __dmul_rn(Ss, Ss), __dmul_rn(c, c));
+}
+
+// cooperative load of the component / atom lists of phase `pb` into shared memory
+__device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int G, PhaseSmem *ps) {
+    const int *pi = bt.phase_i + pb * 8;
+    if (threadIdx.x == 0) {
+        int first = 0;
+        for (int c = 0; c < G; ++c) {
+            const int ci = bt.phase_comp[pi[5] + c];
+            const int *cc = bt.comp_i + ci * 4;
+            ps->comp_first[c] = first;
+            ps->comp_count[c] = cc[1] + cc[2];
+            ps->comp_d001[c] = bt.comp_d[ci * 8 + 0];
+            ps->comp_delta[c] = bt.comp_d[ci * 8 + 2];
+            first += cc[1] + cc[2];
+        }
+    }
+    __syncthreads();
+    for (int c = 0; c < G; ++c) {
+        const int ci = bt.phase_comp[pi[5] + c];
+        const int a0 = bt.comp_i[ci * 4];
+        for (int a = threadIdx.x; a < ps->comp_count[c]; a += blockDim.x) {
+            const int l = ps->comp_first[c] + a;
+            ps->atom_arg[l] = __dmul_rn(PX_TWO_PI, bt.atom_z[a0 + a]);    // 2 * pi * atom.z
+            ps->atom_pn[l] = bt.atom_d[(a0 + a) * 2];
+            ps->atom_type[l] = bt.atom_type[a0 + a];
+        }
+    }
+}
+
+// one atom: (asf * pn) * exp(i * ((2 pi z) * stl))     (atoms.py:64)
+__device__ __forceinline__ void atom_term(double asf, double pn, double arg2piz, double stl, double &sr, double &si) {
+    const double f = __dmul_rn(asf, pn);
+    double sn, cs;
+    sincos(__dmul_rn(arg2piz, stl), &sn, &cs);
+    sr = fma(f, cs, sr);
+    si = fma(f, sn, si);
+}
+
+// phi = exp(2 pi stl (i d001 - pi delta_c stl))      (components.py:53)
+__device__ __forceinline__ void phase_factor(double stl, double d001, double delta_c, double &pr, double &pi_) {
+    const double A = __dmul_rn(PX_TWO_PI, stl);
+    const double re = __dmul_rn(A, -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl));
+    double sn, cs;
+    sincos(__dmul_rn(A, d001), &sn, &cs);
+    const double e = exp(re);
+    pr = e * cs;
+    pi_ = e * sn;
+}
+
+// structure factor SF_c and phase factor phi_c of component c at one point
+// (atoms.py:40-67, components.py:18-54)
+__device__ __forceinline__ void component_factors(const PhaseSmem *ps, int c, double stl, const double *__restrict__ asf_col,
+                                                  long long sumX, double &ur, double &ui, double &pr, double &pi_) {
+    double sr = 0.0, si = 0.0;
+    const int a0 = ps->comp_first[c], a1 = a0 + ps->comp_count[c];
+    for (int a = a0; a < a1; ++a) {
+        const int t = ps->atom_type[a];
+        if (t < 0) continue;                                  // None atom type -> zeros (atoms.py:65-67)
+        atom_term(__ldg(asf_col + (long long)t * sumX), ps->atom_pn[a], ps->atom_arg[a], stl, sr, si);
+    }
+    ur = sr;
+    ui = si;
+    phase_factor(stl, ps->comp_d001[c], ps->comp_delta[c], pr, pi_);
+}
+
+// everything after Re(a^T S b): absolute scale, LPF, machine correction (phases.py:158,81-95, specimen.py:57-62)
+__device__ __forceinline__ double finish_point(double tr, double abs_scale, int flags, double sigma_star,
+                                               const StaticDev &st, int s, long long gx) {
+    double I = tr * abs_scale;
+    if (flags & 2) {
+        const double *d = st.derived + s * 8;
+        I = I * lpf_value(st.sin_t[gx], st.c2t2[gx], sigma_star, d[1], d[2], d[0]);
+    }
+    if (flags & 4) I = I * st.corr[gx];
+    return I;
+}
+
+// ---- ranks up to 9: every vector in registers ------------------------------------
+template <int R, int G>
+__global__ void __launch_bounds__(PX_TPB) k_phase_small(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
+    constexpr int REPS = R / G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PhaseSmem *ps = reinterpret_cast<PhaseSmem *>(smem_raw);
+    double *sP = reinterpret_cast<double *>(smem_raw + sizeof(PhaseSmem));   // [R][R]
+    double *sWG = sP + R * R;                                               // [G][R]
+    double *sCoef = sWG + G * R;                                            // [ntop+1]
+
+    const int job = jobs[blockIdx.x];
+    const int pb = bt.job_pb[job], s = bt.job_spec[job];
+    const int X = st.spec_npts[s];
+    const int x0 = blockIdx.y * PX_TPB;
+    if (x0 >= X) return;
+    const int *pi = bt.phase_i + pb * 8;
+    const double *px = bt.phase_x + pb * 4;
+    const int ntop = (int)px[2];
+    const double mean = px[0], abs_scale = px[1];
+    const int flags = pi[4];
+    const double sigma_star = bt.phase_d[pb * 8];
+
+    load_phase_lists(bt, pb, G, ps);
+    {
+        const double *W = bt.matrices + pi[6];
+        const double *P = W + R * R;
+        for (int i = threadIdx.x; i < R * R; i += PX_TPB) sP[i] = P[i];
+        for (int i = threadIdx.x; i < G * R; i += PX_TPB) {       // WG[c][K] = sum_{J in c} W[J][K]
+            const int c = i / R, K = i % R;
+            double acc = 0.0;
+            for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
+            sWG[i] = acc;
+        }
+        const double *coef = bt.coef + (long long)pb * bt.ncap;
+        for (int i = threadIdx.x; i <= ntop; i += PX_TPB) sCoef[i] = coef[i];
+    }
+    __syncthreads();
+
+    const int x = x0 + threadIdx.x;
+    if (x >= X) return;
+    const long long gx = st.spec_off[s] + x;
+    const double stl = st.stl[gx];
+
+    double ur[G], ui[G], pr[G], pim[G], gr[G], gi[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        component_factors(ps, c, stl, st.asf + gx, st.sumX, ur[c], ui[c], pr[c], pim[c]);
+        gr[c] = pr[c] * ur[c] + pim[c] * ui[c];          // g = phi * conj(u)
+        gi[c] = pim[c] * ur[c] - pr[c] * ui[c];
+    }
+    double yr[R], yi[R];
+#pragma unroll
+    for (int I = 0; I < R; ++I) { yr[I] = 0.0; yi[I] = 0.0; }
+    for (int n = ntop; n >= 1; --n) {
+        const double cn = sCoef[n];
+        double wr[R], wi[R];
+#pragma unroll
+        for (int I = 0; I < R; ++I) {                     // w = phi o (y + c_n b)
+            const int c = I / REPS;
+            wr[I] = fma(pr[c], yr[I], fma(-pim[c], yi[I], cn * gr[c]));
+            wi[I] = fma(pr[c], yi[I], fma(pim[c], yr[I], cn * gi[c]));
+        }
+#pragma unroll
+        for (int I = 0; I < R; ++I) {                     // y = P w
+            double ar = 0.0, ai = 0.0;
+#pragma unroll
+            for (int J = 0; J < R; ++J) {
+                const double p = sP[I * R + J];
+                ar = fma(p, wr[J], ar);
+                ai = fma(p, wi[J], ai);
+            }
+            yr[I] = ar;
+            yi[I] = ai;
+        }
+    }
+    // Re( sum_K a_K (mean b_K + y_K) ), a_K = sum_c u_c WG[c][K], b_K = conj(u_comp(K))
+    double tr = 0.0;
+#pragma unroll
+    for (int K = 0; K < R; ++K) {
+        const int ck = K / REPS;
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+            const double w = sWG[c * R + K];
+            ar = fma(ur[c], w, ar);
+            ai = fma(ui[c], w, ai);
+        }
+        const double sr = fma(mean, ur[ck], yr[K]);
+        const double si = fma(-mean, ui[ck], yi[K]);
+        tr += ar * sr - ai * si;
+    }
+    bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, sigma_star, st, s, gx);
+}
+
+// ---- ranks 16 / 27: w in registers, the new vector staged through shared memory ----
+template <int R, int G>
+__global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
+    constexpr int REPS = R / G;
+    constexpr int RB = (R + 3) / 4;                      // row blocks of 4
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PhaseSmem *ps = reinterpret_cast<PhaseSmem *>(smem_raw);
+    double *sPb = reinterpret_cast<double *>(smem_raw + sizeof(PhaseSmem));  // [RB][R][4]: P[4*ib+q][J]
+    double *sWG = sPb + RB * R * 4;                                          // [G][R]
+    double2 *stage = reinterpret_cast<double2 *>(sWG + G * R + (G * R & 1)); // [R][TPB]
+    double *sCoef = reinterpret_cast<double *>(stage + R * PX_TPB);
+
+    const int job = jobs[blockIdx.x];
+    const int pb = bt.job_pb[job], s = bt.job_spec[job];
+    const int X = st.spec_npts[s];
+    const int x0 = blockIdx.y * PX_TPB;
+    if (x0 >= X) return;
+    const int *pi = bt.phase_i + pb * 8;
+    const double *px = bt.phase_x + pb * 4;
+    const int ntop = (int)px[2];
+    const double mean = px[0], abs_scale = px[1];
+    const int flags = pi[4];
+    const double sigma_star = bt.phase_d[pb * 8];
+
+    load_phase_lists(bt, pb, G, ps);
+    {
+        const double *W = bt.matrices + pi[6];
+        const double *P = W + R * R;
+        for (int i = threadIdx.x; i < RB * R * 4; i += PX_TPB) {
+            const int q = i & 3, J = (i >> 2) % R, ib = (i >> 2) / R;
+            const int I = ib * 4 + q;
+            sPb[i] = (I < R) ? P[I * R + J] : 0.0;
+        }
+        for (int i = threadIdx.x; i < G * R; i += PX_TPB) {
+            const int c = i / R, K = i % R;
+            double acc = 0.0;
+            for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
+            sWG[i] = acc;
+        }
+        const double *coef = bt.coef + (long long)pb * bt.ncap;
+        for (int i = threadIdx.x; i <= ntop; i += PX_TPB) sCoef[i] = coef[i];
+    }
+    __syncthreads();
+
+    const int x = x0 + threadIdx.x;
+    if (x >= X) return;
+    const long long gx = st.spec_off[s] + x;
+    const double stl = st.stl[gx];
+
+    double ur[G], ui[G], pr[G], pim[G], gr[G], gi[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        component_factors(ps, c, stl, st.asf + gx, st.sumX, ur[c], ui[c], pr[c], pim[c]);
+        gr[c] = pr[c] * ur[c] + pim[c] * ui[c];
+        gi[c] = pim[c] * ur[c] - pr[c] * ui[c];
+    }
+    double wr[R], wi[R];
+    {
+        const double cn = (ntop >= 1) ? sCoef[ntop] : 0.0;
+#pragma unroll
+        for (int J = 0; J < R; ++J) { wr[J] = cn * gr[J / REPS]; wi[J] = cn * gi[J / REPS]; }
+    }
+    double tr = 0.0;
+    double2 *mine = stage + threadIdx.x;
+    for (int n = ntop; n >= 1; --n) {
+        const double cnext = (n > 1) ? sCoef[n - 1] : 0.0;
+        for (int ib = 0; ib < RB; ++ib) {
+            const double4 *prow = reinterpret_cast<const double4 *>(sPb + ib * R * 4);
+            double a0r = 0, a0i = 0, a1r = 0, a1i = 0, a2r = 0, a2i = 0, a3r = 0, a3i = 0;
+#pragma unroll
+            for (int J = 0; J < R; ++J) {
+                const double4 p = prow[J];
+                a0r = fma(p.x, wr[J], a0r); a0i = fma(p.x, wi[J], a0i);
+                a1r = fma(p.y, wr[J], a1r); a1i = fma(p.y, wi[J], a1i);
+                a2r = fma(p.z, wr[J], a2r); a2i = fma(p.z, wi[J], a2i);
+                a3r = fma(p.w, wr[J], a3r); a3i = fma(p.w, wi[J], a3i);
+            }
+            const double yr4[4] = {a0r, a1r, a2r, a3r}, yi4[4] = {a0i, a1i, a2i, a3i};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int I = ib * 4 + q;
+                if (I < R) {
+                    const int c = I / REPS;
+                    double prc = pr[0], pic = pim[0], grc = gr[0], gic = gi[0], urc = ur[0], uic = ui[0];
+#pragma unroll
+                    for (int cc = 1; cc < G; ++cc)
+                        if (c == cc) { prc = pr[cc]; pic = pim[cc]; grc = gr[cc]; gic = gi[cc]; urc = ur[cc]; uic = ui[cc]; }
+                    if (n > 1) {
+                        double2 v;
+                        v.x = fma(prc, yr4[q], fma(-pic, yi4[q], cnext * grc));
+                        v.y = fma(prc, yi4[q], fma(pic, yr4[q], cnext * gic));
+                        mine[I * PX_TPB] = v;
+                    } else {
+                        double ar = 0.0, ai = 0.0;
+#pragma unroll
+                        for (int cc = 0; cc < G; ++cc) {
+                            const double w = sWG[cc * R + I];
+                            ar = fma(ur[cc], w, ar);
+                            ai = fma(ui[cc], w, ai);
+                        }
+                        const double sr = fma(mean, urc, yr4[q]);
+                        const double si = fma(-mean, uic, yi4[q]);
+                        tr += ar * sr - ai * si;
+                    }
+                }
+            }
+        }
+        if (n > 1) {
+#pragma unroll
+            for (int J = 0; J < R; ++J) { const double2 v = mine[J * PX_TPB]; wr[J] = v.x; wi[J] = v.y; }
+        }
+    }
+    if (ntop < 1) {      // empty series: S = mean * Id
+#pragma unroll
+        for (int K = 0; K < R; ++K) {
+            const int c = K / REPS;
+            double ar = 0.0, ai = 0.0;
+            for (int cc = 0; cc < G; ++cc) { const double w = sWG[cc * R + K]; ar = fma(ur[cc], w, ar); ai = fma(ui[cc], w, ai); }
+            double urc = ur[0], uic = ui[0];
+            for (int cc = 1; cc < G; ++cc) if (c == cc) { urc = ur[cc]; uic = ui[cc]; }
+            tr += ar * (mean * urc) - ai * (-mean * uic);
+        }
+    }
+    bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, sigma_star, st, s, gx);
+}
+
+// ---- any rank <= 64: vectors in shared memory (fallback, not tuned) --------------
+__global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PhaseSmem *ps = reinterpret_cast<PhaseSmem *>(smem_raw);
+    const int job = jobs[blockIdx.x];
+    const int pb = bt.job_pb[job], s = bt.job_spec[job];
+    const int X = st.spec_npts[s];
+    const int x0 = blockIdx.y * PX_GEN_TPB;
+    if (x0 >= X) return;
+    const int *pi = bt.phase_i + pb * 8;
+    const int G = pi[0], R = pi[1], REPS = R / G;
+    double *sP = reinterpret_cast<double *>(smem_raw + sizeof(PhaseSmem));    // [R][R]
+    double *sWG = sP + R * R;                                                // [G][R]
+    double2 *vy = reinterpret_cast<double2 *>(sWG + G * R + (G * R & 1));    // [R][TPB] y
+    double2 *vw = vy + R * PX_GEN_TPB;                                       // [R][TPB] w
+    double2 *vu = vw + R * PX_GEN_TPB;                                       // [G][TPB] u
+    double2 *vp = vu + 8 * PX_GEN_TPB;                                       // [G][TPB] phi
+    double *sCoef = reinterpret_cast<double *>(vp + 8 * PX_GEN_TPB);
+    const double *px = bt.phase_x + pb * 4;
+    const int ntop = (int)px[2];
+    const double mean = px[0], abs_scale = px[1];
+    const int flags = pi[4];
+    const double sigma_star = bt.phase_d[pb * 8];
+
+    load_phase_lists(bt, pb, G, ps);
+    {
+        const double *W = bt.matrices + pi[6];
+        const double *P = W + R * R;
+        for (int i = threadIdx.x; i < R * R; i += PX_GEN_TPB) sP[i] = P[i];
+        for (int i = threadIdx.x; i < G * R; i += PX_GEN_TPB) {
+            const int c = i / R, K = i % R;
+            double acc = 0.0;
+            for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
+            sWG[i] = acc;
+        }
+        const double *coef = bt.coef + (long long)pb * bt.ncap;
+        for (int i = threadIdx.x; i <= ntop; i += PX_GEN_TPB) sCoef[i] = coef[i];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= X) return;
+    const int t = threadIdx.x;
+    const long long gx = st.spec_off[s] + x;
+    const double stl = st.stl[gx];
+    for (int c = 0; c < G; ++c) {
+        double a, b, p, q;
+        component_factors(ps, c, stl, st.asf + gx, st.sumX, a, b, p, q);
+        vu[c * PX_GEN_TPB + t] = make_double2(a, b);
+        vp[c * PX_GEN_TPB + t] = make_double2(p, q);
+    }
+    for (int I = 0; I < R; ++I) vy[I * PX_GEN_TPB + t] = make_double2(0.0, 0.0);
+    for (int n = ntop; n >= 1; --n) {
+        const double cn = sCoef[n];
+        for (int I = 0; I < R; ++I) {
+            const int c = I / REPS;
+            const double2 u = vu[c * PX_GEN_TPB + t], p = vp[c * PX_GEN_TPB + t], y = vy[I * PX_GEN_TPB + t];
+            const double gr = p.x * u.x + p.y * u.y, gi = p.y * u.x - p.x * u.y;
+            vw[I * PX_GEN_TPB + t] = make_double2(fma(p.x, y.x, fma(-p.y, y.y, cn * gr)),
+                                                  fma(p.x, y.y, fma(p.y, y.x, cn * gi)));
+        }
+        for (int I = 0; I < R; ++I) {
+            double ar = 0.0, ai = 0.0;
+            for (int J = 0; J < R; ++J) {
+                const double p = sP[I * R + J];
+                const double2 w = vw[J * PX_GEN_TPB + t];
+                ar = fma(p, w.x, ar);
+                ai = fma(p, w.y, ai);
+            }
+            vy[I * PX_GEN_TPB + t] = make_double2(ar, ai);
+        }
+    }
+    double tr = 0.0;
+    for (int K = 0; K < R; ++K) {
+        const int ck = K / REPS;
+        double ar = 0.0, ai = 0.0;
+        for (int c = 0; c < G; ++c) {
+            const double w = sWG[c * R + K];
+            const double2 u = vu[c * PX_GEN_TPB + t];
+            ar = fma(u.x, w, ar);
+            ai = fma(u.y, w, ai);
+        }
+        const double2 u = vu[ck * PX_GEN_TPB + t], y = vy[K * PX_GEN_TPB + t];
+        tr += ar * fma(mean, u.x, y.x) - ai * fma(-mean, u.y, y.y);
+    }
+    bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, sigma_star, st, s, gx);
+}
+
+// one component on an arbitrary stl axis (leaf: components.get_factors / atoms.get_structure_factor)
+__global__ void k_leaf_component(const double *stl, long long n, const double *comp_d, int n_layer, int n_inter,
+                                 const double *atom_d, const double *atype_rows, const unsigned char *has_type,
+                                 double2 *sf, double2 *phi, double *z_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double lattice_d = comp_d[3];
+    const double zf = __ddiv_rn(comp_d[0] - lattice_d, comp_d[1] - lattice_d);
+    const double x = stl[i];
+    const double v = __dmul_rn(x, 0.05);
+    const double s = __dmul_rn(v, v);
+    double sr = 0.0, si = 0.0;
+    for (int a = 0; a < n_layer + n_inter; ++a) {
+        const double z0 = atom_d[a * 2 + 1];
+        const double z = (a < n_layer) ? z0 : __dadd_rn(lattice_d, __dmul_rn(zf, z0 - lattice_d));
+        if (i == 0) z_out[a] = z;
+        if (!has_type[a]) continue;
+        atom_term(asf_value(atype_rows + a * 12, s), atom_d[a * 2], __dmul_rn(PX_TWO_PI, z), x, sr, si);
+    }
+    sf[i] = make_double2(sr, si);
+    double pr, pi_;
+    phase_factor(x, comp_d[0], comp_d[2], pr, pi_);
+    phi[i] = make_double2(pr, pi_);
+}
+
+// ---------------------------------------------------------------------------------
+// wavelength distribution: I <- I + interp(asin(stl lambda_j / 2), f_j I)(theta), j in list order,
+// each pass reading the pattern the previous pass produced (specimen.py:64-74)
+// ---------------------------------------------------------------------------------
+__global__ void k_wavelength(StaticDev st, BatchDev bt, int njobs, int use_global, double *scratch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int job = blockIdx.x;
+    if (job >= njobs) return;
+    const int s = bt.job_spec[job];
+    const int nwl = st.spec_nwl[s];
+    const int X = st.spec_npts[s];
+    double *I = bt.intensities + bt.job_out[job];
+    if (bt.job_pb[job] < 0 || nwl == 0) return;          // a zero pattern stays zero
+    double *bufA, *bufB;
+    if (use_global) {
+        bufA = scratch + (long long)job * 2 * st.maxX;
+        bufB = bufA + st.maxX;
+    } else {
+        bufA = reinterpret_cast<double *>(smem_raw);
+        bufB = bufA + st.maxX;
+    }
+    for (int x = threadIdx.x; x < X; x += blockDim.x) bufA[x] = I[x];
+    __syncthreads();
+    const double *frac = st.wl_fraction + st.wl_first[s];
+    for (int j = 0; j < nwl; ++j) {
+        const long long off = st.wl_off[s] + (long long)j * X;
+        const double f = frac[j];
+        for (int x = threadIdx.x; x < X; x += blockDim.x) {
+            const int hi = st.wl_index[off + x];
+            double add = 0.0;
+            if (hi >= 0) {
+                const double y_hi = __dmul_rn(bufA[hi], f), y_lo = __dmul_rn(bufA[hi - 1], f);
+                add = __dadd_rn(__dmul_rn(st.wl_w_hi[off + x], y_hi), __dmul_rn(st.wl_w_lo[off + x], y_lo));
+            }
+            bufB[x] = __dadd_rn(bufA[x], add);
+        }
+        __syncthreads();
+        double *tmp = bufA; bufA = bufB; bufB = tmp;
+    }
+    for (int x = threadIdx.x; x < X; x += blockDim.x) I[x] = bufA[x];
+}
+
+// ---------------------------------------------------------------------------------
+// mixture: total = scale * sum_p frac_p I_p + bg * C ; Rp = 100 sum|obs - total| / sum|obs|
+// grid (S, K), one block per (candidate, specimen)
+// ---------------------------------------------------------------------------------
+__global__ void k_mixture_residual(StaticDev st, BatchDev bt, int want_scaled) {
+    const int s = blockIdx.x, k = blockIdx.y;
+    const int X = st.spec_npts[s], Z = st.Z, M = bt.M;
+    const long long soff = st.spec_off[s];
+    const double *I = bt.intensities + (long long)k * bt.cand_stride + (long long)M * Z * soff;
+    double *scaled = bt.scaled ? bt.scaled + (long long)k * bt.cand_stride + (long long)M * Z * soff : nullptr;
+    double *tot = bt.totals + ((long long)k * st.sumX + soff) * Z;
+    const double *obs = st.observed + (long long)Z * soff;
+    const unsigned char *sel = st.selected + soff;
+    const double *corr = st.corr + soff;
+    const double scale = bt.scales[k * st.S + s], bg = bt.bgshifts[k * st.S + s];
+    const double *frac = bt.fractions + (long long)k * M;
+    double num = 0.0;
+    for (int i = threadIdx.x; i < Z * X; i += blockDim.x) {
+        const int z = i / X, x = i - z * X;
+        double acc = 0.0;
+        for (int p = 0; p < M; ++p) {
+            const double v = __dmul_rn(__dmul_rn(frac[p], I[((long long)p * Z + z) * X + x]), scale);
+            if (want_scaled && scaled) scaled[((long long)p * Z + z) * X + x] = v;
+            acc = __dadd_rn(acc, v);
+        }
+        acc = __dadd_rn(acc, __dmul_rn(bg, corr[x]));
+        tot[i] = acc;
+        if (sel[x]) num += fabs(obs[i] - acc);
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) num += __shfl_down_sync(0xffffffffu, num, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = num;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        num = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) num += __shfl_down_sync(0xffffffffu, num, o);
+        if (threadIdx.x == 0) {
+            const double den = st.derived[s * 8 + 3];
+            // no observations -> 0.0 (mixture.py:247-251)
+            bt.residuals[(long long)k * (st.S + 1) + 1 + s] = (Z * X > 0) ? num / den * 100.0 : 0.0;
+        }
+    }
+}
+
+__global__ void k_mixture_mean(int K, int S, double *residuals) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double *r = residuals + (long long)k * (S + 1);
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) acc += r[1 + s];
+    r[0] = acc / S;                                           // np.average(residuals[1:])
+}
+
+// ---------------------------------------------------------------------------------
+// FP64 FMA peak microbenchmark: 8 independent chains per thread
+// ---------------------------------------------------------------------------------
+__global__ void k_dfma_peak(double *out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

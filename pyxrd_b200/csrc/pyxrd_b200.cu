@@ -1,0 +1,769 @@
+// C-ABI host side of pyxrd_b200 (see include/pyxrd_b200.h for the contract).
+// Owns device memory for tables / parameters / results, builds the job lists and
+// launches the kernels of kernels.cuh on one CUDA stream.  No CPU compute path.
+#include "../../include/pyxrd_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+struct PinBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMallocHost(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+struct RankClass {
+    int rank = 0, G = 0;
+    int max_x = 0;
+    int max_ntop_cap = 0;
+    size_t first = 0;          // position of this class in the device job-id list
+    std::vector<int> jobs;
+};
+
+}  // namespace
+
+struct pyxrd_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int64_t launches = 0;
+    int smem_optin = 0;
+
+    // static
+    bool have_static = false;
+    StaticDev st{};
+    std::vector<int> h_npts;
+    std::vector<long long> h_off;
+    std::vector<int> h_nwl;
+    DevBuf d_npts, d_off, d_gonio, d_derived, d_theta, d_sin, d_stl, d_c2t2, d_corr, d_asf, d_nwl, d_wlfirst,
+        d_wloff, d_wlfrac, d_wlidx, d_wlhi, d_wllo, d_obs, d_sel, d_atypes, d_stlov;
+
+    // batch
+    bool have_batch = false;
+    bool have_intensities = false;
+    BatchDev bt{};
+    int NJ = 0;
+    std::vector<RankClass> classes;
+    DevBuf d_blob;           // all uploaded batch arrays, one allocation
+    PinBuf h_blob;
+    const int *jobids_dev = nullptr;   // inside d_blob
+    DevBuf d_atom_z, d_phase_x, d_coef, d_int, d_scaled, d_tot, d_res, d_scratch;
+    PinBuf h_res;
+    DevBuf d_leaf_a, d_leaf_b, d_leaf_c;
+    int64_t int_count = 0, tot_count = 0;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_set[4] = {false, false, false, false};
+};
+
+namespace {
+
+int fail(pyxrd_ctx *ctx, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                            \
+    do {                                                                                              \
+        ctx->launches++;                                                                              \
+        cudaError_t e__ = cudaGetLastError();                                                         \
+        if (e__ != cudaSuccess) return fail(ctx, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+template <class T>
+int upload(pyxrd_ctx *ctx, DevBuf &buf, const T *src, size_t n) {
+    CK(buf.ensure(std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CK(cudaMemcpyAsync(buf.ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t small_smem(int R, int G, int ntop_cap) {
+    return sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + ntop_cap + 2);
+}
+size_t staged_smem(int R, int G, int ntop_cap) {
+    const int RB = (R + 3) / 4;
+    return sizeof(PhaseSmem) + sizeof(double) * (size_t)(RB * R * 4 + G * R + (G * R & 1)) +
+           sizeof(double2) * (size_t)R * PX_TPB + sizeof(double) * (size_t)(ntop_cap + 2);
+}
+size_t generic_smem(int R, int G, int ntop_cap) {
+    return sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + (G * R & 1)) +
+           sizeof(double2) * (size_t)(2 * R + 16) * PX_GEN_TPB + sizeof(double) * (size_t)(ntop_cap + 2);
+}
+
+template <class K>
+int set_smem(pyxrd_ctx *ctx, K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        if ((int)bytes > ctx->smem_optin) return fail(ctx, "kernel needs %zu B of shared memory, device offers %d", bytes, ctx->smem_optin);
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    return 0;
+}
+
+template <int R, int G>
+int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+    const size_t smem = small_smem(R, G, rc.max_ntop_cap);
+    if (set_smem(ctx, k_phase_small<R, G>, smem)) return 1;
+    dim3 grid((unsigned)rc.jobs.size(), (unsigned)((rc.max_x + PX_TPB - 1) / PX_TPB));
+    k_phase_small<R, G><<<grid, PX_TPB, smem, ctx->stream>>>(ctx->st, ctx->bt, jobs_dev);
+    LAUNCH_CHECK("k_phase_small");
+    return 0;
+}
+
+template <int R, int G>
+int launch_staged(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+    const size_t smem = staged_smem(R, G, rc.max_ntop_cap);
+    if (set_smem(ctx, k_phase_staged<R, G>, smem)) return 1;
+    dim3 grid((unsigned)rc.jobs.size(), (unsigned)((rc.max_x + PX_TPB - 1) / PX_TPB));
+    k_phase_staged<R, G><<<grid, PX_TPB, smem, ctx->stream>>>(ctx->st, ctx->bt, jobs_dev);
+    LAUNCH_CHECK("k_phase_staged");
+    return 0;
+}
+
+int launch_generic(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+    const size_t smem = generic_smem(rc.rank, rc.G, rc.max_ntop_cap);
+    if (set_smem(ctx, k_phase_generic, smem)) return 1;
+    dim3 grid((unsigned)rc.jobs.size(), (unsigned)((rc.max_x + PX_GEN_TPB - 1) / PX_GEN_TPB));
+    k_phase_generic<<<grid, PX_GEN_TPB, smem, ctx->stream>>>(ctx->st, ctx->bt, jobs_dev);
+    LAUNCH_CHECK("k_phase_generic");
+    return 0;
+}
+
+int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+#define SMALL(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_>(ctx, rc, jobs_dev)
+#define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev)
+    SMALL(1, 1); SMALL(2, 2); SMALL(3, 3); SMALL(4, 4); SMALL(5, 5); SMALL(6, 6);   // R0 / R1
+    SMALL(2, 1); SMALL(3, 1); SMALL(4, 1);
+    SMALL(4, 2); SMALL(8, 2); SMALL(9, 3);                                            // R2G2, R3G2, R2G3
+    STAGED(16, 2); STAGED(16, 4); STAGED(27, 3);
+#undef SMALL
+#undef STAGED
+    return launch_generic(ctx, rc, jobs_dev);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pyxrd_create(int device, pyxrd_ctx **out) {
+    if (!out) return 1;
+    *out = nullptr;
+    pyxrd_ctx *ctx = new pyxrd_ctx();
+    ctx->device = device;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device >= count) {
+        fprintf(stderr, "pyxrd_b200: no usable CUDA device (%s); there is no CPU fallback\n",
+                e == cudaSuccess ? "device index out of range" : cudaGetErrorString(e));
+        delete ctx;
+        return 2;
+    }
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return 3;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+    *out = ctx;
+    return 0;
+}
+
+void pyxrd_destroy(pyxrd_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_stl,
+                      &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
+                      &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob,
+                      &ctx->d_atom_z, &ctx->d_phase_x, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
+                      &ctx->d_res, &ctx->d_scratch, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c};
+    for (DevBuf *b : bufs) b->release();
+    ctx->h_blob.release();
+    ctx->h_res.release();
+    for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *pyxrd_last_error(const pyxrd_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int pyxrd_set_stream(pyxrd_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return 1;
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return 0;
+}
+
+int pyxrd_synchronize(pyxrd_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int64_t pyxrd_launch_count(const pyxrd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
+    if (!ctx || !d) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const int S = d->n_specimens, T = d->n_atom_types, Z = d->n_patterns;
+    if (S <= 0 || Z <= 0 || T < 0) return fail(ctx, "set_static: need S > 0 and Z > 0 (S=%d Z=%d T=%d)", S, Z, T);
+    ctx->have_static = false;
+    ctx->have_batch = false;
+    ctx->h_npts.assign(d->spec_npts, d->spec_npts + S);
+    ctx->h_nwl.assign(d->spec_nwl, d->spec_nwl + S);
+    ctx->h_off.assign(S + 1, 0);
+    int maxX = 0;
+    std::vector<int> wlfirst(S);
+    std::vector<long long> wloff(S);
+    long long nwl_total = 0, wl_pts = 0;
+    for (int s = 0; s < S; ++s) {
+        if (d->spec_npts[s] < 0) return fail(ctx, "set_static: negative point count");
+        ctx->h_off[s + 1] = ctx->h_off[s] + d->spec_npts[s];
+        maxX = std::max(maxX, d->spec_npts[s]);
+        wlfirst[s] = (int)nwl_total;
+        wloff[s] = wl_pts;
+        nwl_total += d->spec_nwl[s];
+        wl_pts += (long long)d->spec_nwl[s] * d->spec_npts[s];
+    }
+    const long long sumX = ctx->h_off[S];
+    if (upload(ctx, ctx->d_npts, d->spec_npts, S)) return 1;
+    if (upload(ctx, ctx->d_off, ctx->h_off.data(), S + 1)) return 1;
+    if (upload(ctx, ctx->d_gonio, d->spec_gonio, (size_t)S * PYXRD_GONIO_STRIDE)) return 1;
+    if (upload(ctx, ctx->d_theta, d->theta, sumX)) return 1;
+    if (upload(ctx, ctx->d_nwl, d->spec_nwl, S)) return 1;
+    if (upload(ctx, ctx->d_wlfirst, wlfirst.data(), S)) return 1;
+    if (upload(ctx, ctx->d_wloff, wloff.data(), S)) return 1;
+    if (upload(ctx, ctx->d_wlfrac, d->wl_fraction, nwl_total)) return 1;
+    if (upload(ctx, ctx->d_wlidx, d->wl_index, wl_pts)) return 1;
+    if (upload(ctx, ctx->d_wlhi, d->wl_w_hi, wl_pts)) return 1;
+    if (upload(ctx, ctx->d_wllo, d->wl_w_lo, wl_pts)) return 1;
+    if (upload(ctx, ctx->d_obs, d->observed, (size_t)Z * sumX)) return 1;
+    if (upload(ctx, ctx->d_sel, d->selected, sumX)) return 1;
+    if (upload(ctx, ctx->d_atypes, d->atom_types, (size_t)T * PYXRD_ATYPE_STRIDE)) return 1;
+    if (d->stl_override && upload(ctx, ctx->d_stlov, d->stl_override, sumX)) return 1;
+    // the upload() calls above read caller memory asynchronously only for pinned sources; for
+    // pageable sources cudaMemcpyAsync returns after staging, so the caller may free them now
+    CK(ctx->d_derived.ensure(sizeof(double) * 8 * S));
+    CK(cudaMemsetAsync(ctx->d_derived.ptr, 0, sizeof(double) * 8 * S, ctx->stream));
+    CK(ctx->d_sin.ensure(sizeof(double) * std::max<long long>(sumX, 1)));
+    CK(ctx->d_stl.ensure(sizeof(double) * std::max<long long>(sumX, 1)));
+    CK(ctx->d_c2t2.ensure(sizeof(double) * std::max<long long>(sumX, 1)));
+    CK(ctx->d_corr.ensure(sizeof(double) * std::max<long long>(sumX, 1)));
+    CK(ctx->d_asf.ensure(sizeof(double) * std::max<long long>(sumX * std::max(T, 1), 1)));
+
+    StaticDev &st = ctx->st;
+    st.S = S; st.T = T; st.Z = Z; st.maxX = maxX; st.sumX = sumX;
+    st.spec_npts = ctx->d_npts.as<int>();
+    st.spec_off = ctx->d_off.as<long long>();
+    st.gonio = ctx->d_gonio.as<double>();
+    st.derived = ctx->d_derived.as<double>();
+    st.theta = ctx->d_theta.as<double>();
+    st.sin_t = ctx->d_sin.as<double>();
+    st.stl = ctx->d_stl.as<double>();
+    st.c2t2 = ctx->d_c2t2.as<double>();
+    st.corr = ctx->d_corr.as<double>();
+    st.asf = ctx->d_asf.as<double>();
+    st.spec_nwl = ctx->d_nwl.as<int>();
+    st.wl_first = ctx->d_wlfirst.as<int>();
+    st.wl_off = ctx->d_wloff.as<long long>();
+    st.wl_fraction = ctx->d_wlfrac.as<double>();
+    st.wl_index = ctx->d_wlidx.as<int>();
+    st.wl_w_hi = ctx->d_wlhi.as<double>();
+    st.wl_w_lo = ctx->d_wllo.as<double>();
+    st.observed = ctx->d_obs.as<double>();
+    st.selected = ctx->d_sel.as<unsigned char>();
+    st.atypes = ctx->d_atypes.as<double>();
+
+    k_specimen_derived<<<(S + 63) / 64, 64, 0, ctx->stream>>>(S, st.gonio, ctx->d_derived.as<double>());
+    LAUNCH_CHECK("k_specimen_derived");
+    if (maxX > 0) {
+        dim3 grid((maxX + 255) / 256, S);
+        k_specimen_tables<<<grid, 256, 0, ctx->stream>>>(st, ctx->d_sin.as<double>(), ctx->d_stl.as<double>(),
+                                                         ctx->d_c2t2.as<double>(), ctx->d_corr.as<double>(),
+                                                         d->stl_override ? ctx->d_stlov.as<double>() : nullptr);
+        LAUNCH_CHECK("k_specimen_tables");
+        if (T > 0) {
+            dim3 g2((unsigned)((sumX + 255) / 256), T);
+            k_asf_table<<<g2, 256, 0, ctx->stream>>>(st, ctx->d_asf.as<double>());
+            LAUNCH_CHECK("k_asf_table");
+        }
+    }
+    k_observed_norm<<<S, 256, 0, ctx->stream>>>(st, ctx->d_derived.as<double>());
+    LAUNCH_CHECK("k_observed_norm");
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_static = true;
+    return 0;
+}
+
+int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
+    if (!ctx || !d) return 1;
+    if (!ctx->have_static) return fail(ctx, "set_batch: call pyxrd_set_static first");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_batch = false;
+    ctx->have_intensities = false;
+    const StaticDev &st = ctx->st;
+    const int K = d->n_candidates, M = d->n_phase_slots, NP = d->n_phases, NC = d->n_components, NA = d->n_atoms;
+    const int S = st.S, Z = st.Z;
+    if (K <= 0 || M <= 0) return fail(ctx, "set_batch: need K > 0 and M > 0 (K=%d M=%d)", K, M);
+
+    // ---- validate parameter blocks and find the coefficient stride -------------------
+    int ncap = 2;
+    for (int p = 0; p < NP; ++p) {
+        const int32_t *pi = d->phase_i + (size_t)p * PYXRD_PHASE_I_STRIDE;
+        if (!(pi[4] & PYXRD_FLAG_VALID_PROBS)) continue;
+        const int G = pi[0], r = pi[1];
+        if (G < 1 || G > PYXRD_MAX_COMPONENTS || r < 1 || r > PYXRD_MAX_RANK || r % G != 0)
+            return fail(ctx, "set_batch: phase %d has unsupported G=%d rank=%d (need 1<=G<=%d, rank<=%d, rank %% G == 0)",
+                        p, G, r, PYXRD_MAX_COMPONENTS, PYXRD_MAX_RANK);
+        if (pi[2] < 0 || pi[3] < pi[2]) return fail(ctx, "set_batch: phase %d CSDS range [%d, %d] unsupported", p, pi[2], pi[3]);
+        ncap = std::max(ncap, pi[3] + 2);
+        int atoms = 0;
+        for (int c = 0; c < G; ++c) {
+            const int ci = d->phase_comp[pi[5] + c];
+            if (ci < 0 || ci >= NC) return fail(ctx, "set_batch: phase %d references component %d of %d", p, ci, NC);
+            atoms += d->comp_i[(size_t)ci * PYXRD_COMP_I_STRIDE + 1] + d->comp_i[(size_t)ci * PYXRD_COMP_I_STRIDE + 2];
+        }
+        if (atoms > PX_MAX_ATOMS) return fail(ctx, "set_batch: phase %d has %d atoms (limit %d)", p, atoms, PX_MAX_ATOMS);
+    }
+    for (int a = 0; a < NA; ++a)
+        if (d->atom_type[a] >= st.T) return fail(ctx, "set_batch: atom %d references atom type %d of %d", a, d->atom_type[a], st.T);
+
+    // ---- job lists per (rank, G) class ------------------------------------------------
+    const long long cand_stride = (long long)M * Z * st.sumX;
+    const long long NJ = (long long)K * S * Z * M;
+    if (NJ > 0x7fffffffLL) return fail(ctx, "set_batch: too many patterns (%lld)", NJ);
+    std::vector<int> job_pb((size_t)NJ), job_spec((size_t)NJ);
+    std::vector<long long> job_out((size_t)NJ);
+    std::map<std::pair<int, int>, int> class_of;
+    ctx->classes.clear();
+    long long j = 0;
+    for (int k = 0; k < K; ++k)
+        for (int s = 0; s < S; ++s)
+            for (int z = 0; z < Z; ++z)
+                for (int m = 0; m < M; ++m, ++j) {
+                    int pb = d->job_phase[j];
+                    if (pb >= NP) return fail(ctx, "set_batch: job %lld references phase %d of %d", j, pb, NP);
+                    job_spec[j] = s;
+                    job_out[j] = (long long)k * cand_stride + (long long)M * Z * ctx->h_off[s] +
+                                 ((long long)m * Z + z) * ctx->h_npts[s];
+                    const int32_t *pi = pb >= 0 ? d->phase_i + (size_t)pb * PYXRD_PHASE_I_STRIDE : nullptr;
+                    if (pb >= 0 && !(pi[4] & PYXRD_FLAG_VALID_PROBS)) pb = -1;    // invalid probabilities -> zeros
+                    job_pb[j] = pb;
+                    if (pb < 0 || ctx->h_npts[s] == 0) continue;
+                    auto key = std::make_pair(pi[1], pi[0]);
+                    auto it = class_of.find(key);
+                    if (it == class_of.end()) {
+                        it = class_of.emplace(key, (int)ctx->classes.size()).first;
+                        ctx->classes.emplace_back();
+                        ctx->classes.back().rank = pi[1];
+                        ctx->classes.back().G = pi[0];
+                    }
+                    RankClass &rc = ctx->classes[it->second];
+                    rc.jobs.push_back((int)j);
+                    rc.max_x = std::max(rc.max_x, ctx->h_npts[s]);
+                    rc.max_ntop_cap = std::max(rc.max_ntop_cap, pi[3] + 1);
+                }
+    // heavy classes first so the tail of the grid is filled by the cheap ones
+    std::sort(ctx->classes.begin(), ctx->classes.end(), [](const RankClass &a, const RankClass &b) { return a.rank > b.rank; });
+    std::vector<int> jobids;
+    for (RankClass &rc : ctx->classes) jobids.insert(jobids.end(), rc.jobs.begin(), rc.jobs.end());
+
+    // ---- one pinned blob, one H2D copy ---------------------------------------------------
+    struct Part { const void *src; size_t bytes; size_t off; };
+    std::vector<Part> parts;
+    size_t total = 0;
+    auto add = [&](const void *src, size_t bytes) {
+        Part p{src, bytes, total};
+        total = align_up(total + std::max<size_t>(bytes, 8), 256);
+        parts.push_back(p);
+        return parts.size() - 1;
+    };
+    const size_t i_phase_i = add(d->phase_i, sizeof(int32_t) * (size_t)NP * PYXRD_PHASE_I_STRIDE);
+    const size_t i_phase_d = add(d->phase_d, sizeof(double) * (size_t)NP * PYXRD_PHASE_D_STRIDE);
+    const size_t i_phase_comp = add(d->phase_comp, sizeof(int32_t) * (size_t)d->n_phase_comp);
+    const size_t i_matrices = add(d->matrices, sizeof(double) * (size_t)d->n_matrix);
+    const size_t i_comp_d = add(d->comp_d, sizeof(double) * (size_t)NC * PYXRD_COMP_D_STRIDE);
+    const size_t i_comp_i = add(d->comp_i, sizeof(int32_t) * (size_t)NC * PYXRD_COMP_I_STRIDE);
+    const size_t i_atom_d = add(d->atom_d, sizeof(double) * (size_t)NA * PYXRD_ATOM_D_STRIDE);
+    const size_t i_atom_t = add(d->atom_type, sizeof(int32_t) * (size_t)NA);
+    const size_t i_job_pb = add(job_pb.data(), sizeof(int) * (size_t)NJ);
+    const size_t i_job_spec = add(job_spec.data(), sizeof(int) * (size_t)NJ);
+    const size_t i_job_out = add(job_out.data(), sizeof(long long) * (size_t)NJ);
+    const size_t i_jobids = add(jobids.data(), sizeof(int) * jobids.size());
+    const size_t i_frac = add(d->fractions, sizeof(double) * (size_t)K * M);
+    const size_t i_scales = add(d->scales, sizeof(double) * (size_t)K * S);
+    const size_t i_bg = add(d->bgshifts, sizeof(double) * (size_t)K * S);
+    CK(cudaStreamSynchronize(ctx->stream));        // the pinned blob may still feed a previous copy
+    CK(ctx->h_blob.ensure(total));
+    CK(ctx->d_blob.ensure(total));
+    for (const Part &p : parts)
+        if (p.bytes) memcpy(static_cast<char *>(ctx->h_blob.ptr) + p.off, p.src, p.bytes);
+    CK(cudaMemcpyAsync(ctx->d_blob.ptr, ctx->h_blob.ptr, total, cudaMemcpyHostToDevice, ctx->stream));
+    auto dev = [&](size_t idx) { return static_cast<char *>(ctx->d_blob.ptr) + parts[idx].off; };
+
+    CK(ctx->d_atom_z.ensure(sizeof(double) * std::max(NA, 1)));
+    CK(ctx->d_phase_x.ensure(sizeof(double) * 4 * std::max(NP, 1)));
+    CK(ctx->d_coef.ensure(sizeof(double) * (size_t)ncap * std::max(NP, 1)));
+    ctx->int_count = (int64_t)K * cand_stride;
+    ctx->tot_count = (int64_t)K * Z * st.sumX;
+    CK(ctx->d_int.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
+    CK(ctx->d_tot.ensure(sizeof(double) * std::max<int64_t>(ctx->tot_count, 1)));
+    CK(ctx->d_res.ensure(sizeof(double) * (size_t)K * (S + 1)));
+    CK(ctx->h_res.ensure(sizeof(double) * (size_t)K * (S + 1)));
+
+    BatchDev &bt = ctx->bt;
+    bt.K = K; bt.M = M; bt.NP = NP; bt.NC = NC; bt.NA = NA; bt.ncap = ncap;
+    bt.cand_stride = cand_stride;
+    bt.phase_i = reinterpret_cast<const int *>(dev(i_phase_i));
+    bt.phase_d = reinterpret_cast<const double *>(dev(i_phase_d));
+    bt.phase_comp = reinterpret_cast<const int *>(dev(i_phase_comp));
+    bt.matrices = reinterpret_cast<const double *>(dev(i_matrices));
+    bt.comp_d = reinterpret_cast<const double *>(dev(i_comp_d));
+    bt.comp_i = reinterpret_cast<const int *>(dev(i_comp_i));
+    bt.atom_d = reinterpret_cast<const double *>(dev(i_atom_d));
+    bt.atom_type = reinterpret_cast<const int *>(dev(i_atom_t));
+    bt.atom_z = ctx->d_atom_z.as<double>();
+    bt.phase_x = ctx->d_phase_x.as<double>();
+    bt.coef = ctx->d_coef.as<double>();
+    bt.job_pb = reinterpret_cast<const int *>(dev(i_job_pb));
+    bt.job_spec = reinterpret_cast<const int *>(dev(i_job_spec));
+    bt.job_out = reinterpret_cast<const long long *>(dev(i_job_out));
+    bt.fractions = reinterpret_cast<const double *>(dev(i_frac));
+    bt.scales = reinterpret_cast<const double *>(dev(i_scales));
+    bt.bgshifts = reinterpret_cast<const double *>(dev(i_bg));
+    bt.intensities = ctx->d_int.as<double>();
+    bt.scaled = nullptr;
+    bt.totals = ctx->d_tot.as<double>();
+    bt.residuals = ctx->d_res.as<double>();
+    ctx->NJ = (int)NJ;
+    ctx->jobids_dev = reinterpret_cast<const int *>(dev(i_jobids));
+    {
+        size_t pos = 0;
+        for (RankClass &rc : ctx->classes) {
+            rc.first = pos;
+            pos += rc.jobs.size();
+        }
+    }
+
+    CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    if (NP > 0) {
+        k_phase_prologue<<<(NP + 63) / 64, 64, 0, ctx->stream>>>(bt);
+        LAUNCH_CHECK("k_phase_prologue");
+    }
+    if (NC > 0) {
+        k_component_z<<<(NC + 63) / 64, 64, 0, ctx->stream>>>(bt);
+        LAUNCH_CHECK("k_component_z");
+    }
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    ctx->ev_set[3] = true;
+    ctx->have_batch = true;
+    return 0;
+}
+
+
+int pyxrd_set_solution(pyxrd_ctx *ctx, const double *fractions, const double *scales, const double *bgshifts) {
+    if (!ctx || !ctx->have_batch) return fail(ctx, "set_solution: no resident batch");
+    CK(cudaSetDevice(ctx->device));
+    const BatchDev &bt = ctx->bt;
+    const int S = ctx->st.S;
+    CK(cudaMemcpyAsync(const_cast<double *>(bt.fractions), fractions, sizeof(double) * (size_t)bt.K * bt.M, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(const_cast<double *>(bt.scales), scales, sizeof(double) * (size_t)bt.K * S, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(const_cast<double *>(bt.bgshifts), bgshifts, sizeof(double) * (size_t)bt.K * S, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));     // sources are pageable caller memory
+    return 0;
+}
+
+int pyxrd_set_intensities(pyxrd_ctx *ctx, const double *intensities, int64_t count) {
+    if (!ctx || !ctx->have_batch) return fail(ctx, "set_intensities: no resident batch");
+    if (count != ctx->int_count) return fail(ctx, "set_intensities: got %lld doubles, the batch holds %lld", (long long)count, (long long)ctx->int_count);
+    CK(cudaSetDevice(ctx->device));
+    if (count) CK(cudaMemcpyAsync(ctx->d_int.ptr, intensities, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_intensities = true;
+    return 0;
+}
+
+int pyxrd_compute_intensities(pyxrd_ctx *ctx) {
+    if (!ctx || !ctx->have_batch) return fail(ctx, "compute_intensities: no resident batch");
+    CK(cudaSetDevice(ctx->device));
+    const StaticDev &st = ctx->st;
+    // None phases / invalid probabilities / empty specimens stay zero (specimen.py:63, phases.py:109-111)
+    bool any_zero = false;
+    size_t listed = 0;
+    for (const RankClass &rc : ctx->classes) listed += rc.jobs.size();
+    any_zero = listed != (size_t)ctx->NJ;
+    if (any_zero && ctx->int_count > 0)
+        CK(cudaMemsetAsync(ctx->d_int.ptr, 0, sizeof(double) * (size_t)ctx->int_count, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (const RankClass &rc : ctx->classes)
+        if (!rc.jobs.empty() && launch_class(ctx, rc, ctx->jobids_dev + rc.first)) return 1;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    // wavelength distribution, one block per pattern
+    bool any_wl = false;
+    for (int s = 0; s < st.S; ++s) any_wl = any_wl || (ctx->h_nwl[s] > 0 && ctx->h_npts[s] > 0);
+    if (any_wl && ctx->NJ > 0) {
+        const size_t smem = sizeof(double) * 2 * (size_t)st.maxX;
+        const int use_global = smem > (size_t)ctx->smem_optin;
+        if (use_global) CK(ctx->d_scratch.ensure(sizeof(double) * 2 * (size_t)st.maxX * ctx->NJ));
+        else if (set_smem(ctx, k_wavelength, smem)) return 1;
+        k_wavelength<<<ctx->NJ, 256, use_global ? 0 : smem, ctx->stream>>>(st, ctx->bt, ctx->NJ, use_global,
+                                                                          ctx->d_scratch.as<double>());
+        LAUNCH_CHECK("k_wavelength");
+    }
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->ev_set[0] = ctx->ev_set[1] = true;
+    ctx->have_intensities = true;
+    return 0;
+}
+
+int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled) {
+    if (!ctx || !ctx->have_batch || !ctx->have_intensities) return fail(ctx, "compute_residuals: intensities not computed");
+    CK(cudaSetDevice(ctx->device));
+    BatchDev bt = ctx->bt;
+    if (want_scaled) {
+        CK(ctx->d_scaled.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
+        bt.scaled = ctx->d_scaled.as<double>();
+    }
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    dim3 grid(ctx->st.S, bt.K);
+    k_mixture_residual<<<grid, 256, 0, ctx->stream>>>(ctx->st, bt, want_scaled);
+    LAUNCH_CHECK("k_mixture_residual");
+    k_mixture_mean<<<(bt.K + 127) / 128, 128, 0, ctx->stream>>>(bt.K, ctx->st.S, bt.residuals);
+    LAUNCH_CHECK("k_mixture_mean");
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->ev_set[2] = true;
+    return 0;
+}
+
+int64_t pyxrd_intensity_count(const pyxrd_ctx *ctx) { return ctx ? ctx->int_count : 0; }
+int64_t pyxrd_total_count(const pyxrd_ctx *ctx) { return ctx ? ctx->tot_count : 0; }
+
+static int read_back(pyxrd_ctx *ctx, const void *dev, double *out, int64_t count, int64_t have, const char *what) {
+    if (!dev || count > have || count < 0) return fail(ctx, "read %s: asked for %lld doubles, buffer holds %lld", what, (long long)count, (long long)have);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, dev, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pyxrd_read_intensities(pyxrd_ctx *ctx, double *out, int64_t count) {
+    if (!ctx || !ctx->have_intensities) return fail(ctx, "read intensities: not computed");
+    return read_back(ctx, ctx->d_int.ptr, out, count, ctx->int_count, "intensities");
+}
+int pyxrd_read_scaled(pyxrd_ctx *ctx, double *out, int64_t count) {
+    if (!ctx || !ctx->d_scaled.ptr) return fail(ctx, "read scaled: not computed");
+    return read_back(ctx, ctx->d_scaled.ptr, out, count, ctx->int_count, "scaled intensities");
+}
+int pyxrd_read_totals(pyxrd_ctx *ctx, double *out, int64_t count) {
+    if (!ctx || !ctx->have_batch) return fail(ctx, "read totals: no batch");
+    return read_back(ctx, ctx->d_tot.ptr, out, count, ctx->tot_count, "totals");
+}
+int pyxrd_read_residuals(pyxrd_ctx *ctx, double *out, int64_t count) {
+    if (!ctx || !ctx->have_batch) return fail(ctx, "read residuals: no batch");
+    return read_back(ctx, ctx->d_res.ptr, out, count, (int64_t)ctx->bt.K * (ctx->st.S + 1), "residuals");
+}
+int pyxrd_read_correction(pyxrd_ctx *ctx, double *out, int64_t count) {
+    if (!ctx || !ctx->have_static) return fail(ctx, "read correction: no static tables");
+    return read_back(ctx, ctx->d_corr.ptr, out, count, ctx->st.sumX, "correction");
+}
+
+int pyxrd_device_buffers(pyxrd_ctx *ctx, double **intensities_dev, double **totals_dev, double **residuals_dev) {
+    if (!ctx || !ctx->have_batch) return fail(ctx, "device_buffers: no batch");
+    if (intensities_dev) *intensities_dev = ctx->d_int.as<double>();
+    if (totals_dev) *totals_dev = ctx->d_tot.as<double>();
+    if (residuals_dev) *residuals_dev = ctx->d_res.as<double>();
+    return 0;
+}
+
+int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *residuals_out, double *intensities_out) {
+    if (pyxrd_set_batch(ctx, desc)) return 1;
+    if (pyxrd_compute_intensities(ctx)) return 1;
+    if (pyxrd_compute_residuals(ctx, 0)) return 1;
+    const size_t nres = (size_t)ctx->bt.K * (ctx->st.S + 1);
+    CK(cudaMemcpyAsync(ctx->h_res.ptr, ctx->d_res.ptr, sizeof(double) * nres, cudaMemcpyDeviceToHost, ctx->stream));
+    if (intensities_out)
+        CK(cudaMemcpyAsync(intensities_out, ctx->d_int.ptr, sizeof(double) * (size_t)ctx->int_count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(residuals_out, ctx->h_res.ptr, sizeof(double) * nres);
+    return 0;
+}
+
+// ---- leaf helpers -----------------------------------------------------------------------
+int pyxrd_leaf_asf(pyxrd_ctx *ctx, const double *s, int64_t n, const double *atom_type, double *out) {
+    if (!ctx || n < 0) return 1;
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    if (upload(ctx, ctx->d_leaf_a, s, (size_t)n)) return 1;
+    if (upload(ctx, ctx->d_leaf_b, atom_type, PYXRD_ATYPE_STRIDE)) return 1;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * (size_t)n));
+    k_leaf_asf<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_leaf_a.as<double>(), n, ctx->d_leaf_b.as<double>(), ctx->d_leaf_c.as<double>());
+    LAUNCH_CHECK("k_leaf_asf");
+    return read_back(ctx, ctx->d_leaf_c.ptr, out, n, n, "asf");
+}
+
+int pyxrd_leaf_lpf(pyxrd_ctx *ctx, const double *theta, int64_t n, double sigma_star, double soller1, double soller2,
+                   double mcr_2theta, double *out) {
+    if (!ctx || n < 0) return 1;
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    if (upload(ctx, ctx->d_leaf_a, theta, (size_t)n)) return 1;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * (size_t)n));
+    k_leaf_lpf<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_leaf_a.as<double>(), n, sigma_star, soller1, soller2, mcr_2theta, ctx->d_leaf_c.as<double>());
+    LAUNCH_CHECK("k_leaf_lpf");
+    return read_back(ctx, ctx->d_leaf_c.ptr, out, n, n, "lpf");
+}
+
+int pyxrd_leaf_csds(pyxrd_ctx *ctx, const double *csds6, int minimum, int maximum, double *out_arr, double *out_mean, double *out_coef) {
+    if (!ctx) return 1;
+    if (minimum < 0 || maximum < minimum) return fail(ctx, "leaf_csds: unsupported range [%d, %d]", minimum, maximum);
+    CK(cudaSetDevice(ctx->device));
+    double pd[8] = {0.0, csds6[0], csds6[1], csds6[2], csds6[3], csds6[4], 0.0, 0.0};
+    if (upload(ctx, ctx->d_leaf_a, pd, 8)) return 1;
+    const size_t n_arr = (size_t)maximum + 1, n_coef = (size_t)maximum + 2;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * (n_arr + 1 + n_coef)));
+    double *base = ctx->d_leaf_c.as<double>();
+    k_leaf_csds<<<1, 32, 0, ctx->stream>>>(ctx->d_leaf_a.as<double>(), minimum, maximum, base, base + n_arr, base + n_arr + 1);
+    LAUNCH_CHECK("k_leaf_csds");
+    std::vector<double> host(n_arr + 1 + n_coef);
+    if (read_back(ctx, base, host.data(), (int64_t)host.size(), (int64_t)host.size(), "csds")) return 1;
+    memcpy(out_arr, host.data(), sizeof(double) * n_arr);
+    *out_mean = host[n_arr];
+    memcpy(out_coef, host.data() + n_arr + 1, sizeof(double) * n_coef);
+    return 0;
+}
+
+int pyxrd_leaf_component(pyxrd_ctx *ctx, const double *stl, int64_t n, const double *comp_d, int n_layer, int n_interlayer,
+                         const double *atom_d, const double *atom_type_rows, const uint8_t *atom_has_type,
+                         double *sf_out, double *phi_out, double *z_out) {
+    if (!ctx || n < 0 || n_layer < 0 || n_interlayer < 0) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const int NA = n_layer + n_interlayer;
+    const size_t npt = (size_t)std::max<int64_t>(n, 1);
+    // one scratch allocation: stl | comp | atom_d | rows | has | sf | phi | z
+    size_t off_stl = 0, off_comp = align_up(off_stl + 8 * npt, 256), off_atom = align_up(off_comp + 64, 256);
+    size_t off_rows = align_up(off_atom + 16 * (size_t)std::max(NA, 1), 256);
+    size_t off_has = align_up(off_rows + 96 * (size_t)std::max(NA, 1), 256);
+    size_t off_sf = align_up(off_has + (size_t)std::max(NA, 1), 256), off_phi = align_up(off_sf + 16 * npt, 256);
+    size_t off_z = align_up(off_phi + 16 * npt, 256), total = off_z + 8 * (size_t)std::max(NA, 1);
+    CK(ctx->d_leaf_a.ensure(total));
+    char *base = ctx->d_leaf_a.as<char>();
+    if (n) CK(cudaMemcpyAsync(base + off_stl, stl, 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(base + off_comp, comp_d, 64, cudaMemcpyHostToDevice, ctx->stream));
+    if (NA) {
+        CK(cudaMemcpyAsync(base + off_atom, atom_d, 16 * (size_t)NA, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(base + off_rows, atom_type_rows, 96 * (size_t)NA, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(base + off_has, atom_has_type, (size_t)NA, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (n) {
+        k_leaf_component<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+            reinterpret_cast<double *>(base + off_stl), n, reinterpret_cast<double *>(base + off_comp), n_layer, n_interlayer,
+            reinterpret_cast<double *>(base + off_atom), reinterpret_cast<double *>(base + off_rows),
+            reinterpret_cast<unsigned char *>(base + off_has), reinterpret_cast<double2 *>(base + off_sf),
+            reinterpret_cast<double2 *>(base + off_phi), reinterpret_cast<double *>(base + off_z));
+        LAUNCH_CHECK("k_leaf_component");
+        CK(cudaMemcpyAsync(sf_out, base + off_sf, 16 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(phi_out, base + off_phi, 16 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (NA) CK(cudaMemcpyAsync(z_out, base + off_z, 8 * (size_t)NA, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pyxrd_stage_times(pyxrd_ctx *ctx, double *ms_out) {
+    if (!ctx || !ms_out) return 1;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int pairs[4][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}};
+    for (int i = 0; i < 4; ++i) {
+        float ms = 0.f;
+        if (ctx->ev_set[i]) CK(cudaEventElapsedTime(&ms, ctx->ev[pairs[i][0]], ctx->ev[pairs[i][1]]));
+        ms_out[i] = ms;
+    }
+    return 0;
+}
+
+int pyxrd_dfma_peak(pyxrd_ctx *ctx, int iterations, double *tflops_out, double *ms_out) {
+    if (!ctx) return 1;
+    CK(cudaSetDevice(ctx->device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int blocks = sms * 8, threads = 256;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->d_leaf_c.as<double>(), 16, 1.0);   // warm-up
+    LAUNCH_CHECK("k_dfma_peak");
+    CK(cudaEventRecord(e0, ctx->stream));
+    k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->d_leaf_c.as<double>(), iterations, 1.0);
+    LAUNCH_CHECK("k_dfma_peak");
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iterations * (double)blocks * threads;
+    if (tflops_out) *tflops_out = flops / (ms * 1e-3) * 1e-12;
+    if (ms_out) *ms_out = ms;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+"""Flatten DataObject graphs into the plain arrays of ``include/pyxrd_b200.h``.
+
+This is the host half of the drop-in boundary: the reference
+hands ``pyxrd.calculations`` nested Python objects (data_objects.py:22-271); the
+C-ABI wants structure-of-arrays buffers.  Only *layout* happens here -- every
+per-candidate arithmetic step of the reference runs on the device.
+
+The one numeric thing prepared on the host is the abscissa part of the
+wavelength-distribution interpolation (specimen.py:64-69): indices and lerp
+weights of ``interp1d(arcsin(stl*lambda_j/2), ., fill_value=0)(theta)``.  They are
+candidate-invariant lookup tables; they are built with numpy because whether the
+first / last point falls inside the interpolation range is decided by a 1-ulp
+comparison of numpy's ``arcsin`` against ``theta``, so only
+numpy's own ``arcsin`` reproduces the reference there.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+GONIO_STRIDE = 12
+ATYPE_STRIDE = 12
+PHASE_I_STRIDE = 8
+PHASE_D_STRIDE = 8
+COMP_D_STRIDE = 8
+COMP_I_STRIDE = 4
+ATOM_D_STRIDE = 2
+
+FLAG_VALID_PROBS = 1
+FLAG_APPLY_LPF = 2
+FLAG_APPLY_CORRECTION = 4
+
+_DIV_MODES = {"FIXED": 0.0, "AUTOMATIC": 1.0}
+
+
+def _atype_key(at) -> bytes:
+    row = np.empty(ATYPE_STRIDE)
+    row[0:5] = np.asarray(at.par_a, dtype=float)
+    row[5:10] = np.asarray(at.par_b, dtype=float)
+    row[10] = float(at.par_c)
+    row[11] = float(at.debye)
+    return row.tobytes()
+
+
+def iter_phases(specimen):
+    for row in specimen.phases:
+        for phase in row:
+            if phase is not None:
+                yield phase
+
+
+def collect_atom_types(mixtures_or_specimens) -> Dict[bytes, int]:
+    """value-keyed table of every atom type reachable from the given specimens"""
+    table: Dict[bytes, int] = {}
+    for spec in mixtures_or_specimens:
+        if spec is None:
+            continue
+        for phase in iter_phases(spec):
+            if getattr(phase, "type", "Phase") != "Phase" or not phase.valid_probs:
+                continue
+            for comp in phase.components:
+                for atom in list(comp.layer_atoms) + list(comp.interlayer_atoms):
+                    if atom is not None and atom.atom_type is not None:
+                        table.setdefault(_atype_key(atom.atom_type), len(table))
+    return table
+
+
+def wavelength_tables(theta: np.ndarray, wavelength: float, distribution):
+    """index / weights of the shifted-abscissa linear interpolation, per list entry.
+
+    scipy 1.18.1 ``interp1d._call_linear`` + ``_check_bounds``: ``hi =
+    searchsorted(x, x_new).clip(1, n-1)``, ``y = w_hi*y[hi] + w_lo*y[hi-1]`` with
+    ``w_hi = (x_new-x_lo)/(x_hi-x_lo)``, ``w_lo = (x_hi-x_new)/(x_hi-x_lo)``; 0 outside.
+    """
+    theta = np.asarray(theta, dtype=float)
+    X = theta.size
+    n = len(distribution)
+    idx = np.full((n, X), -1, dtype=np.int32)
+    w_hi = np.zeros((n, X))
+    w_lo = np.zeros((n, X))
+    frac = np.zeros(n)
+    if X == 0:
+        return frac, idx, w_hi, w_lo
+    stl = 2 * np.sin(theta) / wavelength
+    for j, (wl, f) in enumerate(distribution):
+        frac[j] = f
+        shifted = np.arcsin(stl * wl * 0.5)
+        if X < 2 or not np.all(np.isfinite(shifted)) or np.any(np.diff(shifted) <= 0):
+            raise ValueError("wavelength %r gives a non-monotonic / invalid shifted 2-theta axis" % (wl,))
+        hi = np.searchsorted(shifted, theta).clip(1, X - 1).astype(np.int64)
+        x_lo, x_hi = shifted[hi - 1], shifted[hi]
+        w_hi[j] = (theta - x_lo) / (x_hi - x_lo)
+        w_lo[j] = (x_hi - theta) / (x_hi - x_lo)
+        outside = (theta < shifted[0]) | (theta > shifted[-1])
+        idx[j] = np.where(outside, -1, hi).astype(np.int32)
+    return frac, idx, w_hi, w_lo
+
+
+class StaticPack(object):
+    """Candidate-invariant tables of a set of specimens (pyxrd_static_desc)."""
+
+    def __init__(self, specimens: Sequence, atom_types: Dict[bytes, int], n_patterns: Optional[int] = None,
+                 stl_override: Optional[np.ndarray] = None):
+        S = len(specimens)
+        self.stl_override = None if stl_override is None else np.ascontiguousarray(stl_override, dtype=float).ravel()
+        self.S = S
+        self.atom_types = dict(atom_types)
+        self.T = len(self.atom_types)
+        if n_patterns is None:
+            n_patterns = 0
+            for spec in specimens:
+                if spec is not None:
+                    n_patterns = len(spec.z_list)
+                    break
+        self.Z = int(n_patterns)
+        self.npts = np.zeros(S, dtype=np.int32)
+        self.gonio = np.zeros((S, GONIO_STRIDE))
+        self.nwl = np.zeros(S, dtype=np.int32)
+        thetas, fracs, idxs, whis, wlos, obss, sels = [], [], [], [], [], [], []
+        for s, spec in enumerate(specimens):
+            if spec is None:            # None specimen -> residual 0.0 (mixture.py:241-252)
+                continue
+            theta = np.ascontiguousarray(spec.range_theta, dtype=float)
+            X = theta.size
+            self.npts[s] = X
+            g = spec.goniometer
+            mode = _DIV_MODES.get(g.divergence_mode, 2.0)
+            self.gonio[s, :11] = [g.wavelength, g.soller1, g.soller2, g.mcr_2theta, mode,
+                                  g.divergence if g.divergence is not None else 0.0,
+                                  float(g.has_absorption_correction or 0.0), g.absorption,
+                                  g.sample_surf_density, g.sample_length if g.sample_length is not None else 0.0,
+                                  g.radius if g.radius is not None else 1.0]
+            dist = list(g.wavelength_distribution or [])
+            self.nwl[s] = len(dist)
+            frac, idx, w_hi, w_lo = wavelength_tables(theta, g.wavelength, dist)
+            thetas.append(theta)
+            fracs.append(frac)
+            idxs.append(idx.ravel())
+            whis.append(w_hi.ravel())
+            wlos.append(w_lo.ravel())
+            obs = np.asarray(spec.observed_intensity, dtype=float)
+            if obs.size == 0:
+                obs_t = np.zeros((self.Z, X))
+                self.no_observations = getattr(self, "no_observations", set()) | {s}
+            else:
+                obs_t = np.ascontiguousarray(obs.reshape(X, -1).T)
+                if obs_t.shape[0] != self.Z:
+                    raise ValueError("specimen %d: observed_intensity has %d patterns, z_list has %d"
+                                     % (s, obs_t.shape[0], self.Z))
+            obss.append(obs_t.ravel())
+            sel = spec.selected_range
+            sel = np.ones(X, dtype=bool) if sel is None else np.asarray(sel)
+            if sel.dtype != np.bool_:     # an index array selects the same points as a mask
+                mask = np.zeros(X, dtype=bool)
+                mask[sel] = True
+                sel = mask
+            sels.append(sel.astype(np.uint8))
+
+        def cat(parts, dtype):
+            return np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0), dtype=dtype)
+
+        self.theta = cat(thetas, float)
+        self.wl_fraction = cat(fracs, float)
+        self.wl_index = cat(idxs, np.int32)
+        self.wl_w_hi = cat(whis, float)
+        self.wl_w_lo = cat(wlos, float)
+        self.observed = cat(obss, float)
+        self.selected = cat(sels, np.uint8)
+        self.offsets = np.concatenate([[0], np.cumsum(self.npts, dtype=np.int64)])
+        self.sumX = int(self.offsets[-1])
+        self.atype_table = np.zeros((max(self.T, 1), ATYPE_STRIDE))
+        for key, i in self.atom_types.items():
+            self.atype_table[i] = np.frombuffer(key, dtype=float)
+        if not hasattr(self, "no_observations"):
+            self.no_observations = set()
+
+    def signature(self):
+        """cheap identity of the tables, to decide whether a resident copy can be reused"""
+        return (self.S, self.Z, self.T, self.npts.tobytes(), self.gonio.tobytes(), self.theta.tobytes(),
+                self.wl_fraction.tobytes(), self.observed.tobytes(), self.selected.tobytes(),
+                self.atype_table.tobytes(), None if self.stl_override is None else self.stl_override.tobytes())
+
+
+class BatchPack(object):
+    """Per-candidate parameter blocks of K mixtures (pyxrd_batch_desc)."""
+
+    def __init__(self, mixtures: Sequence, static: StaticPack, bgshift_enabled: bool = True):
+        K = len(mixtures)
+        S, Z = static.S, static.Z
+        M = None
+        phase_i: List[List[int]] = []
+        phase_d: List[List[float]] = []
+        phase_comp: List[int] = []
+        matrices: List[np.ndarray] = []
+        mat_off = 0
+        comp_d: List[List[float]] = []
+        comp_i: List[List[int]] = []
+        atom_d: List[float] = []
+        atom_t: List[int] = []
+        jobs: List[int] = []
+        self.components_of_phase: List[List[object]] = []
+        fractions = []
+        scales = np.zeros((K, S))
+        bgshifts = np.zeros((K, S))
+        for k, mix in enumerate(mixtures):
+            specimens = mix.specimens
+            if len(specimens) != S:
+                raise ValueError("candidate %d has %d specimens, the static tables have %d" % (k, len(specimens), S))
+            fr = np.asarray(mix.fractions, dtype=float).ravel()
+            if M is None:
+                M = fr.size
+            if fr.size != M:
+                raise ValueError("candidate %d has %d phases, expected %d" % (k, fr.size, M))
+            fractions.append(fr)
+            scales[k] = np.asarray(mix.scales, dtype=float).ravel()[:S]
+            if bgshift_enabled:
+                bgshifts[k] = np.asarray(mix.bgshifts, dtype=float).ravel()[:S]
+            phase_ids: Dict[int, int] = {}
+            comp_ids: Dict[int, int] = {}
+            for s, spec in enumerate(specimens):
+                for z in range(Z):
+                    row = spec.phases[z] if spec is not None else [None] * M
+                    if len(row) != M:
+                        raise ValueError("specimen %d pattern %d lists %d phases, expected %d" % (s, z, len(row), M))
+                    for phase in row:
+                        if phase is None:
+                            jobs.append(-1)
+                            continue
+                        pid = phase_ids.get(id(phase))
+                        if pid is None:
+                            pid = len(phase_i)
+                            phase_ids[id(phase)] = pid
+                            mat_off = self._pack_phase(phase, static, phase_i, phase_d, phase_comp, matrices, mat_off,
+                                                       comp_d, comp_i, atom_d, atom_t, comp_ids)
+                        jobs.append(pid)
+        self.K, self.M, self.S, self.Z = K, int(M or 0), S, Z
+        self.phase_i = np.ascontiguousarray(np.array(phase_i, dtype=np.int32).reshape(-1, PHASE_I_STRIDE))
+        self.phase_d = np.ascontiguousarray(np.array(phase_d, dtype=float).reshape(-1, PHASE_D_STRIDE))
+        self.phase_comp = np.ascontiguousarray(np.array(phase_comp, dtype=np.int32))
+        self.matrices = np.ascontiguousarray(np.concatenate(matrices) if matrices else np.zeros(0), dtype=float)
+        self.comp_d = np.ascontiguousarray(np.array(comp_d, dtype=float).reshape(-1, COMP_D_STRIDE))
+        self.comp_i = np.ascontiguousarray(np.array(comp_i, dtype=np.int32).reshape(-1, COMP_I_STRIDE))
+        self.atom_d = np.ascontiguousarray(np.array(atom_d, dtype=float).reshape(-1, ATOM_D_STRIDE))
+        self.atom_type = np.ascontiguousarray(np.array(atom_t, dtype=np.int32))
+        self.job_phase = np.ascontiguousarray(np.array(jobs, dtype=np.int32))
+        self.fractions = np.ascontiguousarray(np.array(fractions, dtype=float).reshape(K, self.M))
+        self.scales = np.ascontiguousarray(scales)
+        self.bgshifts = np.ascontiguousarray(bgshifts)
+
+    def _pack_phase(self, phase, static, phase_i, phase_d, phase_comp, matrices, mat_off,
+                    comp_d, comp_i, atom_d, atom_t, comp_ids):
+        ptype = getattr(phase, "type", "Phase")
+        if ptype == "AbtractPhase":
+            raise NotImplementedError          # phases.py:74-75
+        if ptype != "Phase":
+            raise NotImplementedError("phase type %r is not on the device path yet (see DESIGN.md)" % (ptype,))
+        flags = 0
+        if getattr(phase, "apply_lpf", True):
+            flags |= FLAG_APPLY_LPF
+        if getattr(phase, "apply_correction", True):
+            flags |= FLAG_APPLY_CORRECTION
+        if not phase.valid_probs:
+            phase_i.append([0, 0, 0, 0, flags, 0, 0, 0])
+            phase_d.append([0.0] * PHASE_D_STRIDE)
+            self.components_of_phase.append([])
+            return mat_off
+        flags |= FLAG_VALID_PROBS
+        W = np.asarray(phase.W, dtype=float)
+        P = np.asarray(phase.P, dtype=float)
+        rank = P.shape[1]
+        G = int(phase.G)
+        if W.shape != (rank, rank) or P.shape != (rank, rank):
+            raise ValueError("W / P must be rank x rank")
+        csds = phase.CSDS
+        phase_i.append([G, rank, int(csds.minimum), int(csds.maximum), flags, len(phase_comp), mat_off, 0])
+        phase_d.append([float(phase.sigma_star), float(csds.average), float(csds.alpha_scale),
+                        float(csds.alpha_offset), float(csds.beta_scale), float(csds.beta_offset), 0.0, 0.0])
+        matrices.append(W.ravel())
+        matrices.append(P.ravel())
+        mat_off += 2 * rank * rank
+        comps = list(phase.components)
+        if len(comps) != G:
+            raise ValueError("phase has %d components but G = %d" % (len(comps), G))
+        self.components_of_phase.append(comps)
+        for comp in comps:
+            cid = comp_ids.get(id(comp))
+            if cid is None:
+                cid = len(comp_d)
+                comp_ids[id(comp)] = cid
+                layer = list(comp.layer_atoms)
+                inter = list(comp.interlayer_atoms)
+                comp_d.append([float(comp.d001), float(comp.default_c), float(comp.delta_c), float(comp.lattice_d),
+                               float(comp.volume), float(comp.weight), 0.0, 0.0])
+                comp_i.append([len(atom_t), len(layer), len(inter), 0])
+                for atom in layer + inter:
+                    if atom is None or atom.atom_type is None:
+                        atom_d.extend([0.0, 0.0])
+                        atom_t.append(-1)
+                    else:
+                        atom_d.extend([float(atom.pn), float(atom.default_z)])
+                        atom_t.append(static.atom_types[_atype_key(atom.atom_type)])
+            phase_comp.append(cid)
+        return mat_off

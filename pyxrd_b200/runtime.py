@@ -1,0 +1,343 @@
+"""ctypes binding of ``libpyxrd_b200.so`` (the C-ABI of include/pyxrd_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` /
+``pyxrd_b200/csrc/build.py``.  There is no CPU fallback: if the library is
+missing or no CUDA device is present, constructing a :class:`Context` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+
+from .packing import BatchPack, StaticPack
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpyxrd_b200.so")
+
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+class StaticDesc(C.Structure):
+    _fields_ = [("n_specimens", C.c_int32), ("n_atom_types", C.c_int32), ("n_patterns", C.c_int32),
+                ("reserved", C.c_int32), ("spec_npts", _i32p), ("theta", _f64p), ("spec_gonio", _f64p),
+                ("spec_nwl", _i32p), ("wl_fraction", _f64p), ("wl_index", _i32p), ("wl_w_hi", _f64p),
+                ("wl_w_lo", _f64p), ("observed", _f64p), ("selected", _u8p), ("atom_types", _f64p),
+                ("stl_override", _f64p)]
+
+
+class BatchDesc(C.Structure):
+    _fields_ = [("n_candidates", C.c_int32), ("n_phase_slots", C.c_int32), ("n_phases", C.c_int32),
+                ("n_components", C.c_int32), ("n_atoms", C.c_int32), ("n_phase_comp", C.c_int32),
+                ("n_matrix", C.c_int64), ("phase_i", _i32p), ("phase_d", _f64p), ("phase_comp", _i32p),
+                ("matrices", _f64p), ("comp_d", _f64p), ("comp_i", _i32p), ("atom_d", _f64p),
+                ("atom_type", _i32p), ("job_phase", _i32p), ("fractions", _f64p), ("scales", _f64p),
+                ("bgshifts", _f64p)]
+
+
+# every symbol include/pyxrd_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "pyxrd_create", "pyxrd_destroy", "pyxrd_last_error", "pyxrd_set_stream", "pyxrd_synchronize",
+    "pyxrd_launch_count", "pyxrd_set_static", "pyxrd_set_batch", "pyxrd_set_solution", "pyxrd_set_intensities",
+    "pyxrd_compute_intensities", "pyxrd_compute_residuals", "pyxrd_intensity_count", "pyxrd_total_count",
+    "pyxrd_read_intensities", "pyxrd_read_scaled", "pyxrd_read_totals", "pyxrd_read_residuals",
+    "pyxrd_read_correction", "pyxrd_device_buffers", "pyxrd_evaluate_host", "pyxrd_leaf_asf",
+    "pyxrd_leaf_lpf", "pyxrd_leaf_csds", "pyxrd_leaf_component", "pyxrd_stage_times", "pyxrd_dfma_peak",
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+class DeviceError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the in-tree shared library (no compute, no CUDA initialisation)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(pyxrd_b200 has no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        lib.pyxrd_create.argtypes = [C.c_int, C.POINTER(vp)]
+        lib.pyxrd_destroy.argtypes = [vp]
+        lib.pyxrd_destroy.restype = None
+        lib.pyxrd_last_error.argtypes = [vp]
+        lib.pyxrd_last_error.restype = C.c_char_p
+        lib.pyxrd_set_stream.argtypes = [vp, vp]
+        lib.pyxrd_synchronize.argtypes = [vp]
+        lib.pyxrd_launch_count.argtypes = [vp]
+        lib.pyxrd_launch_count.restype = C.c_int64
+        lib.pyxrd_set_static.argtypes = [vp, C.POINTER(StaticDesc)]
+        lib.pyxrd_set_batch.argtypes = [vp, C.POINTER(BatchDesc)]
+        lib.pyxrd_set_solution.argtypes = [vp, _f64p, _f64p, _f64p]
+        lib.pyxrd_set_intensities.argtypes = [vp, _f64p, C.c_int64]
+        lib.pyxrd_compute_intensities.argtypes = [vp]
+        lib.pyxrd_compute_residuals.argtypes = [vp, C.c_int]
+        lib.pyxrd_intensity_count.argtypes = [vp]
+        lib.pyxrd_intensity_count.restype = C.c_int64
+        lib.pyxrd_total_count.argtypes = [vp]
+        lib.pyxrd_total_count.restype = C.c_int64
+        for name in ("pyxrd_read_intensities", "pyxrd_read_scaled", "pyxrd_read_totals", "pyxrd_read_residuals",
+                     "pyxrd_read_correction"):
+            getattr(lib, name).argtypes = [vp, _f64p, C.c_int64]
+        lib.pyxrd_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        lib.pyxrd_evaluate_host.argtypes = [vp, C.POINTER(BatchDesc), _f64p, _f64p]
+        lib.pyxrd_leaf_asf.argtypes = [vp, _f64p, C.c_int64, _f64p, _f64p]
+        lib.pyxrd_leaf_lpf.argtypes = [vp, _f64p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _f64p]
+        lib.pyxrd_leaf_csds.argtypes = [vp, _f64p, C.c_int, C.c_int, _f64p, _f64p, _f64p]
+        lib.pyxrd_leaf_component.argtypes = [vp, _f64p, C.c_int64, _f64p, C.c_int, C.c_int, _f64p, _f64p, _u8p,
+                                             _f64p, _f64p, _f64p]
+        lib.pyxrd_stage_times.argtypes = [vp, _f64p]
+        lib.pyxrd_dfma_peak.argtypes = [vp, C.c_int, _f64p, _f64p]
+        _lib = lib
+        return lib
+
+
+def _p(arr, typ):
+    return arr.ctypes.data_as(typ)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context(object):
+    """One device context = one CUDA stream + resident tables / batch / results."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.pyxrd_create(int(device), C.byref(self._h))
+        if rc != 0 or not self._h:
+            self._h = C.c_void_p()
+            raise DeviceError("pyxrd_create(device=%d) failed with status %d: no usable CUDA device "
+                              "(pyxrd_b200 has no CPU fallback)" % (device, rc))
+        self.device = int(device)
+        self.lock = threading.RLock()
+        self._static: Optional[StaticPack] = None
+        self._static_sig = None
+        self._batch: Optional[BatchPack] = None
+        self._keep = []
+
+    # -- plumbing ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pyxrd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.pyxrd_last_error(self._h)
+            raise DeviceError("%s failed: %s" % (what, msg.decode("utf-8", "replace") if msg else rc))
+
+    def set_stream(self, cuda_stream_handle: Optional[int]):
+        self._check(self._lib.pyxrd_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)), "set_stream")
+
+    def synchronize(self):
+        self._check(self._lib.pyxrd_synchronize(self._h), "synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.pyxrd_launch_count(self._h))
+
+    # -- upload -----------------------------------------------------------------------
+    def set_static(self, static: StaticPack, force: bool = False):
+        sig = static.signature()
+        if not force and self._static_sig == sig:
+            self._static = static
+            return False
+        d = StaticDesc(static.S, static.T, static.Z, 0, _p(static.npts, _i32p), _p(static.theta, _f64p),
+                       _p(static.gonio, _f64p), _p(static.nwl, _i32p), _p(static.wl_fraction, _f64p),
+                       _p(static.wl_index, _i32p), _p(static.wl_w_hi, _f64p), _p(static.wl_w_lo, _f64p),
+                       _p(static.observed, _f64p), _p(static.selected, _u8p), _p(static.atype_table, _f64p),
+                       _p(static.stl_override, _f64p) if static.stl_override is not None else None)
+        self._check(self._lib.pyxrd_set_static(self._h, C.byref(d)), "set_static")
+        self._static, self._static_sig, self._batch = static, sig, None
+        return True
+
+    @staticmethod
+    def batch_desc(b: BatchPack) -> BatchDesc:
+        return BatchDesc(b.K, b.M, b.phase_i.shape[0], b.comp_d.shape[0], b.atom_type.shape[0],
+                         b.phase_comp.shape[0], b.matrices.shape[0], _p(b.phase_i, _i32p), _p(b.phase_d, _f64p),
+                         _p(b.phase_comp, _i32p), _p(b.matrices, _f64p), _p(b.comp_d, _f64p), _p(b.comp_i, _i32p),
+                         _p(b.atom_d, _f64p), _p(b.atom_type, _i32p), _p(b.job_phase, _i32p),
+                         _p(b.fractions, _f64p), _p(b.scales, _f64p), _p(b.bgshifts, _f64p))
+
+    def set_batch(self, batch: BatchPack):
+        d = self.batch_desc(batch)
+        self._check(self._lib.pyxrd_set_batch(self._h, C.byref(d)), "set_batch")
+        self._batch = batch
+
+    def set_solution(self, fractions, scales, bgshifts):
+        b = self._batch
+        f, s, g = _f64(fractions).reshape(b.K, b.M), _f64(scales).reshape(b.K, b.S), _f64(bgshifts).reshape(b.K, b.S)
+        self._check(self._lib.pyxrd_set_solution(self._h, _p(f, _f64p), _p(s, _f64p), _p(g, _f64p)), "set_solution")
+
+    def set_intensities(self, flat):
+        flat = _f64(flat).ravel()
+        self._check(self._lib.pyxrd_set_intensities(self._h, _p(flat, _f64p), flat.size), "set_intensities")
+
+    # -- compute ----------------------------------------------------------------------
+    def compute_intensities(self):
+        self._check(self._lib.pyxrd_compute_intensities(self._h), "compute_intensities")
+
+    def compute_residuals(self, want_scaled: bool = False):
+        self._check(self._lib.pyxrd_compute_residuals(self._h, int(bool(want_scaled))), "compute_residuals")
+
+    def evaluate_host(self, batch: BatchPack, want_intensities: bool = False, out_residuals=None,
+                      out_intensities=None):
+        """one C-ABI call: upload K candidates, compute, return residuals [K, 1+S] (+ intensities).
+        ``out_*`` may be preallocated (e.g. pinned) float64 arrays."""
+        d = self.batch_desc(batch)
+        res = np.empty(batch.K * (batch.S + 1)) if out_residuals is None else out_residuals
+        inten = out_intensities
+        if inten is None and want_intensities:
+            inten = np.empty(batch.K * batch.M * batch.Z * self._static.sumX)
+        self._check(self._lib.pyxrd_evaluate_host(self._h, C.byref(d), _p(res, _f64p),
+                                                  _p(inten, _f64p) if inten is not None else None), "evaluate_host")
+        self._batch = batch
+        return res.reshape(batch.K, batch.S + 1), inten
+
+    # -- results ----------------------------------------------------------------------
+    def _read(self, fn, count):
+        out = np.empty(int(count))
+        self._check(fn(self._h, _p(out, _f64p), int(count)), fn.__name__)
+        return out
+
+    def read_intensities_flat(self):
+        return self._read(self._lib.pyxrd_read_intensities, self._lib.pyxrd_intensity_count(self._h))
+
+    def read_scaled_flat(self):
+        return self._read(self._lib.pyxrd_read_scaled, self._lib.pyxrd_intensity_count(self._h))
+
+    def read_totals_flat(self):
+        return self._read(self._lib.pyxrd_read_totals, self._lib.pyxrd_total_count(self._h))
+
+    def read_residuals(self):
+        b = self._batch
+        return self._read(self._lib.pyxrd_read_residuals, b.K * (b.S + 1)).reshape(b.K, b.S + 1)
+
+    def read_correction_flat(self):
+        return self._read(self._lib.pyxrd_read_correction, self._static.sumX)
+
+    def split_per_specimen(self, flat, lead):
+        """flat [K][S][lead...][X_s] -> list over k of list over s of arrays [lead..., X_s]"""
+        st, b = self._static, self._batch
+        n_lead = int(np.prod(lead))
+        out, pos = [], 0
+        for _ in range(b.K):
+            per = []
+            for s in range(st.S):
+                X = int(st.npts[s])
+                per.append(flat[pos:pos + n_lead * X].reshape(tuple(lead) + (X,)))
+                pos += n_lead * X
+            out.append(per)
+        return out
+
+    def device_buffers(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.pyxrd_device_buffers(self._h, C.byref(a), C.byref(b), C.byref(c)), "device_buffers")
+        return a.value, b.value, c.value
+
+    # -- leaf helpers -----------------------------------------------------------------
+    def leaf_asf(self, s, atom_type_row):
+        s = _f64(s).ravel()
+        row = _f64(atom_type_row).ravel()
+        out = np.empty_like(s)
+        self._check(self._lib.pyxrd_leaf_asf(self._h, _p(s, _f64p), s.size, _p(row, _f64p), _p(out, _f64p)), "leaf_asf")
+        return out
+
+    def leaf_lpf(self, theta, sigma_star, soller1, soller2, mcr_2theta):
+        t = _f64(theta).ravel()
+        out = np.empty_like(t)
+        self._check(self._lib.pyxrd_leaf_lpf(self._h, _p(t, _f64p), t.size, float(sigma_star), float(soller1),
+                                             float(soller2), float(mcr_2theta), _p(out, _f64p)), "leaf_lpf")
+        return out
+
+    def leaf_csds(self, average, alpha_scale, alpha_offset, beta_scale, beta_offset, minimum, maximum):
+        p = _f64([average, alpha_scale, alpha_offset, beta_scale, beta_offset])
+        arr = np.empty(int(maximum) + 1)
+        mean = np.empty(1)
+        coef = np.empty(int(maximum) + 2)
+        self._check(self._lib.pyxrd_leaf_csds(self._h, _p(p, _f64p), int(minimum), int(maximum), _p(arr, _f64p),
+                                              _p(mean, _f64p), _p(coef, _f64p)), "leaf_csds")
+        return arr, float(mean[0]), coef
+
+    def leaf_component(self, stl, comp_row, n_layer, n_inter, atom_d, atom_rows, has_type):
+        """(SF complex[n], phi complex[n], z[NA]) of one component on an arbitrary stl axis"""
+        stl = _f64(stl).ravel()
+        comp_row = _f64(comp_row).ravel()
+        na = int(n_layer) + int(n_inter)
+        atom_d = _f64(atom_d).reshape(max(na, 0), 2) if na else np.zeros((1, 2))
+        atom_rows = _f64(atom_rows).reshape(na, 12) if na else np.zeros((1, 12))
+        has = np.ascontiguousarray(has_type, dtype=np.uint8) if na else np.zeros(1, dtype=np.uint8)
+        sf = np.zeros(stl.size, dtype=np.complex128)
+        phi = np.zeros(stl.size, dtype=np.complex128)
+        z = np.zeros(max(na, 1))
+        self._check(self._lib.pyxrd_leaf_component(self._h, _p(stl, _f64p), stl.size, _p(comp_row, _f64p), int(n_layer),
+                                                   int(n_inter), _p(atom_d, _f64p), _p(atom_rows, _f64p), _p(has, _u8p),
+                                                   sf.ctypes.data_as(_f64p), phi.ctypes.data_as(_f64p), _p(z, _f64p)),
+                    "leaf_component")
+        return sf, phi, z[:na]
+
+    def stage_times(self):
+        """dict of CUDA-event milliseconds of the latest phase / wavelength / residual / prologue stages"""
+        out = np.zeros(4)
+        self._check(self._lib.pyxrd_stage_times(self._h, _p(out, _f64p)), "stage_times")
+        return dict(phase=out[0], wavelength=out[1], residual=out[2], prologue=out[3])
+
+    def residuals_tensor(self):
+        """zero-copy torch view f64[K, 1+S] of the device residual buffer (for the NCCL gather)"""
+        import torch
+        b = self._batch
+        _, _, res = self.device_buffers()
+
+        class _View(object):
+            __cuda_array_interface__ = dict(shape=(b.K, b.S + 1), typestr="<f8", data=(int(res), False), version=3)
+
+        return torch.as_tensor(_View(), device="cuda:%d" % self.device)
+
+    def dfma_peak(self, iterations: int = 4096):
+        t, ms = C.c_double(), C.c_double()
+        self._check(self._lib.pyxrd_dfma_peak(self._h, int(iterations), C.byref(t), C.byref(ms)), "dfma_peak")
+        return t.value, ms.value
+
+
+_contexts = {}
+_ctx_lock = threading.Lock()
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    """Process-wide context, created lazily (after any fork: SURVEY.md §8(b) threading model)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("PYXRD_B200_DEVICE") is None \
+            else int(os.environ["PYXRD_B200_DEVICE"])
+    key = (os.getpid(), device)
+    with _ctx_lock:
+        ctx = _contexts.get(key)
+        if ctx is None:
+            ctx = Context(device)
+            _contexts[key] = ctx
+        return ctx

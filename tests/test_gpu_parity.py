@@ -1,0 +1,254 @@
+"""Parity of the CUDA path (through the C-ABI) against the live-reference golden
+vectors and the CPU oracle.  Tolerance for intensities / totals / residuals at a given
+solution: relative 1e-9 per point (north_star); measured agreement is ~1e-12."""
+import copy
+
+import numpy as np
+import pytest
+
+from helpers import SEED, golden_mixtures, rel_err
+from oracle import pyxrd_oracle as orc
+from pyxrd_b200 import synthetic as syn
+from pyxrd_b200.data_objects import AtomData, AtomTypeData, ComponentData, CSDSData
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9          # north_star tolerance, fp64
+OPT_RTOL = 5e-3      # optimiser end point: only reproducible to ~1e-3 (see test_oracle_golden.py)
+
+KAT_THETA = np.asanyarray([2.2551711385, 2.478038901, 2.7001518288, 2.9214422642, 3.1418428,
+                           3.3612863, 3.5797059197, 3.7970351263])
+
+
+@pytest.fixture(scope="module")
+def calc():
+    import pyxrd_b200.calculations as c
+    return c
+
+
+# ---- the reference's own known-answer vectors, through the device leaf functions ---------
+def test_kat_lpf(calc):
+    got = calc.goniometer.get_lorentz_polarisation_factor(KAT_THETA, 12, 2.3, 2.3, 0)
+    want = [3.00643375e-03, 4.83799816e-03, 1.33173586e-02, 6.56714627e-02, 5.11941694e+02,
+            6.59637604e-02, 1.35695934e-02, 4.97673826e-03]
+    assert np.allclose(got, want)                     # test_goniometer.py:74-86
+    assert rel_err(got, orc.get_lorentz_polarisation_factor(KAT_THETA, 12, 2.3, 2.3, 0)) < 1e-11
+
+
+def test_kat_ads(calc):
+    got = calc.goniometer.get_fixed_to_ads_correction_range(KAT_THETA, None)
+    want = [7.74814435e-01, 6.15920411e-01, 4.27242611e-01, 2.18376385e-01, -2.50146408e-04,
+            -2.17930643e-01, -4.24231682e-01, -6.09510086e-01]
+    assert np.allclose(got, want)                     # test_goniometer.py:63-72
+
+
+def test_kat_asf(calc):
+    at = AtomTypeData(par_a=np.full(5, 10.2), par_b=np.full(5, 10.2), par_c=20.2, debye=0.0)
+    stl = np.array([0.1152, 0.5756, 1.1469])
+    got = calc.atoms.get_atomic_scattering_factor((stl * 0.05) ** 2, at)
+    want = [71.1827439324707, 70.77093939463964, 69.51772020477823]   # test_atom_type.py:58-75
+    assert rel_err(got, want) < 1e-14
+    assert np.array_equal(calc.atoms.get_atomic_scattering_factor(stl, None), np.zeros(3))
+
+
+def test_leaf_component_and_csds(calc, golden):
+    g = golden("kat")
+    h = AtomTypeData(par_a=np.asanyarray([0.413048, 0.294953, 0.187491, 0.080701, 0.023736]),
+                     par_b=np.asanyarray([15.569946, 32.398468, 5.711404, 61.889874, 1.334118]),
+                     par_c=0.000049, debye=0)
+    comp = ComponentData(layer_atoms=[AtomData(atom_type=h, pn=1, default_z=0, z=0)],
+                         interlayer_atoms=[AtomData(atom_type=h, pn=1, default_z=0.55, z=0.55)],
+                         volume=1.0, weight=1.0, d001=0.55, default_c=0.6, delta_c=0.02, lattice_d=0.45)
+    sf, phi = calc.components.get_factors(g["kat_theta"], comp)
+    assert np.max(np.abs(sf - g["kat_comp_sf"])) < 1e-13
+    assert np.max(np.abs(phi - g["kat_comp_phi"])) < 1e-13
+    comp2 = copy.deepcopy(comp)
+    orc.get_factors(g["kat_theta"], comp2)
+    assert comp.interlayer_atoms[0].z == comp2.interlayer_atoms[0].z        # the z write-back
+    sfa = calc.atoms.get_structure_factor(g["kat_theta"], comp.interlayer_atoms[0])
+    assert np.max(np.abs(sfa - orc.get_structure_factor(g["kat_theta"], comp2.interlayer_atoms[0]))) < 1e-13
+    csds = CSDSData(average=10, maximum=50, minimum=1, alpha_scale=0.9485, alpha_offset=0.017,
+                    beta_scale=0.1032, beta_offset=0.0034)
+    arr, mean = calc.CSDS.calculate_distribution(csds)
+    assert rel_err(arr, g["kat_csds_arr"]) < 1e-13 and abs(mean - float(g["kat_csds_mean"])) < 1e-12
+    coef = calc.CSDS.progression_factors(csds)
+    want = orc.progression_factors(g["kat_csds_arr"], 1, 50)
+    assert rel_err(coef[1:51], [want[n] for n in range(1, 51)]) < 1e-12
+
+
+# ---- the BASELINE configs against live-reference outputs ----------------------------------
+@pytest.mark.parametrize("name", ["c1", "c2", "c4", "c5", "c3"])
+def test_config_matches_live_reference(calc, golden, name):
+    g = golden(name)
+    for tag, mix in golden_mixtures(name, g):
+        calc.mixture.calculate_mixture(mix)
+        for s, spec in enumerate(mix.specimens):
+            assert rel_err(spec.correction, g["%s_%s_corr_s%d" % (name, tag, s)]) < 1e-14
+            assert rel_err(spec.phase_intensities, g["%s_%s_pi_s%d" % (name, tag, s)]) < RTOL, (name, tag, s)
+            assert rel_err(spec.total_intensity, g["%s_%s_total_s%d" % (name, tag, s)]) < RTOL
+        assert rel_err(mix.residuals, g["%s_%s_residuals" % (name, tag)]) < RTOL
+        x = np.array(g["%s_%s_x" % (name, tag)])
+        mix.calculated = False
+        res = calc.mixture._get_residuals(x, mix)
+        assert rel_err(res, g["%s_%s_x_residuals" % (name, tag)]) < RTOL
+        for s, spec in enumerate(mix.specimens):
+            assert rel_err(spec.total_intensity, g["%s_%s_x_total_s%d" % (name, tag, s)]) < RTOL
+
+
+@pytest.mark.parametrize("name", ["c1", "c4"])
+def test_optimize_mixture_against_live_reference(calc, golden, name):
+    g = golden(name)
+    for tag, mix in golden_mixtures(name, g)[:2]:
+        r = calc.mixture.get_optimized_residual(mix)
+        want = float(g["%s_%s_opt_residual" % (name, tag)][0])
+        assert r.shape == (1,)
+        assert abs(float(r[0]) - want) <= OPT_RTOL * max(1.0, want), (name, tag, float(r[0]), want)
+        assert mix.optimized and mix.calculated
+        assert abs(np.sum(mix.fractions) - 1.0) < 1e-5
+
+
+def test_population_batch_equals_single_calls(calc, golden):
+    from pyxrd_b200.batched import population_phase_intensities, population_residuals
+    g = golden("c4")
+    mixes = [m for _, m in golden_mixtures("c4", g)]
+    res = population_residuals(mixes)
+    pis = population_phase_intensities(mixes)
+    for k, (tag, mix) in enumerate(golden_mixtures("c4", g)):
+        assert rel_err(res[k], g["c4_%s_residuals" % tag]) < RTOL
+        for s in range(2):
+            assert rel_err(pis[k][s], g["c4_%s_pi_s%d" % (tag, s)]) < RTOL
+
+
+# ---- edge cases the reference handles -------------------------------------------------
+def _oracle_vs_device(calc, mix, tol=RTOL):
+    ref = copy.deepcopy(mix)
+    orc.calculate_mixture(ref)
+    calc.mixture.calculate_mixture(mix)
+    for a, b in zip(mix.specimens, ref.specimens):
+        if a is None:
+            continue
+        assert rel_err(a.phase_intensities, b.phase_intensities) < tol
+        assert rel_err(a.total_intensity, b.total_intensity) < tol
+    assert rel_err(mix.residuals, ref.residuals) < tol
+    return mix, ref
+
+
+def _with_observed(mix, level=50.0):
+    rng = np.random.default_rng(3)
+    for spec in mix.specimens:
+        spec.observed_intensity = rng.uniform(0.5, 1.5, (spec.range_theta.size, 1)) * level
+    return mix
+
+
+def test_none_phase_and_invalid_probabilities_give_zeros(calc):
+    mix = _with_observed(syn.CONFIGS["c4"].truth())
+    mix.specimens[0].phases[0][1] = None
+    mix.specimens[1].phases[0][3].valid_probs = False
+    mix, _ = _oracle_vs_device(calc, mix)
+    assert not mix.specimens[0].phase_intensities[1].any()
+    assert not mix.specimens[1].phase_intensities[3].any()
+
+
+def test_flags_lpf_correction_and_machine_setups(calc):
+    mix = _with_observed(syn.CONFIGS["c4"].truth())
+    mix.specimens[0].phases[0][0].apply_lpf = False
+    mix.specimens[0].phases[0][3].apply_correction = False
+    mix.specimens[0].goniometer = syn.make_goniometer("cu_pair", divergence_mode="AUTOMATIC", absorption=True)
+    mix.specimens[1].goniometer = syn.make_goniometer("single", absorption=True)
+    mix.specimens[1].goniometer.mcr_2theta = 26.6
+    _oracle_vs_device(calc, mix)
+
+
+def test_ragged_specimens_and_exclusions(calc):
+    cfg = syn.CONFIGS["c4"]
+    mix = cfg.truth()
+    th = syn.theta_grid(4.0, 30.0, 0.05)
+    old = mix.specimens[1]
+    mix.specimens[1] = syn.make_specimen(th, old.phases[0], old.goniometer, exclusion=(10.0, 12.5))
+    _with_observed(mix)
+    mix, ref = _oracle_vs_device(calc, mix)
+    assert mix.specimens[1].phase_intensities.shape == (6, 1, th.size)
+
+
+def test_no_observations_and_empty_mixture(calc):
+    mix = syn.CONFIGS["c1"].truth()
+    mix.specimens[0].observed_intensity = np.array([], dtype=float)
+    calc.mixture.calculate_mixture(mix)
+    assert mix.residuals == [0.0, 0.0]
+    empty = syn.make_mixture([], 0)
+    out = calc.mixture.calculate_mixture(empty)           # AssertionError swallowed (mixture.py:229-236)
+    assert out is empty and not empty.calculated
+    assert calc.mixture.optimize_mixture(empty) is empty and not empty.optimized
+
+
+def test_generic_rank_and_csds_quirks(calc):
+    types = syn.atom_types()
+    rng = np.random.default_rng(11)
+    theta = syn.theta_grid(3.0, 20.0, 0.05)
+    phases = []
+    # rank 25 (G=5, R2): generic kernel; rank 16 (G=4, R2) and (G=2, R4): staged kernels; rank 6 R1
+    for G, R in ((5, 2), (4, 2), (2, 4), (6, 1), (3, 2)):
+        comps = [syn.make_component(types, k, rng) for k in
+                 (["illite", "smectite_ad", "chlorite", "smectite_eg", "kaolinite", "illite"][:G])]
+        W, P = syn.make_probabilities(rng, G, R)
+        phases.append(syn.make_phase(comps, W, P, syn.make_csds(6.0 + G), sigma_star=4.0))
+    phases[1].CSDS.minimum = 3                      # n < minimum terms vanish
+    phases[2].CSDS = syn.make_csds(1.2, maximum=1)  # empty series: S = mean * Id
+    phases[3].CSDS.minimum = 0                      # python wrap-around Qn[-1] = Q^(N+1)
+    spec = syn.make_specimen(theta, phases, syn.make_goniometer("cu_pair"))
+    mix = _with_observed(syn.make_mixture([spec], len(phases)))
+    _oracle_vs_device(calc, mix)
+
+
+def test_single_phase_helpers(calc):
+    mix = syn.CONFIGS["c2"].truth()
+    spec = mix.specimens[0]
+    phase = spec.phases[0][0]
+    theta = spec.range_theta[::7]
+    stl = 2 * np.sin(theta) / spec.goniometer.wavelength
+    assert rel_err(calc.phases.get_diffracted_intensity(theta, stl, phase),
+                   orc.get_diffracted_intensity(theta, stl, phase)) < RTOL
+    assert rel_err(calc.phases.get_intensity(theta, stl, 2.3, 2.3, 0.0, phase),
+                   orc.get_intensity(theta, stl, 2.3, 2.3, 0.0, phase)) < RTOL
+    corr, pi = calc.specimen.calculate_phase_intensities(spec)
+    corr_o, pi_o = orc.calculate_phase_intensities(spec)
+    assert rel_err(corr, corr_o) < 1e-14 and rel_err(pi, pi_o) < RTOL
+    assert rel_err(calc.specimen.get_machine_correction_range(spec), corr_o) < 1e-14
+    spec.correction, spec.phase_intensities = corr_o, pi_o
+    ref = copy.deepcopy(spec)
+    calc.specimen.calculate_scaled_intensities(spec, 2.5, np.array([0.7]), 3.0)
+    orc.calculate_scaled_intensities(ref, 2.5, np.array([0.7]), 3.0)
+    assert rel_err(spec.total_intensity, ref.total_intensity) < 1e-14
+    assert rel_err(spec.scaled_phase_intensities, ref.scaled_phase_intensities) < 1e-14
+    assert rel_err(spec.background_intensity, ref.background_intensity) < 1e-14
+
+
+# ---- size-independent properties at full BASELINE sizes -----------------------------------
+def test_properties_full_size(calc):
+    from pyxrd_b200.batched import population_phase_intensities, population_residuals
+    cfg = syn.CONFIGS["c2"]
+    mixes = cfg.population(SEED, 64)
+    for m in mixes:
+        _with_observed(m)
+    pis = population_phase_intensities(mixes)
+    again = population_phase_intensities(mixes[::-1])[::-1]
+    for a, b in zip(pis, again):                      # order independence, bit for bit
+        assert np.array_equal(a[0], b[0])
+    assert all(np.isfinite(p[0]).all() and (p[0] > 0).all() for p in pis)
+    # Rp is homogeneous of degree 0 under a joint rescale of observed and (scale, bgshift)
+    r1 = population_residuals(mixes)
+    for m in mixes:
+        m.specimens[0].observed_intensity = m.specimens[0].observed_intensity * 4.0
+        m.scales = np.asarray(m.scales) * 4.0
+        m.bgshifts = np.asarray(m.bgshifts) * 4.0
+    r2 = population_residuals(mixes)
+    assert rel_err(r2, r1) < 1e-12
+    # a wavelength distribution equal to the single tube wavelength doubles the pattern
+    # (sequential in-place accumulation, specimen.py:71-74) except where the shifted axis
+    # rounds outside the range at the two end points
+    one = syn.CONFIGS["c1"].truth()
+    _with_observed(one)
+    base = population_phase_intensities([one])[0][0]
+    one.specimens[0].goniometer.wavelength_distribution = []
+    bare = population_phase_intensities([one])[0][0]
+    assert rel_err(base[0, 0, 1:-1], 2.0 * bare[0, 0, 1:-1]) < 1e-9
