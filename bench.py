@@ -69,10 +69,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -81,10 +81,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]

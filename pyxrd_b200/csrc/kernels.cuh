@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, Batc
     const int G = pi[0], R = pi[1], REPS = R / G;
     double *sP = reinterpret_cast<double *>(smem_raw + sizeof(PhaseSmem));    // [R][R]
     double *sWG = sP + R * R;                                                // [G][R]
-    double2 *vy = reinterpret_cast<double2 *>(sWG + G * R + (G * R & 1));    // [R][TPB] y
+    double2 *vy = reinterpret_cast<double2 *>(sWG + G * R + ((R * R + G * R) & 1));   // [R][TPB] y, 16-byte aligned
     double2 *vw = vy + R * PX_GEN_TPB;                                       // [R][TPB] w
     double2 *vu = vw + R * PX_GEN_TPB;                                       // [G][TPB] u
     double2 *vp = vu + 8 * PX_GEN_TPB;                                       // [G][TPB] phi

@@ -143,7 +143,7 @@ size_t staged_smem(int R, int G, int ntop_cap) {
            sizeof(double2) * (size_t)R * PX_TPB + sizeof(double) * (size_t)(ntop_cap + 2);
 }
 size_t generic_smem(int R, int G, int ntop_cap) {
-    return sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + (G * R & 1)) +
+    return sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + 1) +
            sizeof(double2) * (size_t)(2 * R + 16) * PX_GEN_TPB + sizeof(double) * (size_t)(ntop_cap + 2);
 }
 

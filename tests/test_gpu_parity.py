@@ -175,7 +175,7 @@ def test_no_observations_and_empty_mixture(calc):
     mix.specimens[0].observed_intensity = np.array([], dtype=float)
     calc.mixture.calculate_mixture(mix)
     assert mix.residuals == [0.0, 0.0]
-    empty = syn.make_mixture([], 0)
+    empty = syn.make_mixture([], 0, fractions=[])
     out = calc.mixture.calculate_mixture(empty)           # AssertionError swallowed (mixture.py:229-236)
     assert out is empty and not empty.calculated
     assert calc.mixture.optimize_mixture(empty) is empty and not empty.optimized
