@@ -26,6 +26,49 @@
 #define PX_SQRT2PI 2.5066282746310002      // math.sqrt(2 * pi)
 #define PX_SQRT8 2.8284271247461903        // math.sqrt(8)
 
+// sin/cos coefficients live in constant memory so that ptxas keeps them in (uniform) registers
+// across the atom loop instead of re-materialising every 64-bit immediate with two UMOVs
+// (measured: 25 % of all issued instructions of the first version of k_phase_small).
+__constant__ double PX_SC[19] = {
+    0.63661977236758138,        // 2/pi
+    6755399441055744.0,         // 1.5 * 2^52: round-to-nearest-integer magic
+    -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33,    // -pi/2 in three parts
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,    // sin minimax, |r| <= pi/4
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,   // cos minimax
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+    -0.5, 1.0};
+
+// sin and cos of a (|a| < 2^30 * pi/2): Cody-Waite reduction with FMAs, 13/14-degree minimax
+// polynomials; max error 1.6 ulp / 1.8e-16 absolute (checked against long-double libm on 2e7 points).
+__device__ __forceinline__ void px_sincos(double a, double &s, double &c) {
+    const double t = fma(a, PX_SC[0], PX_SC[1]);
+    const double q = t - PX_SC[1];
+    const int n = __double2loint(t);
+    double r = fma(q, PX_SC[2], a);
+    r = fma(q, PX_SC[3], r);
+    r = fma(q, PX_SC[4], r);
+    const double r2 = r * r;
+    double ps = PX_SC[5];
+    ps = fma(ps, r2, PX_SC[6]);
+    ps = fma(ps, r2, PX_SC[7]);
+    ps = fma(ps, r2, PX_SC[8]);
+    ps = fma(ps, r2, PX_SC[9]);
+    ps = fma(ps, r2, PX_SC[10]);
+    const double sn = fma(r * r2, ps, r);
+    double pc = PX_SC[11];
+    pc = fma(pc, r2, PX_SC[12]);
+    pc = fma(pc, r2, PX_SC[13]);
+    pc = fma(pc, r2, PX_SC[14]);
+    pc = fma(pc, r2, PX_SC[15]);
+    pc = fma(pc, r2, PX_SC[16]);
+    const double cs = fma(r2 * r2, pc, fma(r2, PX_SC[17], PX_SC[18]));
+    const double S = (n & 1) ? cs : sn, C = (n & 1) ? sn : cs;
+    // quadrant signs by flipping the sign bit of the high word
+    s = __hiloint2double(__double2hiint(S) ^ ((n & 2) << 30), __double2loint(S));
+    c = __hiloint2double(__double2hiint(C) ^ (((n + 1) & 2) << 30), __double2loint(C));
+}
+
 struct StaticDev {
     int S, T, Z, maxX;
     long long sumX;
@@ -57,7 +100,9 @@ struct BatchDev {
     const int *comp_i;               // [NC][4]
     const double *atom_d;            // [NA][2]
     const int *atom_type;            // [NA]
-    double *atom_z;                  // [NA]   derived
+    double *atom_z;                  // [NA]   derived: stretched z
+    int *atom_plane;                 // [NA]   derived: plane index within the component (runs of equal z)
+    int *comp_nplanes;               // [NC]   derived
     double *phase_x;                 // [NP][4] derived: mean, abs_scale, ntop
     double *coef;                    // [NP][ncap] derived, index = power of Q
     const int *job_pb, *job_spec;    // [NJ]
@@ -235,10 +280,17 @@ __global__ void k_component_z(BatchDev bt) {
     const int *cc = bt.comp_i + ci * 4;
     const double lattice_d = cd[3];
     const double zf = __ddiv_rn(cd[0] - lattice_d, cd[1] - lattice_d);   // components.py:36
+    int plane = -1;
+    double prev = 0.0;
     for (int a = 0; a < cc[1] + cc[2]; ++a) {
         const double z0 = bt.atom_d[(cc[0] + a) * 2 + 1];
-        bt.atom_z[cc[0] + a] = (a < cc[1]) ? z0 : __dadd_rn(lattice_d, __dmul_rn(zf, z0 - lattice_d));
+        const double z = (a < cc[1]) ? z0 : __dadd_rn(lattice_d, __dmul_rn(zf, z0 - lattice_d));
+        bt.atom_z[cc[0] + a] = z;
+        if (a == 0 || z != prev) ++plane;       // consecutive atoms at one z share a plane
+        bt.atom_plane[cc[0] + a] = plane;
+        prev = z;
     }
+    bt.comp_nplanes[ci] = plane + 1;
 }
 
 __global__ void k_leaf_csds(const double *pd, int nmin, int nmax, double *arr, double *mean, double *cpow) {
@@ -254,13 +306,14 @@ __global__ void k_leaf_csds(const double *pd, int nmin, int nmax, double *arr, d
 #define PX_MAX_ATOMS 256     // atoms per phase (all components)
 
 struct PhaseSmem {          // header living at the start of dynamic shared memory
-    int comp_first[8];      // first atom (local index) of component c
-    int comp_count[8];
+    int comp_first[8];      // first plane (local index) of component c
+    int comp_count[8];      // number of planes of component c
     double comp_d001[8];
     double comp_delta[8];
-    double atom_arg[PX_MAX_ATOMS];   // (2 pi) * z
-    double atom_pn[PX_MAX_ATOMS];
-    int atom_type[PX_MAX_ATOMS];
+    double plane_arg[PX_MAX_ATOMS];  // (2 pi) * z of a plane = run of consecutive atoms with equal z
+    int plane_end[PX_MAX_ATOMS];     // one past the last atom (local index) of the plane
+    double2 atom_po[PX_MAX_ATOMS];   // .x = pn (0 for a None atom type), .y = bit pattern of the ASF-table offset type * sumX
+    int n_atoms, pad[3];
 };
 
 // Lorentz-polarisation factor for one point (goniometer.py:20-34)
@@ -283,39 +336,41 @@ __global__ void k_leaf_lpf(const double *theta, long long n, double sigma_star, 
     out[i] = lpf_value(sin(th), __dmul_rn(c2, c2), sigma_star, Ss, __dmul_rn(Ss, Ss), __dmul_rn(c, c));
 }
 
-// cooperative load of the component / atom lists of phase `pb` into shared memory
-__device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int G, PhaseSmem *ps) {
+// cooperative load of the component / atom lists of phase `pb` into shared memory.  Atoms of a
+// component that sit at the same z (several species on one crystallographic plane) share one
+// complex exponential: sum_a asf_a pn_a exp(i arg) = (sum_a asf_a pn_a) exp(i arg).
+__device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int G, PhaseSmem *ps, long long sumX) {
     const int *pi = bt.phase_i + pb * 8;
-    if (threadIdx.x == 0) {
-        int first = 0;
-        for (int c = 0; c < G; ++c) {
-            const int ci = bt.phase_comp[pi[5] + c];
-            const int *cc = bt.comp_i + ci * 4;
-            ps->comp_first[c] = first;
-            ps->comp_count[c] = cc[1] + cc[2];
-            ps->comp_d001[c] = bt.comp_d[ci * 8 + 0];
-            ps->comp_delta[c] = bt.comp_d[ci * 8 + 2];
-            first += cc[1] + cc[2];
-        }
-    }
-    __syncthreads();
+    int first_atom = 0, first_plane = 0;
     for (int c = 0; c < G; ++c) {
         const int ci = bt.phase_comp[pi[5] + c];
-        const int a0 = bt.comp_i[ci * 4];
-        for (int a = threadIdx.x; a < ps->comp_count[c]; a += blockDim.x) {
-            const int l = ps->comp_first[c] + a;
-            ps->atom_arg[l] = __dmul_rn(PX_TWO_PI, bt.atom_z[a0 + a]);    // 2 * pi * atom.z
-            ps->atom_pn[l] = bt.atom_d[(a0 + a) * 2];
-            ps->atom_type[l] = bt.atom_type[a0 + a];
+        const int a0 = bt.comp_i[ci * 4], na = bt.comp_i[ci * 4 + 1] + bt.comp_i[ci * 4 + 2];
+        const int np = bt.comp_nplanes[ci];
+        if (threadIdx.x == 0) {
+            ps->comp_first[c] = first_plane;
+            ps->comp_count[c] = np;
+            ps->comp_d001[c] = bt.comp_d[ci * 8 + 0];
+            ps->comp_delta[c] = bt.comp_d[ci * 8 + 2];
         }
+        for (int a = threadIdx.x; a < na; a += blockDim.x) {
+            const int l = first_atom + a;
+            const int pl = bt.atom_plane[a0 + a];
+            const int t = bt.atom_type[a0 + a];         // None atom type -> contributes 0 (atoms.py:65-67)
+            ps->atom_po[l] = make_double2(t >= 0 ? bt.atom_d[(a0 + a) * 2] : 0.0, __longlong_as_double(t >= 0 ? t * sumX : 0LL));
+            if (a == 0 || bt.atom_plane[a0 + a - 1] != pl)
+                ps->plane_arg[first_plane + pl] = __dmul_rn(PX_TWO_PI, bt.atom_z[a0 + a]);     // 2 * pi * atom.z
+            if (a == na - 1 || bt.atom_plane[a0 + a + 1] != pl) ps->plane_end[first_plane + pl] = l + 1;
+        }
+        first_atom += na;
+        first_plane += np;
     }
+    if (threadIdx.x == 0) ps->n_atoms = first_atom;
 }
 
-// one atom: (asf * pn) * exp(i * ((2 pi z) * stl))     (atoms.py:64)
-__device__ __forceinline__ void atom_term(double asf, double pn, double arg2piz, double stl, double &sr, double &si) {
-    const double f = __dmul_rn(asf, pn);
+// one plane: f * exp(i * ((2 pi z) * stl)), f = sum of asf * pn over its atoms     (atoms.py:64)
+__device__ __forceinline__ void plane_term(double f, double arg2piz, double stl, double &sr, double &si) {
     double sn, cs;
-    sincos(__dmul_rn(arg2piz, stl), &sn, &cs);
+    px_sincos(__dmul_rn(arg2piz, stl), sn, cs);
     sr = fma(f, cs, sr);
     si = fma(f, sn, si);
 }
@@ -323,12 +378,16 @@ __device__ __forceinline__ void atom_term(double asf, double pn, double arg2piz,
 // phi = exp(2 pi stl (i d001 - pi delta_c stl))      (components.py:53)
 __device__ __forceinline__ void phase_factor(double stl, double d001, double delta_c, double &pr, double &pi_) {
     const double A = __dmul_rn(PX_TWO_PI, stl);
-    const double re = __dmul_rn(A, -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl));
     double sn, cs;
-    sincos(__dmul_rn(A, d001), &sn, &cs);
-    const double e = exp(re);
-    pr = e * cs;
-    pi_ = e * sn;
+    px_sincos(__dmul_rn(A, d001), sn, cs);
+    if (delta_c != 0.0) {                                   // block-uniform branch
+        const double e = exp(__dmul_rn(A, -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl)));
+        pr = e * cs;
+        pi_ = e * sn;
+    } else {                                                // exp(-0.0) == 1 exactly
+        pr = cs;
+        pi_ = sn;
+    }
 }
 
 // structure factor SF_c and phase factor phi_c of component c at one point
@@ -336,11 +395,16 @@ __device__ __forceinline__ void phase_factor(double stl, double d001, double del
 __device__ __forceinline__ void component_factors(const PhaseSmem *ps, int c, double stl, const double *__restrict__ asf_col,
                                                   long long sumX, double &ur, double &ui, double &pr, double &pi_) {
     double sr = 0.0, si = 0.0;
-    const int a0 = ps->comp_first[c], a1 = a0 + ps->comp_count[c];
-    for (int a = a0; a < a1; ++a) {
-        const int t = ps->atom_type[a];
-        if (t < 0) continue;                                  // None atom type -> zeros (atoms.py:65-67)
-        atom_term(__ldg(asf_col + (long long)t * sumX), ps->atom_pn[a], ps->atom_arg[a], stl, sr, si);
+    const int p0 = ps->comp_first[c], p1 = p0 + ps->comp_count[c];
+    int a = (p0 == 0) ? 0 : ps->plane_end[p0 - 1];
+    for (int p = p0; p < p1; ++p) {
+        const int end = ps->plane_end[p];
+        double f = 0.0;
+        for (; a < end; ++a) {
+            const double2 po = ps->atom_po[a];
+            f = fma(__ldg(asf_col + __double_as_longlong(po.y)), po.x, f);
+        }
+        plane_term(f, ps->plane_arg[p], stl, sr, si);
     }
     ur = sr;
     ui = si;
@@ -381,7 +445,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_small(StaticDev st, BatchDev b
     const int flags = pi[4];
     const double sigma_star = bt.phase_d[pb * 8];
 
-    load_phase_lists(bt, pb, G, ps);
+    load_phase_lists(bt, pb, G, ps, st.sumX);
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
@@ -477,7 +541,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev 
     const int flags = pi[4];
     const double sigma_star = bt.phase_d[pb * 8];
 
-    load_phase_lists(bt, pb, G, ps);
+    load_phase_lists(bt, pb, G, ps, st.sumX);
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
@@ -509,16 +573,16 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev 
         gr[c] = pr[c] * ur[c] + pim[c] * ui[c];
         gi[c] = pim[c] * ur[c] - pr[c] * ui[c];
     }
+    // w = phi o (y + c_n b) = phi o y + c_n g; for the first step y = 0
     double wr[R], wi[R];
     {
         const double cn = (ntop >= 1) ? sCoef[ntop] : 0.0;
 #pragma unroll
         for (int J = 0; J < R; ++J) { wr[J] = cn * gr[J / REPS]; wi[J] = cn * gi[J / REPS]; }
     }
-    double tr = 0.0;
     double2 *mine = stage + threadIdx.x;
     for (int n = ntop; n >= 1; --n) {
-        const double cnext = (n > 1) ? sCoef[n - 1] : 0.0;
+        // y = P w, four rows at a time; P[4 ib + q][J] comes as two broadcast LDS.128 per J
         for (int ib = 0; ib < RB; ++ib) {
             const double4 *prow = reinterpret_cast<const double4 *>(sPb + ib * R * 4);
             double a0r = 0, a0i = 0, a1r = 0, a1i = 0, a2r = 0, a2i = 0, a3r = 0, a3i = 0;
@@ -530,51 +594,42 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev 
                 a2r = fma(p.z, wr[J], a2r); a2i = fma(p.z, wi[J], a2i);
                 a3r = fma(p.w, wr[J], a3r); a3i = fma(p.w, wi[J], a3i);
             }
-            const double yr4[4] = {a0r, a1r, a2r, a3r}, yi4[4] = {a0i, a1i, a2i, a3i};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int I = ib * 4 + q;
-                if (I < R) {
-                    const int c = I / REPS;
-                    double prc = pr[0], pic = pim[0], grc = gr[0], gic = gi[0], urc = ur[0], uic = ui[0];
-#pragma unroll
-                    for (int cc = 1; cc < G; ++cc)
-                        if (c == cc) { prc = pr[cc]; pic = pim[cc]; grc = gr[cc]; gic = gi[cc]; urc = ur[cc]; uic = ui[cc]; }
-                    if (n > 1) {
-                        double2 v;
-                        v.x = fma(prc, yr4[q], fma(-pic, yi4[q], cnext * grc));
-                        v.y = fma(prc, yi4[q], fma(pic, yr4[q], cnext * gic));
-                        mine[I * PX_TPB] = v;
-                    } else {
-                        double ar = 0.0, ai = 0.0;
-#pragma unroll
-                        for (int cc = 0; cc < G; ++cc) {
-                            const double w = sWG[cc * R + I];
-                            ar = fma(ur[cc], w, ar);
-                            ai = fma(ui[cc], w, ai);
-                        }
-                        const double sr = fma(mean, urc, yr4[q]);
-                        const double si = fma(-mean, uic, yi4[q]);
-                        tr += ar * sr - ai * si;
-                    }
-                }
-            }
+            const int I = ib * 4;
+            mine[I * PX_TPB] = make_double2(a0r, a0i);
+            if (I + 1 < R) mine[(I + 1) * PX_TPB] = make_double2(a1r, a1i);
+            if (I + 2 < R) mine[(I + 2) * PX_TPB] = make_double2(a2r, a2i);
+            if (I + 3 < R) mine[(I + 3) * PX_TPB] = make_double2(a3r, a3i);
         }
         if (n > 1) {
+            // next w: the component of column J is a compile-time constant here, so phi / g need no selects
+            const double cn = sCoef[n - 1];
+            double cgr[G], cgi[G];
 #pragma unroll
-            for (int J = 0; J < R; ++J) { const double2 v = mine[J * PX_TPB]; wr[J] = v.x; wi[J] = v.y; }
+            for (int c = 0; c < G; ++c) { cgr[c] = cn * gr[c]; cgi[c] = cn * gi[c]; }
+#pragma unroll
+            for (int J = 0; J < R; ++J) {
+                const double2 y = mine[J * PX_TPB];
+                wr[J] = fma(pr[J / REPS], y.x, fma(-pim[J / REPS], y.y, cgr[J / REPS]));
+                wi[J] = fma(pr[J / REPS], y.y, fma(pim[J / REPS], y.x, cgi[J / REPS]));
+            }
         }
     }
-    if (ntop < 1) {      // empty series: S = mean * Id
+    // Re( sum_K a_K (mean b_K + y_K) ), a_K = sum_c u_c WG[c][K], b_K = conj(u_comp(K))
+    double tr = 0.0;
 #pragma unroll
-        for (int K = 0; K < R; ++K) {
-            const int c = K / REPS;
-            double ar = 0.0, ai = 0.0;
-            for (int cc = 0; cc < G; ++cc) { const double w = sWG[cc * R + K]; ar = fma(ur[cc], w, ar); ai = fma(ui[cc], w, ai); }
-            double urc = ur[0], uic = ui[0];
-            for (int cc = 1; cc < G; ++cc) if (c == cc) { urc = ur[cc]; uic = ui[cc]; }
-            tr += ar * (mean * urc) - ai * (-mean * uic);
+    for (int K = 0; K < R; ++K) {
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+            const double w = sWG[c * R + K];
+            ar = fma(ur[c], w, ar);
+            ai = fma(ui[c], w, ai);
         }
+        double2 y = make_double2(0.0, 0.0);
+        if (ntop >= 1) y = mine[K * PX_TPB];
+        const double sr = fma(mean, ur[K / REPS], y.x);
+        const double si = fma(-mean, ui[K / REPS], y.y);
+        tr += ar * sr - ai * si;
     }
     bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, sigma_star, st, s, gx);
 }
@@ -603,7 +658,7 @@ __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, Batc
     const int flags = pi[4];
     const double sigma_star = bt.phase_d[pb * 8];
 
-    load_phase_lists(bt, pb, G, ps);
+    load_phase_lists(bt, pb, G, ps, st.sumX);
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
@@ -683,7 +738,7 @@ __global__ void k_leaf_component(const double *stl, long long n, const double *c
         const double z = (a < n_layer) ? z0 : __dadd_rn(lattice_d, __dmul_rn(zf, z0 - lattice_d));
         if (i == 0) z_out[a] = z;
         if (!has_type[a]) continue;
-        atom_term(asf_value(atype_rows + a * 12, s), atom_d[a * 2], __dmul_rn(PX_TWO_PI, z), x, sr, si);
+        plane_term(__dmul_rn(asf_value(atype_rows + a * 12, s), atom_d[a * 2]), __dmul_rn(PX_TWO_PI, z), x, sr, si);
     }
     sf[i] = make_double2(sr, si);
     double pr, pi_;

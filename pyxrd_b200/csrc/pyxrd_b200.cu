@@ -91,7 +91,7 @@ struct pyxrd_ctx {
     DevBuf d_blob;           // all uploaded batch arrays, one allocation
     PinBuf h_blob;
     const int *jobids_dev = nullptr;   // inside d_blob
-    DevBuf d_atom_z, d_phase_x, d_coef, d_int, d_scaled, d_tot, d_res, d_scratch;
+    DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_coef, d_int, d_scaled, d_tot, d_res, d_scratch;
     PinBuf h_res;
     DevBuf d_leaf_a, d_leaf_b, d_leaf_c;
     int64_t int_count = 0, tot_count = 0;
@@ -232,7 +232,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_stl,
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob,
-                      &ctx->d_atom_z, &ctx->d_phase_x, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
+                      &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
                       &ctx->d_res, &ctx->d_scratch, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
@@ -458,6 +458,8 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     auto dev = [&](size_t idx) { return static_cast<char *>(ctx->d_blob.ptr) + parts[idx].off; };
 
     CK(ctx->d_atom_z.ensure(sizeof(double) * std::max(NA, 1)));
+    CK(ctx->d_atom_plane.ensure(sizeof(int) * std::max(NA, 1)));
+    CK(ctx->d_comp_np.ensure(sizeof(int) * std::max(NC, 1)));
     CK(ctx->d_phase_x.ensure(sizeof(double) * 4 * std::max(NP, 1)));
     CK(ctx->d_coef.ensure(sizeof(double) * (size_t)ncap * std::max(NP, 1)));
     ctx->int_count = (int64_t)K * cand_stride;
@@ -479,6 +481,8 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     bt.atom_d = reinterpret_cast<const double *>(dev(i_atom_d));
     bt.atom_type = reinterpret_cast<const int *>(dev(i_atom_t));
     bt.atom_z = ctx->d_atom_z.as<double>();
+    bt.atom_plane = ctx->d_atom_plane.as<int>();
+    bt.comp_nplanes = ctx->d_comp_np.as<int>();
     bt.phase_x = ctx->d_phase_x.as<double>();
     bt.coef = ctx->d_coef.as<double>();
     bt.job_pb = reinterpret_cast<const int *>(dev(i_job_pb));

@@ -288,8 +288,12 @@ class BatchPack(object):
             if cid is None:
                 cid = len(comp_d)
                 comp_ids[id(comp)] = cid
-                layer = list(comp.layer_atoms)
-                inter = list(comp.interlayer_atoms)
+                # atoms of one group that share a z are made adjacent: the kernels evaluate one
+                # complex exponential per run of equal z (layer atoms stay in front, the z-stretch
+                # applies to the interlayer group only, components.py:40-45)
+                zkey = lambda atom: float(atom.default_z) if atom is not None else 0.0  # noqa: E731
+                layer = sorted(comp.layer_atoms, key=zkey)
+                inter = sorted(comp.interlayer_atoms, key=zkey)
                 comp_d.append([float(comp.d001), float(comp.default_c), float(comp.delta_c), float(comp.lattice_d),
                                float(comp.volume), float(comp.weight), 0.0, 0.0])
                 comp_i.append([len(atom_t), len(layer), len(inter), 0])
