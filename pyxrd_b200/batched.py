@@ -52,3 +52,11 @@ def population_phase_intensities(mixtures: Sequence, ctx: Optional[Context] = No
         ctx.set_batch(batch)
         ctx.compute_intensities()
         return ctx.split_per_specimen(ctx.read_intensities_flat(), (batch.M, static.Z))
+
+
+def get_optimized_residuals(mixtures: Sequence, ctx: Optional[Context] = None):
+    """``[get_optimized_residual(m) for m in mixtures]`` (mixture.py:268-276) for a population:
+    every mixture is optimised (fractions / scales / background) and left in the same state
+    the per-trial callback would leave it in; returns the list of 1-element residual arrays."""
+    from .calculations import mixture as cm
+    return [cm.get_optimized_residual(m) for m in mixtures]

@@ -1,0 +1,59 @@
+"""Population sharding over the GPUs of one box.
+
+Trials are independent (the reference treats them as independent Pool tasks,
+refinement/async_evaluatable.py:38-50), so the candidate axis is block-partitioned
+over the ranks with no data-path collective; the only exchange is one all-gather of
+the per-candidate residual rows f64[K_rank, 1+S] (NCCL over NVLink on GPUs, gloo in
+the CPU tests).  A single pattern / trial is never split across GPUs.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_bounds(n_items: int, world_size: int) -> List[Tuple[int, int]]:
+    """[lo, hi) of every rank: ceil(K / ws) candidates per rank, the tail ranks may be short/empty"""
+    per = -(-int(n_items) // int(world_size)) if n_items > 0 else 0
+    return [(min(r * per, n_items), min((r + 1) * per, n_items)) for r in range(world_size)]
+
+
+def shard(items: Sequence, rank: int, world_size: int):
+    lo, hi = shard_bounds(len(items), world_size)[rank]
+    return items[lo:hi]
+
+
+def gather_rows(local, n_total: int, world_size: int, group=None):
+    """All-gather row blocks of unequal length: ``local`` is a torch tensor [k_rank, C] on the
+    device the process group communicates on; returns [n_total, C] on every rank."""
+    import torch
+    import torch.distributed as dist
+    per = -(-int(n_total) // int(world_size)) if n_total > 0 else 0
+    cols = local.shape[1]
+    padded = torch.zeros((per, cols), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty((world_size * per, cols), dtype=local.dtype, device=local.device)
+    if world_size > 1:
+        dist.all_gather_into_tensor(out, padded, group=group)
+    else:
+        out.copy_(padded)
+    return out[:n_total]
+
+
+def evaluate_population_sharded(mixtures: Sequence, evaluate, device=None, group=None) -> np.ndarray:
+    """Each rank evaluates its block of the population with ``evaluate(list) -> f64[k, 1+S]``
+    (on the GPU path: ``pyxrd_b200.batched.population_residuals``) and all ranks receive the full
+    [K, 1+S] table, bit-identical to a single-rank evaluation of the same candidates."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = shard(mixtures, rank, world)
+    n_spec = len(mixtures[0].specimens)
+    res = np.asarray(evaluate(mine), dtype=np.float64).reshape(len(mine), 1 + n_spec) if len(mine) else \
+        np.zeros((0, 1 + n_spec))
+    t = torch.from_numpy(np.ascontiguousarray(res))
+    if device is not None:
+        t = t.to(device)
+    return gather_rows(t, len(mixtures), world, group).cpu().numpy()

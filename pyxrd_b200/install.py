@@ -1,0 +1,88 @@
+"""Make a running PyXRD use the device path: rebind the hot-path functions of
+``pyxrd.calculations.*`` -- and the names that PyXRD's model / refinement layers imported
+from them -- to the ``pyxrd_b200.calculations`` implementations.
+
+    import pyxrd_b200.install as b200
+    b200.install()            # before or after PyXRD's modules were imported
+    b200.uninstall()          # restore the reference functions
+
+The reference has no plugin registry for this path: callers do ``from
+pyxrd.calculations.mixture import get_optimized_residual`` etc., so both the defining module
+and every importing module's global have to be rebound.  The import sites are the ones listed
+in SURVEY.md §8(b).
+"""
+import importlib
+import sys
+
+# module of the reference -> {function name: our module}
+_TARGETS = {
+    "pyxrd.calculations.atoms": ("atoms", ["get_atomic_scattering_factor", "get_structure_factor"]),
+    "pyxrd.calculations.components": ("components", ["get_factors"]),
+    "pyxrd.calculations.CSDS": ("CSDS", ["calculate_distribution"]),
+    "pyxrd.calculations.goniometer": ("goniometer", ["get_lorentz_polarisation_factor",
+                                                     "get_fixed_to_ads_correction_range"]),
+    "pyxrd.calculations.phases": ("phases", ["get_diffracted_intensity", "get_intensity"]),
+    "pyxrd.calculations.specimen": ("specimen", ["get_machine_correction_range", "calculate_phase_intensities",
+                                                 "calculate_scaled_intensities"]),
+    "pyxrd.calculations.mixture": ("mixture", ["parse_mixture", "calculate_mixture", "optimize_mixture",
+                                               "calculate_and_optimize_mixture", "get_residual",
+                                               "get_optimized_residual", "_get_residuals"]),
+}
+
+# modules that did ``from pyxrd.calculations.X import name`` (reference path:line in SURVEY.md §8(b))
+_IMPORT_SITES = [
+    "pyxrd.mixture.models.optimizers",        # optimizers.py:10-15
+    "pyxrd.refinement.refine_method",         # refine_method.py:14
+    "pyxrd.phases.models.abstract_phase",     # abstract_phase.py:19
+    "pyxrd.phases.models.component",          # component.py:22
+    "pyxrd.atoms.models",                     # models.py:17
+    "pyxrd.phases.models.CSDS",               # CSDS.py:10
+    "pyxrd.goniometer.models",                # models.py:26-31
+    "pyxrd.calculations.specimen",            # specimen.py:12-13 (imports from phases / goniometer)
+    "pyxrd.calculations.phases",              # phases.py:15-18
+    "pyxrd.calculations.components",          # components.py:13
+    "pyxrd.calculations.mixture",             # mixture.py:18
+]
+
+_saved = []
+
+
+def install(import_reference=True):
+    """Rebind; returns the list of (module, name) pairs that were replaced."""
+    import pyxrd_b200.calculations as ours
+    if _saved:
+        return [(m.__name__, n) for m, n, _ in _saved]
+    replaced = {}
+    for ref_name, (our_name, names) in _TARGETS.items():
+        mod = sys.modules.get(ref_name)
+        if mod is None and import_reference:
+            try:
+                mod = importlib.import_module(ref_name)
+            except Exception:
+                mod = None
+        if mod is None:
+            continue
+        our_mod = getattr(ours, our_name)
+        for name in names:
+            if hasattr(mod, name) and hasattr(our_mod, name):
+                old = getattr(mod, name)
+                new = getattr(our_mod, name)
+                _saved.append((mod, name, old))
+                setattr(mod, name, new)
+                replaced[id(old)] = new
+    for site in _IMPORT_SITES:
+        mod = sys.modules.get(site)
+        if mod is None:
+            continue
+        for name, value in list(vars(mod).items()):
+            new = replaced.get(id(value))
+            if new is not None and value is not new:
+                _saved.append((mod, name, value))
+                setattr(mod, name, new)
+    return [(m.__name__, n) for m, n, _ in _saved]
+
+
+def uninstall():
+    while _saved:
+        mod, name, old = _saved.pop()
+        setattr(mod, name, old)
