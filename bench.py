@@ -108,8 +108,11 @@ def build_population(name, count, rank, ctx_calc):
 
 
 # ---------------------------------------------------------------------------------------
-def time_workload(name, count, args, rank, world, torch, dist, ctx, stream, flush):
-    """-> dict with resident-in-HBM and end-to-end timings of one workload on this rank"""
+def time_workload(name, count, args, rank, world, torch, dist, ctx, stream, flush, optimise=False):
+    """-> dict with resident-in-HBM and end-to-end timings of one workload on this rank.
+    optimise=False: a step = all phase patterns + residuals at the candidates' solutions;
+    optimise=True:  a step = a refinement trial per candidate: all phase patterns + the mixture
+    optimiser (get_optimized_residual semantics)"""
     import pyxrd_b200.calculations as calc
     from pyxrd_b200.batched import pack_population
     cfg, mixes = build_population(name, count, rank, calc)
@@ -136,7 +139,10 @@ def time_workload(name, count, args, rank, world, torch, dist, ctx, stream, flus
         # ---- resident: parameters already in HBM ------------------------------------------
         def step_resident():
             ctx.compute_intensities()
-            ctx.compute_residuals(False)
+            if optimise:
+                ctx.optimize(refine_bg=True)
+            else:
+                ctx.compute_residuals(False)
 
         for _ in range(args.warmup):
             step_resident()
@@ -158,19 +164,27 @@ def time_workload(name, count, args, rank, world, torch, dist, ctx, stream, flus
         launches = ctx.launch_count - launches0
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         # ---- end to end: host buffers in, host buffers out -------------------------------
-        want_int = name in ("c1", "c2", "c3")
+        want_int = not optimise
+        pinned_sol = torch.empty(batch.K * (batch.M + 2 * batch.S), dtype=torch.float64).pin_memory().numpy()
+
+        def step_e2e():
+            if optimise:
+                ctx.optimize_host(batch, refine_bg=True, out_residuals=pinned_res, out_solutions=pinned_sol)
+            else:
+                ctx.evaluate_host(batch, out_residuals=pinned_res, out_intensities=pinned_int if want_int else None)
+
         for _ in range(min(args.warmup, 2)):
-            ctx.evaluate_host(batch, out_residuals=pinned_res, out_intensities=pinned_int if want_int else None)
+            step_e2e()
         sync_all()
         e0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.evaluate_host(batch, out_residuals=pinned_res, out_intensities=pinned_int if want_int else None)
+            step_e2e()
         sync_all()
         e2e_s = time.perf_counter() - e0
         h2d = sum(a.nbytes for a in (batch.phase_i, batch.phase_d, batch.phase_comp, batch.matrices, batch.comp_d,
                                      batch.comp_i, batch.atom_d, batch.atom_type, batch.job_phase, batch.fractions,
                                      batch.scales, batch.bgshifts)) + 20 * batch.job_phase.size
-        d2h = pinned_res.nbytes + (pinned_int.nbytes if want_int else 0)
+        d2h = pinned_res.nbytes + (pinned_int.nbytes if want_int else pinned_sol.nbytes)
     t = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -211,6 +225,31 @@ def cpu_sample(name, budget_s=12.0, processes=1):
                 done += chunk
     dt = time.perf_counter() - t0
     return dict(patterns=done, seconds=dt, pts_per_s=done * pts / dt, trials_per_s=done / dt)
+
+
+def cpu_trials(budget_s=10.0, name="c4"):
+    """oracle get_optimized_residual (= the reference's per-trial callback) on a few candidates"""
+    from oracle import pyxrd_oracle as orc
+    cfg = syn.CONFIGS[name]
+    truth = cfg.truth()
+    mixes = cfg.population(SEED, 64)
+
+    def calc_total(mix):
+        orc.calculate_mixture(mix)
+        return [np.array(s.total_intensity) for s in mix.specimens]
+
+    syn.attach_observed(mixes, truth, calc_total)
+    for m in mixes:
+        m.parsed = m.calculated = m.optimized = False
+    t0 = time.perf_counter()
+    n = 0
+    for m in mixes:
+        orc.get_optimized_residual(m)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(n=n, seconds=dt, trials_per_s=n / dt)
 
 
 def _cpu_one(arg):
@@ -281,7 +320,8 @@ def run_b200(args, rank, world, local_rank):
         clocks = sampler.stop()
         trials = None
         if args.workload != "c4" and not args.no_trials:
-            trials = time_workload("c4", DEFAULT_CANDIDATES["c4"], args, rank, world, torch, dist, ctx, stream, flush)
+            trials = time_workload("c4", DEFAULT_CANDIDATES["c4"], args, rank, world, torch, dist, ctx, stream, flush,
+                                   optimise=True)
         # residual gather (the only collective of the path): [K, 1+S] per rank over NCCL
         gather_us = None
         if world > 1:
@@ -333,14 +373,18 @@ def run_b200(args, rank, world, local_rank):
     }
     if trials is not None:
         tv = trials["K"] * world / (trials["dev_ms"] * 1e-3)
-        line["trials"] = {"metric": "refinement trial evals/s (calculate_mixture semantics: all phase patterns + "
-                                    "residual at the candidate's solution)",
+        line["trials"] = {"metric": "refinement trial evals/s (get_optimized_residual semantics: all phase patterns "
+                                    "of the trial + optimisation of fractions / scales / background + residual)",
                           "value": tv, "unit": "trials/s", "ms_per_step": trials["dev_ms"],
                           "e2e": {"value": trials["K"] * world / (trials["e2e_ms"] * 1e-3), "unit": "trials/s",
                                   "h2d_bytes_per_step": trials["h2d"], "d2h_bytes_per_step": trials["d2h"]},
                           "config": {"workload": "c4: %s" % trials["cfg"].description,
                                      "candidates_per_gpu": trials["K"]},
-                          "stage_ms": trials["stage"], "gpu_launches": trials["launches"],
+                          "stage_ms": {"phase": trials["stage"]["phase"], "wavelength": trials["stage"]["wavelength"],
+                                       "optimiser": trials["stage"]["residual"]},
+                          "optimiser": "device majorise-minimise (pyxrd_optimize), 32 reweightings x <=4 Newton steps; "
+                                       "contract: <= reference L-BFGS-B optimum * (1 + 5e-3)",
+                          "gpu_launches": trials["launches"],
                           "pattern_pts_per_s": trials["points"] * world / (trials["dev_ms"] * 1e-3)}
     if gather_us is not None:
         line["residual_gather_us"] = gather_us
@@ -349,6 +393,11 @@ def run_b200(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": c["pts_per_s"], "unit": "pattern-pts/s", "cores": 1, "kind": "port",
                                 "sample": "%d candidates of %s through oracle.calculate_mixture, single process, "
                                           "%.1f s" % (c["patterns"], args.workload, c["seconds"])}
+        if trials is not None:
+            ct = cpu_trials(budget_s=10.0)
+            line["trials"]["cpu_baseline"] = {"value": ct["trials_per_s"], "unit": "trials/s", "cores": 1, "kind": "port",
+                                              "sample": "%d c4 candidates through oracle.get_optimized_residual (scipy "
+                                                        "L-BFGS-B), single process, %.1f s" % (ct["n"], ct["seconds"])}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

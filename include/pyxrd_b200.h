@@ -137,6 +137,17 @@ int pyxrd_compute_intensities(pyxrd_ctx *ctx);
  * also scaled_phase_intensities f64 [K][S][M][Z][X_s]. */
 int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled);
 
+/* Device-resident optimiser of the mixture solution of every candidate of the resident batch
+ * (optimize_mixture, mixture.py:150-219: minimise the mean Rp over fractions >= 0, scales > 0,
+ * bgshifts >= 0).  Not a port of L-BFGS-B: majorise-minimise on the L1 objective;
+ * the contract is residual <= the reference's optimum * (1 + 5e-3).  Needs computed intensities;
+ * all fractions and all scales must be free (the reference's default masks); refine_bg = 0 keeps
+ * the batch's bgshifts.  Results: pyxrd_read_solutions f64 [K][M + 2S] = fractions (sum 1) |
+ * scales | bgshifts, pyxrd_read_opt_residuals f64 [K][1+S]. */
+int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newton_iterations);
+int pyxrd_read_solutions(pyxrd_ctx *ctx, double *out, int64_t count);
+int pyxrd_read_opt_residuals(pyxrd_ctx *ctx, double *out, int64_t count);
+
 /* ---- results (synchronise, device -> host) ---------------------------------------- */
 int64_t pyxrd_intensity_count(const pyxrd_ctx *ctx); /* doubles in the intensity buffer */
 int64_t pyxrd_total_count(const pyxrd_ctx *ctx);     /* doubles in the totals buffer */
@@ -154,6 +165,12 @@ int pyxrd_device_buffers(pyxrd_ctx *ctx, double **intensities_dev, double **tota
  * intensities_out may be NULL (a refinement trial only needs the residuals). */
 int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *residuals_out,
                         double *intensities_out);
+
+/* The per-generation call of a refinement: set_batch + compute_intensities + optimize + read;
+ * residuals_out [K][1+S] (get_optimized_residual of every trial = residuals_out[k][0]),
+ * solutions_out [K][M+2S] (may be NULL). */
+int pyxrd_optimize_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, int refine_bg, int outer_iterations,
+                        int newton_iterations, double *residuals_out, double *solutions_out);
 
 /* ---- leaf helpers (GUI previews; also the unit-level parity hooks) ---------------- */
 /* get_atomic_scattering_factor (atoms.py:13-38): s -> asf, n points, one atom type */

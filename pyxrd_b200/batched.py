@@ -54,9 +54,75 @@ def population_phase_intensities(mixtures: Sequence, ctx: Optional[Context] = No
         return ctx.split_per_specimen(ctx.read_intensities_flat(), (batch.M, static.Z))
 
 
-def get_optimized_residuals(mixtures: Sequence, ctx: Optional[Context] = None):
-    """``[get_optimized_residual(m) for m in mixtures]`` (mixture.py:268-276) for a population:
-    every mixture is optimised (fractions / scales / background) and left in the same state
-    the per-trial callback would leave it in; returns the list of 1-element residual arrays."""
+def _device_optimisable(mix) -> bool:
+    """the device optimiser covers the reference's default masks: every fraction and every scale
+    free, background shifts all free or all fixed (mixture/models/mixture.py:64-73)"""
+    m_all = len(np.asarray(mix.fractions).ravel())
+    n_all = len(mix.specimens)
+    return (mix.m == m_all and mix.n == n_all and mix.o in (0, n_all) and m_all <= 11 and n_all <= 8
+            and all(sp is not None and np.size(sp.observed_intensity) > 0 for sp in mix.specimens))
+
+
+def get_optimized_residuals(mixtures: Sequence, ctx: Optional[Context] = None, finalize: bool = False,
+                            outer: int = 0, newton: int = 0):
+    """``[get_optimized_residual(m) for m in mixtures]`` (mixture.py:268-276) for a whole
+    population in one launch sequence: phase intensities, then the device-resident optimiser
+    (majorise-minimise on the Rp objective, ``pyxrd_optimize``) for every candidate at once.
+
+    Every mixture is left as ``optimize_mixture`` leaves it (fractions / scales rounded to 6
+    digits, ``residual``, ``optimized``); with ``finalize=True`` the concluding
+    ``calculate_mixture`` of the reference is run too (patterns + ``residuals`` on the host).
+    Returns the list of 1-element residual arrays.  Contract for the optimum: <= the reference's
+    L-BFGS-B end point * (1 + 5e-3); mixtures with partially fixed variables go
+    through the scipy-driven ``optimize_mixture`` with the device evaluating the objective."""
     from .calculations import mixture as cm
-    return [cm.get_optimized_residual(m) for m in mixtures]
+    ctx = ctx or default_context()
+    out = [None] * len(mixtures)
+    todo = []
+    for i, mix in enumerate(mixtures):
+        if mix.optimized:
+            out[i] = cm.get_optimized_residual(mix)
+            continue
+        try:
+            if not mix.parsed:
+                cm._parse_bookkeeping(mix)
+        except AssertionError:
+            if settings.get("DEBUG"):
+                raise
+            out[i] = cm.get_optimized_residual(mix)        # returns the mixture's state unchanged
+            continue
+        if _device_optimisable(mix):
+            todo.append(i)
+        else:
+            mix.parsed = False
+            mix.m, mix.n = mix.real_m, mix.real_n
+            out[i] = cm.get_optimized_residual(mix)
+    if todo:
+        group = [mixtures[i] for i in todo]
+        static, batch = pack_population(group)
+        refine_bg = group[0].o > 0 and bool(settings.get("BGSHIFT"))
+        with ctx.lock:
+            ctx.set_static(static)
+            ctx.set_batch(batch)
+            ctx.compute_intensities()
+            ctx.optimize(refine_bg=refine_bg, outer=outer, newton=newton)
+            sol = ctx.read_solutions()
+            res = ctx.read_opt_residuals()
+            ctx._resident_epoch = None
+            M, S = batch.M, batch.S
+            for row, i in enumerate(todo):
+                mix = mixtures[i]
+                fractions = np.around(sol[row, :M] / np.sum(sol[row, :M]), 6)
+                mix.fractions = fractions
+                mix.scales = np.array(sol[row, M:M + S]).round(6)
+                mix.bgshifts = np.array(sol[row, M + S:M + 2 * S]) if group[0].o > 0 else np.asarray(mix.bgshifts, float)
+                mix.residual = np.array([res[row, 0]])
+                mix.parsed = False            # phase intensities were not copied to the host
+                mix.m, mix.n = mix.real_m, mix.real_n
+                mix.calculated = False
+                mix.optimized = True
+                out[i] = mix.residual
+        if finalize:
+            for i in todo:
+                cm.calculate_mixture(mixtures[i])
+    return out

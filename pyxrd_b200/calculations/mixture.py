@@ -102,10 +102,9 @@ def _device_residuals(mixture, ctx, want_patterns):
 
 
 # ---- the public functions ----------------------------------------------------------------
-def parse_mixture(mixture, force=False):
-    """mixture.py:103-148: bookkeeping of the selected variables + all phase intensities."""
-    if mixture.parsed and not force:
-        return
+def _parse_bookkeeping(mixture):
+    """the host half of parse_mixture (mixture.py:107-138): sanity checks, selected variables,
+    static fraction sum, pattern count"""
     mixture.parsed = False
     assert mixture.n > 0, "Need at least 1 specimen to optimize phase fractions, scales and background."
     assert mixture.n == len(mixture.specimens), "Invalid specimen count on mixture data object."
@@ -132,6 +131,13 @@ def parse_mixture(mixture, force=False):
     for specimen in mixture.specimens:
         if specimen is None:
             logger.warning("parse_mixture reports: 'None found!'")
+
+
+def parse_mixture(mixture, force=False):
+    """mixture.py:103-148: bookkeeping of the selected variables + all phase intensities."""
+    if mixture.parsed and not force:
+        return
+    _parse_bookkeeping(mixture)
     ctx = default_context()
     with ctx.lock:
         _make_resident(mixture, ctx, download=True)

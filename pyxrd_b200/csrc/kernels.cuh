@@ -187,17 +187,24 @@ __global__ void k_observed_norm(StaticDev st, double *derived) {
     const int X = st.spec_npts[s];
     const double *obs = st.observed + (long long)st.Z * st.spec_off[s];
     const unsigned char *sel = st.selected + st.spec_off[s];
-    double acc = 0.0;
+    double acc = 0.0, cnt = 0.0;
     for (int i = threadIdx.x; i < st.Z * X; i += blockDim.x)
-        if (sel[i % X]) acc += fabs(obs[i]);
-    __shared__ double red[32];
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        if (sel[i % X]) { acc += fabs(obs[i]); cnt += 1.0; }
+    __shared__ double red[2][32];
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_down_sync(0xffffffffu, acc, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc; red[1][threadIdx.x >> 5] = cnt; }
     __syncthreads();
     if (threadIdx.x < 32) {
-        acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-        if (threadIdx.x == 0) derived[s * 8 + 3] = acc;
+        acc = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.0;
+        cnt = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_down_sync(0xffffffffu, acc, o);
+            cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        }
+        if (threadIdx.x == 0) { derived[s * 8 + 3] = acc; derived[s * 8 + 5] = cnt; }   // sum|obs|, #selected points
     }
 }
 
@@ -855,4 +862,276 @@ __global__ void k_dfma_peak(double *out, int iters, double seed) {
         }
     }
     out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------------
+// K4: device-resident mixture optimiser, one CTA per candidate.
+//
+// Minimises the reference's objective (mixture.py:166-184: mean over specimens of
+// Rp_s = 100 sum|obs - scale_s sum_p frac_p I_sp - bg_s C_s| / sum|obs|, statistics.py:22-27)
+// over fractions >= 0, scales > 0, bgshifts >= 0 by majorise-minimise (iteratively reweighted
+// least squares): with weights 1/max(|r_i|, delta) the L1 objective is majorised by a weighted
+// least-squares problem whose data enter only through per-specimen Gram matrices
+// B_s = sum_i w_i phi_i phi_i^T, c_s = sum_i w_i phi_i obs_i, phi_i = (I_s1..I_sM, C_s)(i).
+// One pass over the candidate's patterns builds B_s, c_s (thread per point, block reduction);
+// the small bilinear problem in v = (f[M], rho[S], bg[S]), theta_s = (rho_s f, bg_s), is then
+// solved by a projected Levenberg-Marquardt / Newton iteration on thread 0.
+// Parametrisation: unnormalised fractions f with per-specimen factors rho_s; the reference's
+// (fractions, scales) are f / sum f and rho_s * sum f (mixture.py:32-48,196-205).
+// ---------------------------------------------------------------------------------
+#define PX_OPT_MAXS 8
+#define PX_OPT_MAXMB 12
+#define PX_OPT_MAXD (PX_OPT_MAXMB - 1 + 2 * PX_OPT_MAXS)
+#define PX_OPT_TPB 256
+
+struct OptParams {
+    int outer;          // majorise-minimise iterations
+    int lm_iters;       // Newton / LM iterations per majoriser
+    int refine_bg;      // 0: bgshifts stay at the values of the batch
+    int reserved;
+    double delta0, shrink, delta_min;   // weight floor relative to mean |obs|: delta0 * shrink^it >= delta_min
+};
+
+struct OptSmem {
+    double v[PX_OPT_MAXD];
+    double lo[PX_OPT_MAXD];
+    double B[PX_OPT_MAXS][PX_OPT_MAXMB * PX_OPT_MAXMB];
+    double c[PX_OPT_MAXS][PX_OPT_MAXMB];
+    double wgt[PX_OPT_MAXS];        // 100 / (S * sum|obs|)
+    double mean_obs[PX_OPT_MAXS];
+    double obj[PX_OPT_MAXS];        // sum |r| at the solution the last pass was taken at
+    double H[PX_OPT_MAXD * PX_OPT_MAXD];
+    double A[PX_OPT_MAXD * PX_OPT_MAXD];
+    double g[PX_OPT_MAXD], dx[PX_OPT_MAXD], vn[PX_OPT_MAXD], t[PX_OPT_MAXMB];
+    int idx[PX_OPT_MAXD];
+    double red[PX_OPT_TPB / 32][PX_OPT_MAXMB * (PX_OPT_MAXMB + 1) / 2 + PX_OPT_MAXMB + 1];
+};
+
+// majoriser value (up to a constant) at v
+__device__ double opt_q(const OptSmem &sm, const double *v, int M, int S, int MB) {
+    double q = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const double *B = sm.B[s], *c = sm.c[s];
+        const double r = v[M + s], b = v[M + S + s];
+        double fBf = 0.0, Bcf = 0.0, cf = 0.0;
+        for (int p = 0; p < M; ++p) {
+            double t = 0.0;
+            for (int qn = 0; qn < M; ++qn) t = fma(B[p * MB + qn], v[qn], t);
+            fBf = fma(v[p], t, fBf);
+            Bcf = fma(B[p * MB + M], v[p], Bcf);
+            cf = fma(c[p], v[p], cf);
+        }
+        q += sm.wgt[s] * (r * r * fBf + 2.0 * r * b * Bcf + B[M * MB + M] * b * b - 2.0 * r * cf - 2.0 * c[M] * b);
+    }
+    return q;
+}
+
+// in-place Cholesky solve of the n x n system A x = rhs (A row-major, stride n); false if not positive definite
+__device__ bool opt_chol_solve(double *A, double *x, int n) {
+    for (int j = 0; j < n; ++j) {
+        double d = A[j * n + j];
+        for (int k = 0; k < j; ++k) d = fma(-A[j * n + k], A[j * n + k], d);
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        A[j * n + j] = d;
+        const double inv = 1.0 / d;
+        for (int i = j + 1; i < n; ++i) {
+            double a = A[i * n + j];
+            for (int k = 0; k < j; ++k) a = fma(-A[i * n + k], A[j * n + k], a);
+            A[i * n + j] = a * inv;
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        double a = x[i];
+        for (int k = 0; k < i; ++k) a = fma(-A[i * n + k], x[k], a);
+        x[i] = a / A[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double a = x[i];
+        for (int k = i + 1; k < n; ++k) a = fma(-A[k * n + i], x[k], a);
+        x[i] = a / A[i * n + i];
+    }
+    return true;
+}
+
+// projected LM / Newton on the majoriser (thread 0 only)
+__device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, int lm_iters, int refine_bg) {
+    const int d = M + 2 * S;
+    double lam = 1e-3;
+    for (int it = 0; it < lm_iters; ++it) {
+        double *v = sm.v, *g = sm.g, *H = sm.H;
+        for (int i = 0; i < d; ++i) g[i] = 0.0;
+        for (int i = 0; i < d * d; ++i) H[i] = 0.0;
+        for (int s = 0; s < S; ++s) {
+            const double *B = sm.B[s], *c = sm.c[s];
+            const double w = sm.wgt[s], r = v[M + s], b = v[M + S + s];
+            double fBf = 0.0, Bcf = 0.0, cf = 0.0;
+            for (int p = 0; p < M; ++p) {
+                double t = 0.0;
+                for (int q = 0; q < M; ++q) t = fma(B[p * MB + q], v[q], t);
+                sm.t[p] = t;
+                fBf = fma(v[p], t, fBf);
+                Bcf = fma(B[p * MB + M], v[p], Bcf);
+                cf = fma(c[p], v[p], cf);
+            }
+            const int ir = M + s, ib = M + S + s;
+            for (int p = 0; p < M; ++p) {
+                g[p] += w * (2.0 * r * r * sm.t[p] + 2.0 * r * b * B[p * MB + M] - 2.0 * r * c[p]);
+                for (int q = 0; q < M; ++q) H[p * d + q] += 2.0 * w * r * r * B[p * MB + q];
+                const double hfr = w * (4.0 * r * sm.t[p] + 2.0 * b * B[p * MB + M] - 2.0 * c[p]);
+                H[p * d + ir] = hfr;
+                H[ir * d + p] = hfr;
+                const double hfb = 2.0 * w * r * B[p * MB + M];
+                H[p * d + ib] = hfb;
+                H[ib * d + p] = hfb;
+            }
+            g[ir] = w * (2.0 * r * fBf + 2.0 * b * Bcf - 2.0 * cf);
+            g[ib] = w * (2.0 * r * Bcf + 2.0 * B[M * MB + M] * b - 2.0 * c[M]);
+            H[ir * d + ir] = 2.0 * w * fBf;
+            H[ir * d + ib] = H[ib * d + ir] = 2.0 * w * Bcf;
+            H[ib * d + ib] = 2.0 * w * B[M * MB + M];
+        }
+        int n = 0;
+        for (int i = 0; i < d; ++i) {
+            const bool fixed_bg = (!refine_bg && i >= M + S);
+            const bool at_bound = (v[i] <= sm.lo[i] && g[i] > 0.0);
+            if (!fixed_bg && !at_bound && H[i * d + i] > 0.0) sm.idx[n++] = i;
+        }
+        if (n == 0) break;
+        const double qv = opt_q(sm, v, M, S, MB);
+        bool accepted = false;
+        double rel = 0.0;
+        for (int tr = 0; tr < 8 && !accepted; ++tr) {
+            for (int a = 0; a < n; ++a) {
+                for (int bcol = 0; bcol < n; ++bcol) sm.A[a * n + bcol] = H[sm.idx[a] * d + sm.idx[bcol]];
+                sm.A[a * n + a] += lam * fabs(sm.A[a * n + a]) + 1e-300;
+                sm.dx[a] = -g[sm.idx[a]];
+            }
+            if (!opt_chol_solve(sm.A, sm.dx, n)) { lam *= 10.0; continue; }
+            for (int i = 0; i < d; ++i) sm.vn[i] = v[i];
+            for (int a = 0; a < n; ++a) sm.vn[sm.idx[a]] = fmax(sm.lo[sm.idx[a]], v[sm.idx[a]] + sm.dx[a]);
+            const double qn = opt_q(sm, sm.vn, M, S, MB);
+            if (qn < qv) {
+                accepted = true;
+                rel = (qv - qn) / fmax(fabs(qv), 1e-300);
+                for (int i = 0; i < d; ++i) v[i] = sm.vn[i];
+                lam = fmax(lam * 0.2, 1e-12);
+            } else {
+                lam *= 5.0;
+            }
+        }
+        if (!accepted || rel < 1e-13) break;
+    }
+}
+
+template <int MB>
+__global__ void __launch_bounds__(PX_OPT_TPB) k_mixture_optimize(StaticDev st, BatchDev bt, OptParams op,
+                                                                 double *solutions, double *opt_residuals) {
+    constexpr int M = MB - 1;
+    constexpr int NG = MB * (MB + 1) / 2;       // upper triangle of the Gram matrix
+    constexpr int NACC = NG + MB + 1;           // + c + sum|r|
+    __shared__ OptSmem sm;
+    const int k = blockIdx.x, S = st.S, Z = st.Z, tid = threadIdx.x;
+    const int d = M + 2 * S;
+    if (tid == 0) {
+        for (int p = 0; p < M; ++p) { sm.v[p] = 1.0 / M; sm.lo[p] = 0.0; }             // mixture.py:60-68 start
+        for (int s = 0; s < S; ++s) {
+            sm.v[M + s] = 1.0; sm.lo[M + s] = 1e-12;
+            sm.v[M + S + s] = op.refine_bg ? 0.0 : bt.bgshifts[k * S + s]; sm.lo[M + S + s] = 0.0;
+            const double den = st.derived[s * 8 + 3], count = st.derived[s * 8 + 5];
+            sm.wgt[s] = den > 0.0 ? 100.0 / (S * den) : 0.0;
+            sm.mean_obs[s] = (den > 0.0 && count > 0.0) ? den / count : 1.0;
+        }
+    }
+    __syncthreads();
+    for (int it = 0; it <= op.outer; ++it) {
+        const double delta_rel = fmax(op.delta0 * pow(op.shrink, (double)it), op.delta_min);
+        for (int s = 0; s < S; ++s) {
+            const int X = st.spec_npts[s];
+            const long long soff = st.spec_off[s];
+            const double *I = bt.intensities + (long long)k * bt.cand_stride + (long long)M * Z * soff;
+            const double *obs = st.observed + (long long)Z * soff;
+            const unsigned char *sel = st.selected + soff;
+            const double *corr = st.corr + soff;
+            double theta[MB];
+#pragma unroll
+            for (int p = 0; p < M; ++p) theta[p] = sm.v[M + s] * sm.v[p];
+            theta[M] = sm.v[M + S + s];
+            double acc[NACC];
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+            const double delta = delta_rel * sm.mean_obs[s];
+            for (int i = tid; i < Z * X; i += PX_OPT_TPB) {
+                const int z = i / X, x = i - z * X;
+                if (!sel[x]) continue;
+                double phi[MB];
+#pragma unroll
+                for (int p = 0; p < M; ++p) phi[p] = I[((long long)p * Z + z) * X + x];
+                phi[M] = corr[x];
+                const double o = obs[i];
+                double calc = 0.0;
+#pragma unroll
+                for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[p], calc);
+                const double r = o - calc;
+                const double w = 1.0 / fmax(fabs(r), delta);
+                acc[NACC - 1] += fabs(r);
+                int e = 0;
+#pragma unroll
+                for (int p = 0; p < MB; ++p) {
+                    const double wp = w * phi[p];
+                    acc[NG + p] = fma(wp, o, acc[NG + p]);
+#pragma unroll
+                    for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[q], acc[e]);
+                }
+            }
+            // block reduction of NACC (+ count) values
+            const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+                double vsum = acc[a];
+                for (int o2 = 16; o2 > 0; o2 >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, o2);
+                if (lane == 0) sm.red[warp][a] = vsum;
+            }
+            __syncthreads();
+            if (tid < NACC) {
+                double vsum = 0.0;
+                for (int w2 = 0; w2 < PX_OPT_TPB / 32; ++w2) vsum += sm.red[w2][tid];
+                if (tid < NG) {
+                    // unpack upper-triangle index tid -> (p, q) and mirror
+                    int p = 0, e = tid;
+                    while (e >= MB - p) { e -= MB - p; ++p; }
+                    const int q = p + e;
+                    sm.B[s][p * MB + q] = vsum;
+                    sm.B[s][q * MB + p] = vsum;
+                } else if (tid < NG + MB) {
+                    sm.c[s][tid - NG] = vsum;
+                } else {
+                    sm.obj[s] = vsum;
+                }
+            }
+            __syncthreads();
+        }
+        if (it == op.outer) break;                 // the last pass only evaluates the objective
+        if (tid == 0) opt_inner_solve(sm, M, S, MB, op.lm_iters, op.refine_bg);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        // reference units: fractions = f / sum f, scales = rho * sum f (mixture.py:196-205)
+        double fsum = 0.0;
+        for (int p = 0; p < M; ++p) fsum += sm.v[p];
+        double *out = solutions + (long long)k * d;
+        for (int p = 0; p < M; ++p) out[p] = fsum > 0.0 ? sm.v[p] / fsum : 1.0 / M;
+        for (int s = 0; s < S; ++s) {
+            out[M + s] = sm.v[M + s] * (fsum > 0.0 ? fsum : 1.0);
+            out[M + S + s] = sm.v[M + S + s];
+        }
+        double mean = 0.0;
+        for (int s = 0; s < S; ++s) {
+            const double den = st.derived[s * 8 + 3];
+            const double rp = den > 0.0 ? sm.obj[s] / den * 100.0 : 0.0;
+            opt_residuals[(long long)k * (S + 1) + 1 + s] = rp;
+            mean += rp;
+        }
+        opt_residuals[(long long)k * (S + 1)] = mean / S;
+    }
 }

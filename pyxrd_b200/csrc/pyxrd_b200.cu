@@ -93,7 +93,8 @@ struct pyxrd_ctx {
     const int *jobids_dev = nullptr;   // inside d_blob
     DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_coef, d_int, d_scaled, d_tot, d_res, d_scratch;
     PinBuf h_res;
-    DevBuf d_leaf_a, d_leaf_b, d_leaf_c;
+    DevBuf d_leaf_a, d_leaf_b, d_leaf_c, d_sol, d_optres;
+    bool have_opt = false;
     int64_t int_count = 0, tot_count = 0;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_set[4] = {false, false, false, false};
@@ -197,6 +198,23 @@ int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
     return launch_generic(ctx, rc, jobs_dev);
 }
 
+static int read_back(pyxrd_ctx *ctx, const void *dev, double *out, int64_t count, int64_t have, const char *what) {
+    if (!dev || count > have || count < 0) return fail(ctx, "read %s: asked for %lld doubles, buffer holds %lld", what, (long long)count, (long long)have);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, dev, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+
+template <int MB>
+static int launch_optimize(pyxrd_ctx *ctx, const OptParams &op) {
+    k_mixture_optimize<MB><<<ctx->bt.K, PX_OPT_TPB, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
+                                                                       ctx->d_optres.as<double>());
+    LAUNCH_CHECK("k_mixture_optimize");
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -233,7 +251,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob,
                       &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
-                      &ctx->d_res, &ctx->d_scratch, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c};
+                      &ctx->d_res, &ctx->d_scratch, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
     ctx->h_res.release();
@@ -357,6 +375,7 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     CK(cudaSetDevice(ctx->device));
     ctx->have_batch = false;
     ctx->have_intensities = false;
+    ctx->have_opt = false;
     const StaticDev &st = ctx->st;
     const int K = d->n_candidates, M = d->n_phase_slots, NP = d->n_phases, NC = d->n_components, NA = d->n_atoms;
     const int S = st.S, Z = st.Z;
@@ -596,16 +615,57 @@ int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled) {
     return 0;
 }
 
-int64_t pyxrd_intensity_count(const pyxrd_ctx *ctx) { return ctx ? ctx->int_count : 0; }
-int64_t pyxrd_total_count(const pyxrd_ctx *ctx) { return ctx ? ctx->tot_count : 0; }
-
-static int read_back(pyxrd_ctx *ctx, const void *dev, double *out, int64_t count, int64_t have, const char *what) {
-    if (!dev || count > have || count < 0) return fail(ctx, "read %s: asked for %lld doubles, buffer holds %lld", what, (long long)count, (long long)have);
+int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newton_iterations) {
+    if (!ctx || !ctx->have_batch || !ctx->have_intensities) return fail(ctx, "optimize: intensities not computed");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(out, dev, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    const int M = ctx->bt.M, S = ctx->st.S, K = ctx->bt.K;
+    if (M + 1 > PX_OPT_MAXMB || S > PX_OPT_MAXS)
+        return fail(ctx, "optimize: the device optimiser handles up to %d phases and %d specimens (got %d, %d)",
+                    PX_OPT_MAXMB - 1, PX_OPT_MAXS, M, S);
+    CK(ctx->d_sol.ensure(sizeof(double) * (size_t)K * (M + 2 * S)));
+    CK(ctx->d_optres.ensure(sizeof(double) * (size_t)K * (S + 1)));
+    OptParams op;
+    op.outer = outer_iterations > 0 ? outer_iterations : 32;
+    op.lm_iters = newton_iterations > 0 ? newton_iterations : 4;
+    op.refine_bg = refine_bg ? 1 : 0;
+    op.reserved = 0;
+    op.delta0 = 1e-2;
+    op.shrink = 0.5;
+    op.delta_min = 1e-7;
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    int rc = 1;
+    switch (M + 1) {
+        case 2: rc = launch_optimize<2>(ctx, op); break;
+        case 3: rc = launch_optimize<3>(ctx, op); break;
+        case 4: rc = launch_optimize<4>(ctx, op); break;
+        case 5: rc = launch_optimize<5>(ctx, op); break;
+        case 6: rc = launch_optimize<6>(ctx, op); break;
+        case 7: rc = launch_optimize<7>(ctx, op); break;
+        case 8: rc = launch_optimize<8>(ctx, op); break;
+        case 9: rc = launch_optimize<9>(ctx, op); break;
+        case 10: rc = launch_optimize<10>(ctx, op); break;
+        case 11: rc = launch_optimize<11>(ctx, op); break;
+        case 12: rc = launch_optimize<12>(ctx, op); break;
+        default: return fail(ctx, "optimize: unsupported phase count %d", M);
+    }
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->ev_set[2] = true;
+    ctx->have_opt = true;
     return 0;
 }
+
+int pyxrd_read_solutions(pyxrd_ctx *ctx, double *out, int64_t count) {
+    if (!ctx || !ctx->have_opt) return fail(ctx, "read solutions: optimiser has not run");
+    return read_back(ctx, ctx->d_sol.ptr, out, count, (int64_t)ctx->bt.K * (ctx->bt.M + 2 * ctx->st.S), "solutions");
+}
+int pyxrd_read_opt_residuals(pyxrd_ctx *ctx, double *out, int64_t count) {
+    if (!ctx || !ctx->have_opt) return fail(ctx, "read opt residuals: optimiser has not run");
+    return read_back(ctx, ctx->d_optres.ptr, out, count, (int64_t)ctx->bt.K * (ctx->st.S + 1), "optimised residuals");
+}
+
+int64_t pyxrd_intensity_count(const pyxrd_ctx *ctx) { return ctx ? ctx->int_count : 0; }
+int64_t pyxrd_total_count(const pyxrd_ctx *ctx) { return ctx ? ctx->tot_count : 0; }
 
 int pyxrd_read_intensities(pyxrd_ctx *ctx, double *out, int64_t count) {
     if (!ctx || !ctx->have_intensities) return fail(ctx, "read intensities: not computed");
@@ -644,6 +704,21 @@ int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *re
     CK(cudaMemcpyAsync(ctx->h_res.ptr, ctx->d_res.ptr, sizeof(double) * nres, cudaMemcpyDeviceToHost, ctx->stream));
     if (intensities_out)
         CK(cudaMemcpyAsync(intensities_out, ctx->d_int.ptr, sizeof(double) * (size_t)ctx->int_count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(residuals_out, ctx->h_res.ptr, sizeof(double) * nres);
+    return 0;
+}
+
+int pyxrd_optimize_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, int refine_bg, int outer_iterations,
+                        int newton_iterations, double *residuals_out, double *solutions_out) {
+    if (pyxrd_set_batch(ctx, desc)) return 1;
+    if (pyxrd_compute_intensities(ctx)) return 1;
+    if (pyxrd_optimize(ctx, refine_bg, outer_iterations, newton_iterations)) return 1;
+    const size_t nres = (size_t)ctx->bt.K * (ctx->st.S + 1);
+    CK(cudaMemcpyAsync(ctx->h_res.ptr, ctx->d_optres.ptr, sizeof(double) * nres, cudaMemcpyDeviceToHost, ctx->stream));
+    if (solutions_out)
+        CK(cudaMemcpyAsync(solutions_out, ctx->d_sol.ptr, sizeof(double) * (size_t)ctx->bt.K * (ctx->bt.M + 2 * ctx->st.S),
+                           cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     memcpy(residuals_out, ctx->h_res.ptr, sizeof(double) * nres);
     return 0;

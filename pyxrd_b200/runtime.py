@@ -44,9 +44,10 @@ class BatchDesc(C.Structure):
 EXPORTS = [
     "pyxrd_create", "pyxrd_destroy", "pyxrd_last_error", "pyxrd_set_stream", "pyxrd_synchronize",
     "pyxrd_launch_count", "pyxrd_set_static", "pyxrd_set_batch", "pyxrd_set_solution", "pyxrd_set_intensities",
-    "pyxrd_compute_intensities", "pyxrd_compute_residuals", "pyxrd_intensity_count", "pyxrd_total_count",
+    "pyxrd_compute_intensities", "pyxrd_compute_residuals", "pyxrd_optimize", "pyxrd_read_solutions",
+    "pyxrd_read_opt_residuals", "pyxrd_intensity_count", "pyxrd_total_count",
     "pyxrd_read_intensities", "pyxrd_read_scaled", "pyxrd_read_totals", "pyxrd_read_residuals",
-    "pyxrd_read_correction", "pyxrd_device_buffers", "pyxrd_evaluate_host", "pyxrd_leaf_asf",
+    "pyxrd_read_correction", "pyxrd_device_buffers", "pyxrd_evaluate_host", "pyxrd_optimize_host", "pyxrd_leaf_asf",
     "pyxrd_leaf_lpf", "pyxrd_leaf_csds", "pyxrd_leaf_component", "pyxrd_stage_times", "pyxrd_dfma_peak",
 ]
 
@@ -89,6 +90,9 @@ def load_library():
         lib.pyxrd_set_intensities.argtypes = [vp, _f64p, C.c_int64]
         lib.pyxrd_compute_intensities.argtypes = [vp]
         lib.pyxrd_compute_residuals.argtypes = [vp, C.c_int]
+        lib.pyxrd_optimize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        lib.pyxrd_read_solutions.argtypes = [vp, _f64p, C.c_int64]
+        lib.pyxrd_read_opt_residuals.argtypes = [vp, _f64p, C.c_int64]
         lib.pyxrd_intensity_count.argtypes = [vp]
         lib.pyxrd_intensity_count.restype = C.c_int64
         lib.pyxrd_total_count.argtypes = [vp]
@@ -98,6 +102,7 @@ def load_library():
             getattr(lib, name).argtypes = [vp, _f64p, C.c_int64]
         lib.pyxrd_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         lib.pyxrd_evaluate_host.argtypes = [vp, C.POINTER(BatchDesc), _f64p, _f64p]
+        lib.pyxrd_optimize_host.argtypes = [vp, C.POINTER(BatchDesc), C.c_int, C.c_int, C.c_int, _f64p, _f64p]
         lib.pyxrd_leaf_asf.argtypes = [vp, _f64p, C.c_int64, _f64p, _f64p]
         lib.pyxrd_leaf_lpf.argtypes = [vp, _f64p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _f64p]
         lib.pyxrd_leaf_csds.argtypes = [vp, _f64p, C.c_int, C.c_int, _f64p, _f64p, _f64p]
@@ -206,6 +211,18 @@ class Context(object):
     def compute_residuals(self, want_scaled: bool = False):
         self._check(self._lib.pyxrd_compute_residuals(self._h, int(bool(want_scaled))), "compute_residuals")
 
+    def optimize(self, refine_bg: bool = True, outer: int = 0, newton: int = 0):
+        """device optimiser over the resident batch (needs computed intensities)"""
+        self._check(self._lib.pyxrd_optimize(self._h, int(bool(refine_bg)), int(outer), int(newton)), "optimize")
+
+    def read_solutions(self):
+        b = self._batch
+        return self._read(self._lib.pyxrd_read_solutions, b.K * (b.M + 2 * b.S)).reshape(b.K, b.M + 2 * b.S)
+
+    def read_opt_residuals(self):
+        b = self._batch
+        return self._read(self._lib.pyxrd_read_opt_residuals, b.K * (b.S + 1)).reshape(b.K, b.S + 1)
+
     def evaluate_host(self, batch: BatchPack, want_intensities: bool = False, out_residuals=None,
                       out_intensities=None):
         """one C-ABI call: upload K candidates, compute, return residuals [K, 1+S] (+ intensities).
@@ -219,6 +236,18 @@ class Context(object):
                                                   _p(inten, _f64p) if inten is not None else None), "evaluate_host")
         self._batch = batch
         return res.reshape(batch.K, batch.S + 1), inten
+
+    def optimize_host(self, batch: BatchPack, refine_bg: bool = True, outer: int = 0, newton: int = 0,
+                      out_residuals=None, out_solutions=None):
+        """one C-ABI call per generation: K candidates in (host), optimised residuals [K, 1+S] and
+        solutions [K, M+2S] out (host)"""
+        d = self.batch_desc(batch)
+        res = np.empty(batch.K * (batch.S + 1)) if out_residuals is None else out_residuals
+        sol = np.empty(batch.K * (batch.M + 2 * batch.S)) if out_solutions is None else out_solutions
+        self._check(self._lib.pyxrd_optimize_host(self._h, C.byref(d), int(bool(refine_bg)), int(outer), int(newton),
+                                                  _p(res, _f64p), _p(sol, _f64p)), "optimize_host")
+        self._batch = batch
+        return res.reshape(batch.K, batch.S + 1), sol.reshape(batch.K, batch.M + 2 * batch.S)
 
     # -- results ----------------------------------------------------------------------
     def _read(self, fn, count):
