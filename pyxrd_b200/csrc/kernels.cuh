@@ -641,6 +641,217 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev 
     bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, sigma_star, st, s, gx);
 }
 
+// ---- ranks 8..32 on the FP64 tensor cores (DMMA.8x8x4) ----------------------------
+// One Horner step y <- P (phi o y + c_n g) for 8 points at a time is the real matrix product
+//   Y^T[8 points][r] = W^T[8 points][r] * P^T[r][r]      (re and im as two independent products)
+// issued as mma.sync.m8n8k4.f64: A = W^T tile (points x 4 states), B = P^T tile, C = Y^T tile.
+// The contraction index may be enumerated in any order, so k-tile (nt, s) is defined to hold
+// the states of columns {2q + s, q = 0..3} of n-tile nt: then the lane that owns C[p][2q + s]
+// after one step owns exactly the A[p][k = q] element of k-tile (nt, s) of the next step and the
+// recurrence needs NO data movement between steps: the accumulator registers, updated in place
+// by phi o y + c_n g, are the next A fragments.  P^T fragments stay in registers for the whole
+// kernel (KT x NT doubles per lane); the only other FP64 work in the loop is the 6 flop / state
+// elementwise update.  tools/microbench.cu: DMMA sustains 37.0 TFLOP/s with two independent
+// accumulators per warp (DFMA: 36.2), whereas broadcast-LDS-fed DFMAs (k_phase_staged) stop at
+// 25 TFLOP/s for the 2 DFMA / loaded double this product allows.
+template <int R>
+struct MmaShape {
+    static constexpr int NT = (R + 7) / 8;                // n-tiles of 8 states
+    static constexpr int REM = R - 8 * (NT - 1);          // states in the last n-tile
+    static constexpr bool HALF = REM <= 4;                // ... kept in its even columns: k-tile (NT-1, 1) is all padding
+    static constexpr int KT = 2 * NT - (HALF ? 1 : 0);
+    // state held by column col of n-tile nt, -1 for padding
+    __host__ __device__ static constexpr int state(int nt, int col) {
+        if (nt < NT - 1 || !HALF) return (8 * nt + col < R) ? 8 * nt + col : -1;
+        return ((col & 1) == 0 && (col >> 1) < REM) ? 8 * nt + (col >> 1) : -1;
+    }
+};
+
+__device__ __forceinline__ void px_dmma(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// v[c] for a per-lane component c known to lie in [cmin, cmax] (compile-time after unrolling:
+// a slot whose four lanes share one component costs nothing)
+template <int G>
+__device__ __forceinline__ double px_pick(const double (&v)[G], int c, int cmin, int cmax) {
+    double out = v[cmin];
+#pragma unroll
+    for (int k = 1; k < G; ++k)
+        if (k > cmin && k <= cmax) out = (c >= k) ? v[k] : out;
+    return out;
+}
+
+template <int R, int G, int MTC>
+__global__ void __launch_bounds__(PX_TPB) k_phase_mma(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
+    using SH = MmaShape<R>;
+    constexpr int REPS = R / G, NT = SH::NT, KT = SH::KT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PhaseSmem *ps = reinterpret_cast<PhaseSmem *>(smem_raw);
+    double *sP = reinterpret_cast<double *>(smem_raw + sizeof(PhaseSmem));   // [R][R]
+    double *sWG = sP + R * R;                                               // [G][R]
+    double2 *sU = reinterpret_cast<double2 *>(sWG + G * R + ((R * R + G * R) & 1));   // [G][TPB] structure factors
+    double2 *sF = sU + G * PX_TPB;                                          // [G][TPB] phase factors
+    double *sCoef = reinterpret_cast<double *>(sF + G * PX_TPB);
+
+    const int job = jobs[blockIdx.x];
+    const int pb = bt.job_pb[job], s = bt.job_spec[job];
+    const int X = st.spec_npts[s];
+    const int x0 = blockIdx.y * PX_TPB;
+    if (x0 >= X) return;
+    const int *pi = bt.phase_i + pb * 8;
+    const double *px = bt.phase_x + pb * 4;
+    const int ntop = (int)px[2];
+    const double mean = px[0], abs_scale = px[1];
+    const int flags = pi[4];
+    const double sigma_star = bt.phase_d[pb * 8];
+
+    load_phase_lists(bt, pb, G, ps, st.sumX);
+    {
+        const double *W = bt.matrices + pi[6];
+        const double *P = W + R * R;
+        for (int i = threadIdx.x; i < R * R; i += PX_TPB) sP[i] = P[i];
+        for (int i = threadIdx.x; i < G * R; i += PX_TPB) {
+            const int c = i / R, K = i % R;
+            double acc = 0.0;
+            for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
+            sWG[i] = acc;
+        }
+        const double *coef = bt.coef + (long long)pb * bt.ncap;
+        for (int i = threadIdx.x; i <= ntop; i += PX_TPB) sCoef[i] = coef[i];
+    }
+    __syncthreads();
+
+    const int wbase = threadIdx.x & ~31;
+    if (x0 + wbase >= X) return;                          // whole warp beyond the pattern
+    const int x = x0 + threadIdx.x;
+    const bool live = x < X;
+    const long long gx = st.spec_off[s] + (live ? x : X - 1);    // idle lanes of the last warp recompute the last point
+    const double stl = st.stl[gx];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        double a, b, f, g;
+        component_factors(ps, c, stl, st.asf + gx, st.sumX, a, b, f, g);
+        sU[c * PX_TPB + threadIdx.x] = make_double2(a, b);
+        sF[c * PX_TPB + threadIdx.x] = make_double2(f, g);
+    }
+    __syncwarp();
+
+    const int lane = threadIdx.x & 31, q = lane & 3, p = lane >> 2;
+    // B fragments: lane holds P^T[k = q][n = p] = P[state(nto, p)][state(kt / 2, 2 q + kt % 2)]
+    double Pf[KT][NT];
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int nto = 0; nto < NT; ++nto) {
+            const int J = SH::state(kt >> 1, 2 * q + (kt & 1)), I = SH::state(nto, p);
+            Pf[kt][nto] = (I >= 0 && J >= 0) ? sP[I * R + J] : 0.0;
+        }
+
+    double mytr = 0.0;
+#pragma unroll 1
+    for (int mg = 0; mg < 4; mg += MTC) {                 // MTC m-tiles (8 points each) in flight
+        double fpr[MTC][NT][2], fpi[MTC][NT][2], fgr[MTC][NT][2], fgi[MTC][NT][2];
+#pragma unroll
+        for (int m = 0; m < MTC; ++m) {
+            const int src = wbase + 8 * (mg + m) + p;     // the point of this lane's fragment row
+            double tpr[G], tpi[G], tgr[G], tgi[G];
+#pragma unroll
+            for (int c = 0; c < G; ++c) {
+                const double2 u = sU[c * PX_TPB + src], f = sF[c * PX_TPB + src];
+                tpr[c] = f.x;
+                tpi[c] = f.y;
+                tgr[c] = f.x * u.x + f.y * u.y;           // g = phi * conj(u)
+                tgi[c] = f.y * u.x - f.x * u.y;
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    const int I0 = SH::state(nt, sl), I3 = SH::state(nt, 6 + sl), It = SH::state(nt, 2 * q + sl);
+                    const int cmin = (I0 >= 0 ? I0 : R - 1) / REPS, cmax = (I3 >= 0 ? I3 : R - 1) / REPS;
+                    const int ct = (It >= 0 ? It : R - 1) / REPS;
+                    fpr[m][nt][sl] = px_pick<G>(tpr, ct, cmin, cmax);
+                    fpi[m][nt][sl] = px_pick<G>(tpi, ct, cmin, cmax);
+                    fgr[m][nt][sl] = px_pick<G>(tgr, ct, cmin, cmax);
+                    fgi[m][nt][sl] = px_pick<G>(tgi, ct, cmin, cmax);
+                }
+        }
+        double yr[MTC][NT][2], yi[MTC][NT][2];
+#pragma unroll
+        for (int m = 0; m < MTC; ++m)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { yr[m][nt][0] = yr[m][nt][1] = 0.0; yi[m][nt][0] = yi[m][nt][1] = 0.0; }
+#pragma unroll 1
+        for (int n = ntop; n >= 1; --n) {
+            const double cn = sCoef[n];
+            double wr[MTC][NT][2], wi[MTC][NT][2];
+#pragma unroll
+            for (int m = 0; m < MTC; ++m)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl) {      // w = phi o y + c_n g, in the C layout = next A layout
+                        wr[m][nt][sl] = fma(fpr[m][nt][sl], yr[m][nt][sl], fma(-fpi[m][nt][sl], yi[m][nt][sl], cn * fgr[m][nt][sl]));
+                        wi[m][nt][sl] = fma(fpr[m][nt][sl], yi[m][nt][sl], fma(fpi[m][nt][sl], yr[m][nt][sl], cn * fgi[m][nt][sl]));
+                    }
+#pragma unroll
+            for (int m = 0; m < MTC; ++m)
+#pragma unroll
+                for (int nto = 0; nto < NT; ++nto) {
+                    double r0 = 0.0, r1 = 0.0, i0 = 0.0, i1 = 0.0;
+#pragma unroll
+                    for (int kt = 0; kt < KT; ++kt) {
+                        px_dmma(r0, r1, wr[m][kt >> 1][kt & 1], Pf[kt][nto]);
+                        px_dmma(i0, i1, wi[m][kt >> 1][kt & 1], Pf[kt][nto]);
+                    }
+                    yr[m][nto][0] = r0; yr[m][nto][1] = r1;
+                    yi[m][nto][0] = i0; yi[m][nto][1] = i1;
+                }
+        }
+        // Re( sum_K a_K (mean b_K + y_K) ) over this lane's columns, then over the four lanes of the row
+#pragma unroll
+        for (int m = 0; m < MTC; ++m) {
+            const int src = wbase + 8 * (mg + m) + p;
+            double tur[G], tui[G];
+#pragma unroll
+            for (int c = 0; c < G; ++c) {
+                const double2 u = sU[c * PX_TPB + src];
+                tur[c] = u.x;
+                tui[c] = u.y;
+            }
+            double part = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (SH::state(nt, sl) < 0) continue;              // column pair of padding only
+                    const int It = SH::state(nt, 2 * q + sl);
+                    const int K = It >= 0 ? It : 0;
+                    double ar = 0.0, ai = 0.0;
+#pragma unroll
+                    for (int c = 0; c < G; ++c) {
+                        const double w = It >= 0 ? sWG[c * R + K] : 0.0;
+                        ar = fma(tur[c], w, ar);
+                        ai = fma(tui[c], w, ai);
+                    }
+                    const int I0 = SH::state(nt, sl), I3 = SH::state(nt, 6 + sl);
+                    const int cmin = I0 / REPS, cmax = (I3 >= 0 ? I3 : R - 1) / REPS;
+                    const double ukr = px_pick<G>(tur, K / REPS, cmin, cmax), uki = px_pick<G>(tui, K / REPS, cmin, cmax);
+                    const double sr = fma(mean, ukr, yr[m][nt][sl]);
+                    const double si = fma(-mean, uki, yi[m][nt][sl]);
+                    part += ar * sr - ai * si;
+                }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            const double mine = __shfl_sync(0xffffffffu, part, 4 * (lane & 7));   // row lane % 8 of this m-tile
+            if ((lane >> 3) == mg + m) mytr = mine;
+        }
+    }
+    if (live) bt.intensities[bt.job_out[job] + x] = finish_point(mytr, abs_scale, flags, sigma_star, st, s, gx);
+}
+
 // ---- any rank <= 64: vectors in shared memory (fallback, not tuned) --------------
 __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -72,6 +73,7 @@ struct pyxrd_ctx {
     std::string error;
     int64_t launches = 0;
     int smem_optin = 0;
+    bool series_mma = true;   // PYXRD_B200_SERIES=dfma selects the CUDA-core series kernels (A/B measurements only)
 
     // static
     bool have_static = false;
@@ -143,6 +145,10 @@ size_t staged_smem(int R, int G, int ntop_cap) {
     return sizeof(PhaseSmem) + sizeof(double) * (size_t)(RB * R * 4 + G * R + (G * R & 1)) +
            sizeof(double2) * (size_t)R * PX_TPB + sizeof(double) * (size_t)(ntop_cap + 2);
 }
+size_t mma_smem(int R, int G, int ntop_cap) {
+    return sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + ((R * R + G * R) & 1)) +
+           sizeof(double2) * (size_t)2 * G * PX_TPB + sizeof(double) * (size_t)(ntop_cap + 2);
+}
 size_t generic_smem(int R, int G, int ntop_cap) {
     return sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + 1) +
            sizeof(double2) * (size_t)(2 * R + 16) * PX_GEN_TPB + sizeof(double) * (size_t)(ntop_cap + 2);
@@ -177,6 +183,16 @@ int launch_staged(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
     return 0;
 }
 
+template <int R, int G, int MTC>
+int launch_mma(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+    const size_t smem = mma_smem(R, G, rc.max_ntop_cap);
+    if (set_smem(ctx, k_phase_mma<R, G, MTC>, smem)) return 1;
+    dim3 grid((unsigned)rc.jobs.size(), (unsigned)((rc.max_x + PX_TPB - 1) / PX_TPB));
+    k_phase_mma<R, G, MTC><<<grid, PX_TPB, smem, ctx->stream>>>(ctx->st, ctx->bt, jobs_dev);
+    LAUNCH_CHECK("k_phase_mma");
+    return 0;
+}
+
 int launch_generic(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
     const size_t smem = generic_smem(rc.rank, rc.G, rc.max_ntop_cap);
     if (set_smem(ctx, k_phase_generic, smem)) return 1;
@@ -191,10 +207,13 @@ int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
 #define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev)
     SMALL(1, 1); SMALL(2, 2); SMALL(3, 3); SMALL(4, 4); SMALL(5, 5); SMALL(6, 6);   // R0 / R1
     SMALL(2, 1); SMALL(3, 1); SMALL(4, 1);
+#define MMA(R_, G_, MTC_) if (rc.rank == R_ && rc.G == G_ && ctx->series_mma) return launch_mma<R_, G_, MTC_>(ctx, rc, jobs_dev)
+    MMA(8, 2, 4); MMA(16, 2, 2); MMA(16, 4, 2); MMA(27, 3, 1);                        // FP64 tensor cores
     SMALL(4, 2); SMALL(8, 2); SMALL(9, 3);                                            // R2G2, R3G2, R2G3
     STAGED(16, 2); STAGED(16, 4); STAGED(27, 3);
 #undef SMALL
 #undef STAGED
+#undef MMA
     return launch_generic(ctx, rc, jobs_dev);
 }
 
@@ -237,6 +256,7 @@ int pyxrd_create(int device, pyxrd_ctx **out) {
         return 3;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *e = getenv("PYXRD_B200_SERIES")) ctx->series_mma = strcmp(e, "dfma") != 0;
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
     *out = ctx;
