@@ -21,6 +21,7 @@
 
 #define PX_TPB 128          // threads (= 2-theta points) per block in the phase kernels
 #define PX_GEN_TPB 64       // generic-rank fallback
+#define PX_TABLE_PAD 1024    // doubles of slack after every per-point table (multi-point threads read past a pattern end)
 #define PX_TWO_PI 6.283185307179586        // python: 2 * math.pi
 #define PX_PI 3.141592653589793
 #define PX_SQRT2PI 2.5066282746310002      // math.sqrt(2 * pi)
@@ -418,6 +419,88 @@ __device__ __forceinline__ void component_factors(const PhaseSmem *ps, int c, do
     phase_factor(stl, ps->comp_d001[c], ps->comp_delta[c], pr, pi_);
 }
 
+// N independent arguments in lock step: every coefficient is fetched once for N FMAs and the N
+// dependent chains interleave (DFMA latency is 8.5 cycles, tools/microbench.cu)
+template <int N>
+__device__ __forceinline__ void px_sincos_n(const double (&a)[N], double (&s)[N], double (&c)[N]) {
+    double q[N], r[N], r2[N], ps[N], pc[N];
+    int n[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double t = fma(a[k], PX_SC[0], PX_SC[1]);
+        q[k] = t - PX_SC[1];
+        n[k] = __double2loint(t);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = fma(q[k], PX_SC[2], a[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = fma(q[k], PX_SC[3], r[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) { r[k] = fma(q[k], PX_SC[4], r[k]); r2[k] = r[k] * r[k]; ps[k] = PX_SC[5]; pc[k] = PX_SC[11]; }
+#pragma unroll
+    for (int j = 6; j <= 10; ++j)
+#pragma unroll
+        for (int k = 0; k < N; ++k) { ps[k] = fma(ps[k], r2[k], PX_SC[j]); pc[k] = fma(pc[k], r2[k], PX_SC[j + 6]); }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double sn = fma(r[k] * r2[k], ps[k], r[k]);
+        const double cs = fma(r2[k] * r2[k], pc[k], fma(r2[k], PX_SC[17], PX_SC[18]));
+        const double S = (n[k] & 1) ? cs : sn, C = (n[k] & 1) ? sn : cs;
+        s[k] = __hiloint2double(__double2hiint(S) ^ ((n[k] & 2) << 30), __double2loint(S));
+        c[k] = __hiloint2double(__double2hiint(C) ^ (((n[k] + 1) & 2) << 30), __double2loint(C));
+    }
+}
+
+// structure factor and phase factor of component c at the N points gx0 + k * stride of one thread
+// (same arithmetic per point as component_factors)
+template <int N>
+__device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, const double (&stl)[N],
+                                                    const double *__restrict__ asf_col, int stride,
+                                                    double (&ur)[N], double (&ui)[N], double (&pr)[N], double (&pim)[N]) {
+    double sr[N], si[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { sr[k] = 0.0; si[k] = 0.0; }
+    const int p0 = ps->comp_first[c], p1 = p0 + ps->comp_count[c];
+    int a = (p0 == 0) ? 0 : ps->plane_end[p0 - 1];
+    for (int p = p0; p < p1; ++p) {
+        const int end = ps->plane_end[p];
+        double f[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) f[k] = 0.0;
+        for (; a < end; ++a) {
+            const double2 po = ps->atom_po[a];
+            const double *col = asf_col + __double_as_longlong(po.y);
+#pragma unroll
+            for (int k = 0; k < N; ++k) f[k] = fma(__ldg(col + k * stride), po.x, f[k]);
+        }
+        const double arg = ps->plane_arg[p];
+        double ang[N], sn[N], cs[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(arg, stl[k]);
+        px_sincos_n<N>(ang, sn, cs);
+#pragma unroll
+        for (int k = 0; k < N; ++k) { sr[k] = fma(f[k], cs[k], sr[k]); si[k] = fma(f[k], sn[k], si[k]); }
+    }
+    const double d001 = ps->comp_d001[c], delta_c = ps->comp_delta[c];
+    double ang[N], sn[N], cs[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), d001);
+    px_sincos_n<N>(ang, sn, cs);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        ur[k] = sr[k];
+        ui[k] = si[k];
+        if (delta_c != 0.0) {                               // block-uniform branch
+            const double e = exp(__dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl[k])));
+            pr[k] = e * cs[k];
+            pim[k] = e * sn[k];
+        } else {
+            pr[k] = cs[k];
+            pim[k] = sn[k];
+        }
+    }
+}
+
 // everything after Re(a^T S b): absolute scale, LPF, machine correction (phases.py:158,81-95, specimen.py:57-62)
 __device__ __forceinline__ double finish_point(double tr, double abs_scale, int flags, double sigma_star,
                                                const StaticDev &st, int s, long long gx) {
@@ -430,9 +513,14 @@ __device__ __forceinline__ double finish_point(double tr, double abs_scale, int 
     return I;
 }
 
-// ---- ranks up to 9: every vector in registers ------------------------------------
-template <int R, int G>
-__global__ void __launch_bounds__(PX_TPB) k_phase_small(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
+// ---- ranks up to 9: every vector in registers, PPT points per thread -----------------
+// A thread owns the points x0 + t + k * TPB, k < PPT: the warp-uniform work (shared-memory
+// reads of the atom / plane lists and of P, loop control, coefficient fetches) is paid once for
+// PPT points and the dependent FMA chains of the PPT points interleave.  Per-point tables are
+// padded by PX_TABLE_PAD doubles, so the loads of points beyond the end of a pattern are legal;
+// only the stores are guarded.
+template <int R, int G, int PPT, int TPB>
+__global__ void __launch_bounds__(TPB) k_phase_small(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
     constexpr int REPS = R / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PhaseSmem *ps = reinterpret_cast<PhaseSmem *>(smem_raw);
@@ -443,7 +531,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_small(StaticDev st, BatchDev b
     const int job = jobs[blockIdx.x];
     const int pb = bt.job_pb[job], s = bt.job_spec[job];
     const int X = st.spec_npts[s];
-    const int x0 = blockIdx.y * PX_TPB;
+    const int x0 = blockIdx.y * (TPB * PPT);
     if (x0 >= X) return;
     const int *pi = bt.phase_i + pb * 8;
     const double *px = bt.phase_x + pb * 4;
@@ -456,72 +544,95 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_small(StaticDev st, BatchDev b
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
-        for (int i = threadIdx.x; i < R * R; i += PX_TPB) sP[i] = P[i];
-        for (int i = threadIdx.x; i < G * R; i += PX_TPB) {       // WG[c][K] = sum_{J in c} W[J][K]
+        for (int i = threadIdx.x; i < R * R; i += TPB) sP[i] = P[i];
+        for (int i = threadIdx.x; i < G * R; i += TPB) {          // WG[c][K] = sum_{J in c} W[J][K]
             const int c = i / R, K = i % R;
             double acc = 0.0;
             for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
             sWG[i] = acc;
         }
         const double *coef = bt.coef + (long long)pb * bt.ncap;
-        for (int i = threadIdx.x; i <= ntop; i += PX_TPB) sCoef[i] = coef[i];
+        for (int i = threadIdx.x; i <= ntop; i += TPB) sCoef[i] = coef[i];
     }
     __syncthreads();
 
     const int x = x0 + threadIdx.x;
     if (x >= X) return;
     const long long gx = st.spec_off[s] + x;
-    const double stl = st.stl[gx];
+    double stl[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) stl[k] = st.stl[gx + k * TPB];
 
-    double ur[G], ui[G], pr[G], pim[G], gr[G], gi[G];
+    double ur[G][PPT], ui[G][PPT], pr[G][PPT], pim[G][PPT], gr[G][PPT], gi[G][PPT];
 #pragma unroll
     for (int c = 0; c < G; ++c) {
-        component_factors(ps, c, stl, st.asf + gx, st.sumX, ur[c], ui[c], pr[c], pim[c]);
-        gr[c] = pr[c] * ur[c] + pim[c] * ui[c];          // g = phi * conj(u)
-        gi[c] = pim[c] * ur[c] - pr[c] * ui[c];
-    }
-    double yr[R], yi[R];
+        component_factors_n<PPT>(ps, c, stl, st.asf + gx, TPB, ur[c], ui[c], pr[c], pim[c]);
 #pragma unroll
-    for (int I = 0; I < R; ++I) { yr[I] = 0.0; yi[I] = 0.0; }
+        for (int k = 0; k < PPT; ++k) {
+            gr[c][k] = pr[c][k] * ur[c][k] + pim[c][k] * ui[c][k];          // g = phi * conj(u)
+            gi[c][k] = pim[c][k] * ur[c][k] - pr[c][k] * ui[c][k];
+        }
+    }
+    double yr[R][PPT], yi[R][PPT];
+#pragma unroll
+    for (int I = 0; I < R; ++I)
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) { yr[I][k] = 0.0; yi[I][k] = 0.0; }
     for (int n = ntop; n >= 1; --n) {
         const double cn = sCoef[n];
-        double wr[R], wi[R];
+        double wr[R][PPT], wi[R][PPT];
 #pragma unroll
         for (int I = 0; I < R; ++I) {                     // w = phi o (y + c_n b)
             const int c = I / REPS;
-            wr[I] = fma(pr[c], yr[I], fma(-pim[c], yi[I], cn * gr[c]));
-            wi[I] = fma(pr[c], yi[I], fma(pim[c], yr[I], cn * gi[c]));
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                wr[I][k] = fma(pr[c][k], yr[I][k], fma(-pim[c][k], yi[I][k], cn * gr[c][k]));
+                wi[I][k] = fma(pr[c][k], yi[I][k], fma(pim[c][k], yr[I][k], cn * gi[c][k]));
+            }
         }
 #pragma unroll
         for (int I = 0; I < R; ++I) {                     // y = P w
-            double ar = 0.0, ai = 0.0;
+            double ar[PPT], ai[PPT];
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
 #pragma unroll
             for (int J = 0; J < R; ++J) {
                 const double p = sP[I * R + J];
-                ar = fma(p, wr[J], ar);
-                ai = fma(p, wi[J], ai);
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) {
+                    ar[k] = fma(p, wr[J][k], ar[k]);
+                    ai[k] = fma(p, wi[J][k], ai[k]);
+                }
             }
-            yr[I] = ar;
-            yi[I] = ai;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) { yr[I][k] = ar[k]; yi[I][k] = ai[k]; }
         }
     }
     // Re( sum_K a_K (mean b_K + y_K) ), a_K = sum_c u_c WG[c][K], b_K = conj(u_comp(K))
-    double tr = 0.0;
+    double tr[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) tr[k] = 0.0;
 #pragma unroll
     for (int K = 0; K < R; ++K) {
         const int ck = K / REPS;
-        double ar = 0.0, ai = 0.0;
 #pragma unroll
-        for (int c = 0; c < G; ++c) {
-            const double w = sWG[c * R + K];
-            ar = fma(ur[c], w, ar);
-            ai = fma(ui[c], w, ai);
+        for (int k = 0; k < PPT; ++k) {
+            double ar = 0.0, ai = 0.0;
+#pragma unroll
+            for (int c = 0; c < G; ++c) {
+                const double w = sWG[c * R + K];
+                ar = fma(ur[c][k], w, ar);
+                ai = fma(ui[c][k], w, ai);
+            }
+            const double sr = fma(mean, ur[ck][k], yr[K][k]);
+            const double si = fma(-mean, ui[ck][k], yi[K][k]);
+            tr[k] += ar * sr - ai * si;
         }
-        const double sr = fma(mean, ur[ck], yr[K]);
-        const double si = fma(-mean, ui[ck], yi[K]);
-        tr += ar * sr - ai * si;
     }
-    bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, sigma_star, st, s, gx);
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+        if (x + k * TPB < X)
+            bt.intensities[bt.job_out[job] + x + k * TPB] = finish_point(tr[k], abs_scale, flags, sigma_star, st, s, gx + k * TPB);
 }
 
 // ---- ranks 16 / 27: w in registers, the new vector staged through shared memory ----
@@ -966,56 +1077,69 @@ __global__ void k_leaf_component(const double *stl, long long n, const double *c
 
 // ---------------------------------------------------------------------------------
 // wavelength distribution: I <- I + interp(asin(stl lambda_j / 2), f_j I)(theta), j in list order,
-// each pass reading the pattern the previous pass produced (specimen.py:64-74)
+// each pass reading the pattern the previous pass produced (specimen.py:64-74).
+// One launch per pass j, out of place (src -> dst, the caller ping-pongs two buffers): every
+// point is independent, so the pass is a streaming gather with 4 points in flight per thread.
+// The abscissa tables (index of the upper neighbour and the two interpolation weights) are
+// candidate-invariant and L2-resident.
 // ---------------------------------------------------------------------------------
-__global__ void k_wavelength(StaticDev st, BatchDev bt, int njobs, int use_global, double *scratch) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int job = blockIdx.x;
-    if (job >= njobs) return;
+#define PX_WL_TPB 256
+#define PX_WL_PPT 4
+__global__ void __launch_bounds__(PX_WL_TPB) k_wavelength_pass(StaticDev st, BatchDev bt, int job0, int pass,
+                                                               const double *__restrict__ src, double *__restrict__ dst) {
+    const int job = job0 + blockIdx.y;
     const int s = bt.job_spec[job];
-    const int nwl = st.spec_nwl[s];
     const int X = st.spec_npts[s];
-    double *I = bt.intensities + bt.job_out[job];
-    if (bt.job_pb[job] < 0 || nwl == 0) return;          // a zero pattern stays zero
-    double *bufA, *bufB;
-    if (use_global) {
-        bufA = scratch + (long long)job * 2 * st.maxX;
-        bufB = bufA + st.maxX;
-    } else {
-        bufA = reinterpret_cast<double *>(smem_raw);
-        bufB = bufA + st.maxX;
+    const int xb = blockIdx.x * (PX_WL_TPB * PX_WL_PPT) + threadIdx.x;
+    if (xb >= X) return;
+    const long long out = bt.job_out[job];
+    const double *I = src + out;
+    double *O = dst + out;
+    const bool active = bt.job_pb[job] >= 0 && pass < st.spec_nwl[s];     // a zero pattern stays zero
+    const long long off = st.wl_off[s] + (long long)pass * X;
+    const double f = active ? st.wl_fraction[st.wl_first[s] + pass] : 0.0;
+    double v[PX_WL_PPT], hi_v[PX_WL_PPT], lo_v[PX_WL_PPT], whi[PX_WL_PPT], wlo[PX_WL_PPT];
+    int hi[PX_WL_PPT];
+#pragma unroll
+    for (int u = 0; u < PX_WL_PPT; ++u) {
+        const int x = xb + u * PX_WL_TPB;
+        hi[u] = (active && x < X) ? __ldg(st.wl_index + off + x) : -1;
     }
-    for (int x = threadIdx.x; x < X; x += blockDim.x) bufA[x] = I[x];
-    __syncthreads();
-    const double *frac = st.wl_fraction + st.wl_first[s];
-    for (int j = 0; j < nwl; ++j) {
-        const long long off = st.wl_off[s] + (long long)j * X;
-        const double f = frac[j];
-        for (int x = threadIdx.x; x < X; x += blockDim.x) {
-            const int hi = st.wl_index[off + x];
-            double add = 0.0;
-            if (hi >= 0) {
-                const double y_hi = __dmul_rn(bufA[hi], f), y_lo = __dmul_rn(bufA[hi - 1], f);
-                add = __dadd_rn(__dmul_rn(st.wl_w_hi[off + x], y_hi), __dmul_rn(st.wl_w_lo[off + x], y_lo));
-            }
-            bufB[x] = __dadd_rn(bufA[x], add);
+#pragma unroll
+    for (int u = 0; u < PX_WL_PPT; ++u) {
+        const int x = xb + u * PX_WL_TPB;
+        v[u] = (x < X) ? I[x] : 0.0;
+        const bool g = hi[u] >= 0;
+        hi_v[u] = g ? I[hi[u]] : 0.0;
+        lo_v[u] = g ? I[hi[u] - 1] : 0.0;
+        whi[u] = g ? __ldg(st.wl_w_hi + off + x) : 0.0;
+        wlo[u] = g ? __ldg(st.wl_w_lo + off + x) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < PX_WL_PPT; ++u) {
+        const int x = xb + u * PX_WL_TPB;
+        if (x >= X) continue;
+        double add = 0.0;
+        if (hi[u] >= 0) {
+            const double y_hi = __dmul_rn(hi_v[u], f), y_lo = __dmul_rn(lo_v[u], f);
+            add = __dadd_rn(__dmul_rn(whi[u], y_hi), __dmul_rn(wlo[u], y_lo));
         }
-        __syncthreads();
-        double *tmp = bufA; bufA = bufB; bufB = tmp;
+        O[x] = __dadd_rn(v[u], add);
     }
-    for (int x = threadIdx.x; x < X; x += blockDim.x) I[x] = bufA[x];
 }
 
 // ---------------------------------------------------------------------------------
 // mixture: total = scale * sum_p frac_p I_p + bg * C ; Rp = 100 sum|obs - total| / sum|obs|
-// grid (S, K), one block per (candidate, specimen)
+// grid (S, candidates), one block per (candidate, specimen), 4 points in flight per thread
 // ---------------------------------------------------------------------------------
-__global__ void k_mixture_residual(StaticDev st, BatchDev bt, int want_scaled) {
-    const int s = blockIdx.x, k = blockIdx.y;
+#define PX_RES_TPB 256
+#define PX_RES_PPT 4
+__global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, BatchDev bt, int k0, int want_scaled) {
+    const int s = blockIdx.x, k = k0 + blockIdx.y;
     const int X = st.spec_npts[s], Z = st.Z, M = bt.M;
     const long long soff = st.spec_off[s];
     const double *I = bt.intensities + (long long)k * bt.cand_stride + (long long)M * Z * soff;
-    double *scaled = bt.scaled ? bt.scaled + (long long)k * bt.cand_stride + (long long)M * Z * soff : nullptr;
+    double *scaled = (want_scaled && bt.scaled) ? bt.scaled + (long long)k * bt.cand_stride + (long long)M * Z * soff : nullptr;
     double *tot = bt.totals + ((long long)k * st.sumX + soff) * Z;
     const double *obs = st.observed + (long long)Z * soff;
     const unsigned char *sel = st.selected + soff;
@@ -1023,17 +1147,37 @@ __global__ void k_mixture_residual(StaticDev st, BatchDev bt, int want_scaled) {
     const double scale = bt.scales[k * st.S + s], bg = bt.bgshifts[k * st.S + s];
     const double *frac = bt.fractions + (long long)k * M;
     double num = 0.0;
-    for (int i = threadIdx.x; i < Z * X; i += blockDim.x) {
-        const int z = i / X, x = i - z * X;
-        double acc = 0.0;
-        for (int p = 0; p < M; ++p) {
-            const double v = __dmul_rn(__dmul_rn(frac[p], I[((long long)p * Z + z) * X + x]), scale);
-            if (want_scaled && scaled) scaled[((long long)p * Z + z) * X + x] = v;
-            acc = __dadd_rn(acc, v);
+    const int n = Z * X;
+    for (int z = 0; z < Z; ++z) {
+        const double *Iz = I + (long long)z * X;
+        double *Sz = scaled ? scaled + (long long)z * X : nullptr;
+        const long long pstride = (long long)Z * X;                   // phase stride inside [M][Z][X]
+        for (int x0 = threadIdx.x; x0 < X; x0 += PX_RES_TPB * PX_RES_PPT) {
+            double acc[PX_RES_PPT];
+#pragma unroll
+            for (int u = 0; u < PX_RES_PPT; ++u) acc[u] = 0.0;
+            for (int p = 0; p < M; ++p) {
+                const double fp = frac[p];
+                const double *Ip = Iz + p * pstride;
+                double iv[PX_RES_PPT];
+#pragma unroll
+                for (int u = 0; u < PX_RES_PPT; ++u) iv[u] = (x0 + u * PX_RES_TPB < X) ? Ip[x0 + u * PX_RES_TPB] : 0.0;
+#pragma unroll
+                for (int u = 0; u < PX_RES_PPT; ++u) {
+                    const double v = __dmul_rn(__dmul_rn(fp, iv[u]), scale);
+                    if (Sz && x0 + u * PX_RES_TPB < X) Sz[p * pstride + x0 + u * PX_RES_TPB] = v;
+                    acc[u] = __dadd_rn(acc[u], v);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PX_RES_PPT; ++u) {
+                const int x = x0 + u * PX_RES_TPB;
+                if (x >= X) continue;
+                const double t = __dadd_rn(acc[u], __dmul_rn(bg, corr[x]));
+                tot[(long long)z * X + x] = t;
+                if (sel[x]) num += fabs(obs[(long long)z * X + x] - t);
+            }
         }
-        acc = __dadd_rn(acc, __dmul_rn(bg, corr[x]));
-        tot[i] = acc;
-        if (sel[x]) num += fabs(obs[i] - acc);
     }
     __shared__ double red[32];
     for (int o = 16; o > 0; o >>= 1) num += __shfl_down_sync(0xffffffffu, num, o);
@@ -1045,13 +1189,13 @@ __global__ void k_mixture_residual(StaticDev st, BatchDev bt, int want_scaled) {
         if (threadIdx.x == 0) {
             const double den = st.derived[s * 8 + 3];
             // no observations -> 0.0 (mixture.py:247-251)
-            bt.residuals[(long long)k * (st.S + 1) + 1 + s] = (Z * X > 0) ? num / den * 100.0 : 0.0;
+            bt.residuals[(long long)k * (st.S + 1) + 1 + s] = (n > 0) ? num / den * 100.0 : 0.0;
         }
     }
 }
 
-__global__ void k_mixture_mean(int K, int S, double *residuals) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_mixture_mean(int k0, int K, int S, double *residuals) {
+    const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     double *r = residuals + (long long)k * (S + 1);
     double acc = 0.0;

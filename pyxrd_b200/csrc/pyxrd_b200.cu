@@ -70,9 +70,12 @@ struct pyxrd_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device -> host copies of finished candidate chunks (pyxrd_evaluate_host)
+    cudaEvent_t chunk_ev[16] = {};
     std::string error;
     int64_t launches = 0;
     int smem_optin = 0;
+    int tune = 0;             // PYXRD_B200_TUNE: kernel-shape sweeps (development only)
     bool series_mma = true;   // PYXRD_B200_SERIES=dfma selects the CUDA-core series kernels (A/B measurements only)
 
     // static
@@ -93,7 +96,9 @@ struct pyxrd_ctx {
     DevBuf d_blob;           // all uploaded batch arrays, one allocation
     PinBuf h_blob;
     const int *jobids_dev = nullptr;   // inside d_blob
-    DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_coef, d_int, d_scaled, d_tot, d_res, d_scratch;
+    DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
+    int wl_passes = 0;       // longest wavelength list of the specimens = number of ping-pong passes
+    int jobs_per_cand = 0;
     PinBuf h_res;
     DevBuf d_leaf_a, d_leaf_b, d_leaf_c, d_sol, d_optres;
     bool have_opt = false;
@@ -163,58 +168,66 @@ int set_smem(pyxrd_ctx *ctx, K kernel, size_t bytes) {
     return 0;
 }
 
-template <int R, int G>
-int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+template <int R, int G, int PPT, int TPB>
+int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
+    static_assert((PPT - 1) * TPB <= PX_TABLE_PAD, "table padding too small");
     const size_t smem = small_smem(R, G, rc.max_ntop_cap);
-    if (set_smem(ctx, k_phase_small<R, G>, smem)) return 1;
-    dim3 grid((unsigned)rc.jobs.size(), (unsigned)((rc.max_x + PX_TPB - 1) / PX_TPB));
-    k_phase_small<R, G><<<grid, PX_TPB, smem, ctx->stream>>>(ctx->st, ctx->bt, jobs_dev);
+    if (set_smem(ctx, k_phase_small<R, G, PPT, TPB>, smem)) return 1;
+    dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + TPB * PPT - 1) / (TPB * PPT)));
+    k_phase_small<R, G, PPT, TPB><<<grid, TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
     LAUNCH_CHECK("k_phase_small");
     return 0;
 }
 
 template <int R, int G>
-int launch_staged(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+int launch_staged(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     const size_t smem = staged_smem(R, G, rc.max_ntop_cap);
     if (set_smem(ctx, k_phase_staged<R, G>, smem)) return 1;
-    dim3 grid((unsigned)rc.jobs.size(), (unsigned)((rc.max_x + PX_TPB - 1) / PX_TPB));
-    k_phase_staged<R, G><<<grid, PX_TPB, smem, ctx->stream>>>(ctx->st, ctx->bt, jobs_dev);
+    dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + PX_TPB - 1) / PX_TPB));
+    k_phase_staged<R, G><<<grid, PX_TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
     LAUNCH_CHECK("k_phase_staged");
     return 0;
 }
 
 template <int R, int G, int MTC>
-int launch_mma(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+int launch_mma(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     const size_t smem = mma_smem(R, G, rc.max_ntop_cap);
     if (set_smem(ctx, k_phase_mma<R, G, MTC>, smem)) return 1;
-    dim3 grid((unsigned)rc.jobs.size(), (unsigned)((rc.max_x + PX_TPB - 1) / PX_TPB));
-    k_phase_mma<R, G, MTC><<<grid, PX_TPB, smem, ctx->stream>>>(ctx->st, ctx->bt, jobs_dev);
+    dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + PX_TPB - 1) / PX_TPB));
+    k_phase_mma<R, G, MTC><<<grid, PX_TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
     LAUNCH_CHECK("k_phase_mma");
     return 0;
 }
 
-int launch_generic(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
+int launch_generic(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     const size_t smem = generic_smem(rc.rank, rc.G, rc.max_ntop_cap);
     if (set_smem(ctx, k_phase_generic, smem)) return 1;
-    dim3 grid((unsigned)rc.jobs.size(), (unsigned)((rc.max_x + PX_GEN_TPB - 1) / PX_GEN_TPB));
-    k_phase_generic<<<grid, PX_GEN_TPB, smem, ctx->stream>>>(ctx->st, ctx->bt, jobs_dev);
+    dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + PX_GEN_TPB - 1) / PX_GEN_TPB));
+    k_phase_generic<<<grid, PX_GEN_TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
     LAUNCH_CHECK("k_phase_generic");
     return 0;
 }
 
-int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev) {
-#define SMALL(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_>(ctx, rc, jobs_dev)
-#define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev)
-    SMALL(1, 1); SMALL(2, 2); SMALL(3, 3); SMALL(4, 4); SMALL(5, 5); SMALL(6, 6);   // R0 / R1
-    SMALL(2, 1); SMALL(3, 1); SMALL(4, 1);
-#define MMA(R_, G_, MTC_) if (rc.rank == R_ && rc.G == G_ && ctx->series_mma) return launch_mma<R_, G_, MTC_>(ctx, rc, jobs_dev)
+int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
+#define SMALL(R_, G_, PPT_, TPB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_>(ctx, rc, jobs_dev, njobs, bt)
+#define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev, njobs, bt)
+    if (ctx->tune == 1) { SMALL(1, 1, 1, 128); SMALL(2, 2, 1, 128); }
+    if (ctx->tune == 2) { SMALL(1, 1, 2, 128); SMALL(2, 2, 2, 128); }
+    if (ctx->tune == 3) { SMALL(1, 1, 2, 64); SMALL(2, 2, 2, 64); }
+    if (ctx->tune == 4) { SMALL(1, 1, 4, 128); SMALL(2, 2, 4, 128); }
+    if (ctx->tune == 5) { SMALL(1, 1, 3, 64); SMALL(2, 2, 3, 64); }
+    if (ctx->tune == 6) { SMALL(1, 1, 4, 32); SMALL(2, 2, 4, 32); }
+    SMALL(1, 1, 4, 64); SMALL(2, 2, 4, 64); SMALL(3, 3, 2, 128); SMALL(4, 4, 2, 128);  // R0 / R1
+    SMALL(5, 5, 1, 128); SMALL(6, 6, 1, 128);
+    SMALL(2, 1, 4, 64); SMALL(3, 1, 2, 128); SMALL(4, 1, 2, 128);
+#define MMA(R_, G_, MTC_) if (rc.rank == R_ && rc.G == G_ && ctx->series_mma) return launch_mma<R_, G_, MTC_>(ctx, rc, jobs_dev, njobs, bt)
     MMA(8, 2, 4); MMA(16, 2, 2); MMA(16, 4, 2); MMA(27, 3, 1);                        // FP64 tensor cores
-    SMALL(4, 2); SMALL(8, 2); SMALL(9, 3);                                            // R2G2, R3G2, R2G3
+    SMALL(4, 2, 2, 128); SMALL(8, 2, 1, 128); SMALL(9, 3, 1, 128);                                            // R2G2, R3G2, R2G3
     STAGED(16, 2); STAGED(16, 4); STAGED(27, 3);
 #undef SMALL
 #undef STAGED
 #undef MMA
-    return launch_generic(ctx, rc, jobs_dev);
+    return launch_generic(ctx, rc, jobs_dev, njobs, bt);
 }
 
 static int read_back(pyxrd_ctx *ctx, const void *dev, double *out, int64_t count, int64_t have, const char *what) {
@@ -256,9 +269,12 @@ int pyxrd_create(int device, pyxrd_ctx **out) {
         return 3;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *e = getenv("PYXRD_B200_TUNE")) ctx->tune = atoi(e);
     if (const char *e = getenv("PYXRD_B200_SERIES")) ctx->series_mma = strcmp(e, "dfma") != 0;
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
     *out = ctx;
     return 0;
 }
@@ -271,11 +287,13 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob,
                       &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
-                      &ctx->d_res, &ctx->d_scratch, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
+                      &ctx->d_res, &ctx->d_int2, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
     ctx->h_res.release();
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 16; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -339,11 +357,17 @@ int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
     // pageable sources cudaMemcpyAsync returns after staging, so the caller may free them now
     CK(ctx->d_derived.ensure(sizeof(double) * 8 * S));
     CK(cudaMemsetAsync(ctx->d_derived.ptr, 0, sizeof(double) * 8 * S, ctx->stream));
-    CK(ctx->d_sin.ensure(sizeof(double) * std::max<long long>(sumX, 1)));
-    CK(ctx->d_stl.ensure(sizeof(double) * std::max<long long>(sumX, 1)));
-    CK(ctx->d_c2t2.ensure(sizeof(double) * std::max<long long>(sumX, 1)));
-    CK(ctx->d_corr.ensure(sizeof(double) * std::max<long long>(sumX, 1)));
-    CK(ctx->d_asf.ensure(sizeof(double) * std::max<long long>(sumX * std::max(T, 1), 1)));
+    // every per-point table carries PX_TABLE_PAD zeroed doubles of slack: threads of k_phase_small
+    // that own several points load (and discard) values past the end of the last pattern
+    {
+        DevBuf *tabs[] = {&ctx->d_sin, &ctx->d_stl, &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf};
+        const long long counts[] = {sumX, sumX, sumX, sumX, sumX * std::max(T, 1)};
+        for (int i = 0; i < 5; ++i) {
+            const size_t bytes = sizeof(double) * (size_t)(counts[i] + PX_TABLE_PAD);
+            CK(tabs[i]->ensure(bytes));
+            CK(cudaMemsetAsync(tabs[i]->ptr, 0, bytes, ctx->stream));
+        }
+    }
 
     StaticDev &st = ctx->st;
     st.S = S; st.T = T; st.Z = Z; st.maxX = maxX; st.sumX = sumX;
@@ -504,6 +528,11 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     ctx->int_count = (int64_t)K * cand_stride;
     ctx->tot_count = (int64_t)K * Z * st.sumX;
     CK(ctx->d_int.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
+    ctx->wl_passes = 0;
+    for (int s = 0; s < S; ++s)
+        if (ctx->h_npts[s] > 0) ctx->wl_passes = std::max(ctx->wl_passes, ctx->h_nwl[s]);
+    if (ctx->wl_passes > 0) CK(ctx->d_int2.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
+    ctx->jobs_per_cand = S * Z * M;
     CK(ctx->d_tot.ensure(sizeof(double) * std::max<int64_t>(ctx->tot_count, 1)));
     CK(ctx->d_res.ensure(sizeof(double) * (size_t)K * (S + 1)));
     CK(ctx->h_res.ensure(sizeof(double) * (size_t)K * (S + 1)));
@@ -582,36 +611,78 @@ int pyxrd_set_intensities(pyxrd_ctx *ctx, const double *intensities, int64_t cou
     return 0;
 }
 
+}  // extern "C"
+
+namespace {
+
+// phase patterns + wavelength passes of the candidates [k0, k1) on ctx->stream.  The phase kernels
+// write the buffer from which ctx->wl_passes out-of-place passes end in d_int.
+int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
+    const StaticDev &st = ctx->st;
+    double *bufs[2] = {ctx->d_int.as<double>(), ctx->d_int2.as<double>()};
+    int cur = ctx->wl_passes & 1;                      // passes alternate cur -> 1 - cur and must end in 0
+    BatchDev bt = ctx->bt;
+    bt.intensities = bufs[cur];
+    const long long j0 = (long long)k0 * ctx->jobs_per_cand, j1 = (long long)k1 * ctx->jobs_per_cand;
+    // None phases / invalid probabilities / empty specimens stay zero (specimen.py:63, phases.py:109-111)
+    size_t listed = 0;
+    for (const RankClass &rc : ctx->classes) listed += rc.jobs.size();
+    if (listed != (size_t)ctx->NJ && bt.cand_stride > 0)
+        CK(cudaMemsetAsync(bt.intensities + (long long)k0 * bt.cand_stride, 0,
+                           sizeof(double) * (size_t)(k1 - k0) * bt.cand_stride, ctx->stream));
+    if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (const RankClass &rc : ctx->classes) {
+        const size_t a = std::lower_bound(rc.jobs.begin(), rc.jobs.end(), (int)j0) - rc.jobs.begin();
+        const size_t b = std::lower_bound(rc.jobs.begin(), rc.jobs.end(), (int)j1) - rc.jobs.begin();
+        if (b > a && launch_class(ctx, rc, ctx->jobids_dev + rc.first + a, b - a, bt)) return 1;
+    }
+    if (timed) {
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    }
+    if (j1 > j0 && st.maxX > 0)
+        for (int pass = 0; pass < ctx->wl_passes; ++pass) {
+            dim3 grid((unsigned)((st.maxX + PX_WL_TPB * PX_WL_PPT - 1) / (PX_WL_TPB * PX_WL_PPT)), (unsigned)(j1 - j0));
+            k_wavelength_pass<<<grid, PX_WL_TPB, 0, ctx->stream>>>(st, ctx->bt, (int)j0, pass, bufs[cur], bufs[1 - cur]);
+            LAUNCH_CHECK("k_wavelength_pass");
+            cur = 1 - cur;
+        }
+    if (timed) {
+        CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+        ctx->ev_set[0] = ctx->ev_set[1] = true;
+    }
+    return 0;
+}
+
+int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed) {
+    BatchDev bt = ctx->bt;
+    if (want_scaled) {
+        CK(ctx->d_scaled.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
+        bt.scaled = ctx->d_scaled.as<double>();
+    }
+    if (timed) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (k1 > k0) {
+        dim3 grid(ctx->st.S, k1 - k0);
+        k_mixture_residual<<<grid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled);
+        LAUNCH_CHECK("k_mixture_residual");
+        k_mixture_mean<<<(k1 - k0 + 127) / 128, 128, 0, ctx->stream>>>(k0, k1, ctx->st.S, bt.residuals);
+        LAUNCH_CHECK("k_mixture_mean");
+    }
+    if (timed) {
+        CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+        ctx->ev_set[2] = true;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
 int pyxrd_compute_intensities(pyxrd_ctx *ctx) {
     if (!ctx || !ctx->have_batch) return fail(ctx, "compute_intensities: no resident batch");
     CK(cudaSetDevice(ctx->device));
-    const StaticDev &st = ctx->st;
-    // None phases / invalid probabilities / empty specimens stay zero (specimen.py:63, phases.py:109-111)
-    bool any_zero = false;
-    size_t listed = 0;
-    for (const RankClass &rc : ctx->classes) listed += rc.jobs.size();
-    any_zero = listed != (size_t)ctx->NJ;
-    if (any_zero && ctx->int_count > 0)
-        CK(cudaMemsetAsync(ctx->d_int.ptr, 0, sizeof(double) * (size_t)ctx->int_count, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    for (const RankClass &rc : ctx->classes)
-        if (!rc.jobs.empty() && launch_class(ctx, rc, ctx->jobids_dev + rc.first)) return 1;
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    // wavelength distribution, one block per pattern
-    bool any_wl = false;
-    for (int s = 0; s < st.S; ++s) any_wl = any_wl || (ctx->h_nwl[s] > 0 && ctx->h_npts[s] > 0);
-    if (any_wl && ctx->NJ > 0) {
-        const size_t smem = sizeof(double) * 2 * (size_t)st.maxX;
-        const int use_global = smem > (size_t)ctx->smem_optin;
-        if (use_global) CK(ctx->d_scratch.ensure(sizeof(double) * 2 * (size_t)st.maxX * ctx->NJ));
-        else if (set_smem(ctx, k_wavelength, smem)) return 1;
-        k_wavelength<<<ctx->NJ, 256, use_global ? 0 : smem, ctx->stream>>>(st, ctx->bt, ctx->NJ, use_global,
-                                                                          ctx->d_scratch.as<double>());
-        LAUNCH_CHECK("k_wavelength");
-    }
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    ctx->ev_set[0] = ctx->ev_set[1] = true;
+    if (intensities_range(ctx, 0, ctx->bt.K, true)) return 1;
     ctx->have_intensities = true;
     return 0;
 }
@@ -619,20 +690,7 @@ int pyxrd_compute_intensities(pyxrd_ctx *ctx) {
 int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled) {
     if (!ctx || !ctx->have_batch || !ctx->have_intensities) return fail(ctx, "compute_residuals: intensities not computed");
     CK(cudaSetDevice(ctx->device));
-    BatchDev bt = ctx->bt;
-    if (want_scaled) {
-        CK(ctx->d_scaled.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
-        bt.scaled = ctx->d_scaled.as<double>();
-    }
-    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    dim3 grid(ctx->st.S, bt.K);
-    k_mixture_residual<<<grid, 256, 0, ctx->stream>>>(ctx->st, bt, want_scaled);
-    LAUNCH_CHECK("k_mixture_residual");
-    k_mixture_mean<<<(bt.K + 127) / 128, 128, 0, ctx->stream>>>(bt.K, ctx->st.S, bt.residuals);
-    LAUNCH_CHECK("k_mixture_mean");
-    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
-    ctx->ev_set[2] = true;
-    return 0;
+    return residuals_range(ctx, 0, ctx->bt.K, want_scaled, true);
 }
 
 int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newton_iterations) {
@@ -718,13 +776,29 @@ int pyxrd_device_buffers(pyxrd_ctx *ctx, double **intensities_dev, double **tota
 
 int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *residuals_out, double *intensities_out) {
     if (pyxrd_set_batch(ctx, desc)) return 1;
-    if (pyxrd_compute_intensities(ctx)) return 1;
-    if (pyxrd_compute_residuals(ctx, 0)) return 1;
-    const size_t nres = (size_t)ctx->bt.K * (ctx->st.S + 1);
+    const int K = ctx->bt.K;
+    const size_t nres = (size_t)K * (ctx->st.S + 1);
+    // candidate chunks: while chunk c + 1 is computed, the patterns of chunk c travel to the host on
+    // the copy stream (the patterns are the bulk of the result: 8 B per point against ~2 kflop)
+    int nchunks = 1;
+    if (intensities_out && K >= 16) nchunks = std::min(8, K / 8);
+    if (const char *e = getenv("PYXRD_B200_CHUNKS")) nchunks = std::max(1, std::min(16, std::min(K, atoi(e))));
+    for (int c = 0; c < nchunks; ++c) {
+        const int k0 = (int)((long long)K * c / nchunks), k1 = (int)((long long)K * (c + 1) / nchunks);
+        if (intensities_range(ctx, k0, k1, nchunks == 1)) return 1;
+        if (residuals_range(ctx, k0, k1, 0, nchunks == 1)) return 1;
+        if (intensities_out && ctx->bt.cand_stride > 0) {
+            CK(cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[c], 0));
+            CK(cudaMemcpyAsync(intensities_out + (long long)k0 * ctx->bt.cand_stride,
+                               ctx->d_int.as<double>() + (long long)k0 * ctx->bt.cand_stride,
+                               sizeof(double) * (size_t)(k1 - k0) * ctx->bt.cand_stride, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+    }
+    ctx->have_intensities = true;
     CK(cudaMemcpyAsync(ctx->h_res.ptr, ctx->d_res.ptr, sizeof(double) * nres, cudaMemcpyDeviceToHost, ctx->stream));
-    if (intensities_out)
-        CK(cudaMemcpyAsync(intensities_out, ctx->d_int.ptr, sizeof(double) * (size_t)ctx->int_count, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     memcpy(residuals_out, ctx->h_res.ptr, sizeof(double) * nres);
     return 0;
 }
