@@ -382,7 +382,7 @@ def run_b200(args, rank, world, local_rank):
                                      "candidates_per_gpu": trials["K"]},
                           "stage_ms": {"phase": trials["stage"]["phase"], "wavelength": trials["stage"]["wavelength"],
                                        "optimiser": trials["stage"]["residual"]},
-                          "optimiser": "device majorise-minimise (pyxrd_optimize), 32 reweightings x <=4 Newton steps; "
+                          "optimiser": "device majorise-minimise (pyxrd_optimize), 32 reweightings x <=2 Newton steps; "
                                        "contract: <= reference L-BFGS-B optimum * (1 + 5e-3)",
                           "gpu_launches": trials["launches"],
                           "pattern_pts_per_s": trials["points"] * world / (trials["dev_ms"] * 1e-3)}

@@ -1247,6 +1247,8 @@ struct OptParams {
     double delta0, shrink, delta_min;   // weight floor relative to mean |obs|: delta0 * shrink^it >= delta_min
 };
 
+#define PX_OPT_LDA 29      // row stride (doubles) of the d x d work matrices: odd, so a column is spread over all banks
+
 struct OptSmem {
     double v[PX_OPT_MAXD];
     double lo[PX_OPT_MAXD];
@@ -1255,132 +1257,166 @@ struct OptSmem {
     double wgt[PX_OPT_MAXS];        // 100 / (S * sum|obs|)
     double mean_obs[PX_OPT_MAXS];
     double obj[PX_OPT_MAXS];        // sum |r| at the solution the last pass was taken at
-    double H[PX_OPT_MAXD * PX_OPT_MAXD];
-    double A[PX_OPT_MAXD * PX_OPT_MAXD];
-    double g[PX_OPT_MAXD], dx[PX_OPT_MAXD], vn[PX_OPT_MAXD], t[PX_OPT_MAXMB];
+    double H[PX_OPT_MAXD * PX_OPT_LDA];
+    double A[PX_OPT_MAXD * PX_OPT_LDA];
+    double g[PX_OPT_MAXD], vn[PX_OPT_MAXD], invd[PX_OPT_MAXD];
     int idx[PX_OPT_MAXD];
     double red[PX_OPT_TPB / 32][PX_OPT_MAXMB * (PX_OPT_MAXMB + 1) / 2 + PX_OPT_MAXMB + 1];
 };
 
+__device__ __forceinline__ double opt_warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// The small bilinear problem is solved by warp 0 as a team: lane p owns fraction p / row p of the
+// work matrices.  Every function below is called by all 32 lanes and returns warp-uniform values.
+
+// per-specimen quadratic forms f^T B f, B[:,M]^T f, c^T f at v; lane p < M also gets t = (B f)[p]
+__device__ __forceinline__ void opt_forms(const OptSmem &sm, const double *v, int s, int M, int MB, int lane,
+                                          double &t, double &fBf, double &Bcf, double &cf) {
+    const double *B = sm.B[s], *c = sm.c[s];
+    t = 0.0;
+    double a = 0.0, b = 0.0, d = 0.0;
+    if (lane < M) {
+        for (int q = 0; q < M; ++q) t = fma(B[lane * MB + q], v[q], t);
+        a = v[lane] * t;
+        b = B[lane * MB + M] * v[lane];
+        d = c[lane] * v[lane];
+    }
+    fBf = opt_warp_sum(a);
+    Bcf = opt_warp_sum(b);
+    cf = opt_warp_sum(d);
+}
+
 // majoriser value (up to a constant) at v
-__device__ double opt_q(const OptSmem &sm, const double *v, int M, int S, int MB) {
+__device__ double opt_q(const OptSmem &sm, const double *v, int M, int S, int MB, int lane) {
     double q = 0.0;
     for (int s = 0; s < S; ++s) {
-        const double *B = sm.B[s], *c = sm.c[s];
+        double t, fBf, Bcf, cf;
+        opt_forms(sm, v, s, M, MB, lane, t, fBf, Bcf, cf);
         const double r = v[M + s], b = v[M + S + s];
-        double fBf = 0.0, Bcf = 0.0, cf = 0.0;
-        for (int p = 0; p < M; ++p) {
-            double t = 0.0;
-            for (int qn = 0; qn < M; ++qn) t = fma(B[p * MB + qn], v[qn], t);
-            fBf = fma(v[p], t, fBf);
-            Bcf = fma(B[p * MB + M], v[p], Bcf);
-            cf = fma(c[p], v[p], cf);
-        }
-        q += sm.wgt[s] * (r * r * fBf + 2.0 * r * b * Bcf + B[M * MB + M] * b * b - 2.0 * r * cf - 2.0 * c[M] * b);
+        q += sm.wgt[s] * (r * r * fBf + 2.0 * r * b * Bcf + sm.B[s][M * MB + M] * b * b - 2.0 * r * cf - 2.0 * sm.c[s][M] * b);
     }
     return q;
 }
 
-// in-place Cholesky solve of the n x n system A x = rhs (A row-major, stride n); false if not positive definite
-__device__ bool opt_chol_solve(double *A, double *x, int n) {
+// Cholesky factor of the n x n matrix A (lower triangle, in place; lane i owns row i), reciprocal
+// diagonal in invd; false if A is not positive definite
+__device__ bool opt_chol(double *A, double *invd, int n, int lane) {
     for (int j = 0; j < n; ++j) {
-        double d = A[j * n + j];
-        for (int k = 0; k < j; ++k) d = fma(-A[j * n + k], A[j * n + k], d);
-        if (!(d > 0.0)) return false;
-        d = sqrt(d);
-        A[j * n + j] = d;
-        const double inv = 1.0 / d;
-        for (int i = j + 1; i < n; ++i) {
-            double a = A[i * n + j];
-            for (int k = 0; k < j; ++k) a = fma(-A[i * n + k], A[j * n + k], a);
-            A[i * n + j] = a * inv;
+        double a = 0.0;
+        if (lane >= j && lane < n) {
+            a = A[lane * PX_OPT_LDA + j];
+            for (int k = 0; k < j; ++k) a = fma(-A[lane * PX_OPT_LDA + k], A[j * PX_OPT_LDA + k], a);
         }
-    }
-    for (int i = 0; i < n; ++i) {
-        double a = x[i];
-        for (int k = 0; k < i; ++k) a = fma(-A[i * n + k], x[k], a);
-        x[i] = a / A[i * n + i];
-    }
-    for (int i = n - 1; i >= 0; --i) {
-        double a = x[i];
-        for (int k = i + 1; k < n; ++k) a = fma(-A[k * n + i], x[k], a);
-        x[i] = a / A[i * n + i];
+        const double dj = __shfl_sync(0xffffffffu, a, j);
+        if (!(dj > 0.0)) return false;
+        const double sd = sqrt(dj), inv = 1.0 / sd;
+        if (lane == j) { A[j * PX_OPT_LDA + j] = sd; invd[j] = inv; }
+        else if (lane > j && lane < n) A[lane * PX_OPT_LDA + j] = a * inv;
+        __syncwarp();
     }
     return true;
 }
 
-// projected LM / Newton on the majoriser (thread 0 only)
-__device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, int lm_iters, int refine_bg) {
+// solves L L^T x = y; lane i passes y_i and receives x_i
+__device__ double opt_chol_solve(const double *A, const double *invd, int n, int lane, double y) {
+    for (int j = 0; j < n; ++j) {
+        const double zj = __shfl_sync(0xffffffffu, y, j) * invd[j];
+        if (lane == j) y = zj;
+        else if (lane > j && lane < n) y = fma(-A[lane * PX_OPT_LDA + j], zj, y);
+    }
+    for (int j = n - 1; j >= 0; --j) {
+        const double xj = __shfl_sync(0xffffffffu, y, j) * invd[j];
+        if (lane == j) y = xj;
+        else if (lane < j) y = fma(-A[j * PX_OPT_LDA + lane], xj, y);
+    }
+    return y;
+}
+
+// projected Levenberg-Marquardt / Newton on the majoriser (warp 0)
+__device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, int lm_iters, int refine_bg, int lane) {
     const int d = M + 2 * S;
     double lam = 1e-3;
+    double *v = sm.v, *g = sm.g, *H = sm.H;
     for (int it = 0; it < lm_iters; ++it) {
-        double *v = sm.v, *g = sm.g, *H = sm.H;
-        for (int i = 0; i < d; ++i) g[i] = 0.0;
-        for (int i = 0; i < d * d; ++i) H[i] = 0.0;
+        for (int i = lane; i < d * PX_OPT_LDA; i += 32) H[i] = 0.0;
+        __syncwarp();
+        double gp = 0.0;
         for (int s = 0; s < S; ++s) {
             const double *B = sm.B[s], *c = sm.c[s];
             const double w = sm.wgt[s], r = v[M + s], b = v[M + S + s];
-            double fBf = 0.0, Bcf = 0.0, cf = 0.0;
-            for (int p = 0; p < M; ++p) {
-                double t = 0.0;
-                for (int q = 0; q < M; ++q) t = fma(B[p * MB + q], v[q], t);
-                sm.t[p] = t;
-                fBf = fma(v[p], t, fBf);
-                Bcf = fma(B[p * MB + M], v[p], Bcf);
-                cf = fma(c[p], v[p], cf);
-            }
+            double t, fBf, Bcf, cf;
+            opt_forms(sm, v, s, M, MB, lane, t, fBf, Bcf, cf);
             const int ir = M + s, ib = M + S + s;
-            for (int p = 0; p < M; ++p) {
-                g[p] += w * (2.0 * r * r * sm.t[p] + 2.0 * r * b * B[p * MB + M] - 2.0 * r * c[p]);
-                for (int q = 0; q < M; ++q) H[p * d + q] += 2.0 * w * r * r * B[p * MB + q];
-                const double hfr = w * (4.0 * r * sm.t[p] + 2.0 * b * B[p * MB + M] - 2.0 * c[p]);
-                H[p * d + ir] = hfr;
-                H[ir * d + p] = hfr;
+            if (lane < M) {
+                const int p = lane;
+                gp += w * (2.0 * r * r * t + 2.0 * r * b * B[p * MB + M] - 2.0 * r * c[p]);
+                for (int q = 0; q < M; ++q) H[p * PX_OPT_LDA + q] += 2.0 * w * r * r * B[p * MB + q];
+                const double hfr = w * (4.0 * r * t + 2.0 * b * B[p * MB + M] - 2.0 * c[p]);
+                H[p * PX_OPT_LDA + ir] = hfr;
+                H[ir * PX_OPT_LDA + p] = hfr;
                 const double hfb = 2.0 * w * r * B[p * MB + M];
-                H[p * d + ib] = hfb;
-                H[ib * d + p] = hfb;
+                H[p * PX_OPT_LDA + ib] = hfb;
+                H[ib * PX_OPT_LDA + p] = hfb;
             }
-            g[ir] = w * (2.0 * r * fBf + 2.0 * b * Bcf - 2.0 * cf);
-            g[ib] = w * (2.0 * r * Bcf + 2.0 * B[M * MB + M] * b - 2.0 * c[M]);
-            H[ir * d + ir] = 2.0 * w * fBf;
-            H[ir * d + ib] = H[ib * d + ir] = 2.0 * w * Bcf;
-            H[ib * d + ib] = 2.0 * w * B[M * MB + M];
+            if (lane == 0) {
+                g[ir] = w * (2.0 * r * fBf + 2.0 * b * Bcf - 2.0 * cf);
+                g[ib] = w * (2.0 * r * Bcf + 2.0 * B[M * MB + M] * b - 2.0 * c[M]);
+                H[ir * PX_OPT_LDA + ir] = 2.0 * w * fBf;
+                H[ir * PX_OPT_LDA + ib] = H[ib * PX_OPT_LDA + ir] = 2.0 * w * Bcf;
+                H[ib * PX_OPT_LDA + ib] = 2.0 * w * B[M * MB + M];
+            }
         }
-        int n = 0;
-        for (int i = 0; i < d; ++i) {
-            const bool fixed_bg = (!refine_bg && i >= M + S);
-            const bool at_bound = (v[i] <= sm.lo[i] && g[i] > 0.0);
-            if (!fixed_bg && !at_bound && H[i * d + i] > 0.0) sm.idx[n++] = i;
+        if (lane < M) g[lane] = gp;
+        __syncwarp();
+        // free variables: not a fixed background, not held at its bound by the gradient
+        bool free_i = false;
+        if (lane < d) {
+            const bool fixed_bg = (!refine_bg && lane >= M + S);
+            const bool at_bound = (v[lane] <= sm.lo[lane] && g[lane] > 0.0);
+            free_i = !fixed_bg && !at_bound && H[lane * PX_OPT_LDA + lane] > 0.0;
         }
+        const unsigned mask = __ballot_sync(0xffffffffu, free_i);
+        const int n = __popc(mask);
+        if (free_i) sm.idx[__popc(mask & ((1u << lane) - 1u))] = lane;
+        __syncwarp();
         if (n == 0) break;
-        const double qv = opt_q(sm, v, M, S, MB);
+        const double qv = opt_q(sm, v, M, S, MB, lane);
         bool accepted = false;
         double rel = 0.0;
         for (int tr = 0; tr < 8 && !accepted; ++tr) {
-            for (int a = 0; a < n; ++a) {
-                for (int bcol = 0; bcol < n; ++bcol) sm.A[a * n + bcol] = H[sm.idx[a] * d + sm.idx[bcol]];
-                sm.A[a * n + a] += lam * fabs(sm.A[a * n + a]) + 1e-300;
-                sm.dx[a] = -g[sm.idx[a]];
+            if (lane < n) {
+                const int ia = sm.idx[lane];
+                for (int bcol = 0; bcol < n; ++bcol) sm.A[lane * PX_OPT_LDA + bcol] = H[ia * PX_OPT_LDA + sm.idx[bcol]];
+                sm.A[lane * PX_OPT_LDA + lane] += lam * fabs(sm.A[lane * PX_OPT_LDA + lane]) + 1e-300;
             }
-            if (!opt_chol_solve(sm.A, sm.dx, n)) { lam *= 10.0; continue; }
-            for (int i = 0; i < d; ++i) sm.vn[i] = v[i];
-            for (int a = 0; a < n; ++a) sm.vn[sm.idx[a]] = fmax(sm.lo[sm.idx[a]], v[sm.idx[a]] + sm.dx[a]);
-            const double qn = opt_q(sm, sm.vn, M, S, MB);
+            __syncwarp();
+            if (!opt_chol(sm.A, sm.invd, n, lane)) { lam *= 10.0; __syncwarp(); continue; }
+            const double dx = opt_chol_solve(sm.A, sm.invd, n, lane, lane < n ? -g[sm.idx[lane]] : 0.0);
+            if (lane < d) sm.vn[lane] = v[lane];
+            __syncwarp();
+            if (lane < n) sm.vn[sm.idx[lane]] = fmax(sm.lo[sm.idx[lane]], v[sm.idx[lane]] + dx);
+            __syncwarp();
+            const double qn = opt_q(sm, sm.vn, M, S, MB, lane);
             if (qn < qv) {
                 accepted = true;
                 rel = (qv - qn) / fmax(fabs(qv), 1e-300);
-                for (int i = 0; i < d; ++i) v[i] = sm.vn[i];
+                if (lane < d) v[lane] = sm.vn[lane];
                 lam = fmax(lam * 0.2, 1e-12);
             } else {
                 lam *= 5.0;
             }
+            __syncwarp();
         }
         if (!accepted || rel < 1e-13) break;
     }
 }
 
 template <int MB>
-__global__ void __launch_bounds__(PX_OPT_TPB) k_mixture_optimize(StaticDev st, BatchDev bt, OptParams op,
+__global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st, BatchDev bt, OptParams op,
                                                                  double *solutions, double *opt_residuals) {
     constexpr int M = MB - 1;
     constexpr int NG = MB * (MB + 1) / 2;       // upper triangle of the Gram matrix
@@ -1416,29 +1452,40 @@ __global__ void __launch_bounds__(PX_OPT_TPB) k_mixture_optimize(StaticDev st, B
 #pragma unroll
             for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
             const double delta = delta_rel * sm.mean_obs[s];
-            for (int i = tid; i < Z * X; i += PX_OPT_TPB) {
-                const int z = i / X, x = i - z * X;
-                if (!sel[x]) continue;
-                double phi[MB];
+            // two points in flight per thread: the loads of both are issued before the arithmetic
+            for (int z = 0; z < Z; ++z)
+                for (int x0 = tid; x0 < X; x0 += 2 * PX_OPT_TPB) {
+                    double phi[2][MB], o[2];
+                    bool on[2];
 #pragma unroll
-                for (int p = 0; p < M; ++p) phi[p] = I[((long long)p * Z + z) * X + x];
-                phi[M] = corr[x];
-                const double o = obs[i];
-                double calc = 0.0;
+                    for (int u = 0; u < 2; ++u) {
+                        const int x = x0 + u * PX_OPT_TPB;
+                        on[u] = x < X && sel[x];
+                        const int xc = x < X ? x : x0;
 #pragma unroll
-                for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[p], calc);
-                const double r = o - calc;
-                const double w = 1.0 / fmax(fabs(r), delta);
-                acc[NACC - 1] += fabs(r);
-                int e = 0;
+                        for (int p = 0; p < M; ++p) phi[u][p] = I[((long long)p * Z + z) * X + xc];
+                        phi[u][M] = corr[xc];
+                        o[u] = obs[(long long)z * X + xc];
+                    }
 #pragma unroll
-                for (int p = 0; p < MB; ++p) {
-                    const double wp = w * phi[p];
-                    acc[NG + p] = fma(wp, o, acc[NG + p]);
+                    for (int u = 0; u < 2; ++u) {
+                        if (!on[u]) continue;
+                        double calc = 0.0;
 #pragma unroll
-                    for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[q], acc[e]);
+                        for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[u][p], calc);
+                        const double r = o[u] - calc;
+                        const double w = 1.0 / fmax(fabs(r), delta);
+                        acc[NACC - 1] += fabs(r);
+                        int e = 0;
+#pragma unroll
+                        for (int p = 0; p < MB; ++p) {
+                            const double wp = w * phi[u][p];
+                            acc[NG + p] = fma(wp, o[u], acc[NG + p]);
+#pragma unroll
+                            for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[u][q], acc[e]);
+                        }
+                    }
                 }
-            }
             // block reduction of NACC (+ count) values
             const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -1467,7 +1514,7 @@ __global__ void __launch_bounds__(PX_OPT_TPB) k_mixture_optimize(StaticDev st, B
             __syncthreads();
         }
         if (it == op.outer) break;                 // the last pass only evaluates the objective
-        if (tid == 0) opt_inner_solve(sm, M, S, MB, op.lm_iters, op.refine_bg);
+        if (tid < 32) opt_inner_solve(sm, M, S, MB, op.lm_iters, op.refine_bg, tid);
         __syncthreads();
     }
     if (tid == 0) {

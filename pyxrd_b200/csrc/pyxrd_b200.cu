@@ -704,7 +704,7 @@ int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newt
     CK(ctx->d_optres.ensure(sizeof(double) * (size_t)K * (S + 1)));
     OptParams op;
     op.outer = outer_iterations > 0 ? outer_iterations : 32;
-    op.lm_iters = newton_iterations > 0 ? newton_iterations : 4;
+    op.lm_iters = newton_iterations > 0 ? newton_iterations : 2;
     op.refine_bg = refine_bg ? 1 : 0;
     op.reserved = 0;
     op.delta0 = 1e-2;
