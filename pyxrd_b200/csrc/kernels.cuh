@@ -77,7 +77,7 @@ struct StaticDev {
     const long long *spec_off;   // [S+1]
     const double *gonio;         // [S][12]
     const double *derived;       // [S][8]: pol, S_soller, S_soller^2, obs_den
-    const double *theta, *sin_t, *stl, *c2t2, *corr;   // [sumX]
+    const double *theta, *sin_t, *inv_sin, *stl, *c2t2, *corr;   // [sumX]
     const double *asf;           // [T][sumX]
     const int *spec_nwl;         // [S]
     const int *wl_first;         // [S] first entry in wl_fraction
@@ -134,7 +134,7 @@ __global__ void k_specimen_derived(int S, const double *gonio, double *derived) 
     derived[s * 8 + 4] = g[9] / __dmul_rn(g[10], tan(div * (PX_PI / 180.0)));
 }
 
-__global__ void k_specimen_tables(StaticDev st, double *sin_t, double *stl, double *c2t2, double *corr,
+__global__ void k_specimen_tables(StaticDev st, double *sin_t, double *inv_sin, double *stl, double *c2t2, double *corr,
                                   const double *stl_override) {
     const int s = blockIdx.y;
     const int X = st.spec_npts[s];
@@ -145,6 +145,7 @@ __global__ void k_specimen_tables(StaticDev st, double *sin_t, double *stl, doub
     const double th = st.theta[gx];
     const double sn = sin(th);
     sin_t[gx] = sn;
+    inv_sin[gx] = __ddiv_rn(1.0, sn);
     stl[gx] = stl_override ? stl_override[gx] : __ddiv_rn(__dmul_rn(2.0, sn), g[0]);   // 2 * sin(theta) / wavelength
     const double c2 = cos(__dmul_rn(2.0, th));
     c2t2[gx] = __dmul_rn(c2, c2);
@@ -322,6 +323,7 @@ struct PhaseSmem {          // header living at the start of dynamic shared memo
     int plane_end[PX_MAX_ATOMS];     // one past the last atom (local index) of the plane
     double2 atom_po[PX_MAX_ATOMS];   // .x = pn (0 for a None atom type), .y = bit pattern of the ASF-table offset type * sumX
     int n_atoms, pad[3];
+    double lpf_q, lpf_k1, lpf_k2, lpf_pol;   // Lorentz-polarisation constants of this (phase, specimen), see lpf_point
 };
 
 // Lorentz-polarisation factor for one point (goniometer.py:20-34)
@@ -330,6 +332,23 @@ __device__ __forceinline__ double lpf_value(double st, double c2t2, double sigma
     const double Q = Ss / ((PX_SQRT8 * st) * sig);
     const double T = erf(Q) * PX_SQRT2PI / ((2.0 * sig) * Ss) - (2.0 * st) * (1.0 - exp(-(Q * Q))) / Ss2;
     return T * (1.0 + pol * c2t2) / st;
+}
+
+// The same factor inside the phase kernels: the divisions by block-uniform quantities are
+// multiplications by reciprocals taken once per block, and 1 / sin(theta) is a static table
+// (differs from lpf_value by rounding only, ~2 ulp).
+//   Q = lpf_q / st, lpf_q = S / (sqrt8 sigma);  T = erf(Q) lpf_k1 - 2 st (1 - exp(-Q^2)) lpf_k2
+__device__ __forceinline__ void lpf_setup(PhaseSmem *ps, double sigma_star, const double *derived_s) {
+    const double sig = fmax(sigma_star, 1e-18), Ss = derived_s[1], Ss2 = derived_s[2];
+    ps->lpf_q = Ss / (PX_SQRT8 * sig);
+    ps->lpf_k1 = PX_SQRT2PI / ((2.0 * sig) * Ss);
+    ps->lpf_k2 = 1.0 / Ss2;
+    ps->lpf_pol = derived_s[0];
+}
+__device__ __forceinline__ double lpf_point(const PhaseSmem *ps, double st, double inv_st, double c2t2) {
+    const double Q = ps->lpf_q * inv_st;
+    const double T = erf(Q) * ps->lpf_k1 - (2.0 * st) * (1.0 - exp(-(Q * Q))) * ps->lpf_k2;
+    return T * (1.0 + ps->lpf_pol * c2t2) * inv_st;
 }
 
 __global__ void k_leaf_lpf(const double *theta, long long n, double sigma_star, double s1, double s2,
@@ -347,7 +366,8 @@ __global__ void k_leaf_lpf(const double *theta, long long n, double sigma_star, 
 // cooperative load of the component / atom lists of phase `pb` into shared memory.  Atoms of a
 // component that sit at the same z (several species on one crystallographic plane) share one
 // complex exponential: sum_a asf_a pn_a exp(i arg) = (sum_a asf_a pn_a) exp(i arg).
-__device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int G, PhaseSmem *ps, long long sumX) {
+__device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int G, PhaseSmem *ps, long long sumX,
+                                                 const double *derived_s) {
     const int *pi = bt.phase_i + pb * 8;
     int first_atom = 0, first_plane = 0;
     for (int c = 0; c < G; ++c) {
@@ -372,7 +392,10 @@ __device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int
         first_atom += na;
         first_plane += np;
     }
-    if (threadIdx.x == 0) ps->n_atoms = first_atom;
+    if (threadIdx.x == 0) {
+        ps->n_atoms = first_atom;
+        lpf_setup(ps, bt.phase_d[pb * 8], derived_s);
+    }
 }
 
 // one plane: f * exp(i * ((2 pi z) * stl)), f = sum of asf * pn over its atoms     (atoms.py:64)
@@ -502,13 +525,10 @@ __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, 
 }
 
 // everything after Re(a^T S b): absolute scale, LPF, machine correction (phases.py:158,81-95, specimen.py:57-62)
-__device__ __forceinline__ double finish_point(double tr, double abs_scale, int flags, double sigma_star,
-                                               const StaticDev &st, int s, long long gx) {
+__device__ __forceinline__ double finish_point(double tr, double abs_scale, int flags, const PhaseSmem *ps,
+                                               const StaticDev &st, long long gx) {
     double I = tr * abs_scale;
-    if (flags & 2) {
-        const double *d = st.derived + s * 8;
-        I = I * lpf_value(st.sin_t[gx], st.c2t2[gx], sigma_star, d[1], d[2], d[0]);
-    }
+    if (flags & 2) I = I * lpf_point(ps, st.sin_t[gx], st.inv_sin[gx], st.c2t2[gx]);
     if (flags & 4) I = I * st.corr[gx];
     return I;
 }
@@ -538,9 +558,8 @@ __global__ void __launch_bounds__(TPB) k_phase_small(StaticDev st, BatchDev bt, 
     const int ntop = (int)px[2];
     const double mean = px[0], abs_scale = px[1];
     const int flags = pi[4];
-    const double sigma_star = bt.phase_d[pb * 8];
 
-    load_phase_lists(bt, pb, G, ps, st.sumX);
+    load_phase_lists(bt, pb, G, ps, st.sumX, st.derived + s * 8);
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
@@ -578,34 +597,101 @@ __global__ void __launch_bounds__(TPB) k_phase_small(StaticDev st, BatchDev bt, 
     for (int I = 0; I < R; ++I)
 #pragma unroll
         for (int k = 0; k < PPT; ++k) { yr[I][k] = 0.0; yi[I][k] = 0.0; }
-    for (int n = ntop; n >= 1; --n) {
-        const double cn = sCoef[n];
-        double wr[R][PPT], wi[R][PPT];
+    if constexpr (R == 1) {
+        // scalar series: y = (sum_n c_n q^n) b, q = P00 phi, by Horner on the real coefficients (4 flop-pairs / term)
+        const double p00 = sP[0];
+        double qr[PPT], qi[PPT], sr[PPT], si[PPT];
 #pragma unroll
-        for (int I = 0; I < R; ++I) {                     // w = phi o (y + c_n b)
-            const int c = I / REPS;
+        for (int k = 0; k < PPT; ++k) { qr[k] = p00 * pr[0][k]; qi[k] = p00 * pim[0][k]; sr[k] = 0.0; si[k] = 0.0; }
+        for (int n = ntop; n >= 1; --n) {
+            const double cn = sCoef[n];
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                wr[I][k] = fma(pr[c][k], yr[I][k], fma(-pim[c][k], yi[I][k], cn * gr[c][k]));
-                wi[I][k] = fma(pr[c][k], yi[I][k], fma(pim[c][k], yr[I][k], cn * gi[c][k]));
+            for (int k = 0; k < PPT; ++k) {             // s <- (s + c_n) q
+                const double tr_ = sr[k] + cn;
+                const double nr = fma(tr_, qr[k], -si[k] * qi[k]);
+                si[k] = fma(tr_, qi[k], si[k] * qr[k]);
+                sr[k] = nr;
             }
         }
 #pragma unroll
-        for (int I = 0; I < R; ++I) {                     // y = P w
-            double ar[PPT], ai[PPT];
+        for (int k = 0; k < PPT; ++k) {                 // y = s conj(u)
+            yr[0][k] = sr[k] * ur[0][k] + si[k] * ui[0][k];
+            yi[0][k] = si[k] * ur[0][k] - sr[k] * ui[0][k];
+        }
+    } else if constexpr (R == 2) {
+        // 2 x 2: Cayley-Hamilton Q^2 = t Q - d Id (t = trace, d = determinant) makes the powers a
+        // three-term recurrence, summed by Clenshaw's backward recurrence B_k = c_k + t B_{k+1} - d B_{k+2}
+        // on complex SCALARS (8 flop-pairs / term instead of 20 for the vector Horner step):
+        //   sum_{n>=1} c_n Q^n = B_1 Q - d B_2 Id.
+        // |eigenvalues of Q| <= 1 (P stochastic, |phi| <= 1), so the recurrence does not amplify
+        // rounding errors; measured against an 80-bit evaluation it is as accurate as the Horner
+        // form (7e-15 relative on c2).
+        constexpr int C1 = 1 / REPS;                    // component of state 1 (0 when G == 1)
+        const double p00 = sP[0], p01 = sP[1], p10 = sP[2], p11 = sP[3];
+        double tr_[PPT], ti_[PPT], dr[PPT], di[PPT], b1r[PPT], b1i[PPT], b2r[PPT], b2i[PPT];
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
+        for (int k = 0; k < PPT; ++k) {
+            // Q[I][J] = P[I][J] phi_J
+            tr_[k] = fma(p00, pr[0][k], p11 * pr[C1][k]);
+            ti_[k] = fma(p00, pim[0][k], p11 * pim[C1][k]);
+            const double ffr = pr[0][k] * pr[C1][k] - pim[0][k] * pim[C1][k];   // phi_0 phi_1
+            const double ffi = pr[0][k] * pim[C1][k] + pim[0][k] * pr[C1][k];
+            const double dp = p00 * p11 - p01 * p10;
+            dr[k] = dp * ffr;
+            di[k] = dp * ffi;
+            b1r[k] = 0.0; b1i[k] = 0.0; b2r[k] = 0.0; b2i[k] = 0.0;
+        }
+        for (int n = ntop; n >= 1; --n) {
+            const double cn = sCoef[n];
 #pragma unroll
-            for (int J = 0; J < R; ++J) {
-                const double p = sP[I * R + J];
+            for (int k = 0; k < PPT; ++k) {
+                const double nr = fma(tr_[k], b1r[k], fma(-ti_[k], b1i[k], fma(-dr[k], b2r[k], fma(di[k], b2i[k], cn))));
+                const double ni = fma(tr_[k], b1i[k], fma(ti_[k], b1r[k], fma(-dr[k], b2i[k], -di[k] * b2r[k])));
+                b2r[k] = b1r[k]; b2i[k] = b1i[k];
+                b1r[k] = nr; b1i[k] = ni;
+            }
+        }
 #pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            // y = B_1 (Q b) - (d B_2) b, b_J = conj(u_comp(J)), (Q b)_I = sum_J P[I][J] g_J, g = phi conj(u)
+            const double e_r = dr[k] * b2r[k] - di[k] * b2i[k], e_i = dr[k] * b2i[k] + di[k] * b2r[k];
+            const double q0r = fma(p00, gr[0][k], p01 * gr[C1][k]), q0i = fma(p00, gi[0][k], p01 * gi[C1][k]);
+            const double q1r = fma(p10, gr[0][k], p11 * gr[C1][k]), q1i = fma(p10, gi[0][k], p11 * gi[C1][k]);
+            yr[0][k] = b1r[k] * q0r - b1i[k] * q0i - (e_r * ur[0][k] + e_i * ui[0][k]);
+            yi[0][k] = b1r[k] * q0i + b1i[k] * q0r - (e_i * ur[0][k] - e_r * ui[0][k]);
+            yr[1][k] = b1r[k] * q1r - b1i[k] * q1i - (e_r * ur[C1][k] + e_i * ui[C1][k]);
+            yi[1][k] = b1r[k] * q1i + b1i[k] * q1r - (e_i * ur[C1][k] - e_r * ui[C1][k]);
+        }
+    } else {
+        for (int n = ntop; n >= 1; --n) {
+            const double cn = sCoef[n];
+            double wr[R][PPT], wi[R][PPT];
+    #pragma unroll
+            for (int I = 0; I < R; ++I) {                     // w = phi o (y + c_n b)
+                const int c = I / REPS;
+    #pragma unroll
                 for (int k = 0; k < PPT; ++k) {
-                    ar[k] = fma(p, wr[J][k], ar[k]);
-                    ai[k] = fma(p, wi[J][k], ai[k]);
+                    wr[I][k] = fma(pr[c][k], yr[I][k], fma(-pim[c][k], yi[I][k], cn * gr[c][k]));
+                    wi[I][k] = fma(pr[c][k], yi[I][k], fma(pim[c][k], yr[I][k], cn * gi[c][k]));
                 }
             }
-#pragma unroll
-            for (int k = 0; k < PPT; ++k) { yr[I][k] = ar[k]; yi[I][k] = ai[k]; }
+    #pragma unroll
+            for (int I = 0; I < R; ++I) {                     // y = P w
+                double ar[PPT], ai[PPT];
+    #pragma unroll
+                for (int k = 0; k < PPT; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
+    #pragma unroll
+                for (int J = 0; J < R; ++J) {
+                    const double p = sP[I * R + J];
+    #pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        ar[k] = fma(p, wr[J][k], ar[k]);
+                        ai[k] = fma(p, wi[J][k], ai[k]);
+                    }
+                }
+    #pragma unroll
+                for (int k = 0; k < PPT; ++k) { yr[I][k] = ar[k]; yi[I][k] = ai[k]; }
+            }
         }
     }
     // Re( sum_K a_K (mean b_K + y_K) ), a_K = sum_c u_c WG[c][K], b_K = conj(u_comp(K))
@@ -629,10 +715,12 @@ __global__ void __launch_bounds__(TPB) k_phase_small(StaticDev st, BatchDev bt, 
             tr[k] += ar * sr - ai * si;
         }
     }
+    double out[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) out[k] = finish_point(tr[k], abs_scale, flags, ps, st, gx + k * TPB);   // padded tables: safe past X
 #pragma unroll
     for (int k = 0; k < PPT; ++k)
-        if (x + k * TPB < X)
-            bt.intensities[bt.job_out[job] + x + k * TPB] = finish_point(tr[k], abs_scale, flags, sigma_star, st, s, gx + k * TPB);
+        if (x + k * TPB < X) bt.intensities[bt.job_out[job] + x + k * TPB] = out[k];
 }
 
 // ---- ranks 16 / 27: w in registers, the new vector staged through shared memory ----
@@ -657,9 +745,8 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev 
     const int ntop = (int)px[2];
     const double mean = px[0], abs_scale = px[1];
     const int flags = pi[4];
-    const double sigma_star = bt.phase_d[pb * 8];
 
-    load_phase_lists(bt, pb, G, ps, st.sumX);
+    load_phase_lists(bt, pb, G, ps, st.sumX, st.derived + s * 8);
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
@@ -749,7 +836,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev 
         const double si = fma(-mean, ui[K / REPS], y.y);
         tr += ar * sr - ai * si;
     }
-    bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, sigma_star, st, s, gx);
+    bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, ps, st, gx);
 }
 
 // ---- ranks 8..32 on the FP64 tensor cores (DMMA.8x8x4) ----------------------------
@@ -816,9 +903,8 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_mma(StaticDev st, BatchDev bt,
     const int ntop = (int)px[2];
     const double mean = px[0], abs_scale = px[1];
     const int flags = pi[4];
-    const double sigma_star = bt.phase_d[pb * 8];
 
-    load_phase_lists(bt, pb, G, ps, st.sumX);
+    load_phase_lists(bt, pb, G, ps, st.sumX, st.derived + s * 8);
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
@@ -960,7 +1046,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_mma(StaticDev st, BatchDev bt,
             if ((lane >> 3) == mg + m) mytr = mine;
         }
     }
-    if (live) bt.intensities[bt.job_out[job] + x] = finish_point(mytr, abs_scale, flags, sigma_star, st, s, gx);
+    if (live) bt.intensities[bt.job_out[job] + x] = finish_point(mytr, abs_scale, flags, ps, st, gx);
 }
 
 // ---- any rank <= 64: vectors in shared memory (fallback, not tuned) --------------
@@ -985,9 +1071,8 @@ __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, Batc
     const int ntop = (int)px[2];
     const double mean = px[0], abs_scale = px[1];
     const int flags = pi[4];
-    const double sigma_star = bt.phase_d[pb * 8];
 
-    load_phase_lists(bt, pb, G, ps, st.sumX);
+    load_phase_lists(bt, pb, G, ps, st.sumX, st.derived + s * 8);
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
@@ -1047,7 +1132,7 @@ __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, Batc
         const double2 u = vu[ck * PX_GEN_TPB + t], y = vy[K * PX_GEN_TPB + t];
         tr += ar * fma(mean, u.x, y.x) - ai * fma(-mean, u.y, y.y);
     }
-    bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, sigma_star, st, s, gx);
+    bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, ps, st, gx);
 }
 
 // one component on an arbitrary stl axis (leaf: components.get_factors / atoms.get_structure_factor)

@@ -84,7 +84,7 @@ struct pyxrd_ctx {
     std::vector<int> h_npts;
     std::vector<long long> h_off;
     std::vector<int> h_nwl;
-    DevBuf d_npts, d_off, d_gonio, d_derived, d_theta, d_sin, d_stl, d_c2t2, d_corr, d_asf, d_nwl, d_wlfirst,
+    DevBuf d_npts, d_off, d_gonio, d_derived, d_theta, d_sin, d_invsin, d_stl, d_c2t2, d_corr, d_asf, d_nwl, d_wlfirst,
         d_wloff, d_wlfrac, d_wlidx, d_wlhi, d_wllo, d_obs, d_sel, d_atypes, d_stlov;
 
     // batch
@@ -283,7 +283,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_stl,
+    DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_invsin, &ctx->d_stl,
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob,
                       &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
@@ -360,9 +360,9 @@ int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
     // every per-point table carries PX_TABLE_PAD zeroed doubles of slack: threads of k_phase_small
     // that own several points load (and discard) values past the end of the last pattern
     {
-        DevBuf *tabs[] = {&ctx->d_sin, &ctx->d_stl, &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf};
-        const long long counts[] = {sumX, sumX, sumX, sumX, sumX * std::max(T, 1)};
-        for (int i = 0; i < 5; ++i) {
+        DevBuf *tabs[] = {&ctx->d_sin, &ctx->d_stl, &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_invsin};
+        const long long counts[] = {sumX, sumX, sumX, sumX, sumX * std::max(T, 1), sumX};
+        for (int i = 0; i < 6; ++i) {
             const size_t bytes = sizeof(double) * (size_t)(counts[i] + PX_TABLE_PAD);
             CK(tabs[i]->ensure(bytes));
             CK(cudaMemsetAsync(tabs[i]->ptr, 0, bytes, ctx->stream));
@@ -377,6 +377,7 @@ int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
     st.derived = ctx->d_derived.as<double>();
     st.theta = ctx->d_theta.as<double>();
     st.sin_t = ctx->d_sin.as<double>();
+    st.inv_sin = ctx->d_invsin.as<double>();
     st.stl = ctx->d_stl.as<double>();
     st.c2t2 = ctx->d_c2t2.as<double>();
     st.corr = ctx->d_corr.as<double>();
@@ -396,7 +397,7 @@ int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
     LAUNCH_CHECK("k_specimen_derived");
     if (maxX > 0) {
         dim3 grid((maxX + 255) / 256, S);
-        k_specimen_tables<<<grid, 256, 0, ctx->stream>>>(st, ctx->d_sin.as<double>(), ctx->d_stl.as<double>(),
+        k_specimen_tables<<<grid, 256, 0, ctx->stream>>>(st, ctx->d_sin.as<double>(), ctx->d_invsin.as<double>(), ctx->d_stl.as<double>(),
                                                          ctx->d_c2t2.as<double>(), ctx->d_corr.as<double>(),
                                                          d->stl_override ? ctx->d_stlov.as<double>() : nullptr);
         LAUNCH_CHECK("k_specimen_tables");
