@@ -36,12 +36,24 @@ DEFAULT_CANDIDATES = {"c1": 4096, "c2": 2048, "c3": 64, "c4": 256, "c5": 1024}
 # algorithmic work: flops per phase-pattern point
 # ---------------------------------------------------------------------------------------
 def work_per_point(G, r, n_terms, atoms):
-    """Series with a REAL probability matrix: per Horner step r*r real-x-complex MACs (4 flop)
-    + r complex updates (10 flop); transcendental equivalents as SURVEY.md §8(d):
-    sincos 32, exp 20, erf 30."""
-    series = n_terms * (4 * r * r + 10 * r) + 16 * r
+    """flops of the algorithm the kernels execute (fma = 2, mul / add = 1), DESIGN.md §3:
+    series per term: rank 1 scalar Horner 7; rank 2 Clenshaw on (trace, det) 15; otherwise the vector
+    Horner step with the REAL probability matrix, r*r real-x-complex MACs (4 flop) + r complex updates
+    (10 flop); transcendental equivalents as SURVEY.md §8(d): sincos 32, exp 20, erf 30."""
+    per_term = 7 if r == 1 else 15 if r == 2 else 4 * r * r + 10 * r
+    series = n_terms * per_term + 16 * r
     factors = atoms * (32 + 8 + 2) + G * (20 + 32 + 12)
     return series + factors + 120
+
+
+def measured_traffic(workload, candidates):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the phase kernel from the committed ncu --set full
+    capture of this workload at this population size (profiles/r1_traffic.json), else None"""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[workload]
+        return rec["dram_bytes"] if rec.get("candidates") == candidates else None
+    except Exception:
+        return None
 
 
 def mixture_work(mix):
@@ -365,7 +377,8 @@ def run_b200(args, rank, world, local_rank):
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                      "peak_source": "DFMA microbenchmark pyxrd_dfma_peak measured in this run (MEASURED_PEAKS.json "
                                     "has no fp64 entry)",
-                     "kernel_ms": phase_ms, "algorithmic_flops_per_launch": main["flops"], "traffic": None,
+                     "kernel_ms": phase_ms, "algorithmic_flops_per_launch": main["flops"],
+                     "traffic": measured_traffic(args.workload, main["K"]),
                      "hbm": {"achieved_gbs": 16.0 * main["points"] / (phase_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
                              "frac": 16.0 * main["points"] / (phase_ms * 1e-3) * 1e-9 / hbm_peak,
                              "peak_source": "of measured" if peaks else "of fallback"}},

@@ -539,8 +539,8 @@ __device__ __forceinline__ double finish_point(double tr, double abs_scale, int 
 // PPT points and the dependent FMA chains of the PPT points interleave.  Per-point tables are
 // padded by PX_TABLE_PAD doubles, so the loads of points beyond the end of a pattern are legal;
 // only the stores are guarded.
-template <int R, int G, int PPT, int TPB>
-__global__ void __launch_bounds__(TPB) k_phase_small(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
+template <int R, int G, int PPT, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
     constexpr int REPS = R / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PhaseSmem *ps = reinterpret_cast<PhaseSmem *>(smem_raw);

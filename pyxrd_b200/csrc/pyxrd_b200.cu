@@ -75,7 +75,6 @@ struct pyxrd_ctx {
     std::string error;
     int64_t launches = 0;
     int smem_optin = 0;
-    int tune = 0;             // PYXRD_B200_TUNE: kernel-shape sweeps (development only)
     bool series_mma = true;   // PYXRD_B200_SERIES=dfma selects the CUDA-core series kernels (A/B measurements only)
 
     // static
@@ -168,13 +167,13 @@ int set_smem(pyxrd_ctx *ctx, K kernel, size_t bytes) {
     return 0;
 }
 
-template <int R, int G, int PPT, int TPB>
+template <int R, int G, int PPT, int TPB, int MINB = 0>
 int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     static_assert((PPT - 1) * TPB <= PX_TABLE_PAD, "table padding too small");
     const size_t smem = small_smem(R, G, rc.max_ntop_cap);
-    if (set_smem(ctx, k_phase_small<R, G, PPT, TPB>, smem)) return 1;
+    if (set_smem(ctx, k_phase_small<R, G, PPT, TPB, MINB>, smem)) return 1;
     dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + TPB * PPT - 1) / (TPB * PPT)));
-    k_phase_small<R, G, PPT, TPB><<<grid, TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
+    k_phase_small<R, G, PPT, TPB, MINB><<<grid, TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
     LAUNCH_CHECK("k_phase_small");
     return 0;
 }
@@ -210,21 +209,19 @@ int launch_generic(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, siz
 
 int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
 #define SMALL(R_, G_, PPT_, TPB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_>(ctx, rc, jobs_dev, njobs, bt)
+#define SMALLB(R_, G_, PPT_, TPB_, MINB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_, MINB_>(ctx, rc, jobs_dev, njobs, bt)
 #define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev, njobs, bt)
-    if (ctx->tune == 1) { SMALL(1, 1, 1, 128); SMALL(2, 2, 1, 128); }
-    if (ctx->tune == 2) { SMALL(1, 1, 2, 128); SMALL(2, 2, 2, 128); }
-    if (ctx->tune == 3) { SMALL(1, 1, 2, 64); SMALL(2, 2, 2, 64); }
-    if (ctx->tune == 4) { SMALL(1, 1, 4, 128); SMALL(2, 2, 4, 128); }
-    if (ctx->tune == 5) { SMALL(1, 1, 3, 64); SMALL(2, 2, 3, 64); }
-    if (ctx->tune == 6) { SMALL(1, 1, 4, 32); SMALL(2, 2, 4, 32); }
-    SMALL(1, 1, 4, 64); SMALL(2, 2, 4, 64); SMALL(3, 3, 2, 128); SMALL(4, 4, 2, 128);  // R0 / R1
+    // (points per thread, threads per block, min blocks per SM) from sweeps on B200 (profiles/r1_summary.md)
+    SMALLB(1, 1, 4, 32, 0); SMALLB(2, 2, 4, 32, 16); SMALLB(2, 1, 4, 32, 16);
+    SMALL(3, 3, 2, 128); SMALL(4, 4, 2, 128);  // R0 / R1
     SMALL(5, 5, 1, 128); SMALL(6, 6, 1, 128);
-    SMALL(2, 1, 4, 64); SMALL(3, 1, 2, 128); SMALL(4, 1, 2, 128);
+    SMALL(3, 1, 2, 128); SMALL(4, 1, 2, 128);
 #define MMA(R_, G_, MTC_) if (rc.rank == R_ && rc.G == G_ && ctx->series_mma) return launch_mma<R_, G_, MTC_>(ctx, rc, jobs_dev, njobs, bt)
     MMA(8, 2, 4); MMA(16, 2, 2); MMA(16, 4, 2); MMA(27, 3, 1);                        // FP64 tensor cores
     SMALL(4, 2, 2, 128); SMALL(8, 2, 1, 128); SMALL(9, 3, 1, 128);                                            // R2G2, R3G2, R2G3
     STAGED(16, 2); STAGED(16, 4); STAGED(27, 3);
 #undef SMALL
+#undef SMALLB
 #undef STAGED
 #undef MMA
     return launch_generic(ctx, rc, jobs_dev, njobs, bt);
@@ -269,7 +266,6 @@ int pyxrd_create(int device, pyxrd_ctx **out) {
         return 3;
     }
     ctx->stream = ctx->own_stream;
-    if (const char *e = getenv("PYXRD_B200_TUNE")) ctx->tune = atoi(e);
     if (const char *e = getenv("PYXRD_B200_SERIES")) ctx->series_mma = strcmp(e, "dfma") != 0;
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
