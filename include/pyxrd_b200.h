@@ -39,6 +39,7 @@ typedef struct pyxrd_ctx pyxrd_ctx;
 #define PYXRD_FLAG_VALID_PROBS 1      /* PhaseData.valid_probs (phases.py:109-111) */
 #define PYXRD_FLAG_APPLY_LPF 2        /* PhaseData.apply_lpf (phases.py:88) */
 #define PYXRD_FLAG_APPLY_CORRECTION 4 /* PhaseData.apply_correction (specimen.py:57) */
+#define PYXRD_FLAG_RAW_PATTERN 8       /* RawPatternPhase (phases.py:97-104): G = rank = 0, csds_min = n, matrix_offset -> raw_x[n] | raw_y[n] */
 
 #define PYXRD_MAX_RANK 64
 #define PYXRD_MAX_COMPONENTS 8
@@ -136,6 +137,16 @@ int pyxrd_compute_intensities(pyxrd_ctx *ctx);
  * ([k][0] = mean over specimens), totals f64 [K][S][Z][X_s]; with want_scaled != 0
  * also scaled_phase_intensities f64 [K][S][M][Z][X_s]. */
 int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled);
+
+/* Which pattern residual pyxrd_compute_residuals / pyxrd_evaluate_host report (settings.py:27-32,
+ * mixture.py:22-27,89): PYXRD_RESIDUAL_RP = statistics.py:22-27 (default), PYXRD_RESIDUAL_RPDER =
+ * statistics.py:29-48 (Rp of the first derivatives of the 31-tap-Blackman-smoothed clipped patterns,
+ * math_tools.py:46-99).  "Rpw" and "Rphase" cannot be evaluated by the reference itself (they raise
+ * for every 2-D input, statistics.py:50-68,81 / mixture.py:89); the host layer re-raises the same
+ * exceptions.  The device optimiser (pyxrd_optimize) always minimises Rp. */
+#define PYXRD_RESIDUAL_RP 0
+#define PYXRD_RESIDUAL_RPDER 1
+int pyxrd_set_residual_method(pyxrd_ctx *ctx, int method);
 
 /* Device-resident optimiser of the mixture solution of every candidate of the resident batch
  * (optimize_mixture, mixture.py:150-219: minimise the mean Rp over fractions >= 0, scales > 0,

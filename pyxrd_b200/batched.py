@@ -39,6 +39,7 @@ def population_residuals(mixtures: Sequence, ctx: Optional[Context] = None, want
     static, batch = pack_population(mixtures)
     with ctx.lock:
         ctx.set_static(static)
+        ctx.set_residual_method(settings.get("RESIDUAL_METHOD"))
         res, inten = ctx.evaluate_host(batch, want_intensities=want_intensities)
     return (res, inten) if want_intensities else res
 
@@ -59,7 +60,8 @@ def _device_optimisable(mix) -> bool:
     free, background shifts all free or all fixed (mixture/models/mixture.py:64-73)"""
     m_all = len(np.asarray(mix.fractions).ravel())
     n_all = len(mix.specimens)
-    return (mix.m == m_all and mix.n == n_all and mix.o in (0, n_all) and m_all <= 11 and n_all <= 8
+    return (settings.get("RESIDUAL_METHOD") == "Rp"        # the device optimiser minimises Rp only
+            and mix.m == m_all and mix.n == n_all and mix.o in (0, n_all) and m_all <= 11 and n_all <= 8
             and all(sp is not None and np.size(sp.observed_intensity) > 0 for sp in mix.specimens))
 
 

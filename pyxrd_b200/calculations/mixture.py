@@ -97,6 +97,8 @@ def _device_residuals(mixture, ctx, want_patterns):
     S = len(mixture.specimens)
     bg = np.asarray(mixture.bgshifts, dtype=float) if settings.get("BGSHIFT") else np.zeros(S)
     ctx.set_solution(np.asarray(mixture.fractions, dtype=float), np.asarray(mixture.scales, dtype=float)[:S], bg[:S])
+    has_obs = any(sp is not None and np.size(sp.observed_intensity) > 0 for sp in mixture.specimens)
+    ctx.set_residual_method(settings.get("RESIDUAL_METHOD") if has_obs else "Rp")
     ctx.compute_residuals(want_scaled=want_patterns)
     return ctx.read_residuals()[0]
 
@@ -173,9 +175,6 @@ def calculate_mixture(mixture, force=False):
             specimen.scaled_phase_intensities = scaled[s].copy()
             specimen.total_intensity = totals[s].copy()
             if np.size(specimen.observed_intensity) > 0:
-                if settings.get("RESIDUAL_METHOD") != "Rp":
-                    raise NotImplementedError("only the default residual 'Rp' is on the device path "
-                                              "(settings.RESIDUAL_METHOD = %r)" % (settings.get("RESIDUAL_METHOD"),))
                 value = float(res[1 + s])
             else:
                 logger.warning("calculate_mixture reports: 'Zero observations found!'")

@@ -67,6 +67,7 @@ def calculate_scaled_intensities(specimen, scale, fractions, bgshift):
         batch = BatchPack([_solo_mixture(shadow, M, fractions, scale, bgshift)], static)
         ctx.set_batch(batch)
         ctx.set_intensities(pi)
+        ctx.set_residual_method("Rp")                    # only the scaled / total patterns are read back
         ctx.compute_residuals(want_scaled=True)
         specimen.scaled_phase_intensities = ctx.read_scaled_flat().reshape(M, Z, X)
         specimen.total_intensity = ctx.read_totals_flat().reshape(Z, X)

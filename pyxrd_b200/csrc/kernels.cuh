@@ -261,7 +261,7 @@ __global__ void k_phase_prologue(BatchDev bt) {
     const int *pi = bt.phase_i + pb * 8;
     const double *pd = bt.phase_d + pb * 8;
     double *px = bt.phase_x + pb * 4;
-    if (!(pi[4] & 1)) { px[0] = 0.0; px[1] = 0.0; px[2] = 0.0; return; }
+    if (!(pi[4] & 1) || (pi[4] & 8)) { px[0] = 0.0; px[1] = 0.0; px[2] = 0.0; return; }   // invalid probabilities / raw pattern
     const int G = pi[0], r = pi[1];
     double mean;
     int ntop;
@@ -1049,6 +1049,42 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_mma(StaticDev st, BatchDev bt,
     if (live) bt.intensities[bt.job_out[job] + x] = finish_point(mytr, abs_scale, flags, ps, st, gx);
 }
 
+// ---- RawPatternPhase: a measured pattern resampled onto the specimen's 2-theta axis --------
+// phases.py:97-104: interp1d(raw_x, raw_y, bounds_error=False, fill_value=0)(rad2deg(2 theta)),
+// then LPF / machine correction like any other phase (phases.py:81-95, specimen.py:57-62).
+// The pool entry of the phase holds raw_x (ascending, n values) followed by raw_y.
+// scipy 1.18.1 _call_linear: hi = searchsorted(x, x_new) clipped to [1, n-1],
+//   slope form  y = ((x_new - x_lo) / (x_hi - x_lo)) * y_hi + ((x_hi - x_new) / (x_hi - x_lo)) * y_lo
+__global__ void __launch_bounds__(128) k_phase_raw(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
+    __shared__ PhaseSmem ps_store;
+    PhaseSmem *ps = &ps_store;
+    const int job = jobs[blockIdx.x];
+    const int pb = bt.job_pb[job], s = bt.job_spec[job];
+    const int X = st.spec_npts[s];
+    const int x = blockIdx.y * 128 + threadIdx.x;
+    const int *pi = bt.phase_i + pb * 8;
+    const int n = pi[2], flags = pi[4];
+    if (threadIdx.x == 0) lpf_setup(ps, bt.phase_d[pb * 8], st.derived + s * 8);
+    __syncthreads();
+    if (x >= X) return;
+    const double *rx = bt.matrices + pi[6], *ry = rx + n;
+    const long long gx = st.spec_off[s] + x;
+    const double xq = __dmul_rn(__dmul_rn(2.0, st.theta[gx]), 57.29577951308232);   // np.rad2deg(2 * theta)
+    double v = 0.0;
+    if (n >= 2 && xq >= rx[0] && xq <= rx[n - 1]) {
+        int lo = 0, hi = n;                              // searchsorted, side = 'left': first index with rx[i] >= xq
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rx[mid] < xq) lo = mid + 1; else hi = mid;
+        }
+        hi = min(max(lo, 1), n - 1);
+        const double x_lo = rx[hi - 1], x_hi = rx[hi], den = __dadd_rn(x_hi, -x_lo);
+        v = __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn(xq, -x_lo), den), ry[hi]),
+                      __dmul_rn(__ddiv_rn(__dadd_rn(x_hi, -xq), den), ry[hi - 1]));
+    }
+    bt.intensities[bt.job_out[job] + x] = finish_point(v, 1.0, flags, ps, st, gx);
+}
+
 // ---- any rank <= 64: vectors in shared memory (fallback, not tuned) --------------
 __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1276,6 +1312,101 @@ __global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, B
             // no observations -> 0.0 (mixture.py:247-251)
             bt.residuals[(long long)k * (st.S + 1) + 1 + s] = (n > 0) ? num / den * 100.0 : 0.0;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Rpder (settings.RESIDUAL_METHOD = "Rpder", statistics.py:29-48, math_tools.py:46-99):
+//   Rp(gradient(smooth(exp, 15)), gradient(smooth(calc, 15))) on the CLIPPED patterns, i.e. the
+//   selected points of all Z patterns flattened into one vector (smooth() flattens, :84-85).
+//   smooth = 31-tap normalised Blackman window over s = [x[30:0:-1], x, x[-1:-31:-1]] ('valid'
+//   convolution, then [15:-15]):  y[i] = sum_k w[k] xr(i + 15 - k),
+//   xr(t) = x[-t] (t < 0), x[t], x[2n - 1 - t] (t >= n)  -- the right reflection repeats the edge.
+//   np.gradient: (y[i+1] - y[i-1]) / 2 inside, one-sided differences at the two ends.
+// One block per (specimen, candidate); the clipped exp / calc vectors are staged in shared
+// memory when they fit (use_smem), else gathered from global memory.
+// ---------------------------------------------------------------------------------
+__constant__ double PX_BLACKMAN[31];      // np.blackman(31) / sum, written once by pyxrd_create
+
+__global__ void k_selected_positions(StaticDev st, int *sel_pos, int *sel_count) {
+    const int s = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const int X = st.spec_npts[s];
+    const unsigned char *sel = st.selected + st.spec_off[s];
+    int *out = sel_pos + st.spec_off[s];
+    int n = 0;
+    for (int x = 0; x < X; ++x)
+        if (sel[x]) out[n++] = x;
+    sel_count[s] = n;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ double rpder_value(const double *v, const double *pat, const int *pos, int nsel, int X, int j) {
+    if (SMEM) return v[j];
+    const int z = j / nsel;
+    return pat[(long long)z * X + pos[j - z * nsel]];
+}
+
+template <bool SMEM>
+__device__ __forceinline__ double rpder_smooth(const double *v, const double *pat, const int *pos, int nsel, int X, int n, int i) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 31; ++k) {
+        const int t = i + 15 - k;
+        const int j = t < 0 ? -t : (t >= n ? 2 * n - 1 - t : t);
+        acc = fma(PX_BLACKMAN[k], rpder_value<SMEM>(v, pat, pos, nsel, X, j), acc);
+    }
+    return acc;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ double rpder_gradient(const double *v, const double *pat, const int *pos, int nsel, int X, int n, int i) {
+    const int a = i > 0 ? i - 1 : 0, b = i < n - 1 ? i + 1 : n - 1;
+    const double d = rpder_smooth<SMEM>(v, pat, pos, nsel, X, n, b) - rpder_smooth<SMEM>(v, pat, pos, nsel, X, n, a);
+    return (i > 0 && i < n - 1) ? d / 2.0 : d;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_residual_rpder(StaticDev st, BatchDev bt, int k0, const int *sel_pos, const int *sel_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int s = blockIdx.x, k = k0 + blockIdx.y;
+    const int X = st.spec_npts[s], Z = st.Z;
+    const int nsel = sel_count[s], n = Z * nsel;
+    const long long soff = st.spec_off[s];
+    const double *tot = bt.totals + ((long long)k * st.sumX + soff) * Z;
+    const double *obs = st.observed + (long long)Z * soff;
+    const int *pos = sel_pos + soff;
+    double *ve = reinterpret_cast<double *>(smem_raw), *vc = ve + n;
+    if (SMEM) {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const int z = j / nsel, x = pos[j - z * nsel];
+            ve[j] = obs[(long long)z * X + x];
+            vc[j] = tot[(long long)z * X + x];
+        }
+        __syncthreads();
+    }
+    double num = 0.0, den = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double de = rpder_gradient<SMEM>(ve, obs, pos, nsel, X, n, i);
+        const double dc = rpder_gradient<SMEM>(vc, tot, pos, nsel, X, n, i);
+        num += fabs(de - dc);
+        den += fabs(de);
+    }
+    __shared__ double red[2][32];
+    for (int o = 16; o > 0; o >>= 1) {
+        num += __shfl_down_sync(0xffffffffu, num, o);
+        den += __shfl_down_sync(0xffffffffu, den, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = num; red[1][threadIdx.x >> 5] = den; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        num = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.0;
+        den = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            num += __shfl_down_sync(0xffffffffu, num, o);
+            den += __shfl_down_sync(0xffffffffu, den, o);
+        }
+        if (threadIdx.x == 0) bt.residuals[(long long)k * (st.S + 1) + 1 + s] = (Z * X > 0) ? num / den * 100.0 : 0.0;
     }
 }
 

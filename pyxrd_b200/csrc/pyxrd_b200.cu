@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -96,6 +97,9 @@ struct pyxrd_ctx {
     PinBuf h_blob;
     const int *jobids_dev = nullptr;   // inside d_blob
     DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
+    int residual_method = PYXRD_RESIDUAL_RP;   // settings.RESIDUAL_METHOD (mixture.py:22-27,89)
+    DevBuf d_selpos, d_selcount;
+    std::vector<int> h_selcount;
     int wl_passes = 0;       // longest wavelength list of the specimens = number of ping-pong passes
     int jobs_per_cand = 0;
     PinBuf h_res;
@@ -207,7 +211,15 @@ int launch_generic(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, siz
     return 0;
 }
 
+int launch_raw(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
+    dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + 127) / 128));
+    k_phase_raw<<<grid, 128, 0, ctx->stream>>>(ctx->st, bt, jobs_dev);
+    LAUNCH_CHECK("k_phase_raw");
+    return 0;
+}
+
 int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
+    if (rc.rank == 0 && rc.G == 0) return launch_raw(ctx, rc, jobs_dev, njobs, bt);
 #define SMALL(R_, G_, PPT_, TPB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_>(ctx, rc, jobs_dev, njobs, bt)
 #define SMALLB(R_, G_, PPT_, TPB_, MINB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_, MINB_>(ctx, rc, jobs_dev, njobs, bt)
 #define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev, njobs, bt)
@@ -270,6 +282,16 @@ int pyxrd_create(int device, pyxrd_ctx **out) {
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    {   // np.blackman(31) / np.blackman(31).sum()  (math_tools.py:93-98 with half_window_len = 15)
+        double w[31], sum = 0.0;
+        for (int i = 0; i < 31; ++i) {
+            const double n = 2.0 * i - 30.0;      // arange(1 - M, M, 2)
+            w[i] = 0.42 + 0.5 * cos(PX_PI * n / 30.0) + 0.08 * cos(2.0 * PX_PI * n / 30.0);
+            sum += w[i];
+        }
+        for (int i = 0; i < 31; ++i) w[i] /= sum;
+        cudaMemcpyToSymbol(PX_BLACKMAN, w, sizeof(w));
+    }
     for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
     *out = ctx;
     return 0;
@@ -283,7 +305,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob,
                       &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
-                      &ctx->d_res, &ctx->d_int2, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
+                      &ctx->d_res, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
     ctx->h_res.release();
@@ -405,6 +427,12 @@ int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
     }
     k_observed_norm<<<S, 256, 0, ctx->stream>>>(st, ctx->d_derived.as<double>());
     LAUNCH_CHECK("k_observed_norm");
+    CK(ctx->d_selpos.ensure(sizeof(int) * std::max<long long>(sumX, 1)));
+    CK(ctx->d_selcount.ensure(sizeof(int) * S));
+    k_selected_positions<<<S, 32, 0, ctx->stream>>>(st, ctx->d_selpos.as<int>(), ctx->d_selcount.as<int>());
+    LAUNCH_CHECK("k_selected_positions");
+    ctx->h_selcount.assign(S, 0);
+    CK(cudaMemcpyAsync(ctx->h_selcount.data(), ctx->d_selcount.ptr, sizeof(int) * S, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_static = true;
     return 0;
@@ -428,6 +456,11 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
         const int32_t *pi = d->phase_i + (size_t)p * PYXRD_PHASE_I_STRIDE;
         if (!(pi[4] & PYXRD_FLAG_VALID_PROBS)) continue;
         const int G = pi[0], r = pi[1];
+        if (pi[4] & PYXRD_FLAG_RAW_PATTERN) {           // RawPatternPhase: pool entry = raw_x[n] | raw_y[n]
+            if (G != 0 || r != 0 || pi[2] < 0 || pi[6] < 0 || (int64_t)pi[6] + 2 * (int64_t)pi[2] > d->n_matrix)
+                return fail(ctx, "set_batch: raw-pattern phase %d is malformed (n=%d, offset=%d, pool=%lld)", p, pi[2], pi[6], (long long)d->n_matrix);
+            continue;
+        }
         if (G < 1 || G > PYXRD_MAX_COMPONENTS || r < 1 || r > PYXRD_MAX_RANK || r % G != 0)
             return fail(ctx, "set_batch: phase %d has unsupported G=%d rank=%d (need 1<=G<=%d, rank<=%d, rank %% G == 0)",
                         p, G, r, PYXRD_MAX_COMPONENTS, PYXRD_MAX_RANK);
@@ -662,6 +695,24 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed)
         dim3 grid(ctx->st.S, k1 - k0);
         k_mixture_residual<<<grid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled);
         LAUNCH_CHECK("k_mixture_residual");
+        if (ctx->residual_method == PYXRD_RESIDUAL_RPDER) {
+            // the Rp kernel above has produced the totals; its residuals are replaced
+            int maxn = 0;
+            for (int s = 0; s < ctx->st.S; ++s) {
+                const int n = ctx->st.Z * ctx->h_selcount[s];
+                if (ctx->h_npts[s] > 0 && n < 31)
+                    return fail(ctx, "Input vector needs to be bigger than window size.");   // math_tools.py:87-88
+                maxn = std::max(maxn, n);
+            }
+            const size_t smem = sizeof(double) * 2 * (size_t)maxn;
+            if (smem + 1024 <= (size_t)ctx->smem_optin) {
+                if (set_smem(ctx, k_residual_rpder<true>, smem)) return 1;
+                k_residual_rpder<true><<<grid, 256, smem, ctx->stream>>>(ctx->st, bt, k0, ctx->d_selpos.as<int>(), ctx->d_selcount.as<int>());
+            } else {
+                k_residual_rpder<false><<<grid, 256, 0, ctx->stream>>>(ctx->st, bt, k0, ctx->d_selpos.as<int>(), ctx->d_selcount.as<int>());
+            }
+            LAUNCH_CHECK("k_residual_rpder");
+        }
         k_mixture_mean<<<(k1 - k0 + 127) / 128, 128, 0, ctx->stream>>>(k0, k1, ctx->st.S, bt.residuals);
         LAUNCH_CHECK("k_mixture_mean");
     }
@@ -681,6 +732,14 @@ int pyxrd_compute_intensities(pyxrd_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     if (intensities_range(ctx, 0, ctx->bt.K, true)) return 1;
     ctx->have_intensities = true;
+    return 0;
+}
+
+int pyxrd_set_residual_method(pyxrd_ctx *ctx, int method) {
+    if (!ctx) return 1;
+    if (method != PYXRD_RESIDUAL_RP && method != PYXRD_RESIDUAL_RPDER)
+        return fail(ctx, "set_residual_method: unknown method %d (0 = Rp, 1 = Rpder)", method);
+    ctx->residual_method = method;
     return 0;
 }
 

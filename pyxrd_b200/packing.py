@@ -30,6 +30,7 @@ ATOM_D_STRIDE = 2
 FLAG_VALID_PROBS = 1
 FLAG_APPLY_LPF = 2
 FLAG_APPLY_CORRECTION = 4
+FLAG_RAW_PATTERN = 8
 
 _DIV_MODES = {"FIXED": 0.0, "AUTOMATIC": 1.0}
 
@@ -253,13 +254,27 @@ class BatchPack(object):
         ptype = getattr(phase, "type", "Phase")
         if ptype == "AbtractPhase":
             raise NotImplementedError          # phases.py:74-75
-        if ptype != "Phase":
-            raise NotImplementedError("phase type %r is not on the device path yet (see DESIGN.md)" % (ptype,))
+        if ptype not in ("Phase", "RawPatternPhase"):
+            raise NotImplementedError("unknown phase type %r" % (ptype,))
         flags = 0
         if getattr(phase, "apply_lpf", True):
             flags |= FLAG_APPLY_LPF
         if getattr(phase, "apply_correction", True):
             flags |= FLAG_APPLY_CORRECTION
+        if ptype == "RawPatternPhase":
+            # phases.py:97-104: interp1d sorts its abscissa (stable argsort) before searching; the
+            # device kernel expects raw_x ascending followed by raw_y (layout only)
+            rx = np.asarray(phase.raw_pattern_x, dtype=float).ravel()
+            ry = np.asarray(phase.raw_pattern_y, dtype=float).ravel()
+            if rx.size != ry.size:
+                raise ValueError("x and y arrays must be equal in length along interpolation axis.")
+            order = np.argsort(rx, kind="mergesort")
+            phase_i.append([0, 0, int(rx.size), 0, flags | FLAG_VALID_PROBS | FLAG_RAW_PATTERN, 0, mat_off, 0])
+            phase_d.append([float(getattr(phase, "sigma_star", 3.0))] + [0.0] * (PHASE_D_STRIDE - 1))
+            matrices.append(rx[order])
+            matrices.append(ry[order])
+            self.components_of_phase.append([])
+            return mat_off + 2 * rx.size
         if not phase.valid_probs:
             phase_i.append([0, 0, 0, 0, flags, 0, 0, 0])
             phase_d.append([0.0] * PHASE_D_STRIDE)

@@ -44,7 +44,7 @@ class BatchDesc(C.Structure):
 EXPORTS = [
     "pyxrd_create", "pyxrd_destroy", "pyxrd_last_error", "pyxrd_set_stream", "pyxrd_synchronize",
     "pyxrd_launch_count", "pyxrd_set_static", "pyxrd_set_batch", "pyxrd_set_solution", "pyxrd_set_intensities",
-    "pyxrd_compute_intensities", "pyxrd_compute_residuals", "pyxrd_optimize", "pyxrd_read_solutions",
+    "pyxrd_compute_intensities", "pyxrd_compute_residuals", "pyxrd_set_residual_method", "pyxrd_optimize", "pyxrd_read_solutions",
     "pyxrd_read_opt_residuals", "pyxrd_intensity_count", "pyxrd_total_count",
     "pyxrd_read_intensities", "pyxrd_read_scaled", "pyxrd_read_totals", "pyxrd_read_residuals",
     "pyxrd_read_correction", "pyxrd_device_buffers", "pyxrd_evaluate_host", "pyxrd_optimize_host", "pyxrd_leaf_asf",
@@ -90,6 +90,7 @@ def load_library():
         lib.pyxrd_set_intensities.argtypes = [vp, _f64p, C.c_int64]
         lib.pyxrd_compute_intensities.argtypes = [vp]
         lib.pyxrd_compute_residuals.argtypes = [vp, C.c_int]
+        lib.pyxrd_set_residual_method.argtypes = [vp, C.c_int]
         lib.pyxrd_optimize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         lib.pyxrd_read_solutions.argtypes = [vp, _f64p, C.c_int64]
         lib.pyxrd_read_opt_residuals.argtypes = [vp, _f64p, C.c_int64]
@@ -207,6 +208,20 @@ class Context(object):
     # -- compute ----------------------------------------------------------------------
     def compute_intensities(self):
         self._check(self._lib.pyxrd_compute_intensities(self._h), "compute_intensities")
+
+    def set_residual_method(self, name: str = "Rp"):
+        """settings.RESIDUAL_METHOD (mixture.py:22-27,89).  "Rp" and "Rpder" run on the device; "Rpw" and
+        "Rphase" raise exactly what the reference raises for them (its own implementations cannot be
+        called with the 2-D clipped patterns mixture.py:88-89 passes: statistics.py:58-61,81)."""
+        if name == "Rpw":
+            raise ValueError("The truth value of an array with more than one element is ambiguous. "
+                             "Use a.any() or a.all()")
+        if name == "Rphase":
+            raise TypeError("Rphase() missing 1 required positional argument: 'phase'")
+        code = {"Rp": 0, "Rpder": 1}[name]          # KeyError for an unknown name, like the reference's dict
+        if getattr(self, "_residual_method", 0) != code:
+            self._check(self._lib.pyxrd_set_residual_method(self._h, code), "set_residual_method")
+            self._residual_method = code
 
     def compute_residuals(self, want_scaled: bool = False):
         self._check(self._lib.pyxrd_compute_residuals(self._h, int(bool(want_scaled))), "compute_residuals")

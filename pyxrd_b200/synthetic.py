@@ -365,6 +365,32 @@ def _c5(rng):
     return make_mixture([spec], 4)
 
 
+def make_raw_phase(x, y, apply_lpf: bool = False, apply_correction: bool = False, sigma_star: float = 3.0) -> PhaseData:
+    """RawPatternPhase data object as phases/models/raw_pattern_phase.py:36-43 builds it."""
+    return PhaseData(type="RawPatternPhase", valid_probs=True, apply_lpf=apply_lpf, apply_correction=apply_correction,
+                     components=[], sigma_star=float(sigma_star), raw_pattern_x=np.asarray(x, dtype=float),
+                     raw_pattern_y=np.asarray(y, dtype=float))
+
+
+def raw_case() -> MixtureData:
+    """c1's specimen with two RawPatternPhases next to the calculated illite: an unsorted, coarser raw
+    abscissa that covers only part of the 2-theta range (fill 0 outside), the model's defaults
+    (no LPF, no correction) for one and both switched on for the other."""
+    mix = _c1(None)
+    spec = mix.specimens[0]
+    rng = np.random.default_rng(4242)
+    x = np.linspace(5.013, 39.77, 811)
+    y = 40.0 + 25.0 * np.sin(x * 0.9) ** 2 + rng.uniform(0.0, 3.0, x.size)
+    shuffle = rng.permutation(x.size)
+    raw_a = make_raw_phase(x[shuffle], y[shuffle])
+    x2 = np.sort(rng.uniform(2.0, 60.0, 300))
+    raw_b = make_raw_phase(x2, rng.uniform(0.0, 80.0, x2.size), apply_lpf=True, apply_correction=True, sigma_star=7.5)
+    spec.phases = [[spec.phases[0][0], raw_a, raw_b]]
+    out = make_mixture([spec], 3, fractions=[0.5, 0.3, 0.2], scales=[1.7], bgshifts=[2.5])
+    spec.observed_intensity = rng.uniform(20.0, 90.0, (spec.range_theta.size, 1))
+    return out
+
+
 CONFIGS = {
     "c1": Config("c1", "single-phase R0 illite, G=1, CSDS mean 10, X=2100", _c1, 1, 1),
     "c2": Config("c2", "illite-smectite R1 G=2, air-dry, X=6700", _c2, 1, 1),
@@ -396,3 +422,15 @@ def attach_observed(candidates: Sequence[MixtureData], truth: MixtureData,
     for mix in list(candidates) + [truth]:
         for spec, obs in zip(mix.specimens, observed):
             spec.observed_intensity = obs.copy()
+
+
+def rpder_case() -> MixtureData:
+    """c4 candidate 1 with a pseudo-observed pattern and a 2-degree exclusion window on specimen 0."""
+    mix = CONFIGS["c4"].candidate(2024, 1)
+    rng = np.random.default_rng(515)
+    for s, spec in enumerate(mix.specimens):
+        tt = np.degrees(2.0 * spec.range_theta)
+        spec.observed_intensity = (50.0 + 30.0 * np.sin(tt * 0.7) ** 2 + rng.uniform(0.0, 4.0, tt.size)).reshape(-1, 1)
+        if s == 0:
+            spec.selected_range = ~((tt >= 20.0) & (tt <= 22.0))
+    return mix

@@ -119,14 +119,45 @@ def run_config(ref, name, out):
         print("  %s %s done (%.1f s)" % (name, tag, time.time() - t0), flush=True)
 
 
+def extras(ref, out):
+    """cases beyond the BASELINE configs: RawPatternPhase (phases.py:97-104)"""
+    mix = syn.raw_case()
+    ref.mixture.calculate_mixture(mix)
+    spec = mix.specimens[0]
+    out["raw_pi"] = np.array(spec.phase_intensities)
+    out["raw_total"] = np.array(spec.total_intensity)
+    out["raw_residuals"] = np.array(mix.residuals, dtype=float)
+    theta = spec.range_theta
+    stl = 2 * np.sin(theta) / spec.goniometer.wavelength
+    out["raw_single"] = ref.phases.get_diffracted_intensity(theta, stl, spec.phases[0][1])
+    out["raw_single_lpf"] = ref.phases.get_intensity(theta, stl, 2.3, 2.3, 0.0, spec.phases[0][2])
+    # settings.RESIDUAL_METHOD = "Rpder" (statistics.py:29-48) on the raw case (one specimen, no
+    # exclusion) and on c4 (two specimens) with an exclusion window on the first specimen
+    from pyxrd.data import settings
+    settings.RESIDUAL_METHOD = "Rpder"
+    try:
+        mix = syn.raw_case()
+        ref.mixture.calculate_mixture(mix)
+        out["rpder_raw_residuals"] = np.array(mix.residuals, dtype=float)
+        mix = syn.rpder_case()
+        ref.mixture.calculate_mixture(mix)
+        out["rpder_c4_residuals"] = np.array(mix.residuals, dtype=float)
+        r = ref.mixture.get_optimized_residual(syn.rpder_case())
+        out["rpder_c4_opt_residual"] = np.array(r, dtype=float)
+    finally:
+        settings.RESIDUAL_METHOD = "Rp"
+
+
 def main():
     ref = _live_reference.load()
-    names = sys.argv[1:] or ["kat", "c1", "c2", "c4", "c5", "c3"]
+    names = sys.argv[1:] or ["kat", "extras", "c1", "c2", "c4", "c5", "c3"]
     for name in names:
         out = {"versions": np.array("numpy %s scipy %s python %s reference 0.8.4"
                                     % (np.__version__, scipy.__version__, sys.version.split()[0]))}
         if name == "kat":
             kats(ref, out)
+        elif name == "extras":
+            extras(ref, out)
         else:
             run_config(ref, name, out)
         path = os.path.join(HERE, "%s.npz" % name)

@@ -314,3 +314,55 @@ def test_device_optimizer_fixed_background_and_fallback(calc, golden):
     part.fractions_mask = np.array([1, 1, 1, 0, 1, 1])
     r = get_optimized_residuals([part])[0]
     assert np.isfinite(r[0]) and part.optimized and abs(part.fractions[3] - 0.25) < 1e-6
+
+
+# ---- RawPatternPhase and the alternative residual methods -------------------------------------
+def test_raw_pattern_phase_matches_live_reference(calc, golden):
+    """phases.py:97-104 through k_phase_raw: unsorted raw abscissa, fill 0 outside, LPF / correction flags"""
+    g = golden("extras")
+    mix = syn.raw_case()
+    calc.mixture.calculate_mixture(mix)
+    spec = mix.specimens[0]
+    assert rel_err(spec.phase_intensities, g["raw_pi"]) < RTOL
+    assert np.array_equal(spec.phase_intensities[1, 0] == 0.0, g["raw_pi"][1, 0] == 0.0)
+    assert rel_err(spec.total_intensity, g["raw_total"]) < RTOL
+    assert rel_err(mix.residuals, g["raw_residuals"]) < RTOL
+    theta = spec.range_theta
+    stl = 2 * np.sin(theta) / spec.goniometer.wavelength
+    assert rel_err(calc.phases.get_diffracted_intensity(theta, stl, spec.phases[0][1]), g["raw_single"]) < RTOL
+    assert rel_err(calc.phases.get_intensity(theta, stl, 2.3, 2.3, 0.0, spec.phases[0][2]), g["raw_single_lpf"]) < RTOL
+
+
+def test_residual_methods(calc, golden):
+    """settings.RESIDUAL_METHOD: Rpder on the device (statistics.py:29-48); Rpw / Rphase raise what the
+    reference raises for them (statistics.py:58-61,81 cannot take the 2-D clipped patterns)."""
+    from pyxrd_b200 import settings
+    from pyxrd_b200.batched import get_optimized_residuals, population_residuals
+    g = golden("extras")
+    try:
+        settings.RESIDUAL_METHOD = "Rpder"
+        mix = syn.raw_case()
+        calc.mixture.calculate_mixture(mix)
+        assert rel_err(mix.residuals, g["rpder_raw_residuals"]) < RTOL
+        mix = syn.rpder_case()
+        calc.mixture.calculate_mixture(mix)
+        assert rel_err(mix.residuals, g["rpder_c4_residuals"]) < RTOL
+        assert rel_err(population_residuals([syn.rpder_case()])[0], g["rpder_c4_residuals"]) < RTOL
+        # the optimiser minimises whatever settings select: scipy-driven path with the device objective
+        want = float(g["rpder_c4_opt_residual"][0])
+        got = float(get_optimized_residuals([syn.rpder_case()])[0][0])
+        assert got <= want * (1.0 + 5e-2), (got, want)
+        settings.RESIDUAL_METHOD = "Rpw"
+        with pytest.raises(ValueError):
+            calc.mixture.calculate_mixture(syn.raw_case())
+        settings.RESIDUAL_METHOD = "Rphase"
+        with pytest.raises(TypeError):
+            calc.mixture.calculate_mixture(syn.raw_case())
+        settings.RESIDUAL_METHOD = "nonsense"
+        with pytest.raises(KeyError):
+            calc.mixture.calculate_mixture(syn.raw_case())
+    finally:
+        settings.RESIDUAL_METHOD = "Rp"
+    mix = syn.raw_case()
+    calc.mixture.calculate_mixture(mix)
+    assert rel_err(mix.residuals, g["raw_residuals"]) < RTOL

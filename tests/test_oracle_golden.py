@@ -105,3 +105,27 @@ def test_oracle_optimizer_matches_live_reference(golden, name):
         # end point of c4 by 1.8e-4 relative (8.40815 vs 8.40966) -- the optimum is only
         # reproducible to ~1e-3, hence OPT_RTOL
         assert abs(float(r[0]) - want) <= OPT_RTOL * max(1.0, want), (name, tag, float(r[0]), want)
+
+
+def test_oracle_raw_pattern_phase_and_rpder(golden):
+    """RawPatternPhase (phases.py:97-104) and settings.RESIDUAL_METHOD = "Rpder" (statistics.py:29-48)
+    against live-reference outputs (tests/golden/extras.npz)."""
+    from pyxrd_b200 import synthetic as syn
+    g = golden("extras")
+    mix = syn.raw_case()
+    orc.calculate_mixture(mix)
+    spec = mix.specimens[0]
+    assert rel_err(spec.phase_intensities, g["raw_pi"]) < TOL
+    assert rel_err(spec.total_intensity, g["raw_total"]) < TOL
+    assert rel_err(mix.residuals, g["raw_residuals"]) < 1e-12
+    assert np.count_nonzero(g["raw_pi"][1, 0] == 0.0) > 100      # fill_value = 0 outside the raw range is exercised
+    orc.SETTINGS["RESIDUAL_METHOD"] = "Rpder"
+    try:
+        mix = syn.raw_case()
+        orc.calculate_mixture(mix)
+        assert rel_err(mix.residuals, g["rpder_raw_residuals"]) < 1e-11
+        mix = syn.rpder_case()
+        orc.calculate_mixture(mix)
+        assert rel_err(mix.residuals, g["rpder_c4_residuals"]) < 1e-11
+    finally:
+        orc.SETTINGS["RESIDUAL_METHOD"] = "Rp"
