@@ -296,7 +296,11 @@ def run_reference(args, rank):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs / max(len(steps), 1) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (name, syn.CONFIGS[name].description)},
+            "config": {"workload": "%s: %s" % (name, syn.CONFIGS[name].description),
+                       "candidates_per_gpu": args.candidates or DEFAULT_CANDIDATES[name],
+                       "points_per_pattern": [int(sp.range_theta.size) for sp in syn.CONFIGS[name].truth().specimens],
+                       "specimens": syn.CONFIGS[name].n_specimens, "phases": syn.CONFIGS[name].n_phases,
+                       "l2": "256 MiB flush write between timed steps", "population_seed": SEED},
             "cpu_baseline": {"value": value, "unit": "pattern-pts/s", "cores": cores, "kind": "port",
                              "sample": "%d candidates per step in a %d-process pool (multiprocessing, as "
                                        "pyxrd/server/pyxrd_server.py:57-76 does)" % (steps[0]["patterns"], cores)},
