@@ -94,7 +94,86 @@ typedef struct {
     const double *fractions;  /* [K][M]  MixtureData.fractions */
     const double *scales;     /* [K][S]  MixtureData.scales */
     const double *bgshifts;   /* [K][S]  MixtureData.bgshifts (already 0 when settings.BGSHIFT is off) */
+    /* optional (both NULL: every phase carries W / P in `matrices`): probability model of each phase
+     * (PYXRD_PROB_*) and its parameters; for a model-driven phase the device computes W, P into the
+     * phase's pool entry and valid_probs itself (probabilities/models/*.py, phases/models/phase.py:45) */
+    const int32_t *prob_model;  /* [NP] */
+    const double *prob_params;  /* [NP][PYXRD_PROB_STRIDE] */
 } pyxrd_batch_desc;
+
+/* Probability models evaluated on the device.  Parameters in the order of the
+ * reference's properties, clamped to the properties' bounds like the setters do
+ * (mvc/models/properties/cast_property.py:44-47):
+ *   R0   (any G <= 6): F1 .. F(G-1)                                   R0models.py:68-83
+ *   R1G2: W1, P11_or_P22                                              R1models.py:125-139
+ *   R2G2: W1 (>= 1/2), P112_or_P211, P21, P122_or_P221                R2models.py:195-233
+ *   R3G2: W1 (>= 2/3), P1111_or_P2112                                 R3models.py:158-198
+ * followed by solve() and validate() (base_models.py:142-241). */
+#define PYXRD_PROB_FIXED 0
+#define PYXRD_PROB_R0 1
+#define PYXRD_PROB_R1G2 2
+#define PYXRD_PROB_R2G2 3
+#define PYXRD_PROB_R3G2 4
+#define PYXRD_PROB_STRIDE 8
+
+/* ---- population from a template ---------------------------------------
+ * A refinement proposes K solution vectors x_k of d refinable values.  Instead of rebuilding K
+ * DataObject graphs and packing each of them (refinement/refiner.py:91-109,
+ * mixture/models/mixture.py:53-85: 6.4 ms per trial in the reference, 70 us per trial in packing.py),
+ * the template candidate is packed once and a binding table says which packed slot every refinable
+ * drives: slot = scale * x[param] + offset.  The expansion is native host code (memcpy + K * n_bindings
+ * multiply-adds); everything numeric that depends on the bound values -- probability matrices, CSDS
+ * distribution, absolute scale, z-stretch -- is computed on the device by the batch prologue. */
+#define PYXRD_BIND_PHASE_D 0    /* phase_d[index]: phase * 8 + {0 sigma_star, 1 CSDS average, 2..5 alpha / beta} */
+#define PYXRD_BIND_COMP_D 1     /* comp_d[index]: component * 8 + {0 d001, 1 default_c, 2 delta_c, 3 lattice_d, 4 volume, 5 weight} */
+#define PYXRD_BIND_ATOM_D 2     /* atom_d[index]: atom * 2 + {0 pn, 1 default_z} */
+#define PYXRD_BIND_MATRIX 3     /* matrices[index] */
+#define PYXRD_BIND_PROB_PARAM 4 /* prob_params[index]: phase * 8 + parameter number */
+#define PYXRD_BIND_FRACTION 5   /* fractions[index], index < M */
+#define PYXRD_BIND_SCALE 6      /* scales[index], index < S */
+#define PYXRD_BIND_BGSHIFT 7    /* bgshifts[index], index < S */
+typedef struct {
+    int32_t param;              /* column of x */
+    int32_t target;             /* PYXRD_BIND_* */
+    int32_t index;              /* flat index inside the TEMPLATE's array */
+    int32_t reserved;
+    double scale, offset;
+} pyxrd_binding;
+
+typedef struct {
+    int32_t n_candidates;       /* K */
+    int32_t n_params;           /* d */
+    int32_t n_bindings;
+    int32_t n_specimens;        /* S of the static tables (scales / bgshifts per candidate) */
+    int32_t n_patterns;         /* Z of the static tables (the template's job table is [S][Z][M]) */
+    int32_t reserved;
+    const double *x;            /* [K][d] */
+    const pyxrd_binding *bindings;
+    /* optional [NP of the template]: 1 = after binding set CSDS maximum = int(csds_factor * average)
+     * (phases/models/CSDS.py:127,140 with settings.LOG_NORMAL_MAX_CSDS_FACTOR, settings.py:26) */
+    const uint8_t *csds_auto_maximum;
+    double csds_factor;
+} pyxrd_population_desc;
+
+typedef struct pyxrd_expanded pyxrd_expanded;
+/* host only (no device needed): the K-candidate batch the template and the table describe */
+int pyxrd_expand_population(const pyxrd_batch_desc *template_desc, const pyxrd_population_desc *pop,
+                            pyxrd_expanded **out);
+void pyxrd_expanded_desc(const pyxrd_expanded *e, pyxrd_batch_desc *out);
+void pyxrd_expanded_free(pyxrd_expanded *e);
+const char *pyxrd_expand_error(void);   /* message of the last failed pyxrd_expand_population of this thread */
+/* expand + pyxrd_set_batch */
+int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *template_desc, const pyxrd_population_desc *pop);
+/* set_population + compute_intensities + compute_residuals -> residuals [K][1+S] */
+int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *template_desc, const pyxrd_population_desc *pop,
+                              double *residuals_out);
+/* set_population + compute_intensities + optimize -> residuals [K][1+S], solutions [K][M+2S] (may be NULL) */
+int pyxrd_optimize_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *template_desc, const pyxrd_population_desc *pop,
+                              int refine_bg, int outer_iterations, int newton_iterations, double *residuals_out,
+                              double *solutions_out);
+/* one probability model (GUI previews, tests): W, P f64[rank*rank] row major, valid_probs, rank */
+int pyxrd_leaf_probabilities(pyxrd_ctx *ctx, int model, int G, const double *params, double *W_out, double *P_out,
+                             int *valid_out, int *rank_out);
 
 /* ---- lifetime ------------------------------------------------------------------ */
 int pyxrd_create(int device, pyxrd_ctx **out);

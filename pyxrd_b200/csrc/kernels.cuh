@@ -106,6 +106,9 @@ struct BatchDev {
     int *comp_nplanes;               // [NC]   derived
     double *phase_x;                 // [NP][4] derived: mean, abs_scale, ntop
     double *coef;                    // [NP][ncap] derived, index = power of Q
+    const int *prob_model;           // [NP] PX_PROB_* (nullptr: every phase carries its W / P in the pool)
+    const double *prob_params;       // [NP][8] probability parameters of the model
+    int *phase_valid;                // [NP]   derived: valid_probs (host flag, or the device model's verdict)
     const int *job_pb, *job_spec;    // [NJ]
     const long long *job_out;        // [NJ]
     const double *fractions, *scales, *bgshifts;   // [K][M], [K][S], [K][S]
@@ -211,6 +214,202 @@ __global__ void k_observed_norm(StaticDev st, double *derived) {
 }
 
 // ---------------------------------------------------------------------------------
+// probability models on the device: W, P and valid_probs of a phase from
+// its refinable probability parameters, as pyxrd/probabilities/models do in update() + solve() +
+// validate() (base_models.py:142-241).  Families: R0 G1..G6 (R0models.py:68-83), R1G2
+// (R1models.py:125-139), R2G2 (R2models.py:195-233), R3G2 (R3models.py:158-198).
+// The level matrices lW[r] / lP[r] (rank G^(r+1)) and the multi-index access mW[i,j,..] /
+// mP[i,j,..] of base_models.py:52-70,243-285 are kept as they are in the reference, so that
+// every model reads like its update(); all arithmetic is single IEEE operations in the
+// reference's order (bit-identical W, P; tests/golden/models.npz).  Parameters are clamped to the
+// bounds of their properties first (cast_property.py:44-47).  State convention: the converged
+// level matrices (a model object that has seen update() twice), i.e. update() is evaluated twice.
+// ---------------------------------------------------------------------------------
+#define PX_PROB_FIXED 0
+#define PX_PROB_R0 1
+#define PX_PROB_R1G2 2
+#define PX_PROB_R2G2 3
+#define PX_PROB_R3G2 4
+
+struct ProbLevels {
+    int R, G, Rp;
+    double W[4][64];      // lW[0 .. Rp-1], lW[Rp] = W . P
+    double P[3][64];      // lP[0 .. Rp-1]
+    __device__ int ipow(int e) const { int v = 1; for (int i = 0; i < e; ++i) v *= G; return v; }
+    __device__ int wrank(int r) const { return ipow(r < Rp ? r + 1 : Rp); }
+    __device__ int prank(int r) const { return ipow(r + 1); }
+    __device__ void xy(const int *ind, int Rl, int &x, int &y) const {
+        x = 0; y = 0;
+        for (int i = 1; i <= Rl; ++i) { const int f = ipow(Rl - i); x += ind[i - 1] * f; y += ind[i] * f; }
+    }
+    __device__ double &mW(const int *ind, int l) {             // base_models.py:263-281
+        if (l == Rp + 1) {
+            int x, y;
+            xy(ind, l - 1 > 1 ? l - 1 : 1, x, y);
+            return W[l - 1][x * wrank(l - 1) + y];
+        }
+        int x = 0;
+        for (int i = 0; i < l; ++i) x += ind[i] * ipow(l - (i + 1));
+        return W[l - 1][x * wrank(l - 1) + x];
+    }
+    __device__ double &mP(const int *ind, int l) {             // base_models.py:243-261
+        int x, y;
+        xy(ind, l - 1 > 1 ? l - 1 : 1, x, y);
+        return P[l - 2][x * prank(l - 2) + y];
+    }
+    __device__ double &W1(int a) { int i[1] = {a}; return mW(i, 1); }
+    __device__ double &W2(int a, int b) { int i[2] = {a, b}; return mW(i, 2); }
+    __device__ double &W3(int a, int b, int c) { int i[3] = {a, b, c}; return mW(i, 3); }
+    __device__ double &P2(int a, int b) { int i[2] = {a, b}; return mP(i, 2); }
+    __device__ double &P3(int a, int b, int c) { int i[3] = {a, b, c}; return mP(i, 3); }
+    __device__ double &P4(int a, int b, int c, int d) { int i[4] = {a, b, c, d}; return mP(i, 4); }
+};
+
+__device__ __forceinline__ double pm_clamp(double v, double lo) { return fmin(fmax(v, lo), 1.0); }
+__device__ __forceinline__ double pm_c01(double v) { return fmax(fmin(v, 1.0), 0.0); }      // max(min(v, 1.0), 0.0)
+__device__ __forceinline__ double pm_sub(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ double pm_muldiv(double a, double b, double c) { return __ddiv_rn(__dmul_rn(a, b), c); }
+
+__device__ void prob_solve(ProbLevels &lv) {                    // base_models.py:142-162
+    const int G = lv.G;
+    for (int num = 1; num < lv.R; ++num) {
+        int base[4];
+        for (int code = 0, n = lv.ipow(num); code < n; ++code) {
+            for (int i = 0, c = code; i < num; ++i) { base[num - i] = c % G; c /= G; }      // base[1..num]
+            double acc = 0.0;
+            for (int i = 0; i < G; ++i) { base[0] = i; acc = __dadd_rn(acc, lv.mW(base, num + 1)); }
+            lv.mW(base + 1, num) = acc;
+        }
+        for (int code = 0, n = lv.ipow(num + 1); code < n; ++code) {
+            for (int i = 0, c = code; i <= num; ++i) { base[num - i] = c % G; c /= G; }      // base[0..num]
+            const double w = lv.mW(base, num);
+            lv.mP(base, num + 1) = w > 0.0 ? __ddiv_rn(lv.mW(base, num + 1), w) : 0.0;
+        }
+    }
+    const int r = lv.wrank(lv.Rp);
+    const double *Wt = lv.W[lv.Rp - 1], *Pt = lv.P[lv.Rp - 1];
+    for (int i = 0; i < r; ++i)
+        for (int j = 0; j < r; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < r; ++k) acc = fma(Wt[i * r + k], Pt[k * r + j], acc);
+            lv.W[lv.Rp][i * r + j] = acc;
+        }
+}
+
+__device__ void prob_update(ProbLevels &lv, int model, const double *par) {
+    const int G = lv.G;
+    if (model == PX_PROB_R0) {
+        if (G > 1) {
+            double run = 0.0;                                   // np.sum(np.diag(W)[0:i]), sequential
+            for (int i = 0; i < G - 1; ++i) {
+                const double F = pm_clamp(par[i], 0.0);
+                const double w = i > 0 ? __dmul_rn(F, pm_sub(1.0, run)) : F;
+                lv.W1(i) = w;
+                run = i > 0 ? __dadd_rn(run, w) : w;
+            }
+            lv.W1(G - 1) = pm_sub(1.0, run);
+        } else {
+            lv.W1(0) = 1.0;
+        }
+        for (int i = 0; i < G; ++i)
+            for (int j = 0; j < G; ++j) lv.P[0][i * G + j] = lv.W[0][j * G + j];
+    } else if (model == PX_PROB_R1G2) {
+        const double W1 = pm_clamp(par[0], 0.0), Pxx = pm_clamp(par[1], 0.0);
+        lv.W1(0) = W1;
+        lv.W1(1) = pm_sub(1.0, W1);
+        if (lv.W1(0) <= 0.5) {
+            lv.P2(0, 0) = Pxx;
+            lv.P2(0, 1) = pm_sub(1.0, lv.P2(0, 0));
+            lv.P2(1, 0) = pm_muldiv(lv.W1(0), lv.P2(0, 1), lv.W1(1));
+            lv.P2(1, 1) = pm_sub(1.0, lv.P2(1, 0));
+        } else {
+            lv.P2(1, 1) = Pxx;
+            lv.P2(1, 0) = pm_sub(1.0, lv.P2(1, 1));
+            lv.P2(0, 1) = pm_muldiv(lv.W1(1), lv.P2(1, 0), lv.W1(0));
+            lv.P2(0, 0) = pm_sub(1.0, lv.P2(0, 1));
+        }
+    } else if (model == PX_PROB_R2G2) {
+        const double W1 = pm_clamp(par[0], 0.5), Pa = pm_clamp(par[1], 0.0), P21 = pm_clamp(par[2], 0.0),
+                     Pb = pm_clamp(par[3], 0.0);
+        lv.W1(0) = W1;
+        lv.W1(1) = pm_sub(1.0, lv.W1(0));
+        lv.P2(1, 0) = P21;
+        lv.P2(1, 1) = pm_sub(1.0, lv.P2(1, 0));
+        lv.W2(1, 0) = __dmul_rn(lv.W1(1), lv.P2(1, 0));
+        lv.W2(1, 1) = __dmul_rn(lv.W1(1), lv.P2(1, 1));
+        lv.W2(0, 1) = lv.W2(1, 0);
+        lv.W2(0, 0) = pm_sub(lv.W1(0), lv.W2(1, 0));
+        if (lv.W1(0) <= 2.0 / 3.0) {
+            lv.P3(0, 0, 1) = Pa;
+            lv.P3(1, 0, 0) = lv.W2(1, 0) == 0.0 ? 0.0 : pm_muldiv(lv.P3(0, 0, 1), lv.W2(0, 0), lv.W2(1, 0));
+        } else {
+            lv.P3(1, 0, 0) = Pa;
+            lv.P3(0, 0, 1) = lv.W2(0, 0) == 0.0 ? 0.0 : pm_muldiv(lv.P3(1, 0, 0), lv.W2(1, 0), lv.W2(0, 0));
+        }
+        lv.P3(1, 0, 1) = pm_sub(1.0, lv.P3(1, 0, 0));
+        lv.P3(0, 0, 0) = pm_sub(1.0, lv.P3(0, 0, 1));
+        if (lv.P2(1, 0) <= 0.5) {
+            lv.P3(0, 1, 1) = Pb;
+            lv.P3(1, 1, 0) = pm_muldiv(lv.P3(0, 1, 1), lv.W2(0, 1), lv.W2(1, 1));
+        } else {
+            lv.P3(1, 1, 0) = Pb;
+            lv.P3(0, 1, 1) = pm_muldiv(lv.P3(1, 1, 0), lv.W2(1, 1), lv.W2(0, 1));
+        }
+        lv.P3(0, 1, 0) = pm_sub(1.0, lv.P3(0, 1, 1));
+        lv.P3(1, 1, 1) = pm_sub(1.0, lv.P3(1, 1, 0));
+    } else if (model == PX_PROB_R3G2) {
+        const double W1 = pm_clamp(par[0], 2.0 / 3.0), Px = pm_clamp(par[1], 0.0);
+        lv.W1(0) = W1;
+        lv.W1(1) = pm_sub(1.0, W1);
+        const double w0 = lv.W1(0), w1 = lv.W1(1), w0m2w1 = pm_sub(w0, __dmul_rn(2.0, w1));
+        if (w0 <= 0.75) {
+            lv.P4(0, 0, 0, 0) = Px;
+            lv.P4(0, 0, 0, 1) = pm_c01(pm_sub(1.0, lv.P4(0, 0, 0, 0)));
+            lv.P4(1, 0, 0, 0) = pm_c01(pm_muldiv(lv.P4(0, 0, 0, 1), w0m2w1, w1));
+            lv.P4(1, 0, 0, 1) = pm_c01(pm_sub(1.0, lv.P4(1, 0, 0, 0)));
+        } else {
+            lv.P4(1, 0, 0, 1) = Px;
+            lv.P4(1, 0, 0, 0) = pm_c01(pm_sub(1.0, lv.P4(1, 0, 0, 1)));
+            lv.P4(0, 0, 0, 0) = pm_c01(pm_sub(1.0, pm_muldiv(lv.P4(1, 0, 0, 0), w1, w0m2w1)));
+            lv.P4(0, 0, 0, 1) = pm_c01(pm_sub(1.0, lv.P4(0, 0, 0, 0)));
+        }
+        const int fixed[6][3] = {{0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}, {1, 1, 1}};
+        for (int t = 0; t < 6; ++t) {
+            lv.P4(fixed[t][0], fixed[t][1], fixed[t][2], 0) = 1.0;
+            lv.P4(fixed[t][0], fixed[t][1], fixed[t][2], 1) = 0.0;
+        }
+        lv.W3(0, 0, 0) = pm_c01(pm_sub(__dmul_rn(3.0, w0), 2.0));
+        lv.W3(1, 0, 1) = 0.0; lv.W3(1, 1, 0) = 0.0; lv.W3(1, 1, 1) = 0.0; lv.W3(0, 1, 1) = 0.0;
+        const double wm = pm_c01(pm_sub(1.0, w0));
+        lv.W3(1, 0, 0) = wm; lv.W3(0, 1, 0) = wm; lv.W3(0, 0, 1) = wm;
+    }
+    prob_solve(lv);
+}
+
+// -> rank; W (diagonal matrix) and P written row-major, *valid = every entry of every level in [0, 1]
+__device__ int prob_evaluate(int model, int G, const double *par, double *Wout, double *Pout, int *valid) {
+    ProbLevels lv;
+    lv.G = G;
+    lv.R = model == PX_PROB_R0 ? 0 : model == PX_PROB_R1G2 ? 1 : model == PX_PROB_R2G2 ? 2 : 3;
+    lv.Rp = lv.R > 1 ? lv.R : 1;
+    for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 64; ++i) lv.W[r][i] = 0.0;
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < 64; ++i) lv.P[r][i] = 0.0;
+    prob_update(lv, model, par);
+    prob_update(lv, model, par);
+    bool ok = true;
+    for (int r = 0; r <= lv.Rp; ++r)
+        for (int i = 0, n = lv.wrank(r) * lv.wrank(r); i < n; ++i) ok = ok && !(lv.W[r][i] < 0.0 || lv.W[r][i] > 1.0);
+    for (int r = 0; r < lv.Rp; ++r)
+        for (int i = 0, n = lv.prank(r) * lv.prank(r); i < n; ++i) ok = ok && !(lv.P[r][i] < 0.0 || lv.P[r][i] > 1.0);
+    const int rank = lv.wrank(lv.Rp);
+    for (int i = 0; i < rank * rank; ++i) { Wout[i] = lv.W[lv.Rp - 1][i]; Pout[i] = lv.P[lv.Rp - 1][i]; }
+    *valid = ok ? 1 : 0;
+    return rank;
+}
+
+// ---------------------------------------------------------------------------------
 // per-candidate prologue
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ double lognormal_dev(double T, double a, double b) {
@@ -255,13 +454,34 @@ __device__ void csds_series(const double *pd, int nmin, int nmax, double *arr, d
     *ntop_out = ntop;
 }
 
+// thread per phase: W | P of the pool entry and valid_probs from the probability parameters
+__global__ void k_probabilities(BatchDev bt) {
+    const int pb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pb >= bt.NP) return;
+    const int *pi = bt.phase_i + pb * 8;
+    int valid = (pi[4] & 1) ? 1 : 0;
+    const int model = bt.prob_model ? bt.prob_model[pb] : PX_PROB_FIXED;
+    if (valid && model != PX_PROB_FIXED && !(pi[4] & 8)) {
+        double *W = const_cast<double *>(bt.matrices) + pi[6];
+        prob_evaluate(model, pi[0], bt.prob_params + pb * 8, W, W + pi[1] * pi[1], &valid);
+    }
+    bt.phase_valid[pb] = valid;
+}
+
+__global__ void k_leaf_probabilities(int model, int G, const double *par, double *W, double *P, int *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int valid;
+    out[1] = prob_evaluate(model, G, par, W, P, &valid);
+    out[0] = valid;
+}
+
 __global__ void k_phase_prologue(BatchDev bt) {
     const int pb = blockIdx.x * blockDim.x + threadIdx.x;
     if (pb >= bt.NP) return;
     const int *pi = bt.phase_i + pb * 8;
     const double *pd = bt.phase_d + pb * 8;
     double *px = bt.phase_x + pb * 4;
-    if (!(pi[4] & 1) || (pi[4] & 8)) { px[0] = 0.0; px[1] = 0.0; px[2] = 0.0; return; }   // invalid probabilities / raw pattern
+    if (!bt.phase_valid[pb] || (pi[4] & 8)) { px[0] = 0.0; px[1] = 0.0; px[2] = 0.0; return; }   // invalid probabilities / raw pattern
     const int G = pi[0], r = pi[1];
     double mean;
     int ntop;
@@ -533,6 +753,14 @@ __device__ __forceinline__ double finish_point(double tr, double abs_scale, int 
     return I;
 }
 
+// invalid probabilities (decided on the device for model-driven phases) -> zeros (phases.py:109-111)
+__device__ __forceinline__ bool phase_is_invalid(const BatchDev &bt, int pb, int job, int X, int x0, int tile) {
+    if (bt.phase_valid[pb]) return false;
+    double *out = bt.intensities + bt.job_out[job];
+    for (int x = x0 + threadIdx.x; x < X && x < x0 + tile; x += blockDim.x) out[x] = 0.0;
+    return true;
+}
+
 // ---- ranks up to 9: every vector in registers, PPT points per thread -----------------
 // A thread owns the points x0 + t + k * TPB, k < PPT: the warp-uniform work (shared-memory
 // reads of the atom / plane lists and of P, loop control, coefficient fetches) is paid once for
@@ -552,7 +780,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     const int pb = bt.job_pb[job], s = bt.job_spec[job];
     const int X = st.spec_npts[s];
     const int x0 = blockIdx.y * (TPB * PPT);
-    if (x0 >= X) return;
+    if (x0 >= X || phase_is_invalid(bt, pb, job, X, x0, TPB * PPT)) return;
     const int *pi = bt.phase_i + pb * 8;
     const double *px = bt.phase_x + pb * 4;
     const int ntop = (int)px[2];
@@ -739,7 +967,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev 
     const int pb = bt.job_pb[job], s = bt.job_spec[job];
     const int X = st.spec_npts[s];
     const int x0 = blockIdx.y * PX_TPB;
-    if (x0 >= X) return;
+    if (x0 >= X || phase_is_invalid(bt, pb, job, X, x0, PX_TPB)) return;
     const int *pi = bt.phase_i + pb * 8;
     const double *px = bt.phase_x + pb * 4;
     const int ntop = (int)px[2];
@@ -897,7 +1125,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_mma(StaticDev st, BatchDev bt,
     const int pb = bt.job_pb[job], s = bt.job_spec[job];
     const int X = st.spec_npts[s];
     const int x0 = blockIdx.y * PX_TPB;
-    if (x0 >= X) return;
+    if (x0 >= X || phase_is_invalid(bt, pb, job, X, x0, PX_TPB)) return;
     const int *pi = bt.phase_i + pb * 8;
     const double *px = bt.phase_x + pb * 4;
     const int ntop = (int)px[2];
@@ -1093,7 +1321,7 @@ __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, Batc
     const int pb = bt.job_pb[job], s = bt.job_spec[job];
     const int X = st.spec_npts[s];
     const int x0 = blockIdx.y * PX_GEN_TPB;
-    if (x0 >= X) return;
+    if (x0 >= X || phase_is_invalid(bt, pb, job, X, x0, PX_GEN_TPB)) return;
     const int *pi = bt.phase_i + pb * 8;
     const int G = pi[0], R = pi[1], REPS = R / G;
     double *sP = reinterpret_cast<double *>(smem_raw + sizeof(PhaseSmem));    // [R][R]

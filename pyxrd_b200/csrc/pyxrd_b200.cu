@@ -96,7 +96,7 @@ struct pyxrd_ctx {
     DevBuf d_blob;           // all uploaded batch arrays, one allocation
     PinBuf h_blob;
     const int *jobids_dev = nullptr;   // inside d_blob
-    DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
+    DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_phase_valid, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
     int residual_method = PYXRD_RESIDUAL_RP;   // settings.RESIDUAL_METHOD (mixture.py:22-27,89)
     DevBuf d_selpos, d_selcount;
     std::vector<int> h_selcount;
@@ -304,7 +304,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_invsin, &ctx->d_stl,
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob,
-                      &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
+                      &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
                       &ctx->d_res, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
@@ -465,6 +465,12 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
             return fail(ctx, "set_batch: phase %d has unsupported G=%d rank=%d (need 1<=G<=%d, rank<=%d, rank %% G == 0)",
                         p, G, r, PYXRD_MAX_COMPONENTS, PYXRD_MAX_RANK);
         if (pi[2] < 0 || pi[3] < pi[2]) return fail(ctx, "set_batch: phase %d CSDS range [%d, %d] unsupported", p, pi[2], pi[3]);
+        if (d->prob_model && d->prob_params && d->prob_model[p] != PYXRD_PROB_FIXED) {
+            const int m = d->prob_model[p];
+            const int want = m == PYXRD_PROB_R0 ? G : m == PYXRD_PROB_R1G2 ? 2 : m == PYXRD_PROB_R2G2 ? 4 : m == PYXRD_PROB_R3G2 ? 8 : -1;
+            if (want != r || (m != PYXRD_PROB_R0 && G != 2) || (m == PYXRD_PROB_R0 && G > 6))
+                return fail(ctx, "set_batch: phase %d: probability model %d does not fit G=%d rank=%d", p, m, G, r);
+        }
         ncap = std::max(ncap, pi[3] + 2);
         int atoms = 0;
         for (int c = 0; c < G; ++c) {
@@ -542,6 +548,9 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     const size_t i_frac = add(d->fractions, sizeof(double) * (size_t)K * M);
     const size_t i_scales = add(d->scales, sizeof(double) * (size_t)K * S);
     const size_t i_bg = add(d->bgshifts, sizeof(double) * (size_t)K * S);
+    const bool model_driven = d->prob_model && d->prob_params;
+    const size_t i_pmodel = add(model_driven ? d->prob_model : nullptr, model_driven ? sizeof(int32_t) * (size_t)NP : 0);
+    const size_t i_pparam = add(model_driven ? d->prob_params : nullptr, model_driven ? sizeof(double) * (size_t)NP * PYXRD_PROB_STRIDE : 0);
     CK(cudaStreamSynchronize(ctx->stream));        // the pinned blob may still feed a previous copy
     CK(ctx->h_blob.ensure(total));
     CK(ctx->d_blob.ensure(total));
@@ -554,6 +563,7 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     CK(ctx->d_atom_plane.ensure(sizeof(int) * std::max(NA, 1)));
     CK(ctx->d_comp_np.ensure(sizeof(int) * std::max(NC, 1)));
     CK(ctx->d_phase_x.ensure(sizeof(double) * 4 * std::max(NP, 1)));
+    CK(ctx->d_phase_valid.ensure(sizeof(int) * std::max(NP, 1)));
     CK(ctx->d_coef.ensure(sizeof(double) * (size_t)ncap * std::max(NP, 1)));
     ctx->int_count = (int64_t)K * cand_stride;
     ctx->tot_count = (int64_t)K * Z * st.sumX;
@@ -583,6 +593,9 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     bt.comp_nplanes = ctx->d_comp_np.as<int>();
     bt.phase_x = ctx->d_phase_x.as<double>();
     bt.coef = ctx->d_coef.as<double>();
+    bt.prob_model = model_driven ? reinterpret_cast<const int *>(dev(i_pmodel)) : nullptr;
+    bt.prob_params = model_driven ? reinterpret_cast<const double *>(dev(i_pparam)) : nullptr;
+    bt.phase_valid = ctx->d_phase_valid.as<int>();
     bt.job_pb = reinterpret_cast<const int *>(dev(i_job_pb));
     bt.job_spec = reinterpret_cast<const int *>(dev(i_job_spec));
     bt.job_out = reinterpret_cast<const long long *>(dev(i_job_out));
@@ -605,6 +618,8 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
 
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
     if (NP > 0) {
+        k_probabilities<<<(NP + 63) / 64, 64, 0, ctx->stream>>>(bt);
+        LAUNCH_CHECK("k_probabilities");
         k_phase_prologue<<<(NP + 63) / 64, 64, 0, ctx->stream>>>(bt);
         LAUNCH_CHECK("k_phase_prologue");
     }
@@ -952,6 +967,167 @@ int pyxrd_leaf_component(pyxrd_ctx *ctx, const double *stl, int64_t n, const dou
         if (NA) CK(cudaMemcpyAsync(z_out, base + off_z, 8 * (size_t)NA, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- population from a template + binding table (host side: layout only) ------------------------
+}  // extern "C"
+
+struct pyxrd_expanded {
+    pyxrd_batch_desc desc{};
+    std::vector<int32_t> phase_i, phase_comp, comp_i, atom_type, job_phase, prob_model;
+    std::vector<double> phase_d, matrices, comp_d, atom_d, fractions, scales, bgshifts, prob_params;
+};
+
+namespace {
+thread_local std::string g_expand_error;
+
+template <class T>
+void replicate(std::vector<T> &dst, const T *src, size_t n, int K) {
+    dst.resize(n * (size_t)K);
+    for (int k = 0; k < K; ++k)
+        if (n) memcpy(dst.data() + (size_t)k * n, src, n * sizeof(T));
+}
+}  // namespace
+
+extern "C" {
+
+const char *pyxrd_expand_error(void) { return g_expand_error.c_str(); }
+
+int pyxrd_expand_population(const pyxrd_batch_desc *t, const pyxrd_population_desc *pop, pyxrd_expanded **out) {
+    auto bad = [&](const std::string &msg) { g_expand_error = msg; return 1; };
+    if (!t || !pop || !out) return bad("expand_population: null argument");
+    *out = nullptr;
+    if (t->n_candidates != 1) return bad("expand_population: the template must hold exactly one candidate");
+    const int K = pop->n_candidates, D = pop->n_params, S = pop->n_specimens, Z = pop->n_patterns;
+    if (K <= 0 || D < 0 || pop->n_bindings < 0 || S <= 0 || Z <= 0) return bad("expand_population: need K, S, Z > 0");
+    const int NP = t->n_phases, NC = t->n_components, NA = t->n_atoms, NPC = t->n_phase_comp, M = t->n_phase_slots;
+    const int64_t NM = t->n_matrix;
+    const size_t JPC = (size_t)S * Z * M;
+    if ((int64_t)NP * K > 0x7fffffffLL || (int64_t)NA * K > 0x7fffffffLL || NM * K > 0x7fffffffLL)
+        return bad("expand_population: population too large for 32-bit indices");
+    pyxrd_expanded *e = new pyxrd_expanded();
+    replicate(e->phase_i, t->phase_i, (size_t)NP * PYXRD_PHASE_I_STRIDE, K);
+    replicate(e->phase_d, t->phase_d, (size_t)NP * PYXRD_PHASE_D_STRIDE, K);
+    replicate(e->phase_comp, t->phase_comp, (size_t)NPC, K);
+    replicate(e->matrices, t->matrices, (size_t)NM, K);
+    replicate(e->comp_d, t->comp_d, (size_t)NC * PYXRD_COMP_D_STRIDE, K);
+    replicate(e->comp_i, t->comp_i, (size_t)NC * PYXRD_COMP_I_STRIDE, K);
+    replicate(e->atom_d, t->atom_d, (size_t)NA * PYXRD_ATOM_D_STRIDE, K);
+    replicate(e->atom_type, t->atom_type, (size_t)NA, K);
+    replicate(e->job_phase, t->job_phase, JPC, K);
+    replicate(e->fractions, t->fractions, (size_t)M, K);
+    replicate(e->scales, t->scales, (size_t)S, K);
+    replicate(e->bgshifts, t->bgshifts, (size_t)S, K);
+    const bool model_driven = t->prob_model && t->prob_params;
+    if (model_driven) {
+        replicate(e->prob_model, t->prob_model, (size_t)NP, K);
+        replicate(e->prob_params, t->prob_params, (size_t)NP * PYXRD_PROB_STRIDE, K);
+    }
+    // the indices that point into per-candidate tables move with the candidate
+    for (int k = 1; k < K; ++k) {
+        for (int p = 0; p < NP; ++p) {
+            int32_t *pi = e->phase_i.data() + ((size_t)k * NP + p) * PYXRD_PHASE_I_STRIDE;
+            pi[5] += k * NPC;
+            pi[6] += (int32_t)(k * NM);
+        }
+        for (int i = 0; i < NPC; ++i) e->phase_comp[(size_t)k * NPC + i] += k * NC;
+        for (int c = 0; c < NC; ++c) e->comp_i[((size_t)k * NC + c) * PYXRD_COMP_I_STRIDE] += k * NA;
+        for (size_t j = 0; j < JPC; ++j)
+            if (e->job_phase[(size_t)k * JPC + j] >= 0) e->job_phase[(size_t)k * JPC + j] += k * NP;
+    }
+    // slot = scale * x[param] + offset
+    struct Target { double *base; size_t per_candidate; };
+    const Target targets[8] = {{e->phase_d.data(), (size_t)NP * PYXRD_PHASE_D_STRIDE}, {e->comp_d.data(), (size_t)NC * PYXRD_COMP_D_STRIDE},
+                               {e->atom_d.data(), (size_t)NA * PYXRD_ATOM_D_STRIDE}, {e->matrices.data(), (size_t)NM},
+                               {e->prob_params.data(), model_driven ? (size_t)NP * PYXRD_PROB_STRIDE : 0}, {e->fractions.data(), (size_t)M},
+                               {e->scales.data(), (size_t)S}, {e->bgshifts.data(), (size_t)S}};
+    for (int b = 0; b < pop->n_bindings; ++b) {
+        const pyxrd_binding &bd = pop->bindings[b];
+        if (bd.target < 0 || bd.target > 7 || bd.param < 0 || bd.param >= D || bd.index < 0 ||
+            (size_t)bd.index >= targets[bd.target].per_candidate) {
+            delete e;
+            return bad("expand_population: binding " + std::to_string(b) + " is out of range");
+        }
+        const Target &tg = targets[bd.target];
+        for (int k = 0; k < K; ++k)
+            tg.base[(size_t)k * tg.per_candidate + bd.index] = bd.scale * pop->x[(size_t)k * D + bd.param] + bd.offset;
+    }
+    if (pop->csds_auto_maximum)
+        for (int k = 0; k < K; ++k)
+            for (int p = 0; p < NP; ++p)
+                if (pop->csds_auto_maximum[p])      // maximum = int(factor * average)  (phases/models/CSDS.py:127,140)
+                    e->phase_i[((size_t)k * NP + p) * PYXRD_PHASE_I_STRIDE + 3] =
+                        (int32_t)(pop->csds_factor * e->phase_d[((size_t)k * NP + p) * PYXRD_PHASE_D_STRIDE + 1]);
+    pyxrd_batch_desc &d = e->desc;
+    d.n_candidates = K; d.n_phase_slots = M; d.n_phases = NP * K; d.n_components = NC * K; d.n_atoms = NA * K;
+    d.n_phase_comp = NPC * K; d.n_matrix = NM * K;
+    d.phase_i = e->phase_i.data(); d.phase_d = e->phase_d.data(); d.phase_comp = e->phase_comp.data();
+    d.matrices = e->matrices.data(); d.comp_d = e->comp_d.data(); d.comp_i = e->comp_i.data();
+    d.atom_d = e->atom_d.data(); d.atom_type = e->atom_type.data(); d.job_phase = e->job_phase.data();
+    d.fractions = e->fractions.data(); d.scales = e->scales.data(); d.bgshifts = e->bgshifts.data();
+    d.prob_model = model_driven ? e->prob_model.data() : nullptr;
+    d.prob_params = model_driven ? e->prob_params.data() : nullptr;
+    *out = e;
+    return 0;
+}
+
+void pyxrd_expanded_desc(const pyxrd_expanded *e, pyxrd_batch_desc *out) {
+    if (e && out) *out = e->desc;
+}
+
+void pyxrd_expanded_free(pyxrd_expanded *e) { delete e; }
+
+int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop) {
+    if (!ctx) return 1;
+    if (!ctx->have_static) return fail(ctx, "set_population: call pyxrd_set_static first");
+    if (pop && (pop->n_specimens != ctx->st.S || pop->n_patterns != ctx->st.Z))
+        return fail(ctx, "set_population: S / Z of the population (%d, %d) differ from the static tables (%d, %d)",
+                    pop->n_specimens, pop->n_patterns, ctx->st.S, ctx->st.Z);
+    pyxrd_expanded *e = nullptr;
+    if (pyxrd_expand_population(t, pop, &e)) return fail(ctx, "%s", g_expand_error.c_str());
+    const int rc = pyxrd_set_batch(ctx, &e->desc);       // copies everything into its pinned blob
+    pyxrd_expanded_free(e);
+    return rc;
+}
+
+int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop, double *residuals_out) {
+    if (pyxrd_set_population(ctx, t, pop)) return 1;
+    if (pyxrd_compute_intensities(ctx)) return 1;
+    if (pyxrd_compute_residuals(ctx, 0)) return 1;
+    return pyxrd_read_residuals(ctx, residuals_out, (int64_t)ctx->bt.K * (ctx->st.S + 1));
+}
+
+int pyxrd_optimize_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop, int refine_bg,
+                              int outer_iterations, int newton_iterations, double *residuals_out, double *solutions_out) {
+    if (pyxrd_set_population(ctx, t, pop)) return 1;
+    if (pyxrd_compute_intensities(ctx)) return 1;
+    if (pyxrd_optimize(ctx, refine_bg, outer_iterations, newton_iterations)) return 1;
+    if (pyxrd_read_opt_residuals(ctx, residuals_out, (int64_t)ctx->bt.K * (ctx->st.S + 1))) return 1;
+    if (solutions_out) return pyxrd_read_solutions(ctx, solutions_out, (int64_t)ctx->bt.K * (ctx->bt.M + 2 * ctx->st.S));
+    return 0;
+}
+
+int pyxrd_leaf_probabilities(pyxrd_ctx *ctx, int model, int G, const double *params, double *W_out, double *P_out,
+                             int *valid_out, int *rank_out) {
+    if (!ctx || !params) return 1;
+    const int want = model == PYXRD_PROB_R0 ? G : model == PYXRD_PROB_R1G2 ? 2 : model == PYXRD_PROB_R2G2 ? 4 : model == PYXRD_PROB_R3G2 ? 8 : -1;
+    if (want < 1 || (model != PYXRD_PROB_R0 && G != 2) || (model == PYXRD_PROB_R0 && (G < 1 || G > 6)))
+        return fail(ctx, "leaf_probabilities: model %d with G = %d is not available", model, G);
+    CK(cudaSetDevice(ctx->device));
+    if (upload(ctx, ctx->d_leaf_a, params, PYXRD_PROB_STRIDE)) return 1;
+    CK(ctx->d_leaf_b.ensure(sizeof(double) * 128));
+    CK(ctx->d_leaf_c.ensure(sizeof(int) * 2));
+    k_leaf_probabilities<<<1, 32, 0, ctx->stream>>>(model, G, ctx->d_leaf_a.as<double>(), ctx->d_leaf_b.as<double>(),
+                                                     ctx->d_leaf_b.as<double>() + 64, ctx->d_leaf_c.as<int>());
+    LAUNCH_CHECK("k_leaf_probabilities");
+    int flags[2] = {0, 0};
+    CK(cudaMemcpyAsync(flags, ctx->d_leaf_c.ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(W_out, ctx->d_leaf_b.ptr, sizeof(double) * want * want, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(P_out, ctx->d_leaf_b.as<double>() + 64, sizeof(double) * want * want, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (valid_out) *valid_out = flags[0];
+    if (rank_out) *rank_out = flags[1];
     return 0;
 }
 

@@ -32,7 +32,33 @@ FLAG_APPLY_LPF = 2
 FLAG_APPLY_CORRECTION = 4
 FLAG_RAW_PATTERN = 8
 
+PROB_STRIDE = 8
+# PYXRD_PROB_* of include/pyxrd_b200.h: probability models the device evaluates itself
+PROB_MODELS = {"fixed": 0, "R0": 1, "R1G2": 2, "R2G2": 3, "R3G2": 4}
+_PROB_RANK = {1: lambda G: G, 2: lambda G: 2, 3: lambda G: 4, 4: lambda G: 8}
+_PROB_NPAR = {1: lambda G: G - 1, 2: lambda G: 2, 3: lambda G: 4, 4: lambda G: 2}
+
 _DIV_MODES = {"FIXED": 0.0, "AUTOMATIC": 1.0}
+
+
+def prob_model_of(phase):
+    """(model code, parameter list) of a phase whose W / P the device derives from its probability
+    parameters: ad-hoc attributes ``prob_model`` ("R0" | "R1G2" | "R2G2" | "R3G2" or the code) and
+    ``prob_params`` on the PhaseData (a DataObject is an attribute bag, data_objects.py:29-31)."""
+    model = getattr(phase, "prob_model", None)
+    if model is None:
+        return 0, ()
+    code = PROB_MODELS[model] if isinstance(model, str) else int(model)
+    if code == 0:
+        return 0, ()
+    G = int(phase.G)
+    params = [float(v) for v in getattr(phase, "prob_params", ())]
+    if code not in _PROB_RANK or (code != 1 and G != 2) or (code == 1 and not 1 <= G <= 6):
+        raise ValueError("probability model %r is not available for G = %d" % (model, G))
+    if len(params) != _PROB_NPAR[code](G):
+        raise ValueError("probability model %r with G = %d takes %d parameters, got %d"
+                         % (model, G, _PROB_NPAR[code](G), len(params)))
+    return code, params
 
 
 def _atype_key(at) -> bytes:
@@ -58,7 +84,9 @@ def collect_atom_types(mixtures_or_specimens) -> Dict[bytes, int]:
         if spec is None:
             continue
         for phase in iter_phases(spec):
-            if getattr(phase, "type", "Phase") != "Phase" or not phase.valid_probs:
+            if getattr(phase, "type", "Phase") != "Phase":
+                continue
+            if not phase.valid_probs and getattr(phase, "prob_model", None) is None:
                 continue
             for comp in phase.components:
                 for atom in list(comp.layer_atoms) + list(comp.interlayer_atoms):
@@ -201,11 +229,18 @@ class BatchPack(object):
         atom_t: List[int] = []
         jobs: List[int] = []
         self.components_of_phase: List[List[object]] = []
+        self.prob_model_list: List[int] = []
+        self.prob_param_list: List[List[float]] = []
+        # id(object) -> packed index, of the FIRST candidate (what a population template binds to)
+        self.phase_index: Dict[int, int] = {}
+        self.comp_index: Dict[int, int] = {}
+        self.atom_index: Dict[int, int] = {}
         fractions = []
         scales = np.zeros((K, S))
         bgshifts = np.zeros((K, S))
         for k, mix in enumerate(mixtures):
             specimens = mix.specimens
+            self._atom_index_open = k == 0
             if len(specimens) != S:
                 raise ValueError("candidate %d has %d specimens, the static tables have %d" % (k, len(specimens), S))
             fr = np.asarray(mix.fractions, dtype=float).ravel()
@@ -235,6 +270,8 @@ class BatchPack(object):
                             mat_off = self._pack_phase(phase, static, phase_i, phase_d, phase_comp, matrices, mat_off,
                                                        comp_d, comp_i, atom_d, atom_t, comp_ids)
                         jobs.append(pid)
+            if k == 0:
+                self.phase_index, self.comp_index = dict(phase_ids), dict(comp_ids)
         self.K, self.M, self.S, self.Z = K, int(M or 0), S, Z
         self.phase_i = np.ascontiguousarray(np.array(phase_i, dtype=np.int32).reshape(-1, PHASE_I_STRIDE))
         self.phase_d = np.ascontiguousarray(np.array(phase_d, dtype=float).reshape(-1, PHASE_D_STRIDE))
@@ -248,6 +285,15 @@ class BatchPack(object):
         self.fractions = np.ascontiguousarray(np.array(fractions, dtype=float).reshape(K, self.M))
         self.scales = np.ascontiguousarray(scales)
         self.bgshifts = np.ascontiguousarray(bgshifts)
+        if any(self.prob_model_list):
+            self.prob_model = np.ascontiguousarray(np.array(self.prob_model_list, dtype=np.int32))
+            self.prob_params = np.zeros((len(self.prob_param_list), PROB_STRIDE))
+            for i, row in enumerate(self.prob_param_list):
+                self.prob_params[i, :len(row)] = row
+        else:
+            self.prob_model = self.prob_params = None
+
+    _atom_index_open = True
 
     def _pack_phase(self, phase, static, phase_i, phase_d, phase_comp, matrices, mat_off,
                     comp_d, comp_i, atom_d, atom_t, comp_ids):
@@ -274,17 +320,28 @@ class BatchPack(object):
             matrices.append(rx[order])
             matrices.append(ry[order])
             self.components_of_phase.append([])
+            self.prob_model_list.append(0)
+            self.prob_param_list.append([])
             return mat_off + 2 * rx.size
-        if not phase.valid_probs:
+        model, model_params = prob_model_of(phase)
+        if not model and not phase.valid_probs:
             phase_i.append([0, 0, 0, 0, flags, 0, 0, 0])
             phase_d.append([0.0] * PHASE_D_STRIDE)
             self.components_of_phase.append([])
+            self.prob_model_list.append(0)
+            self.prob_param_list.append([])
             return mat_off
-        flags |= FLAG_VALID_PROBS
-        W = np.asarray(phase.W, dtype=float)
-        P = np.asarray(phase.P, dtype=float)
-        rank = P.shape[1]
+        flags |= FLAG_VALID_PROBS          # model-driven phases: the device decides (k_probabilities)
         G = int(phase.G)
+        if model:
+            rank = _PROB_RANK[model](G)
+            W = P = np.zeros((rank, rank))  # pool entry the device fills
+        else:
+            W = np.asarray(phase.W, dtype=float)
+            P = np.asarray(phase.P, dtype=float)
+            rank = P.shape[1]
+        self.prob_model_list.append(model)
+        self.prob_param_list.append(list(model_params))
         if W.shape != (rank, rank) or P.shape != (rank, rank):
             raise ValueError("W / P must be rank x rank")
         csds = phase.CSDS
@@ -313,6 +370,8 @@ class BatchPack(object):
                                float(comp.volume), float(comp.weight), 0.0, 0.0])
                 comp_i.append([len(atom_t), len(layer), len(inter), 0])
                 for atom in layer + inter:
+                    if self._atom_index_open and atom is not None:
+                        self.atom_index[id(atom)] = len(atom_t)
                     if atom is None or atom.atom_type is None:
                         atom_d.extend([0.0, 0.0])
                         atom_t.append(-1)

@@ -37,7 +37,23 @@ class BatchDesc(C.Structure):
                 ("n_matrix", C.c_int64), ("phase_i", _i32p), ("phase_d", _f64p), ("phase_comp", _i32p),
                 ("matrices", _f64p), ("comp_d", _f64p), ("comp_i", _i32p), ("atom_d", _f64p),
                 ("atom_type", _i32p), ("job_phase", _i32p), ("fractions", _f64p), ("scales", _f64p),
-                ("bgshifts", _f64p)]
+                ("bgshifts", _f64p), ("prob_model", _i32p), ("prob_params", _f64p)]
+
+
+class Binding(C.Structure):
+    _fields_ = [("param", C.c_int32), ("target", C.c_int32), ("index", C.c_int32), ("reserved", C.c_int32),
+                ("scale", C.c_double), ("offset", C.c_double)]
+
+
+BINDING_DTYPE = np.dtype([("param", "<i4"), ("target", "<i4"), ("index", "<i4"), ("reserved", "<i4"),
+                          ("scale", "<f8"), ("offset", "<f8")])
+
+
+class PopulationDesc(C.Structure):
+    _fields_ = [("n_candidates", C.c_int32), ("n_params", C.c_int32), ("n_bindings", C.c_int32),
+                ("n_specimens", C.c_int32), ("n_patterns", C.c_int32), ("reserved", C.c_int32),
+                ("x", _f64p), ("bindings", C.POINTER(Binding)), ("csds_auto_maximum", _u8p),
+                ("csds_factor", C.c_double)]
 
 
 # every symbol include/pyxrd_b200.h declares (checked by tests/test_abi.py)
@@ -49,6 +65,8 @@ EXPORTS = [
     "pyxrd_read_intensities", "pyxrd_read_scaled", "pyxrd_read_totals", "pyxrd_read_residuals",
     "pyxrd_read_correction", "pyxrd_device_buffers", "pyxrd_evaluate_host", "pyxrd_optimize_host", "pyxrd_leaf_asf",
     "pyxrd_leaf_lpf", "pyxrd_leaf_csds", "pyxrd_leaf_component", "pyxrd_stage_times", "pyxrd_dfma_peak",
+    "pyxrd_expand_population", "pyxrd_expanded_desc", "pyxrd_expanded_free", "pyxrd_expand_error",
+    "pyxrd_set_population", "pyxrd_evaluate_population", "pyxrd_optimize_population", "pyxrd_leaf_probabilities",
 ]
 
 _lib = None
@@ -110,6 +128,19 @@ def load_library():
         lib.pyxrd_leaf_component.argtypes = [vp, _f64p, C.c_int64, _f64p, C.c_int, C.c_int, _f64p, _f64p, _u8p,
                                              _f64p, _f64p, _f64p]
         lib.pyxrd_stage_times.argtypes = [vp, _f64p]
+        lib.pyxrd_expand_population.argtypes = [C.POINTER(BatchDesc), C.POINTER(PopulationDesc), C.POINTER(vp)]
+        lib.pyxrd_expanded_desc.argtypes = [vp, C.POINTER(BatchDesc)]
+        lib.pyxrd_expanded_desc.restype = None
+        lib.pyxrd_expanded_free.argtypes = [vp]
+        lib.pyxrd_expanded_free.restype = None
+        lib.pyxrd_expand_error.argtypes = []
+        lib.pyxrd_expand_error.restype = C.c_char_p
+        lib.pyxrd_set_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc)]
+        lib.pyxrd_evaluate_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc), _f64p]
+        lib.pyxrd_optimize_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc), C.c_int, C.c_int,
+                                                  C.c_int, _f64p, _f64p]
+        lib.pyxrd_leaf_probabilities.argtypes = [vp, C.c_int, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_int),
+                                                 C.POINTER(C.c_int)]
         lib.pyxrd_dfma_peak.argtypes = [vp, C.c_int, _f64p, _f64p]
         _lib = lib
         return lib
@@ -189,7 +220,9 @@ class Context(object):
                          b.phase_comp.shape[0], b.matrices.shape[0], _p(b.phase_i, _i32p), _p(b.phase_d, _f64p),
                          _p(b.phase_comp, _i32p), _p(b.matrices, _f64p), _p(b.comp_d, _f64p), _p(b.comp_i, _i32p),
                          _p(b.atom_d, _f64p), _p(b.atom_type, _i32p), _p(b.job_phase, _i32p),
-                         _p(b.fractions, _f64p), _p(b.scales, _f64p), _p(b.bgshifts, _f64p))
+                         _p(b.fractions, _f64p), _p(b.scales, _f64p), _p(b.bgshifts, _f64p),
+                         _p(b.prob_model, _i32p) if getattr(b, "prob_model", None) is not None else None,
+                         _p(b.prob_params, _f64p) if getattr(b, "prob_params", None) is not None else None)
 
     def set_batch(self, batch: BatchPack):
         d = self.batch_desc(batch)
@@ -346,6 +379,64 @@ class Context(object):
                     "leaf_component")
         return sf, phi, z[:na]
 
+    def leaf_probabilities(self, model, G, params):
+        """(W [r, r], P [r, r], valid_probs) of one probability model (PYXRD_PROB_*), evaluated on the
+        device as probabilities/models/*.py update() + solve() + validate() do"""
+        from .packing import PROB_MODELS, PROB_STRIDE
+        code = PROB_MODELS[model] if isinstance(model, str) else int(model)
+        p = np.zeros(PROB_STRIDE)
+        params = _f64(params).ravel()
+        p[:params.size] = params
+        W, P = np.zeros(64), np.zeros(64)
+        valid, rank = C.c_int(), C.c_int()
+        self._check(self._lib.pyxrd_leaf_probabilities(self._h, code, int(G), _p(p, _f64p), _p(W, _f64p), _p(P, _f64p),
+                                                       C.byref(valid), C.byref(rank)), "leaf_probabilities")
+        r = rank.value
+        return W[:r * r].reshape(r, r).copy(), P[:r * r].reshape(r, r).copy(), bool(valid.value)
+
+    # -- populations from a template + binding table ----------------------------------------
+    def _population_desc(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.ndim != 2:
+            raise ValueError("x must be [K, d]")
+        bindings = np.ascontiguousarray(bindings, dtype=BINDING_DTYPE)
+        auto = None if csds_auto is None else np.ascontiguousarray(csds_auto, dtype=np.uint8)
+        pop = PopulationDesc(x.shape[0], x.shape[1], bindings.size, template.S, template.Z, 0, _p(x, _f64p),
+                             bindings.ctypes.data_as(C.POINTER(Binding)), _p(auto, _u8p) if auto is not None else None,
+                             float(csds_factor))
+        return pop, (x, bindings, auto)
+
+    def evaluate_population(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5):
+        """residuals f64[K, 1+S] of the K candidates ``x`` [K, d] describes (one C-ABI call)"""
+        d = self.batch_desc(template)
+        pop, keep = self._population_desc(template, x, bindings, csds_auto, csds_factor)
+        K = keep[0].shape[0]
+        res = np.empty(K * (template.S + 1))
+        self._check(self._lib.pyxrd_evaluate_population(self._h, C.byref(d), C.byref(pop), _p(res, _f64p)),
+                    "evaluate_population")
+        self._batch = _Shape(K, template.M, template.S, template.Z)
+        return res.reshape(K, template.S + 1)
+
+    def set_population(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5):
+        d = self.batch_desc(template)
+        pop, keep = self._population_desc(template, x, bindings, csds_auto, csds_factor)
+        self._check(self._lib.pyxrd_set_population(self._h, C.byref(d), C.byref(pop)), "set_population")
+        self._batch = _Shape(keep[0].shape[0], template.M, template.S, template.Z)
+
+    def optimize_population(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5,
+                            refine_bg: bool = True, outer: int = 0, newton: int = 0):
+        """(optimised residuals [K, 1+S], solutions [K, M+2S]) of the K candidates (one C-ABI call)"""
+        d = self.batch_desc(template)
+        pop, keep = self._population_desc(template, x, bindings, csds_auto, csds_factor)
+        K = keep[0].shape[0]
+        res = np.empty(K * (template.S + 1))
+        sol = np.empty(K * (template.M + 2 * template.S))
+        self._check(self._lib.pyxrd_optimize_population(self._h, C.byref(d), C.byref(pop), int(bool(refine_bg)),
+                                                        int(outer), int(newton), _p(res, _f64p), _p(sol, _f64p)),
+                    "optimize_population")
+        self._batch = _Shape(K, template.M, template.S, template.Z)
+        return res.reshape(K, template.S + 1), sol.reshape(K, template.M + 2 * template.S)
+
     def stage_times(self):
         """dict of CUDA-event milliseconds of the latest phase / wavelength / residual / prologue stages"""
         out = np.zeros(4)
@@ -367,6 +458,58 @@ class Context(object):
         t, ms = C.c_double(), C.c_double()
         self._check(self._lib.pyxrd_dfma_peak(self._h, int(iterations), C.byref(t), C.byref(ms)), "dfma_peak")
         return t.value, ms.value
+
+
+class _Shape(object):
+    """K / M / S / Z of a batch that was expanded natively (nothing else of it exists on the Python side)"""
+
+    def __init__(self, K, M, S, Z):
+        self.K, self.M, self.S, self.Z = K, M, S, Z
+
+
+def expand_population(template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5):
+    """Host-only (no device): the arrays of the K-candidate batch ``pyxrd_expand_population`` builds from the
+    template and the binding table, as a dict of numpy copies (tests, debugging)."""
+    lib = load_library()
+    d = Context.batch_desc(template)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    bindings = np.ascontiguousarray(bindings, dtype=BINDING_DTYPE)
+    auto = None if csds_auto is None else np.ascontiguousarray(csds_auto, dtype=np.uint8)
+    pop = PopulationDesc(x.shape[0], x.shape[1], bindings.size, template.S, template.Z, 0, _p(x, _f64p),
+                         bindings.ctypes.data_as(C.POINTER(Binding)), _p(auto, _u8p) if auto is not None else None,
+                         float(csds_factor))
+    handle = C.c_void_p()
+    if lib.pyxrd_expand_population(C.byref(d), C.byref(pop), C.byref(handle)) != 0:
+        raise ValueError(lib.pyxrd_expand_error().decode("utf-8", "replace"))
+    try:
+        e = BatchDesc()
+        lib.pyxrd_expanded_desc(handle, C.byref(e))
+        K, S, Z, M = e.n_candidates, template.S, template.Z, e.n_phase_slots
+
+        def arr(ptr, n, dtype):
+            if not ptr or n == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+
+        out = dict(
+            K=K, M=M,
+            phase_i=arr(e.phase_i, e.n_phases * 8, np.int32).reshape(-1, 8),
+            phase_d=arr(e.phase_d, e.n_phases * 8, float).reshape(-1, 8),
+            phase_comp=arr(e.phase_comp, e.n_phase_comp, np.int32),
+            matrices=arr(e.matrices, e.n_matrix, float),
+            comp_d=arr(e.comp_d, e.n_components * 8, float).reshape(-1, 8),
+            comp_i=arr(e.comp_i, e.n_components * 4, np.int32).reshape(-1, 4),
+            atom_d=arr(e.atom_d, e.n_atoms * 2, float).reshape(-1, 2),
+            atom_type=arr(e.atom_type, e.n_atoms, np.int32),
+            job_phase=arr(e.job_phase, K * S * Z * M, np.int32),
+            fractions=arr(e.fractions, K * M, float).reshape(K, M),
+            scales=arr(e.scales, K * S, float).reshape(K, S),
+            bgshifts=arr(e.bgshifts, K * S, float).reshape(K, S),
+            prob_model=arr(e.prob_model, e.n_phases, np.int32) if e.prob_model else None,
+            prob_params=arr(e.prob_params, e.n_phases * 8, float).reshape(-1, 8) if e.prob_params else None)
+        return out
+    finally:
+        lib.pyxrd_expanded_free(handle)
 
 
 _contexts = {}

@@ -434,3 +434,83 @@ def rpder_case() -> MixtureData:
         if s == 0:
             spec.selected_range = ~((tt >= 20.0) & (tt <= 22.0))
     return mix
+
+
+# ---------------------------------------------------------------------------
+# Templates + refinables of the configurations (population path)
+# ---------------------------------------------------------------------------
+def _phase_refinables(tag, phases, avg_range, ss_range=(1.0, 15.0)):
+    """CSDS average (+ automatic maximum) and sigma* of a phase; ``phases`` = the DataObjects that share
+    the values (the AD / EG copies of one model phase)."""
+    from .population import Refinable
+    return [Refinable(tag + ".csds_average", [(p.CSDS, "average") for p in phases], *avg_range),
+            Refinable(tag + ".sigma_star", [(p, "sigma_star") for p in phases], *ss_range)]
+
+
+def _d001_refinable(tag, comps, lo, hi):
+    """d001 of a component; the cell volume follows it as make_component defines it (0.52 * 0.90 * d001)"""
+    from .population import Refinable
+    targets = []
+    for c in comps:
+        targets += [(c, "d001"), (c, "volume", 0.52 * 0.90, 0.0)]
+    return Refinable(tag + ".d001", targets, lo, hi)
+
+
+def _prob_refinables(tag, phases, model, params, bounds):
+    from .population import Refinable
+    for p in phases:
+        p.prob_model, p.prob_params = model, list(params)
+    return [Refinable("%s.prob%d" % (tag, i), [(p, "prob:%d" % i) for p in phases], lo, hi)
+            for i, (lo, hi) in enumerate(bounds)]
+
+
+def template(name: str):
+    """(template MixtureData, [Refinable]) of a configuration: the truth candidate with its probability
+    matrices handed over to the device models (``prob_model`` / ``prob_params`` on the PhaseData) and the
+    refinable parameters a refinement of that configuration would vary."""
+    mix = CONFIGS[name].truth()
+    refs = []
+    if name == "c1":
+        ph = mix.specimens[0].phases[0][0]
+        refs += [_d001_refinable("illite", [ph.components[0]], 0.99, 1.01)]
+        refs += _phase_refinables("illite", [ph], (8.0, 12.9))
+    elif name == "c2":
+        ph = mix.specimens[0].phases[0][0]
+        refs += [_d001_refinable("illite", [ph.components[0]], 0.99, 1.005),
+                 _d001_refinable("smectite", [ph.components[1]], 1.20, 1.30)]
+        refs += _prob_refinables("IS", [ph], "R1G2", [0.7, 0.7], [(0.5, 0.9), (0.05, 0.95)])
+        refs += _phase_refinables("IS", [ph], (8.0, 12.9))
+    elif name == "c4":
+        ad, eg = mix.specimens[0].phases[0], mix.specimens[1].phases[0]
+        pairs = [[a, e] for a, e in zip(ad, eg)]
+        refs += [_d001_refinable("illite", [p.components[0] for p in pairs[0]], 0.995, 1.002)]
+        refs += _phase_refinables("illite", pairs[0], (14.0, 22.0), (2.0, 10.0))
+        refs += _phase_refinables("kaolinite", pairs[1], (20.0, 30.0), (2.0, 10.0))
+        refs += _phase_refinables("chlorite", pairs[2], (10.0, 18.0), (2.0, 10.0))
+        refs += _prob_refinables("IS_R1", pairs[3], "R1G2", [0.6, 0.7], [(0.3, 0.9), (0.05, 0.95)])
+        refs += [_d001_refinable("IS_R1.smectite_ad", [pairs[3][0].components[1]], 1.22, 1.28),
+                 _d001_refinable("IS_R1.smectite_eg", [pairs[3][1].components[1]], 1.66, 1.72)]
+        refs += _phase_refinables("IS_R1", pairs[3], (8.0, 14.0), (2.0, 12.0))
+        refs += _prob_refinables("IS_R0", pairs[4], "R0", [0.4], [(0.05, 0.95)])
+        refs += _phase_refinables("IS_R0", pairs[4], (5.0, 9.0), (4.0, 14.0))
+        refs += _prob_refinables("IS_R2", pairs[5], "R2G2", [0.7, 0.6, 0.5, 0.4],
+                                 [(0.5, 0.95), (0.05, 0.95), (0.05, 0.95), (0.05, 0.95)])
+        refs += _phase_refinables("IS_R2", pairs[5], (8.0, 16.0), (2.0, 12.0))
+    elif name == "c5":
+        for i, ph in enumerate(mix.specimens[0].phases[0]):
+            tag = "IS_R3_%d" % i
+            refs += _prob_refinables(tag, [ph], "R3G2", [0.8, 0.6], [(0.67, 0.95), (0.05, 0.95)])
+            refs += [_d001_refinable(tag + ".illite", [ph.components[0]], 0.995, 1.002),
+                     _d001_refinable(tag + ".smectite", [ph.components[1]], 1.66, 1.72)]
+            refs += _phase_refinables(tag, [ph], (28.0, 32.0), (2.0, 12.0))
+    else:
+        raise KeyError("configuration %r has no template (its W / P are not produced by a probability model)" % name)
+    return mix, refs
+
+
+def sample_solutions(refinables, seed: int, count: int) -> np.ndarray:
+    """x f64[count, d] uniform inside the refinables' bounds (refinement_generator.py:26-33 style)"""
+    rng = np.random.default_rng([int(seed), 77])
+    lo = np.array([r.minimum for r in refinables])
+    hi = np.array([r.maximum for r in refinables])
+    return lo + rng.uniform(0.0, 1.0, (int(count), lo.size)) * (hi - lo)

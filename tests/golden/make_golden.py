@@ -148,9 +148,54 @@ def extras(ref, out):
         settings.RESIDUAL_METHOD = "Rp"
 
 
+MODEL_CASES = [(1, 1, 0), (1, 2, 1), (1, 3, 2), (1, 4, 3), (1, 5, 4), (1, 6, 5), (2, 2, 2), (3, 2, 4), (4, 2, 2)]
+
+
+def model_parameter_sets(npar, n=120, seed=99):
+    """deterministic parameter vectors: special values, in-range, and out-of-range (clamped by the setters)"""
+    rng = np.random.default_rng([seed, npar])
+    out = []
+    for t in range(n):
+        if npar and t < 16:
+            out.append(rng.choice([0.0, 0.5, 1.0, 2.0 / 3.0, 0.75, 0.25], npar))
+        elif t % 5 == 0:
+            out.append(rng.uniform(-0.2, 1.2, npar))
+        else:
+            out.append(rng.uniform(0.0, 1.0, npar))
+    return np.array(out, dtype=float).reshape(n, npar)
+
+
+def models(out):
+    """probability models through the live reference MODEL layer:
+    W, P, valid_probs (phases/models/phase.py:45) after a second update() (converged level matrices)"""
+    import warnings
+    import _live_models
+    pm = _live_models.load().probabilities
+    for model, G, npar in MODEL_CASES:
+        params = model_parameter_sets(npar)
+        r = G ** {1: 1, 2: 1, 3: 2, 4: 3}[model]
+        Ws, Ps, valid = np.zeros((len(params), r, r)), np.zeros((len(params), r, r)), np.zeros(len(params), dtype=bool)
+        for t, p in enumerate(params):
+            if model == 1:
+                m = getattr(pm, "R0G%dModel" % G)(**{"F%d" % (i + 1): p[i] for i in range(G - 1)})
+            elif model == 2:
+                m = pm.R1G2Model(W1=p[0], P11_or_P22=p[1])
+            elif model == 3:
+                m = pm.R2G2Model(W1=p[0], P112_or_P211=p[1], P21=p[2], P122_or_P221=p[3])
+            else:
+                m = pm.R3G2Model(W1=p[0], P1111_or_P2112=p[1])
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                m.update()
+            Ws[t], Ps[t] = m.get_distribution_matrix(), m.get_probability_matrix()
+            valid[t] = bool(all(m.P_valid) and all(m.W_valid))
+        key = "m%d_g%d" % (model, G)
+        out[key + "_params"], out[key + "_W"], out[key + "_P"], out[key + "_valid"] = params, Ws, Ps, valid
+
+
 def main():
     ref = _live_reference.load()
-    names = sys.argv[1:] or ["kat", "extras", "c1", "c2", "c4", "c5", "c3"]
+    names = sys.argv[1:] or ["kat", "extras", "models", "c1", "c2", "c4", "c5", "c3"]
     for name in names:
         out = {"versions": np.array("numpy %s scipy %s python %s reference 0.8.4"
                                     % (np.__version__, scipy.__version__, sys.version.split()[0]))}
@@ -158,6 +203,8 @@ def main():
             kats(ref, out)
         elif name == "extras":
             extras(ref, out)
+        elif name == "models":
+            models(out)
         else:
             run_config(ref, name, out)
         path = os.path.join(HERE, "%s.npz" % name)

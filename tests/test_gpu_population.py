@@ -1,0 +1,178 @@
+"""Population path on the device through the C-ABI:
+probability models (``k_probabilities`` / ``pyxrd_leaf_probabilities``) against the live reference's model
+classes, and template + binding-table populations against the oracle run on separately rebuilt DataObject
+graphs.  Tolerances: W / P bit-identical; intensities / residuals relative 1e-9 (north_star)."""
+import copy
+
+import numpy as np
+import pytest
+
+from helpers import rel_err
+from oracle import pyxrd_oracle as orc
+from oracle import pyxrd_oracle_models as om
+from pyxrd_b200 import synthetic as syn
+from pyxrd_b200.population import PopulationTemplate, Refinable
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+OPT_RTOL = 5e-3
+CASES = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (2, 2), (3, 2), (4, 2)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pyxrd_b200.runtime import default_context
+    return default_context()
+
+
+@pytest.mark.parametrize("model,G", CASES)
+def test_device_models_bit_identical_to_live_reference(ctx, golden, model, G):
+    g = golden("models")
+    key = "m%d_g%d" % (model, G)
+    for p, W, P, v in zip(g[key + "_params"], g[key + "_W"], g[key + "_P"], g[key + "_valid"]):
+        gW, gP, gv = ctx.leaf_probabilities(model, G, p)
+        assert np.array_equal(gW, W, equal_nan=True), (key, p)
+        assert np.array_equal(gP, P, equal_nan=True), (key, p)
+        assert gv == bool(v), (key, p)
+
+
+def test_leaf_probabilities_rejects_unknown_models(ctx):
+    from pyxrd_b200.runtime import DeviceError
+    with pytest.raises(DeviceError):
+        ctx.leaf_probabilities(2, 3, [0.5, 0.5])           # R1 exists for G = 2 only here
+    with pytest.raises(DeviceError):
+        ctx.leaf_probabilities(9, 2, [0.5, 0.5])
+
+
+def _observe(mix, level=50.0):
+    rng = np.random.default_rng(3)
+    for spec in mix.specimens:
+        spec.observed_intensity = rng.uniform(0.5, 1.5, (spec.range_theta.size, 1)) * level
+    return mix
+
+
+def _template(name):
+    mix, refs = syn.template(name)
+    _observe(mix)
+    return PopulationTemplate(mix, refs), refs
+
+
+@pytest.mark.parametrize("name,K", [("c1", 6), ("c2", 6), ("c4", 5), ("c5", 3)])
+def test_population_matches_oracle_on_rebuilt_graphs(ctx, name, K):
+    tmpl, refs = _template(name)
+    x = syn.sample_solutions(refs, 5, K)
+    res = tmpl.residuals(x)
+    pis = tmpl.phase_intensities(x)
+    assert res.shape == (K, 1 + tmpl.static.S)
+    for k in range(K):
+        tmpl.apply(x[k], probabilities=om.probabilities)
+        ref = copy.deepcopy(tmpl.mixture)
+        orc.calculate_mixture(ref)
+        for s, spec in enumerate(ref.specimens):
+            assert rel_err(pis[k][s], spec.phase_intensities) < RTOL, (name, k, s)
+        assert rel_err(res[k], ref.residuals) < RTOL, (name, k)
+
+
+def test_population_equals_the_batch_path_bit_for_bit(ctx):
+    """same kernels, same packed values: a template population and K packed DataObject graphs agree exactly"""
+    from pyxrd_b200.batched import population_residuals
+    tmpl, refs = _template("c4")
+    x = syn.sample_solutions(refs, 6, 8)
+    res = tmpl.residuals(x)
+    graphs = []
+    for row in x:
+        tmpl.apply(row, ctx=ctx)                  # W / P from the device leaf
+        graphs.append(copy.deepcopy(tmpl.mixture))
+    for g in graphs:                              # hand the matrices over as fixed ones
+        for spec in g.specimens:
+            for ph in spec.phases[0]:
+                ph.prob_model = None
+    assert np.array_equal(res, population_residuals(graphs))
+
+
+def test_invalid_probabilities_inside_a_population(ctx):
+    tmpl, refs = _template("c4")
+    names = [r.name for r in refs]
+    x = syn.sample_solutions(refs, 8, 4)
+    # R2G2 with W1 = 0.5, P21 = 0.1, P112 = 0.5: P211 = P112 * W11 / W21 = 4.5 leaves [0, 1]
+    x[1, names.index("IS_R2.prob0")] = 0.5
+    x[1, names.index("IS_R2.prob1")] = 0.5
+    x[1, names.index("IS_R2.prob2")] = 0.1
+    x[1, names.index("IS_R2.prob3")] = 0.9
+    assert not om.probabilities(om.R2G2, 2, x[1, names.index("IS_R2.prob0"):names.index("IS_R2.prob0") + 4])[2]
+    pis = tmpl.phase_intensities(x)
+    res = tmpl.residuals(x)
+    assert not pis[1][0][5].any() and not pis[1][1][5].any()        # zeros (phases.py:109-111)
+    assert pis[0][0][5].any() and pis[1][0][4].any()
+    tmpl.apply(x[1], probabilities=om.probabilities)
+    assert not tmpl.mixture.specimens[0].phases[0][5].valid_probs
+    ref = copy.deepcopy(tmpl.mixture)
+    orc.calculate_mixture(ref)
+    assert rel_err(res[1], ref.residuals) < RTOL
+
+
+def test_out_of_range_parameters_are_clamped_like_the_setters(ctx):
+    tmpl, refs = _template("c2")
+    names = [r.name for r in refs]
+    x = syn.sample_solutions(refs, 9, 2)
+    x[0, names.index("IS.prob1")] = 1.3           # clamped to 1.0 (cast_property.py:44-47)
+    x[1, names.index("IS.prob1")] = 1.0
+    x[1, [i for i in range(len(names)) if i != names.index("IS.prob1")]] = \
+        x[0, [i for i in range(len(names)) if i != names.index("IS.prob1")]]
+    res = tmpl.residuals(x)
+    assert np.array_equal(res[0], res[1])
+
+
+def test_population_optimiser(ctx):
+    """get_optimized_residual semantics for a whole population: equal to the batch path's device optimiser"""
+    from pyxrd_b200.batched import get_optimized_residuals
+    tmpl, refs = _template("c4")
+    x = syn.sample_solutions(refs, 10, 6)
+    got, sol = tmpl.optimized_residuals(x, want_solutions=True)
+    graphs = []
+    for row in x:
+        tmpl.apply(row, ctx=ctx)
+        g = copy.deepcopy(tmpl.mixture)
+        for spec in g.specimens:
+            for ph in spec.phases[0]:
+                ph.prob_model = None
+        graphs.append(g)
+    want = np.array([r[0] for r in get_optimized_residuals(graphs)])
+    assert np.array_equal(got, want)
+    M = tmpl.batch.M
+    assert np.all(np.abs(sol[:, :M].sum(axis=1) - 1.0) < 1e-12) and np.all(sol[:, :M] >= 0)
+    # against the oracle's scipy-driven optimiser on one rebuilt graph (one-sided contract of DESIGN.md §4)
+    ref = copy.deepcopy(graphs[0])
+    ref.optimized = False
+    want0 = float(orc.get_optimized_residual(ref)[0])
+    assert got[0] <= want0 * (1.0 + OPT_RTOL), (got[0], want0)
+
+
+def test_full_size_population_properties(ctx):
+    """c2 at bench size (2048 candidates x 6700 points): permutation of the solution rows permutes the
+    residuals bit for bit; duplicated rows give duplicated residuals; everything finite"""
+    tmpl, refs = _template("c2")
+    x = syn.sample_solutions(refs, 12, 2048)
+    x[1000] = x[3]
+    res = tmpl.residuals(x)
+    assert np.isfinite(res).all() and (res >= 0).all()
+    assert np.array_equal(res[1000], res[3])
+    perm = np.random.default_rng(0).permutation(len(x))
+    assert np.array_equal(tmpl.residuals(x[perm]), res[perm])
+
+
+def test_binding_to_fixed_matrices_and_mixture_values(ctx):
+    mix = _observe(syn.CONFIGS["c4"].truth())
+    ph_ad, ph_eg = mix.specimens[0].phases[0][3], mix.specimens[1].phases[0][3]
+    refs = [Refinable("f0", [(mix, "fractions:0")]), Refinable("s1", [(mix, "scales:1")]),
+            Refinable("b0", [(mix, "bgshifts:0")]),
+            Refinable("p01", [(ph_ad, "P:0:1"), (ph_ad, "P:0:0", -1.0, 1.0), (ph_eg, "P:0:1"), (ph_eg, "P:0:0", -1.0, 1.0)])]
+    tmpl = PopulationTemplate(mix, refs, csds_auto_maximum=False)
+    x = np.array([[0.2, 3.0, 1.5, 0.25], [0.4, 0.5, 0.0, 0.5]])
+    res = tmpl.residuals(x)
+    for k in range(2):
+        tmpl.apply(x[k], probabilities=om.probabilities)
+        ref = copy.deepcopy(tmpl.mixture)
+        orc.calculate_mixture(ref)
+        assert rel_err(res[k], ref.residuals) < RTOL

@@ -1,0 +1,102 @@
+"""Host half of the population path, no GPU: the native expansion of a
+template + binding table (``pyxrd_expand_population``) must produce exactly the arrays that packing K
+separately built DataObject graphs produces."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import pyxrd_oracle_models as om
+from pyxrd_b200 import packing, runtime
+from pyxrd_b200 import synthetic as syn
+from pyxrd_b200.population import PopulationTemplate, Refinable
+
+
+def _ensure_built():
+    import os
+    if not os.path.exists(runtime.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+def built_candidates(tmpl, x):
+    """K independent DataObject graphs: the template with solution x[k] written into it"""
+    out = []
+    for row in x:
+        tmpl.apply(row, probabilities=om.probabilities)
+        out.append(copy.deepcopy(tmpl.mixture))
+    return out
+
+
+@pytest.mark.parametrize("name,K", [("c1", 5), ("c2", 7), ("c4", 4), ("c5", 3)])
+def test_expansion_equals_packing_of_rebuilt_graphs(name, K):
+    _ensure_built()
+    mix, refs = syn.template(name)
+    tmpl = PopulationTemplate(mix, refs)
+    x = syn.sample_solutions(refs, 11, K)
+    got = tmpl.expand(x)
+    want = packing.BatchPack(built_candidates(tmpl, x), tmpl.static)
+    assert got["K"] == K == want.K and got["M"] == want.M
+    for key in ("phase_i", "phase_d", "phase_comp", "comp_d", "comp_i", "atom_d", "atom_type", "job_phase",
+                "fractions", "scales", "bgshifts", "prob_model", "prob_params"):
+        assert np.array_equal(got[key], getattr(want, key)), key
+    # fixed (not model-driven) matrices travel unchanged
+    for p, row in enumerate(want.phase_i):
+        if (want.prob_model is None or want.prob_model[p] == 0) and row[1] > 0:
+            n = 2 * row[1] * row[1]
+            assert np.array_equal(got["matrices"][row[6]:row[6] + n], want.matrices[row[6]:row[6] + n])
+    # the automatic CSDS maximum follows the bound average (phases/models/CSDS.py:127,140)
+    assert np.array_equal(got["phase_i"][:, 3], (2.5 * got["phase_d"][:, 1]).astype(np.int32))
+
+
+def test_mixture_level_and_matrix_bindings():
+    _ensure_built()
+    mix = syn.CONFIGS["c4"].truth()
+    ph = mix.specimens[0].phases[0][3]
+    refs = [Refinable("f0", [(mix, "fractions:0"), (mix, "fractions:2", -1.0, 0.5)]),
+            Refinable("s1", [(mix, "scales:1", 2.0, 0.0)]),
+            Refinable("b0", [(mix, "bgshifts:0")]),
+            Refinable("p01", [(ph, "P:0:1"), (ph, "P:0:0", -1.0, 1.0)]),
+            Refinable("pn", [(ph.components[0].layer_atoms[2], "pn")])]
+    tmpl = PopulationTemplate(mix, refs, csds_auto_maximum=False)
+    x = np.array([[0.2, 3.0, 1.5, 0.25, 7.0], [0.4, 5.0, -2.0, 0.5, 9.0]])
+    got = tmpl.expand(x)
+    base = tmpl.batch
+    assert np.array_equal(got["fractions"][:, 0], x[:, 0]) and np.array_equal(got["fractions"][:, 2], 0.5 - x[:, 0])
+    assert np.array_equal(got["fractions"][:, 1], np.repeat(base.fractions[0, 1], 2))
+    assert np.array_equal(got["scales"][:, 1], 2.0 * x[:, 1]) and np.array_equal(got["bgshifts"][:, 0], x[:, 2])
+    pid = base.phase_index[id(ph)]
+    off, NM = base.phase_i[pid, 6], base.matrices.size
+    for k in range(2):
+        P = got["matrices"][k * NM + off + 4:k * NM + off + 8].reshape(2, 2)
+        assert P[0, 1] == x[k, 3] and P[0, 0] == 1.0 - x[k, 3]
+        assert np.array_equal(P[1], np.asarray(ph.P)[1])
+    aidx = base.atom_index[id(ph.components[0].layer_atoms[2])]
+    NA = base.atom_type.size
+    assert got["atom_d"][aidx, 0] == 7.0 and got["atom_d"][NA + aidx, 0] == 9.0
+    # indices of the second candidate point into its own tables
+    NP = base.phase_i.shape[0]
+    assert np.array_equal(got["job_phase"][base.job_phase.size:], base.job_phase + NP)
+    assert np.array_equal(got["phase_i"][NP:, 6], base.phase_i[:, 6] + NM)
+    assert np.array_equal(got["phase_i"][:NP, 3], base.phase_i[:, 3])        # maximum untouched
+
+
+def test_binding_errors():
+    _ensure_built()
+    mix, refs = syn.template("c2")
+    tmpl = PopulationTemplate(mix, refs)
+    with pytest.raises(ValueError):
+        tmpl.expand(np.zeros((2, 3)))                       # wrong number of columns
+    bad = tmpl.bindings.copy()
+    bad["index"][0] = 10 ** 6
+    with pytest.raises(ValueError, match="out of range"):
+        runtime.expand_population(tmpl.batch, np.zeros((1, len(refs))), bad)
+    other = syn.CONFIGS["c1"].truth()
+    with pytest.raises(KeyError):
+        PopulationTemplate(mix, [Refinable("x", [(other.specimens[0].phases[0][0], "sigma_star")])])
+    with pytest.raises(KeyError):
+        PopulationTemplate(mix, [Refinable("x", [(mix.specimens[0].phases[0][0], "W:0:0")])])   # model-driven
+    with pytest.raises(ValueError):
+        ph = syn.CONFIGS["c2"].truth().specimens[0].phases[0][0]
+        ph.prob_model, ph.prob_params = "R2G2", [0.5]
+        packing.prob_model_of(ph)
