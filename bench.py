@@ -197,13 +197,41 @@ def time_workload(name, count, args, rank, world, torch, dist, ctx, stream, flus
                                      batch.comp_i, batch.atom_d, batch.atom_type, batch.job_phase, batch.fractions,
                                      batch.scales, batch.bgshifts)) + 20 * batch.job_phase.size
         d2h = pinned_res.nbytes + (pinned_int.nbytes if want_int else pinned_sol.nbytes)
-    t = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device="cuda")
+        # ---- population from a template: solution vectors x[K, d] in (host), residuals out (host) ----------
+        pop = None
+        if name in ("c1", "c2", "c4", "c5"):
+            from pyxrd_b200.population import PopulationTemplate
+            tmix, refs = syn.template(name)
+            for spec, src in zip(tmix.specimens, mixes[0].specimens):
+                spec.observed_intensity = np.array(src.observed_intensity)
+            tmpl = PopulationTemplate(tmix, refs)
+            x = syn.sample_solutions(refs, SEED + rank, batch.K)
+            ctx.set_static(tmpl.static)
+
+            def step_pop():
+                if optimise:
+                    return ctx.optimize_population(tmpl.batch, x, tmpl.bindings, tmpl.csds_auto, tmpl.csds_factor, refine_bg=True)[0]
+                return ctx.evaluate_population(tmpl.batch, x, tmpl.bindings, tmpl.csds_auto, tmpl.csds_factor)
+
+            for _ in range(min(args.warmup, 2)):
+                step_pop()
+            sync_all()
+            p0 = time.perf_counter()
+            for _ in range(args.steps):
+                r_pop = step_pop()
+            sync_all()
+            pop = dict(ms=(time.perf_counter() - p0) * 1e3 / args.steps, d=x.shape[1], h2d=x.nbytes, d2h=r_pop.nbytes,
+                       finite=bool(np.isfinite(r_pop).all()))
+    t = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, pop["ms"] * args.steps if pop else 0.0], dtype=torch.float64,
+                     device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms = [float(v) for v in t.tolist()]
+    dev_ms, e2e_ms, wall_ms, pop_ms = [float(v) for v in t.tolist()]
+    if pop:
+        pop["ms"] = pop_ms / args.steps
     return dict(cfg=cfg, K=batch.K, points=points_1, flops=flops_1, dev_ms=dev_ms / args.steps,
                 e2e_ms=e2e_ms / args.steps, wall_ms=wall_ms / args.steps, stage={k: v / args.steps for k, v in stage.items()},
-                launches=launches, h2d=h2d, d2h=d2h, pack_s=pack_s, residual_sample=float(pinned_res[0]),
+                launches=launches, h2d=h2d, d2h=d2h, pack_s=pack_s, residual_sample=float(pinned_res[0]), pop=pop,
                 n_specimens=batch.S, n_phases=batch.M, X=[int(v) for v in static.npts])
 
 
@@ -388,6 +416,13 @@ def run_b200(args, rank, world, local_rank):
                              "peak_source": "of measured" if peaks else "of fallback"}},
         "stage_ms": main["stage"], "host_pack_s": main["pack_s"], "clocks": clocks,
     }
+    if main["pop"]:
+        p = main["pop"]
+        line["population"] = {"call": "pyxrd_evaluate_population: solution vectors x[K, d] on the host -> native expansion "
+                                      "of the packed template + binding table -> phase patterns -> residuals on the host",
+                              "value": total_pts / (p["ms"] * 1e-3), "unit": "pattern-pts/s", "ms_per_step": p["ms"],
+                              "evals_per_s": main["K"] * world / (p["ms"] * 1e-3), "refinables": p["d"],
+                              "h2d_bytes_per_step": p["h2d"], "d2h_bytes_per_step": p["d2h"]}
     if trials is not None:
         tv = trials["K"] * world / (trials["dev_ms"] * 1e-3)
         line["trials"] = {"metric": "refinement trial evals/s (get_optimized_residual semantics: all phase patterns "
@@ -401,6 +436,10 @@ def run_b200(args, rank, world, local_rank):
                                        "optimiser": trials["stage"]["residual"]},
                           "optimiser": "device majorise-minimise (pyxrd_optimize), 32 reweightings x <=2 Newton steps; "
                                        "contract: <= reference L-BFGS-B optimum * (1 + 5e-3)",
+                          "population": None if not trials["pop"] else {
+                              "call": "pyxrd_optimize_population: x[K, d] on the host -> optimised residuals + solutions on the host",
+                              "value": trials["K"] * world / (trials["pop"]["ms"] * 1e-3), "unit": "trials/s",
+                              "ms_per_step": trials["pop"]["ms"], "refinables": trials["pop"]["d"]},
                           "gpu_launches": trials["launches"],
                           "pattern_pts_per_s": trials["points"] * world / (trials["dev_ms"] * 1e-3)}
     if gather_us is not None:

@@ -108,13 +108,20 @@ typedef struct {
  *   R1G2: W1, P11_or_P22                                              R1models.py:125-139
  *   R2G2: W1 (>= 1/2), P112_or_P211, P21, P122_or_P221                R2models.py:195-233
  *   R3G2: W1 (>= 2/3), P1111_or_P2112                                 R3models.py:158-198
+ *   R1G3: W1, P11_or_P22, G1, G2, G3, G4                              R1models.py:367-410
+ *   R1G4: W1, P11_or_P22, R1, R2, G1, G2, G11, G12, G21, G22, G31, G32  R1models.py:747-797
+ *   R2G3: W1 (>= 1/2), P111_or_P212, G1, G2, G3, G4                   R2models.py:485-535
  * followed by solve() and validate() (base_models.py:142-241). */
 #define PYXRD_PROB_FIXED 0
 #define PYXRD_PROB_R0 1
 #define PYXRD_PROB_R1G2 2
 #define PYXRD_PROB_R2G2 3
 #define PYXRD_PROB_R3G2 4
-#define PYXRD_PROB_STRIDE 8
+#define PYXRD_PROB_R1G3 5
+#define PYXRD_PROB_R1G4 6
+#define PYXRD_PROB_R2G3 7
+#define PYXRD_PROB_STRIDE 12
+#define PYXRD_PROB_MAX_RANK 9   /* R2G3; W_out / P_out of pyxrd_leaf_probabilities hold up to 81 doubles */
 
 /* ---- population from a template ---------------------------------------
  * A refinement proposes K solution vectors x_k of d refinable values.  Instead of rebuilding K
@@ -128,7 +135,7 @@ typedef struct {
 #define PYXRD_BIND_COMP_D 1     /* comp_d[index]: component * 8 + {0 d001, 1 default_c, 2 delta_c, 3 lattice_d, 4 volume, 5 weight} */
 #define PYXRD_BIND_ATOM_D 2     /* atom_d[index]: atom * 2 + {0 pn, 1 default_z} */
 #define PYXRD_BIND_MATRIX 3     /* matrices[index] */
-#define PYXRD_BIND_PROB_PARAM 4 /* prob_params[index]: phase * 8 + parameter number */
+#define PYXRD_BIND_PROB_PARAM 4 /* prob_params[index]: phase * PYXRD_PROB_STRIDE + parameter number */
 #define PYXRD_BIND_FRACTION 5   /* fractions[index], index < M */
 #define PYXRD_BIND_SCALE 6      /* scales[index], index < S */
 #define PYXRD_BIND_BGSHIFT 7    /* bgshifts[index], index < S */

@@ -1,6 +1,6 @@
 """CPU oracle (TEST INFRASTRUCTURE ONLY) for the probability models of SURVEY.md §8(f) rank 2:
-numpy restatement of ``pyxrd/probabilities/models`` (v0.8.4) for the model families the BASELINE
-configurations use -- R0 G1..G6, R1 G2, R2 G2, R3 G2.  Only ``tests/`` may import this module.
+numpy restatement of every probability model ``pyxrd/probabilities/models`` (v0.8.4) ships
+(probabilities/models/__init__.py:9-12) -- R0 G1..G6, R1 G2 / G3 / G4, R2 G2 / G3, R3 G2.  Only ``tests/`` may import this module.
 
 Pinned against the live reference model classes (``tests/golden/make_golden.py models`` ->
 ``tests/golden/models.npz``; the reference runs headless behind ``tests/golden/_live_models.py``).
@@ -17,9 +17,10 @@ from itertools import product
 
 import numpy as np
 
-R0, R1G2, R2G2, R3G2 = 1, 2, 3, 4          # = PYXRD_PROB_* of include/pyxrd_b200.h
-N_PARAMS = {R1G2: 2, R2G2: 4, R3G2: 2}
-SHAPE = {R1G2: (1, 2), R2G2: (2, 2), R3G2: (3, 2)}
+R0, R1G2, R2G2, R3G2, R1G3, R1G4, R2G3 = 1, 2, 3, 4, 5, 6, 7          # = PYXRD_PROB_* of include/pyxrd_b200.h
+PROB_CODES = {"R0": R0, "R1G2": R1G2, "R2G2": R2G2, "R3G2": R3G2, "R1G3": R1G3, "R1G4": R1G4, "R2G3": R2G3}
+N_PARAMS = {R1G2: 2, R2G2: 4, R3G2: 2, R1G3: 6, R1G4: 12, R2G3: 6}
+SHAPE = {R1G2: (1, 2), R2G2: (2, 2), R3G2: (3, 2), R1G3: (1, 3), R1G4: (1, 4), R2G3: (2, 3)}
 
 
 class Levels(object):
@@ -95,7 +96,7 @@ class Levels(object):
 
 
 # lower bound of the first parameter (W1): R2models.py:115 (0.5), R3models.py:119 (2/3); everything else [0, 1]
-W1_MINIMUM = {R0: 0.0, R1G2: 0.0, R2G2: 0.5, R3G2: 2.0 / 3.0}
+W1_MINIMUM = {R0: 0.0, R1G2: 0.0, R2G2: 0.5, R3G2: 2.0 / 3.0, R1G3: 0.0, R1G4: 0.0, R2G3: 0.5}   # R2models.py:370
 
 
 def _clamp(v, lo=0.0):
@@ -180,6 +181,98 @@ def _update(model, G, params, lv):
                 lv.setW(t, 0.0)
             for t in ((1, 0, 0), (0, 1, 0), (0, 0, 1)):
                 lv.setW(t, c01(1 - lv.W(0)))
+        elif model == R1G3:                               # R1models.py:367-410
+            W1, P11_or_P22, G1, G2, G3, G4 = p
+            lv.setW((0,), W1)
+            lv.setW((1,), (1 - lv.W(0)) * G1)
+            lv.setW((2,), 1.0 - lv.W(0) - lv.W(1))
+            W0inv = 1.0 / lv.W(0) if lv.W(0) > 0.0 else 0.0
+            if lv.W(0) <= 0.5:
+                lv.setP((0, 0), P11_or_P22)
+                Wxx = lv.W(0) * (lv.P(0, 0) - 1) + lv.W(1) + lv.W(2)
+            else:
+                Wxx = (1.0 - lv.W(0)) * P11_or_P22
+            lv.setW((1, 1), Wxx * G2 * G3)
+            lv.setW((1, 2), Wxx * G2 * (1 - G3))
+            lv.setP((1, 1), lv.W(1, 1) / lv.W(1) if lv.W(1) > 0.0 else 0.0)
+            lv.setW((2, 1), Wxx * (1 - G2) * G4)
+            lv.setW((2, 2), Wxx * (1 - G2) * (1 - G4))
+            lv.setP((1, 2), (lv.W(1, 2) / lv.W(1)) if lv.W(1) > 0.0 else 0.0)
+            lv.setP((1, 0), 1 - lv.P(1, 1) - lv.P(1, 2))
+            lv.setP((2, 1), (lv.W(2, 1) / lv.W(2)) if lv.W(2) > 0.0 else 0.0)
+            lv.setP((2, 2), (lv.W(2, 2) / lv.W(2)) if lv.W(2) > 0.0 else 0.0)
+            lv.setP((2, 0), 1 - lv.P(2, 1) - lv.P(2, 2))
+            lv.setP((0, 1), (lv.W(1) - lv.W(1, 1) - lv.W(2, 1)) * W0inv)
+            lv.setP((0, 2), (lv.W(2) - lv.W(1, 2) - lv.W(2, 2)) * W0inv)
+            if lv.W(0) > 0.5:
+                lv.setP((0, 0), 1 - lv.P(0, 1) - lv.P(0, 2))
+            # :405-407 rewrite the two-index weights, which solve() replaces by W . P anyway
+        elif model == R1G4:                               # R1models.py:747-797
+            W1, P11_or_P22, R1, R2, G1, G2, G11, G12, G21, G22, G31, G32 = p
+            lv.setW((0,), W1)
+            lv.setW((1,), (1.0 - lv.W(0)) * R1)
+            lv.setW((2,), (1.0 - lv.W(0) - lv.W(1)) * R2)
+            lv.setW((3,), 1.0 - lv.W(0) - lv.W(1) - lv.W(2))
+            W0inv = 1.0 / lv.W(0) if lv.W(0) > 0.0 else 0.0
+            if lv.W(0) < 0.5:
+                lv.setP((0, 0), P11_or_P22)
+                Wxx = lv.W(0) * (lv.P(0, 0) - 1) + lv.W(1) + lv.W(2) + lv.W(3)
+            else:
+                Wxx = P11_or_P22 * (lv.W(1) + lv.W(2) + lv.W(3))
+            W1x = Wxx * G1
+            Wyx = (Wxx - W1x)
+            W2x = Wyx * G2
+            W3x = Wyx - W2x
+            for i, (Ga, Gb, Wix) in enumerate(((G11, G12, W1x), (G21, G22, W2x), (G31, G32, W3x)), start=1):
+                lv.setW((i, 1), Ga * Wix)
+                lv.setW((i, 2), Gb * (Wix - lv.W(i, 1)))
+                lv.setW((i, 3), Wix - lv.W(i, 1) - lv.W(i, 2))
+            for i in range(1, 4):
+                lv.setP((i, 0), 1)
+                for j in range(1, 4):
+                    lv.setP((i, j), lv.W(i, j) / lv.W(i) if lv.W(i) > 0 else 0)
+                    lv.setP((i, 0), lv.P(i, 0) - lv.P(i, j))
+                lv.setW((i, 0), lv.W(i) * lv.P(i, 0))
+            lv.setP((0, 1), (lv.W(1) - lv.W(1, 1) - lv.W(2, 1) - lv.W(3, 1)) * W0inv)
+            lv.setP((0, 2), (lv.W(2) - lv.W(1, 2) - lv.W(2, 2) - lv.W(3, 2)) * W0inv)
+            lv.setP((0, 3), (lv.W(3) - lv.W(1, 3) - lv.W(2, 3) - lv.W(3, 3)) * W0inv)
+            if lv.W(0) >= 0.5:
+                lv.setP((0, 0), 1 - lv.P(0, 1) - lv.P(0, 2) - lv.P(0, 3))
+        elif model == R2G3:                               # R2models.py:485-535
+            W1, P111_or_P212, G1, G2, G3, G4 = p
+            lv.setW((0,), W1)
+            lv.setW((1,), (1.0 - lv.W(0)) * G1)
+            lv.setW((2,), 1.0 - lv.W(0) - lv.W(1))
+            for t in ((1, 1), (1, 2), (2, 1), (2, 2)):
+                lv.setW(t, 0)
+            for t in ((1, 0), (0, 1), (0, 1, 0)):
+                lv.setW(t, lv.W(1))
+            for t in ((2, 0), (0, 2), (0, 2, 0)):
+                lv.setW(t, lv.W(2))
+            lv.setW((0, 0), lv.W(0) - lv.W(0, 1) - lv.W(0, 2))
+            Wx = lv.W(1) + lv.W(2)
+            if lv.W(0) < 2.0 / 3.0:
+                lv.setP((0, 0, 0), P111_or_P212)
+                Px0x = 1 - (lv.W(0) - Wx) / Wx * (1 - lv.P(0, 0, 0)) if Wx != 0 else 0.0
+            else:
+                Px0x = P111_or_P212
+                lv.setP((0, 0, 0), 1 - Wx / (lv.W(0) - Wx) * (1 - Px0x) if (lv.W(0) - Wx) != 0 else 0.0)
+            Wx0x = Wx * Px0x
+            W10x = G2 * Wx0x
+            W20x = Wx0x - W10x
+            lv.setW((1, 0, 1), G3 * W10x)
+            lv.setW((1, 0, 2), (1 - G3) * W10x)
+            lv.setW((1, 0, 0), lv.W(1, 0) - lv.W(1, 0, 1) - lv.W(1, 0, 2))
+            lv.setW((2, 0, 1), G4 * W20x)
+            lv.setW((2, 0, 2), (1 - G4) * W20x)
+            lv.setW((2, 0, 0), lv.W(2, 0) - lv.W(2, 0, 1) - lv.W(2, 0, 2))
+            lv.setW((0, 0, 0), lv.W(0, 0) * lv.P(0, 0, 0))
+            lv.setW((0, 0, 1), lv.W(0, 1) - lv.W(1, 0, 1) - lv.W(2, 0, 1))
+            lv.setW((0, 0, 2), lv.W(0, 2) - lv.W(1, 0, 2) - lv.W(2, 0, 2))
+            for i in range(3):
+                for j in range(3):
+                    for k in range(3):
+                        lv.setP((i, j, k), lv.W(i, j, k) / lv.W(i, j) if lv.W(i, j) > 0 else 0.0)
         else:
             raise ValueError("unknown probability model %r" % (model,))
         lv.solve()

@@ -107,7 +107,7 @@ struct BatchDev {
     double *phase_x;                 // [NP][4] derived: mean, abs_scale, ntop
     double *coef;                    // [NP][ncap] derived, index = power of Q
     const int *prob_model;           // [NP] PX_PROB_* (nullptr: every phase carries its W / P in the pool)
-    const double *prob_params;       // [NP][8] probability parameters of the model
+    const double *prob_params;       // [NP][PX_PROB_STRIDE] probability parameters of the model
     int *phase_valid;                // [NP]   derived: valid_probs (host flag, or the device model's verdict)
     const int *job_pb, *job_spec;    // [NJ]
     const long long *job_out;        // [NJ]
@@ -216,8 +216,9 @@ __global__ void k_observed_norm(StaticDev st, double *derived) {
 // ---------------------------------------------------------------------------------
 // probability models on the device: W, P and valid_probs of a phase from
 // its refinable probability parameters, as pyxrd/probabilities/models do in update() + solve() +
-// validate() (base_models.py:142-241).  Families: R0 G1..G6 (R0models.py:68-83), R1G2
-// (R1models.py:125-139), R2G2 (R2models.py:195-233), R3G2 (R3models.py:158-198).
+// validate() (base_models.py:142-241).  Every family the reference ships (models/__init__.py:9-12):
+// R0 G1..G6 (R0models.py:68-83), R1G2 (R1models.py:125-139), R1G3 (:367-410), R1G4 (:747-797),
+// R2G2 (R2models.py:195-233), R2G3 (:485-535), R3G2 (R3models.py:158-198).
 // The level matrices lW[r] / lP[r] (rank G^(r+1)) and the multi-index access mW[i,j,..] /
 // mP[i,j,..] of base_models.py:52-70,243-285 are kept as they are in the reference, so that
 // every model reads like its update(); all arithmetic is single IEEE operations in the
@@ -230,11 +231,16 @@ __global__ void k_observed_norm(StaticDev st, double *derived) {
 #define PX_PROB_R1G2 2
 #define PX_PROB_R2G2 3
 #define PX_PROB_R3G2 4
+#define PX_PROB_R1G3 5
+#define PX_PROB_R1G4 6
+#define PX_PROB_R2G3 7
+#define PX_PROB_STRIDE 12
+#define PX_PROB_MAXSQ 81  // largest level matrix: rank 9 (R2G3)
 
 struct ProbLevels {
     int R, G, Rp;
-    double W[4][64];      // lW[0 .. Rp-1], lW[Rp] = W . P
-    double P[3][64];      // lP[0 .. Rp-1]
+    double W[4][PX_PROB_MAXSQ];      // lW[0 .. Rp-1], lW[Rp] = W . P
+    double P[3][PX_PROB_MAXSQ];      // lP[0 .. Rp-1]
     __device__ int ipow(int e) const { int v = 1; for (int i = 0; i < e; ++i) v *= G; return v; }
     __device__ int wrank(int r) const { return ipow(r < Rp ? r + 1 : Rp); }
     __device__ int prank(int r) const { return ipow(r + 1); }
@@ -269,6 +275,10 @@ __device__ __forceinline__ double pm_clamp(double v, double lo) { return fmin(fm
 __device__ __forceinline__ double pm_c01(double v) { return fmax(fmin(v, 1.0), 0.0); }      // max(min(v, 1.0), 0.0)
 __device__ __forceinline__ double pm_sub(double a, double b) { return __dadd_rn(a, -b); }
 __device__ __forceinline__ double pm_muldiv(double a, double b, double c) { return __ddiv_rn(__dmul_rn(a, b), c); }
+__device__ __forceinline__ double pm_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double pm_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double pm_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double pm_ratio(double a, double b) { return b > 0.0 ? __ddiv_rn(a, b) : 0.0; }   // a / b if b > 0 else 0
 
 __device__ void prob_solve(ProbLevels &lv) {                    // base_models.py:142-162
     const int G = lv.G;
@@ -382,6 +392,100 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
         lv.W3(1, 0, 1) = 0.0; lv.W3(1, 1, 0) = 0.0; lv.W3(1, 1, 1) = 0.0; lv.W3(0, 1, 1) = 0.0;
         const double wm = pm_c01(pm_sub(1.0, w0));
         lv.W3(1, 0, 0) = wm; lv.W3(0, 1, 0) = wm; lv.W3(0, 0, 1) = wm;
+    } else if (model == PX_PROB_R1G3) {
+        const double W1 = pm_clamp(par[0], 0.0), Pxx = pm_clamp(par[1], 0.0), G1 = pm_clamp(par[2], 0.0),
+                     G2 = pm_clamp(par[3], 0.0), G3 = pm_clamp(par[4], 0.0), G4 = pm_clamp(par[5], 0.0);
+        lv.W1(0) = W1;
+        lv.W1(1) = pm_mul(pm_sub(1.0, lv.W1(0)), G1);
+        lv.W1(2) = pm_sub(pm_sub(1.0, lv.W1(0)), lv.W1(1));
+        const double W0inv = lv.W1(0) > 0.0 ? pm_div(1.0, lv.W1(0)) : 0.0;
+        double Wxx;
+        if (lv.W1(0) <= 0.5) {
+            lv.P2(0, 0) = Pxx;
+            Wxx = pm_add(pm_add(pm_mul(lv.W1(0), pm_sub(lv.P2(0, 0), 1.0)), lv.W1(1)), lv.W1(2));
+        } else {
+            Wxx = pm_mul(pm_sub(1.0, lv.W1(0)), Pxx);
+        }
+        lv.W2(1, 1) = pm_mul(pm_mul(Wxx, G2), G3);
+        lv.W2(1, 2) = pm_mul(pm_mul(Wxx, G2), pm_sub(1.0, G3));
+        lv.P2(1, 1) = pm_ratio(lv.W2(1, 1), lv.W1(1));
+        lv.W2(2, 1) = pm_mul(pm_mul(Wxx, pm_sub(1.0, G2)), G4);
+        lv.W2(2, 2) = pm_mul(pm_mul(Wxx, pm_sub(1.0, G2)), pm_sub(1.0, G4));
+        lv.P2(1, 2) = pm_ratio(lv.W2(1, 2), lv.W1(1));
+        lv.P2(1, 0) = pm_sub(pm_sub(1.0, lv.P2(1, 1)), lv.P2(1, 2));
+        lv.P2(2, 1) = pm_ratio(lv.W2(2, 1), lv.W1(2));
+        lv.P2(2, 2) = pm_ratio(lv.W2(2, 2), lv.W1(2));
+        lv.P2(2, 0) = pm_sub(pm_sub(1.0, lv.P2(2, 1)), lv.P2(2, 2));
+        lv.P2(0, 1) = pm_mul(pm_sub(pm_sub(lv.W1(1), lv.W2(1, 1)), lv.W2(2, 1)), W0inv);
+        lv.P2(0, 2) = pm_mul(pm_sub(pm_sub(lv.W1(2), lv.W2(1, 2)), lv.W2(2, 2)), W0inv);
+        if (lv.W1(0) > 0.5) lv.P2(0, 0) = pm_sub(pm_sub(1.0, lv.P2(0, 1)), lv.P2(0, 2));
+        // R1models.py:405-407 rewrite the two-index weights, which solve() replaces by W . P anyway
+    } else if (model == PX_PROB_R1G4) {
+        double q[12];
+        for (int i = 0; i < 12; ++i) q[i] = pm_clamp(par[i], 0.0);      // W1 P11_or_P22 R1 R2 G1 G2 G11 G12 G21 G22 G31 G32
+        lv.W1(0) = q[0];
+        lv.W1(1) = pm_mul(pm_sub(1.0, lv.W1(0)), q[2]);
+        lv.W1(2) = pm_mul(pm_sub(pm_sub(1.0, lv.W1(0)), lv.W1(1)), q[3]);
+        lv.W1(3) = pm_sub(pm_sub(pm_sub(1.0, lv.W1(0)), lv.W1(1)), lv.W1(2));
+        const double W0inv = lv.W1(0) > 0.0 ? pm_div(1.0, lv.W1(0)) : 0.0;
+        double Wxx;
+        if (lv.W1(0) < 0.5) {
+            lv.P2(0, 0) = q[1];
+            Wxx = pm_add(pm_add(pm_add(pm_mul(lv.W1(0), pm_sub(lv.P2(0, 0), 1.0)), lv.W1(1)), lv.W1(2)), lv.W1(3));
+        } else {
+            Wxx = pm_mul(q[1], pm_add(pm_add(lv.W1(1), lv.W1(2)), lv.W1(3)));
+        }
+        const double W1x = pm_mul(Wxx, q[4]), Wyx = pm_sub(Wxx, W1x), W2x = pm_mul(Wyx, q[5]), W3x = pm_sub(Wyx, W2x);
+        const double Wix[3] = {W1x, W2x, W3x};
+        for (int i = 1; i < 4; ++i) {
+            lv.W2(i, 1) = pm_mul(q[4 + 2 * i], Wix[i - 1]);
+            lv.W2(i, 2) = pm_mul(q[5 + 2 * i], pm_sub(Wix[i - 1], lv.W2(i, 1)));
+            lv.W2(i, 3) = pm_sub(pm_sub(Wix[i - 1], lv.W2(i, 1)), lv.W2(i, 2));
+        }
+        for (int i = 1; i < 4; ++i) {
+            lv.P2(i, 0) = 1.0;
+            for (int j = 1; j < 4; ++j) {
+                lv.P2(i, j) = pm_ratio(lv.W2(i, j), lv.W1(i));
+                lv.P2(i, 0) = pm_sub(lv.P2(i, 0), lv.P2(i, j));
+            }
+            lv.W2(i, 0) = pm_mul(lv.W1(i), lv.P2(i, 0));
+        }
+        for (int j = 1; j < 4; ++j)
+            lv.P2(0, j) = pm_mul(pm_sub(pm_sub(pm_sub(lv.W1(j), lv.W2(1, j)), lv.W2(2, j)), lv.W2(3, j)), W0inv);
+        if (lv.W1(0) >= 0.5) lv.P2(0, 0) = pm_sub(pm_sub(pm_sub(1.0, lv.P2(0, 1)), lv.P2(0, 2)), lv.P2(0, 3));
+    } else if (model == PX_PROB_R2G3) {
+        const double W1 = pm_clamp(par[0], 0.5), Pxx = pm_clamp(par[1], 0.0), G1 = pm_clamp(par[2], 0.0),
+                     G2 = pm_clamp(par[3], 0.0), G3 = pm_clamp(par[4], 0.0), G4 = pm_clamp(par[5], 0.0);
+        lv.W1(0) = W1;
+        lv.W1(1) = pm_mul(pm_sub(1.0, lv.W1(0)), G1);
+        lv.W1(2) = pm_sub(pm_sub(1.0, lv.W1(0)), lv.W1(1));
+        lv.W2(1, 1) = 0.0; lv.W2(1, 2) = 0.0; lv.W2(2, 1) = 0.0; lv.W2(2, 2) = 0.0;
+        lv.W2(1, 0) = lv.W1(1); lv.W2(0, 1) = lv.W1(1); lv.W3(0, 1, 0) = lv.W1(1);
+        lv.W2(2, 0) = lv.W1(2); lv.W2(0, 2) = lv.W1(2); lv.W3(0, 2, 0) = lv.W1(2);
+        lv.W2(0, 0) = pm_sub(pm_sub(lv.W1(0), lv.W2(0, 1)), lv.W2(0, 2));
+        const double Wx = pm_add(lv.W1(1), lv.W1(2));
+        double Px0x;
+        if (lv.W1(0) < 2.0 / 3.0) {
+            lv.P3(0, 0, 0) = Pxx;
+            Px0x = Wx != 0.0 ? pm_sub(1.0, pm_mul(pm_div(pm_sub(lv.W1(0), Wx), Wx), pm_sub(1.0, lv.P3(0, 0, 0)))) : 0.0;
+        } else {
+            Px0x = Pxx;
+            const double den = pm_sub(lv.W1(0), Wx);
+            lv.P3(0, 0, 0) = den != 0.0 ? pm_sub(1.0, pm_mul(pm_div(Wx, den), pm_sub(1.0, Px0x))) : 0.0;
+        }
+        const double Wx0x = pm_mul(Wx, Px0x), W10x = pm_mul(G2, Wx0x), W20x = pm_sub(Wx0x, W10x);
+        lv.W3(1, 0, 1) = pm_mul(G3, W10x);
+        lv.W3(1, 0, 2) = pm_mul(pm_sub(1.0, G3), W10x);
+        lv.W3(1, 0, 0) = pm_sub(pm_sub(lv.W2(1, 0), lv.W3(1, 0, 1)), lv.W3(1, 0, 2));
+        lv.W3(2, 0, 1) = pm_mul(G4, W20x);
+        lv.W3(2, 0, 2) = pm_mul(pm_sub(1.0, G4), W20x);
+        lv.W3(2, 0, 0) = pm_sub(pm_sub(lv.W2(2, 0), lv.W3(2, 0, 1)), lv.W3(2, 0, 2));
+        lv.W3(0, 0, 0) = pm_mul(lv.W2(0, 0), lv.P3(0, 0, 0));
+        lv.W3(0, 0, 1) = pm_sub(pm_sub(lv.W2(0, 1), lv.W3(1, 0, 1)), lv.W3(2, 0, 1));
+        lv.W3(0, 0, 2) = pm_sub(pm_sub(lv.W2(0, 2), lv.W3(1, 0, 2)), lv.W3(2, 0, 2));
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                for (int k = 0; k < 3; ++k) lv.P3(i, j, k) = pm_ratio(lv.W3(i, j, k), lv.W2(i, j));
     }
     prob_solve(lv);
 }
@@ -390,12 +494,13 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
 __device__ int prob_evaluate(int model, int G, const double *par, double *Wout, double *Pout, int *valid) {
     ProbLevels lv;
     lv.G = G;
-    lv.R = model == PX_PROB_R0 ? 0 : model == PX_PROB_R1G2 ? 1 : model == PX_PROB_R2G2 ? 2 : 3;
+    lv.R = model == PX_PROB_R0 ? 0 : (model == PX_PROB_R1G2 || model == PX_PROB_R1G3 || model == PX_PROB_R1G4) ? 1
+           : (model == PX_PROB_R2G2 || model == PX_PROB_R2G3) ? 2 : 3;
     lv.Rp = lv.R > 1 ? lv.R : 1;
     for (int r = 0; r < 4; ++r)
-        for (int i = 0; i < 64; ++i) lv.W[r][i] = 0.0;
+        for (int i = 0; i < PX_PROB_MAXSQ; ++i) lv.W[r][i] = 0.0;
     for (int r = 0; r < 3; ++r)
-        for (int i = 0; i < 64; ++i) lv.P[r][i] = 0.0;
+        for (int i = 0; i < PX_PROB_MAXSQ; ++i) lv.P[r][i] = 0.0;
     prob_update(lv, model, par);
     prob_update(lv, model, par);
     bool ok = true;
@@ -463,7 +568,7 @@ __global__ void k_probabilities(BatchDev bt) {
     const int model = bt.prob_model ? bt.prob_model[pb] : PX_PROB_FIXED;
     if (valid && model != PX_PROB_FIXED && !(pi[4] & 8)) {
         double *W = const_cast<double *>(bt.matrices) + pi[6];
-        prob_evaluate(model, pi[0], bt.prob_params + pb * 8, W, W + pi[1] * pi[1], &valid);
+        prob_evaluate(model, pi[0], bt.prob_params + pb * PX_PROB_STRIDE, W, W + pi[1] * pi[1], &valid);
     }
     bt.phase_valid[pb] = valid;
 }

@@ -67,6 +67,20 @@ struct RankClass {
 
 }  // namespace
 
+// rank of the matrices a probability model produces for G components; -1 when the reference has no such model
+static int pyxrd_prob_rank(int model, int G) {
+    switch (model) {
+        case PYXRD_PROB_R0: return (G >= 1 && G <= 6) ? G : -1;
+        case PYXRD_PROB_R1G2: return G == 2 ? 2 : -1;
+        case PYXRD_PROB_R2G2: return G == 2 ? 4 : -1;
+        case PYXRD_PROB_R3G2: return G == 2 ? 8 : -1;
+        case PYXRD_PROB_R1G3: return G == 3 ? 3 : -1;
+        case PYXRD_PROB_R1G4: return G == 4 ? 4 : -1;
+        case PYXRD_PROB_R2G3: return G == 3 ? 9 : -1;
+        default: return -1;
+    }
+}
+
 struct pyxrd_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -467,8 +481,7 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
         if (pi[2] < 0 || pi[3] < pi[2]) return fail(ctx, "set_batch: phase %d CSDS range [%d, %d] unsupported", p, pi[2], pi[3]);
         if (d->prob_model && d->prob_params && d->prob_model[p] != PYXRD_PROB_FIXED) {
             const int m = d->prob_model[p];
-            const int want = m == PYXRD_PROB_R0 ? G : m == PYXRD_PROB_R1G2 ? 2 : m == PYXRD_PROB_R2G2 ? 4 : m == PYXRD_PROB_R3G2 ? 8 : -1;
-            if (want != r || (m != PYXRD_PROB_R0 && G != 2) || (m == PYXRD_PROB_R0 && G > 6))
+            if (pyxrd_prob_rank(m, G) != r)
                 return fail(ctx, "set_batch: phase %d: probability model %d does not fit G=%d rank=%d", p, m, G, r);
         }
         ncap = std::max(ncap, pi[3] + 2);
@@ -1111,20 +1124,20 @@ int pyxrd_optimize_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const p
 int pyxrd_leaf_probabilities(pyxrd_ctx *ctx, int model, int G, const double *params, double *W_out, double *P_out,
                              int *valid_out, int *rank_out) {
     if (!ctx || !params) return 1;
-    const int want = model == PYXRD_PROB_R0 ? G : model == PYXRD_PROB_R1G2 ? 2 : model == PYXRD_PROB_R2G2 ? 4 : model == PYXRD_PROB_R3G2 ? 8 : -1;
-    if (want < 1 || (model != PYXRD_PROB_R0 && G != 2) || (model == PYXRD_PROB_R0 && (G < 1 || G > 6)))
+    const int want = pyxrd_prob_rank(model, G);
+    if (want < 1)
         return fail(ctx, "leaf_probabilities: model %d with G = %d is not available", model, G);
     CK(cudaSetDevice(ctx->device));
     if (upload(ctx, ctx->d_leaf_a, params, PYXRD_PROB_STRIDE)) return 1;
-    CK(ctx->d_leaf_b.ensure(sizeof(double) * 128));
+    CK(ctx->d_leaf_b.ensure(sizeof(double) * 2 * PX_PROB_MAXSQ));
     CK(ctx->d_leaf_c.ensure(sizeof(int) * 2));
     k_leaf_probabilities<<<1, 32, 0, ctx->stream>>>(model, G, ctx->d_leaf_a.as<double>(), ctx->d_leaf_b.as<double>(),
-                                                     ctx->d_leaf_b.as<double>() + 64, ctx->d_leaf_c.as<int>());
+                                                     ctx->d_leaf_b.as<double>() + PX_PROB_MAXSQ, ctx->d_leaf_c.as<int>());
     LAUNCH_CHECK("k_leaf_probabilities");
     int flags[2] = {0, 0};
     CK(cudaMemcpyAsync(flags, ctx->d_leaf_c.ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(W_out, ctx->d_leaf_b.ptr, sizeof(double) * want * want, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(P_out, ctx->d_leaf_b.as<double>() + 64, sizeof(double) * want * want, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(P_out, ctx->d_leaf_b.as<double>() + PX_PROB_MAXSQ, sizeof(double) * want * want, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (valid_out) *valid_out = flags[0];
     if (rank_out) *rank_out = flags[1];

@@ -32,18 +32,19 @@ FLAG_APPLY_LPF = 2
 FLAG_APPLY_CORRECTION = 4
 FLAG_RAW_PATTERN = 8
 
-PROB_STRIDE = 8
+PROB_STRIDE = 12
 # PYXRD_PROB_* of include/pyxrd_b200.h: probability models the device evaluates itself
-PROB_MODELS = {"fixed": 0, "R0": 1, "R1G2": 2, "R2G2": 3, "R3G2": 4}
-_PROB_RANK = {1: lambda G: G, 2: lambda G: 2, 3: lambda G: 4, 4: lambda G: 8}
-_PROB_NPAR = {1: lambda G: G - 1, 2: lambda G: 2, 3: lambda G: 4, 4: lambda G: 2}
+PROB_MODELS = {"fixed": 0, "R0": 1, "R1G2": 2, "R2G2": 3, "R3G2": 4, "R1G3": 5, "R1G4": 6, "R2G3": 7}
+_PROB_G = {2: 2, 3: 2, 4: 2, 5: 3, 6: 4, 7: 3}
+_PROB_RANK = {1: lambda G: G, 2: lambda G: 2, 3: lambda G: 4, 4: lambda G: 8, 5: lambda G: 3, 6: lambda G: 4, 7: lambda G: 9}
+_PROB_NPAR = {1: lambda G: G - 1, 2: lambda G: 2, 3: lambda G: 4, 4: lambda G: 2, 5: lambda G: 6, 6: lambda G: 12, 7: lambda G: 6}
 
 _DIV_MODES = {"FIXED": 0.0, "AUTOMATIC": 1.0}
 
 
 def prob_model_of(phase):
     """(model code, parameter list) of a phase whose W / P the device derives from its probability
-    parameters: ad-hoc attributes ``prob_model`` ("R0" | "R1G2" | "R2G2" | "R3G2" or the code) and
+    parameters: ad-hoc attributes ``prob_model`` ("R0" | "R1G2" | "R1G3" | "R1G4" | "R2G2" | "R2G3" | "R3G2" or the code) and
     ``prob_params`` on the PhaseData (a DataObject is an attribute bag, data_objects.py:29-31)."""
     model = getattr(phase, "prob_model", None)
     if model is None:
@@ -53,7 +54,7 @@ def prob_model_of(phase):
         return 0, ()
     G = int(phase.G)
     params = [float(v) for v in getattr(phase, "prob_params", ())]
-    if code not in _PROB_RANK or (code != 1 and G != 2) or (code == 1 and not 1 <= G <= 6):
+    if code not in _PROB_RANK or (code != 1 and G != _PROB_G[code]) or (code == 1 and not 1 <= G <= 6):
         raise ValueError("probability model %r is not available for G = %d" % (model, G))
     if len(params) != _PROB_NPAR[code](G):
         raise ValueError("probability model %r with G = %d takes %d parameters, got %d"

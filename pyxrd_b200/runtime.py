@@ -387,7 +387,7 @@ class Context(object):
         p = np.zeros(PROB_STRIDE)
         params = _f64(params).ravel()
         p[:params.size] = params
-        W, P = np.zeros(64), np.zeros(64)
+        W, P = np.zeros(81), np.zeros(81)
         valid, rank = C.c_int(), C.c_int()
         self._check(self._lib.pyxrd_leaf_probabilities(self._h, code, int(G), _p(p, _f64p), _p(W, _f64p), _p(P, _f64p),
                                                        C.byref(valid), C.byref(rank)), "leaf_probabilities")
@@ -506,7 +506,7 @@ def expand_population(template: BatchPack, x, bindings, csds_auto=None, csds_fac
             scales=arr(e.scales, K * S, float).reshape(K, S),
             bgshifts=arr(e.bgshifts, K * S, float).reshape(K, S),
             prob_model=arr(e.prob_model, e.n_phases, np.int32) if e.prob_model else None,
-            prob_params=arr(e.prob_params, e.n_phases * 8, float).reshape(-1, 8) if e.prob_params else None)
+            prob_params=arr(e.prob_params, e.n_phases * 12, float).reshape(-1, 12) if e.prob_params else None)
         return out
     finally:
         lib.pyxrd_expanded_free(handle)

@@ -468,6 +468,8 @@ def template(name: str):
     """(template MixtureData, [Refinable]) of a configuration: the truth candidate with its probability
     matrices handed over to the device models (``prob_model`` / ``prob_params`` on the PhaseData) and the
     refinable parameters a refinement of that configuration would vary."""
+    if name == "models":
+        return _models_template()
     mix = CONFIGS[name].truth()
     refs = []
     if name == "c1":
@@ -506,6 +508,26 @@ def template(name: str):
     else:
         raise KeyError("configuration %r has no template (its W / P are not produced by a probability model)" % name)
     return mix, refs
+
+
+def _models_template():
+    """one specimen with a phase of each multi-component probability model the reference ships beyond the
+    BASELINE configurations: R1G3 (rank 3), R1G4 (rank 4), R2G3 (rank 9); every probability parameter refinable.
+    The ranges keep part of the samples inside [0, 1]; the rest exercise valid_probs = False."""
+    types = atom_types()
+    kinds = ["illite", "chlorite", "smectite_ad", "kaolinite"]
+    refs, phases = [], []
+    for tag, model, G, r, start, bounds in (
+            ("R1G3", "R1G3", 3, 3, [0.6, 0.7, 0.6, 0.5, 0.5, 0.5], [(0.3, 0.9)] + [(0.2, 0.9)] * 5),
+            ("R1G4", "R1G4", 4, 4, [0.6, 0.5, 0.5, 0.5, 0.5, 0.4, 0.5, 0.5, 0.8, 0.75, 0.7, 0.5], [(0.3, 0.9)] + [(0.2, 0.9)] * 11),
+            ("R2G3", "R2G3", 3, 9, [0.8, 0.9, 0.9, 0.9, 0.9, 0.9], [(0.55, 0.95)] + [(0.5, 0.98)] * 5)):
+        comps = [make_component(types, k, delta_c=0.02 if "smectite" in k else 0.0) for k in kinds[:G]]
+        ph = make_phase(comps, np.eye(r) / r, np.full((r, r), 1.0 / r), make_csds(9.0), sigma_star=5.0)
+        refs += _prob_refinables(tag, [ph], model, start, bounds)
+        refs += _phase_refinables(tag, [ph], (7.0, 12.0), (2.0, 12.0))
+        phases.append(ph)
+    spec = make_specimen(theta_grid(3.0, 40.0, 0.05), phases, make_goniometer("cu_pair"))
+    return make_mixture([spec], 3, fractions=[0.4, 0.3, 0.3]), refs
 
 
 def sample_solutions(refinables, seed: int, count: int) -> np.ndarray:

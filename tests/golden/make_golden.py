@@ -148,7 +148,8 @@ def extras(ref, out):
         settings.RESIDUAL_METHOD = "Rp"
 
 
-MODEL_CASES = [(1, 1, 0), (1, 2, 1), (1, 3, 2), (1, 4, 3), (1, 5, 4), (1, 6, 5), (2, 2, 2), (3, 2, 4), (4, 2, 2)]
+MODEL_CASES = [(1, 1, 0), (1, 2, 1), (1, 3, 2), (1, 4, 3), (1, 5, 4), (1, 6, 5), (2, 2, 2), (3, 2, 4), (4, 2, 2),
+               (5, 3, 6), (6, 4, 12), (7, 3, 6)]
 
 
 def model_parameter_sets(npar, n=120, seed=99):
@@ -173,7 +174,7 @@ def models(out):
     pm = _live_models.load().probabilities
     for model, G, npar in MODEL_CASES:
         params = model_parameter_sets(npar)
-        r = G ** {1: 1, 2: 1, 3: 2, 4: 3}[model]
+        r = G ** {1: 1, 2: 1, 3: 2, 4: 3, 5: 1, 6: 1, 7: 2}[model]
         Ws, Ps, valid = np.zeros((len(params), r, r)), np.zeros((len(params), r, r)), np.zeros(len(params), dtype=bool)
         for t, p in enumerate(params):
             if model == 1:
@@ -182,8 +183,14 @@ def models(out):
                 m = pm.R1G2Model(W1=p[0], P11_or_P22=p[1])
             elif model == 3:
                 m = pm.R2G2Model(W1=p[0], P112_or_P211=p[1], P21=p[2], P122_or_P221=p[3])
-            else:
+            elif model == 4:
                 m = pm.R3G2Model(W1=p[0], P1111_or_P2112=p[1])
+            elif model == 5:
+                m = pm.R1G3Model(*p)
+            elif model == 6:
+                m = pm.R1G4Model(*p)
+            else:
+                m = pm.R2G3Model(*p)
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 m.update()

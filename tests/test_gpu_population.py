@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-9
 OPT_RTOL = 5e-3
-CASES = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (2, 2), (3, 2), (4, 2)]
+CASES = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (2, 2), (3, 2), (4, 2), (5, 3), (6, 4), (7, 3)]
 
 
 @pytest.fixture(scope="module")
@@ -58,7 +58,7 @@ def _template(name):
     return PopulationTemplate(mix, refs), refs
 
 
-@pytest.mark.parametrize("name,K", [("c1", 6), ("c2", 6), ("c4", 5), ("c5", 3)])
+@pytest.mark.parametrize("name,K", [("c1", 6), ("c2", 6), ("c4", 5), ("c5", 3), ("models", 12)])
 def test_population_matches_oracle_on_rebuilt_graphs(ctx, name, K):
     tmpl, refs = _template(name)
     x = syn.sample_solutions(refs, 5, K)
@@ -72,6 +72,10 @@ def test_population_matches_oracle_on_rebuilt_graphs(ctx, name, K):
         for s, spec in enumerate(ref.specimens):
             assert rel_err(pis[k][s], spec.phase_intensities) < RTOL, (name, k, s)
         assert rel_err(res[k], ref.residuals) < RTOL, (name, k)
+    if name == "models":         # both verdicts of validate() occur in the sample
+        valid = [[om.probabilities(om.PROB_CODES[p.prob_model], p.G, p.prob_params)[2] for p in
+                  tmpl.apply(row, probabilities=om.probabilities).specimens[0].phases[0]] for row in x]
+        assert np.any(valid) and not np.all(valid)
 
 
 def test_population_equals_the_batch_path_bit_for_bit(ctx):

@@ -5,7 +5,7 @@ import pytest
 
 from oracle import pyxrd_oracle_models as om
 
-CASES = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (2, 2), (3, 2), (4, 2)]
+CASES = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (2, 2), (3, 2), (4, 2), (5, 3), (6, 4), (7, 3)]
 
 
 @pytest.mark.parametrize("model,G", CASES)
@@ -20,7 +20,7 @@ def test_oracle_models_bit_identical_to_live_reference(golden, model, G):
         assert np.array_equal(gW, W, equal_nan=True) and np.array_equal(gP, P, equal_nan=True), (key, p)
         assert gv == bool(v), (key, p)
         seen.add(bool(v))
-    if model == om.R2G2:        # the only family whose relations can leave [0, 1] (R1G2 cannot, R3G2 clamps)
+    if model not in (om.R0, om.R1G2, om.R3G2):        # R0 / R1G2 cannot leave [0, 1], R3G2 clamps
         assert seen == {True, False}, "golden set must exercise valid and invalid parameter sets"
 
 

@@ -28,7 +28,7 @@ def built_candidates(tmpl, x):
     return out
 
 
-@pytest.mark.parametrize("name,K", [("c1", 5), ("c2", 7), ("c4", 4), ("c5", 3)])
+@pytest.mark.parametrize("name,K", [("c1", 5), ("c2", 7), ("c4", 4), ("c5", 3), ("models", 6)])
 def test_expansion_equals_packing_of_rebuilt_graphs(name, K):
     _ensure_built()
     mix, refs = syn.template(name)
