@@ -128,9 +128,10 @@ typedef struct {
  * DataObject graphs and packing each of them (refinement/refiner.py:91-109,
  * mixture/models/mixture.py:53-85: 6.4 ms per trial in the reference, 70 us per trial in packing.py),
  * the template candidate is packed once and a binding table says which packed slot every refinable
- * drives: slot = scale * x[param] + offset.  The expansion is native host code (memcpy + K * n_bindings
- * multiply-adds); everything numeric that depends on the bound values -- probability matrices, CSDS
- * distribution, absolute scale, z-stretch -- is computed on the device by the batch prologue. */
+ * drives: slot = scale * x[param] + offset.  The expansion runs on the device (pyxrd_set_population and the
+ * calls built on it; pyxrd_expand_population is the same expansion as native host code, for inspection and
+ * tests); everything numeric that depends on the bound values -- probability matrices, CSDS distribution,
+ * absolute scale, z-stretch -- is computed on the device by the batch prologue. */
 #define PYXRD_BIND_PHASE_D 0    /* phase_d[index]: phase * 8 + {0 sigma_star, 1 CSDS average, 2..5 alpha / beta} */
 #define PYXRD_BIND_COMP_D 1     /* comp_d[index]: component * 8 + {0 d001, 1 default_c, 2 delta_c, 3 lattice_d, 4 volume, 5 weight} */
 #define PYXRD_BIND_ATOM_D 2     /* atom_d[index]: atom * 2 + {0 pn, 1 default_z} */
@@ -169,7 +170,9 @@ int pyxrd_expand_population(const pyxrd_batch_desc *template_desc, const pyxrd_p
 void pyxrd_expanded_desc(const pyxrd_expanded *e, pyxrd_batch_desc *out);
 void pyxrd_expanded_free(pyxrd_expanded *e);
 const char *pyxrd_expand_error(void);   /* message of the last failed pyxrd_expand_population of this thread */
-/* expand + pyxrd_set_batch */
+/* the same expansion on the DEVICE (k_expand_population): the packed template, x[K][d] and the table are uploaded
+ * (K * d * 8 bytes per generation instead of K parameter blocks), every candidate's slice of the batch arrays, its
+ * job table and job lists are written by one kernel, then the batch prologue runs as after pyxrd_set_batch */
 int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *template_desc, const pyxrd_population_desc *pop);
 /* set_population + compute_intensities + compute_residuals -> residuals [K][1+S] */
 int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *template_desc, const pyxrd_population_desc *pop,

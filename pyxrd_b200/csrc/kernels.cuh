@@ -515,6 +515,88 @@ __device__ int prob_evaluate(int model, int G, const double *par, double *Wout, 
 }
 
 // ---------------------------------------------------------------------------------
+// population from a template + binding table, expanded on the device:
+// per generation only the solution vectors x[K][d] cross PCIe.  Block k writes candidate k's slice of
+// every batch array (template values, table indices moved into the candidate's own tables), applies the
+// bindings slot = scale * x[k][param] + offset in table order (a later row wins, as in the host version
+// pyxrd_expand_population), then the automatic CSDS maximum int(factor * average)
+// (phases/models/CSDS.py:127,140).  Job tables and the per-class job lists are generated alongside.
+// ---------------------------------------------------------------------------------
+struct ExpandDev {
+    int K, D, NB, NP, NC, NA, NPC, M, S, JPC, NCLS;
+    long long NM, cand_stride;
+    // template (one candidate)
+    const int *t_phase_i, *t_phase_comp, *t_comp_i, *t_atom_t, *t_job_pb, *t_job_spec, *t_jobids, *t_pmodel;
+    const long long *t_job_out;
+    const double *t_phase_d, *t_matrices, *t_comp_d, *t_atom_d, *t_frac, *t_scales, *t_bg, *t_pparam;
+    const int *cls_first, *cls_n;            // [NCLS] position / length of each class inside t_jobids
+    const double *x;                         // [K][D]
+    const pyxrd_binding *bind;               // [NB]
+    const unsigned char *auto_max;           // [NP] or nullptr
+    double factor;
+    // destination (K candidates)
+    int *phase_i, *phase_comp, *comp_i, *atom_t, *job_pb, *job_spec, *jobids, *pmodel;
+    long long *job_out;
+    double *phase_d, *matrices, *comp_d, *atom_d, *frac, *scales, *bg, *pparam;
+};
+
+__global__ void __launch_bounds__(128) k_expand_population(ExpandDev e) {
+    const int k = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+    for (int i = t; i < e.NP * 8; i += nt) {
+        int v = e.t_phase_i[i];
+        if ((i & 7) == 5) v += k * e.NPC;
+        if ((i & 7) == 6) v += (int)(k * e.NM);
+        e.phase_i[(size_t)k * e.NP * 8 + i] = v;
+    }
+    for (int i = t; i < e.NP * 8; i += nt) e.phase_d[(size_t)k * e.NP * 8 + i] = e.t_phase_d[i];
+    for (int i = t; i < e.NPC; i += nt) e.phase_comp[(size_t)k * e.NPC + i] = e.t_phase_comp[i] + k * e.NC;
+    for (long long i = t; i < e.NM; i += nt) e.matrices[(size_t)k * e.NM + i] = e.t_matrices[i];
+    for (int i = t; i < e.NC * 8; i += nt) e.comp_d[(size_t)k * e.NC * 8 + i] = e.t_comp_d[i];
+    for (int i = t; i < e.NC * 4; i += nt) e.comp_i[(size_t)k * e.NC * 4 + i] = e.t_comp_i[i] + ((i & 3) == 0 ? k * e.NA : 0);
+    for (int i = t; i < e.NA * 2; i += nt) e.atom_d[(size_t)k * e.NA * 2 + i] = e.t_atom_d[i];
+    for (int i = t; i < e.NA; i += nt) e.atom_t[(size_t)k * e.NA + i] = e.t_atom_t[i];
+    for (int i = t; i < e.M; i += nt) e.frac[(size_t)k * e.M + i] = e.t_frac[i];
+    for (int i = t; i < e.S; i += nt) { e.scales[(size_t)k * e.S + i] = e.t_scales[i]; e.bg[(size_t)k * e.S + i] = e.t_bg[i]; }
+    if (e.pmodel) {
+        for (int i = t; i < e.NP; i += nt) e.pmodel[(size_t)k * e.NP + i] = e.t_pmodel[i];
+        for (int i = t; i < e.NP * PX_PROB_STRIDE; i += nt) e.pparam[(size_t)k * e.NP * PX_PROB_STRIDE + i] = e.t_pparam[i];
+    }
+    for (int i = t; i < e.JPC; i += nt) {
+        const int pb = e.t_job_pb[i];
+        e.job_pb[(size_t)k * e.JPC + i] = pb >= 0 ? pb + k * e.NP : pb;
+        e.job_spec[(size_t)k * e.JPC + i] = e.t_job_spec[i];
+        e.job_out[(size_t)k * e.JPC + i] = e.t_job_out[i] + k * e.cand_stride;
+    }
+    for (int c = 0; c < e.NCLS; ++c) {
+        const int first = e.cls_first[c], n = e.cls_n[c];
+        for (int i = t; i < n; i += nt) e.jobids[(size_t)first * e.K + (size_t)k * n + i] = k * e.JPC + e.t_jobids[first + i];
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double *xk = e.x + (size_t)k * e.D;
+        for (int b = 0; b < e.NB; ++b) {
+            const pyxrd_binding bd = e.bind[b];
+            const double v = __dadd_rn(__dmul_rn(bd.scale, xk[bd.param]), bd.offset);
+            switch (bd.target) {
+                case 0: e.phase_d[(size_t)k * e.NP * 8 + bd.index] = v; break;
+                case 1: e.comp_d[(size_t)k * e.NC * 8 + bd.index] = v; break;
+                case 2: e.atom_d[(size_t)k * e.NA * 2 + bd.index] = v; break;
+                case 3: e.matrices[(size_t)k * e.NM + bd.index] = v; break;
+                case 4: e.pparam[(size_t)k * e.NP * PX_PROB_STRIDE + bd.index] = v; break;
+                case 5: e.frac[(size_t)k * e.M + bd.index] = v; break;
+                case 6: e.scales[(size_t)k * e.S + bd.index] = v; break;
+                default: e.bg[(size_t)k * e.S + bd.index] = v; break;
+            }
+        }
+    }
+    __syncthreads();
+    if (e.auto_max)
+        for (int p = t; p < e.NP; p += nt)
+            if (e.auto_max[p])
+                e.phase_i[((size_t)k * e.NP + p) * 8 + 3] = (int)__dmul_rn(e.factor, e.phase_d[((size_t)k * e.NP + p) * 8 + 1]);
+}
+
+// ---------------------------------------------------------------------------------
 // per-candidate prologue
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ double lognormal_dev(double T, double a, double b) {

@@ -62,7 +62,18 @@ struct RankClass {
     int max_x = 0;
     int max_ntop_cap = 0;
     size_t first = 0;          // position of this class in the device job-id list
-    std::vector<int> jobs;
+    std::vector<int> jobs;     // ascending job ids (general batches)
+    // populations expanded on the device: every candidate has the template's per_cand jobs of this class, the
+    // device list holds them candidate by candidate; `jobs` is empty then
+    size_t per_cand = 0;
+    bool uniform = false;
+    size_t count(int K) const { return uniform ? per_cand * (size_t)K : jobs.size(); }
+    // [a, b) inside this class's device list of the jobs of candidates [k0, k1)
+    void range(int k0, int k1, long long j0, long long j1, size_t &a, size_t &b) const {
+        if (uniform) { a = per_cand * (size_t)k0; b = per_cand * (size_t)k1; return; }
+        a = std::lower_bound(jobs.begin(), jobs.end(), (int)j0) - jobs.begin();
+        b = std::lower_bound(jobs.begin(), jobs.end(), (int)j1) - jobs.begin();
+    }
 };
 
 }  // namespace
@@ -109,6 +120,8 @@ struct pyxrd_ctx {
     std::vector<RankClass> classes;
     DevBuf d_blob;           // all uploaded batch arrays, one allocation
     PinBuf h_blob;
+    DevBuf d_tmpl;           // template candidate + solution vectors + binding table of a device-expanded population
+    PinBuf h_tmpl;
     const int *jobids_dev = nullptr;   // inside d_blob
     DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_phase_valid, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
     int residual_method = PYXRD_RESIDUAL_RP;   // settings.RESIDUAL_METHOD (mixture.py:22-27,89)
@@ -317,11 +330,12 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_invsin, &ctx->d_stl,
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
-                      &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob,
+                      &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob, &ctx->d_tmpl,
                       &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
                       &ctx->d_res, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
+    ctx->h_tmpl.release();
     ctx->h_res.release();
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
@@ -452,19 +466,47 @@ int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
     return 0;
 }
 
-int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
-    if (!ctx || !d) return 1;
-    if (!ctx->have_static) return fail(ctx, "set_batch: call pyxrd_set_static first");
-    CK(cudaSetDevice(ctx->device));
-    ctx->have_batch = false;
-    ctx->have_intensities = false;
-    ctx->have_opt = false;
-    const StaticDev &st = ctx->st;
-    const int K = d->n_candidates, M = d->n_phase_slots, NP = d->n_phases, NC = d->n_components, NA = d->n_atoms;
-    const int S = st.S, Z = st.Z;
-    if (K <= 0 || M <= 0) return fail(ctx, "set_batch: need K > 0 and M > 0 (K=%d M=%d)", K, M);
+}  // extern "C"
 
-    // ---- validate parameter blocks and find the coefficient stride -------------------
+namespace {
+
+// parts of the batch blob (one device allocation, identical layout for uploaded and device-expanded batches)
+enum { P_PHASE_I, P_PHASE_D, P_PHASE_COMP, P_MATRICES, P_COMP_D, P_COMP_I, P_ATOM_D, P_ATOM_T, P_JOB_PB, P_JOB_SPEC,
+       P_JOB_OUT, P_JOBIDS, P_FRAC, P_SCALES, P_BG, P_PMODEL, P_PPARAM, P_COUNT };
+
+struct BatchSizes {
+    int K = 0, M = 0, NP = 0, NC = 0, NA = 0, NPC = 0;
+    int64_t NM = 0;
+    long long NJ = 0;
+    size_t njobids = 0;
+    bool model_driven = false;
+};
+
+struct BlobLayout {
+    size_t off[P_COUNT], bytes[P_COUNT], total = 0;
+};
+
+BlobLayout plan_blob(const BatchSizes &z, int S) {
+    BlobLayout L;
+    const size_t bytes[P_COUNT] = {
+        sizeof(int32_t) * (size_t)z.NP * PYXRD_PHASE_I_STRIDE, sizeof(double) * (size_t)z.NP * PYXRD_PHASE_D_STRIDE,
+        sizeof(int32_t) * (size_t)z.NPC, sizeof(double) * (size_t)z.NM, sizeof(double) * (size_t)z.NC * PYXRD_COMP_D_STRIDE,
+        sizeof(int32_t) * (size_t)z.NC * PYXRD_COMP_I_STRIDE, sizeof(double) * (size_t)z.NA * PYXRD_ATOM_D_STRIDE,
+        sizeof(int32_t) * (size_t)z.NA, sizeof(int) * (size_t)z.NJ, sizeof(int) * (size_t)z.NJ, sizeof(long long) * (size_t)z.NJ,
+        sizeof(int) * z.njobids, sizeof(double) * (size_t)z.K * z.M, sizeof(double) * (size_t)z.K * S, sizeof(double) * (size_t)z.K * S,
+        z.model_driven ? sizeof(int32_t) * (size_t)z.NP : 0, z.model_driven ? sizeof(double) * (size_t)z.NP * PYXRD_PROB_STRIDE : 0};
+    for (int i = 0; i < P_COUNT; ++i) {
+        L.off[i] = L.total;
+        L.bytes[i] = bytes[i];
+        L.total = align_up(L.total + std::max<size_t>(bytes[i], 8), 256);
+    }
+    return L;
+}
+
+// parameter blocks of a batch descriptor are well formed; *ncap = coefficient stride (largest CSDS maximum + 2)
+int validate_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, int *ncap_out) {
+    const StaticDev &st = ctx->st;
+    const int NP = d->n_phases, NC = d->n_components, NA = d->n_atoms;
     int ncap = 2;
     for (int p = 0; p < NP; ++p) {
         const int32_t *pi = d->phase_i + (size_t)p * PYXRD_PHASE_I_STRIDE;
@@ -479,6 +521,8 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
             return fail(ctx, "set_batch: phase %d has unsupported G=%d rank=%d (need 1<=G<=%d, rank<=%d, rank %% G == 0)",
                         p, G, r, PYXRD_MAX_COMPONENTS, PYXRD_MAX_RANK);
         if (pi[2] < 0 || pi[3] < pi[2]) return fail(ctx, "set_batch: phase %d CSDS range [%d, %d] unsupported", p, pi[2], pi[3]);
+        if (pi[6] < 0 || (int64_t)pi[6] + 2 * (int64_t)r * r > d->n_matrix)
+            return fail(ctx, "set_batch: phase %d: W / P at offset %d leave the matrix pool (%lld doubles)", p, pi[6], (long long)d->n_matrix);
         if (d->prob_model && d->prob_params && d->prob_model[p] != PYXRD_PROB_FIXED) {
             const int m = d->prob_model[p];
             if (pyxrd_prob_rank(m, G) != r)
@@ -486,6 +530,7 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
         }
         ncap = std::max(ncap, pi[3] + 2);
         int atoms = 0;
+        if (pi[5] < 0 || pi[5] + G > d->n_phase_comp) return fail(ctx, "set_batch: phase %d: component list leaves phase_comp", p);
         for (int c = 0; c < G; ++c) {
             const int ci = d->phase_comp[pi[5] + c];
             if (ci < 0 || ci >= NC) return fail(ctx, "set_batch: phase %d references component %d of %d", p, ci, NC);
@@ -495,13 +540,21 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     }
     for (int a = 0; a < NA; ++a)
         if (d->atom_type[a] >= st.T) return fail(ctx, "set_batch: atom %d references atom type %d of %d", a, d->atom_type[a], st.T);
+    *ncap_out = ncap;
+    return 0;
+}
 
-    // ---- job lists per (rank, G) class ------------------------------------------------
+// job tables [K][S][Z][M] of a descriptor and the job lists per (rank, G) class, heavy classes first
+int build_jobs(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, std::vector<int> &job_pb, std::vector<int> &job_spec,
+               std::vector<long long> &job_out, std::vector<int> &jobids) {
+    const StaticDev &st = ctx->st;
+    const int K = d->n_candidates, M = d->n_phase_slots, NP = d->n_phases, S = st.S, Z = st.Z;
     const long long cand_stride = (long long)M * Z * st.sumX;
     const long long NJ = (long long)K * S * Z * M;
     if (NJ > 0x7fffffffLL) return fail(ctx, "set_batch: too many patterns (%lld)", NJ);
-    std::vector<int> job_pb((size_t)NJ), job_spec((size_t)NJ);
-    std::vector<long long> job_out((size_t)NJ);
+    job_pb.assign((size_t)NJ, 0);
+    job_spec.assign((size_t)NJ, 0);
+    job_out.assign((size_t)NJ, 0);
     std::map<std::pair<int, int>, int> class_of;
     ctx->classes.clear();
     long long j = 0;
@@ -533,45 +586,17 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
                 }
     // heavy classes first so the tail of the grid is filled by the cheap ones
     std::sort(ctx->classes.begin(), ctx->classes.end(), [](const RankClass &a, const RankClass &b) { return a.rank > b.rank; });
-    std::vector<int> jobids;
+    jobids.clear();
     for (RankClass &rc : ctx->classes) jobids.insert(jobids.end(), rc.jobs.begin(), rc.jobs.end());
+    return 0;
+}
 
-    // ---- one pinned blob, one H2D copy ---------------------------------------------------
-    struct Part { const void *src; size_t bytes; size_t off; };
-    std::vector<Part> parts;
-    size_t total = 0;
-    auto add = [&](const void *src, size_t bytes) {
-        Part p{src, bytes, total};
-        total = align_up(total + std::max<size_t>(bytes, 8), 256);
-        parts.push_back(p);
-        return parts.size() - 1;
-    };
-    const size_t i_phase_i = add(d->phase_i, sizeof(int32_t) * (size_t)NP * PYXRD_PHASE_I_STRIDE);
-    const size_t i_phase_d = add(d->phase_d, sizeof(double) * (size_t)NP * PYXRD_PHASE_D_STRIDE);
-    const size_t i_phase_comp = add(d->phase_comp, sizeof(int32_t) * (size_t)d->n_phase_comp);
-    const size_t i_matrices = add(d->matrices, sizeof(double) * (size_t)d->n_matrix);
-    const size_t i_comp_d = add(d->comp_d, sizeof(double) * (size_t)NC * PYXRD_COMP_D_STRIDE);
-    const size_t i_comp_i = add(d->comp_i, sizeof(int32_t) * (size_t)NC * PYXRD_COMP_I_STRIDE);
-    const size_t i_atom_d = add(d->atom_d, sizeof(double) * (size_t)NA * PYXRD_ATOM_D_STRIDE);
-    const size_t i_atom_t = add(d->atom_type, sizeof(int32_t) * (size_t)NA);
-    const size_t i_job_pb = add(job_pb.data(), sizeof(int) * (size_t)NJ);
-    const size_t i_job_spec = add(job_spec.data(), sizeof(int) * (size_t)NJ);
-    const size_t i_job_out = add(job_out.data(), sizeof(long long) * (size_t)NJ);
-    const size_t i_jobids = add(jobids.data(), sizeof(int) * jobids.size());
-    const size_t i_frac = add(d->fractions, sizeof(double) * (size_t)K * M);
-    const size_t i_scales = add(d->scales, sizeof(double) * (size_t)K * S);
-    const size_t i_bg = add(d->bgshifts, sizeof(double) * (size_t)K * S);
-    const bool model_driven = d->prob_model && d->prob_params;
-    const size_t i_pmodel = add(model_driven ? d->prob_model : nullptr, model_driven ? sizeof(int32_t) * (size_t)NP : 0);
-    const size_t i_pparam = add(model_driven ? d->prob_params : nullptr, model_driven ? sizeof(double) * (size_t)NP * PYXRD_PROB_STRIDE : 0);
-    CK(cudaStreamSynchronize(ctx->stream));        // the pinned blob may still feed a previous copy
-    CK(ctx->h_blob.ensure(total));
-    CK(ctx->d_blob.ensure(total));
-    for (const Part &p : parts)
-        if (p.bytes) memcpy(static_cast<char *>(ctx->h_blob.ptr) + p.off, p.src, p.bytes);
-    CK(cudaMemcpyAsync(ctx->d_blob.ptr, ctx->h_blob.ptr, total, cudaMemcpyHostToDevice, ctx->stream));
-    auto dev = [&](size_t idx) { return static_cast<char *>(ctx->d_blob.ptr) + parts[idx].off; };
-
+// derived buffers, the BatchDev view of the blob, and the per-candidate prologue kernels
+int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int ncap) {
+    const StaticDev &st = ctx->st;
+    const int K = z.K, M = z.M, NP = z.NP, NC = z.NC, NA = z.NA, S = st.S, Z = st.Z;
+    const long long cand_stride = (long long)M * Z * st.sumX;
+    auto dev = [&](int idx) { return static_cast<char *>(ctx->d_blob.ptr) + L.off[idx]; };
     CK(ctx->d_atom_z.ensure(sizeof(double) * std::max(NA, 1)));
     CK(ctx->d_atom_plane.ensure(sizeof(int) * std::max(NA, 1)));
     CK(ctx->d_comp_np.ensure(sizeof(int) * std::max(NC, 1)));
@@ -593,39 +618,39 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     BatchDev &bt = ctx->bt;
     bt.K = K; bt.M = M; bt.NP = NP; bt.NC = NC; bt.NA = NA; bt.ncap = ncap;
     bt.cand_stride = cand_stride;
-    bt.phase_i = reinterpret_cast<const int *>(dev(i_phase_i));
-    bt.phase_d = reinterpret_cast<const double *>(dev(i_phase_d));
-    bt.phase_comp = reinterpret_cast<const int *>(dev(i_phase_comp));
-    bt.matrices = reinterpret_cast<const double *>(dev(i_matrices));
-    bt.comp_d = reinterpret_cast<const double *>(dev(i_comp_d));
-    bt.comp_i = reinterpret_cast<const int *>(dev(i_comp_i));
-    bt.atom_d = reinterpret_cast<const double *>(dev(i_atom_d));
-    bt.atom_type = reinterpret_cast<const int *>(dev(i_atom_t));
+    bt.phase_i = reinterpret_cast<const int *>(dev(P_PHASE_I));
+    bt.phase_d = reinterpret_cast<const double *>(dev(P_PHASE_D));
+    bt.phase_comp = reinterpret_cast<const int *>(dev(P_PHASE_COMP));
+    bt.matrices = reinterpret_cast<const double *>(dev(P_MATRICES));
+    bt.comp_d = reinterpret_cast<const double *>(dev(P_COMP_D));
+    bt.comp_i = reinterpret_cast<const int *>(dev(P_COMP_I));
+    bt.atom_d = reinterpret_cast<const double *>(dev(P_ATOM_D));
+    bt.atom_type = reinterpret_cast<const int *>(dev(P_ATOM_T));
     bt.atom_z = ctx->d_atom_z.as<double>();
     bt.atom_plane = ctx->d_atom_plane.as<int>();
     bt.comp_nplanes = ctx->d_comp_np.as<int>();
     bt.phase_x = ctx->d_phase_x.as<double>();
     bt.coef = ctx->d_coef.as<double>();
-    bt.prob_model = model_driven ? reinterpret_cast<const int *>(dev(i_pmodel)) : nullptr;
-    bt.prob_params = model_driven ? reinterpret_cast<const double *>(dev(i_pparam)) : nullptr;
+    bt.prob_model = z.model_driven ? reinterpret_cast<const int *>(dev(P_PMODEL)) : nullptr;
+    bt.prob_params = z.model_driven ? reinterpret_cast<const double *>(dev(P_PPARAM)) : nullptr;
     bt.phase_valid = ctx->d_phase_valid.as<int>();
-    bt.job_pb = reinterpret_cast<const int *>(dev(i_job_pb));
-    bt.job_spec = reinterpret_cast<const int *>(dev(i_job_spec));
-    bt.job_out = reinterpret_cast<const long long *>(dev(i_job_out));
-    bt.fractions = reinterpret_cast<const double *>(dev(i_frac));
-    bt.scales = reinterpret_cast<const double *>(dev(i_scales));
-    bt.bgshifts = reinterpret_cast<const double *>(dev(i_bg));
+    bt.job_pb = reinterpret_cast<const int *>(dev(P_JOB_PB));
+    bt.job_spec = reinterpret_cast<const int *>(dev(P_JOB_SPEC));
+    bt.job_out = reinterpret_cast<const long long *>(dev(P_JOB_OUT));
+    bt.fractions = reinterpret_cast<const double *>(dev(P_FRAC));
+    bt.scales = reinterpret_cast<const double *>(dev(P_SCALES));
+    bt.bgshifts = reinterpret_cast<const double *>(dev(P_BG));
     bt.intensities = ctx->d_int.as<double>();
     bt.scaled = nullptr;
     bt.totals = ctx->d_tot.as<double>();
     bt.residuals = ctx->d_res.as<double>();
-    ctx->NJ = (int)NJ;
-    ctx->jobids_dev = reinterpret_cast<const int *>(dev(i_jobids));
+    ctx->NJ = (int)z.NJ;
+    ctx->jobids_dev = reinterpret_cast<const int *>(dev(P_JOBIDS));
     {
         size_t pos = 0;
         for (RankClass &rc : ctx->classes) {
             rc.first = pos;
-            pos += rc.jobs.size();
+            pos += rc.count(K);
         }
     }
 
@@ -644,6 +669,44 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     ctx->ev_set[3] = true;
     ctx->have_batch = true;
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
+    if (!ctx || !d) return 1;
+    if (!ctx->have_static) return fail(ctx, "set_batch: call pyxrd_set_static first");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_batch = false;
+    ctx->have_intensities = false;
+    ctx->have_opt = false;
+    const StaticDev &st = ctx->st;
+    if (d->n_candidates <= 0 || d->n_phase_slots <= 0)
+        return fail(ctx, "set_batch: need K > 0 and M > 0 (K=%d M=%d)", d->n_candidates, d->n_phase_slots);
+    int ncap = 2;
+    if (validate_batch(ctx, d, &ncap)) return 1;
+    std::vector<int> job_pb, job_spec, jobids;
+    std::vector<long long> job_out;
+    if (build_jobs(ctx, d, job_pb, job_spec, job_out, jobids)) return 1;
+
+    BatchSizes z;
+    z.K = d->n_candidates; z.M = d->n_phase_slots; z.NP = d->n_phases; z.NC = d->n_components; z.NA = d->n_atoms;
+    z.NPC = d->n_phase_comp; z.NM = d->n_matrix; z.NJ = (long long)job_pb.size(); z.njobids = jobids.size();
+    z.model_driven = d->prob_model && d->prob_params;
+    const BlobLayout L = plan_blob(z, st.S);
+    // ---- one pinned blob, one H2D copy ---------------------------------------------------
+    const void *src[P_COUNT] = {d->phase_i, d->phase_d, d->phase_comp, d->matrices, d->comp_d, d->comp_i, d->atom_d, d->atom_type,
+                                job_pb.data(), job_spec.data(), job_out.data(), jobids.data(), d->fractions, d->scales, d->bgshifts,
+                                z.model_driven ? d->prob_model : nullptr, z.model_driven ? d->prob_params : nullptr};
+    CK(cudaStreamSynchronize(ctx->stream));        // the pinned blob may still feed a previous copy
+    CK(ctx->h_blob.ensure(L.total));
+    CK(ctx->d_blob.ensure(L.total));
+    for (int i = 0; i < P_COUNT; ++i)
+        if (L.bytes[i] && src[i]) memcpy(static_cast<char *>(ctx->h_blob.ptr) + L.off[i], src[i], L.bytes[i]);
+    CK(cudaMemcpyAsync(ctx->d_blob.ptr, ctx->h_blob.ptr, L.total, cudaMemcpyHostToDevice, ctx->stream));
+    return bind_batch(ctx, z, L, ncap);
 }
 
 
@@ -684,14 +747,14 @@ int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
     const long long j0 = (long long)k0 * ctx->jobs_per_cand, j1 = (long long)k1 * ctx->jobs_per_cand;
     // None phases / invalid probabilities / empty specimens stay zero (specimen.py:63, phases.py:109-111)
     size_t listed = 0;
-    for (const RankClass &rc : ctx->classes) listed += rc.jobs.size();
+    for (const RankClass &rc : ctx->classes) listed += rc.count(ctx->bt.K);
     if (listed != (size_t)ctx->NJ && bt.cand_stride > 0)
         CK(cudaMemsetAsync(bt.intensities + (long long)k0 * bt.cand_stride, 0,
                            sizeof(double) * (size_t)(k1 - k0) * bt.cand_stride, ctx->stream));
     if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     for (const RankClass &rc : ctx->classes) {
-        const size_t a = std::lower_bound(rc.jobs.begin(), rc.jobs.end(), (int)j0) - rc.jobs.begin();
-        const size_t b = std::lower_bound(rc.jobs.begin(), rc.jobs.end(), (int)j1) - rc.jobs.begin();
+        size_t a, b;
+        rc.range(k0, k1, j0, j1, a, b);
         if (b > a && launch_class(ctx, rc, ctx->jobids_dev + rc.first + a, b - a, bt)) return 1;
     }
     if (timed) {
@@ -1093,15 +1156,157 @@ void pyxrd_expanded_free(pyxrd_expanded *e) { delete e; }
 
 int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop) {
     if (!ctx) return 1;
+    if (!t || !pop) return fail(ctx, "set_population: null argument");
     if (!ctx->have_static) return fail(ctx, "set_population: call pyxrd_set_static first");
-    if (pop && (pop->n_specimens != ctx->st.S || pop->n_patterns != ctx->st.Z))
+    const StaticDev &st = ctx->st;
+    if (pop->n_specimens != st.S || pop->n_patterns != st.Z)
         return fail(ctx, "set_population: S / Z of the population (%d, %d) differ from the static tables (%d, %d)",
-                    pop->n_specimens, pop->n_patterns, ctx->st.S, ctx->st.Z);
-    pyxrd_expanded *e = nullptr;
-    if (pyxrd_expand_population(t, pop, &e)) return fail(ctx, "%s", g_expand_error.c_str());
-    const int rc = pyxrd_set_batch(ctx, &e->desc);       // copies everything into its pinned blob
-    pyxrd_expanded_free(e);
-    return rc;
+                    pop->n_specimens, pop->n_patterns, st.S, st.Z);
+    if (t->n_candidates != 1) return fail(ctx, "set_population: the template must hold exactly one candidate");
+    const int K = pop->n_candidates, D = pop->n_params, NB = pop->n_bindings, S = st.S, Z = st.Z;
+    if (K <= 0 || D < 0 || NB < 0 || t->n_phase_slots <= 0) return fail(ctx, "set_population: need K > 0, M > 0");
+    if (NB > 0 && (!pop->bindings || !pop->x)) return fail(ctx, "set_population: bindings without a table / solution vectors");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_batch = false;
+    ctx->have_intensities = false;
+    ctx->have_opt = false;
+    const int NP = t->n_phases, NC = t->n_components, NA = t->n_atoms, NPC = t->n_phase_comp, M = t->n_phase_slots;
+    const int64_t NM = t->n_matrix;
+    if ((int64_t)NP * K > 0x7fffffffLL || (int64_t)NA * K > 0x7fffffffLL || NM * K > 0x7fffffffLL)
+        return fail(ctx, "set_population: population too large for 32-bit indices");
+    int ncap = 2;
+    if (validate_batch(ctx, t, &ncap)) return 1;
+    const bool model_driven = t->prob_model && t->prob_params;
+    const size_t per[8] = {(size_t)NP * PYXRD_PHASE_D_STRIDE, (size_t)NC * PYXRD_COMP_D_STRIDE, (size_t)NA * PYXRD_ATOM_D_STRIDE, (size_t)NM,
+                           model_driven ? (size_t)NP * PYXRD_PROB_STRIDE : 0, (size_t)M, (size_t)S, (size_t)S};
+    for (int b = 0; b < NB; ++b) {
+        const pyxrd_binding &bd = pop->bindings[b];
+        if (bd.target < 0 || bd.target > 7 || bd.param < 0 || bd.param >= D || bd.index < 0 || (size_t)bd.index >= per[bd.target])
+            return fail(ctx, "set_population: binding %d is out of range", b);
+    }
+    // template job tables and classes (K = 1); every candidate repeats them
+    std::vector<int> job_pb, job_spec, jobids;
+    std::vector<long long> job_out;
+    if (build_jobs(ctx, t, job_pb, job_spec, job_out, jobids)) return 1;
+    // the automatic CSDS maximum depends on the bound average: its range over the population sizes the coefficient
+    // table and the shared memory of each class (the last binding of a slot wins, as in the expansion)
+    std::vector<int> pmax(NP), pmin(NP);
+    for (int p = 0; p < NP; ++p) pmax[p] = pmin[p] = t->phase_i[(size_t)p * PYXRD_PHASE_I_STRIDE + 3];
+    if (pop->csds_auto_maximum)
+        for (int p = 0; p < NP; ++p) {
+            if (!pop->csds_auto_maximum[p]) continue;
+            const pyxrd_binding *last = nullptr;
+            for (int b = 0; b < NB; ++b)
+                if (pop->bindings[b].target == PYXRD_BIND_PHASE_D && pop->bindings[b].index == p * PYXRD_PHASE_D_STRIDE + 1) last = &pop->bindings[b];
+            int lo, hi;
+            if (!last) {
+                lo = hi = (int32_t)(pop->csds_factor * t->phase_d[(size_t)p * PYXRD_PHASE_D_STRIDE + 1]);
+            } else {
+                lo = 0x7fffffff; hi = -0x7fffffff;
+                for (int k = 0; k < K; ++k) {
+                    const double avg = last->scale * pop->x[(size_t)k * D + last->param] + last->offset;
+                    const double mx = pop->csds_factor * avg;
+                    if (!(mx > -1e9 && mx < 1e9)) return fail(ctx, "set_population: candidate %d: CSDS average %g of phase %d is not usable", k, avg, p);
+                    lo = std::min(lo, (int)mx);
+                    hi = std::max(hi, (int)mx);
+                }
+            }
+            pmin[p] = lo; pmax[p] = hi;
+            const int32_t *pi = t->phase_i + (size_t)p * PYXRD_PHASE_I_STRIDE;
+            if ((pi[4] & PYXRD_FLAG_VALID_PROBS) && !(pi[4] & PYXRD_FLAG_RAW_PATTERN) && lo < pi[2])
+                return fail(ctx, "set_batch: phase %d CSDS range [%d, %d] unsupported", p, pi[2], lo);
+        }
+    const size_t JPC = job_pb.size();
+    std::vector<int> cls_first, cls_n;
+    {
+        size_t pos = 0;
+        for (RankClass &rc : ctx->classes) {
+            cls_first.push_back((int)pos);
+            cls_n.push_back((int)rc.jobs.size());
+            pos += rc.jobs.size();
+            for (int j : rc.jobs) {
+                const int pb = job_pb[j];
+                const int32_t *pi = t->phase_i + (size_t)pb * PYXRD_PHASE_I_STRIDE;
+                if (!(pi[4] & PYXRD_FLAG_RAW_PATTERN)) {
+                    rc.max_ntop_cap = std::max(rc.max_ntop_cap, pmax[pb] + 1);
+                    ncap = std::max(ncap, pmax[pb] + 2);
+                }
+            }
+            rc.per_cand = rc.jobs.size();
+            rc.uniform = true;
+            rc.jobs.clear();
+        }
+    }
+    const int NCLS = (int)ctx->classes.size();
+
+    BatchSizes z;
+    z.K = K; z.M = M; z.NP = NP * K; z.NC = NC * K; z.NA = NA * K; z.NPC = NPC * K; z.NM = NM * K;
+    z.NJ = (long long)JPC * K; z.njobids = jobids.size() * (size_t)K; z.model_driven = model_driven;
+    if (z.NJ > 0x7fffffffLL) return fail(ctx, "set_batch: too many patterns (%lld)", z.NJ);
+    const BlobLayout L = plan_blob(z, S);
+    CK(ctx->d_blob.ensure(L.total));
+
+    // ---- template + solution vectors + table: one pinned staging blob, one H2D copy ------------------
+    struct Part { const void *src; size_t bytes, off; };
+    std::vector<Part> parts;
+    size_t total = 0;
+    auto add = [&](const void *src, size_t bytes) {
+        parts.push_back(Part{src, src ? bytes : 0, total});
+        total = align_up(total + std::max<size_t>(bytes, 8), 256);
+        return (int)parts.size() - 1;
+    };
+    const int a_phase_i = add(t->phase_i, sizeof(int32_t) * (size_t)NP * PYXRD_PHASE_I_STRIDE);
+    const int a_phase_d = add(t->phase_d, sizeof(double) * (size_t)NP * PYXRD_PHASE_D_STRIDE);
+    const int a_phase_comp = add(t->phase_comp, sizeof(int32_t) * (size_t)NPC);
+    const int a_matrices = add(t->matrices, sizeof(double) * (size_t)NM);
+    const int a_comp_d = add(t->comp_d, sizeof(double) * (size_t)NC * PYXRD_COMP_D_STRIDE);
+    const int a_comp_i = add(t->comp_i, sizeof(int32_t) * (size_t)NC * PYXRD_COMP_I_STRIDE);
+    const int a_atom_d = add(t->atom_d, sizeof(double) * (size_t)NA * PYXRD_ATOM_D_STRIDE);
+    const int a_atom_t = add(t->atom_type, sizeof(int32_t) * (size_t)NA);
+    const int a_job_pb = add(job_pb.data(), sizeof(int) * JPC);
+    const int a_job_spec = add(job_spec.data(), sizeof(int) * JPC);
+    const int a_job_out = add(job_out.data(), sizeof(long long) * JPC);
+    const int a_jobids = add(jobids.data(), sizeof(int) * jobids.size());
+    const int a_frac = add(t->fractions, sizeof(double) * (size_t)M);
+    const int a_scales = add(t->scales, sizeof(double) * (size_t)S);
+    const int a_bg = add(t->bgshifts, sizeof(double) * (size_t)S);
+    const int a_pmodel = add(model_driven ? t->prob_model : nullptr, sizeof(int32_t) * (size_t)NP);
+    const int a_pparam = add(model_driven ? t->prob_params : nullptr, sizeof(double) * (size_t)NP * PYXRD_PROB_STRIDE);
+    const int a_cls_first = add(cls_first.data(), sizeof(int) * (size_t)NCLS);
+    const int a_cls_n = add(cls_n.data(), sizeof(int) * (size_t)NCLS);
+    const int a_x = add(pop->x, sizeof(double) * (size_t)K * D);
+    const int a_bind = add(pop->bindings, sizeof(pyxrd_binding) * (size_t)NB);
+    const int a_auto = add(pop->csds_auto_maximum, sizeof(uint8_t) * (size_t)NP);
+    CK(cudaStreamSynchronize(ctx->stream));        // the staging blob may still feed a previous copy
+    CK(ctx->h_tmpl.ensure(total));
+    CK(ctx->d_tmpl.ensure(total));
+    for (const Part &p : parts)
+        if (p.bytes) memcpy(static_cast<char *>(ctx->h_tmpl.ptr) + p.off, p.src, p.bytes);
+    CK(cudaMemcpyAsync(ctx->d_tmpl.ptr, ctx->h_tmpl.ptr, total, cudaMemcpyHostToDevice, ctx->stream));
+
+    ExpandDev e{};
+    e.K = K; e.D = D; e.NB = NB; e.NP = NP; e.NC = NC; e.NA = NA; e.NPC = NPC; e.M = M; e.S = S; e.JPC = (int)JPC; e.NCLS = NCLS;
+    e.NM = NM; e.cand_stride = (long long)M * Z * st.sumX;
+    auto tp = [&](int idx) { return static_cast<char *>(ctx->d_tmpl.ptr) + parts[idx].off; };
+    auto dp = [&](int idx) { return static_cast<char *>(ctx->d_blob.ptr) + L.off[idx]; };
+    e.t_phase_i = (const int *)tp(a_phase_i); e.t_phase_d = (const double *)tp(a_phase_d); e.t_phase_comp = (const int *)tp(a_phase_comp);
+    e.t_matrices = (const double *)tp(a_matrices); e.t_comp_d = (const double *)tp(a_comp_d); e.t_comp_i = (const int *)tp(a_comp_i);
+    e.t_atom_d = (const double *)tp(a_atom_d); e.t_atom_t = (const int *)tp(a_atom_t); e.t_job_pb = (const int *)tp(a_job_pb);
+    e.t_job_spec = (const int *)tp(a_job_spec); e.t_job_out = (const long long *)tp(a_job_out); e.t_jobids = (const int *)tp(a_jobids);
+    e.t_frac = (const double *)tp(a_frac); e.t_scales = (const double *)tp(a_scales); e.t_bg = (const double *)tp(a_bg);
+    e.t_pmodel = (const int *)tp(a_pmodel); e.t_pparam = (const double *)tp(a_pparam);
+    e.cls_first = (const int *)tp(a_cls_first); e.cls_n = (const int *)tp(a_cls_n);
+    e.x = (const double *)tp(a_x); e.bind = (const pyxrd_binding *)tp(a_bind);
+    e.auto_max = pop->csds_auto_maximum ? (const unsigned char *)tp(a_auto) : nullptr;
+    e.factor = pop->csds_factor;
+    e.phase_i = (int *)dp(P_PHASE_I); e.phase_d = (double *)dp(P_PHASE_D); e.phase_comp = (int *)dp(P_PHASE_COMP);
+    e.matrices = (double *)dp(P_MATRICES); e.comp_d = (double *)dp(P_COMP_D); e.comp_i = (int *)dp(P_COMP_I);
+    e.atom_d = (double *)dp(P_ATOM_D); e.atom_t = (int *)dp(P_ATOM_T); e.job_pb = (int *)dp(P_JOB_PB); e.job_spec = (int *)dp(P_JOB_SPEC);
+    e.job_out = (long long *)dp(P_JOB_OUT); e.jobids = (int *)dp(P_JOBIDS); e.frac = (double *)dp(P_FRAC); e.scales = (double *)dp(P_SCALES);
+    e.bg = (double *)dp(P_BG); e.pmodel = model_driven ? (int *)dp(P_PMODEL) : nullptr; e.pparam = model_driven ? (double *)dp(P_PPARAM) : nullptr;
+    k_expand_population<<<K, 128, 0, ctx->stream>>>(e);
+    LAUNCH_CHECK("k_expand_population");
+    return bind_batch(ctx, z, L, ncap);
 }
 
 int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop, double *residuals_out) {

@@ -180,3 +180,42 @@ def test_binding_to_fixed_matrices_and_mixture_values(ctx):
         ref = copy.deepcopy(tmpl.mixture)
         orc.calculate_mixture(ref)
         assert rel_err(res[k], ref.residuals) < RTOL
+
+
+@pytest.mark.parametrize("name,K", [("c4", 7), ("models", 9), ("c5", 4)])
+def test_device_expansion_equals_host_expansion(ctx, name, K):
+    """pyxrd_set_population expands on the device (k_expand_population); pyxrd_expand_population is the same
+    expansion on the host (checked against packing on the CPU): identical batches, identical bits out"""
+    import types
+    tmpl, refs = _template(name)
+    x = syn.sample_solutions(refs, 21, K)
+    with ctx.lock:
+        ctx.set_static(tmpl.static)
+        ctx.set_population(tmpl.batch, x, tmpl.bindings, tmpl.csds_auto, tmpl.csds_factor)
+        ctx.compute_intensities()
+        ctx.compute_residuals()
+        dev_int, dev_res = ctx.read_intensities_flat(), ctx.read_residuals()
+        host = types.SimpleNamespace(**tmpl.expand(x))
+        host.S, host.Z = tmpl.batch.S, tmpl.batch.Z
+        ctx.set_batch(host)
+        ctx.compute_intensities()
+        ctx.compute_residuals()
+        assert np.array_equal(dev_int, ctx.read_intensities_flat())
+        assert np.array_equal(dev_res, ctx.read_residuals())
+
+
+def test_population_errors(ctx):
+    from pyxrd_b200.runtime import DeviceError
+    tmpl, refs = _template("c2")
+    x = syn.sample_solutions(refs, 3, 4)
+    bad = tmpl.bindings.copy()
+    bad["index"][0] = 10 ** 6
+    with ctx.lock:
+        ctx.set_static(tmpl.static)
+        with pytest.raises(DeviceError, match="out of range"):
+            ctx.evaluate_population(tmpl.batch, x, bad, tmpl.csds_auto, tmpl.csds_factor)
+        xs = x.copy()
+        xs[2, [r.name for r in refs].index("IS.csds_average")] = 0.1      # maximum = int(0.25) = 0 < minimum = 1
+        with pytest.raises(DeviceError, match="CSDS range"):
+            ctx.evaluate_population(tmpl.batch, xs, tmpl.bindings, tmpl.csds_auto, tmpl.csds_factor)
+        assert np.isfinite(ctx.evaluate_population(tmpl.batch, x, tmpl.bindings, tmpl.csds_auto, tmpl.csds_factor)).all()
