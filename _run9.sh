@@ -1,8 +1,9 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-python bench.py > gpurun_out/bench6.json 2> gpurun_out/bench6.err; tail -c 300 gpurun_out/bench6.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python tools/opt_sweep.py c4 256 2>&1 | grep "outer  32\|outer  48\|outer  24 newton 2"
+python bench.py > gpurun_out/bench7.json 2> gpurun_out/bench7.err; tail -c 300 gpurun_out/bench7.err
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench6.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/bench7.json').read().strip().splitlines()[-1])
 print('pts/s %.3e'%d['value'], 'ms %.3f'%d['ms_per_step'], 'roof %.3f'%d['roofline']['frac'], d['stage_ms'], 'e2e %.3e'%d['e2e']['value'], 'pack_s', d['host_pack_s'])
 print('population', d.get('population'))
 t=d['trials']; print('trials/s %.1f e2e %.1f'%(t['value'], t['e2e']['value']), t['stage_ms'], t.get('population'))

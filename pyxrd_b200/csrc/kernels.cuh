@@ -1891,6 +1891,10 @@ struct OptSmem {
     double H[PX_OPT_MAXD * PX_OPT_LDA];
     double A[PX_OPT_MAXD * PX_OPT_LDA];
     double g[PX_OPT_MAXD], vn[PX_OPT_MAXD], invd[PX_OPT_MAXD];
+    double lam;                     // Levenberg-Marquardt damping, carried from one majoriser to the next
+#ifdef PX_OPT_PROFILE
+    long long prof[8];              // cycles: gram, reduce, newton, assembly, chol, solve+q; counts: tries, lm iterations
+#endif
     int idx[PX_OPT_MAXD];
     double red[PX_OPT_TPB / 32][PX_OPT_MAXMB * (PX_OPT_MAXMB + 1) / 2 + PX_OPT_MAXMB + 1];
 };
@@ -1916,9 +1920,16 @@ __device__ __forceinline__ void opt_forms(const OptSmem &sm, const double *v, in
         b = B[lane * MB + M] * v[lane];
         d = c[lane] * v[lane];
     }
-    fBf = opt_warp_sum(a);
-    Bcf = opt_warp_sum(b);
-    cf = opt_warp_sum(d);
+    // the three butterflies interleaved: 5 dependent steps instead of 15
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double a2 = __shfl_xor_sync(0xffffffffu, a, o), b2 = __shfl_xor_sync(0xffffffffu, b, o),
+                     d2 = __shfl_xor_sync(0xffffffffu, d, o);
+        a += a2; b += b2; d += d2;
+    }
+    fBf = a;
+    Bcf = b;
+    cf = d;
 }
 
 // majoriser value (up to a constant) at v
@@ -1944,7 +1955,7 @@ __device__ bool opt_chol(double *A, double *invd, int n, int lane) {
         }
         const double dj = __shfl_sync(0xffffffffu, a, j);
         if (!(dj > 0.0)) return false;
-        const double sd = sqrt(dj), inv = 1.0 / sd;
+        const double inv = rsqrt(dj), sd = dj * inv;       // one reciprocal square root instead of sqrt + division
         if (lane == j) { A[j * PX_OPT_LDA + j] = sd; invd[j] = inv; }
         else if (lane > j && lane < n) A[lane * PX_OPT_LDA + j] = a * inv;
         __syncwarp();
@@ -1970,17 +1981,21 @@ __device__ double opt_chol_solve(const double *A, const double *invd, int n, int
 // projected Levenberg-Marquardt / Newton on the majoriser (warp 0)
 __device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, int lm_iters, int refine_bg, int lane) {
     const int d = M + 2 * S;
-    double lam = 1e-3;
+    double lam = sm.lam;
     double *v = sm.v, *g = sm.g, *H = sm.H;
     for (int it = 0; it < lm_iters; ++it) {
+#ifdef PX_OPT_PROFILE
+        long long tA = clock64();
+#endif
         for (int i = lane; i < d * PX_OPT_LDA; i += 32) H[i] = 0.0;
         __syncwarp();
-        double gp = 0.0;
+        double gp = 0.0, qv = 0.0;                      // qv: majoriser value at v, a by-product of the forms below
         for (int s = 0; s < S; ++s) {
             const double *B = sm.B[s], *c = sm.c[s];
             const double w = sm.wgt[s], r = v[M + s], b = v[M + S + s];
             double t, fBf, Bcf, cf;
             opt_forms(sm, v, s, M, MB, lane, t, fBf, Bcf, cf);
+            qv += w * (r * r * fBf + 2.0 * r * b * Bcf + B[M * MB + M] * b * b - 2.0 * r * cf - 2.0 * c[M] * b);
             const int ir = M + s, ib = M + S + s;
             if (lane < M) {
                 const int p = lane;
@@ -2015,7 +2030,9 @@ __device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, 
         if (free_i) sm.idx[__popc(mask & ((1u << lane) - 1u))] = lane;
         __syncwarp();
         if (n == 0) break;
-        const double qv = opt_q(sm, v, M, S, MB, lane);
+#ifdef PX_OPT_PROFILE
+        if (lane == 0) { sm.prof[3] += clock64() - tA; sm.prof[7] += 1; }
+#endif
         bool accepted = false;
         double rel = 0.0;
         for (int tr = 0; tr < 8 && !accepted; ++tr) {
@@ -2025,7 +2042,15 @@ __device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, 
                 sm.A[lane * PX_OPT_LDA + lane] += lam * fabs(sm.A[lane * PX_OPT_LDA + lane]) + 1e-300;
             }
             __syncwarp();
+#ifdef PX_OPT_PROFILE
+            long long tC = clock64();
+            if (lane == 0) sm.prof[6] += 1;
+#endif
             if (!opt_chol(sm.A, sm.invd, n, lane)) { lam *= 10.0; __syncwarp(); continue; }
+#ifdef PX_OPT_PROFILE
+            if (lane == 0) sm.prof[4] += clock64() - tC;
+            tC = clock64();
+#endif
             const double dx = opt_chol_solve(sm.A, sm.invd, n, lane, lane < n ? -g[sm.idx[lane]] : 0.0);
             if (lane < d) sm.vn[lane] = v[lane];
             __syncwarp();
@@ -2041,9 +2066,190 @@ __device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, 
                 lam *= 5.0;
             }
             __syncwarp();
+#ifdef PX_OPT_PROFILE
+            if (lane == 0) sm.prof[5] += clock64() - tC;
+#endif
         }
         if (!accepted || rel < 1e-13) break;
     }
+    if (lane == 0) sm.lam = fmin(lam, 1e-3);            // never start a majoriser more damped than the first one
+}
+
+// The same projected Levenberg-Marquardt step with everything in registers (M, S compile-time, D = M + 2 S <= 12):
+// lane i owns variable i, its gradient entry and row i of the (symmetric) matrices.  Variables that are not free
+// (fixed background, held at a bound by the gradient) get an identity row / column and a zero gradient instead of
+// being compacted away, so every index is static.  Right-looking Cholesky: column j is scaled by rsqrt(d_jj)
+// and broadcast entry by entry (independent shuffles, no dependent LDS chain); lane j keeps the broadcast column
+// as row j of L^T for the backward substitution.
+template <int M, int S>
+__device__ __forceinline__ double opt_q_reg(const OptSmem &sm, double vi, int lane) {
+    constexpr int MB = M + 1;
+    double q = 0.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const double *B = sm.B[s], *c = sm.c[s];
+        const double r = __shfl_sync(0xffffffffu, vi, M + s), b = __shfl_sync(0xffffffffu, vi, M + S + s);
+        double t = 0.0;
+#pragma unroll
+        for (int q2 = 0; q2 < M; ++q2) {
+            const double fq = __shfl_sync(0xffffffffu, vi, q2);
+            if (lane < M) t = fma(B[lane * MB + q2], fq, t);
+        }
+        double a = 0.0, bb = 0.0, dd = 0.0;
+        if (lane < M) { a = vi * t; bb = B[lane * MB + M] * vi; dd = c[lane] * vi; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double a2 = __shfl_xor_sync(0xffffffffu, a, o), b2 = __shfl_xor_sync(0xffffffffu, bb, o),
+                         d2 = __shfl_xor_sync(0xffffffffu, dd, o);
+            a += a2; bb += b2; dd += d2;
+        }
+        q += sm.wgt[s] * (r * r * a + 2.0 * r * b * bb + B[M * MB + M] * b * b - 2.0 * r * dd - 2.0 * c[M] * b);
+    }
+    return q;
+}
+
+template <int M, int S>
+__device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int refine_bg, int lane) {
+    constexpr int MB = M + 1, D = M + 2 * S;
+    double lam = sm.lam;
+    double vi = lane < D ? sm.v[lane] : 0.0;
+    const double lo_i = lane < D ? sm.lo[lane] : 0.0;
+    const bool fixed_bg = (!refine_bg && lane >= M + S);
+    for (int it = 0; it < lm_iters; ++it) {
+#ifdef PX_OPT_PROFILE
+        long long tA = clock64();
+#endif
+        double h[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) h[j] = 0.0;
+        double gi = 0.0, qv = 0.0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const double *B = sm.B[s], *c = sm.c[s];
+            const double w = sm.wgt[s];
+            const double r = __shfl_sync(0xffffffffu, vi, M + s), b = __shfl_sync(0xffffffffu, vi, M + S + s);
+            double brow[M], t = 0.0, bm = 0.0, cl = 0.0;
+#pragma unroll
+            for (int q = 0; q < M; ++q) {
+                const double fq = __shfl_sync(0xffffffffu, vi, q);
+                brow[q] = lane < M ? B[lane * MB + q] : 0.0;
+                t = fma(brow[q], fq, t);
+            }
+            if (lane < M) { bm = B[lane * MB + M]; cl = c[lane]; }
+            double a = lane < M ? vi * t : 0.0, bb = lane < M ? bm * vi : 0.0, dd = lane < M ? cl * vi : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double a2 = __shfl_xor_sync(0xffffffffu, a, o), b2 = __shfl_xor_sync(0xffffffffu, bb, o),
+                             d2 = __shfl_xor_sync(0xffffffffu, dd, o);
+                a += a2; bb += b2; dd += d2;
+            }
+            const double fBf = a, Bcf = bb, cf = dd, BMM = B[M * MB + M], cM = c[M];
+            qv += w * (r * r * fBf + 2.0 * r * b * Bcf + BMM * b * b - 2.0 * r * cf - 2.0 * cM * b);
+            const double hfr = w * (4.0 * r * t + 2.0 * b * bm - 2.0 * cl), hfb = 2.0 * w * r * bm;
+            if (lane < M) {
+                gi += w * (2.0 * r * r * t + 2.0 * r * b * bm - 2.0 * r * cl);
+#pragma unroll
+                for (int q = 0; q < M; ++q) h[q] += 2.0 * w * r * r * brow[q];
+                h[M + s] = hfr;
+                h[M + S + s] = hfb;
+            }
+#pragma unroll
+            for (int q = 0; q < M; ++q) {                  // rows of the scale / background variables of this specimen
+                const double x1 = __shfl_sync(0xffffffffu, hfr, q), x2 = __shfl_sync(0xffffffffu, hfb, q);
+                if (lane == M + s) h[q] = x1;
+                if (lane == M + S + s) h[q] = x2;
+            }
+            if (lane == M + s) { gi = w * (2.0 * r * fBf + 2.0 * b * Bcf - 2.0 * cf); h[M + s] = 2.0 * w * fBf; h[M + S + s] = 2.0 * w * Bcf; }
+            if (lane == M + S + s) { gi = w * (2.0 * r * Bcf + 2.0 * BMM * b - 2.0 * cM); h[M + s] = 2.0 * w * Bcf; h[M + S + s] = 2.0 * w * BMM; }
+        }
+        double hd = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) hd = (lane == j) ? h[j] : hd;
+        const bool at_bound = (vi <= lo_i && gi > 0.0);
+        const bool free_i = lane < D && !fixed_bg && !at_bound && hd > 0.0;
+        const unsigned mask = __ballot_sync(0xffffffffu, free_i);
+        if (mask == 0u) break;
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            if (!free_i || !((mask >> j) & 1u)) h[j] = (lane == j) ? 1.0 : 0.0;
+        const double gfree = free_i ? gi : 0.0;
+#ifdef PX_OPT_PROFILE
+        if (lane == 0) { sm.prof[3] += clock64() - tA; sm.prof[7] += 1; }
+#endif
+        bool accepted = false;
+        double rel = 0.0;
+        for (int tr = 0; tr < 8 && !accepted; ++tr) {
+#ifdef PX_OPT_PROFILE
+            long long tC = clock64();
+            if (lane == 0) sm.prof[6] += 1;
+#endif
+            double a[D], ut[D], invd[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) { a[j] = (lane == j) ? h[j] + (lam * fabs(h[j]) + 1e-300) : h[j]; ut[j] = 0.0; }
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const double djj = __shfl_sync(0xffffffffu, a[j], j);
+                if (!(djj > 0.0)) ok = false;                 // warp-uniform
+                const double inv = rsqrt(ok ? djj : 1.0);
+                invd[j] = inv;
+                const double lij = lane > j ? a[j] * inv : 0.0;
+                a[j] = lij;
+#pragma unroll
+                for (int k = j + 1; k < D; ++k) {
+                    const double lkj = __shfl_sync(0xffffffffu, lij, k);
+                    a[k] = fma(-lij, lkj, a[k]);
+                    if (lane == j) ut[k] = lkj;
+                }
+            }
+            if (!ok) { lam *= 10.0; continue; }
+#ifdef PX_OPT_PROFILE
+            if (lane == 0) sm.prof[4] += clock64() - tC;
+            tC = clock64();
+#endif
+            // L z = -g, L^T x = z; the diagonal of L is 1 / invd
+            double y = -gfree;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const double zj = __shfl_sync(0xffffffffu, y, j) * invd[j];
+                if (lane == j) y = zj;
+                else if (lane > j) y = fma(-a[j], zj, y);
+            }
+#pragma unroll
+            for (int j = D - 1; j >= 0; --j) {
+                const double xj = __shfl_sync(0xffffffffu, y, j) * invd[j];
+                if (lane == j) y = xj;
+                else if (lane < j) y = fma(-ut[j], xj, y);
+            }
+            const double vn = free_i ? fmax(lo_i, vi + y) : vi;
+            const double qn = opt_q_reg<M, S>(sm, vn, lane);
+            if (qn < qv) {
+                accepted = true;
+                rel = (qv - qn) / fmax(fabs(qv), 1e-300);
+                vi = vn;
+                if (tr == 0) lam = fmax(lam * 0.2, 1e-12);    // a step that needed more damping keeps it
+            } else {
+                lam *= 5.0;
+            }
+#ifdef PX_OPT_PROFILE
+            if (lane == 0) sm.prof[5] += clock64() - tC;
+#endif
+        }
+        if (!accepted || rel < 1e-13) break;
+    }
+    if (lane < D) sm.v[lane] = vi;
+    if (lane == 0) sm.lam = fmin(lam, 1e-3);
+    __syncwarp();
+}
+
+// register version where the problem is small enough (S <= 3 and D = M + 2 S <= 12), shared-memory version
+// otherwise.  Each kernel instantiation (M fixed) compiles at most three solvers.
+template <int M>
+__device__ __forceinline__ void opt_solve_dispatch(OptSmem &sm, int S, int lm_iters, int refine_bg, int lane) {
+    if constexpr (M + 2 <= 12) { if (S == 1) { opt_inner_solve_reg<M, 1>(sm, lm_iters, refine_bg, lane); return; } }
+    if constexpr (M + 4 <= 12) { if (S == 2) { opt_inner_solve_reg<M, 2>(sm, lm_iters, refine_bg, lane); return; } }
+    if constexpr (M + 6 <= 12) { if (S == 3) { opt_inner_solve_reg<M, 3>(sm, lm_iters, refine_bg, lane); return; } }
+    opt_inner_solve(sm, M, S, M + 1, lm_iters, refine_bg, lane);
 }
 
 template <int MB>
@@ -2056,6 +2262,10 @@ __global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st
     const int k = blockIdx.x, S = st.S, Z = st.Z, tid = threadIdx.x;
     const int d = M + 2 * S;
     if (tid == 0) {
+#ifdef PX_OPT_PROFILE
+        for (int i = 0; i < 8; ++i) sm.prof[i] = 0;
+#endif
+        sm.lam = 1e-3;
         for (int p = 0; p < M; ++p) { sm.v[p] = 1.0 / M; sm.lo[p] = 0.0; }             // mixture.py:60-68 start
         for (int s = 0; s < S; ++s) {
             sm.v[M + s] = 1.0; sm.lo[M + s] = 1e-12;
@@ -2083,6 +2293,9 @@ __global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st
 #pragma unroll
             for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
             const double delta = delta_rel * sm.mean_obs[s];
+#ifdef PX_OPT_PROFILE
+            long long tG = clock64();
+#endif
             // two points in flight per thread: the loads of both are issued before the arithmetic
             for (int z = 0; z < Z; ++z)
                 for (int x0 = tid; x0 < X; x0 += 2 * PX_OPT_TPB) {
@@ -2119,6 +2332,10 @@ __global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st
                 }
             // block reduction of NACC (+ count) values
             const int lane = tid & 31, warp = tid >> 5;
+#ifdef PX_OPT_PROFILE
+            if (tid == 0) sm.prof[0] += clock64() - tG;
+            tG = clock64();
+#endif
 #pragma unroll
             for (int a = 0; a < NACC; ++a) {
                 double vsum = acc[a];
@@ -2143,11 +2360,25 @@ __global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st
                 }
             }
             __syncthreads();
+#ifdef PX_OPT_PROFILE
+            if (tid == 0) sm.prof[1] += clock64() - tG;
+#endif
         }
         if (it == op.outer) break;                 // the last pass only evaluates the objective
-        if (tid < 32) opt_inner_solve(sm, M, S, MB, op.lm_iters, op.refine_bg, tid);
+#ifdef PX_OPT_PROFILE
+        long long tN = clock64();
+#endif
+        if (tid < 32) opt_solve_dispatch<M>(sm, S, op.lm_iters, op.refine_bg, tid);
         __syncthreads();
+#ifdef PX_OPT_PROFILE
+        if (tid == 0) sm.prof[2] += clock64() - tN;
+#endif
     }
+#ifdef PX_OPT_PROFILE
+    if (tid == 0 && (k == 0 || k == 100))
+        printf("opt profile k=%d: gram %lld reduce %lld newton %lld (assembly %lld chol %lld solve+q %lld) tries %lld lm %lld\n", k,
+               sm.prof[0], sm.prof[1], sm.prof[2], sm.prof[3], sm.prof[4], sm.prof[5], sm.prof[6], sm.prof[7]);
+#endif
     if (tid == 0) {
         // reference units: fractions = f / sum f, scales = rho * sum f (mixture.py:196-205)
         double fsum = 0.0;

@@ -2,6 +2,7 @@
 // Owns device memory for tables / parameters / results, builds the job lists and
 // launches the kernels of kernels.cuh on one CUDA stream.  No CPU compute path.
 #include "../../include/pyxrd_b200.h"
+#include <cstdio>
 #include "kernels.cuh"
 
 #include <algorithm>
