@@ -1878,6 +1878,9 @@ struct OptParams {
     double delta0, shrink, delta_min;   // weight floor relative to mean |obs|: delta0 * shrink^it >= delta_min
 };
 
+#ifndef PX_OPT_NDAMP
+#define PX_OPT_NDAMP 4     // warps (= dampings tried side by side) of the register Levenberg-Marquardt solver
+#endif
 #define PX_OPT_LDA 29      // row stride (doubles) of the d x d work matrices: odd, so a column is spread over all banks
 
 struct OptSmem {
@@ -1892,6 +1895,8 @@ struct OptSmem {
     double A[PX_OPT_MAXD * PX_OPT_LDA];
     double g[PX_OPT_MAXD], vn[PX_OPT_MAXD], invd[PX_OPT_MAXD];
     double lam;                     // Levenberg-Marquardt damping, carried from one majoriser to the next
+    double cand_q[PX_OPT_NDAMP];                    // majoriser value each warp's damping reaches (register solver)
+    double cand_v[PX_OPT_NDAMP][PX_OPT_MAXD];       // and its trial point
 #ifdef PX_OPT_PROFILE
     long long prof[8];              // cycles: gram, reduce, newton, assembly, chol, solve+q; counts: tries, lm iterations
 #endif
@@ -1904,6 +1909,10 @@ __device__ __forceinline__ double opt_warp_sum(double x) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
 }
+
+#ifdef PX_OPT_PROFILE
+__device__ __forceinline__ unsigned __smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#endif
 
 // The small bilinear problem is solved by warp 0 as a team: lane p owns fraction p / row p of the
 // work matrices.  Every function below is called by all 32 lanes and returns warp-uniform values.
@@ -2081,6 +2090,9 @@ __device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, 
 // being compacted away, so every index is static.  Right-looking Cholesky: column j is scaled by rsqrt(d_jj)
 // and broadcast entry by entry (independent shuffles, no dependent LDS chain); lane j keeps the broadcast column
 // as row j of L^T for the backward substitution.
+// barrier of the PX_OPT_NDAMP solver warps (named barrier 1; the rest of the block waits at barrier 0)
+__device__ __forceinline__ void opt_team_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PX_OPT_NDAMP * 32) : "memory"); }
+
 template <int M, int S>
 __device__ __forceinline__ double opt_q_reg(const OptSmem &sm, double vi, int lane) {
     constexpr int MB = M + 1;
@@ -2109,8 +2121,8 @@ __device__ __forceinline__ double opt_q_reg(const OptSmem &sm, double vi, int la
 }
 
 template <int M, int S>
-__device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int refine_bg, int lane) {
-    constexpr int MB = M + 1, D = M + 2 * S;
+__device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int refine_bg, int lane, int warp) {
+    constexpr int MB = M + 1, D = M + 2 * S, NW = PX_OPT_NDAMP;
     double lam = sm.lam;
     double vi = lane < D ? sm.v[lane] : 0.0;
     const double lo_i = lane < D ? sm.lo[lane] : 0.0;
@@ -2174,18 +2186,24 @@ __device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int 
             if (!free_i || !((mask >> j) & 1u)) h[j] = (lane == j) ? 1.0 : 0.0;
         const double gfree = free_i ? gi : 0.0;
 #ifdef PX_OPT_PROFILE
-        if (lane == 0) { sm.prof[3] += clock64() - tA; sm.prof[7] += 1; }
+        if (lane == 0 && warp == 0) { sm.prof[3] += clock64() - tA; sm.prof[7] += 1; }
 #endif
+        // the first PX_OPT_NDAMP warps of the block each take the step with their own damping lam * 5^(warp - 1) -- the
+        // retries of a serial Levenberg-Marquardt loop side by side on warps that would otherwise wait; the best point
+        // wins.  (More warps than this make every warp slower: the solver lives on shuffles.)
         bool accepted = false;
         double rel = 0.0;
-        for (int tr = 0; tr < 8 && !accepted; ++tr) {
+#pragma unroll 1
+        for (int round = 0; round < 4 && !accepted; ++round) {      // a round nobody wins moves the whole ladder up
 #ifdef PX_OPT_PROFILE
             long long tC = clock64();
-            if (lane == 0) sm.prof[6] += 1;
+            if (lane == 0 && warp == 0) sm.prof[6] += 1;
 #endif
+            double lam_w = lam * 0.2;
+            for (int i = 0; i < warp; ++i) lam_w *= 5.0;
             double a[D], ut[D], invd[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) { a[j] = (lane == j) ? h[j] + (lam * fabs(h[j]) + 1e-300) : h[j]; ut[j] = 0.0; }
+            for (int j = 0; j < D; ++j) { a[j] = (lane == j) ? h[j] + (lam_w * fabs(h[j]) + 1e-300) : h[j]; ut[j] = 0.0; }
             bool ok = true;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
@@ -2202,9 +2220,8 @@ __device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int 
                     if (lane == j) ut[k] = lkj;
                 }
             }
-            if (!ok) { lam *= 10.0; continue; }
 #ifdef PX_OPT_PROFILE
-            if (lane == 0) sm.prof[4] += clock64() - tC;
+            if (lane == 0 && warp == 0) sm.prof[4] += clock64() - tC;
             tC = clock64();
 #endif
             // L z = -g, L^T x = z; the diagonal of L is 1 / invd
@@ -2221,35 +2238,52 @@ __device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int 
                 if (lane == j) y = xj;
                 else if (lane < j) y = fma(-ut[j], xj, y);
             }
-            const double vn = free_i ? fmax(lo_i, vi + y) : vi;
-            const double qn = opt_q_reg<M, S>(sm, vn, lane);
-            if (qn < qv) {
-                accepted = true;
-                rel = (qv - qn) / fmax(fabs(qv), 1e-300);
-                vi = vn;
-                if (tr == 0) lam = fmax(lam * 0.2, 1e-12);    // a step that needed more damping keeps it
-            } else {
-                lam *= 5.0;
+            const double vn = (free_i && ok) ? fmax(lo_i, vi + y) : vi;
+            const double qn = ok ? opt_q_reg<M, S>(sm, vn, lane) : qv;
+            if (lane == 0) sm.cand_q[warp] = (ok && qn < qv) ? qn : qv;
+            if (lane < D) sm.cand_v[warp][lane] = vn;
+            opt_team_sync();
+            int best = -1;
+            double qbest = qv;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) {
+                const double qw = sm.cand_q[w2];
+                if (qw < qbest) { qbest = qw; best = w2; }
             }
+            if (best >= 0) {
+                accepted = true;
+                rel = (qv - qbest) / fmax(fabs(qv), 1e-300);
+                if (lane < D) vi = sm.cand_v[best][lane];
+                double lam_b = lam * 0.2;
+                for (int i = 0; i < best; ++i) lam_b *= 5.0;
+                lam = fmax(lam_b, 1e-12);
+            } else {
+                for (int i = 0; i < NW; ++i) lam *= 5.0;      // beyond every damping tried
+            }
+            opt_team_sync();                                  // cand_* are rewritten by the next step
 #ifdef PX_OPT_PROFILE
-            if (lane == 0) sm.prof[5] += clock64() - tC;
+            if (lane == 0 && warp == 0) sm.prof[5] += clock64() - tC;
 #endif
         }
         if (!accepted || rel < 1e-13) break;
     }
-    if (lane < D) sm.v[lane] = vi;
-    if (lane == 0) sm.lam = fmin(lam, 1e-3);
-    __syncwarp();
+    if (warp == 0) {
+        if (lane < D) sm.v[lane] = vi;
+        if (lane == 0) sm.lam = fmin(lam, 1e-3);
+    }
 }
 
-// register version where the problem is small enough (S <= 3 and D = M + 2 S <= 12), shared-memory version
-// otherwise.  Each kernel instantiation (M fixed) compiles at most three solvers.
+// register version (PX_OPT_NDAMP warps of the block, one damping each) where the problem is small enough (S <= 3 and
+// D = M + 2 S <= 12), shared-memory version (warp 0) otherwise.  Each kernel instantiation (M fixed) compiles at most
+// three register solvers.  Called by every thread of the block.
 template <int M>
-__device__ __forceinline__ void opt_solve_dispatch(OptSmem &sm, int S, int lm_iters, int refine_bg, int lane) {
-    if constexpr (M + 2 <= 12) { if (S == 1) { opt_inner_solve_reg<M, 1>(sm, lm_iters, refine_bg, lane); return; } }
-    if constexpr (M + 4 <= 12) { if (S == 2) { opt_inner_solve_reg<M, 2>(sm, lm_iters, refine_bg, lane); return; } }
-    if constexpr (M + 6 <= 12) { if (S == 3) { opt_inner_solve_reg<M, 3>(sm, lm_iters, refine_bg, lane); return; } }
-    opt_inner_solve(sm, M, S, M + 1, lm_iters, refine_bg, lane);
+__device__ __forceinline__ void opt_solve_dispatch(OptSmem &sm, int S, int lm_iters, int refine_bg, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool team = warp < PX_OPT_NDAMP;
+    if constexpr (M + 2 <= 12) { if (S == 1) { if (team) opt_inner_solve_reg<M, 1>(sm, lm_iters, refine_bg, lane, warp); return; } }
+    if constexpr (M + 4 <= 12) { if (S == 2) { if (team) opt_inner_solve_reg<M, 2>(sm, lm_iters, refine_bg, lane, warp); return; } }
+    if constexpr (M + 6 <= 12) { if (S == 3) { if (team) opt_inner_solve_reg<M, 3>(sm, lm_iters, refine_bg, lane, warp); return; } }
+    if (warp == 0) opt_inner_solve(sm, M, S, M + 1, lm_iters, refine_bg, lane);
 }
 
 template <int MB>
@@ -2265,6 +2299,11 @@ __global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st
 #ifdef PX_OPT_PROFILE
         for (int i = 0; i < 8; ++i) sm.prof[i] = 0;
 #endif
+    }
+#ifdef PX_OPT_PROFILE
+    const long long t_begin = clock64();
+#endif
+    if (tid == 0) {
         sm.lam = 1e-3;
         for (int p = 0; p < M; ++p) { sm.v[p] = 1.0 / M; sm.lo[p] = 0.0; }             // mixture.py:60-68 start
         for (int s = 0; s < S; ++s) {
@@ -2368,15 +2407,15 @@ __global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st
 #ifdef PX_OPT_PROFILE
         long long tN = clock64();
 #endif
-        if (tid < 32) opt_solve_dispatch<M>(sm, S, op.lm_iters, op.refine_bg, tid);
+        opt_solve_dispatch<M>(sm, S, op.lm_iters, op.refine_bg, tid);
         __syncthreads();
 #ifdef PX_OPT_PROFILE
         if (tid == 0) sm.prof[2] += clock64() - tN;
 #endif
     }
 #ifdef PX_OPT_PROFILE
-    if (tid == 0 && (k == 0 || k == 100))
-        printf("opt profile k=%d: gram %lld reduce %lld newton %lld (assembly %lld chol %lld solve+q %lld) tries %lld lm %lld\n", k,
+    if (tid == 0)
+        printf("opt profile k=%d sm=%d total %lld: gram %lld reduce %lld newton %lld (assembly %lld chol %lld solve+q %lld) tries %lld lm %lld\n", k, (int)__smid(), clock64() - t_begin,
                sm.prof[0], sm.prof[1], sm.prof[2], sm.prof[3], sm.prof[4], sm.prof[5], sm.prof[6], sm.prof[7]);
 #endif
     if (tid == 0) {

@@ -858,6 +858,10 @@ int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newt
     op.delta0 = 1e-2;
     op.shrink = 0.5;
     op.delta_min = 1e-7;
+    // experiment knobs of tools/opt_sweep.py (weight-floor schedule of the majorise-minimise iteration)
+    if (const char *e = getenv("PYXRD_B200_OPT_DELTA0")) op.delta0 = atof(e);
+    if (const char *e = getenv("PYXRD_B200_OPT_SHRINK")) op.shrink = atof(e);
+    if (const char *e = getenv("PYXRD_B200_OPT_DELTA_MIN")) op.delta_min = atof(e);
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     int rc = 1;
     switch (M + 1) {

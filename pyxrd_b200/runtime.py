@@ -87,11 +87,12 @@ def load_library():
     with _lib_lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("PYXRD_B200_LIB", LIB_PATH)      # A/B builds of the same source (tools/)
+        if not os.path.exists(path):
             raise NativeLibraryMissing(
                 "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                "(pyxrd_b200 has no CPU fallback)" % LIB_PATH)
-        lib = C.CDLL(LIB_PATH)
+                "(pyxrd_b200 has no CPU fallback)" % path)
+        lib = C.CDLL(path)
         vp = C.c_void_p
         lib.pyxrd_create.argtypes = [C.c_int, C.POINTER(vp)]
         lib.pyxrd_destroy.argtypes = [vp]
