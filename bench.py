@@ -342,6 +342,8 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pyxrd_b200 has no CPU fallback")
+    from pyxrd_b200.distributed import bind_process_to_device
+    numa_bound = bind_process_to_device(local_rank)          # before any pinned allocation
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -415,6 +417,7 @@ def run_b200(args, rank, world, local_rank):
                              "frac": 16.0 * main["points"] / (phase_ms * 1e-3) * 1e-9 / hbm_peak,
                              "peak_source": "of measured" if peaks else "of fallback"}},
         "stage_ms": main["stage"], "host_pack_s": main["pack_s"], "clocks": clocks,
+        "cpu_affinity": "NVML ideal affinity of the rank's GPU" if numa_bound else "unchanged",
     }
     if main["pop"]:
         p = main["pop"]

@@ -109,6 +109,12 @@ struct BatchDev {
     const int *prob_model;           // [NP] PX_PROB_* (nullptr: every phase carries its W / P in the pool)
     const double *prob_params;       // [NP][PX_PROB_STRIDE] probability parameters of the model
     int *phase_valid;                // [NP]   derived: valid_probs (host flag, or the device model's verdict)
+    // derived by k_phase_planes: planes of a phase that sit at the same z in several components, listed once
+    int acap;                        // row stride of the three tables = most atoms of any phase
+    int *ph_nu;                      // [NP]        number of distinct planes
+    double *ph_uz;                   // [NP][acap]  z of distinct plane u
+    int *ph_uend;                    // [NP][acap]  one past the last segment of distinct plane u
+    int *ph_useg;                    // [NP][acap]  segments ordered by distinct plane: first atom | end atom << 9 | component << 18
     const int *job_pb, *job_spec;    // [NJ]
     const long long *job_out;        // [NJ]
     const double *fractions, *scales, *bgshifts;   // [K][M], [K][S], [K][S]
@@ -709,6 +715,69 @@ __global__ void k_component_z(BatchDev bt) {
     bt.comp_nplanes[ci] = plane + 1;
 }
 
+#define PX_MAX_ATOMS 256     // atoms per phase (all components)
+
+// warp per phase: planes (runs of atoms with equal z inside a component) that occur at the same z in several
+// components of the phase -- the shared silicate layer of a mixed-layer phase -- are listed once, so that the phase
+// kernels evaluate exp(2 pi i z stl) once per DISTINCT plane.  Segment = (component, atom range) of one plane.
+__global__ void __launch_bounds__(32) k_phase_planes(BatchDev bt) {
+    const int pb = blockIdx.x, lane = threadIdx.x;
+    __shared__ double seg_z[PX_MAX_ATOMS];
+    __shared__ int seg_info[PX_MAX_ATOMS], seg_first[PX_MAX_ATOMS], seg_u[PX_MAX_ATOMS];
+    const int *pi = bt.phase_i + pb * 8;
+    int *nu_out = bt.ph_nu + pb;
+    if (!(pi[4] & 1) || (pi[4] & 8)) { if (lane == 0) *nu_out = 0; return; }
+    const int G = pi[0];
+    int first_atom = 0, nseg = 0;
+    for (int c = 0; c < G; ++c) {
+        const int ci = bt.phase_comp[pi[5] + c];
+        const int a0 = bt.comp_i[ci * 4], na = bt.comp_i[ci * 4 + 1] + bt.comp_i[ci * 4 + 2];
+        for (int a = lane; a < na; a += 32) {
+            const int pl = bt.atom_plane[a0 + a];
+            if (a == 0 || bt.atom_plane[a0 + a - 1] != pl) {
+                int e = a + 1;
+                while (e < na && bt.atom_plane[a0 + e] == pl) ++e;
+                seg_z[nseg + pl] = bt.atom_z[a0 + a];
+                seg_info[nseg + pl] = (first_atom + a) | ((first_atom + e) << 9) | (c << 18);
+            }
+        }
+        first_atom += na;
+        nseg += bt.comp_nplanes[ci];
+    }
+    __syncwarp();
+    for (int j = lane; j < nseg; j += 32) {            // first segment at the same z
+        int f = j;
+        const double z = seg_z[j];
+        for (int i = 0; i < j; ++i)
+            if (seg_z[i] == z) { f = i; break; }
+        seg_first[j] = f;
+    }
+    __syncwarp();
+    for (int j = lane; j < nseg; j += 32) {            // index of the distinct plane a segment belongs to
+        const int f = seg_first[j];
+        int u = 0;
+        for (int i = 0; i < f; ++i) u += (seg_first[i] == i);
+        seg_u[j] = u;
+    }
+    __syncwarp();
+    int nu = 0;
+    for (int i = 0; i < nseg; ++i) nu += (seg_first[i] == i);
+    double *uz = bt.ph_uz + (long long)pb * bt.acap;
+    int *uend = bt.ph_uend + (long long)pb * bt.acap, *useg = bt.ph_useg + (long long)pb * bt.acap;
+    for (int j = lane; j < nseg; j += 32) {            // stable ordering of the segments by distinct plane
+        const int u = seg_u[j];
+        int pos = 0, upto = 0;
+        for (int i = 0; i < nseg; ++i) {
+            const int ui = seg_u[i];
+            pos += (ui < u) || (ui == u && i < j);
+            upto += (ui <= u);
+        }
+        useg[pos] = seg_info[j];
+        if (seg_first[j] == j) { uz[u] = seg_z[j]; uend[u] = upto; }
+    }
+    if (lane == 0) *nu_out = nu;
+}
+
 __global__ void k_leaf_csds(const double *pd, int nmin, int nmax, double *arr, double *mean, double *cpow) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int ntop;
@@ -719,7 +788,6 @@ __global__ void k_leaf_csds(const double *pd, int nmin, int nmax, double *arr, d
 // ---------------------------------------------------------------------------------
 // phase kernels: shared-memory staging of one phase parameter block
 // ---------------------------------------------------------------------------------
-#define PX_MAX_ATOMS 256     // atoms per phase (all components)
 
 struct PhaseSmem {          // header living at the start of dynamic shared memory
     int comp_first[8];      // first plane (local index) of component c
@@ -729,7 +797,9 @@ struct PhaseSmem {          // header living at the start of dynamic shared memo
     double plane_arg[PX_MAX_ATOMS];  // (2 pi) * z of a plane = run of consecutive atoms with equal z
     int plane_end[PX_MAX_ATOMS];     // one past the last atom (local index) of the plane
     double2 atom_po[PX_MAX_ATOMS];   // .x = pn (0 for a None atom type), .y = bit pattern of the ASF-table offset type * sumX
-    int n_atoms, pad[3];
+    int useg[PX_MAX_ATOMS];          // distinct-plane mode (k_phase_small): plane_arg / plane_end describe DISTINCT planes of the
+                                     // whole phase, plane_end[u] = one past the last entry of useg that belongs to plane u
+    int n_atoms, n_u, pad[2];
     double lpf_q, lpf_k1, lpf_k2, lpf_pol;   // Lorentz-polarisation constants of this (phase, specimen), see lpf_point
 };
 
@@ -773,6 +843,7 @@ __global__ void k_leaf_lpf(const double *theta, long long n, double sigma_star, 
 // cooperative load of the component / atom lists of phase `pb` into shared memory.  Atoms of a
 // component that sit at the same z (several species on one crystallographic plane) share one
 // complex exponential: sum_a asf_a pn_a exp(i arg) = (sum_a asf_a pn_a) exp(i arg).
+template <bool DISTINCT = false>
 __device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int G, PhaseSmem *ps, long long sumX,
                                                  const double *derived_s) {
     const int *pi = bt.phase_i + pb * 8;
@@ -802,6 +873,20 @@ __device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int
     if (threadIdx.x == 0) {
         ps->n_atoms = first_atom;
         lpf_setup(ps, bt.phase_d[pb * 8], derived_s);
+    }
+    if constexpr (DISTINCT) {
+        // plane_arg / plane_end written above are replaced by the distinct-plane tables of k_phase_planes (the writes
+        // above and below touch the same addresses from different threads: order them)
+        __syncthreads();
+        const int nu = bt.ph_nu[pb];
+        const double *uz = bt.ph_uz + (long long)pb * bt.acap;
+        const int *uend = bt.ph_uend + (long long)pb * bt.acap, *useg = bt.ph_useg + (long long)pb * bt.acap;
+        for (int u = threadIdx.x; u < nu; u += blockDim.x) {
+            ps->plane_arg[u] = __dmul_rn(PX_TWO_PI, uz[u]);
+            ps->plane_end[u] = uend[u];
+        }
+        for (int i = threadIdx.x; i < first_plane; i += blockDim.x) ps->useg[i] = useg[i];
+        if (threadIdx.x == 0) ps->n_u = nu;
     }
 }
 
@@ -931,6 +1016,66 @@ __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, 
     }
 }
 
+// structure factors and phase factors of ALL G components at the N points of one thread, one complex exponential per
+// DISTINCT plane of the phase (load_phase_lists<true>); per plane the arithmetic is that of component_factors_n
+template <int G, int N>
+__device__ __forceinline__ void phase_factors_n(const PhaseSmem *ps, const double (&stl)[N], const double *__restrict__ asf_col,
+                                                int stride, double (&ur)[G][N], double (&ui)[G][N], double (&pr)[G][N],
+                                                double (&pim)[G][N]) {
+#pragma unroll
+    for (int c = 0; c < G; ++c)
+#pragma unroll
+        for (int k = 0; k < N; ++k) { ur[c][k] = 0.0; ui[c][k] = 0.0; }
+    const int nu = ps->n_u;
+    int sg = 0;
+    for (int u = 0; u < nu; ++u) {
+        const double arg = ps->plane_arg[u];
+        double ang[N], sn[N], cs[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(arg, stl[k]);
+        px_sincos_n<N>(ang, sn, cs);
+        const int sg_end = ps->plane_end[u];
+        for (; sg < sg_end; ++sg) {
+            const int info = ps->useg[sg];
+            const int a1 = (info >> 9) & 0x1ff, comp = info >> 18;
+            double f[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) f[k] = 0.0;
+            for (int a = info & 0x1ff; a < a1; ++a) {
+                const double2 po = ps->atom_po[a];
+                const double *col = asf_col + __double_as_longlong(po.y);
+#pragma unroll
+                for (int k = 0; k < N; ++k) f[k] = fma(__ldg(col + k * stride), po.x, f[k]);
+            }
+#pragma unroll
+            for (int c = 0; c < G; ++c)
+                if (comp == c) {                            // block-uniform
+#pragma unroll
+                    for (int k = 0; k < N; ++k) { ur[c][k] = fma(f[k], cs[k], ur[c][k]); ui[c][k] = fma(f[k], sn[k], ui[c][k]); }
+                }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        const double d001 = ps->comp_d001[c], delta_c = ps->comp_delta[c];
+        double ang[N], sn[N], cs[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), d001);
+        px_sincos_n<N>(ang, sn, cs);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (delta_c != 0.0) {                           // block-uniform branch
+                const double e = exp(__dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl[k])));
+                pr[c][k] = e * cs[k];
+                pim[c][k] = e * sn[k];
+            } else {
+                pr[c][k] = cs[k];
+                pim[c][k] = sn[k];
+            }
+        }
+    }
+}
+
 // everything after Re(a^T S b): absolute scale, LPF, machine correction (phases.py:158,81-95, specimen.py:57-62)
 __device__ __forceinline__ double finish_point(double tr, double abs_scale, int flags, const PhaseSmem *ps,
                                                const StaticDev &st, long long gx) {
@@ -974,7 +1119,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     const double mean = px[0], abs_scale = px[1];
     const int flags = pi[4];
 
-    load_phase_lists(bt, pb, G, ps, st.sumX, st.derived + s * 8);
+    constexpr bool DISTINCT = G > 1;        // one component: nothing to share between components
+    load_phase_lists<DISTINCT>(bt, pb, G, ps, st.sumX, st.derived + s * 8);
     {
         const double *W = bt.matrices + pi[6];
         const double *P = W + R * R;
@@ -998,9 +1144,10 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     for (int k = 0; k < PPT; ++k) stl[k] = st.stl[gx + k * TPB];
 
     double ur[G][PPT], ui[G][PPT], pr[G][PPT], pim[G][PPT], gr[G][PPT], gi[G][PPT];
+    if constexpr (DISTINCT) phase_factors_n<G, PPT>(ps, stl, st.asf + gx, TPB, ur, ui, pr, pim);
 #pragma unroll
     for (int c = 0; c < G; ++c) {
-        component_factors_n<PPT>(ps, c, stl, st.asf + gx, TPB, ur[c], ui[c], pr[c], pim[c]);
+        if constexpr (!DISTINCT) component_factors_n<PPT>(ps, c, stl, st.asf + gx, TPB, ur[c], ui[c], pr[c], pim[c]);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             gr[c][k] = pr[c][k] * ur[c][k] + pim[c][k] * ui[c][k];          // g = phi * conj(u)

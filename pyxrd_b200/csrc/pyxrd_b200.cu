@@ -124,6 +124,7 @@ struct pyxrd_ctx {
     DevBuf d_tmpl;           // template candidate + solution vectors + binding table of a device-expanded population
     PinBuf h_tmpl;
     const int *jobids_dev = nullptr;   // inside d_blob
+    DevBuf d_ph_nu, d_ph_uz, d_ph_uend, d_ph_useg;
     DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_phase_valid, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
     int residual_method = PYXRD_RESIDUAL_RP;   // settings.RESIDUAL_METHOD (mixture.py:22-27,89)
     DevBuf d_selpos, d_selcount;
@@ -332,7 +333,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_invsin, &ctx->d_stl,
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob, &ctx->d_tmpl,
-                      &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
+                      &ctx->d_ph_nu, &ctx->d_ph_uz, &ctx->d_ph_uend, &ctx->d_ph_useg, &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
                       &ctx->d_res, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
@@ -505,10 +506,10 @@ BlobLayout plan_blob(const BatchSizes &z, int S) {
 }
 
 // parameter blocks of a batch descriptor are well formed; *ncap = coefficient stride (largest CSDS maximum + 2)
-int validate_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, int *ncap_out) {
+int validate_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, int *ncap_out, int *acap_out) {
     const StaticDev &st = ctx->st;
     const int NP = d->n_phases, NC = d->n_components, NA = d->n_atoms;
-    int ncap = 2;
+    int ncap = 2, acap = 1;
     for (int p = 0; p < NP; ++p) {
         const int32_t *pi = d->phase_i + (size_t)p * PYXRD_PHASE_I_STRIDE;
         if (!(pi[4] & PYXRD_FLAG_VALID_PROBS)) continue;
@@ -538,10 +539,12 @@ int validate_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, int *ncap_out) {
             atoms += d->comp_i[(size_t)ci * PYXRD_COMP_I_STRIDE + 1] + d->comp_i[(size_t)ci * PYXRD_COMP_I_STRIDE + 2];
         }
         if (atoms > PX_MAX_ATOMS) return fail(ctx, "set_batch: phase %d has %d atoms (limit %d)", p, atoms, PX_MAX_ATOMS);
+        acap = std::max(acap, atoms);
     }
     for (int a = 0; a < NA; ++a)
         if (d->atom_type[a] >= st.T) return fail(ctx, "set_batch: atom %d references atom type %d of %d", a, d->atom_type[a], st.T);
     *ncap_out = ncap;
+    *acap_out = acap;
     return 0;
 }
 
@@ -593,7 +596,7 @@ int build_jobs(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, std::vector<int> &job_
 }
 
 // derived buffers, the BatchDev view of the blob, and the per-candidate prologue kernels
-int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int ncap) {
+int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int ncap, int acap) {
     const StaticDev &st = ctx->st;
     const int K = z.K, M = z.M, NP = z.NP, NC = z.NC, NA = z.NA, S = st.S, Z = st.Z;
     const long long cand_stride = (long long)M * Z * st.sumX;
@@ -604,6 +607,10 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
     CK(ctx->d_phase_x.ensure(sizeof(double) * 4 * std::max(NP, 1)));
     CK(ctx->d_phase_valid.ensure(sizeof(int) * std::max(NP, 1)));
     CK(ctx->d_coef.ensure(sizeof(double) * (size_t)ncap * std::max(NP, 1)));
+    CK(ctx->d_ph_nu.ensure(sizeof(int) * std::max(NP, 1)));
+    CK(ctx->d_ph_uz.ensure(sizeof(double) * (size_t)acap * std::max(NP, 1)));
+    CK(ctx->d_ph_uend.ensure(sizeof(int) * (size_t)acap * std::max(NP, 1)));
+    CK(ctx->d_ph_useg.ensure(sizeof(int) * (size_t)acap * std::max(NP, 1)));
     ctx->int_count = (int64_t)K * cand_stride;
     ctx->tot_count = (int64_t)K * Z * st.sumX;
     CK(ctx->d_int.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
@@ -635,6 +642,11 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
     bt.prob_model = z.model_driven ? reinterpret_cast<const int *>(dev(P_PMODEL)) : nullptr;
     bt.prob_params = z.model_driven ? reinterpret_cast<const double *>(dev(P_PPARAM)) : nullptr;
     bt.phase_valid = ctx->d_phase_valid.as<int>();
+    bt.acap = acap;
+    bt.ph_nu = ctx->d_ph_nu.as<int>();
+    bt.ph_uz = ctx->d_ph_uz.as<double>();
+    bt.ph_uend = ctx->d_ph_uend.as<int>();
+    bt.ph_useg = ctx->d_ph_useg.as<int>();
     bt.job_pb = reinterpret_cast<const int *>(dev(P_JOB_PB));
     bt.job_spec = reinterpret_cast<const int *>(dev(P_JOB_SPEC));
     bt.job_out = reinterpret_cast<const long long *>(dev(P_JOB_OUT));
@@ -666,6 +678,10 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
         k_component_z<<<(NC + 63) / 64, 64, 0, ctx->stream>>>(bt);
         LAUNCH_CHECK("k_component_z");
     }
+    if (NP > 0) {
+        k_phase_planes<<<NP, 32, 0, ctx->stream>>>(bt);
+        LAUNCH_CHECK("k_phase_planes");
+    }
     CK(cudaEventRecord(ctx->ev[7], ctx->stream));
     ctx->ev_set[3] = true;
     ctx->have_batch = true;
@@ -686,8 +702,8 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     const StaticDev &st = ctx->st;
     if (d->n_candidates <= 0 || d->n_phase_slots <= 0)
         return fail(ctx, "set_batch: need K > 0 and M > 0 (K=%d M=%d)", d->n_candidates, d->n_phase_slots);
-    int ncap = 2;
-    if (validate_batch(ctx, d, &ncap)) return 1;
+    int ncap = 2, acap = 1;
+    if (validate_batch(ctx, d, &ncap, &acap)) return 1;
     std::vector<int> job_pb, job_spec, jobids;
     std::vector<long long> job_out;
     if (build_jobs(ctx, d, job_pb, job_spec, job_out, jobids)) return 1;
@@ -707,7 +723,7 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     for (int i = 0; i < P_COUNT; ++i)
         if (L.bytes[i] && src[i]) memcpy(static_cast<char *>(ctx->h_blob.ptr) + L.off[i], src[i], L.bytes[i]);
     CK(cudaMemcpyAsync(ctx->d_blob.ptr, ctx->h_blob.ptr, L.total, cudaMemcpyHostToDevice, ctx->stream));
-    return bind_batch(ctx, z, L, ncap);
+    return bind_batch(ctx, z, L, ncap, acap);
 }
 
 
@@ -1179,8 +1195,8 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     const int64_t NM = t->n_matrix;
     if ((int64_t)NP * K > 0x7fffffffLL || (int64_t)NA * K > 0x7fffffffLL || NM * K > 0x7fffffffLL)
         return fail(ctx, "set_population: population too large for 32-bit indices");
-    int ncap = 2;
-    if (validate_batch(ctx, t, &ncap)) return 1;
+    int ncap = 2, acap = 1;
+    if (validate_batch(ctx, t, &ncap, &acap)) return 1;
     const bool model_driven = t->prob_model && t->prob_params;
     const size_t per[8] = {(size_t)NP * PYXRD_PHASE_D_STRIDE, (size_t)NC * PYXRD_COMP_D_STRIDE, (size_t)NA * PYXRD_ATOM_D_STRIDE, (size_t)NM,
                            model_driven ? (size_t)NP * PYXRD_PROB_STRIDE : 0, (size_t)M, (size_t)S, (size_t)S};
@@ -1311,7 +1327,7 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     e.bg = (double *)dp(P_BG); e.pmodel = model_driven ? (int *)dp(P_PMODEL) : nullptr; e.pparam = model_driven ? (double *)dp(P_PPARAM) : nullptr;
     k_expand_population<<<K, 128, 0, ctx->stream>>>(e);
     LAUNCH_CHECK("k_expand_population");
-    return bind_batch(ctx, z, L, ncap);
+    return bind_batch(ctx, z, L, ncap, acap);
 }
 
 int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop, double *residuals_out) {
