@@ -668,17 +668,59 @@ __global__ void k_leaf_probabilities(int model, int G, const double *par, double
     out[0] = valid;
 }
 
-__global__ void k_phase_prologue(BatchDev bt) {
-    const int pb = blockIdx.x * blockDim.x + threadIdx.x;
+// warp per phase.  The transcendental part of csds_series (one log-normal density per layer count) is spread over
+// the lanes; the sums are then taken by lane 0 in the order csds_series takes them, so both give the same bits.
+#define PX_PROLOGUE_WARPS 4
+#define PX_PROLOGUE_QCAP 512      // layer counts staged per warp; longer distributions take the serial path
+__global__ void __launch_bounds__(32 * PX_PROLOGUE_WARPS) k_phase_prologue(BatchDev bt) {
+    __shared__ double sq[PX_PROLOGUE_WARPS][PX_PROLOGUE_QCAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pb = blockIdx.x * PX_PROLOGUE_WARPS + warp;
     if (pb >= bt.NP) return;
     const int *pi = bt.phase_i + pb * 8;
     const double *pd = bt.phase_d + pb * 8;
     double *px = bt.phase_x + pb * 4;
-    if (!bt.phase_valid[pb] || (pi[4] & 8)) { px[0] = 0.0; px[1] = 0.0; px[2] = 0.0; return; }   // invalid probabilities / raw pattern
-    const int G = pi[0], r = pi[1];
+    if (!bt.phase_valid[pb] || (pi[4] & 8)) {               // invalid probabilities / raw pattern
+        if (lane == 0) { px[0] = 0.0; px[1] = 0.0; px[2] = 0.0; }
+        return;
+    }
+    const int G = pi[0], r = pi[1], nmin = pi[2], nmax = pi[3];
+    double *cpow = bt.coef + (long long)pb * bt.ncap;
     double mean;
     int ntop;
-    csds_series(pd, pi[2], pi[3], nullptr, &mean, bt.coef + (long long)pb * bt.ncap, &ntop);
+    if (nmax - nmin + 1 > PX_PROLOGUE_QCAP) {
+        if (lane == 0) csds_series(pd, nmin, nmax, nullptr, &mean, cpow, &ntop);
+    } else {
+        double *q = sq[warp];
+        const double lavg = log(pd[1]);
+        const double a = pd[2] * lavg + pd[3];
+        const double b = sqrt(pd[4] * lavg + pd[5]);
+        for (int T = nmin + lane; T <= nmax; T += 32) q[T - nmin] = lognormal_dev(fmax((double)T, 1e-50), a, b);
+        for (int n = lane; n <= nmax + 1; n += 32) cpow[n] = 0.0;
+        __syncwarp();
+        if (lane == 0) {
+            double total = 0.0, msum = 0.0;
+            for (int T = nmin; T <= nmax; ++T) {           // CSDS.py:29-36,40-44
+                total += q[T - nmin];
+                msum += (double)T * q[T - nmin];
+            }
+            mean = msum / total;
+            // coef_n = 2 sum_{m>n} (m-n) q_m (phases.py:147-151) by the two running sums of csds_series
+            double tail = 0.0, c = 0.0;
+            ntop = 0;
+            for (int n = nmax; n >= 0; --n) {
+                if (n >= nmin) {
+                    const int power = (n >= 1) ? n : nmax + 1;     // Qn[n-1] with python wrap-around for n = 0
+                    cpow[power] += 2.0 * c;
+                    if (c != 0.0 && power > ntop) ntop = power;
+                }
+                const double qn = (n >= nmin && n >= 1) ? q[n - nmin] / total : 0.0;
+                tail += qn;
+                c += tail;
+            }
+        }
+    }
+    if (lane != 0) return;
     // absolute scale, phases.py:48-66 (first G diagonal entries of W)
     const double *W = bt.matrices + pi[6];
     double vol = 0.0, d001 = 0.0, dens = 0.0;

@@ -671,7 +671,7 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
     if (NP > 0) {
         k_probabilities<<<(NP + 63) / 64, 64, 0, ctx->stream>>>(bt);
         LAUNCH_CHECK("k_probabilities");
-        k_phase_prologue<<<(NP + 63) / 64, 64, 0, ctx->stream>>>(bt);
+        k_phase_prologue<<<(NP + PX_PROLOGUE_WARPS - 1) / PX_PROLOGUE_WARPS, 32 * PX_PROLOGUE_WARPS, 0, ctx->stream>>>(bt);
         LAUNCH_CHECK("k_phase_prologue");
     }
     if (NC > 0) {
