@@ -219,3 +219,32 @@ def test_population_errors(ctx):
         with pytest.raises(DeviceError, match="CSDS range"):
             ctx.evaluate_population(tmpl.batch, xs, tmpl.bindings, tmpl.csds_auto, tmpl.csds_factor)
         assert np.isfinite(ctx.evaluate_population(tmpl.batch, x, tmpl.bindings, tmpl.csds_auto, tmpl.csds_factor)).all()
+
+
+def test_batched_lbfgsb_equals_trial_by_trial_lbfgsb(ctx):
+    """the L BFGS B run (scipy_runs.py:39-48) with every gradient's d + 1 probes in one device batch takes the path
+    of the trial-by-trial run: the device results do not depend on how trials are grouped"""
+    from scipy.optimize import fmin_l_bfgs_b
+    from pyxrd_b200 import drivers
+    tmpl, refs = _template("c2")
+    x0 = syn.sample_solutions(refs, 31, 1)[0]
+    sol, res, info = drivers.lbfgsb(tmpl, x0, maxiter=4)
+    one = lambda x: float(tmpl.optimized_residuals(np.asarray(x)[None, :])[0])          # noqa: E731
+    want_sol, want_res, want_info = fmin_l_bfgs_b(one, x0, approx_grad=True, epsilon=1e-4, maxiter=4,
+                                                  bounds=[tuple(b) for b in tmpl.bounds()])
+    assert np.array_equal(sol, want_sol) and res == want_res and info["nit"] == want_info["nit"]
+    assert info["trials"] == want_info["funcalls"] and info["batches"] * (len(refs) + 1) == info["trials"]
+    assert res < one(x0)
+
+
+def test_brute_force_generation(ctx):
+    from pyxrd_b200 import drivers
+    tmpl, refs = _template("c1")
+    best, value, grid, values = drivers.brute_force(tmpl, num_samples=5)
+    assert grid.shape == (3 * 25, 3) and np.isfinite(values).all()
+    k = int(np.argmin(values))
+    tmpl.apply(grid[k], probabilities=om.probabilities)
+    ref = copy.deepcopy(tmpl.mixture)
+    want = float(orc.get_optimized_residual(ref)[0])
+    assert value <= want * (1.0 + OPT_RTOL)
+    assert np.array_equal(drivers.evaluate_generation(tmpl, grid[:7], optimize=False), tmpl.residuals(grid[:7])[:, 0])
