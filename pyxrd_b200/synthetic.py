@@ -391,6 +391,29 @@ def raw_case() -> MixtureData:
     return out
 
 
+def z2_case() -> MixtureData:
+    """two patterns per specimen (``z_list`` of length 2: specimen.py:52-63 loops over it, ``observed_intensity`` is
+    [X, 2], ``phases`` is [Z][M]): c4's air-dry specimen carries its own phase set as pattern 0 and the glycolated
+    set as pattern 1; the second specimen keeps one ... two patterns as well (both of its own set, one phase None)"""
+    mix = _c4(None)
+    ad, eg = mix.specimens
+    theta = ad.range_theta
+    rng = np.random.default_rng(777)
+    row_ad, row_eg = list(ad.phases[0]), list(eg.phases[0])
+    row_b = list(row_eg)
+    row_b[2] = None
+    specs = []
+    for rows, gon, excl in (([row_ad, row_eg], ad.goniometer, None), ([row_eg, row_b], eg.goniometer, (26.0, 28.0))):
+        sp = make_specimen(theta, rows[0], gon, exclusion=excl)
+        sp.phases = [list(r) for r in rows]
+        sp.z_list = [0.0, 1.0]
+        tt = np.degrees(2.0 * theta)
+        sp.observed_intensity = np.stack([40.0 + 25.0 * np.sin(tt * 0.8) ** 2 + rng.uniform(0.0, 5.0, tt.size),
+                                          55.0 + 20.0 * np.cos(tt * 0.5) ** 2 + rng.uniform(0.0, 5.0, tt.size)], axis=1)
+        specs.append(sp)
+    return make_mixture(specs, 6, fractions=[0.3, 0.1, 0.1, 0.25, 0.1, 0.15], scales=[1.3, 0.8], bgshifts=[2.0, 4.0])
+
+
 CONFIGS = {
     "c1": Config("c1", "single-phase R0 illite, G=1, CSDS mean 10, X=2100", _c1, 1, 1),
     "c2": Config("c2", "illite-smectite R1 G=2, air-dry, X=6700", _c2, 1, 1),

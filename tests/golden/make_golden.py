@@ -131,6 +131,15 @@ def extras(ref, out):
     stl = 2 * np.sin(theta) / spec.goniometer.wavelength
     out["raw_single"] = ref.phases.get_diffracted_intensity(theta, stl, spec.phases[0][1])
     out["raw_single_lpf"] = ref.phases.get_intensity(theta, stl, 2.3, 2.3, 0.0, spec.phases[0][2])
+    # two patterns per specimen (z_list of length 2, observed [X, 2], phases [Z][M])
+    mix = syn.z2_case()
+    ref.mixture.calculate_mixture(mix)
+    for s, spec in enumerate(mix.specimens):
+        out["z2_pi_s%d" % s] = np.array(spec.phase_intensities)
+        out["z2_total_s%d" % s] = np.array(spec.total_intensity)
+    out["z2_residuals"] = np.array(mix.residuals, dtype=float)
+    mix = syn.z2_case()
+    out["z2_opt_residual"] = np.array(ref.mixture.get_optimized_residual(mix), dtype=float)
     # settings.RESIDUAL_METHOD = "Rpder" (statistics.py:29-48) on the raw case (one specimen, no
     # exclusion) and on c4 (two specimens) with an exclusion window on the first specimen
     from pyxrd.data import settings

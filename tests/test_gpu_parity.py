@@ -366,3 +366,23 @@ def test_residual_methods(calc, golden):
     mix = syn.raw_case()
     calc.mixture.calculate_mixture(mix)
     assert rel_err(mix.residuals, g["raw_residuals"]) < RTOL
+
+
+def test_two_patterns_per_specimen(calc, golden):
+    """Z = 2 (z_list of length 2): per-pattern phase sets, a None phase in one pattern only, observed [X, 2]"""
+    from pyxrd_b200.batched import get_optimized_residuals, population_residuals
+    g = golden("extras")
+    mix = syn.z2_case()
+    calc.mixture.calculate_mixture(mix)
+    for s, spec in enumerate(mix.specimens):
+        assert spec.phase_intensities.shape == (6, 2, 2100) and spec.total_intensity.shape == (2, 2100)
+        assert rel_err(spec.phase_intensities, g["z2_pi_s%d" % s]) < RTOL
+        assert rel_err(spec.total_intensity, g["z2_total_s%d" % s]) < RTOL
+    assert not mix.specimens[1].phase_intensities[2, 1].any()
+    assert rel_err(mix.residuals, g["z2_residuals"]) < RTOL
+    assert rel_err(population_residuals([syn.z2_case(), syn.z2_case()])[1], g["z2_residuals"]) < RTOL
+    want = float(g["z2_opt_residual"][0])
+    got = float(get_optimized_residuals([syn.z2_case()])[0][0])
+    assert got <= want * (1.0 + OPT_RTOL), (got, want)
+    got = float(calc.mixture.get_optimized_residual(syn.z2_case())[0])
+    assert abs(got - want) <= OPT_RTOL * want

@@ -129,3 +129,20 @@ def test_oracle_raw_pattern_phase_and_rpder(golden):
         assert rel_err(mix.residuals, g["rpder_c4_residuals"]) < 1e-11
     finally:
         orc.SETTINGS["RESIDUAL_METHOD"] = "Rp"
+
+
+def test_oracle_two_patterns_per_specimen(golden):
+    """z_list of length 2: phases [Z][M], observed [X, Z] (specimen.py:52-63, mixture.py:82-89)"""
+    import copy
+    from pyxrd_b200 import synthetic as syn
+    g = golden("extras")
+    mix = syn.z2_case()
+    orc.calculate_mixture(mix)
+    for s, spec in enumerate(mix.specimens):
+        assert spec.phase_intensities.shape == (6, 2, 2100)
+        assert rel_err(spec.phase_intensities, g["z2_pi_s%d" % s]) < TOL
+        assert rel_err(spec.total_intensity, g["z2_total_s%d" % s]) < TOL
+    assert not mix.specimens[1].phase_intensities[2, 1].any()          # the None phase of pattern 1
+    assert rel_err(mix.residuals, g["z2_residuals"]) < TOL
+    r = orc.get_optimized_residual(syn.z2_case())
+    assert abs(float(r[0]) - float(g["z2_opt_residual"][0])) <= OPT_RTOL * float(g["z2_opt_residual"][0])

@@ -1,3 +1,5 @@
+# ncu recipe of the round (run under gpurun from the repository root): launch list of the default bench command, then
+# one --set full capture per kernel family; summaries: python tools/ncu_summary.py gpurun_out/<name>.ncu-rep > profiles/<name>_summary.txt
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu"
 $CMD > gpurun_out/plain_e.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r1e_launches_c2.csv $CMD > gpurun_out/ncu_e0.log 2>&1
