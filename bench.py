@@ -150,11 +150,11 @@ def time_workload(name, count, args, rank, world, torch, dist, ctx, stream, flus
 
         # ---- resident: parameters already in HBM ------------------------------------------
         def step_resident():
-            ctx.compute_intensities()
             if optimise:
+                ctx.compute_intensities()
                 ctx.optimize(refine_bg=True)
             else:
-                ctx.compute_residuals(False)
+                ctx.compute_all(False)
 
         for _ in range(args.warmup):
             step_resident()

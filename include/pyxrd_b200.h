@@ -226,6 +226,8 @@ int pyxrd_compute_intensities(pyxrd_ctx *ctx);
  * ([k][0] = mean over specimens), totals f64 [K][S][Z][X_s]; with want_scaled != 0
  * also scaled_phase_intensities f64 [K][S][M][Z][X_s]. */
 int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled);
+/* pyxrd_compute_intensities + pyxrd_compute_residuals as one call (calculate_mixture for the resident batch) */
+int pyxrd_compute_all(pyxrd_ctx *ctx, int want_scaled);
 
 /* Which pattern residual pyxrd_compute_residuals / pyxrd_evaluate_host report (settings.py:27-32,
  * mixture.py:22-27,89): PYXRD_RESIDUAL_RP = statistics.py:22-27 (default), PYXRD_RESIDUAL_RPDER =

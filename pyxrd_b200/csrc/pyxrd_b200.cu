@@ -755,12 +755,10 @@ namespace {
 
 // phase patterns + wavelength passes of the candidates [k0, k1) on ctx->stream.  The phase kernels
 // write the buffer from which ctx->wl_passes out-of-place passes end in d_int.
-int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
-    const StaticDev &st = ctx->st;
-    double *bufs[2] = {ctx->d_int.as<double>(), ctx->d_int2.as<double>()};
-    int cur = ctx->wl_passes & 1;                      // passes alternate cur -> 1 - cur and must end in 0
+// phase kernels of the candidates [k0, k1) into `target` (one of the two pattern buffers)
+int phase_range(pyxrd_ctx *ctx, int k0, int k1, double *target, bool timed) {
     BatchDev bt = ctx->bt;
-    bt.intensities = bufs[cur];
+    bt.intensities = target;
     const long long j0 = (long long)k0 * ctx->jobs_per_cand, j1 = (long long)k1 * ctx->jobs_per_cand;
     // None phases / invalid probabilities / empty specimens stay zero (specimen.py:63, phases.py:109-111)
     size_t listed = 0;
@@ -778,6 +776,15 @@ int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     }
+    return 0;
+}
+
+int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
+    const StaticDev &st = ctx->st;
+    double *bufs[2] = {ctx->d_int.as<double>(), ctx->d_int2.as<double>()};
+    int cur = ctx->wl_passes & 1;                      // passes alternate cur -> 1 - cur and must end in 0
+    const long long j0 = (long long)k0 * ctx->jobs_per_cand, j1 = (long long)k1 * ctx->jobs_per_cand;
+    if (phase_range(ctx, k0, k1, bufs[cur], timed)) return 1;
     if (j1 > j0 && st.maxX > 0)
         for (int pass = 0; pass < ctx->wl_passes; ++pass) {
             dim3 grid((unsigned)((st.maxX + PX_WL_TPB * PX_WL_PPT - 1) / (PX_WL_TPB * PX_WL_PPT)), (unsigned)(j1 - j0));
@@ -792,6 +799,7 @@ int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
     return 0;
 }
 
+// mixture totals + residuals of the candidates [k0, k1)
 int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed) {
     BatchDev bt = ctx->bt;
     if (want_scaled) {
@@ -831,9 +839,25 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed)
     return 0;
 }
 
+// patterns + residuals of the candidates [k0, k1) at the batch's solution.  (A single pass that composes the
+// wavelength entries per point and forms totals / residuals on the fly was measured: 0.23 ms against 0.21 ms for
+// the three streaming kernels on c2 -- three levels of dependent gathers per point -- and dropped.)
+int evaluate_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed) {
+    if (intensities_range(ctx, k0, k1, timed)) return 1;
+    return residuals_range(ctx, k0, k1, want_scaled, timed);
+}
+
 }  // namespace
 
 extern "C" {
+
+int pyxrd_compute_all(pyxrd_ctx *ctx, int want_scaled) {
+    if (!ctx || !ctx->have_batch) return fail(ctx, "compute_all: no resident batch");
+    CK(cudaSetDevice(ctx->device));
+    if (evaluate_range(ctx, 0, ctx->bt.K, want_scaled, true)) return 1;
+    ctx->have_intensities = true;
+    return 0;
+}
 
 int pyxrd_compute_intensities(pyxrd_ctx *ctx) {
     if (!ctx || !ctx->have_batch) return fail(ctx, "compute_intensities: no resident batch");
@@ -953,8 +977,7 @@ int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *re
     if (const char *e = getenv("PYXRD_B200_CHUNKS")) nchunks = std::max(1, std::min(16, std::min(K, atoi(e))));
     for (int c = 0; c < nchunks; ++c) {
         const int k0 = (int)((long long)K * c / nchunks), k1 = (int)((long long)K * (c + 1) / nchunks);
-        if (intensities_range(ctx, k0, k1, nchunks == 1)) return 1;
-        if (residuals_range(ctx, k0, k1, 0, nchunks == 1)) return 1;
+        if (evaluate_range(ctx, k0, k1, 0, nchunks == 1)) return 1;
         if (intensities_out && ctx->bt.cand_stride > 0) {
             CK(cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[c], 0));
@@ -1332,8 +1355,7 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
 
 int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop, double *residuals_out) {
     if (pyxrd_set_population(ctx, t, pop)) return 1;
-    if (pyxrd_compute_intensities(ctx)) return 1;
-    if (pyxrd_compute_residuals(ctx, 0)) return 1;
+    if (pyxrd_compute_all(ctx, 0)) return 1;
     return pyxrd_read_residuals(ctx, residuals_out, (int64_t)ctx->bt.K * (ctx->st.S + 1));
 }
 

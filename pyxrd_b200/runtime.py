@@ -60,7 +60,7 @@ class PopulationDesc(C.Structure):
 EXPORTS = [
     "pyxrd_create", "pyxrd_destroy", "pyxrd_last_error", "pyxrd_set_stream", "pyxrd_synchronize",
     "pyxrd_launch_count", "pyxrd_set_static", "pyxrd_set_batch", "pyxrd_set_solution", "pyxrd_set_intensities",
-    "pyxrd_compute_intensities", "pyxrd_compute_residuals", "pyxrd_set_residual_method", "pyxrd_optimize", "pyxrd_read_solutions",
+    "pyxrd_compute_intensities", "pyxrd_compute_residuals", "pyxrd_compute_all", "pyxrd_set_residual_method", "pyxrd_optimize", "pyxrd_read_solutions",
     "pyxrd_read_opt_residuals", "pyxrd_intensity_count", "pyxrd_total_count",
     "pyxrd_read_intensities", "pyxrd_read_scaled", "pyxrd_read_totals", "pyxrd_read_residuals",
     "pyxrd_read_correction", "pyxrd_device_buffers", "pyxrd_evaluate_host", "pyxrd_optimize_host", "pyxrd_leaf_asf",
@@ -109,6 +109,7 @@ def load_library():
         lib.pyxrd_set_intensities.argtypes = [vp, _f64p, C.c_int64]
         lib.pyxrd_compute_intensities.argtypes = [vp]
         lib.pyxrd_compute_residuals.argtypes = [vp, C.c_int]
+        lib.pyxrd_compute_all.argtypes = [vp, C.c_int]
         lib.pyxrd_set_residual_method.argtypes = [vp, C.c_int]
         lib.pyxrd_optimize.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         lib.pyxrd_read_solutions.argtypes = [vp, _f64p, C.c_int64]
@@ -259,6 +260,10 @@ class Context(object):
 
     def compute_residuals(self, want_scaled: bool = False):
         self._check(self._lib.pyxrd_compute_residuals(self._h, int(bool(want_scaled))), "compute_residuals")
+
+    def compute_all(self, want_scaled: bool = False):
+        """phase patterns + wavelength distribution + totals / residuals of the resident batch (fused pass)"""
+        self._check(self._lib.pyxrd_compute_all(self._h, int(bool(want_scaled))), "compute_all")
 
     def optimize(self, refine_bg: bool = True, outer: int = 0, newton: int = 0):
         """device optimiser over the resident batch (needs computed intensities)"""

@@ -386,3 +386,33 @@ def test_two_patterns_per_specimen(calc, golden):
     assert got <= want * (1.0 + OPT_RTOL), (got, want)
     got = float(calc.mixture.get_optimized_residual(syn.z2_case())[0])
     assert abs(got - want) <= OPT_RTOL * want
+
+
+def test_compute_all_equals_the_two_calls(calc, golden):
+    """pyxrd_compute_all = pyxrd_compute_intensities + pyxrd_compute_residuals; a None phase stays zero through the
+    wavelength passes; specimens with wavelength lists of different length share the launches"""
+    from pyxrd_b200.batched import pack_population
+    from pyxrd_b200.runtime import default_context
+    g = golden("c4")
+    mixes = [m for _, m in golden_mixtures("c4", g)]
+    mixes[1].specimens[0].phases[0][2] = None
+    mixes[2].specimens[1].goniometer.wavelength_distribution = [(syn.CU_KA1, 1.0)]
+    static, batch = pack_population(mixes)
+    ctx = default_context()
+    with ctx.lock:
+        ctx.set_static(static, force=True)
+        ctx.set_batch(batch)
+        ctx.compute_intensities()
+        ctx.compute_residuals(True)
+        want = [ctx.read_intensities_flat(), ctx.read_totals_flat(), ctx.read_scaled_flat(), ctx.read_residuals()]
+        ctx.set_batch(batch)
+        ctx.compute_all(True)
+        got = [ctx.read_intensities_flat(), ctx.read_totals_flat(), ctx.read_scaled_flat(), ctx.read_residuals()]
+        ctx._resident_epoch = None
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    assert rel_err(got[3][0], g["c4_truth_residuals"]) < RTOL
+    for k, mix in enumerate(mixes[:3]):
+        ref = copy.deepcopy(mix)
+        orc.calculate_mixture(ref)
+        assert rel_err(got[3][k], ref.residuals) < RTOL
