@@ -127,6 +127,20 @@ def wavelength_tables(theta: np.ndarray, wavelength: float, distribution):
     return frac, idx, w_hi, w_lo
 
 
+def specimen_signature(spec):
+    """what a specimen contributes to the candidate-invariant tables, as a cheap comparable tuple (the abscissa by
+    size and end points, the goniometer row, the wavelength list): the candidates of one batch must agree on it"""
+    if spec is None:
+        return None
+    g = spec.goniometer
+    theta = spec.range_theta
+    n = int(np.size(theta))
+    ends = (float(theta[0]), float(theta[-1])) if n else ()
+    return (n, ends, g.wavelength, g.soller1, g.soller2, g.mcr_2theta, g.divergence_mode, g.divergence,
+            bool(g.has_absorption_correction), g.absorption, g.sample_surf_density, g.sample_length, g.radius,
+            tuple((float(w), float(f)) for w, f in (g.wavelength_distribution or [])), int(np.size(spec.observed_intensity)))
+
+
 class StaticPack(object):
     """Candidate-invariant tables of a set of specimens (pyxrd_static_desc)."""
 
@@ -144,6 +158,7 @@ class StaticPack(object):
                     n_patterns = len(spec.z_list)
                     break
         self.Z = int(n_patterns)
+        self.specimen_signatures = [specimen_signature(spec) for spec in specimens]
         self.npts = np.zeros(S, dtype=np.int32)
         self.gonio = np.zeros((S, GONIO_STRIDE))
         self.nwl = np.zeros(S, dtype=np.int32)
@@ -256,6 +271,9 @@ class BatchPack(object):
             phase_ids: Dict[int, int] = {}
             comp_ids: Dict[int, int] = {}
             for s, spec in enumerate(specimens):
+                if specimen_signature(spec) != static.specimen_signatures[s]:
+                    raise ValueError("candidate %d, specimen %d: abscissa / goniometer / observations differ from the "
+                                     "resident static tables (specimens are shared by the candidates of a batch)" % (k, s))
                 for z in range(Z):
                     row = spec.phases[z] if spec is not None else [None] * M
                     if len(row) != M:

@@ -90,3 +90,17 @@ def test_wavelength_tables_match_oracle_interpolation():
             hi = idx[j]
             got = np.where(hi >= 0, w_hi[j] * (y * f)[np.maximum(hi, 1)] + w_lo[j] * (y * f)[np.maximum(hi, 1) - 1], 0.0)
             assert np.array_equal(got, want)
+
+
+def test_candidates_of_a_batch_must_share_their_specimens():
+    mixes = syn.CONFIGS["c4"].population(7, 3)
+    types = packing.collect_atom_types([s for m in mixes for s in m.specimens])
+    static = packing.StaticPack(mixes[0].specimens, types)
+    packing.BatchPack(mixes, static)
+    mixes[2].specimens[1].goniometer.wavelength_distribution = [(syn.CU_KA1, 1.0)]
+    with pytest.raises(ValueError, match="shared by the candidates"):
+        packing.BatchPack(mixes, static)
+    mixes = syn.CONFIGS["c4"].population(7, 2)
+    mixes[1].specimens[0].range_theta = mixes[1].specimens[0].range_theta[:-5]
+    with pytest.raises(ValueError, match="shared by the candidates"):
+        packing.BatchPack(mixes, static)
