@@ -416,3 +416,63 @@ def test_compute_all_equals_the_two_calls(calc, golden):
         ref = copy.deepcopy(mix)
         orc.calculate_mixture(ref)
         assert rel_err(got[3][k], ref.residuals) < RTOL
+
+
+def _random_mixture(rng, types):
+    """a random small mixture over the shapes the reference's model layer can produce (and a few it cannot)"""
+    kinds = ["illite", "smectite_ad", "chlorite", "smectite_eg", "kaolinite", "illite"]
+    shapes = [(1, 0), (2, 0), (3, 0), (4, 0), (2, 1), (3, 1), (4, 1), (2, 2), (3, 2), (2, 3), (5, 1), (6, 0)]
+    S, Z, M = int(rng.integers(1, 4)), int(rng.integers(1, 3)), int(rng.integers(1, 5))
+    specs = []
+    for s in range(S):
+        theta = syn.theta_grid(float(rng.uniform(2.0, 6.0)), float(rng.uniform(25.0, 60.0)), float(rng.uniform(0.11, 0.3)))
+        rows = []
+        for z in range(Z):
+            row = []
+            for m in range(M):
+                if rng.uniform() < 0.12:
+                    row.append(None)
+                    continue
+                G, R = shapes[int(rng.integers(len(shapes)))]
+                comps = [syn.make_component(types, kinds[(m + c) % len(kinds)], rng, delta_c=float(rng.choice([0.0, 0.02, 0.05])))
+                         for c in range(G)]
+                W, P = syn.make_probabilities(rng, G, R)
+                avg = float(rng.uniform(3.0, 24.0))
+                csds = syn.make_csds(avg, minimum=int(rng.choice([0, 1, 1, 1, 2])))
+                ph = syn.make_phase(comps, W, P, csds, sigma_star=float(rng.uniform(1.0, 20.0)),
+                                    apply_lpf=bool(rng.uniform() < 0.85), apply_correction=bool(rng.uniform() < 0.85),
+                                    valid=bool(rng.uniform() < 0.93))
+                row.append(ph)
+            rows.append(row)
+        gon = syn.make_goniometer(str(rng.choice(["single", "cu_pair"])), divergence_mode=str(rng.choice(["FIXED", "AUTOMATIC"])),
+                                  absorption=bool(rng.uniform() < 0.4))
+        gon.mcr_2theta = float(rng.choice([0.0, 26.6]))
+        if rng.uniform() < 0.2:
+            gon.wavelength_distribution = []
+        excl = (12.0, 14.0) if rng.uniform() < 0.4 else None
+        sp = syn.make_specimen(theta, rows[0], gon, exclusion=excl)
+        sp.phases = rows
+        sp.z_list = [float(z) for z in range(Z)]
+        sp.observed_intensity = rng.uniform(10.0, 90.0, (theta.size, Z))
+        specs.append(sp)
+    fr = rng.dirichlet(np.ones(M))
+    return syn.make_mixture(specs, M, fractions=fr, scales=rng.uniform(0.3, 3.0, S), bgshifts=rng.uniform(0.0, 6.0, S))
+
+
+def test_random_mixtures_against_the_oracle(calc):
+    """32 random mixtures: 1-3 ragged specimens, 1-2 patterns each, 1-4 phases of random (G, R) / CSDS / flags, None phases,
+    invalid probabilities, both divergence modes, absorption, monochromator, empty / single / double wavelength lists"""
+    rng = np.random.default_rng(20261020)
+    types = syn.atom_types()
+    worst = 0.0
+    for _ in range(32):
+        mix = _random_mixture(rng, types)
+        ref = copy.deepcopy(mix)
+        orc.calculate_mixture(ref)
+        calc.mixture.calculate_mixture(mix)
+        for a, b in zip(mix.specimens, ref.specimens):
+            assert a.phase_intensities.shape == b.phase_intensities.shape
+            worst = max(worst, rel_err(a.phase_intensities, b.phase_intensities), rel_err(a.total_intensity, b.total_intensity))
+            assert np.array_equal(a.phase_intensities == 0.0, b.phase_intensities == 0.0)
+        worst = max(worst, rel_err(mix.residuals, ref.residuals))
+    assert worst < RTOL, worst
