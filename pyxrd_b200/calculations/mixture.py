@@ -199,8 +199,10 @@ def get_residual(mixture):
 
 @wrap_exceptions
 def optimize_mixture(mixture, force=False):
-    """mixture.py:150-219: scipy L-BFGS-B (finite-difference gradient, bounds) over
-    [fractions | scales | bgshifts]; the objective is evaluated on the device."""
+    """mixture.py:150-219.  ``settings.MIXTURE_OPTIMIZER == "device"`` (default): the device-resident optimiser when the
+    mixture is in its scope (all fractions and scales free, Rp); otherwise / ``"scipy"``: the reference's own call --
+    scipy L-BFGS-B (finite-difference gradient, bounds) over [fractions | scales | bgshifts] with the objective evaluated
+    on the device."""
     from scipy.optimize import fmin_l_bfgs_b
     if mixture.optimized and not force:
         return mixture
@@ -210,9 +212,28 @@ def optimize_mixture(mixture, force=False):
         if settings.get("DEBUG"):
             raise
         return mixture
+    ctx = default_context()
+    if settings.get("MIXTURE_OPTIMIZER") == "device":
+        from ..batched import _device_optimisable
+        if _device_optimisable(mixture):
+            # the whole minimisation in one kernel on the resident patterns (k_mixture_optimize)
+            with ctx.lock:
+                _ensure_resident(mixture, ctx)
+                refine_bg = mixture.o > 0 and bool(settings.get("BGSHIFT"))
+                ctx.optimize(refine_bg=refine_bg)
+                sol = ctx.read_solutions()[0]
+                res = ctx.read_opt_residuals()[0]
+            M, S = len(np.asarray(mixture.fractions).ravel()), len(mixture.specimens)
+            mixture.fractions = np.around(sol[:M] / np.sum(sol[:M]), 6)
+            mixture.scales = np.array(sol[M:M + S]).round(6)
+            if mixture.o > 0:
+                mixture.bgshifts = np.array(sol[M + S:M + 2 * S])
+            mixture.residual = np.array([res[0]])
+            mixture.calculated = False
+            mixture.optimized = True
+            return mixture
     x0 = get_zero_solution(mixture)
     bounds = get_bounds(mixture)
-    ctx = default_context()
     no_obs = [s for s, sp in enumerate(mixture.specimens) if sp is None or np.size(sp.observed_intensity) == 0]
 
     def objective(x):

@@ -8,6 +8,11 @@ RESIDUAL_METHOD = "Rp"
 BGSHIFT = True
 DEBUG = False
 LOG_NORMAL_MAX_CSDS_FACTOR = 2.5
+# not a reference flag: how optimize_mixture minimises.  "device" = the device-resident optimiser (pyxrd_optimize; end
+# point <= the reference's L-BFGS-B end point * (1 + 5e-3)) whenever the mixture is in its scope,
+# "scipy" = the reference's own fmin_l_bfgs_b call with the device evaluating the objective (same path as the
+# reference, ~700 device round trips per trial)
+MIXTURE_OPTIMIZER = "device"
 
 
 def get(name):

@@ -96,15 +96,28 @@ def test_config_matches_live_reference(calc, golden, name):
 
 
 @pytest.mark.parametrize("name", ["c1", "c4"])
-def test_optimize_mixture_against_live_reference(calc, golden, name):
+@pytest.mark.parametrize("mode", ["scipy", "device"])
+def test_optimize_mixture_against_live_reference(calc, golden, name, mode):
+    """"scipy": the reference's own L-BFGS-B call with the device objective ends where the reference ends;
+    "device" (default): never worse than that end point (one-sided)"""
+    from pyxrd_b200 import settings
     g = golden(name)
-    for tag, mix in golden_mixtures(name, g)[:2]:
-        r = calc.mixture.get_optimized_residual(mix)
-        want = float(g["%s_%s_opt_residual" % (name, tag)][0])
-        assert r.shape == (1,)
-        assert abs(float(r[0]) - want) <= OPT_RTOL * max(1.0, want), (name, tag, float(r[0]), want)
-        assert mix.optimized and mix.calculated
-        assert abs(np.sum(mix.fractions) - 1.0) < 1e-5
+    settings.MIXTURE_OPTIMIZER = mode
+    try:
+        for tag, mix in golden_mixtures(name, g)[:2]:
+            r = calc.mixture.get_optimized_residual(mix)
+            want = float(g["%s_%s_opt_residual" % (name, tag)][0])
+            assert r.shape == (1,)
+            if mode == "scipy":
+                assert abs(float(r[0]) - want) <= OPT_RTOL * max(1.0, want), (name, tag, float(r[0]), want)
+            else:
+                assert float(r[0]) <= want * (1.0 + OPT_RTOL), (name, tag, float(r[0]), want)
+            assert mix.optimized and mix.calculated
+            assert abs(np.sum(mix.fractions) - 1.0) < 1e-5
+            # the reported residual is the objective at the solution handed back (up to the 6-digit rounding)
+            assert abs(mix.residuals[0] - float(r[0])) <= 2e-3 * max(1.0, float(r[0]))
+    finally:
+        settings.MIXTURE_OPTIMIZER = "device"
 
 
 def test_population_batch_equals_single_calls(calc, golden):
@@ -385,7 +398,7 @@ def test_two_patterns_per_specimen(calc, golden):
     got = float(get_optimized_residuals([syn.z2_case()])[0][0])
     assert got <= want * (1.0 + OPT_RTOL), (got, want)
     got = float(calc.mixture.get_optimized_residual(syn.z2_case())[0])
-    assert abs(got - want) <= OPT_RTOL * want
+    assert got <= want * (1.0 + OPT_RTOL)
 
 
 def test_compute_all_equals_the_two_calls(calc, golden):
