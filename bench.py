@@ -365,9 +365,9 @@ def run_b200(args, rank, world, local_rank):
                              torch, dist, ctx, stream, flush)
         clocks = sampler.stop()
         trials = None
-        if args.workload != "c4" and not args.no_trials:
-            trials = time_workload("c4", DEFAULT_CANDIDATES["c4"], args, rank, world, torch, dist, ctx, stream, flush,
-                                   optimise=True)
+        if args.workload != args.trials_workload and not args.no_trials:
+            trials = time_workload(args.trials_workload, args.trials_candidates or DEFAULT_CANDIDATES[args.trials_workload],
+                                   args, rank, world, torch, dist, ctx, stream, flush, optimise=True)
         # residual gather (the only collective of the path): [K, 1+S] per rank over NCCL
         gather_us = None
         if world > 1:
@@ -433,7 +433,7 @@ def run_b200(args, rank, world, local_rank):
                           "value": tv, "unit": "trials/s", "ms_per_step": trials["dev_ms"],
                           "e2e": {"value": trials["K"] * world / (trials["e2e_ms"] * 1e-3), "unit": "trials/s",
                                   "h2d_bytes_per_step": trials["h2d"], "d2h_bytes_per_step": trials["d2h"]},
-                          "config": {"workload": "c4: %s" % trials["cfg"].description,
+                          "config": {"workload": "%s: %s" % (args.trials_workload, trials["cfg"].description),
                                      "candidates_per_gpu": trials["K"]},
                           "stage_ms": {"phase": trials["stage"]["phase"], "wavelength": trials["stage"]["wavelength"],
                                        "optimiser": trials["stage"]["residual"]},
@@ -453,7 +453,7 @@ def run_b200(args, rank, world, local_rank):
                                 "sample": "%d candidates of %s through oracle.calculate_mixture, single process, "
                                           "%.1f s" % (c["patterns"], args.workload, c["seconds"])}
         if trials is not None:
-            ct = cpu_trials(budget_s=10.0)
+            ct = cpu_trials(budget_s=10.0, name=args.trials_workload)
             line["trials"]["cpu_baseline"] = {"value": ct["trials_per_s"], "unit": "trials/s", "cores": 1, "kind": "port",
                                               "sample": "%d c4 candidates through oracle.get_optimized_residual (scipy "
                                                         "L-BFGS-B), single process, %.1f s" % (ct["n"], ct["seconds"])}
@@ -471,6 +471,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(syn.CONFIGS))
     ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU (default per workload)")
     ap.add_argument("--no-trials", action="store_true")
+    ap.add_argument("--trials-workload", default="c4", choices=sorted(syn.CONFIGS),
+                    help="configuration of the trial-evaluation measurement (BASELINE configs[3] by default)")
+    ap.add_argument("--trials-candidates", type=int, default=0, help="trials per GPU of that measurement")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -503,10 +503,11 @@ __device__ int prob_evaluate(int model, int G, const double *par, double *Wout, 
     lv.R = model == PX_PROB_R0 ? 0 : (model == PX_PROB_R1G2 || model == PX_PROB_R1G3 || model == PX_PROB_R1G4) ? 1
            : (model == PX_PROB_R2G2 || model == PX_PROB_R2G3) ? 2 : 3;
     lv.Rp = lv.R > 1 ? lv.R : 1;
-    for (int r = 0; r < 4; ++r)
-        for (int i = 0; i < PX_PROB_MAXSQ; ++i) lv.W[r][i] = 0.0;
-    for (int r = 0; r < 3; ++r)
-        for (int i = 0; i < PX_PROB_MAXSQ; ++i) lv.P[r][i] = 0.0;
+    const int nsq = lv.wrank(lv.Rp) * lv.wrank(lv.Rp);          // the largest level matrix of this model
+    for (int r = 0; r <= lv.Rp; ++r)
+        for (int i = 0; i < nsq; ++i) lv.W[r][i] = 0.0;
+    for (int r = 0; r < lv.Rp; ++r)
+        for (int i = 0; i < nsq; ++i) lv.P[r][i] = 0.0;
     prob_update(lv, model, par);
     prob_update(lv, model, par);
     bool ok = true;
@@ -1812,10 +1813,10 @@ __global__ void k_leaf_component(const double *stl, long long n, const double *c
 #define PX_WL_PPT 4
 __global__ void __launch_bounds__(PX_WL_TPB) k_wavelength_pass(StaticDev st, BatchDev bt, int job0, int pass,
                                                                const double *__restrict__ src, double *__restrict__ dst) {
-    const int job = job0 + blockIdx.y;
+    const int job = job0 + blockIdx.x;                  // jobs on x: grid.y stops at 65535
     const int s = bt.job_spec[job];
     const int X = st.spec_npts[s];
-    const int xb = blockIdx.x * (PX_WL_TPB * PX_WL_PPT) + threadIdx.x;
+    const int xb = blockIdx.y * (PX_WL_TPB * PX_WL_PPT) + threadIdx.x;
     if (xb >= X) return;
     const long long out = bt.job_out[job];
     const double *I = src + out;
@@ -1855,12 +1856,12 @@ __global__ void __launch_bounds__(PX_WL_TPB) k_wavelength_pass(StaticDev st, Bat
 
 // ---------------------------------------------------------------------------------
 // mixture: total = scale * sum_p frac_p I_p + bg * C ; Rp = 100 sum|obs - total| / sum|obs|
-// grid (S, candidates), one block per (candidate, specimen), 4 points in flight per thread
+// grid (candidates, S), one block per (candidate, specimen), 4 points in flight per thread
 // ---------------------------------------------------------------------------------
 #define PX_RES_TPB 256
 #define PX_RES_PPT 4
 __global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, BatchDev bt, int k0, int want_scaled) {
-    const int s = blockIdx.x, k = k0 + blockIdx.y;
+    const int s = blockIdx.y, k = k0 + blockIdx.x;      // candidates on x: grid.y stops at 65535
     const int X = st.spec_npts[s], Z = st.Z, M = bt.M;
     const long long soff = st.spec_off[s];
     const double *I = bt.intensities + (long long)k * bt.cand_stride + (long long)M * Z * soff;
@@ -1973,7 +1974,7 @@ __device__ __forceinline__ double rpder_gradient(const double *v, const double *
 template <bool SMEM>
 __global__ void __launch_bounds__(256) k_residual_rpder(StaticDev st, BatchDev bt, int k0, const int *sel_pos, const int *sel_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int s = blockIdx.x, k = k0 + blockIdx.y;
+    const int s = blockIdx.y, k = k0 + blockIdx.x;      // candidates on x: grid.y stops at 65535
     const int X = st.spec_npts[s], Z = st.Z;
     const int nsel = sel_count[s], n = Z * nsel;
     const long long soff = st.spec_off[s];

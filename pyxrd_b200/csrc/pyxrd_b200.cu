@@ -669,7 +669,7 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
 
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
     if (NP > 0) {
-        k_probabilities<<<(NP + 63) / 64, 64, 0, ctx->stream>>>(bt);
+        k_probabilities<<<(NP + 31) / 32, 32, 0, ctx->stream>>>(bt);        // serial per phase: spread over the SMs
         LAUNCH_CHECK("k_probabilities");
         k_phase_prologue<<<(NP + PX_PROLOGUE_WARPS - 1) / PX_PROLOGUE_WARPS, 32 * PX_PROLOGUE_WARPS, 0, ctx->stream>>>(bt);
         LAUNCH_CHECK("k_phase_prologue");
@@ -787,7 +787,7 @@ int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
     if (phase_range(ctx, k0, k1, bufs[cur], timed)) return 1;
     if (j1 > j0 && st.maxX > 0)
         for (int pass = 0; pass < ctx->wl_passes; ++pass) {
-            dim3 grid((unsigned)((st.maxX + PX_WL_TPB * PX_WL_PPT - 1) / (PX_WL_TPB * PX_WL_PPT)), (unsigned)(j1 - j0));
+            dim3 grid((unsigned)(j1 - j0), (unsigned)((st.maxX + PX_WL_TPB * PX_WL_PPT - 1) / (PX_WL_TPB * PX_WL_PPT)));
             k_wavelength_pass<<<grid, PX_WL_TPB, 0, ctx->stream>>>(st, ctx->bt, (int)j0, pass, bufs[cur], bufs[1 - cur]);
             LAUNCH_CHECK("k_wavelength_pass");
             cur = 1 - cur;
@@ -808,7 +808,7 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed)
     }
     if (timed) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (k1 > k0) {
-        dim3 grid(ctx->st.S, k1 - k0);
+        dim3 grid(k1 - k0, ctx->st.S);
         k_mixture_residual<<<grid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled);
         LAUNCH_CHECK("k_mixture_residual");
         if (ctx->residual_method == PYXRD_RESIDUAL_RPDER) {

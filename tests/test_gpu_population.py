@@ -248,3 +248,31 @@ def test_brute_force_generation(ctx):
     want = float(orc.get_optimized_residual(ref)[0])
     assert value <= want * (1.0 + OPT_RTOL)
     assert np.array_equal(drivers.evaluate_generation(tmpl, grid[:7], optimize=False), tmpl.residuals(grid[:7])[:, 0])
+
+
+def test_more_than_65535_patterns_in_one_batch(ctx):
+    """grid.y stops at 65535: candidates / patterns ride on grid.x in every kernel (70 000 one-phase candidates, and a
+    6-phase x 2-specimen mixture with 6 000 candidates = 72 000 patterns)"""
+    mix, refs = syn.template("c1")
+    spec = mix.specimens[0]
+    theta = spec.range_theta[::30]                                   # 70 points
+    mix.specimens[0] = syn.make_specimen(theta, spec.phases[0], spec.goniometer)
+    mix.specimens[0].goniometer.wavelength_distribution = list(syn.CU_PAIR)
+    _observe(mix)
+    tmpl = PopulationTemplate(mix, refs)
+    x = syn.sample_solutions(refs, 41, 70000)
+    res = tmpl.residuals(x)
+    assert res.shape == (70000, 2) and np.isfinite(res).all()
+    pick = np.array([0, 1, 65534, 65535, 65536, 69999])
+    assert np.array_equal(res[pick], tmpl.residuals(x[pick]))
+    opt = tmpl.optimized_residuals(x)
+    assert np.isfinite(opt).all() and np.array_equal(opt[pick], tmpl.optimized_residuals(x[pick]))
+    mix, refs = syn.template("c4")
+    for s, spec in enumerate(mix.specimens):
+        mix.specimens[s] = syn.make_specimen(spec.range_theta[::30], spec.phases[0], spec.goniometer)
+    _observe(mix)
+    tmpl = PopulationTemplate(mix, refs)
+    x = syn.sample_solutions(refs, 42, 6000)
+    res = tmpl.residuals(x)
+    pick = np.array([0, 5461, 5462, 5999])
+    assert np.isfinite(res).all() and np.array_equal(res[pick], tmpl.residuals(x[pick]))
