@@ -2476,8 +2476,10 @@ __device__ __forceinline__ void opt_solve_dispatch(OptSmem &sm, int S, int lm_it
     if (warp == 0) opt_inner_solve(sm, M, S, M + 1, lm_iters, refine_bg, lane);
 }
 
-template <int MB>
-__global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st, BatchDev bt, OptParams op,
+// TPB = 256 for populations that fit the machine in one wave (shortest chain per candidate), 128 for larger ones
+// (twice as many candidates in flight: the Newton steps, which keep four warps busy, overlap better)
+template <int MB, int TPB>
+__global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev st, BatchDev bt, OptParams op,
                                                                  double *solutions, double *opt_residuals) {
     constexpr int M = MB - 1;
     constexpr int NG = MB * (MB + 1) / 2;       // upper triangle of the Gram matrix
@@ -2527,12 +2529,12 @@ __global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st
 #endif
             // two points in flight per thread: the loads of both are issued before the arithmetic
             for (int z = 0; z < Z; ++z)
-                for (int x0 = tid; x0 < X; x0 += 2 * PX_OPT_TPB) {
+                for (int x0 = tid; x0 < X; x0 += 2 * TPB) {
                     double phi[2][MB], o[2];
                     bool on[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const int x = x0 + u * PX_OPT_TPB;
+                        const int x = x0 + u * TPB;
                         on[u] = x < X && sel[x];
                         const int xc = x < X ? x : x0;
 #pragma unroll
@@ -2574,7 +2576,7 @@ __global__ void __launch_bounds__(PX_OPT_TPB, 2) k_mixture_optimize(StaticDev st
             __syncthreads();
             if (tid < NACC) {
                 double vsum = 0.0;
-                for (int w2 = 0; w2 < PX_OPT_TPB / 32; ++w2) vsum += sm.red[w2][tid];
+                for (int w2 = 0; w2 < TPB / 32; ++w2) vsum += sm.red[w2][tid];
                 if (tid < NG) {
                     // unpack upper-triangle index tid -> (p, q) and mirror
                     int p = 0, e = tid;

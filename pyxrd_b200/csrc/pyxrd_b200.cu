@@ -102,6 +102,7 @@ struct pyxrd_ctx {
     std::string error;
     int64_t launches = 0;
     int smem_optin = 0;
+    int sm_count = 148;
     bool series_mma = true;   // PYXRD_B200_SERIES=dfma selects the CUDA-core series kernels (A/B measurements only)
 
     // static
@@ -279,8 +280,15 @@ static int read_back(pyxrd_ctx *ctx, const void *dev, double *out, int64_t count
 
 template <int MB>
 static int launch_optimize(pyxrd_ctx *ctx, const OptParams &op) {
-    k_mixture_optimize<MB><<<ctx->bt.K, PX_OPT_TPB, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
-                                                                       ctx->d_optres.as<double>());
+    // one wave of 256-thread blocks (2 per SM) when the population fits it, else 128-thread blocks (4 per SM)
+    int tpb = ctx->bt.K <= 2 * ctx->sm_count ? 256 : 128;
+    if (const char *e = getenv("PYXRD_B200_OPT_TPB")) tpb = atoi(e) == 128 ? 128 : 256;
+    if (tpb == 256)
+        k_mixture_optimize<MB, 256><<<ctx->bt.K, 256, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
+                                                                        ctx->d_optres.as<double>());
+    else
+        k_mixture_optimize<MB, 128><<<ctx->bt.K, 128, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
+                                                                        ctx->d_optres.as<double>());
     LAUNCH_CHECK("k_mixture_optimize");
     return 0;
 }
@@ -309,6 +317,7 @@ int pyxrd_create(int device, pyxrd_ctx **out) {
     ctx->stream = ctx->own_stream;
     if (const char *e = getenv("PYXRD_B200_SERIES")) ctx->series_mma = strcmp(e, "dfma") != 0;
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     {   // np.blackman(31) / np.blackman(31).sum()  (math_tools.py:93-98 with half_window_len = 15)
