@@ -20,7 +20,9 @@ def load():
     if not hasattr(scipy.integrate, "trapz"):
         scipy.integrate.trapz = scipy.integrate.trapezoid
     if "imp" not in sys.modules:
-        sys.modules["imp"] = types.ModuleType("imp")
+        imp = types.ModuleType("imp")
+        imp.find_module = lambda *a, **k: None           # imported, never called (refinement/methods/__init__.py:12)
+        sys.modules["imp"] = imp
     for name in ("gi", "gi.repository", "cairocffi", "matplotlib", "matplotlib.pyplot", "matplotlib.figure",
                  "matplotlib.backends", "matplotlib.backends.backend_gtk3", "matplotlib.backends.backend_gtk3cairo",
                  "matplotlib.font_manager", "matplotlib.transforms", "matplotlib.text", "matplotlib.patches",

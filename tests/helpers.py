@@ -52,3 +52,14 @@ def golden_mixtures(name, g, n=None):
         for s, spec in enumerate(mix.specimens):
             spec.observed_intensity = np.array(g["%s_observed_s%d" % (name, s)])
     return out
+
+
+def reference_fixture():
+    """(MixtureData, golden outputs) of the reference's own integration fixture ``test/test_mixture/test refinement.pyxrd``
+    (tests/golden/make_fixture.py): the DataObject graph the reference's model layer builds for it, carried into
+    pyxrd_b200.data_objects instances"""
+    import pickle
+    golden = os.path.join(ROOT, "tests", "golden")
+    with open(os.path.join(golden, "fixture.pkl"), "rb") as f:
+        mix = pickle.load(f)
+    return mix, np.load(os.path.join(golden, "fixture.npz"))

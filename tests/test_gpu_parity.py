@@ -489,3 +489,33 @@ def test_random_mixtures_against_the_oracle(calc):
             assert np.array_equal(a.phase_intensities == 0.0, b.phase_intensities == 0.0)
         worst = max(worst, rel_err(mix.residuals, ref.residuals))
     assert worst < RTOL, worst
+
+
+def test_reference_integration_fixture(calc):
+    """the reference's own project file test/test_mixture/test refinement.pyxrd, as its model layer hands it over
+    (Mixture.data_object): patterns / totals / residuals at 1e-9 against the live reference, optimised residual
+    (live reference: 0.05744468) within the optimiser contract in both modes"""
+    from helpers import reference_fixture
+    from pyxrd_b200 import settings
+    from pyxrd_b200.batched import get_optimized_residuals
+    mix, g = reference_fixture()
+    work = copy.deepcopy(mix)
+    calc.mixture.calculate_mixture(work)
+    for s, spec in enumerate(work.specimens):
+        assert rel_err(spec.correction, g["corr_s%d" % s]) < 1e-14
+        assert rel_err(spec.phase_intensities, g["pi_s%d" % s]) < RTOL
+        assert rel_err(spec.total_intensity, g["total_s%d" % s]) < RTOL
+    assert rel_err(work.residuals, g["residuals"]) < RTOL
+    want = float(g["opt_residual"][0])
+    r = calc.mixture.get_optimized_residual(copy.deepcopy(mix))
+    assert float(r[0]) <= want * (1.0 + OPT_RTOL) + 1e-9, (float(r[0]), want)
+    r = get_optimized_residuals([copy.deepcopy(mix), copy.deepcopy(mix)])
+    assert float(r[1][0]) <= want * (1.0 + OPT_RTOL) + 1e-9
+    settings.MIXTURE_OPTIMIZER = "scipy"
+    try:
+        work = copy.deepcopy(mix)
+        r = calc.mixture.get_optimized_residual(work)
+        assert abs(float(r[0]) - want) <= OPT_RTOL * max(1.0, want), (float(r[0]), want)
+        assert rel_err(work.fractions, g["opt_fractions"]) < 1e-3
+    finally:
+        settings.MIXTURE_OPTIMIZER = "device"

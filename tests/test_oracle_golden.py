@@ -146,3 +146,21 @@ def test_oracle_two_patterns_per_specimen(golden):
     assert rel_err(mix.residuals, g["z2_residuals"]) < TOL
     r = orc.get_optimized_residual(syn.z2_case())
     assert abs(float(r[0]) - float(g["z2_opt_residual"][0])) <= OPT_RTOL * float(g["z2_opt_residual"][0])
+
+
+def test_oracle_on_the_reference_integration_fixture():
+    """test/test_mixture/test refinement.pyxrd: 3 specimens x 3 phases, real atom types"""
+    import copy
+    from helpers import reference_fixture
+    mix, g = reference_fixture()
+    assert len(mix.specimens) == 3 and [p.G for p in mix.specimens[0].phases[0]] == [1, 1, 3]
+    work = copy.deepcopy(mix)
+    orc.calculate_mixture(work)
+    for s, spec in enumerate(work.specimens):
+        assert rel_err(spec.correction, g["corr_s%d" % s]) < 1e-14
+        assert rel_err(spec.phase_intensities, g["pi_s%d" % s]) < TOL
+        assert rel_err(spec.total_intensity, g["total_s%d" % s]) < TOL
+    assert rel_err(work.residuals, g["residuals"]) < TOL
+    r = orc.get_optimized_residual(copy.deepcopy(mix))
+    want = float(g["opt_residual"][0])
+    assert abs(float(r[0]) - want) <= OPT_RTOL * max(1.0, want)
