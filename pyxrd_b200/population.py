@@ -98,6 +98,26 @@ class PopulationTemplate(object):
             self.bindings[i] = (col, target, index, 0, scale, offset)
         self.csds_auto = auto if auto.any() else None
 
+    @classmethod
+    def from_table(cls, mixture, bindings, bounds, names=None, csds_auto=None, csds_factor: Optional[float] = None,
+                   static: Optional[StaticPack] = None):
+        """a template whose binding table is given (``discover_template``, or a table stored with a project): ``bindings``
+        structured array / rows ``(param, target, index, scale, offset)``; ``bounds`` f64[d, 2]"""
+        bounds = np.asarray(bounds, dtype=float).reshape(-1, 2)
+        names = list(names) if names is not None else ["x%d" % i for i in range(len(bounds))]
+        self = cls(mixture, [Refinable(n, [], lo, hi) for n, (lo, hi) in zip(names, bounds)], csds_auto_maximum=False,
+                   csds_factor=csds_factor, static=static)
+        table = np.asarray(bindings)
+        if table.dtype != BINDING_DTYPE:
+            rows = [tuple(r) for r in table]
+            table = np.zeros(len(rows), dtype=BINDING_DTYPE)
+            for i, (param, target, index, scale, offset) in enumerate(rows):
+                table[i] = (int(param), int(target), int(index), 0, float(scale), float(offset))
+        self.bindings = np.ascontiguousarray(table)
+        auto = None if csds_auto is None else np.ascontiguousarray(csds_auto, dtype=np.uint8)
+        self.csds_auto = auto if auto is not None and auto.any() else None
+        return self
+
     # -- resolution of (object, attribute) to packed slots --------------------------------------
     def _resolve(self, obj, attr, csds_phases):
         b = self.batch
@@ -231,3 +251,185 @@ class PopulationTemplate(object):
             phase.W, phase.P, phase.valid_probs = probabilities(model, int(phase.G), params)
         self.mixture.parsed = self.mixture.calculated = self.mixture.optimized = False
         return self.mixture
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# binding tables discovered from a running model layer
+# ---------------------------------------------------------------------------------------------------------------------
+# parameter order of the probability models = include/pyxrd_b200.h (the property names of probabilities/models/*.py)
+MODEL_PARAMETERS = {
+    "R0": ["F1", "F2", "F3", "F4", "F5"],
+    "R1G2": ["W1", "P11_or_P22"],
+    "R1G3": ["W1", "P11_or_P22", "G1", "G2", "G3", "G4"],
+    "R1G4": ["W1", "P11_or_P22", "R1", "R2", "G1", "G2", "G11", "G12", "G21", "G22", "G31", "G32"],
+    "R2G2": ["W1", "P112_or_P211", "P21", "P122_or_P221"],
+    "R2G3": ["W1", "P111_or_P212", "G1", "G2", "G3", "G4"],
+    "R3G2": ["W1", "P1111_or_P2112"],
+}
+
+
+def probability_model_of_object(model):
+    """(``prob_model`` name, parameter names, current values) of a reference probability model OBJECT
+    (probabilities/models: classes ``R<r>G<g>Model``), or None for anything else"""
+    import re
+    m = re.match(r"^R(\d)G(\d)Model$", type(model).__name__)
+    if not m:
+        return None
+    R, G = int(m.group(1)), int(m.group(2))
+    name = "R0" if R == 0 else "R%dG%d" % (R, G)
+    if name not in MODEL_PARAMETERS:
+        return None
+    names = MODEL_PARAMETERS[name][:G - 1] if R == 0 else MODEL_PARAMETERS[name]
+    return name, names, [float(getattr(model, n)) for n in names]
+
+
+_SLOT_ARRAYS = (("phase_d", BIND_PHASE_D), ("comp_d", BIND_COMP_D), ("atom_d", BIND_ATOM_D), ("matrices", BIND_MATRIX),
+                ("prob_params", BIND_PROB_PARAM), ("fractions", BIND_FRACTION), ("scales", BIND_SCALE),
+                ("bgshifts", BIND_BGSHIFT))
+_STRUCTURE_ARRAYS = ("phase_comp", "comp_i", "atom_type", "job_phase", "prob_model")
+
+
+def discover_template(get_data_object, x0, bounds, names=None, phase_model=None, csds_factor: Optional[float] = None,
+                      verify: int = 3, seed: int = 0):
+    """Binding table of a refinement found by PROBING the model layer instead of knowing it.
+
+    ``get_data_object(x) -> MixtureData`` is the reference's own route from a solution to the calculation input
+    (``Refiner.get_data_object``, refinement/refiner.py:100-106: it writes x into the MVC model -- inheritance, unit-cell
+    and atom-ratio relations included -- and rebuilds the DataObject graph).  The template is the packed graph at ``x0``;
+    every refinable is moved twice, the packed arrays are compared, and every slot that moved must have moved affinely
+    (``slot = scale * x_i + offset``); the table is then checked against ``verify`` random solutions.  Non-affine slots are
+    accepted in two forms only: the CSDS maximum following its average (``int(factor * average)``), and probability
+    matrices of phases for which ``phase_model(s, z, m) -> (name, parameter names, values) | None`` names the reference's
+    probability model -- those phases become model-driven (W, P computed on the device) and the refinable is bound to the
+    model parameter that moved.  Anything else raises ``NotImplementedError`` naming the refinable: the caller then keeps
+    evaluating that refinement graph by graph (``batched.get_optimized_residuals``).  (2 d + 1 + verify) graph builds."""
+    x0 = np.array(x0, dtype=float).ravel()
+    bounds = np.asarray(bounds, dtype=float).reshape(-1, 2)
+    d = x0.size
+    names = list(names) if names is not None else ["x%d" % i for i in range(d)]
+    factor = float(settings.get("LOG_NORMAL_MAX_CSDS_FACTOR") if csds_factor is None else csds_factor)
+    state = {}
+
+    def annotated(x):
+        """the model layer's graph for x, its model-driven phases carrying prob_model / prob_params of THAT solution"""
+        data = get_data_object(np.array(x, dtype=float))
+        if phase_model is not None:
+            for s, spec in enumerate(data.specimens):
+                if spec is None:
+                    continue
+                for z, row in enumerate(spec.phases):
+                    for m, phase in enumerate(row):
+                        if phase is None or getattr(phase, "type", "Phase") != "Phase":
+                            continue
+                        info = phase_model(s, z, m)
+                        if info is not None:
+                            phase.prob_model, phase.prob_params = info[0], list(info[2])
+                            phase.prob_param_names = list(info[1])
+        return data
+
+    def pack(x):
+        data = annotated(x)
+        if "static" not in state:
+            types = collect_atom_types(data.specimens)
+            z = next((len(sp.z_list) for sp in data.specimens if sp is not None), 0)
+            state["static"] = StaticPack(data.specimens, types, n_patterns=z)
+        batch = BatchPack([data], state["static"], bgshift_enabled=bool(settings.get("BGSHIFT")))
+        return data, batch
+
+    def arrays(batch):
+        out = {k: np.array(getattr(batch, k), dtype=float).ravel() if getattr(batch, k, None) is not None else np.zeros(0)
+               for k, _ in _SLOT_ARRAYS}
+        out["maximum"] = np.array(batch.phase_i[:, 3], dtype=np.int64)
+        out["structure"] = [np.array(getattr(batch, k)).ravel() if getattr(batch, k, None) is not None else np.zeros(0)
+                            for k in _STRUCTURE_ARRAYS] + [np.delete(np.array(batch.phase_i), 3, axis=1).ravel()]
+        return out
+
+    def same_structure(a, b):
+        return all(u.shape == v.shape and np.array_equal(u, v) for u, v in zip(a["structure"], b["structure"]))
+
+    data0, batch0 = pack(x0)
+    import copy
+    template_data = copy.deepcopy(data0)                  # the model layer reuses its DataObjects between calls
+    base = arrays(batch0)
+    NM = base["matrices"].size
+    # matrix-pool ranges of the phases: [offset, offset + 2 r^2) -> packed phase index
+    pool_owner = np.full(NM, -1, dtype=np.int64)
+    for p, row in enumerate(batch0.phase_i):
+        if row[4] & 1 and not row[4] & 8:
+            pool_owner[row[6]:row[6] + 2 * row[1] * row[1]] = p
+    model_driven = batch0.prob_model if batch0.prob_model is not None else np.zeros(len(batch0.phase_i), dtype=np.int32)
+    rows, bound_by = [], {}
+    auto = np.zeros(len(batch0.phase_i), dtype=np.uint8)
+    for i in range(d):
+        lo, hi = bounds[i]
+        step = 0.25 * (hi - x0[i]) if (hi - x0[i]) >= (x0[i] - lo) else -0.25 * (x0[i] - lo)
+        if step == 0.0:
+            raise ValueError("refinable %r has an empty range" % (names[i],))
+        xa, xb = x0.copy(), x0.copy()
+        xa[i] += step
+        xb[i] += 2.0 * step
+        A, B = arrays(pack(xa)[1]), arrays(pack(xb)[1])
+        if not (same_structure(base, A) and same_structure(base, B)):
+            raise NotImplementedError("refinable %r changes the structure of the packed mixture" % (names[i],))
+        da, db = xa[i] - x0[i], xb[i] - x0[i]
+        for key, target in _SLOT_ARRAYS:
+            v0, va, vb = base[key], A[key], B[key]
+            for idx in np.nonzero((va != v0) | (vb != v0))[0]:
+                if key == "matrices" and model_driven[pool_owner[idx]] != 0:
+                    continue                              # W / P of a model-driven phase: computed on the device
+                scale = (vb[idx] - v0[idx]) / db
+                if abs((va[idx] - v0[idx]) - scale * da) > 1e-9 * max(abs(v0[idx]), abs(vb[idx]), abs(scale * db)):
+                    what = "a probability matrix of a phase whose model was not named" if key == "matrices" else key
+                    raise NotImplementedError("refinable %r drives %s[%d] non-affinely" % (names[i], what, idx))
+                if abs(scale - 1.0) < 1e-12:
+                    scale = 1.0
+                offset = v0[idx] - scale * x0[i]
+                if abs(offset) < 1e-12 * max(abs(v0[idx]), 1e-300) or (scale == 1.0 and abs(offset) < 1e-15):
+                    offset = 0.0
+                slot = (target, int(idx))
+                if slot in bound_by:
+                    raise NotImplementedError("%s[%d] depends on the refinables %r and %r together" %
+                                              (key, idx, names[bound_by[slot]], names[i]))
+                bound_by[slot] = i
+                rows.append((i, target, int(idx), float(scale), float(offset)))
+        for p in np.nonzero((A["maximum"] != base["maximum"]) | (B["maximum"] != base["maximum"]))[0]:
+            avg = [arr["phase_d"][p * PHASE_D_STRIDE + 1] for arr in (base, A, B)]
+            if [int(factor * a) for a in avg] != [int(arr["maximum"][p]) for arr in (base, A, B)]:
+                raise NotImplementedError("refinable %r moves the CSDS maximum of phase %d in an unknown way" % (names[i], p))
+            auto[p] = 1
+    tmpl = PopulationTemplate.from_table(template_data, rows, bounds, names=names, csds_auto=auto, csds_factor=factor)
+    tmpl.get_data_object = annotated
+    # the table against the model layer at random solutions
+    rng = np.random.default_rng(seed)
+    for _ in range(int(verify)):
+        x = bounds[:, 0] + rng.uniform(0.0, 1.0, d) * (bounds[:, 1] - bounds[:, 0])
+        want = arrays(pack(x)[1])
+        got = tmpl.expand(x[np.newaxis, :])
+        for key, _ in _SLOT_ARRAYS:
+            g = np.array(got[key], dtype=float).ravel() if got.get(key) is not None else np.zeros(0)
+            w = want[key]
+            if key == "matrices":
+                keep = model_driven[pool_owner] == 0 if NM else np.zeros(0, dtype=bool)
+                g, w = g[keep], w[keep]
+            if g.shape != w.shape or not np.allclose(g, w, rtol=1e-10, atol=1e-300):
+                bad = int(np.argmax(np.abs(g - w))) if g.shape == w.shape and g.size else -1
+                raise NotImplementedError("binding table does not reproduce %s (entry %d) at a random solution: the "
+                                          "refinables interact" % (key, bad))
+        if not np.array_equal(got["phase_i"][:, 3], want["maximum"]):
+            raise NotImplementedError("binding table does not reproduce the CSDS maxima at a random solution")
+    return tmpl
+
+
+def template_from_refiner(refiner, mixture_model, **kwargs):
+    """``discover_template`` for a reference ``Refiner`` (refinement/refiner.py) and the ``Mixture`` MODEL it refines:
+    solutions go through ``refiner.get_data_object``; the probability model of the phase in slot (s, m) is read from
+    ``mixture_model.phase_matrix`` (mixture/models/mixture.py:87-89)."""
+    def phase_model(s, z, m):
+        phase = mixture_model.phase_matrix[s, ...].flatten()[m]
+        prob = getattr(phase, "probabilities", None) if phase is not None else None
+        return probability_model_of_object(prob) if prob is not None else None
+
+    x0 = np.array([r.value for r in refiner.refinables], dtype=float)
+    bounds = np.array(refiner.ranges, dtype=float)
+    names = [r.text_title for r in refiner.refinables]
+    return discover_template(refiner.get_data_object, x0, bounds, names=names, phase_model=phase_model, **kwargs)

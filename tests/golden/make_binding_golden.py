@@ -1,0 +1,100 @@
+"""Golden vectors for the binding table discovered from the reference's RUNNING model layer.
+Build container only.
+
+The reference's integration fixture is loaded through its unmodified model layer, a set of its refinables is switched
+on (the two R0G3 weight fractions the project ships with, basal spacings, C-length deviations, sigma*), and a reference
+``Refiner`` (refinement/refiner.py) is asked for the DataObject graph of solutions.  ``population.template_from_refiner``
+discovers the binding table by probing it.  Stored: the template graph carried into ``pyxrd_b200.data_objects``
+instances, the table, and -- for a set of random solutions -- what the REFERENCE makes of them: the packed arrays of
+``refiner.get_data_object(x)``, ``calculate_mixture`` residuals and ``get_optimized_residual`` (= ``refiner.get_residual``).
+
+    python tests/golden/make_binding_golden.py   ->   tests/golden/binding.pkl, tests/golden/binding.npz
+"""
+import copy
+import os
+import pickle
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import _live_models  # noqa: E402
+from make_fixture import FIXTURE, convert  # noqa: E402
+
+N_SOLUTIONS = 12
+
+
+def main():
+    ref = _live_models.load()
+    import pyxrd.project.models  # noqa: F401
+    from pyxrd.file_parsers.json_parser import JSONParser
+    from oracle import pyxrd_oracle_models as om
+    from pyxrd_b200 import packing
+    from pyxrd_b200.population import template_from_refiner
+    project = JSONParser.parse(FIXTURE)
+    mixture = project.mixtures[0]
+    chosen = 0
+    for node in mixture.refinement.refinables.iter_children():
+        r = node.object
+        if r.prop_descr is None or not r.refinable:
+            continue
+        if r.label in ("d001", "delta_c", "sigma_star", "F1", "F2"):
+            if r.label == "d001" and r.value_max - r.value_min > 1.0:      # the project leaves some at [0, 5]
+                r.value_min, r.value_max = 0.97 * r.value, 1.03 * r.value
+            r.refine = True
+            chosen += 1
+    mixture.refinement.refine_method_index = 0            # L BFGS B (any method: only the refiner's plumbing is used)
+    refiner = mixture.refinement.get_refiner()
+    tmpl = template_from_refiner(refiner, mixture, verify=4)
+    d = tmpl.n_params
+    print("refinables:", d, "of", chosen, "chosen; bindings:", len(tmpl.bindings))
+    rng = np.random.default_rng(2026)
+    bounds = tmpl.bounds()
+    xs = bounds[:, 0] + rng.uniform(0.0, 1.0, (N_SOLUTIONS, d)) * (bounds[:, 1] - bounds[:, 0])
+    out = {"bindings": tmpl.bindings, "bounds": bounds, "names": np.array([r.name for r in tmpl.refinables]),
+           "csds_auto": tmpl.csds_auto if tmpl.csds_auto is not None else np.zeros(0, dtype=np.uint8),
+           "csds_factor": np.array(tmpl.csds_factor), "x": xs, "x0": np.array([r.value for r in refiner.refinables], dtype=float)}
+    keys = ("phase_i", "phase_d", "comp_d", "atom_d", "prob_params", "fractions", "scales", "bgshifts")
+    packed = {k: [] for k in keys}
+    residuals, optimised, valid = [], [], []
+    start = [np.array(getattr(tmpl.mixture, k), dtype=float) for k in ("fractions", "scales", "bgshifts")]
+    for x in xs:
+        data = tmpl.get_data_object(x)
+        # the reference keeps ONE MixtureData per mixture and its optimiser leaves its result in it
+        # (mixture.py:206-211): every solution starts from the fractions / scales of the template
+        data.fractions, data.scales, data.bgshifts = [v.copy() for v in start]
+        batch = packing.BatchPack([data], tmpl.static)
+        for k in keys:
+            packed[k].append(np.array(getattr(batch, k)))
+        valid.append([[bool(p.valid_probs) for p in sp.phases[0]] for sp in data.specimens])
+        work = copy.deepcopy(data)
+        for sp in work.specimens:
+            for p in sp.phases[0]:
+                p.prob_model = None                       # the reference computes with the model layer's own W, P
+        ref.mixture.calculate_mixture(work)
+        residuals.append(np.array(work.residuals, dtype=float))
+        optimised.append(float(refiner.get_residual(x)[0]))
+    for k in keys:
+        out["packed_" + k] = np.array(packed[k])
+    out["valid_probs"] = np.array(valid)
+    out["residuals"] = np.array(residuals)
+    out["optimised"] = np.array(optimised)
+    refiner.apply_solution(out["x0"])
+    with open(os.path.join(HERE, "binding.pkl"), "wb") as f:
+        pickle.dump(convert(tmpl.mixture, {}), f, protocol=4)
+    np.savez_compressed(os.path.join(HERE, "binding.npz"), **out)
+    print("residuals[:3]", out["residuals"][:3, 0], "optimised[:3]", out["optimised"][:3])
+    # the device models must give the model layer's matrices: checked here with the oracle's models
+    data = tmpl.get_data_object(xs[0])
+    for sp in data.specimens:
+        for p in sp.phases[0]:
+            W, P, ok = om.probabilities(om.PROB_CODES[p.prob_model], p.G, p.prob_params)
+            assert np.array_equal(W, p.W) and np.array_equal(P, p.P) and ok == bool(p.valid_probs)
+
+
+if __name__ == "__main__":
+    main()

@@ -276,3 +276,23 @@ def test_more_than_65535_patterns_in_one_batch(ctx):
     res = tmpl.residuals(x)
     pick = np.array([0, 5461, 5462, 5999])
     assert np.isfinite(res).all() and np.array_equal(res[pick], tmpl.residuals(x[pick]))
+
+
+def test_table_discovered_from_the_reference_model_layer(ctx):
+    """tests/golden/binding.*: the table was discovered by probing the reference's RUNNING model layer (its integration
+    fixture, 36 refinables); here the device evaluates the 12 stored solutions from the table alone and must agree with
+    what the reference computed for the graphs its MVC built: calculate_mixture residuals at 1e-9, get_optimized_residual
+    (= Refiner.get_residual) within the optimiser contract"""
+    from test_binding_golden import reference_binding
+    tmpl, g = reference_binding()
+    x = g["x"]
+    res = tmpl.residuals(x)
+    assert rel_err(res, g["residuals"]) < RTOL
+    opt = tmpl.optimized_residuals(x)
+    assert np.all(opt <= g["optimised"] * (1.0 + OPT_RTOL) + 1e-9), (opt, g["optimised"])
+    # W, P, valid_probs of the model-driven phases as the model layer had them
+    pis = tmpl.phase_intensities(x[:3])
+    for k in range(3):
+        for s in range(len(pis[k])):
+            for m in range(pis[k][s].shape[0]):
+                assert bool(pis[k][s][m].any()) == bool(g["valid_probs"][k][s][m])
