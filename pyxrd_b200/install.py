@@ -47,13 +47,66 @@ _IMPORT_SITES = [
 _saved = []
 
 
-def install(import_reference=True):
-    """Rebind; returns the list of (module, name) pairs that were replaced."""
+def _generation_evaluator(original):
+    """``RefineAsyncHelper.do_async_evaluation`` (refinement/refine_async_helper.py:16-23) for the default residual
+    path: the generation's solutions are evaluated together from the refiner's binding table
+    (``population.template_from_refiner``, discovered once per refiner) instead of one MVC round trip + one task each.
+    Custom eval / data functions, refinements a table cannot express and failures of the discovery keep the reference's
+    own loop."""
+    import logging
+    import numpy as np
+    logger = logging.getLogger(__name__)
+
+    def do_async_evaluation(self, iter_func, eval_func=None, data_func=None, result_func=None):
+        refiner = getattr(self, "refiner", None)
+        template = None
+        if refiner is not None and eval_func is None and data_func is None:
+            template = getattr(refiner, "_b200_template", None)
+            if template is None:
+                try:
+                    from .population import mixture_model_of, template_from_refiner
+                    template = template_from_refiner(refiner, mixture_model_of(refiner))
+                except Exception as error:          # NotImplementedError: not expressible; anything else: stay safe
+                    logger.info("pyxrd_b200: generations of this refinement stay on the per-trial path (%s)", error)
+                    template = False
+                refiner._b200_template = template
+        if not template:
+            return original(self, iter_func, eval_func, data_func, result_func)
+        solutions = []
+        for solution in iter_func():
+            solutions.append(solution)
+            if self._user_cancelled():
+                break
+        if solutions:
+            values = template.optimized_residuals(np.array([np.asarray(s, dtype=float) for s in solutions]))
+            report = result_func if result_func is not None else refiner.update
+            for solution, value in zip(solutions, values):
+                report(solution, np.array([value]))      # get_optimized_residual returns a 1-element array
+        return solutions
+
+    return do_async_evaluation
+
+
+def install(import_reference=True, generations=True, calculations=True):
+    """Rebind; returns the list of (module, name) pairs that were replaced.  ``generations``: also evaluate the
+    generations of the population methods (CMA-ES, MPSO, PS-CMA-ES, brute force) from a binding table;
+    ``calculations=False`` leaves ``pyxrd.calculations.*`` alone (only the generation evaluator is installed)."""
     import pyxrd_b200.calculations as ours
     if _saved:
         return [(m.__name__, n) for m, n, _ in _saved]
+    if generations:
+        try:
+            helper = importlib.import_module("pyxrd.refinement.refine_async_helper") if import_reference \
+                else sys.modules.get("pyxrd.refinement.refine_async_helper")
+            cls = getattr(helper, "RefineAsyncHelper", None)
+            if cls is not None:
+                old = cls.__dict__["do_async_evaluation"]
+                _saved.append((cls, "do_async_evaluation", old))
+                cls.do_async_evaluation = _generation_evaluator(old)
+        except Exception:
+            pass
     replaced = {}
-    for ref_name, (our_name, names) in _TARGETS.items():
+    for ref_name, (our_name, names) in (_TARGETS.items() if calculations else ()):
         mod = sys.modules.get(ref_name)
         if mod is None and import_reference:
             try:

@@ -166,10 +166,16 @@ class PopulationTemplate(object):
     def bounds(self):
         return np.array([[r.minimum, r.maximum] for r in self.refinables])
 
+    clip_to_bounds = False      # discovered templates: the reference's wrappers clamp a value to its range
+                                # (refinables/wrapper.py:101) before the model layer sees it
+
     def _x(self, x):
         x = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=float)))
         if x.shape[1] != self.n_params:
             raise ValueError("x has %d columns, the template has %d refinables" % (x.shape[1], self.n_params))
+        if self.clip_to_bounds:
+            b = self.bounds()
+            x = np.ascontiguousarray(np.clip(x, b[:, 0], b[:, 1]))
         return x
 
     def expand(self, x):
@@ -399,6 +405,7 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
             auto[p] = 1
     tmpl = PopulationTemplate.from_table(template_data, rows, bounds, names=names, csds_auto=auto, csds_factor=factor)
     tmpl.get_data_object = annotated
+    tmpl.clip_to_bounds = True
     # the table against the model layer at random solutions
     rng = np.random.default_rng(seed)
     for _ in range(int(verify)):
@@ -433,3 +440,22 @@ def template_from_refiner(refiner, mixture_model, **kwargs):
     bounds = np.array(refiner.ranges, dtype=float)
     names = [r.text_title for r in refiner.refinables]
     return discover_template(refiner.get_data_object, x0, bounds, names=names, phase_model=phase_model, **kwargs)
+
+
+def mixture_model_of(refiner):
+    """the ``Mixture`` MODEL a reference ``Refiner`` works on: the refiner only holds ``data_callback = lambda:
+    self.mixture.data_object`` (refinement/refinement.py:118-127), so the model is taken from that closure, or found
+    through the project of the phases listed in ``refiner.metadata``"""
+    callback = getattr(refiner, "data_callback", None)
+    for cell in getattr(callback, "__closure__", None) or ():
+        owner = cell.cell_contents
+        mixture = getattr(owner, "mixture", None)
+        if mixture is not None and hasattr(mixture, "phase_matrix"):
+            return mixture
+    phases = (getattr(refiner, "metadata", None) or {}).get("phases") or []
+    for phase in phases:
+        project = getattr(phase, "parent", None)
+        for mixture in getattr(project, "mixtures", None) or []:
+            if any(p is phase for p in mixture.phases):
+                return mixture
+    raise LookupError("cannot find the Mixture model of this refiner")

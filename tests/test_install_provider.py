@@ -69,3 +69,51 @@ def test_install_rebinds_reference_modules():
     finally:
         inst.uninstall()
     assert ref.mixture.get_optimized_residual is original
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="needs the reference tree (build container only)")
+def test_generations_of_a_reference_refinement_go_through_the_binding_table(monkeypatch):
+    """install(generations=True) inside the live reference: its brute-force run (custom_brute.py:36-56) hands the whole
+    grid to ONE PopulationTemplate call (table discovered from its own Refiner); the reference's bookkeeping
+    (Refiner.update -> history) receives the values.  The device evaluation itself is replaced by a stand-in here (no
+    GPU in the build container; its numerics are pinned by tests/test_gpu_population.py on binding.npz)."""
+    import threading
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import _live_models
+    _live_models.load()
+    import pyxrd.project.models  # noqa: F401
+    from pyxrd.file_parsers.json_parser import JSONParser
+    import pyxrd_b200.install as inst
+    from pyxrd_b200 import population
+    project = JSONParser.parse("/root/reference/test/test_mixture/test refinement.pyxrd")
+    mixture = project.mixtures[0]
+    n = 0
+    for node in mixture.refinement.refinables.iter_children():
+        r = node.object
+        if r.prop_descr is not None and r.refine:
+            n += 1
+            if n > 2:
+                r.refine = False
+    calls = []
+
+    def stand_in(self, x, ctx=None, **kwargs):
+        calls.append(np.array(x))
+        return np.array([1e-3 + float(np.sum((row - np.array([7.0, 18.0])) ** 2)) * 1e-6 for row in np.atleast_2d(x)])
+
+    monkeypatch.setattr(population.PopulationTemplate, "optimized_residuals", stand_in)
+    try:
+        inst.install(calculations=False)
+        mixture.refinement.refine_method_index = 3          # brute force
+        refiner = mixture.refinement.get_refiner()
+        assert [r.text_title for r in refiner.refinables] == ["Average CSDS", "Average CSDS"]
+        refiner.refine(stop=threading.Event())
+    finally:
+        inst.uninstall()
+    assert len(calls) == 1 and calls[0].shape == (121, 2)                      # 11 x 11 grid, one call
+    tmpl = refiner._b200_template
+    assert isinstance(tmpl, population.PopulationTemplate) and tmpl.clip_to_bounds
+    assert tmpl.csds_auto is not None and tmpl.csds_auto.sum() >= 2            # maximum follows the bound average
+    grid = calls[0]
+    best = grid[np.argmin(np.sum((grid - np.array([7.0, 18.0])) ** 2, axis=1))]
+    assert np.allclose(refiner.history.best_solution, best) and refiner.history.best_residual < 2e-3
