@@ -53,23 +53,13 @@ def _generation_evaluator(original):
     (``population.template_from_refiner``, discovered once per refiner) instead of one MVC round trip + one task each.
     Custom eval / data functions, refinements a table cannot express and failures of the discovery keep the reference's
     own loop."""
-    import logging
     import numpy as np
-    logger = logging.getLogger(__name__)
 
     def do_async_evaluation(self, iter_func, eval_func=None, data_func=None, result_func=None):
         refiner = getattr(self, "refiner", None)
         template = None
         if refiner is not None and eval_func is None and data_func is None:
-            template = getattr(refiner, "_b200_template", None)
-            if template is None:
-                try:
-                    from .population import mixture_model_of, template_from_refiner
-                    template = template_from_refiner(refiner, mixture_model_of(refiner))
-                except Exception as error:          # NotImplementedError: not expressible; anything else: stay safe
-                    logger.info("pyxrd_b200: generations of this refinement stay on the per-trial path (%s)", error)
-                    template = False
-                refiner._b200_template = template
+            template = _refiner_template(refiner)
         if not template:
             return original(self, iter_func, eval_func, data_func, result_func)
         solutions = []
@@ -85,6 +75,37 @@ def _generation_evaluator(original):
         return solutions
 
     return do_async_evaluation
+
+
+def _refiner_template(refiner):
+    """the binding-table template of a reference Refiner (discovered once, cached on it); False if not expressible"""
+    import logging
+    template = getattr(refiner, "_b200_template", None)
+    if template is None:
+        try:
+            from .population import mixture_model_of, template_from_refiner
+            template = template_from_refiner(refiner, mixture_model_of(refiner))
+        except Exception as error:          # NotImplementedError: not expressible; anything else: stay safe
+            logging.getLogger(__name__).info("pyxrd_b200: this refinement stays on the per-trial path (%s)", error)
+            template = False
+        refiner._b200_template = template
+    return template
+
+
+def _lbfgsb_run(original):
+    """``RefineLBFGSBRun.run`` (refinement/methods/scipy_runs.py:35-52) with the d + 1 probes of every forward-difference
+    gradient in one device batch (``drivers.lbfgsb``: the same steps scipy's ``approx_grad`` takes)."""
+    def run(self, refiner, maxfun=15000, maxiter=15000, iprint=0, **kwargs):
+        template = _refiner_template(refiner)
+        if not template:
+            return original(self, refiner, maxfun=maxfun, maxiter=maxiter, iprint=iprint, **kwargs)
+        from .drivers import lbfgsb
+        solution, residual, info = lbfgsb(template, refiner.history.initial_solution, bounds=refiner.ranges, epsilon=1e-4,
+                                          maxfun=maxfun, maxiter=maxiter, callback=refiner.update)
+        refiner.update(solution, residual=residual)
+        return info
+
+    return run
 
 
 def install(import_reference=True, generations=True, calculations=True):
@@ -103,6 +124,16 @@ def install(import_reference=True, generations=True, calculations=True):
                 old = cls.__dict__["do_async_evaluation"]
                 _saved.append((cls, "do_async_evaluation", old))
                 cls.do_async_evaluation = _generation_evaluator(old)
+        except Exception:
+            pass
+        try:
+            runs = importlib.import_module("pyxrd.refinement.methods.scipy_runs") if import_reference \
+                else sys.modules.get("pyxrd.refinement.methods.scipy_runs")
+            cls = getattr(runs, "RefineLBFGSBRun", None)
+            if cls is not None:
+                old = cls.__dict__["run"]
+                _saved.append((cls, "run", old))
+                cls.run = _lbfgsb_run(old)
         except Exception:
             pass
     replaced = {}

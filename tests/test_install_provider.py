@@ -71,6 +71,7 @@ def test_install_rebinds_reference_modules():
     assert ref.mixture.get_optimized_residual is original
 
 
+@pytest.mark.filterwarnings("ignore")
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="needs the reference tree (build container only)")
 def test_generations_of_a_reference_refinement_go_through_the_binding_table(monkeypatch):
     """install(generations=True) inside the live reference: its brute-force run (custom_brute.py:36-56) hands the whole
@@ -95,11 +96,11 @@ def test_generations_of_a_reference_refinement_go_through_the_binding_table(monk
             n += 1
             if n > 2:
                 r.refine = False
-    calls = []
+    calls, steepness = [], [1e-6]
 
     def stand_in(self, x, ctx=None, **kwargs):
         calls.append(np.array(x))
-        return np.array([1e-3 + float(np.sum((row - np.array([7.0, 18.0])) ** 2)) * 1e-6 for row in np.atleast_2d(x)])
+        return np.array([1e-3 + float(np.sum((row - np.array([7.0, 18.0])) ** 2)) * steepness[0] for row in np.atleast_2d(x)])
 
     monkeypatch.setattr(population.PopulationTemplate, "optimized_residuals", stand_in)
     try:
@@ -117,3 +118,17 @@ def test_generations_of_a_reference_refinement_go_through_the_binding_table(monk
     grid = calls[0]
     best = grid[np.argmin(np.sum((grid - np.array([7.0, 18.0])) ** 2, axis=1))]
     assert np.allclose(refiner.history.best_solution, best) and refiner.history.best_residual < 2e-3
+    # the L BFGS B run (scipy_runs.py:35-52): every gradient = one call with d + 1 rows
+    del calls[:]
+    steepness[0] = 1e-2
+    monkeypatch.setattr(type(refiner), "update", lambda self, solution, residual=None, iteration=0: None)
+    try:
+        inst.install(calculations=False)
+        mixture.refinement.refine_method_index = 0
+        refiner = mixture.refinement.get_refiner()
+        refiner.refine(stop=threading.Event())
+    finally:
+        inst.uninstall()
+    assert len(calls) >= 2 and all(c.shape == (3, 2) for c in calls)
+    b = tmpl.bounds()
+    assert np.allclose(calls[-1][0], np.clip([7.0, 18.0], b[:, 0], b[:, 1]), atol=1e-2)     # the stand-in's minimum inside the ranges
