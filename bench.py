@@ -35,12 +35,25 @@ DEFAULT_CANDIDATES = {"c1": 4096, "c2": 2048, "c3": 64, "c4": 256, "c5": 1024}
 # ---------------------------------------------------------------------------------------
 # algorithmic work: flops per phase-pattern point
 # ---------------------------------------------------------------------------------------
-def work_per_point(G, r, n_terms, atoms):
+def structured_transitions(P, G):
+    """True if P (r x r, r > G) is zero outside the columns (I mod r/G) G + j of row I: the transition structure of
+    every Reichweite >= 2 model (base_models.py:243-261), for which the kernels take G instead of r MACs per state"""
+    P = np.asarray(P)
+    r = P.shape[0]
+    if G < 2 or r <= G or r % G:
+        return False
+    tails = r // G
+    I, J = np.indices(P.shape)
+    return bool(np.all(P[(J // G) != (I % tails)] == 0.0))
+
+
+def work_per_point(G, r, n_terms, atoms, structured=False):
     """flops of the algorithm the kernels execute (fma = 2, mul / add = 1), DESIGN.md §3:
     series per term: rank 1 scalar Horner 7; rank 2 Clenshaw on (trace, det) 15; otherwise the vector
-    Horner step with the REAL probability matrix, r*r real-x-complex MACs (4 flop) + r complex updates
-    (10 flop); transcendental equivalents as SURVEY.md §8(d): sincos 32, exp 20, erf 30."""
-    per_term = 7 if r == 1 else 15 if r == 2 else 4 * r * r + 10 * r
+    Horner step with the REAL probability matrix, r*r real-x-complex MACs (4 flop; r*G for a matrix with the
+    Reichweite >= 2 transition structure) + r complex updates (10 flop); transcendental equivalents as
+    SURVEY.md §8(d): sincos 32, exp 20, erf 30."""
+    per_term = 7 if r == 1 else 15 if r == 2 else 4 * r * (G if structured else r) + 10 * r
     series = n_terms * per_term + 16 * r
     factors = atoms * (32 + 8 + 2) + G * (20 + 32 + 12)
     return series + factors + 120
@@ -68,7 +81,7 @@ def mixture_work(mix):
                     continue
                 atoms = sum(len(c.layer_atoms) + len(c.interlayer_atoms) for c in ph.components)
                 n_terms = max(int(ph.CSDS.maximum) - 1, 0)
-                flops += X * work_per_point(ph.G, ph.P.shape[0], n_terms, atoms)
+                flops += X * work_per_point(ph.G, ph.P.shape[0], n_terms, atoms, structured_transitions(ph.P, ph.G))
                 points += X
     return flops, points
 

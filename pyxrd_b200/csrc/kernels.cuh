@@ -1142,7 +1142,11 @@ __device__ __forceinline__ bool phase_is_invalid(const BatchDev &bt, int pb, int
 // PPT points and the dependent FMA chains of the PPT points interleave.  Per-point tables are
 // padded by PX_TABLE_PAD doubles, so the loads of points beyond the end of a pattern are legal;
 // only the stores are guarded.
-template <int R, int G, int PPT, int TPB, int MINB>
+// DB: P has the structure every Reichweite >= 2 model produces (base_models.py:243-261): state I = (i1 .. iR) only
+// reaches the states (i2 .. iR, j), i.e. row I is zero outside the columns (I mod R/G) * G + j, j < G.  The host checks
+// it entry by entry (or knows it from the probability model) and the product y = P w then takes G instead of R
+// multiply-adds per state.
+template <int R, int G, int PPT, int TPB, int MINB, bool DB = false>
 __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
     constexpr int REPS = R / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1285,13 +1289,27 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
                 double ar[PPT], ai[PPT];
     #pragma unroll
                 for (int k = 0; k < PPT; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
+                if constexpr (DB) {
     #pragma unroll
-                for (int J = 0; J < R; ++J) {
-                    const double p = sP[I * R + J];
+                    for (int j = 0; j < G; ++j) {
+                        constexpr int TAILS = R / G;
+                        const int J = (I % TAILS) * G + j;      // compile-time: I and j are unrolled
+                        const double p = sP[I * R + J];
     #pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        ar[k] = fma(p, wr[J][k], ar[k]);
-                        ai[k] = fma(p, wi[J][k], ai[k]);
+                        for (int k = 0; k < PPT; ++k) {
+                            ar[k] = fma(p, wr[J][k], ar[k]);
+                            ai[k] = fma(p, wi[J][k], ai[k]);
+                        }
+                    }
+                } else {
+    #pragma unroll
+                    for (int J = 0; J < R; ++J) {
+                        const double p = sP[I * R + J];
+    #pragma unroll
+                        for (int k = 0; k < PPT; ++k) {
+                            ar[k] = fma(p, wr[J][k], ar[k]);
+                            ai[k] = fma(p, wi[J][k], ai[k]);
+                        }
                     }
                 }
     #pragma unroll

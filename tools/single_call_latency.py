@@ -6,7 +6,7 @@ from pyxrd_b200 import synthetic as syn
 import pyxrd_b200.calculations as calc
 from pyxrd_b200.batched import get_optimized_residuals
 
-for name in ("c1", "c2", "c4"):
+for name in (sys.argv[1:] or ["c1", "c2", "c4", "c3", "c5"]):
     cfg = syn.CONFIGS[name]
     mix = cfg.candidate(2024, 0)
     rng = np.random.default_rng(1)
