@@ -36,24 +36,28 @@ DEFAULT_CANDIDATES = {"c1": 4096, "c2": 2048, "c3": 64, "c4": 256, "c5": 1024}
 # algorithmic work: flops per phase-pattern point
 # ---------------------------------------------------------------------------------------
 def structured_transitions(P, G):
-    """True if P (r x r, r > G) is zero outside the columns (I mod r/G) G + j of row I: the transition structure of
-    every Reichweite >= 2 model (base_models.py:243-261), for which the kernels take G instead of r MACs per state"""
+    """1 if P (r x r, r > G) is zero outside the columns (I mod r/G) G + j of row I: the transition structure of
+    every Reichweite >= 2 model (base_models.py:243-261), for which the kernels take G instead of r MACs per state;
+    2 if r = G >= 2 and every row of P is the same (Reichweite 0): scalar series; else 0"""
     P = np.asarray(P)
     r = P.shape[0]
-    if G < 2 or r <= G or r % G:
-        return False
+    if G < 2 or r % G:
+        return 0
+    if r == G:
+        return 2 if bool(np.all(P == P[0])) else 0
     tails = r // G
     I, J = np.indices(P.shape)
-    return bool(np.all(P[(J // G) != (I % tails)] == 0.0))
+    return 1 if bool(np.all(P[(J // G) != (I % tails)] == 0.0)) else 0
 
 
-def work_per_point(G, r, n_terms, atoms, structured=False):
+def work_per_point(G, r, n_terms, atoms, structured=0):
     """flops of the algorithm the kernels execute (fma = 2, mul / add = 1), DESIGN.md §3:
     series per term: rank 1 scalar Horner 7; rank 2 Clenshaw on (trace, det) 15; otherwise the vector
     Horner step with the REAL probability matrix, r*r real-x-complex MACs (4 flop; r*G for a matrix with the
-    Reichweite >= 2 transition structure) + r complex updates (10 flop); transcendental equivalents as
+    Reichweite >= 2 transition structure) + r complex updates (10 flop), Reichweite 0 (equal rows): the rank-1 count;
+    transcendental equivalents as
     SURVEY.md §8(d): sincos 32, exp 20, erf 30."""
-    per_term = 7 if r == 1 else 15 if r == 2 else 4 * r * (G if structured else r) + 10 * r
+    per_term = 7 if (r == 1 or structured == 2) else 15 if r == 2 else 4 * r * (G if structured == 1 else r) + 10 * r
     series = n_terms * per_term + 16 * r
     factors = atoms * (32 + 8 + 2) + G * (20 + 32 + 12)
     return series + factors + 120

@@ -1142,11 +1142,14 @@ __device__ __forceinline__ bool phase_is_invalid(const BatchDev &bt, int pb, int
 // PPT points and the dependent FMA chains of the PPT points interleave.  Per-point tables are
 // padded by PX_TABLE_PAD doubles, so the loads of points beyond the end of a pattern are legal;
 // only the stores are guarded.
-// DB: P has the structure every Reichweite >= 2 model produces (base_models.py:243-261): state I = (i1 .. iR) only
-// reaches the states (i2 .. iR, j), i.e. row I is zero outside the columns (I mod R/G) * G + j, j < G.  The host checks
-// it entry by entry (or knows it from the probability model) and the product y = P w then takes G instead of R
-// multiply-adds per state.
-template <int R, int G, int PPT, int TPB, int MINB, bool DB = false>
+// STRUCT (the host checks the matrix entry by entry, or knows it from the probability model):
+//  1  P has the structure every Reichweite >= 2 model produces (base_models.py:243-261): state I = (i1 .. iR) only
+//     reaches the states (i2 .. iR, j), i.e. row I is zero outside the columns (I mod R/G) * G + j, j < G: the product
+//     y = P w takes G instead of R multiply-adds per state;
+//  2  every row of P is the same vector w (Reichweite 0, R0models.py:80-83): Q^n = 1 (w o phi)^T q^(n-1) with the
+//     complex SCALAR q = sum_J w_J phi_J, so the series is a scalar Horner recurrence whatever G is:
+//     sum_n c_n Q^n b = 1 * (sum_J w_J phi_J b_J) * sum_n c_n q^(n-1).
+template <int R, int G, int PPT, int TPB, int MINB, int STRUCT = 0>
 __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
     constexpr int REPS = R / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1206,7 +1209,38 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     for (int I = 0; I < R; ++I)
 #pragma unroll
         for (int k = 0; k < PPT; ++k) { yr[I][k] = 0.0; yi[I][k] = 0.0; }
-    if constexpr (R == 1) {
+    if constexpr (STRUCT == 2) {
+        constexpr int REPS2 = R / G;
+        double qr[PPT], qi[PPT], br[PPT], bi[PPT], sr[PPT], si[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) { qr[k] = 0.0; qi[k] = 0.0; br[k] = 0.0; bi[k] = 0.0; sr[k] = 0.0; si[k] = 0.0; }
+#pragma unroll
+        for (int J = 0; J < R; ++J) {
+            const double w = sP[J];                     // first row = every row
+            const int c = J / REPS2;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                qr[k] = fma(w, pr[c][k], qr[k]); qi[k] = fma(w, pim[c][k], qi[k]);
+                br[k] = fma(w, gr[c][k], br[k]); bi[k] = fma(w, gi[c][k], bi[k]);
+            }
+        }
+        for (int n = ntop; n >= 1; --n) {               // sigma = c_1 + q (c_2 + q (c_3 + ...))
+            const double cn = sCoef[n];
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const double nr = fma(sr[k], qr[k], fma(-si[k], qi[k], cn));
+                si[k] = fma(sr[k], qi[k], si[k] * qr[k]);
+                sr[k] = nr;
+            }
+        }
+#pragma unroll
+        for (int I = 0; I < R; ++I)
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {             // y_I = beta sigma
+                yr[I][k] = br[k] * sr[k] - bi[k] * si[k];
+                yi[I][k] = br[k] * si[k] + bi[k] * sr[k];
+            }
+    } else if constexpr (R == 1) {
         // scalar series: y = (sum_n c_n q^n) b, q = P00 phi, by Horner on the real coefficients (4 flop-pairs / term)
         const double p00 = sP[0];
         double qr[PPT], qi[PPT], sr[PPT], si[PPT];
@@ -1289,7 +1323,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
                 double ar[PPT], ai[PPT];
     #pragma unroll
                 for (int k = 0; k < PPT; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
-                if constexpr (DB) {
+                if constexpr (STRUCT == 1) {
     #pragma unroll
                     for (int j = 0; j < G; ++j) {
                         constexpr int TAILS = R / G;

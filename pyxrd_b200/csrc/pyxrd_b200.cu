@@ -60,7 +60,8 @@ struct PinBuf {
 
 struct RankClass {
     int rank = 0, G = 0;
-    bool db = false;           // every P of the class has the Reichweite >= 2 transition structure (k_phase_small<.., DB>)
+    int structure = 0;         // 1: every P of the class has the Reichweite >= 2 transition structure, 2: equal rows
+                               // (Reichweite 0): k_phase_small<.., STRUCT>
     int max_x = 0;
     int max_ntop_cap = 0;
     size_t first = 0;          // position of this class in the device job-id list
@@ -203,13 +204,13 @@ int set_smem(pyxrd_ctx *ctx, K kernel, size_t bytes) {
     return 0;
 }
 
-template <int R, int G, int PPT, int TPB, int MINB = 0, bool DB = false>
+template <int R, int G, int PPT, int TPB, int MINB = 0, int STRUCT = 0>
 int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     static_assert((PPT - 1) * TPB <= PX_TABLE_PAD, "table padding too small");
     const size_t smem = small_smem(R, G, rc.max_ntop_cap);
-    if (set_smem(ctx, k_phase_small<R, G, PPT, TPB, MINB, DB>, smem)) return 1;
+    if (set_smem(ctx, k_phase_small<R, G, PPT, TPB, MINB, STRUCT>, smem)) return 1;
     dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + TPB * PPT - 1) / (TPB * PPT)));
-    k_phase_small<R, G, PPT, TPB, MINB, DB><<<grid, TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
+    k_phase_small<R, G, PPT, TPB, MINB, STRUCT><<<grid, TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
     LAUNCH_CHECK("k_phase_small");
     return 0;
 }
@@ -255,12 +256,20 @@ int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_
 #define SMALL(R_, G_, PPT_, TPB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_>(ctx, rc, jobs_dev, njobs, bt)
 #define SMALLB(R_, G_, PPT_, TPB_, MINB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_, MINB_>(ctx, rc, jobs_dev, njobs, bt)
 #define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev, njobs, bt)
-    if (rc.db && ctx->use_structure) {
+    if (rc.structure == 2 && ctx->use_structure) {
+        // Reichweite 0 with G components: a scalar series whatever G is
+        if (rc.rank == 2 && rc.G == 2) return launch_small<2, 2, 4, 32, 16, 2>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 3 && rc.G == 3) return launch_small<3, 3, 2, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 4 && rc.G == 4) return launch_small<4, 4, 2, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 5 && rc.G == 5) return launch_small<5, 5, 1, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 6 && rc.G == 6) return launch_small<6, 6, 1, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
+    }
+    if (rc.structure == 1 && ctx->use_structure) {
         // structured transition matrices (Reichweite >= 2 models): G instead of R multiply-adds per state
         // (shapes from a sweep on B200: rank 8 one point per thread, 118 registers; two points per thread need 204)
-        if (rc.rank == 4 && rc.G == 2) return launch_small<4, 2, 2, 128, 0, true>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 8 && rc.G == 2) return launch_small<8, 2, 1, 128, 0, true>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 9 && rc.G == 3) return launch_small<9, 3, 1, 128, 0, true>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 4 && rc.G == 2) return launch_small<4, 2, 2, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 8 && rc.G == 2) return launch_small<8, 2, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 9 && rc.G == 3) return launch_small<9, 3, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
     }
     // (points per thread, threads per block, min blocks per SM) from sweeps on B200 (profiles/r1_summary.md)
     SMALLB(1, 1, 4, 32, 0); SMALLB(2, 2, 4, 32, 16); SMALLB(2, 1, 4, 32, 16);
@@ -585,13 +594,22 @@ int build_jobs(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, std::vector<int> &job_
         const int32_t *pi = d->phase_i + (size_t)p * PYXRD_PHASE_I_STRIDE;
         if (!(pi[4] & PYXRD_FLAG_VALID_PROBS) || (pi[4] & PYXRD_FLAG_RAW_PATTERN)) continue;
         const int G = pi[0], r = pi[1];
-        if (G < 2 || r <= G || r % G != 0) continue;
+        if (G < 2 || r % G != 0) continue;
         const int model = (d->prob_model && d->prob_params) ? d->prob_model[p] : PYXRD_PROB_FIXED;
         if (model != PYXRD_PROB_FIXED) {
-            structured[p] = (model == PYXRD_PROB_R2G2 || model == PYXRD_PROB_R3G2 || model == PYXRD_PROB_R2G3);
+            structured[p] = (model == PYXRD_PROB_R2G2 || model == PYXRD_PROB_R3G2 || model == PYXRD_PROB_R2G3) ? 1
+                            : model == PYXRD_PROB_R0 ? 2 : 0;
             continue;
         }
         const double *P = d->matrices + pi[6] + (size_t)r * r;
+        if (r == G) {                                  // Reichweite 0: every row equals the first
+            bool same = true;
+            for (int I = 1; I < r && same; ++I)
+                for (int J = 0; J < r; ++J)
+                    if (P[(size_t)I * r + J] != P[J]) { same = false; break; }
+            structured[p] = same ? 2 : 0;
+            continue;
+        }
         const int tails = r / G;
         bool ok = true;
         for (int I = 0; I < r && ok; ++I)
@@ -615,14 +633,14 @@ int build_jobs(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, std::vector<int> &job_
                     if (pb >= 0 && !(pi[4] & PYXRD_FLAG_VALID_PROBS)) pb = -1;    // invalid probabilities -> zeros
                     job_pb[j] = pb;
                     if (pb < 0 || ctx->h_npts[s] == 0) continue;
-                    auto key = std::make_pair(pi[1] * 2 + (structured[pb] ? 1 : 0), pi[0]);
+                    auto key = std::make_pair(pi[1] * 4 + structured[pb], pi[0]);
                     auto it = class_of.find(key);
                     if (it == class_of.end()) {
                         it = class_of.emplace(key, (int)ctx->classes.size()).first;
                         ctx->classes.emplace_back();
                         ctx->classes.back().rank = pi[1];
                         ctx->classes.back().G = pi[0];
-                        ctx->classes.back().db = structured[pb] != 0;
+                        ctx->classes.back().structure = structured[pb];
                     }
                     RankClass &rc = ctx->classes[it->second];
                     rc.jobs.push_back((int)j);
