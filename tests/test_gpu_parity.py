@@ -519,3 +519,27 @@ def test_reference_integration_fixture(calc):
         assert rel_err(work.fractions, g["opt_fractions"]) < 1e-3
     finally:
         settings.MIXTURE_OPTIMIZER = "device"
+
+
+def test_dense_and_structured_matrices_of_the_same_rank(calc):
+    """ranks 4 / 8 / 9 / 16: a P with the Reichweite >= 2 transition structure takes the structured kernels
+    (k_phase_small<.., STRUCT = 1>), a dense P of the same rank the dense ones (vector Horner, DMMA for 8 / 16);
+    Reichweite 0 with 3 - 6 components takes the scalar series, a P of that rank with unequal rows the dense kernel"""
+    types = syn.atom_types()
+    rng = np.random.default_rng(77)
+    theta = syn.theta_grid(3.0, 30.0, 0.05)
+    kinds = ["illite", "smectite_ad", "chlorite", "smectite_eg", "kaolinite", "illite"]
+    phases = []
+    for G, R in ((2, 2), (2, 3), (3, 2), (2, 4)):
+        for dense in (False, True):
+            comps = [syn.make_component(types, kinds[c], rng) for c in range(G)]
+            W, P = syn.make_probabilities(rng, G, R, dense=dense)
+            phases.append(syn.make_phase(comps, W, P, syn.make_csds(7.0 + G + R), sigma_star=5.0))
+    for G in (3, 4, 5, 6):
+        for equal_rows in (True, False):
+            comps = [syn.make_component(types, kinds[c], rng) for c in range(G)]
+            W, P = syn.make_probabilities(rng, G, 0) if equal_rows else syn.make_probabilities(rng, G, 1)
+            phases.append(syn.make_phase(comps, W, P, syn.make_csds(9.0), sigma_star=4.0))
+    spec = syn.make_specimen(theta, phases, syn.make_goniometer("cu_pair"))
+    mix = _with_observed(syn.make_mixture([spec], len(phases)))
+    _oracle_vs_device(calc, mix)
