@@ -1908,29 +1908,34 @@ __global__ void __launch_bounds__(PX_WL_TPB) k_wavelength_pass(StaticDev st, Bat
 
 // ---------------------------------------------------------------------------------
 // mixture: total = scale * sum_p frac_p I_p + bg * C ; Rp = 100 sum|obs - total| / sum|obs|
-// grid (candidates, S), one block per (candidate, specimen), 4 points in flight per thread
+// 4 points in flight per thread
 // ---------------------------------------------------------------------------------
 #define PX_RES_TPB 256
 #define PX_RES_PPT 4
-__global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, BatchDev bt, int k0, int want_scaled) {
-    const int s = blockIdx.y, k = k0 + blockIdx.x;      // candidates on x: grid.y stops at 65535
+// grid (candidates, 1024-point tiles, S): a block owns one tile of one (candidate, specimen) for all Z patterns and M
+// phases (a streaming pass like k_wavelength_pass; one block per (candidate, specimen) looping over the whole pattern
+// was latency-bound: 91 us against 50 us for c2).  Its sum |obs - total| goes to partial[((k - k0) S + s) ntiles + tile];
+// k_residual_finish adds the tiles in order (deterministic).
+__global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, BatchDev bt, int k0, int want_scaled,
+                                                                double *__restrict__ partial) {
+    const int s = blockIdx.z, k = k0 + blockIdx.x, tile = blockIdx.y;       // candidates on x: grid.y / z stop at 65535
     const int X = st.spec_npts[s], Z = st.Z, M = bt.M;
-    const long long soff = st.spec_off[s];
-    const double *I = bt.intensities + (long long)k * bt.cand_stride + (long long)M * Z * soff;
-    double *scaled = (want_scaled && bt.scaled) ? bt.scaled + (long long)k * bt.cand_stride + (long long)M * Z * soff : nullptr;
-    double *tot = bt.totals + ((long long)k * st.sumX + soff) * Z;
-    const double *obs = st.observed + (long long)Z * soff;
-    const unsigned char *sel = st.selected + soff;
-    const double *corr = st.corr + soff;
-    const double scale = bt.scales[k * st.S + s], bg = bt.bgshifts[k * st.S + s];
-    const double *frac = bt.fractions + (long long)k * M;
+    const int xb = tile * (PX_RES_TPB * PX_RES_PPT) + threadIdx.x;
     double num = 0.0;
-    const int n = Z * X;
-    for (int z = 0; z < Z; ++z) {
-        const double *Iz = I + (long long)z * X;
-        double *Sz = scaled ? scaled + (long long)z * X : nullptr;
+    if (tile * (PX_RES_TPB * PX_RES_PPT) < X) {
+        const long long soff = st.spec_off[s];
+        const double *I = bt.intensities + (long long)k * bt.cand_stride + (long long)M * Z * soff;
+        double *scaled = (want_scaled && bt.scaled) ? bt.scaled + (long long)k * bt.cand_stride + (long long)M * Z * soff : nullptr;
+        double *tot = bt.totals + ((long long)k * st.sumX + soff) * Z;
+        const double *obs = st.observed + (long long)Z * soff;
+        const unsigned char *sel = st.selected + soff;
+        const double *corr = st.corr + soff;
+        const double scale = bt.scales[k * st.S + s], bg = bt.bgshifts[k * st.S + s];
+        const double *frac = bt.fractions + (long long)k * M;
         const long long pstride = (long long)Z * X;                   // phase stride inside [M][Z][X]
-        for (int x0 = threadIdx.x; x0 < X; x0 += PX_RES_TPB * PX_RES_PPT) {
+        for (int z = 0; z < Z; ++z) {
+            const double *Iz = I + (long long)z * X;
+            double *Sz = scaled ? scaled + (long long)z * X : nullptr;
             double acc[PX_RES_PPT];
 #pragma unroll
             for (int u = 0; u < PX_RES_PPT; ++u) acc[u] = 0.0;
@@ -1939,17 +1944,17 @@ __global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, B
                 const double *Ip = Iz + p * pstride;
                 double iv[PX_RES_PPT];
 #pragma unroll
-                for (int u = 0; u < PX_RES_PPT; ++u) iv[u] = (x0 + u * PX_RES_TPB < X) ? Ip[x0 + u * PX_RES_TPB] : 0.0;
+                for (int u = 0; u < PX_RES_PPT; ++u) iv[u] = (xb + u * PX_RES_TPB < X) ? Ip[xb + u * PX_RES_TPB] : 0.0;
 #pragma unroll
                 for (int u = 0; u < PX_RES_PPT; ++u) {
                     const double v = __dmul_rn(__dmul_rn(fp, iv[u]), scale);
-                    if (Sz && x0 + u * PX_RES_TPB < X) Sz[p * pstride + x0 + u * PX_RES_TPB] = v;
+                    if (Sz && xb + u * PX_RES_TPB < X) Sz[p * pstride + xb + u * PX_RES_TPB] = v;
                     acc[u] = __dadd_rn(acc[u], v);
                 }
             }
 #pragma unroll
             for (int u = 0; u < PX_RES_PPT; ++u) {
-                const int x = x0 + u * PX_RES_TPB;
+                const int x = xb + u * PX_RES_TPB;
                 if (x >= X) continue;
                 const double t = __dadd_rn(acc[u], __dmul_rn(bg, corr[x]));
                 tot[(long long)z * X + x] = t;
@@ -1964,12 +1969,21 @@ __global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, B
     if (threadIdx.x < 32) {
         num = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
         for (int o = 16; o > 0; o >>= 1) num += __shfl_down_sync(0xffffffffu, num, o);
-        if (threadIdx.x == 0) {
-            const double den = st.derived[s * 8 + 3];
-            // no observations -> 0.0 (mixture.py:247-251)
-            bt.residuals[(long long)k * (st.S + 1) + 1 + s] = (n > 0) ? num / den * 100.0 : 0.0;
-        }
+        if (threadIdx.x == 0) partial[((long long)(k - k0) * st.S + s) * gridDim.y + tile] = num;
     }
+}
+
+// residual of every (candidate, specimen) from the tile sums, in tile order
+__global__ void k_residual_finish(StaticDev st, BatchDev bt, int k0, int k1, int ntiles, const double *__restrict__ partial) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int S = st.S;
+    if (i >= (k1 - k0) * S) return;
+    const int k = k0 + i / S, s = i % S;
+    double num = 0.0;
+    for (int t = 0; t < ntiles; ++t) num += partial[(long long)i * ntiles + t];
+    const double den = st.derived[s * 8 + 3];
+    const int n = st.Z * st.spec_npts[s];
+    bt.residuals[(long long)k * (S + 1) + 1 + s] = (n > 0) ? num / den * 100.0 : 0.0;     // no observations -> 0.0 (mixture.py:247-251)
 }
 
 // ---------------------------------------------------------------------------------

@@ -128,7 +128,7 @@ struct pyxrd_ctx {
     DevBuf d_tmpl;           // template candidate + solution vectors + binding table of a device-expanded population
     PinBuf h_tmpl;
     const int *jobids_dev = nullptr;   // inside d_blob
-    DevBuf d_ph_nu, d_ph_uz, d_ph_uend, d_ph_useg;
+    DevBuf d_ph_nu, d_ph_uz, d_ph_uend, d_ph_useg, d_partial;
     DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_phase_valid, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
     int residual_method = PYXRD_RESIDUAL_RP;   // settings.RESIDUAL_METHOD (mixture.py:22-27,89)
     DevBuf d_selpos, d_selcount;
@@ -361,7 +361,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_invsin, &ctx->d_stl,
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob, &ctx->d_tmpl,
-                      &ctx->d_ph_nu, &ctx->d_ph_uz, &ctx->d_ph_uend, &ctx->d_ph_useg, &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
+                      &ctx->d_partial, &ctx->d_ph_nu, &ctx->d_ph_uz, &ctx->d_ph_uend, &ctx->d_ph_useg, &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
                       &ctx->d_res, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
@@ -868,8 +868,14 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed)
     if (timed) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (k1 > k0) {
         dim3 grid(k1 - k0, ctx->st.S);
-        k_mixture_residual<<<grid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled);
+        const int tile = PX_RES_TPB * PX_RES_PPT, ntiles = std::max(1, (ctx->st.maxX + tile - 1) / tile);
+        CK(ctx->d_partial.ensure(sizeof(double) * (size_t)(k1 - k0) * ctx->st.S * ntiles));
+        dim3 tgrid(k1 - k0, ntiles, ctx->st.S);
+        k_mixture_residual<<<tgrid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled, ctx->d_partial.as<double>());
         LAUNCH_CHECK("k_mixture_residual");
+        k_residual_finish<<<((k1 - k0) * ctx->st.S + 127) / 128, 128, 0, ctx->stream>>>(ctx->st, bt, k0, k1, ntiles,
+                                                                                      ctx->d_partial.as<double>());
+        LAUNCH_CHECK("k_residual_finish");
         if (ctx->residual_method == PYXRD_RESIDUAL_RPDER) {
             // the Rp kernel above has produced the totals; its residuals are replaced
             int maxn = 0;
