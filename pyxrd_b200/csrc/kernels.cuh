@@ -2544,6 +2544,47 @@ __device__ __forceinline__ void opt_solve_dispatch(OptSmem &sm, int S, int lm_it
 
 // TPB = 256 for populations that fit the machine in one wave (shortest chain per candidate), 128 for larger ones
 // (twice as many candidates in flight: the Newton steps, which keep four warps busy, overlap better)
+// Warp totals of N accumulators with ~N instead of 5 N shuffles: at every butterfly step a lane keeps one half of its
+// values and hands the other half to its partner (lanes with bit O set keep the upper half).  After the five steps a
+// lane holds ceil(N / 32) totals; opt_store_reduced unwinds which entries they are and writes them to out[0 .. N).
+template <int N, int COUNT, int O>
+__device__ __forceinline__ void opt_warp_reduce_many(double (&acc)[N], int lane) {
+    constexpr int HALF = (COUNT + 1) / 2;
+    const bool upper = (lane & O) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const double a = acc[i];
+        const double b = (i + HALF < COUNT) ? acc[i + HALF] : 0.0;
+        const double send = upper ? a : b, keep = upper ? b : a;
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+    }
+    if constexpr (O > 1) opt_warp_reduce_many<N, HALF, O / 2>(acc, lane);
+}
+
+// level (COUNT, O) of the unwinding: `base` = offset accumulated by the finer levels is added AFTER this level's own
+// offset is known, so recurse first to the finest level and add offsets on the way back
+template <int N, int COUNT, int O>
+__device__ __forceinline__ void opt_store_reduced(const double (&acc)[N], int lane, int, bool, double *out) {
+    // sizes of the five levels
+    constexpr int C0 = COUNT, H0 = (C0 + 1) / 2, H1 = (H0 + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2, H4 = (H3 + 1) / 2;
+    static_assert(O == 16, "unwinds the five steps 16, 8, 4, 2, 1");
+#pragma unroll
+    for (int j = 0; j < H4; ++j) {
+        // index inside the input of step 1 (size H3), then step 2 (H2), 4 (H1), 8 (H0), 16 (C0)
+        int idx = j + ((lane & 1) ? H4 : 0);
+        bool ok = idx < H3;
+        idx += (lane & 2) ? H3 : 0;
+        ok = ok && idx < H2;
+        idx += (lane & 4) ? H2 : 0;
+        ok = ok && idx < H1;
+        idx += (lane & 8) ? H1 : 0;
+        ok = ok && idx < H0;
+        idx += (lane & 16) ? H0 : 0;
+        ok = ok && idx < C0;
+        if (ok) out[idx] = acc[j];
+    }
+}
+
 template <int MB, int TPB>
 __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev st, BatchDev bt, OptParams op,
                                                                  double *solutions, double *opt_residuals) {
@@ -2633,12 +2674,8 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
             if (tid == 0) sm.prof[0] += clock64() - tG;
             tG = clock64();
 #endif
-#pragma unroll
-            for (int a = 0; a < NACC; ++a) {
-                double vsum = acc[a];
-                for (int o2 = 16; o2 > 0; o2 >>= 1) vsum += __shfl_down_sync(0xffffffffu, vsum, o2);
-                if (lane == 0) sm.red[warp][a] = vsum;
-            }
+            opt_warp_reduce_many<NACC, NACC, 16>(acc, lane);
+            opt_store_reduced<NACC, NACC, 16>(acc, lane, 0, true, sm.red[warp]);
             __syncthreads();
             if (tid < NACC) {
                 double vsum = 0.0;
