@@ -13,7 +13,6 @@ inputs (``numpy.random.default_rng`` / PCG64 streams are platform independent).
 """
 from __future__ import annotations
 
-import math
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np

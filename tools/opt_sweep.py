@@ -2,7 +2,6 @@
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
 from pyxrd_b200 import synthetic as syn
 import pyxrd_b200.calculations as calc
 from pyxrd_b200.batched import pack_population
