@@ -475,10 +475,11 @@ def _random_mixture(rng, types):
 def test_random_mixtures_against_the_oracle(calc):
     """32 random mixtures: 1-3 ragged specimens, 1-2 patterns each, 1-4 phases of random (G, R) / CSDS / flags, None phases,
     invalid probabilities, both divergence modes, absorption, monochromator, empty / single / double wavelength lists"""
-    rng = np.random.default_rng(20261020)
+    import os
+    rng = np.random.default_rng(int(os.environ.get("PYXRD_FUZZ_SEED", "20261020")))
     types = syn.atom_types()
     worst = 0.0
-    for _ in range(32):
+    for _ in range(int(os.environ.get("PYXRD_FUZZ_COUNT", "32"))):
         mix = _random_mixture(rng, types)
         ref = copy.deepcopy(mix)
         orc.calculate_mixture(ref)

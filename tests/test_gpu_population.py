@@ -60,8 +60,10 @@ def _template(name):
 
 @pytest.mark.parametrize("name,K", [("c1", 6), ("c2", 6), ("c4", 5), ("c5", 3), ("models", 12)])
 def test_population_matches_oracle_on_rebuilt_graphs(ctx, name, K):
+    import os
+    K = int(os.environ.get("PYXRD_FUZZ_COUNT", K))
     tmpl, refs = _template(name)
-    x = syn.sample_solutions(refs, 5, K)
+    x = syn.sample_solutions(refs, int(os.environ.get("PYXRD_FUZZ_SEED", "5")), K)
     res = tmpl.residuals(x)
     pis = tmpl.phase_intensities(x)
     assert res.shape == (K, 1 + tmpl.static.S)
