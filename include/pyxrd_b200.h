@@ -277,9 +277,19 @@ int pyxrd_optimize_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, int refine
 /* ---- leaf helpers (GUI previews; also the unit-level parity hooks) ---------------- */
 /* get_atomic_scattering_factor (atoms.py:13-38): s -> asf, n points, one atom type */
 int pyxrd_leaf_asf(pyxrd_ctx *ctx, const double *s, int64_t n, const double *atom_type, double *out);
+/* pyxrd/calculations/statistics.py on plain arrays (GUI pattern statistics, specimen/models/statistics.py:16,115-118):
+ * kind 0 Rp (:22-27), 1 Rpw (:50-68), 2 R_squared (:12-20), 3 Rpe with extra = number of parameters (:70-79),
+ * 4 Rphase with the phase pattern in `phase` (:81-100); calc / phase may be NULL where the statistic does not use them */
+int pyxrd_leaf_statistic(pyxrd_ctx *ctx, int kind, const double *exp, const double *calc, const double *phase, int64_t n,
+                         double extra, double *out);
+/* derive() = np.gradient(smooth(pattern, 15)) (statistics.py:29-41, math_tools.py:46-99: 31-tap Blackman window with
+ * reflected ends); smooth_only != 0: smooth_pattern().  n >= 31, else the reference's ValueError text is the error */
+int pyxrd_leaf_derive(pyxrd_ctx *ctx, const double *pattern, int64_t n, int smooth_only, double *out);
 /* get_lorentz_polarisation_factor (goniometer.py:15-34) */
 int pyxrd_leaf_lpf(pyxrd_ctx *ctx, const double *theta, int64_t n, double sigma_star,
                    double soller1, double soller2, double mcr_2theta, double *out);
+/* get_T (goniometer.py:20-25): the Lorentz part of that factor */
+int pyxrd_leaf_lorentz(pyxrd_ctx *ctx, const double *theta, int64_t n, double sigma_star, double soller1, double soller2, double *out);
 /* calculate_distribution (CSDS.py:13-46): out_arr[maximum+1], out_mean[1];
  * progression factors (phases.py:147-151) into out_coef[maximum+2] (index = power of Q) */
 int pyxrd_leaf_csds(pyxrd_ctx *ctx, const double *csds6, int minimum, int maximum,

@@ -362,6 +362,38 @@ def Rpw(exp, calc, *args):
         return 0
 
 
+def R_squared(exp, calc, *args):
+    """statistics.py:12-20."""
+    avg = sum(exp) / exp.size
+    return 1 - (np.sum((exp - calc) ** 2) / np.sum((exp - avg) ** 2))
+
+
+def derive(pattern):
+    """statistics.py:35-41."""
+    return np.gradient(smooth_blackman(pattern, 15))
+
+
+def Rpe(exp, calc, num_params):
+    """statistics.py:70-79."""
+    return np.sqrt((exp.size - num_params) / np.sum(exp ** 2)) * 100
+
+
+def Rphase(exp, calc, phase):
+    """statistics.py:81-100."""
+    exp, calc, phase = np.ravel(exp), np.ravel(calc), np.ravel(phase)
+    sm1 = sm2 = 0
+    for e, c, p in zip(exp, calc, phase):
+        with np.errstate(all="ignore"):
+            t = (e - c) ** 2 * p / (e ** 2)
+        if not (np.isnan(t) or np.isinf(t)):
+            sm1 += t
+            sm2 += abs(p)
+    try:
+        return math.sqrt(sm1 / sm2) * 100
+    except Exception:
+        return 0
+
+
 _RESIDUALS = {"Rp": Rp, "Rpw": Rpw, "Rpder": Rpder}
 
 

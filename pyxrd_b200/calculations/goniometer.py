@@ -15,6 +15,14 @@ def get_S(soller1, soller2):
     return sqrt((soller1 * 0.5) ** 2 + (soller2 * 0.5) ** 2), soller1 * soller2
 
 
+def get_T(range_theta, sigma_star, soller1, soller2):
+    """goniometer.py:20-25."""
+    theta = np.asarray(range_theta, dtype=float)
+    ctx = default_context()
+    with ctx.lock:
+        return ctx.leaf_T(theta, sigma_star, soller1, soller2).reshape(theta.shape)
+
+
 def get_lorentz_polarisation_factor(range_theta, sigma_star, soller1, soller2, mcr_2theta):
     """goniometer.py:20-34."""
     theta = np.asarray(range_theta, dtype=float)

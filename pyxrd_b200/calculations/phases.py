@@ -59,3 +59,32 @@ def get_intensity(range_theta, range_stl, soller1, soller2, mcr_2theta, phase):
     if phase.type == "Phase" and not phase.valid_probs:
         return np.zeros_like(np.asarray(range_stl, dtype=float))
     return _single_phase_pattern(range_theta, range_stl, soller1, soller2, mcr_2theta, phase, with_lpf=True)
+
+
+def get_structure_factors(range_stl, G, comp_list):
+    """phases.py:20-39: structure factors and phase factors of the components, c128[X, G] each
+    (``components.get_factors`` per component, evaluated on the device)."""
+    from .components import get_factors
+    range_stl = np.asarray(range_stl, dtype=float)
+    shape = range_stl.shape + (G,)
+    SF = np.zeros(shape, dtype=np.complex128)
+    PF = np.zeros(shape, dtype=np.complex128)
+    for i, comp in enumerate(comp_list):
+        SF[:, i], PF[:, i] = get_factors(range_stl, comp)
+    return SF, PF
+
+
+def get_absolute_scale(components, CSDS_real_mean, W):
+    """phases.py:48-66: a dozen scalar operations on model constants (inside the batch path the prologue kernel does
+    them per phase, k_phase_prologue); first G diagonal entries of W, ``None`` components skipped, 0 if the mass is 0."""
+    W = np.diag(np.asarray(W, dtype=float))
+    mean_volume = mean_d001 = mean_density = 0.0
+    for i, comp in enumerate(components):
+        if comp is not None:
+            mean_volume += comp.volume * W[i]
+            mean_d001 += comp.d001 * W[i]
+            mean_density += (comp.weight * W[i] / comp.volume)
+        else:
+            logger.debug("- calc: get_absolute_scale reports: 'Zero observations found!'")
+    mean_mass = (CSDS_real_mean * mean_volume ** 2 * mean_density)
+    return mean_d001 / mean_mass if mean_mass != 0.0 else 0.0

@@ -871,8 +871,9 @@ __device__ __forceinline__ double lpf_point(const PhaseSmem *ps, double st, doub
     return T * (1.0 + ps->lpf_pol * c2t2) * inv_st;
 }
 
+// t_only: get_T (goniometer.py:20-25) instead of the whole factor
 __global__ void k_leaf_lpf(const double *theta, long long n, double sigma_star, double s1, double s2,
-                           double mcr, double *out) {
+                           double mcr, double *out, int t_only) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double c = cos(mcr * (PX_PI / 180.0));
@@ -880,6 +881,12 @@ __global__ void k_leaf_lpf(const double *theta, long long n, double sigma_star, 
     const double Ss = sqrt(__dadd_rn(__dmul_rn(h1, h1), __dmul_rn(h2, h2)));
     const double th = theta[i];
     const double c2 = cos(2.0 * th);
+    if (t_only) {
+        const double st = sin(th), sig = fmax(sigma_star, 1e-18);
+        const double Q = Ss / ((PX_SQRT8 * st) * sig);
+        out[i] = erf(Q) * PX_SQRT2PI / ((2.0 * sig) * Ss) - (2.0 * st) * (1.0 - exp(-(Q * Q))) / __dmul_rn(Ss, Ss);
+        return;
+    }
     out[i] = lpf_value(sin(th), __dmul_rn(c2, c2), sigma_star, Ss, __dmul_rn(Ss, Ss), __dmul_rn(c, c));
 }
 
@@ -2104,6 +2111,72 @@ __global__ void k_dfma_peak(double *out, int iters, double seed) {
         }
     }
     out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------------
+// pyxrd/calculations/statistics.py on plain arrays (the GUI's pattern statistics, specimen/models/statistics.py:16,
+// 115-118): one block per call.
+//   kind 0  Rp          100 sum|e - c| / sum|e|                                   statistics.py:22-27
+//   kind 1  Rpw         100 sqrt( sum' (e - c)^2 / e  /  sum' |e| ), terms that are nan / inf skipped; 0 when the
+//                       quotient cannot be formed                                  statistics.py:50-68
+//   kind 2  R_squared   1 - sum (e - c)^2 / sum (e - mean e)^2                    statistics.py:12-20
+//   kind 3  Rpe         100 sqrt( (n - extra) / sum e^2 )                          statistics.py:70-79
+//   kind 4  Rphase      100 sqrt( sum' (e - c)^2 p / e^2  /  sum' |p| )            statistics.py:81-100
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double leaf_block_sum(double v, double *red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];      // same order in every thread
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_leaf_statistic(int kind, const double *__restrict__ e, const double *__restrict__ c,
+                                                        const double *__restrict__ ph, long long n, double extra, double *out) {
+    __shared__ double red[8];
+    double a = 0.0, b = 0.0;
+    if (kind == 2) {                                     // mean first
+        double sum = 0.0;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) sum += e[i];
+        const double avg = leaf_block_sum(sum, red) / (double)n;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const double d = e[i] - c[i], m = e[i] - avg;
+            a = fma(d, d, a);
+            b = fma(m, m, b);
+        }
+    } else {
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const double ei = e[i], d = ei - (c ? c[i] : 0.0);
+            if (kind == 0) { a += fabs(d); b += fabs(ei); }
+            else if (kind == 1) {
+                const double t = __ddiv_rn(__dmul_rn(d, d), ei);
+                if (!(isnan(t) || isinf(t))) { a += t; b += fabs(ei); }
+            } else if (kind == 3) { b = fma(ei, ei, b); }
+            else {
+                const double t = __ddiv_rn(__dmul_rn(__dmul_rn(d, d), ph[i]), __dmul_rn(ei, ei));
+                if (!(isnan(t) || isinf(t))) { a += t; b += fabs(ph[i]); }
+            }
+        }
+    }
+    a = leaf_block_sum(a, red);
+    b = leaf_block_sum(b, red);
+    if (threadIdx.x == 0) {
+        double r;
+        if (kind == 0) r = a / b * 100.0;
+        else if (kind == 1 || kind == 4) { const double q = a / b; r = (b != 0.0 && q >= 0.0) ? sqrt(q) * 100.0 : 0.0; }
+        else if (kind == 2) r = 1.0 - a / b;
+        else r = sqrt(((double)n - extra) / b) * 100.0;
+        out[0] = r;
+    }
+}
+
+// derive() = np.gradient(smooth(pattern, 15)) (statistics.py:29-41, math_tools.py:46-99); smooth_only: smooth_pattern()
+__global__ void k_leaf_derive(const double *__restrict__ v, int n, int smooth_only, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = smooth_only ? rpder_smooth<true>(v, nullptr, nullptr, 0, 0, n, i) : rpder_gradient<true>(v, nullptr, nullptr, 0, 0, n, i);
 }
 
 // ---------------------------------------------------------------------------------

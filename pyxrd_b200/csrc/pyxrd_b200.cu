@@ -136,7 +136,7 @@ struct pyxrd_ctx {
     int wl_passes = 0;       // longest wavelength list of the specimens = number of ping-pong passes
     int jobs_per_cand = 0;
     PinBuf h_res;
-    DevBuf d_leaf_a, d_leaf_b, d_leaf_c, d_sol, d_optres;
+    DevBuf d_leaf_a, d_leaf_b, d_leaf_c, d_leaf_d, d_sol, d_optres;
     bool have_opt = false;
     int64_t int_count = 0, tot_count = 0;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -362,7 +362,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob, &ctx->d_tmpl,
                       &ctx->d_partial, &ctx->d_ph_nu, &ctx->d_ph_uz, &ctx->d_ph_uend, &ctx->d_ph_useg, &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
-                      &ctx->d_res, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_sol, &ctx->d_optres};
+                      &ctx->d_res, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_leaf_d, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
     ctx->h_tmpl.release();
@@ -1087,6 +1087,36 @@ int pyxrd_leaf_asf(pyxrd_ctx *ctx, const double *s, int64_t n, const double *ato
     return read_back(ctx, ctx->d_leaf_c.ptr, out, n, n, "asf");
 }
 
+int pyxrd_leaf_statistic(pyxrd_ctx *ctx, int kind, const double *exp, const double *calc, const double *phase, int64_t n,
+                         double extra, double *out) {
+    if (!ctx || !exp || !out || n < 0) return 1;
+    if (kind < 0 || kind > 4) return fail(ctx, "leaf_statistic: unknown statistic %d", kind);
+    if ((kind != 3 && !calc) || (kind == 4 && !phase)) return fail(ctx, "leaf_statistic: statistic %d needs more patterns", kind);
+    CK(cudaSetDevice(ctx->device));
+    if (upload(ctx, ctx->d_leaf_a, exp, (size_t)n)) return 1;
+    if (calc && upload(ctx, ctx->d_leaf_b, calc, (size_t)n)) return 1;
+    if (kind == 4 && upload(ctx, ctx->d_leaf_d, phase, (size_t)n)) return 1;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * 2));
+    k_leaf_statistic<<<1, 256, 0, ctx->stream>>>(kind, ctx->d_leaf_a.as<double>(), calc ? ctx->d_leaf_b.as<double>() : nullptr,
+                                                 kind == 4 ? ctx->d_leaf_d.as<double>() : nullptr, (long long)n, extra,
+                                                 ctx->d_leaf_c.as<double>());
+    LAUNCH_CHECK("k_leaf_statistic");
+    return read_back(ctx, ctx->d_leaf_c.ptr, out, 1, 1, "statistic");
+}
+
+int pyxrd_leaf_derive(pyxrd_ctx *ctx, const double *pattern, int64_t n, int smooth_only, double *out) {
+    if (!ctx || !pattern || !out || n < 0) return 1;
+    if (n < 31) return fail(ctx, "Input vector needs to be bigger than window size.");       // math_tools.py:87-88
+    if (n > 0x7fffffffLL) return fail(ctx, "leaf_derive: pattern too long");
+    CK(cudaSetDevice(ctx->device));
+    if (upload(ctx, ctx->d_leaf_a, pattern, (size_t)n)) return 1;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * (size_t)n));
+    k_leaf_derive<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_leaf_a.as<double>(), (int)n, smooth_only,
+                                                                      ctx->d_leaf_c.as<double>());
+    LAUNCH_CHECK("k_leaf_derive");
+    return read_back(ctx, ctx->d_leaf_c.ptr, out, n, n, "derive");
+}
+
 int pyxrd_leaf_lpf(pyxrd_ctx *ctx, const double *theta, int64_t n, double sigma_star, double soller1, double soller2,
                    double mcr_2theta, double *out) {
     if (!ctx || n < 0) return 1;
@@ -1094,9 +1124,20 @@ int pyxrd_leaf_lpf(pyxrd_ctx *ctx, const double *theta, int64_t n, double sigma_
     if (n == 0) return 0;
     if (upload(ctx, ctx->d_leaf_a, theta, (size_t)n)) return 1;
     CK(ctx->d_leaf_c.ensure(sizeof(double) * (size_t)n));
-    k_leaf_lpf<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_leaf_a.as<double>(), n, sigma_star, soller1, soller2, mcr_2theta, ctx->d_leaf_c.as<double>());
+    k_leaf_lpf<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_leaf_a.as<double>(), n, sigma_star, soller1, soller2, mcr_2theta, ctx->d_leaf_c.as<double>(), 0);
     LAUNCH_CHECK("k_leaf_lpf");
     return read_back(ctx, ctx->d_leaf_c.ptr, out, n, n, "lpf");
+}
+
+int pyxrd_leaf_lorentz(pyxrd_ctx *ctx, const double *theta, int64_t n, double sigma_star, double soller1, double soller2, double *out) {
+    if (!ctx || n < 0) return 1;
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    if (upload(ctx, ctx->d_leaf_a, theta, (size_t)n)) return 1;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * (size_t)n));
+    k_leaf_lpf<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_leaf_a.as<double>(), n, sigma_star, soller1, soller2, 0.0, ctx->d_leaf_c.as<double>(), 1);
+    LAUNCH_CHECK("k_leaf_lpf");
+    return read_back(ctx, ctx->d_leaf_c.ptr, out, n, n, "T");
 }
 
 int pyxrd_leaf_csds(pyxrd_ctx *ctx, const double *csds6, int minimum, int maximum, double *out_arr, double *out_mean, double *out_coef) {

@@ -19,11 +19,13 @@ _TARGETS = {
     "pyxrd.calculations.atoms": ("atoms", ["get_atomic_scattering_factor", "get_structure_factor"]),
     "pyxrd.calculations.components": ("components", ["get_factors"]),
     "pyxrd.calculations.CSDS": ("CSDS", ["calculate_distribution"]),
-    "pyxrd.calculations.goniometer": ("goniometer", ["get_lorentz_polarisation_factor",
+    "pyxrd.calculations.goniometer": ("goniometer", ["get_T", "get_lorentz_polarisation_factor",
                                                      "get_fixed_to_ads_correction_range"]),
-    "pyxrd.calculations.phases": ("phases", ["get_diffracted_intensity", "get_intensity"]),
+    "pyxrd.calculations.phases": ("phases", ["get_diffracted_intensity", "get_intensity", "get_structure_factors"]),
     "pyxrd.calculations.specimen": ("specimen", ["get_machine_correction_range", "calculate_phase_intensities",
                                                  "calculate_scaled_intensities"]),
+    "pyxrd.calculations.statistics": ("statistics", ["R_squared", "Rp", "smooth_pattern", "derive", "Rpder", "Rpw", "Rpe",
+                                                    "Rphase"]),
     "pyxrd.calculations.mixture": ("mixture", ["parse_mixture", "calculate_mixture", "optimize_mixture",
                                                "calculate_and_optimize_mixture", "get_residual",
                                                "get_optimized_residual", "_get_residuals"]),
@@ -38,6 +40,7 @@ _IMPORT_SITES = [
     "pyxrd.atoms.models",                     # models.py:17
     "pyxrd.phases.models.CSDS",               # CSDS.py:10
     "pyxrd.goniometer.models",                # models.py:26-31
+    "pyxrd.specimen.models.statistics",       # statistics.py:16 (Rpw, Rp, derive)
     "pyxrd.calculations.specimen",            # specimen.py:12-13 (imports from phases / goniometer)
     "pyxrd.calculations.phases",              # phases.py:15-18
     "pyxrd.calculations.components",          # components.py:13

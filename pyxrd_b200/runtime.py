@@ -67,6 +67,7 @@ EXPORTS = [
     "pyxrd_leaf_lpf", "pyxrd_leaf_csds", "pyxrd_leaf_component", "pyxrd_stage_times", "pyxrd_dfma_peak",
     "pyxrd_expand_population", "pyxrd_expanded_desc", "pyxrd_expanded_free", "pyxrd_expand_error",
     "pyxrd_set_population", "pyxrd_evaluate_population", "pyxrd_optimize_population", "pyxrd_leaf_probabilities",
+    "pyxrd_leaf_statistic", "pyxrd_leaf_derive", "pyxrd_leaf_lorentz",
 ]
 
 _lib = None
@@ -125,6 +126,9 @@ def load_library():
         lib.pyxrd_evaluate_host.argtypes = [vp, C.POINTER(BatchDesc), _f64p, _f64p]
         lib.pyxrd_optimize_host.argtypes = [vp, C.POINTER(BatchDesc), C.c_int, C.c_int, C.c_int, _f64p, _f64p]
         lib.pyxrd_leaf_asf.argtypes = [vp, _f64p, C.c_int64, _f64p, _f64p]
+        lib.pyxrd_leaf_statistic.argtypes = [vp, C.c_int, _f64p, _f64p, _f64p, C.c_int64, C.c_double, _f64p]
+        lib.pyxrd_leaf_derive.argtypes = [vp, _f64p, C.c_int64, C.c_int, _f64p]
+        lib.pyxrd_leaf_lorentz.argtypes = [vp, _f64p, C.c_int64, C.c_double, C.c_double, C.c_double, _f64p]
         lib.pyxrd_leaf_lpf.argtypes = [vp, _f64p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _f64p]
         lib.pyxrd_leaf_csds.argtypes = [vp, _f64p, C.c_int, C.c_int, _f64p, _f64p, _f64p]
         lib.pyxrd_leaf_component.argtypes = [vp, _f64p, C.c_int64, _f64p, C.c_int, C.c_int, _f64p, _f64p, _u8p,
@@ -352,11 +356,41 @@ class Context(object):
         self._check(self._lib.pyxrd_leaf_asf(self._h, _p(s, _f64p), s.size, _p(row, _f64p), _p(out, _f64p)), "leaf_asf")
         return out
 
+    def leaf_statistic(self, kind: int, exp, calc=None, phase=None, extra: float = 0.0) -> float:
+        """statistics.py on plain arrays: kind 0 Rp, 1 Rpw, 2 R_squared, 3 Rpe (extra = parameters), 4 Rphase"""
+        e = _f64(exp).ravel()
+        c = _f64(calc).ravel() if calc is not None else None
+        p = _f64(phase).ravel() if phase is not None else None
+        for other in (c, p):
+            if other is not None and other.size != e.size:
+                raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,)" % (e.size, other.size))
+        out = np.zeros(1)
+        self._check(self._lib.pyxrd_leaf_statistic(self._h, int(kind), _p(e, _f64p), _p(c, _f64p) if c is not None else None,
+                                                   _p(p, _f64p) if p is not None else None, e.size, float(extra),
+                                                   _p(out, _f64p)), "leaf_statistic")
+        return float(out[0])
+
+    def leaf_derive(self, pattern, smooth_only: bool = False):
+        v = _f64(pattern).ravel()
+        if v.size < 31:
+            raise ValueError("Input vector needs to be bigger than window size.")        # math_tools.py:87-88
+        out = np.empty_like(v)
+        self._check(self._lib.pyxrd_leaf_derive(self._h, _p(v, _f64p), v.size, int(bool(smooth_only)), _p(out, _f64p)),
+                    "leaf_derive")
+        return out
+
     def leaf_lpf(self, theta, sigma_star, soller1, soller2, mcr_2theta):
         t = _f64(theta).ravel()
         out = np.empty_like(t)
         self._check(self._lib.pyxrd_leaf_lpf(self._h, _p(t, _f64p), t.size, float(sigma_star), float(soller1),
                                              float(soller2), float(mcr_2theta), _p(out, _f64p)), "leaf_lpf")
+        return out
+
+    def leaf_T(self, theta, sigma_star, soller1, soller2):
+        t = _f64(theta).ravel()
+        out = np.empty_like(t)
+        self._check(self._lib.pyxrd_leaf_lorentz(self._h, _p(t, _f64p), t.size, float(sigma_star), float(soller1), float(soller2),
+                                           _p(out, _f64p)), "leaf_T")
         return out
 
     def leaf_csds(self, average, alpha_scale, alpha_offset, beta_scale, beta_offset, minimum, maximum):

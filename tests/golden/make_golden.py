@@ -131,6 +131,20 @@ def extras(ref, out):
     stl = 2 * np.sin(theta) / spec.goniometer.wavelength
     out["raw_single"] = ref.phases.get_diffracted_intensity(theta, stl, spec.phases[0][1])
     out["raw_single_lpf"] = ref.phases.get_intensity(theta, stl, 2.3, 2.3, 0.0, spec.phases[0][2])
+    # statistics.py on plain arrays (GUI pattern statistics): zeros in exp make Rpw / Rphase skip terms
+    from pyxrd.calculations import statistics as rs
+    rng = np.random.default_rng(31)
+    e = rng.uniform(5.0, 500.0, 1500)
+    e[[3, 77, 900]] = 0.0
+    c = e * rng.uniform(0.9, 1.1, e.size) + rng.uniform(-2.0, 2.0, e.size)
+    ph = rng.uniform(0.0, 80.0, e.size)
+    out["stat_exp"], out["stat_calc"], out["stat_phase"] = e, c, ph
+    with np.errstate(all="ignore"):
+        out["stat_values"] = np.array([rs.Rp(e, c), rs.Rpw(e, c), rs.R_squared(e, c), rs.Rpe(e, c, 7), rs.Rphase(e, c, ph),
+                                       rs.Rpder(e, c)], dtype=float)
+    out["stat_derive"] = rs.derive(e)
+    out["stat_smooth"] = rs.smooth_pattern(e)
+    out["stat_rpw_all_zero"] = np.array(rs.Rpw(np.zeros(40), np.ones(40)), dtype=float)
     # two patterns per specimen (z_list of length 2, observed [X, 2], phases [Z][M])
     mix = syn.z2_case()
     ref.mixture.calculate_mixture(mix)

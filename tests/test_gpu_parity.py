@@ -544,3 +544,40 @@ def test_dense_and_structured_matrices_of_the_same_rank(calc):
     spec = syn.make_specimen(theta, phases, syn.make_goniometer("cu_pair"))
     mix = _with_observed(syn.make_mixture([spec], len(phases)))
     _oracle_vs_device(calc, mix)
+
+
+def test_statistics_on_plain_arrays(calc, golden):
+    """pyxrd_b200.calculations.statistics (k_leaf_statistic, k_leaf_derive) against the live reference"""
+    g = golden("extras")
+    st = calc.statistics
+    e, c, ph = g["stat_exp"], g["stat_calc"], g["stat_phase"]
+    got = [st.Rp(e, c), st.Rpw(e, c), st.R_squared(e, c), st.Rpe(e, c, 7), st.Rphase(e, c, ph), st.Rpder(e, c)]
+    assert rel_err(got, g["stat_values"]) < 1e-12
+    assert np.max(np.abs(st.derive(e) - g["stat_derive"])) < 1e-10 * np.max(np.abs(g["stat_derive"]))
+    assert np.max(np.abs(st.smooth_pattern(e) - g["stat_smooth"])) < 1e-12 * np.max(np.abs(g["stat_smooth"]))
+    assert st.Rpw(np.zeros(40), np.ones(40)) == 0
+    with pytest.raises(ValueError, match="window size"):
+        st.derive(np.ones(20))
+    with pytest.raises(ValueError):
+        st.Rpw(np.ones((2, 40)), np.ones((2, 40)))
+    with pytest.raises(ValueError):
+        st.Rp(np.ones(10), np.ones(11))
+
+
+def test_remaining_leaf_helpers(calc, golden):
+    """get_T (goniometer.py:20-25), get_structure_factors (phases.py:20-39), get_absolute_scale (phases.py:48-66)"""
+    g = golden("kat")
+    theta = g["kat_theta"]
+    T = calc.goniometer.get_T(theta, 12, 2.3, 2.3)
+    lpf = calc.goniometer.get_lorentz_polarisation_factor(theta, 12, 2.3, 2.3, 0)
+    assert rel_err(T * (1.0 + np.cos(2.0 * theta) ** 2) / np.sin(theta), lpf) < 1e-14
+    assert rel_err(T, orc.get_T(theta, 12, 2.3, 2.3)) < 1e-13
+    mix = syn.CONFIGS["c2"].truth()
+    ph = mix.specimens[0].phases[0][0]
+    stl = 2 * np.sin(mix.specimens[0].range_theta[::50]) / mix.specimens[0].goniometer.wavelength
+    SF, PF = calc.phases.get_structure_factors(stl, ph.G, ph.components)
+    SFo, PFo = orc.get_structure_factors(stl, ph.G, copy.deepcopy(ph.components))
+    assert SF.shape == (stl.size, 2) and np.max(np.abs(SF - SFo)) < 1e-11 * np.max(np.abs(SFo))
+    assert np.max(np.abs(PF - PFo)) < 1e-13
+    assert calc.phases.get_absolute_scale(ph.components, 9.7, ph.W) == orc.get_absolute_scale(ph.components, 9.7, ph.W)
+    assert calc.phases.get_absolute_scale([None, None], 9.7, ph.W) == 0.0

@@ -164,3 +164,13 @@ def test_oracle_on_the_reference_integration_fixture():
     r = orc.get_optimized_residual(copy.deepcopy(mix))
     want = float(g["opt_residual"][0])
     assert abs(float(r[0]) - want) <= OPT_RTOL * max(1.0, want)
+
+
+def test_oracle_statistics_on_plain_arrays(golden):
+    """pyxrd/calculations/statistics.py (GUI pattern statistics) against the live reference"""
+    g = golden("extras")
+    e, c, ph = g["stat_exp"], g["stat_calc"], g["stat_phase"]
+    got = [orc.Rp(e, c), orc.Rpw(e, c), orc.R_squared(e, c), orc.Rpe(e, c, 7), orc.Rphase(e, c, ph), orc.Rpder(e, c)]
+    assert rel_err(got, g["stat_values"]) < 1e-13
+    assert rel_err(orc.derive(e), g["stat_derive"]) < 1e-12
+    assert orc.Rpw(np.zeros(40), np.ones(40)) == float(g["stat_rpw_all_zero"]) == 0
