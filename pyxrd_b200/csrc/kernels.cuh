@@ -2707,13 +2707,15 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
 #ifdef PX_OPT_PROFILE
             long long tG = clock64();
 #endif
-            // two points in flight per thread: the loads of both are issued before the arithmetic
+            // PIF points in flight per thread: the loads of all of them are issued before the arithmetic (few phases
+            // leave registers for more points: the pass is bound by the latency of these loads)
+            constexpr int PIF = MB <= 2 ? 8 : MB <= 4 ? 4 : 2;
             for (int z = 0; z < Z; ++z)
-                for (int x0 = tid; x0 < X; x0 += 2 * TPB) {
-                    double phi[2][MB], o[2];
-                    bool on[2];
+                for (int x0 = tid; x0 < X; x0 += PIF * TPB) {
+                    double phi[PIF][MB], o[PIF];
+                    bool on[PIF];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < PIF; ++u) {
                         const int x = x0 + u * TPB;
                         on[u] = x < X && sel[x];
                         const int xc = x < X ? x : x0;
@@ -2723,7 +2725,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
                         o[u] = obs[(long long)z * X + xc];
                     }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < PIF; ++u) {
                         if (!on[u]) continue;
                         double calc = 0.0;
 #pragma unroll
