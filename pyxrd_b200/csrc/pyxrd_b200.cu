@@ -100,6 +100,9 @@ struct pyxrd_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // device -> host copies of finished candidate chunks (pyxrd_evaluate_host)
+    cudaStream_t class_stream[3] = {};       // the job classes after the first run beside it (their tails overlap)
+    cudaEvent_t fork_ev = nullptr, join_ev[3] = {};
+    bool overlap_classes = true;             // PYXRD_B200_OVERLAP=0: one class after the other
     cudaEvent_t chunk_ev[16] = {};
     std::string error;
     int64_t launches = 0;
@@ -339,6 +342,12 @@ int pyxrd_create(int device, pyxrd_ctx **out) {
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 3; ++i) {
+        cudaStreamCreateWithFlags(&ctx->class_stream[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+    if (const char *e = getenv("PYXRD_B200_OVERLAP")) ctx->overlap_classes = atoi(e) != 0;
     {   // np.blackman(31) / np.blackman(31).sum()  (math_tools.py:93-98 with half_window_len = 15)
         double w[31], sum = 0.0;
         for (int i = 0; i < 31; ++i) {
@@ -370,6 +379,11 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->class_stream[i]) cudaStreamDestroy(ctx->class_stream[i]);
+        if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -826,11 +840,33 @@ int phase_range(pyxrd_ctx *ctx, int k0, int k1, double *target, bool timed) {
         CK(cudaMemsetAsync(bt.intensities + (long long)k0 * bt.cand_stride, 0,
                            sizeof(double) * (size_t)(k1 - k0) * bt.cand_stride, ctx->stream));
     if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // the heaviest class on the context's stream, the others beside it on auxiliary streams: the classes write
+    // disjoint patterns, and the tail of one launch is filled by the blocks of the next
+    cudaStream_t main_stream = ctx->stream;
+    const bool overlap = ctx->overlap_classes && ctx->classes.size() > 1;
+    if (overlap) CK(cudaEventRecord(ctx->fork_ev, main_stream));
+    bool used[3] = {false, false, false};
+    int index = 0, rc_status = 0;
     for (const RankClass &rc : ctx->classes) {
         size_t a, b;
         rc.range(k0, k1, j0, j1, a, b);
-        if (b > a && launch_class(ctx, rc, ctx->jobids_dev + rc.first + a, b - a, bt)) return 1;
+        if (b <= a) continue;
+        const int aux = (index - 1) % 3;
+        if (overlap && index > 0) {
+            if (!used[aux]) CK(cudaStreamWaitEvent(ctx->class_stream[aux], ctx->fork_ev, 0));
+            used[aux] = true;
+            ctx->stream = ctx->class_stream[aux];
+        }
+        rc_status = launch_class(ctx, rc, ctx->jobids_dev + rc.first + a, b - a, bt);
+        ctx->stream = main_stream;
+        if (rc_status) return 1;
+        ++index;
     }
+    for (int i = 0; i < 3; ++i)
+        if (used[i]) {
+            CK(cudaEventRecord(ctx->join_ev[i], ctx->class_stream[i]));
+            CK(cudaStreamWaitEvent(main_stream, ctx->join_ev[i], 0));
+        }
     if (timed) {
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         CK(cudaEventRecord(ctx->ev[2], ctx->stream));
