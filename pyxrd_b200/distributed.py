@@ -85,3 +85,27 @@ def evaluate_population_sharded(mixtures: Sequence, evaluate, device=None, group
     if device is not None:
         t = t.to(device)
     return gather_rows(t, len(mixtures), world, group).cpu().numpy()
+
+
+def evaluate_solutions_sharded(x, evaluate, device=None, group=None) -> np.ndarray:
+    """The template path over several GPUs: every rank evaluates its block of the solution matrix ``x`` f64[K, d] with
+    ``evaluate(x_block) -> f64[k] or f64[k, C]`` (on the GPU path ``PopulationTemplate.optimized_residuals`` /
+    ``.residuals`` of the rank's own template) and all ranks receive the values of all K solutions in order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    lo, hi = shard_bounds(len(x), world)[rank]
+    values = np.asarray(evaluate(x[lo:hi]), dtype=np.float64) if hi > lo else np.zeros(0)
+    cols = int(values.shape[1]) if values.ndim == 2 else 1
+    if world > 1:                                  # empty tail ranks learn the column count from rank 0
+        c = torch.tensor([cols], dtype=torch.int64, device=device if device is not None else "cpu")
+        dist.broadcast(c, src=0, group=group)
+        cols = int(c.item())
+    squeeze = values.ndim == 1 and cols == 1
+    t = torch.from_numpy(np.ascontiguousarray(values.reshape(hi - lo, cols)))
+    if device is not None:
+        t = t.to(device)
+    out = gather_rows(t, len(x), world, group).cpu().numpy()
+    return out[:, 0] if squeeze else out

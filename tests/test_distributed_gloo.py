@@ -35,6 +35,12 @@ def _worker(rank, world, port, out_dir):
         m.specimens[0].observed_intensity = obs.copy()
     table = evaluate_population_sharded(mixes, evaluate)
     np.save(os.path.join(out_dir, "rank%d.npy" % rank), table)
+    # the template path: solution rows instead of DataObject graphs
+    from pyxrd_b200.distributed import evaluate_solutions_sharded
+    x = np.arange(7 * 3, dtype=float).reshape(7, 3)                  # 7 solutions over 2 ranks: 4 + 3
+    one = evaluate_solutions_sharded(x, lambda block: block.sum(axis=1) * 2.0)
+    two = evaluate_solutions_sharded(x, lambda block: np.stack([block[:, 0], block[:, 2] - block[:, 1]], axis=1))
+    np.save(os.path.join(out_dir, "sol%d.npy" % rank), np.column_stack([one, two]))
     dist.destroy_process_group()
 
 
@@ -63,3 +69,6 @@ def test_two_rank_gather_equals_single_rank(tmp_path):
         orc.calculate_mixture(m)
         want.append(m.residuals)
     assert np.array_equal(a, np.array(want, dtype=float))
+    x = np.arange(7 * 3, dtype=float).reshape(7, 3)
+    want = np.column_stack([x.sum(axis=1) * 2.0, x[:, 0], x[:, 2] - x[:, 1]])
+    assert np.array_equal(np.load(tmp_path / "sol0.npy"), want) and np.array_equal(np.load(tmp_path / "sol1.npy"), want)
