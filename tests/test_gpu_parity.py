@@ -581,3 +581,26 @@ def test_remaining_leaf_helpers(calc, golden):
     assert np.max(np.abs(PF - PFo)) < 1e-13
     assert calc.phases.get_absolute_scale(ph.components, 9.7, ph.W) == orc.get_absolute_scale(ph.components, 9.7, ph.W)
     assert calc.phases.get_absolute_scale([None, None], 9.7, ph.W) == 0.0
+
+
+def test_rank_two_series_with_nearly_degenerate_eigenvalues(calc):
+    """the rank-2 series runs as a Clenshaw recurrence on (trace, determinant) of Q; segregated (P11, P22 -> 1) and
+    nearly periodic (P11, P22 -> 0) stackings put both eigenvalues of Q close to the unit circle / to each other, long
+    CSDS distributions (N = 120) give the recurrence time to amplify rounding errors"""
+    types = syn.atom_types()
+    theta = syn.theta_grid(3.0, 50.0, 0.02)
+    phases = []
+    for w1, p11 in ((0.5, 0.999), (0.5, 0.9999999), (0.5, 1e-4), (0.9, 0.999), (0.7, 0.71), (0.5, 0.5), (0.999, 0.9995)):
+        w2 = 1.0 - w1
+        p12 = 1.0 - p11
+        p21 = w1 * p12 / w2
+        P = np.array([[p11, p12], [p21, 1.0 - p21]])
+        comps = [syn.make_component(types, "illite"), syn.make_component(types, "smectite_ad", delta_c=0.0)]
+        phases.append(syn.make_phase(comps, np.diag([w1, w2]), P, syn.make_csds(48.0, maximum=120), sigma_star=6.0))
+    # the same with identical components: phi_0 = phi_1, Q has the eigenvalues phi and phi (p11 + p22 - 1)
+    comps = [syn.make_component(types, "illite"), syn.make_component(types, "illite")]
+    phases.append(syn.make_phase(comps, np.diag([0.5, 0.5]), np.array([[0.999, 0.001], [0.001, 0.999]]),
+                                 syn.make_csds(48.0, maximum=120), sigma_star=6.0))
+    spec = syn.make_specimen(theta, phases, syn.make_goniometer("single"))
+    mix = _with_observed(syn.make_mixture([spec], len(phases)))
+    _oracle_vs_device(calc, mix)
