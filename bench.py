@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 from pyxrd_b200 import synthetic as syn  # noqa: E402
 
 SEED = 2024
-DEFAULT_CANDIDATES = {"c1": 4096, "c2": 2048, "c3": 64, "c4": 256, "c5": 1024}
+DEFAULT_CANDIDATES = {"c1": 4096, "c2": 2048, "c3": 64, "c3s": 256, "c4": 256, "c5": 1024}
 
 
 # ---------------------------------------------------------------------------------------

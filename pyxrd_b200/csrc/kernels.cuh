@@ -1143,7 +1143,16 @@ __device__ __forceinline__ bool phase_is_invalid(const BatchDev &bt, int pb, int
     return true;
 }
 
-// ---- ranks up to 9: every vector in registers, PPT points per thread -----------------
+// helpers of the in-place structured series (k_phase_small, STRUCT = 1): states are digit strings (i1 .. iD) in base
+// G, R = G^D; px_rotl moves the leading digit to the end, px_rot applies it s times
+template <int V> struct px_int { static constexpr int value = V; };
+__host__ __device__ constexpr int px_digits(int R, int G) { int d = 0; for (int v = 1; v < R; v *= G) ++d; return d; }
+__host__ __device__ constexpr int px_rot(int L, int s, int R, int G) {
+    for (int i = 0; i < s; ++i) L = (L % (R / G)) * G + L / (R / G);
+    return L;
+}
+
+// ---- ranks up to 9 (structured transition matrices: up to 27): every vector in registers, PPT points per thread ----
 // A thread owns the points x0 + t + k * TPB, k < PPT: the warp-uniform work (shared-memory
 // reads of the atom / plane lists and of P, loop control, coefficient fetches) is paid once for
 // PPT points and the dependent FMA chains of the PPT points interleave.  Per-point tables are
@@ -1212,6 +1221,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
         }
     }
     double yr[R][PPT], yi[R][PPT];
+    int y_layout = 0;         // STRUCT = 1: the registers hold the state vector rotated by this many digits
 #pragma unroll
     for (int I = 0; I < R; ++I)
 #pragma unroll
@@ -1312,6 +1322,61 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
             yr[1][k] = b1r[k] * q1r - b1i[k] * q1i - (e_r * ur[C1][k] + e_i * ui[C1][k]);
             yi[1][k] = b1r[k] * q1i + b1i[k] * q1r - (e_i * ur[C1][k] - e_r * ui[C1][k]);
         }
+    } else if constexpr (STRUCT == 1) {
+        // Structured transitions, IN PLACE.  The new value of state (a, i2 .. iD) is a combination of the G old values of
+        // the states (i2 .. iD, j), and those G old values are needed by exactly the G new states a = 0 .. G-1: a group of
+        // G registers is read, then overwritten with the G results.  The result for (a, g) lands where (g, a) was, i.e.
+        // after a step the registers hold the vector rotated by one digit; after D steps the layout is back, so the
+        // loop body is D steps with compile-time layouts.  One vector instead of two: half the registers of the y / w
+        // version.
+        constexpr int T = R / G, D = px_digits(R, G);
+        auto substep = [&](auto S, const double cn) {
+            constexpr int sft = decltype(S)::value;
+            double cgr[G][PPT], cgi[G][PPT];
+#pragma unroll
+            for (int c = 0; c < G; ++c)
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) { cgr[c][k] = cn * gr[c][k]; cgi[c][k] = cn * gi[c][k]; }
+#pragma unroll
+            for (int g = 0; g < T; ++g) {
+                double wr[G][PPT], wi[G][PPT];
+#pragma unroll
+                for (int j = 0; j < G; ++j) {                 // w_J = phi_c(J) y_J + c_n g_c(J), J = (g, j)
+                    const int J = g * G + j, c = J / REPS, pj = px_rot(J, sft, R, G);
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        wr[j][k] = fma(pr[c][k], yr[pj][k], fma(-pim[c][k], yi[pj][k], cgr[c][k]));
+                        wi[j][k] = fma(pr[c][k], yi[pj][k], fma(pim[c][k], yr[pj][k], cgi[c][k]));
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < G; ++a) {                 // y_(a, g) = sum_j P[(a, g)][(g, j)] w_(g, j)
+                    const int I = a * T + g, pa = px_rot(g * G + a, sft, R, G);
+                    double ar[PPT], ai[PPT];
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        const double p = sP[I * R + g * G + j];
+#pragma unroll
+                        for (int k = 0; k < PPT; ++k) { ar[k] = fma(p, wr[j][k], ar[k]); ai[k] = fma(p, wi[j][k], ai[k]); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) { yr[pa][k] = ar[k]; yi[pa][k] = ai[k]; }
+                }
+            }
+        };
+        int n = ntop, layout = 0;                             // logical state L lives in register px_rot(L, layout)
+#define PX_SUBSTEP(S_) if (n >= 1) { substep(px_int<S_>{}, sCoef[n]); --n; layout = (S_ + 1) % D; }
+        while (n >= 1) {
+            PX_SUBSTEP(0)
+            if constexpr (D > 1) PX_SUBSTEP(1)
+            if constexpr (D > 2) PX_SUBSTEP(2)
+            if constexpr (D > 3) PX_SUBSTEP(3)
+        }
+#undef PX_SUBSTEP
+        static_assert(D <= 4, "Reichweite of the structured in-place series");
+        y_layout = layout;                                    // the trace below reads the rotated registers
     } else {
         for (int n = ntop; n >= 1; --n) {
             const double cn = sCoef[n];
@@ -1362,22 +1427,34 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     double tr[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) tr[k] = 0.0;
+    auto trace = [&](auto S) {
+        constexpr int sft = decltype(S)::value;
 #pragma unroll
-    for (int K = 0; K < R; ++K) {
-        const int ck = K / REPS;
+        for (int K = 0; K < R; ++K) {
+            const int ck = K / REPS;
+            const int pk = (STRUCT == 1) ? px_rot(K, sft, R, G) : K;       // where y_K lives
 #pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-            double ar = 0.0, ai = 0.0;
+            for (int k = 0; k < PPT; ++k) {
+                double ar = 0.0, ai = 0.0;
 #pragma unroll
-            for (int c = 0; c < G; ++c) {
-                const double w = sWG[c * R + K];
-                ar = fma(ur[c][k], w, ar);
-                ai = fma(ui[c][k], w, ai);
+                for (int c = 0; c < G; ++c) {
+                    const double w = sWG[c * R + K];
+                    ar = fma(ur[c][k], w, ar);
+                    ai = fma(ui[c][k], w, ai);
+                }
+                const double sr = fma(mean, ur[ck][k], yr[pk][k]);
+                const double si = fma(-mean, ui[ck][k], yi[pk][k]);
+                tr[k] += ar * sr - ai * si;
             }
-            const double sr = fma(mean, ur[ck][k], yr[K][k]);
-            const double si = fma(-mean, ui[ck][k], yi[K][k]);
-            tr[k] += ar * sr - ai * si;
         }
+    };
+    if constexpr (STRUCT == 1) {
+        if (y_layout == 0) trace(px_int<0>{});
+        else if (y_layout == 1) trace(px_int<1>{});
+        else if (y_layout == 2) trace(px_int<2>{});
+        else trace(px_int<3>{});
+    } else {
+        trace(px_int<0>{});
     }
     double out[PPT];
 #pragma unroll

@@ -269,10 +269,15 @@ int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_
     }
     if (rc.structure == 1 && ctx->use_structure) {
         // structured transition matrices (Reichweite >= 2 models): G instead of R multiply-adds per state
-        // (shapes from a sweep on B200: rank 8 one point per thread, 118 registers; two points per thread need 204)
+        // (shapes from sweeps on B200)
         if (rc.rank == 4 && rc.G == 2) return launch_small<4, 2, 2, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 8 && rc.G == 2) return launch_small<8, 2, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 8 && rc.G == 2) return launch_small<8, 2, 2, 64, 8, 1>(ctx, rc, jobs_dev, njobs, bt);   // 3.64 ms on c5; 1 x 128: 4.02
         if (rc.rank == 9 && rc.G == 3) return launch_small<9, 3, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
+        // larger ranks: the in-place series needs the state vector once (254 registers at rank 27); c3s 1.52 ms per 256
+        // candidates, 4.07 ms with the vector staged through shared memory, 7.89 ms with the dense DMMA kernel
+        if (rc.rank == 27 && rc.G == 3) return launch_small<27, 3, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 16 && rc.G == 2) return launch_small<16, 2, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 16 && rc.G == 4) return launch_small<16, 4, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
     }
     // (points per thread, threads per block, min blocks per SM) from sweeps on B200 (profiles/r1_summary.md)
     SMALLB(1, 1, 4, 32, 0); SMALLB(2, 2, 4, 32, 16); SMALLB(2, 1, 4, 32, 16);

@@ -283,6 +283,21 @@ def _c3(rng):
     return make_mixture([spec], 1)
 
 
+def _c3s(rng):
+    """c3 with the transition structure a real Reichweite-3 chain of three components has: state (i1, i2, i3) only
+    reaches (i2, i3, j) -- 3 non-zero entries per row of the 27 x 27 matrix instead of 27."""
+    types = atom_types()
+    base = np.random.default_rng(1003)
+    comps = [make_component(types, "illite", d001=_u(rng, 0.99, 1.005, 0.998)),
+             make_component(types, "chlorite", d001=_u(rng, 1.41, 1.43, 1.42)),
+             make_component(types, "smectite_eg", d001=_u(rng, 1.66, 1.72, 1.69), delta_c=0.02)]
+    W, P = make_probabilities(base if rng is None else rng, 3, 3, dense=False)
+    phase = make_phase(comps, W, P, make_csds(_u(rng, 28.0, 32.0, 30.0), maximum=120),
+                       sigma_star=_u(rng, 1.0, 15.0, 3.0))
+    spec = make_specimen(theta_grid(3.0, 45.0, 0.02), [phase], make_goniometer("single"))
+    return make_mixture([spec], 1)
+
+
 def _mixed_layer_set(rng, base_seed, states):
     """Shared-parameter phase set for an (AD, EG) specimen pair: each phase is built
     twice with the same CSDS / sigma* / W / P and different smectite hydration state."""
@@ -417,6 +432,7 @@ CONFIGS = {
     "c1": Config("c1", "single-phase R0 illite, G=1, CSDS mean 10, X=2100", _c1, 1, 1),
     "c2": Config("c2", "illite-smectite R1 G=2, air-dry, X=6700", _c2, 1, 1),
     "c3": Config("c3", "illite-chlorite-smectite rank 27, CSDS mean 30 max 120, X=2100", _c3, 1, 1),
+    "c3s": Config("c3s", "c3 with the Reichweite-3 transition structure (3 non-zeros per row of the 27 x 27 matrix)", _c3s, 1, 1),
     "c4": Config("c4", "AD+EG specimens x 6 shared-parameter phases (CMA-ES population)", _c4, 2, 6),
     "c5": Config("c5", "4-phase R3 (rank 8) mixture population sweep", _c5, 1, 4),
 }

@@ -523,15 +523,16 @@ def test_reference_integration_fixture(calc):
 
 
 def test_dense_and_structured_matrices_of_the_same_rank(calc):
-    """ranks 4 / 8 / 9 / 16: a P with the Reichweite >= 2 transition structure takes the structured kernels
-    (k_phase_small<.., STRUCT = 1>), a dense P of the same rank the dense ones (vector Horner, DMMA for 8 / 16);
+    """ranks 4 / 8 / 9 / 16 / 27: a P with the Reichweite >= 2 transition structure takes the structured kernels
+    (k_phase_small<.., STRUCT = 1>, k_phase_staged<.., STRUCT = 1> for 16 / 27), a dense P of the same rank the dense
+    ones (vector Horner, DMMA for 8 / 16 / 27);
     Reichweite 0 with 3 - 6 components takes the scalar series, a P of that rank with unequal rows the dense kernel"""
     types = syn.atom_types()
     rng = np.random.default_rng(77)
     theta = syn.theta_grid(3.0, 30.0, 0.05)
     kinds = ["illite", "smectite_ad", "chlorite", "smectite_eg", "kaolinite", "illite"]
     phases = []
-    for G, R in ((2, 2), (2, 3), (3, 2), (2, 4)):
+    for G, R in ((2, 2), (2, 3), (3, 2), (2, 4), (4, 2), (3, 3)):
         for dense in (False, True):
             comps = [syn.make_component(types, kinds[c], rng) for c in range(G)]
             W, P = syn.make_probabilities(rng, G, R, dense=dense)
