@@ -2679,15 +2679,187 @@ __device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int 
     }
 }
 
+// The same step for very small problems (D = M + 2 S <= 5: one or two phases in one specimen, one phase in two) by ONE
+// thread with everything in its registers: the warp version spends its time in shuffles whatever D is (assembly and
+// majoriser values are butterflies), here an iteration is a few hundred scalar operations.  Same damping ladder
+// (lam * 5^(w - 1), w = 0 .. 3, best point wins, a round nobody wins moves the ladder up).
+template <int M, int S>
+__device__ __forceinline__ double opt_q_scalar(const OptSmem &sm, const double (&v)[M + 2 * S]) {
+    constexpr int MB = M + 1;
+    double q = 0.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const double *B = sm.B[s], *c = sm.c[s];
+        const double r = v[M + s], b = v[M + S + s];
+        double fBf = 0.0, Bcf = 0.0, cf = 0.0;
+#pragma unroll
+        for (int p = 0; p < M; ++p) {
+            double t = 0.0;
+#pragma unroll
+            for (int q2 = 0; q2 < M; ++q2) t = fma(B[p * MB + q2], v[q2], t);
+            fBf = fma(v[p], t, fBf);
+            Bcf = fma(B[p * MB + M], v[p], Bcf);
+            cf = fma(c[p], v[p], cf);
+        }
+        q += sm.wgt[s] * (r * r * fBf + 2.0 * r * b * Bcf + B[M * MB + M] * b * b - 2.0 * r * cf - 2.0 * c[M] * b);
+    }
+    return q;
+}
+
+template <int M, int S>
+__device__ __noinline__ void opt_inner_solve_scalar(OptSmem &sm, int lm_iters, int refine_bg) {
+    constexpr int MB = M + 1, D = M + 2 * S;
+    double v[D], lo[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { v[i] = sm.v[i]; lo[i] = sm.lo[i]; }
+    double lam = sm.lam;
+    for (int it = 0; it < lm_iters; ++it) {
+        double H[D][D], g[D], qv = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            g[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) H[i][j] = 0.0;
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const double *B = sm.B[s], *c = sm.c[s];
+            const double w = sm.wgt[s], r = v[M + s], b = v[M + S + s];
+            constexpr int dummy = 0; (void)dummy;
+            const int ir = M + s, ib = M + S + s;
+            double fBf = 0.0, Bcf = 0.0, cf = 0.0;
+#pragma unroll
+            for (int p = 0; p < M; ++p) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < M; ++q) {
+                    t = fma(B[p * MB + q], v[q], t);
+                    H[p][q] += 2.0 * w * r * r * B[p * MB + q];
+                }
+                const double bm = B[p * MB + M], cl = c[p];
+                fBf = fma(v[p], t, fBf);
+                Bcf = fma(bm, v[p], Bcf);
+                cf = fma(cl, v[p], cf);
+                g[p] += w * (2.0 * r * r * t + 2.0 * r * b * bm - 2.0 * r * cl);
+                const double hfr = w * (4.0 * r * t + 2.0 * b * bm - 2.0 * cl), hfb = 2.0 * w * r * bm;
+                H[p][ir] = hfr; H[ir][p] = hfr;
+                H[p][ib] = hfb; H[ib][p] = hfb;
+            }
+            const double BMM = B[M * MB + M], cM = c[M];
+            qv += w * (r * r * fBf + 2.0 * r * b * Bcf + BMM * b * b - 2.0 * r * cf - 2.0 * cM * b);
+            g[ir] = w * (2.0 * r * fBf + 2.0 * b * Bcf - 2.0 * cf);
+            g[ib] = w * (2.0 * r * Bcf + 2.0 * BMM * b - 2.0 * cM);
+            H[ir][ir] = 2.0 * w * fBf;
+            H[ir][ib] = 2.0 * w * Bcf; H[ib][ir] = 2.0 * w * Bcf;
+            H[ib][ib] = 2.0 * w * BMM;
+        }
+        bool fr[D], any = false;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const bool fixed_bg = (!refine_bg && i >= M + S);
+            fr[i] = !fixed_bg && !(v[i] <= lo[i] && g[i] > 0.0) && H[i][i] > 0.0;
+            any = any || fr[i];
+        }
+        if (!any) break;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (!fr[i] || !fr[j]) H[i][j] = (i == j) ? 1.0 : 0.0;
+        bool accepted = false;
+        double rel = 0.0;
+#pragma unroll 1
+        for (int round = 0; round < 4 && !accepted; ++round) {
+            double qbest = qv, vbest[D], lam_best = lam;
+            bool found = false;
+            double lam_w = lam * 0.2;
+#pragma unroll 1
+            for (int wdx = 0; wdx < PX_OPT_NDAMP; ++wdx, lam_w *= 5.0) {
+                double A[D][D], y[D];
+                bool ok = true;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) A[i][j] = H[i][j];
+                    A[i][i] = H[i][i] + (lam_w * fabs(H[i][i]) + 1e-300);
+                    y[i] = fr[i] ? -g[i] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < D; ++j) {                 // Cholesky, lower triangle in place; A[j][j] <- 1 / l_jj
+                    double djj = A[j][j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) djj = fma(-A[j][k], A[j][k], djj);
+                    if (!(djj > 0.0)) ok = false;
+                    const double inv = rsqrt(ok ? djj : 1.0);
+#pragma unroll
+                    for (int i = j + 1; i < D; ++i) {
+                        double a = A[i][j];
+#pragma unroll
+                        for (int k = 0; k < j; ++k) a = fma(-A[i][k], A[j][k], a);
+                        A[i][j] = a * inv;
+                    }
+                    A[j][j] = inv;
+                }
+                if (!ok) continue;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {                 // L z = -g
+                    double z = y[j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) z = fma(-A[j][k], y[k], z);
+                    y[j] = z * A[j][j];
+                }
+#pragma unroll
+                for (int j = D - 1; j >= 0; --j) {            // L^T x = z
+                    double z = y[j];
+#pragma unroll
+                    for (int k = j + 1; k < D; ++k) z = fma(-A[k][j], y[k], z);
+                    y[j] = z * A[j][j];
+                }
+                double vn[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) vn[i] = fr[i] ? fmax(lo[i], v[i] + y[i]) : v[i];
+                const double qn = opt_q_scalar<M, S>(sm, vn);
+                if (qn < qbest) {
+                    qbest = qn; found = true; lam_best = lam_w;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) vbest[i] = vn[i];
+                }
+            }
+            if (found) {
+                accepted = true;
+                rel = (qv - qbest) / fmax(fabs(qv), 1e-300);
+#pragma unroll
+                for (int i = 0; i < D; ++i) v[i] = vbest[i];
+                lam = fmax(lam_best, 1e-12);
+            } else {
+                for (int i = 0; i < PX_OPT_NDAMP; ++i) lam *= 5.0;
+            }
+        }
+        if (!accepted || rel < 1e-13) break;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) sm.v[i] = v[i];
+    sm.lam = fmin(lam, 1e-3);
+}
+
 // register version (PX_OPT_NDAMP warps of the block, one damping each) where the problem is small enough (S <= 3 and
 // D = M + 2 S <= 12), shared-memory version (warp 0) otherwise.  Each kernel instantiation (M fixed) compiles at most
-// three register solvers.  Called by every thread of the block.
+// three register solvers; D <= 5 goes to the single-thread scalar solver.  Called by every thread of the block.
+#ifdef PX_OPT_NO_SCALAR
+#define PX_OPT_SCALAR_D 0
+#else
+#define PX_OPT_SCALAR_D 5
+#endif
 template <int M>
 __device__ __forceinline__ void opt_solve_dispatch(OptSmem &sm, int S, int lm_iters, int refine_bg, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
+#ifndef PX_OPT_NO_SCALAR
+    if constexpr (M + 2 <= 5) { if (S == 1) { if (tid == 0) opt_inner_solve_scalar<M, 1>(sm, lm_iters, refine_bg); return; } }
+    if constexpr (M + 4 <= 5) { if (S == 2) { if (tid == 0) opt_inner_solve_scalar<M, 2>(sm, lm_iters, refine_bg); return; } }
+#endif
     const bool team = warp < PX_OPT_NDAMP;
-    if constexpr (M + 2 <= 12) { if (S == 1) { if (team) opt_inner_solve_reg<M, 1>(sm, lm_iters, refine_bg, lane, warp); return; } }
-    if constexpr (M + 4 <= 12) { if (S == 2) { if (team) opt_inner_solve_reg<M, 2>(sm, lm_iters, refine_bg, lane, warp); return; } }
+    if constexpr (PX_OPT_SCALAR_D < M + 2 && M + 2 <= 12) { if (S == 1) { if (team) opt_inner_solve_reg<M, 1>(sm, lm_iters, refine_bg, lane, warp); return; } }
+    if constexpr (PX_OPT_SCALAR_D < M + 4 && M + 4 <= 12) { if (S == 2) { if (team) opt_inner_solve_reg<M, 2>(sm, lm_iters, refine_bg, lane, warp); return; } }
     if constexpr (M + 6 <= 12) { if (S == 3) { if (team) opt_inner_solve_reg<M, 3>(sm, lm_iters, refine_bg, lane, warp); return; } }
     if (warp == 0) opt_inner_solve(sm, M, S, M + 1, lm_iters, refine_bg, lane);
 }
