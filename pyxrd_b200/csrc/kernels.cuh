@@ -2679,10 +2679,11 @@ __device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int 
     }
 }
 
-// The same step for very small problems (D = M + 2 S <= 5: one or two phases in one specimen, one phase in two) by ONE
-// thread with everything in its registers: the warp version spends its time in shuffles whatever D is (assembly and
-// majoriser values are butterflies), here an iteration is a few hundred scalar operations.  Same damping ladder
-// (lam * 5^(w - 1), w = 0 .. 3, best point wins, a round nobody wins moves the ladder up).
+// The same step for very small problems (D = M + 2 S <= 5: one or two phases in one specimen, one phase in two) with the
+// whole system in the registers of ONE lane: the team version spends its time in shuffles whatever D is (assembly and
+// majoriser values are butterflies), here an iteration is a few hundred scalar operations, a chain bound by the latency
+// of the fp64 pipe.  The four dampings of the ladder (lam * 5^(w - 1), w = 0 .. 3) run on four neighbouring lanes of
+// warp 0, the best point wins, a round nobody wins moves the ladder up.  Called by warp 0.
 template <int M, int S>
 __device__ __forceinline__ double opt_q_scalar(const OptSmem &sm, const double (&v)[M + 2 * S]) {
     constexpr int MB = M + 1;
@@ -2707,7 +2708,7 @@ __device__ __forceinline__ double opt_q_scalar(const OptSmem &sm, const double (
 }
 
 template <int M, int S>
-__device__ __noinline__ void opt_inner_solve_scalar(OptSmem &sm, int lm_iters, int refine_bg) {
+__device__ __noinline__ void opt_inner_solve_scalar(OptSmem &sm, int lm_iters, int refine_bg, int lane) {
     constexpr int MB = M + 1, D = M + 2 * S;
     double v[D], lo[D];
 #pragma unroll
@@ -2725,7 +2726,6 @@ __device__ __noinline__ void opt_inner_solve_scalar(OptSmem &sm, int lm_iters, i
         for (int s = 0; s < S; ++s) {
             const double *B = sm.B[s], *c = sm.c[s];
             const double w = sm.wgt[s], r = v[M + s], b = v[M + S + s];
-            constexpr int dummy = 0; (void)dummy;
             const int ir = M + s, ib = M + S + s;
             double fBf = 0.0, Bcf = 0.0, cf = 0.0;
 #pragma unroll
@@ -2770,76 +2770,78 @@ __device__ __noinline__ void opt_inner_solve_scalar(OptSmem &sm, int lm_iters, i
         double rel = 0.0;
 #pragma unroll 1
         for (int round = 0; round < 4 && !accepted; ++round) {
-            double qbest = qv, vbest[D], lam_best = lam;
-            bool found = false;
+            // the four dampings of the ladder on four neighbouring lanes (the other lanes of the warp repeat them)
+            const int wdx = lane & (PX_OPT_NDAMP - 1);
             double lam_w = lam * 0.2;
-#pragma unroll 1
-            for (int wdx = 0; wdx < PX_OPT_NDAMP; ++wdx, lam_w *= 5.0) {
-                double A[D][D], y[D];
-                bool ok = true;
+            for (int i = 0; i < wdx; ++i) lam_w *= 5.0;
+            double A[D][D], y[D], vn[D];
+            bool ok = true;
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
+            for (int i = 0; i < D; ++i) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) A[i][j] = H[i][j];
-                    A[i][i] = H[i][i] + (lam_w * fabs(H[i][i]) + 1e-300);
-                    y[i] = fr[i] ? -g[i] : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < D; ++j) {                 // Cholesky, lower triangle in place; A[j][j] <- 1 / l_jj
-                    double djj = A[j][j];
-#pragma unroll
-                    for (int k = 0; k < j; ++k) djj = fma(-A[j][k], A[j][k], djj);
-                    if (!(djj > 0.0)) ok = false;
-                    const double inv = rsqrt(ok ? djj : 1.0);
-#pragma unroll
-                    for (int i = j + 1; i < D; ++i) {
-                        double a = A[i][j];
-#pragma unroll
-                        for (int k = 0; k < j; ++k) a = fma(-A[i][k], A[j][k], a);
-                        A[i][j] = a * inv;
-                    }
-                    A[j][j] = inv;
-                }
-                if (!ok) continue;
-#pragma unroll
-                for (int j = 0; j < D; ++j) {                 // L z = -g
-                    double z = y[j];
-#pragma unroll
-                    for (int k = 0; k < j; ++k) z = fma(-A[j][k], y[k], z);
-                    y[j] = z * A[j][j];
-                }
-#pragma unroll
-                for (int j = D - 1; j >= 0; --j) {            // L^T x = z
-                    double z = y[j];
-#pragma unroll
-                    for (int k = j + 1; k < D; ++k) z = fma(-A[k][j], y[k], z);
-                    y[j] = z * A[j][j];
-                }
-                double vn[D];
-#pragma unroll
-                for (int i = 0; i < D; ++i) vn[i] = fr[i] ? fmax(lo[i], v[i] + y[i]) : v[i];
-                const double qn = opt_q_scalar<M, S>(sm, vn);
-                if (qn < qbest) {
-                    qbest = qn; found = true; lam_best = lam_w;
-#pragma unroll
-                    for (int i = 0; i < D; ++i) vbest[i] = vn[i];
-                }
+                for (int j = 0; j < D; ++j) A[i][j] = H[i][j];
+                A[i][i] = H[i][i] + (lam_w * fabs(H[i][i]) + 1e-300);
+                y[i] = fr[i] ? -g[i] : 0.0;
             }
-            if (found) {
-                accepted = true;
-                rel = (qv - qbest) / fmax(fabs(qv), 1e-300);
 #pragma unroll
-                for (int i = 0; i < D; ++i) v[i] = vbest[i];
-                lam = fmax(lam_best, 1e-12);
+            for (int j = 0; j < D; ++j) {                     // Cholesky, lower triangle in place; A[j][j] <- 1 / l_jj
+                double djj = A[j][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) djj = fma(-A[j][k], A[j][k], djj);
+                if (!(djj > 0.0)) ok = false;
+                const double inv = rsqrt(ok ? djj : 1.0);
+#pragma unroll
+                for (int i = j + 1; i < D; ++i) {
+                    double a = A[i][j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) a = fma(-A[i][k], A[j][k], a);
+                    A[i][j] = a * inv;
+                }
+                A[j][j] = inv;
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) {                     // L z = -g
+                double z = y[j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) z = fma(-A[j][k], y[k], z);
+                y[j] = z * A[j][j];
+            }
+#pragma unroll
+            for (int j = D - 1; j >= 0; --j) {                // L^T x = z
+                double z = y[j];
+#pragma unroll
+                for (int k = j + 1; k < D; ++k) z = fma(-A[k][j], y[k], z);
+                y[j] = z * A[j][j];
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) vn[i] = fr[i] ? fmax(lo[i], v[i] + y[i]) : v[i];
+            const double qn = opt_q_scalar<M, S>(sm, vn);
+            double qb = (ok && qn < qv) ? qn : __longlong_as_double(0x7ff0000000000000LL);        // best of the four: lowest value, then lowest damping
+            int wb = wdx;
+#pragma unroll
+            for (int o = 1; o < PX_OPT_NDAMP; o <<= 1) {
+                const double q2 = __shfl_xor_sync(0xffffffffu, qb, o);
+                const int w2 = __shfl_xor_sync(0xffffffffu, wb, o);
+                if (q2 < qb || (q2 == qb && w2 < wb)) { qb = q2; wb = w2; }
+            }
+            if (qb < qv) {
+                accepted = true;
+                rel = (qv - qb) / fmax(fabs(qv), 1e-300);
+                const int src = (lane & ~(PX_OPT_NDAMP - 1)) | wb;
+#pragma unroll
+                for (int i = 0; i < D; ++i) v[i] = __shfl_sync(0xffffffffu, vn[i], src);
+                lam = fmax(__shfl_sync(0xffffffffu, lam_w, src), 1e-12);
             } else {
                 for (int i = 0; i < PX_OPT_NDAMP; ++i) lam *= 5.0;
             }
         }
         if (!accepted || rel < 1e-13) break;
     }
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) sm.v[i] = v[i];
-    sm.lam = fmin(lam, 1e-3);
+        for (int i = 0; i < D; ++i) sm.v[i] = v[i];
+        sm.lam = fmin(lam, 1e-3);
+    }
 }
 
 // register version (PX_OPT_NDAMP warps of the block, one damping each) where the problem is small enough (S <= 3 and
@@ -2854,8 +2856,8 @@ template <int M>
 __device__ __forceinline__ void opt_solve_dispatch(OptSmem &sm, int S, int lm_iters, int refine_bg, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
 #ifndef PX_OPT_NO_SCALAR
-    if constexpr (M + 2 <= 5) { if (S == 1) { if (tid == 0) opt_inner_solve_scalar<M, 1>(sm, lm_iters, refine_bg); return; } }
-    if constexpr (M + 4 <= 5) { if (S == 2) { if (tid == 0) opt_inner_solve_scalar<M, 2>(sm, lm_iters, refine_bg); return; } }
+    if constexpr (M + 2 <= 5) { if (S == 1) { if (warp == 0) opt_inner_solve_scalar<M, 1>(sm, lm_iters, refine_bg, lane); return; } }
+    if constexpr (M + 4 <= 5) { if (S == 2) { if (warp == 0) opt_inner_solve_scalar<M, 2>(sm, lm_iters, refine_bg, lane); return; } }
 #endif
     const bool team = warp < PX_OPT_NDAMP;
     if constexpr (PX_OPT_SCALAR_D < M + 2 && M + 2 <= 12) { if (S == 1) { if (team) opt_inner_solve_reg<M, 1>(sm, lm_iters, refine_bg, lane, warp); return; } }
@@ -2980,7 +2982,11 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
 #pragma unroll
                         for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[u][p], calc);
                         const double r = o[u] - calc;
-                        const double w = 1.0 / fmax(fabs(r), delta);
+                        // weight of the majoriser 1 / max(|r|, delta): the 20-bit reciprocal of the special-function unit
+                        // is enough (any positive weight majorises, the objective itself is summed exactly) and keeps
+                        // the division's Newton steps off the fp64 pipe this pass is bound by
+                        double w;
+                        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(w) : "d"(fmax(fabs(r), delta)));
                         acc[NACC - 1] += fabs(r);
                         int e = 0;
 #pragma unroll

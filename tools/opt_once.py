@@ -1,4 +1,4 @@
-"""one optimiser call on the c4 bench population (profiling aid: build with -DPX_OPT_PROFILE for cycle counters)"""
+"""one optimiser call on a bench population (argv: candidates, configuration name; default 256 c4) (profiling aid: build with -DPX_OPT_PROFILE for cycle counters)"""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +7,7 @@ import pyxrd_b200.calculations as calc
 from pyxrd_b200.batched import pack_population
 from pyxrd_b200.runtime import default_context
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-cfg = syn.CONFIGS["c4"]
+cfg = syn.CONFIGS[sys.argv[2] if len(sys.argv) > 2 else "c4"]
 truth, mixes = cfg.truth(), cfg.population(2024, K)
 def calc_total(mix):
     calc.mixture.calculate_mixture(mix)
