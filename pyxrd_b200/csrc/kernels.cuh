@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #define PX_TPB 128          // threads (= 2-theta points) per block in the phase kernels
 #define PX_GEN_TPB 64       // generic-rank fallback
@@ -2961,43 +2962,79 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
             // PIF points in flight per thread: the loads of all of them are issued before the arithmetic (few phases
             // leave registers for more points: the pass is bound by the latency of these loads)
             constexpr int PIF = MB <= 2 ? 8 : MB <= 4 ? 4 : 2;
-            for (int z = 0; z < Z; ++z)
-                for (int x0 = tid; x0 < X; x0 += PIF * TPB) {
+            auto accumulate = [&](const double (&phi)[PIF][MB], const double (&o)[PIF], const bool (&on)[PIF]) {
+#pragma unroll
+                for (int u = 0; u < PIF; ++u) {
+                    if (!on[u]) continue;
+                    double calc = 0.0;
+#pragma unroll
+                    for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[u][p], calc);
+                    const double r = o[u] - calc;
+                    // weight of the majoriser 1 / max(|r|, delta): the 20-bit reciprocal of the special-function unit
+                    // is enough (any positive weight majorises, the objective itself is summed exactly) and keeps
+                    // the division's Newton steps off the fp64 pipe
+                    double w;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(w) : "d"(fmax(fabs(r), delta)));
+                    acc[NACC - 1] += fabs(r);
+                    int e = 0;
+#pragma unroll
+                    for (int p = 0; p < MB; ++p) {
+                        const double wp = w * phi[u][p];
+                        acc[NG + p] = fma(wp, o[u], acc[NG + p]);
+#pragma unroll
+                        for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[u][q], acc[e]);
+                    }
+                }
+            };
+            if constexpr (MB <= 4) {
+                // few phases: the pass is bound by instruction issue, not by the fp64 pipe.  Full groups of PIF points
+                // read at constant offsets from one running pointer per array (no index arithmetic per load); the
+                // ragged end of the pattern goes through the same body with clamped offsets.
+                auto group = [&](auto full_c, const double *Ix, const double *cx, const double *ox,
+                                 const unsigned char *sx, int left) {
+                    constexpr bool FULL = decltype(full_c)::value;
                     double phi[PIF][MB], o[PIF];
                     bool on[PIF];
 #pragma unroll
                     for (int u = 0; u < PIF; ++u) {
-                        const int x = x0 + u * TPB;
-                        on[u] = x < X && sel[x];
-                        const int xc = x < X ? x : x0;
+                        const int off = FULL ? u * TPB : (u * TPB < left ? u * TPB : 0);
+                        on[u] = (FULL || u * TPB < left) && sx[off];
 #pragma unroll
-                        for (int p = 0; p < M; ++p) phi[u][p] = I[((long long)p * Z + z) * X + xc];
-                        phi[u][M] = corr[xc];
-                        o[u] = obs[(long long)z * X + xc];
+                        for (int p = 0; p < M; ++p) phi[u][p] = Ix[(long long)p * Z * X + off];
+                        phi[u][M] = cx[off];
+                        o[u] = ox[off];
                     }
-#pragma unroll
-                    for (int u = 0; u < PIF; ++u) {
-                        if (!on[u]) continue;
-                        double calc = 0.0;
-#pragma unroll
-                        for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[u][p], calc);
-                        const double r = o[u] - calc;
-                        // weight of the majoriser 1 / max(|r|, delta): the 20-bit reciprocal of the special-function unit
-                        // is enough (any positive weight majorises, the objective itself is summed exactly) and keeps
-                        // the division's Newton steps off the fp64 pipe this pass is bound by
-                        double w;
-                        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(w) : "d"(fmax(fabs(r), delta)));
-                        acc[NACC - 1] += fabs(r);
-                        int e = 0;
-#pragma unroll
-                        for (int p = 0; p < MB; ++p) {
-                            const double wp = w * phi[u][p];
-                            acc[NG + p] = fma(wp, o[u], acc[NG + p]);
-#pragma unroll
-                            for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[u][q], acc[e]);
-                        }
-                    }
+                    accumulate(phi, o, on);
+                };
+                for (int z = 0; z < Z; ++z) {
+                    const double *Ix = I + (long long)z * X + tid, *ox = obs + (long long)z * X + tid;
+                    const double *cx = corr + tid;
+                    const unsigned char *sx = sel + tid;
+                    int left = X - tid;                     // points from this thread's position to the end
+                    for (; left > (PIF - 1) * TPB; left -= PIF * TPB, Ix += PIF * TPB, ox += PIF * TPB, cx += PIF * TPB,
+                                                   sx += PIF * TPB)
+                        group(std::true_type(), Ix, cx, ox, sx, left);
+                    if (left > 0) group(std::false_type(), Ix, cx, ox, sx, left);
                 }
+            } else {
+                // many phases: indexed loads (a running pointer per phase would cost the registers of the accumulators)
+                for (int z = 0; z < Z; ++z)
+                    for (int x0 = tid; x0 < X; x0 += PIF * TPB) {
+                        double phi[PIF][MB], o[PIF];
+                        bool on[PIF];
+#pragma unroll
+                        for (int u = 0; u < PIF; ++u) {
+                            const int x = x0 + u * TPB;
+                            on[u] = x < X && sel[x];
+                            const int xc = x < X ? x : x0;
+#pragma unroll
+                            for (int p = 0; p < M; ++p) phi[u][p] = I[((long long)p * Z + z) * X + xc];
+                            phi[u][M] = corr[xc];
+                            o[u] = obs[(long long)z * X + xc];
+                        }
+                        accumulate(phi, o, on);
+                    }
+            }
             // block reduction of NACC (+ count) values
             const int lane = tid & 31, warp = tid >> 5;
 #ifdef PX_OPT_PROFILE
