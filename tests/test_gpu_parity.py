@@ -286,12 +286,14 @@ def test_device_optimizer_reaches_reference_optimum(calc, golden, name):
         assert (np.asarray(mix.bgshifts) >= 0).all()
 
 
-def test_device_optimizer_reports_the_true_objective(calc, golden):
-    """the residual the optimiser returns is the reference objective at the solution it returns"""
+@pytest.mark.parametrize("name", ["c1", "c2", "c4"])
+def test_device_optimizer_reports_the_true_objective(calc, golden, name):
+    """the residual the optimiser returns is the reference objective at the solution it returns (c1 / c2: the
+    single-lane solver for at most five unknowns, c4: the register team solver)"""
     from pyxrd_b200.batched import pack_population
     from pyxrd_b200.runtime import default_context
-    g = golden("c4")
-    mixes = [m for _, m in golden_mixtures("c4", g)]
+    g = golden(name)
+    mixes = [m for _, m in golden_mixtures(name, g)]
     for m in mixes:
         calc.mixture._parse_bookkeeping(m)
     static, batch = pack_population(mixes)
@@ -322,6 +324,14 @@ def test_device_optimizer_fixed_background_and_fallback(calc, golden):
     for m, a, b in zip(mixes, fixed, free):
         assert np.array_equal(m.bgshifts, [15.0, 18.0])
         assert a[0] >= b[0] * (1 - 1e-6)              # fewer free variables cannot fit better
+    # the same with one specimen and one phase (single-lane solver, background row fixed)
+    g2 = golden("c2")
+    one = [m for _, m in golden_mixtures("c2", g2)][:1]
+    one[0].bgshifts_mask = np.zeros(1)
+    one[0].bgshifts = np.array([7.0])
+    a = get_optimized_residuals(one)[0]
+    b = get_optimized_residuals([m for _, m in golden_mixtures("c2", g2)][:1])[0]
+    assert np.array_equal(one[0].bgshifts, [7.0]) and np.isfinite(a[0]) and a[0] >= b[0] * (1 - 1e-6)
     # a partially fixed fraction vector is outside the device optimiser: scipy-driven path
     part = [m for _, m in golden_mixtures("c4", g)][0]
     part.fractions_mask = np.array([1, 1, 1, 0, 1, 1])
