@@ -2288,6 +2288,9 @@ struct OptParams {
 #ifndef PX_OPT_NDAMP
 #define PX_OPT_NDAMP 4     // warps (= dampings tried side by side) of the register Levenberg-Marquardt solver
 #endif
+#ifndef PX_OPT_PTR_MB
+#define PX_OPT_PTR_MB 4      // up to this many columns the Gram pass reads through running pointers
+#endif
 #define PX_OPT_LDA 29      // row stride (doubles) of the d x d work matrices: odd, so a column is spread over all banks
 
 struct OptSmem {
@@ -2986,7 +2989,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
                     }
                 }
             };
-            if constexpr (MB <= 4) {
+            if constexpr (MB <= PX_OPT_PTR_MB) {
                 // few phases: the pass is bound by instruction issue, not by the fp64 pipe.  Full groups of PIF points
                 // read at constant offsets from one running pointer per array (no index arithmetic per load); the
                 // ragged end of the pattern goes through the same body with clamped offsets.
