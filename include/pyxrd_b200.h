@@ -128,7 +128,9 @@ typedef struct {
  * DataObject graphs and packing each of them (refinement/refiner.py:91-109,
  * mixture/models/mixture.py:53-85: 6.4 ms per trial in the reference, 70 us per trial in packing.py),
  * the template candidate is packed once and a binding table says which packed slot every refinable
- * drives: slot = scale * x[param] + offset.  The expansion runs on the device (pyxrd_set_population and the
+ * drives: slot = scale * x[param] + offset (or, for a slot several refinables drive together, slot *= ... / slot += ...:
+ * a cell volume a * b * d001 with b and d001 both refined, a component weight summed over two refined atom contents;
+ * phases/models/unit_cell_prop.py:199, atom_relations.py:244,363,498).  Rows apply in table order.  The expansion runs on the device (pyxrd_set_population and the
  * calls built on it; pyxrd_expand_population is the same expansion as native host code, for inspection and
  * tests); everything numeric that depends on the bound values -- probability matrices, CSDS distribution,
  * absolute scale, z-stretch -- is computed on the device by the batch prologue. */
@@ -140,11 +142,14 @@ typedef struct {
 #define PYXRD_BIND_FRACTION 5   /* fractions[index], index < M */
 #define PYXRD_BIND_SCALE 6      /* scales[index], index < S */
 #define PYXRD_BIND_BGSHIFT 7    /* bgshifts[index], index < S */
+#define PYXRD_BIND_MODE_SET 0       /* slot = v */
+#define PYXRD_BIND_MODE_MULTIPLY 1  /* slot = slot * v (after the row that set it) */
+#define PYXRD_BIND_MODE_ADD 2       /* slot = slot + v */
 typedef struct {
     int32_t param;              /* column of x */
     int32_t target;             /* PYXRD_BIND_* */
     int32_t index;              /* flat index inside the TEMPLATE's array */
-    int32_t reserved;
+    int32_t mode;               /* PYXRD_BIND_MODE_*: with v = scale * x[param] + offset */
     double scale, offset;
 } pyxrd_binding;
 

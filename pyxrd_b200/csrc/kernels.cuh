@@ -585,16 +585,19 @@ __global__ void __launch_bounds__(128) k_expand_population(ExpandDev e) {
         for (int b = 0; b < e.NB; ++b) {
             const pyxrd_binding bd = e.bind[b];
             const double v = __dadd_rn(__dmul_rn(bd.scale, xk[bd.param]), bd.offset);
+            double *slot;
             switch (bd.target) {
-                case 0: e.phase_d[(size_t)k * e.NP * 8 + bd.index] = v; break;
-                case 1: e.comp_d[(size_t)k * e.NC * 8 + bd.index] = v; break;
-                case 2: e.atom_d[(size_t)k * e.NA * 2 + bd.index] = v; break;
-                case 3: e.matrices[(size_t)k * e.NM + bd.index] = v; break;
-                case 4: e.pparam[(size_t)k * e.NP * PX_PROB_STRIDE + bd.index] = v; break;
-                case 5: e.frac[(size_t)k * e.M + bd.index] = v; break;
-                case 6: e.scales[(size_t)k * e.S + bd.index] = v; break;
-                default: e.bg[(size_t)k * e.S + bd.index] = v; break;
+                case 0: slot = e.phase_d + (size_t)k * e.NP * 8; break;
+                case 1: slot = e.comp_d + (size_t)k * e.NC * 8; break;
+                case 2: slot = e.atom_d + (size_t)k * e.NA * 2; break;
+                case 3: slot = e.matrices + (size_t)k * e.NM; break;
+                case 4: slot = e.pparam + (size_t)k * e.NP * PX_PROB_STRIDE; break;
+                case 5: slot = e.frac + (size_t)k * e.M; break;
+                case 6: slot = e.scales + (size_t)k * e.S; break;
+                default: slot = e.bg + (size_t)k * e.S; break;
             }
+            slot += bd.index;
+            *slot = bd.mode == 1 ? __dmul_rn(*slot, v) : bd.mode == 2 ? __dadd_rn(*slot, v) : v;
         }
     }
     __syncthreads();

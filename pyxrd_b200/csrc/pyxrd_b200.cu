@@ -1311,14 +1311,17 @@ int pyxrd_expand_population(const pyxrd_batch_desc *t, const pyxrd_population_de
                                {e->scales.data(), (size_t)S}, {e->bgshifts.data(), (size_t)S}};
     for (int b = 0; b < pop->n_bindings; ++b) {
         const pyxrd_binding &bd = pop->bindings[b];
-        if (bd.target < 0 || bd.target > 7 || bd.param < 0 || bd.param >= D || bd.index < 0 ||
+        if (bd.target < 0 || bd.target > 7 || bd.param < 0 || bd.param >= D || bd.index < 0 || bd.mode < 0 || bd.mode > 2 ||
             (size_t)bd.index >= targets[bd.target].per_candidate) {
             delete e;
             return bad("expand_population: binding " + std::to_string(b) + " is out of range");
         }
         const Target &tg = targets[bd.target];
-        for (int k = 0; k < K; ++k)
-            tg.base[(size_t)k * tg.per_candidate + bd.index] = bd.scale * pop->x[(size_t)k * D + bd.param] + bd.offset;
+        for (int k = 0; k < K; ++k) {
+            double &slot = tg.base[(size_t)k * tg.per_candidate + bd.index];
+            const double v = bd.scale * pop->x[(size_t)k * D + bd.param] + bd.offset;
+            slot = bd.mode == PYXRD_BIND_MODE_MULTIPLY ? slot * v : bd.mode == PYXRD_BIND_MODE_ADD ? slot + v : v;
+        }
     }
     if (pop->csds_auto_maximum)
         for (int k = 0; k < K; ++k)
@@ -1372,8 +1375,12 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
                            model_driven ? (size_t)NP * PYXRD_PROB_STRIDE : 0, (size_t)M, (size_t)S, (size_t)S};
     for (int b = 0; b < NB; ++b) {
         const pyxrd_binding &bd = pop->bindings[b];
-        if (bd.target < 0 || bd.target > 7 || bd.param < 0 || bd.param >= D || bd.index < 0 || (size_t)bd.index >= per[bd.target])
+        if (bd.target < 0 || bd.target > 7 || bd.param < 0 || bd.param >= D || bd.index < 0 || bd.mode < 0 || bd.mode > 2 ||
+            (size_t)bd.index >= per[bd.target])
             return fail(ctx, "set_population: binding %d is out of range", b);
+        if (bd.mode != PYXRD_BIND_MODE_SET && pop->csds_auto_maximum && bd.target == PYXRD_BIND_PHASE_D &&
+            bd.index % PYXRD_PHASE_D_STRIDE == 1 && pop->csds_auto_maximum[bd.index / PYXRD_PHASE_D_STRIDE])
+            return fail(ctx, "set_population: binding %d: a CSDS average with an automatic maximum takes one refinable", b);
     }
     // template job tables and classes (K = 1); every candidate repeats them
     std::vector<int> job_pb, job_spec, jobids;

@@ -28,6 +28,7 @@ from .runtime import BINDING_DTYPE, Context, default_context, expand_population
 
 # PYXRD_BIND_* of include/pyxrd_b200.h
 BIND_PHASE_D, BIND_COMP_D, BIND_ATOM_D, BIND_MATRIX, BIND_PROB_PARAM, BIND_FRACTION, BIND_SCALE, BIND_BGSHIFT = range(8)
+BIND_MODE_SET, BIND_MODE_MULTIPLY, BIND_MODE_ADD = range(3)      # include/pyxrd_b200.h PYXRD_BIND_MODE_*
 
 _PHASE_SLOTS = {"sigma_star": 0}
 _CSDS_SLOTS = {"average": 1, "alpha_scale": 2, "alpha_offset": 3, "beta_scale": 4, "beta_offset": 5}
@@ -102,17 +103,24 @@ class PopulationTemplate(object):
     def from_table(cls, mixture, bindings, bounds, names=None, csds_auto=None, csds_factor: Optional[float] = None,
                    static: Optional[StaticPack] = None):
         """a template whose binding table is given (``discover_template``, or a table stored with a project): ``bindings``
-        structured array / rows ``(param, target, index, scale, offset)``; ``bounds`` f64[d, 2]"""
+        structured array / rows ``(param, target, index, scale, offset[, mode])``; ``bounds`` f64[d, 2].  Rows apply in
+        order; ``mode`` BIND_MODE_SET (default) ``slot = scale x + offset``, BIND_MODE_MULTIPLY ``slot *= ...``,
+        BIND_MODE_ADD ``slot += ...``"""
         bounds = np.asarray(bounds, dtype=float).reshape(-1, 2)
         names = list(names) if names is not None else ["x%d" % i for i in range(len(bounds))]
         self = cls(mixture, [Refinable(n, [], lo, hi) for n, (lo, hi) in zip(names, bounds)], csds_auto_maximum=False,
                    csds_factor=csds_factor, static=static)
-        table = np.asarray(bindings)
-        if table.dtype != BINDING_DTYPE:
-            rows = [tuple(r) for r in table]
+        table = bindings if isinstance(bindings, np.ndarray) else None
+        if table is None or table.dtype != BINDING_DTYPE:
+            if table is not None and table.dtype.names:     # a stored table with other field names: by position
+                rows = [(r[0], r[1], r[2], r[4], r[5], r[3]) for r in table]
+            else:
+                rows = [tuple(r) for r in bindings]
             table = np.zeros(len(rows), dtype=BINDING_DTYPE)
-            for i, (param, target, index, scale, offset) in enumerate(rows):
-                table[i] = (int(param), int(target), int(index), 0, float(scale), float(offset))
+            for i, row in enumerate(rows):
+                param, target, index, scale, offset = row[:5]
+                mode = int(row[5]) if len(row) > 5 else BIND_MODE_SET
+                table[i] = (int(param), int(target), int(index), mode, float(scale), float(offset))
         self.bindings = np.ascontiguousarray(table)
         auto = None if csds_auto is None else np.ascontiguousarray(csds_auto, dtype=np.uint8)
         self.csds_auto = auto if auto is not None and auto.any() else None
@@ -303,7 +311,9 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
     (``Refiner.get_data_object``, refinement/refiner.py:100-106: it writes x into the MVC model -- inheritance, unit-cell
     and atom-ratio relations included -- and rebuilds the DataObject graph).  The template is the packed graph at ``x0``;
     every refinable is moved twice, the packed arrays are compared, and every slot that moved must have moved affinely
-    (``slot = scale * x_i + offset``); the table is then checked against ``verify`` random solutions.  Non-affine slots are
+    (``slot = scale * x_i + offset``); a slot that two or more refinables move is probed once more with both moved and
+    bound as their product (cell volume a * b * d001) or their sum (component weight over refined atom contents);
+    the table is then checked against ``verify`` random solutions.  Non-affine slots are
     accepted in two forms only: the CSDS maximum following its average (``int(factor * average)``), and probability
     matrices of phases for which ``phase_model(s, z, m) -> (name, parameter names, values) | None`` names the reference's
     probability model -- those phases become model-driven (W, P computed on the device) and the refinable is bound to the
@@ -365,6 +375,15 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
             pool_owner[row[6]:row[6] + 2 * row[1] * row[1]] = p
     model_driven = batch0.prob_model if batch0.prob_model is not None else np.zeros(len(batch0.phase_i), dtype=np.int32)
     rows, bound_by = [], {}
+    probes, joint_cache = {}, {}          # refinable -> (its first probe value, the arrays there); (j, i) -> arrays
+
+    def joint_probe(j, i):
+        if (j, i) not in joint_cache:
+            x = x0.copy()
+            x[j], x[i] = probes[j][0], probes[i][0]
+            joint_cache[(j, i)] = arrays(pack(x)[1])
+        return joint_cache[(j, i)]
+
     auto = np.zeros(len(batch0.phase_i), dtype=np.uint8)
     for i in range(d):
         lo, hi = bounds[i]
@@ -375,6 +394,7 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
         xa[i] += step
         xb[i] += 2.0 * step
         A, B = arrays(pack(xa)[1]), arrays(pack(xb)[1])
+        probes[i] = (xa[i], A)
         if not (same_structure(base, A) and same_structure(base, B)):
             raise NotImplementedError("refinable %r changes the structure of the packed mixture" % (names[i],))
         da, db = xa[i] - x0[i], xb[i] - x0[i]
@@ -394,10 +414,31 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
                     offset = 0.0
                 slot = (target, int(idx))
                 if slot in bound_by:
-                    raise NotImplementedError("%s[%d] depends on the refinables %r and %r together" %
-                                              (key, idx, names[bound_by[slot]], names[i]))
-                bound_by[slot] = i
-                rows.append((i, target, int(idx), float(scale), float(offset)))
+                    # a slot two refinables drive: a product (cell volume a * b * d001) or a sum (component weight over
+                    # two refined atom contents).  One joint probe tells which; the row multiplies / adds to what
+                    # the earlier rows of the slot left.
+                    j = bound_by[slot][0]
+                    joint = joint_probe(j, i)[key][idx]
+                    dj = probes[j][1][key][idx] - v0[idx]
+                    di = va[idx] - v0[idx]
+                    tol = 1e-9 * max(abs(v0[idx]), abs(joint), abs(di), abs(dj))
+                    if key == "phase_d" and idx % PHASE_D_STRIDE == 1:
+                        raise NotImplementedError("the CSDS average phase_d[%d] depends on the refinables %r and %r together"
+                                                  % (idx, names[j], names[i]))
+                    if abs(joint - (v0[idx] + di + dj)) <= tol:
+                        rows.append((i, target, int(idx), float(scale), float(-scale * x0[i]), BIND_MODE_ADD))
+                    elif v0[idx] != 0.0 and abs(joint - (v0[idx] + di) * (v0[idx] + dj) / v0[idx]) <= tol:
+                        rel = scale / v0[idx]
+                        one = 1.0 - rel * x0[i]
+                        rows.append((i, target, int(idx), float(rel), 0.0 if abs(one) < 1e-12 else float(one),
+                                     BIND_MODE_MULTIPLY))
+                    else:
+                        raise NotImplementedError("%s[%d] depends on the refinables %r and %r together, neither as a sum "
+                                                  "nor as a product" % (key, idx, names[j], names[i]))
+                    bound_by[slot].append(i)
+                    continue
+                bound_by[slot] = [i]
+                rows.append((i, target, int(idx), float(scale), float(offset), BIND_MODE_SET))
         for p in np.nonzero((A["maximum"] != base["maximum"]) | (B["maximum"] != base["maximum"]))[0]:
             avg = [arr["phase_d"][p * PHASE_D_STRIDE + 1] for arr in (base, A, B)]
             if [int(factor * a) for a in avg] != [int(arr["maximum"][p]) for arr in (base, A, B)]:

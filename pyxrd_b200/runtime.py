@@ -41,11 +41,11 @@ class BatchDesc(C.Structure):
 
 
 class Binding(C.Structure):
-    _fields_ = [("param", C.c_int32), ("target", C.c_int32), ("index", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("param", C.c_int32), ("target", C.c_int32), ("index", C.c_int32), ("mode", C.c_int32),
                 ("scale", C.c_double), ("offset", C.c_double)]
 
 
-BINDING_DTYPE = np.dtype([("param", "<i4"), ("target", "<i4"), ("index", "<i4"), ("reserved", "<i4"),
+BINDING_DTYPE = np.dtype([("param", "<i4"), ("target", "<i4"), ("index", "<i4"), ("mode", "<i4"),
                           ("scale", "<f8"), ("offset", "<f8")])
 
 

@@ -2,7 +2,8 @@
 Build container only.
 
 The reference's integration fixture is loaded through its unmodified model layer, a set of its refinables is switched
-on (the two R0G3 weight fractions the project ships with, basal spacings, C-length deviations, sigma*), and a reference
+on (the two R0G3 weight fractions the project ships with, basal spacings, C-length deviations, sigma*, the one
+refinable cell length b), and a reference
 ``Refiner`` (refinement/refiner.py) is asked for the DataObject graph of solutions.  ``population.template_from_refiner``
 discovers the binding table by probing it.  Stored: the template graph carried into ``pyxrd_b200.data_objects``
 instances, the table, and -- for a set of random solutions -- what the REFERENCE makes of them: the packed arrays of
@@ -42,9 +43,11 @@ def main():
         r = node.object
         if r.prop_descr is None or not r.refinable:
             continue
-        if r.label in ("d001", "delta_c", "sigma_star", "F1", "F2"):
+        if r.label in ("d001", "delta_c", "sigma_star", "F1", "F2", "ucp_b"):
             if r.label == "d001" and r.value_max - r.value_min > 1.0:      # the project leaves some at [0, 5]
                 r.value_min, r.value_max = 0.97 * r.value, 1.03 * r.value
+            if r.label == "ucp_b":              # cell length b: the volume a * b * d001 of a component whose d001 is
+                r.value_min, r.value_max = 0.97 * r.value, 1.03 * r.value      # refined too (a product binding)
             r.refine = True
             chosen += 1
     mixture.refinement.refine_method_index = 0            # L BFGS B (any method: only the refiner's plumbing is used)

@@ -1,7 +1,7 @@
 """Binding tables discovered from a model layer (population.discover_template).
 
 ``binding.pkl / binding.npz`` were made in the build container by ``tests/golden/make_binding_golden.py``: the REFERENCE's
-running model layer (its integration fixture, 36 refinables switched on, a reference ``Refiner``) was probed for the table;
+running model layer (its integration fixture, 37 refinables switched on, a reference ``Refiner``) was probed for the table;
 the golden vectors are what the reference itself makes of 12 random solutions."""
 import copy
 import os
@@ -30,7 +30,7 @@ def reference_binding():
 def test_discovered_table_reproduces_the_reference_model_layer():
     """expansion of the stored table = packing of the graphs the reference's MVC built for the same solutions"""
     tmpl, g = reference_binding()
-    assert tmpl.n_params == 36 and len(tmpl.bindings) == 49
+    assert tmpl.n_params == 37 and len(tmpl.bindings) == 50
     got = tmpl.expand(g["x"])
     K = len(g["x"])
     for key in ("phase_d", "comp_d", "atom_d", "prob_params", "fractions", "scales", "bgshifts"):
@@ -44,6 +44,13 @@ def test_discovered_table_reproduces_the_reference_model_layer():
     names = [str(n) for n in g["names"]]
     assert sum("W1/Sum" in n or "W2/Sum" in n for n in names) == 6
     assert int(np.sum(tmpl.bindings["target"] == 4)) == 6
+    # and the cell length b of a component whose d001 is refined as well: its volume a * b * d001
+    # (phases/models/unit_cell_prop.py:199) is set by b and multiplied by d001 / d001_0
+    b = names.index("Cell length b [nm]")
+    row = tmpl.bindings[tmpl.bindings["param"] == b]
+    assert len(row) == 1 and int(row["target"][0]) == 1 and int(row["index"][0]) % 8 == 4 and int(row["mode"][0]) == 0
+    shared = tmpl.bindings[(tmpl.bindings["target"] == 1) & (tmpl.bindings["index"] == row["index"][0])]
+    assert len(shared) == 2 and int(shared["mode"][1]) == 1 and shared["offset"][1] == 0.0
 
 
 def _toy_model_layer(nonlinear=False, coupled=False):
@@ -61,7 +68,10 @@ def _toy_model_layer(nonlinear=False, coupled=False):
             row[0].CSDS.average = x[2]
             row[0].CSDS.maximum = int(2.5 * x[2])
         a[3].components[1].d001 = x[3]
-        a[3].components[1].volume = 0.468 * x[3] * (x[0] if coupled else 1.0)
+        a[3].components[1].volume = 0.468 * (x[3] * (x[0] + 2.0) if coupled == "product" else
+                                             x[3] * x[0] + x[3] + x[0] if coupled == "mixed" else x[3])
+        if coupled == "product":                      # a sum as well: a component weight over two refined contents
+            a[3].components[1].weight = 300.0 + 16.0 * x[1] + 27.0 * x[4]
         if nonlinear:
             e[3].components[1].delta_c = 0.01 * x[3] ** 2
         mix.fractions = np.array([x[4], 0.1, 0.1, 0.25, 0.1, 0.45 - x[4]])
@@ -102,13 +112,37 @@ def test_discovery_on_a_toy_model_layer():
     assert np.array_equal(got["phase_i"][:, 3], want.phase_i[:, 3])
 
 
+def test_discovery_of_slots_driven_by_two_refinables():
+    """a cell volume a * b * d001 with two of the factors refined (phases/models/unit_cell_prop.py:199) is a product
+    of affine functions, a component weight over two refined atom contents (atom_relations.py:244) a sum: both are
+    found with one joint probe and expanded by multiply / add rows"""
+    from pyxrd_b200 import packing
+    from pyxrd_b200.population import BIND_MODE_ADD, BIND_MODE_MULTIPLY, BIND_MODE_SET
+    build, _ = _toy_model_layer(coupled="product")
+    x0 = np.array([6.0, 0.6, 10.0, 1.25, 0.3])
+    bounds = np.array([[2.0, 12.0], [0.3, 0.9], [8.0, 14.0], [1.22, 1.28], [0.05, 0.4]])
+    tmpl = discover_template(build, x0, bounds, verify=5)
+    modes = {(int(r["param"]), int(r["mode"])) for r in tmpl.bindings if int(r["target"]) == 1}
+    assert (0, BIND_MODE_SET) in modes and (3, BIND_MODE_MULTIPLY) in modes          # volume: sigma first, then d001
+    assert (1, BIND_MODE_SET) in modes and (4, BIND_MODE_ADD) in modes               # weight: W1 first, then f0
+    x = bounds[:, 0] + np.random.default_rng(3).uniform(0, 1, (7, 5)) * (bounds[:, 1] - bounds[:, 0])
+    got = tmpl.expand(x)
+    want = packing.BatchPack([build(row) for row in x], tmpl.static)
+    for key in ("phase_d", "comp_d", "atom_d", "prob_params", "fractions"):
+        assert np.allclose(got[key], getattr(want, key), rtol=1e-12, atol=0.0), key
+    # the stored table round-trips through rows with and without the mode column
+    again = PopulationTemplate.from_table(tmpl.mixture, [tuple(r) for r in tmpl.bindings[["param", "target", "index", "scale", "offset", "mode"]]],
+                                          bounds, csds_auto=tmpl.csds_auto, csds_factor=tmpl.csds_factor)
+    assert np.array_equal(again.bindings, tmpl.bindings)
+
+
 def test_discovery_refuses_what_a_table_cannot_express():
     x0 = np.array([6.0, 0.6, 10.0, 1.25, 0.3])
     bounds = np.array([[2.0, 12.0], [0.3, 0.9], [8.0, 14.0], [1.22, 1.28], [0.05, 0.4]])
     build, _ = _toy_model_layer(nonlinear=True)
     with pytest.raises(NotImplementedError, match="non-affinely"):
         discover_template(build, x0, bounds)
-    build, _ = _toy_model_layer(coupled=True)
+    build, _ = _toy_model_layer(coupled="mixed")
     with pytest.raises(NotImplementedError, match="together|interact"):
         discover_template(build, x0, bounds)
 

@@ -206,6 +206,42 @@ def test_device_expansion_equals_host_expansion(ctx, name, K):
         assert np.array_equal(dev_res, ctx.read_residuals())
 
 
+def test_multiply_and_add_rows_on_the_device(ctx):
+    """slots driven by two refinables (a product: cell volume; a sum: component weight): the device expansion applies
+    the rows in table order like the host expansion, and the result is what the model layer packs"""
+    import types
+    from pyxrd_b200 import packing
+    from pyxrd_b200.population import discover_template
+    from test_binding_golden import _toy_model_layer
+    build, _ = _toy_model_layer(coupled="product")
+    x0 = np.array([6.0, 0.6, 10.0, 1.25, 0.3])
+    bounds = np.array([[2.0, 12.0], [0.3, 0.9], [8.0, 14.0], [1.22, 1.28], [0.05, 0.4]])
+    tmpl = discover_template(build, x0, bounds, verify=2)
+    assert {1, 2} <= set(int(m) for m in tmpl.bindings["mode"])
+    x = bounds[:, 0] + np.random.default_rng(5).uniform(0, 1, (6, 5)) * (bounds[:, 1] - bounds[:, 0])
+    with ctx.lock:
+        ctx.set_static(tmpl.static)
+        ctx.set_population(tmpl.batch, x, tmpl.bindings, tmpl.csds_auto, tmpl.csds_factor)
+        ctx.compute_intensities()
+        dev_int = ctx.read_intensities_flat()
+        host = types.SimpleNamespace(**tmpl.expand(x))
+        host.S, host.Z = tmpl.batch.S, tmpl.batch.Z
+        ctx.set_batch(host)
+        ctx.compute_intensities()
+        assert np.array_equal(dev_int, ctx.read_intensities_flat())
+        want = packing.BatchPack([build(row) for row in x], tmpl.static)
+        ctx.set_batch(want)
+        ctx.compute_intensities()
+        assert rel_err(dev_int, ctx.read_intensities_flat()) < 1e-12
+    bad = tmpl.bindings.copy()
+    bad["mode"][0] = 3
+    from pyxrd_b200.runtime import DeviceError
+    with pytest.raises(DeviceError, match="out of range"):
+        tmpl2 = copy.copy(tmpl)
+        tmpl2.bindings = bad
+        tmpl2.residuals(x)
+
+
 def test_population_errors(ctx):
     from pyxrd_b200.runtime import DeviceError
     tmpl, refs = _template("c2")
@@ -282,7 +318,8 @@ def test_more_than_65535_patterns_in_one_batch(ctx):
 
 def test_table_discovered_from_the_reference_model_layer(ctx):
     """tests/golden/binding.*: the table was discovered by probing the reference's RUNNING model layer (its integration
-    fixture, 36 refinables); here the device evaluates the 12 stored solutions from the table alone and must agree with
+    fixture, 37 refinables, one slot bound as a product); here the device evaluates the 12 stored solutions from the table
+    alone and must agree with
     what the reference computed for the graphs its MVC built: calculate_mixture residuals at 1e-9, get_optimized_residual
     (= Refiner.get_residual) within the optimiser contract"""
     from test_binding_golden import reference_binding
