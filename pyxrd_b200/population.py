@@ -318,7 +318,8 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
     matrices of phases for which ``phase_model(s, z, m) -> (name, parameter names, values) | None`` names the reference's
     probability model -- those phases become model-driven (W, P computed on the device) and the refinable is bound to the
     model parameter that moved.  Anything else raises ``NotImplementedError`` naming the refinable: the caller then keeps
-    evaluating that refinement graph by graph (``batched.get_optimized_residuals``).  (2 d + 1 + verify) graph builds."""
+    evaluating that refinement graph by graph (``batched.get_optimized_residuals``).  (2 d + 2 + verify) graph builds,
+    one more per pair of refinables that share a slot."""
     x0 = np.array(x0, dtype=float).ravel()
     bounds = np.asarray(bounds, dtype=float).reshape(-1, 2)
     d = x0.size
@@ -363,6 +364,14 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
     def same_structure(a, b):
         return all(u.shape == v.shape and np.array_equal(u, v) for u, v in zip(a["structure"], b["structure"]))
 
+    # a model layer may carry values it only refreshes when something changes (the reference's unit-cell lengths follow
+    # atom contents through change signals, unit_cell_prop.py:199-201, and are stale in a freshly loaded project): move
+    # every refinable once before the template is taken, so that x0 is seen the way a refinement sees it
+    def first_step(i):
+        lo, hi = bounds[i]
+        return 0.25 * (hi - x0[i]) if (hi - x0[i]) >= (x0[i] - lo) else -0.25 * (x0[i] - lo)
+
+    get_data_object(x0 + np.array([first_step(i) for i in range(d)]))
     data0, batch0 = pack(x0)
     import copy
     template_data = copy.deepcopy(data0)                  # the model layer reuses its DataObjects between calls
@@ -386,8 +395,7 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
 
     auto = np.zeros(len(batch0.phase_i), dtype=np.uint8)
     for i in range(d):
-        lo, hi = bounds[i]
-        step = 0.25 * (hi - x0[i]) if (hi - x0[i]) >= (x0[i] - lo) else -0.25 * (x0[i] - lo)
+        step = first_step(i)
         if step == 0.0:
             raise ValueError("refinable %r has an empty range" % (names[i],))
         xa, xb = x0.copy(), x0.copy()

@@ -3,7 +3,7 @@ Build container only.
 
 The reference's integration fixture is loaded through its unmodified model layer, a set of its refinables is switched
 on (the two R0G3 weight fractions the project ships with, basal spacings, C-length deviations, sigma*, the one
-refinable cell length b), and a reference
+refinable cell length b, three interlayer atom contents of one component), and a reference
 ``Refiner`` (refinement/refiner.py) is asked for the DataObject graph of solutions.  ``population.template_from_refiner``
 discovers the binding table by probing it.  Stored: the template graph carried into ``pyxrd_b200.data_objects``
 instances, the table, and -- for a set of random solutions -- what the REFERENCE makes of them: the packed arrays of
@@ -41,7 +41,20 @@ def main():
     chosen = 0
     for node in mixture.refinement.refinables.iter_children():
         r = node.object
-        if r.prop_descr is None or not r.refinable:
+        if r.prop_descr is None:
+            # atom relations are refinement values themselves (phases/models/atom_relations.py:74-160): the three
+            # interlayer contents of one smectite component (several pn each; the component weight is their sum: add
+            # rows).  The Fe / Al ratios of this project are left out: cell lengths a and b both follow them, the
+            # volume is quadratic in the ratio and discover_template refuses it by name.
+            relation = type(r.obj).__name__ == "AtomContents" and r.refinable
+            where = (r.obj.component.name, r.obj.component.phase.name) if relation else None
+            if relation and where == ("Di-Smectite 2gly", "ISS R0 Ca-EG") and r.obj.name in (
+                    "Glycol content", "Water content", "Ca content"):
+                r.value_min, r.value_max = 0.9 * r.value, 1.1 * r.value
+                r.refine = True
+                chosen += 1
+            continue
+        if not r.refinable:
             continue
         if r.label in ("d001", "delta_c", "sigma_star", "F1", "F2", "ucp_b"):
             if r.label == "d001" and r.value_max - r.value_min > 1.0:      # the project leaves some at [0, 5]

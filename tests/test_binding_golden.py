@@ -1,7 +1,7 @@
 """Binding tables discovered from a model layer (population.discover_template).
 
 ``binding.pkl / binding.npz`` were made in the build container by ``tests/golden/make_binding_golden.py``: the REFERENCE's
-running model layer (its integration fixture, 37 refinables switched on, a reference ``Refiner``) was probed for the table;
+running model layer (its integration fixture, 40 refinables switched on, a reference ``Refiner``) was probed for the table;
 the golden vectors are what the reference itself makes of 12 random solutions."""
 import copy
 import os
@@ -30,7 +30,7 @@ def reference_binding():
 def test_discovered_table_reproduces_the_reference_model_layer():
     """expansion of the stored table = packing of the graphs the reference's MVC built for the same solutions"""
     tmpl, g = reference_binding()
-    assert tmpl.n_params == 37 and len(tmpl.bindings) == 50
+    assert tmpl.n_params == 40 and len(tmpl.bindings) == 60
     got = tmpl.expand(g["x"])
     K = len(g["x"])
     for key in ("phase_d", "comp_d", "atom_d", "prob_params", "fractions", "scales", "bgshifts"):
@@ -51,6 +51,14 @@ def test_discovered_table_reproduces_the_reference_model_layer():
     assert len(row) == 1 and int(row["target"][0]) == 1 and int(row["index"][0]) % 8 == 4 and int(row["mode"][0]) == 0
     shared = tmpl.bindings[(tmpl.bindings["target"] == 1) & (tmpl.bindings["index"] == row["index"][0])]
     assert len(shared) == 2 and int(shared["mode"][1]) == 1 and shared["offset"][1] == 0.0
+    # three interlayer atom contents of one smectite component (atom_relations.py:416: every content drives the pn of
+    # its atoms): the component weight is set by the first and the other two add to it
+    contents = [i for i, n in enumerate(names) if n in ("Glycol content", "Water content", "Ca content")]
+    assert len(contents) == 3
+    weight = tmpl.bindings[np.isin(tmpl.bindings["param"], contents) & (tmpl.bindings["target"] == 1)]
+    assert len(weight) == 3 and len(set(weight["index"])) == 1 and int(weight["index"][0]) % 8 == 5
+    assert [int(m) for m in weight["mode"]] == [0, 2, 2]
+    assert int(np.sum(np.isin(tmpl.bindings["param"], contents) & (tmpl.bindings["target"] == 2))) == 7     # the pn slots
 
 
 def _toy_model_layer(nonlinear=False, coupled=False):

@@ -318,7 +318,7 @@ def test_more_than_65535_patterns_in_one_batch(ctx):
 
 def test_table_discovered_from_the_reference_model_layer(ctx):
     """tests/golden/binding.*: the table was discovered by probing the reference's RUNNING model layer (its integration
-    fixture, 37 refinables, one slot bound as a product); here the device evaluates the 12 stored solutions from the table
+    fixture, 40 refinables, one slot bound as a product, one as a sum of three); here the device evaluates the 12 stored solutions from the table
     alone and must agree with
     what the reference computed for the graphs its MVC built: calculate_mixture residuals at 1e-9, get_optimized_residual
     (= Refiner.get_residual) within the optimiser contract"""
