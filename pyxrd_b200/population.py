@@ -312,7 +312,9 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
     and atom-ratio relations included -- and rebuilds the DataObject graph).  The template is the packed graph at ``x0``;
     every refinable is moved twice, the packed arrays are compared, and every slot that moved must have moved affinely
     (``slot = scale * x_i + offset``); a slot that two or more refinables move is probed once more with both moved and
-    bound as their product (cell volume a * b * d001) or their sum (component weight over refined atom contents);
+    bound as their product (cell volume a * b * d001) or their sum (component weight over refined atom contents); a
+    slot that is quadratic in one refinable with real roots (cell lengths a and b both following an atom ratio) becomes
+    two rows of that refinable, confirmed by a third probe;
     the table is then checked against ``verify`` random solutions.  Non-affine slots are
     accepted in two forms only: the CSDS maximum following its average (``int(factor * average)``), and probability
     matrices of phases for which ``phase_model(s, z, m) -> (name, parameter names, values) | None`` names the reference's
@@ -393,6 +395,15 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
             joint_cache[(j, i)] = arrays(pack(x)[1])
         return joint_cache[(j, i)]
 
+    third_cache = {}
+
+    def third_probe(i):
+        if i not in third_cache:
+            x = x0.copy()
+            x[i] += 3.0 * first_step(i)
+            third_cache[i] = (x[i], arrays(pack(x)[1]))
+        return third_cache[i]
+
     auto = np.zeros(len(batch0.phase_i), dtype=np.uint8)
     for i in range(d):
         step = first_step(i)
@@ -411,15 +422,35 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
             for idx in np.nonzero((va != v0) | (vb != v0))[0]:
                 if key == "matrices" and model_driven[pool_owner[idx]] != 0:
                     continue                              # W / P of a model-driven phase: computed on the device
+                what = "a probability matrix of a phase whose model was not named" if key == "matrices" else key
                 scale = (vb[idx] - v0[idx]) / db
-                if abs((va[idx] - v0[idx]) - scale * da) > 1e-9 * max(abs(v0[idx]), abs(vb[idx]), abs(scale * db)):
-                    what = "a probability matrix of a phase whose model was not named" if key == "matrices" else key
-                    raise NotImplementedError("refinable %r drives %s[%d] non-affinely" % (names[i], what, idx))
-                if abs(scale - 1.0) < 1e-12:
-                    scale = 1.0
-                offset = v0[idx] - scale * x0[i]
-                if abs(offset) < 1e-12 * max(abs(v0[idx]), 1e-300) or (scale == 1.0 and abs(offset) < 1e-15):
-                    offset = 0.0
+                if abs((va[idx] - v0[idx]) - scale * da) <= 1e-9 * max(abs(v0[idx]), abs(vb[idx]), abs(scale * db)):
+                    if abs(scale - 1.0) < 1e-12:
+                        scale = 1.0
+                    offset = v0[idx] - scale * x0[i]
+                    if abs(offset) < 1e-12 * max(abs(v0[idx]), 1e-300) or (scale == 1.0 and abs(offset) < 1e-15):
+                        offset = 0.0
+                    factors = [(float(scale), float(offset))]
+                else:
+                    # not affine: a product of two affine functions of the refinable?  (cell lengths a and b both follow
+                    # an Fe / Al ratio, unit_cell_prop.py:199-201: the volume is quadratic in it.)  v = v0 (1 + alpha t)
+                    # (1 + beta t), t = x - x0, from the two probes; a third probe confirms.
+                    if key == "matrices" or v0[idx] == 0.0:
+                        raise NotImplementedError("refinable %r drives %s[%d] non-affinely" % (names[i], what, idx))
+                    c2 = ((vb[idx] - v0[idx]) / db - (va[idx] - v0[idx]) / da) / (db - da)
+                    c1 = (va[idx] - v0[idx]) / da - c2 * da
+                    p_, q_ = c1 / v0[idx], c2 / v0[idx]
+                    disc = p_ * p_ - 4.0 * q_
+                    if disc < 0.0 and -disc < 1e-5 * p_ * p_:
+                        disc = 0.0                            # a square (volume ~ b^2): the roots coincide up to rounding
+                    third = third_probe(i)
+                    dc = third[0] - x0[i]
+                    vc = third[1][key][idx]
+                    if disc < 0.0 or abs(v0[idx] + c1 * dc + c2 * dc * dc - vc) > 1e-9 * max(abs(v0[idx]), abs(vc)):
+                        raise NotImplementedError("refinable %r drives %s[%d] non-affinely" % (names[i], what, idx))
+                    alpha, beta = 0.5 * (p_ + np.sqrt(disc)), 0.5 * (p_ - np.sqrt(disc))
+                    factors = [(float(v0[idx] * alpha), float(v0[idx] * (1.0 - alpha * x0[i]))),
+                               (float(beta), float(1.0 - beta * x0[i]))]
                 slot = (target, int(idx))
                 if slot in bound_by:
                     # a slot two refinables drive: a product (cell volume a * b * d001) or a sum (component weight over
@@ -433,20 +464,23 @@ def discover_template(get_data_object, x0, bounds, names=None, phase_model=None,
                     if key == "phase_d" and idx % PHASE_D_STRIDE == 1:
                         raise NotImplementedError("the CSDS average phase_d[%d] depends on the refinables %r and %r together"
                                                   % (idx, names[j], names[i]))
-                    if abs(joint - (v0[idx] + di + dj)) <= tol:
-                        rows.append((i, target, int(idx), float(scale), float(-scale * x0[i]), BIND_MODE_ADD))
+                    if len(factors) == 1 and abs(joint - (v0[idx] + di + dj)) <= tol:
+                        rows.append((i, target, int(idx), factors[0][0], float(-factors[0][0] * x0[i]), BIND_MODE_ADD))
                     elif v0[idx] != 0.0 and abs(joint - (v0[idx] + di) * (v0[idx] + dj) / v0[idx]) <= tol:
-                        rel = scale / v0[idx]
-                        one = 1.0 - rel * x0[i]
-                        rows.append((i, target, int(idx), float(rel), 0.0 if abs(one) < 1e-12 else float(one),
-                                     BIND_MODE_MULTIPLY))
+                        for n, (f_scale, f_offset) in enumerate(factors):
+                            if n == 0:                        # relative to the value the earlier rows leave at x0
+                                f_scale, f_offset = f_scale / v0[idx], f_offset / v0[idx]
+                                if abs(f_offset) < 1e-12:
+                                    f_offset = 0.0
+                            rows.append((i, target, int(idx), float(f_scale), float(f_offset), BIND_MODE_MULTIPLY))
                     else:
                         raise NotImplementedError("%s[%d] depends on the refinables %r and %r together, neither as a sum "
                                                   "nor as a product" % (key, idx, names[j], names[i]))
                     bound_by[slot].append(i)
                     continue
                 bound_by[slot] = [i]
-                rows.append((i, target, int(idx), float(scale), float(offset), BIND_MODE_SET))
+                for n, (f_scale, f_offset) in enumerate(factors):
+                    rows.append((i, target, int(idx), f_scale, f_offset, BIND_MODE_SET if n == 0 else BIND_MODE_MULTIPLY))
         for p in np.nonzero((A["maximum"] != base["maximum"]) | (B["maximum"] != base["maximum"]))[0]:
             avg = [arr["phase_d"][p * PHASE_D_STRIDE + 1] for arr in (base, A, B)]
             if [int(factor * a) for a in avg] != [int(arr["maximum"][p]) for arr in (base, A, B)]:

@@ -44,8 +44,10 @@ def main():
         if r.prop_descr is None:
             # atom relations are refinement values themselves (phases/models/atom_relations.py:74-160): the three
             # interlayer contents of one smectite component (several pn each; the component weight is their sum: add
-            # rows).  The Fe / Al ratios of this project are left out: cell lengths a and b both follow them, the
-            # volume is quadratic in the ratio and discover_template refuses it by name.
+            # rows).  The Fe / Al ratios of this project are left out: cell length b follows the ratio and cell length
+            # a follows b, but a is refreshed one solution late (it is computed from the b of the PREVIOUS solution:
+            # the volume the reference uses depends on the order in which solutions were applied), which no table can
+            # express; discover_template refuses it by name and such a refinement stays on the graph-by-graph path.
             relation = type(r.obj).__name__ == "AtomContents" and r.refinable
             where = (r.obj.component.name, r.obj.component.phase.name) if relation else None
             if relation and where == ("Di-Smectite 2gly", "ISS R0 Ca-EG") and r.obj.name in (

@@ -81,7 +81,10 @@ def _toy_model_layer(nonlinear=False, coupled=False):
         if coupled == "product":                      # a sum as well: a component weight over two refined contents
             a[3].components[1].weight = 300.0 + 16.0 * x[1] + 27.0 * x[4]
         if nonlinear:
-            e[3].components[1].delta_c = 0.01 * x[3] ** 2
+            e[3].components[1].delta_c = 0.01 * x[3] ** 3
+        if coupled == "product":                      # quadratic in one refinable: distinct roots, and a square
+            e[3].components[1].delta_c = 0.01 * (x[3] + 0.5) * (2.0 * x[3] - 1.0)
+            e[3].components[1].volume = 0.3 * (0.2 * x[3] + 0.9) ** 2
         mix.fractions = np.array([x[4], 0.1, 0.1, 0.25, 0.1, 0.45 - x[4]])
         return mix
 
@@ -133,6 +136,11 @@ def test_discovery_of_slots_driven_by_two_refinables():
     modes = {(int(r["param"]), int(r["mode"])) for r in tmpl.bindings if int(r["target"]) == 1}
     assert (0, BIND_MODE_SET) in modes and (3, BIND_MODE_MULTIPLY) in modes          # volume: sigma first, then d001
     assert (1, BIND_MODE_SET) in modes and (4, BIND_MODE_ADD) in modes               # weight: W1 first, then f0
+    # quadratic in d001 alone (cell lengths a and b both following one atom ratio make a volume like this): two rows
+    quad = {}
+    for r in tmpl.bindings[(tmpl.bindings["param"] == 3) & (tmpl.bindings["target"] == 1)]:
+        quad.setdefault(int(r["index"]), []).append(int(r["mode"]))
+    assert sorted(quad.values()) == [[0], [0, 1], [0, 1], [1]]      # d001 itself, delta_c, the square, the product above
     x = bounds[:, 0] + np.random.default_rng(3).uniform(0, 1, (7, 5)) * (bounds[:, 1] - bounds[:, 0])
     got = tmpl.expand(x)
     want = packing.BatchPack([build(row) for row in x], tmpl.static)
