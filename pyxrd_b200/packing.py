@@ -62,7 +62,14 @@ def prob_model_of(phase):
     return code, params
 
 
-def _atype_key(at) -> bytes:
+def _atype_key(at, memo: Optional[dict] = None) -> bytes:
+    """value key of an atom type; ``memo`` (id -> key, valid for the duration of ONE packing call: the objects are
+    alive and unchanged meanwhile) saves rebuilding it for every atom that shares the type object"""
+    if memo is not None:
+        key = memo.get(id(at))
+        if key is None:
+            key = memo[id(at)] = _atype_key(at)
+        return key
     row = np.empty(ATYPE_STRIDE)
     row[0:5] = np.asarray(at.par_a, dtype=float)
     row[5:10] = np.asarray(at.par_b, dtype=float)
@@ -81,6 +88,7 @@ def iter_phases(specimen):
 def collect_atom_types(mixtures_or_specimens) -> Dict[bytes, int]:
     """value-keyed table of every atom type reachable from the given specimens"""
     table: Dict[bytes, int] = {}
+    memo: dict = {}
     for spec in mixtures_or_specimens:
         if spec is None:
             continue
@@ -92,11 +100,28 @@ def collect_atom_types(mixtures_or_specimens) -> Dict[bytes, int]:
             for comp in phase.components:
                 for atom in list(comp.layer_atoms) + list(comp.interlayer_atoms):
                     if atom is not None and atom.atom_type is not None:
-                        table.setdefault(_atype_key(atom.atom_type), len(table))
+                        table.setdefault(_atype_key(atom.atom_type, memo), len(table))
     return table
 
 
+_WL_CACHE: Dict[tuple, tuple] = {}      # the serial drop-in calls rebuild the same tables for every trial
+
+
 def wavelength_tables(theta: np.ndarray, wavelength: float, distribution):
+    """``_wavelength_tables`` behind a small value-keyed cache (abscissa bytes, wavelength, list): read-only results"""
+    key = (np.ascontiguousarray(theta, dtype=float).tobytes(), float(wavelength),
+           tuple((float(w), float(f)) for w, f in distribution))
+    hit = _WL_CACHE.get(key)
+    if hit is None:
+        if len(_WL_CACHE) >= 32:
+            _WL_CACHE.clear()
+        hit = _WL_CACHE[key] = _wavelength_tables(theta, wavelength, distribution)
+        for arr in hit:
+            arr.setflags(write=False)
+    return hit
+
+
+def _wavelength_tables(theta: np.ndarray, wavelength: float, distribution):
     """index / weights of the shifted-abscissa linear interpolation, per list entry.
 
     scipy 1.18.1 ``interp1d._call_linear`` + ``_check_bounds``: ``hi =
@@ -251,6 +276,7 @@ class BatchPack(object):
         self.phase_index: Dict[int, int] = {}
         self.comp_index: Dict[int, int] = {}
         self.atom_index: Dict[int, int] = {}
+        self._atype_memo: dict = {}
         fractions = []
         scales = np.zeros((K, S))
         bgshifts = np.zeros((K, S))
@@ -296,6 +322,7 @@ class BatchPack(object):
         self.phase_d = np.ascontiguousarray(np.array(phase_d, dtype=float).reshape(-1, PHASE_D_STRIDE))
         self.phase_comp = np.ascontiguousarray(np.array(phase_comp, dtype=np.int32))
         self.matrices = np.ascontiguousarray(np.concatenate(matrices) if matrices else np.zeros(0), dtype=float)
+        self._atype_memo = {}              # ids are only meaningful while the graphs are being walked
         self.comp_d = np.ascontiguousarray(np.array(comp_d, dtype=float).reshape(-1, COMP_D_STRIDE))
         self.comp_i = np.ascontiguousarray(np.array(comp_i, dtype=np.int32).reshape(-1, COMP_I_STRIDE))
         self.atom_d = np.ascontiguousarray(np.array(atom_d, dtype=float).reshape(-1, ATOM_D_STRIDE))
@@ -396,6 +423,6 @@ class BatchPack(object):
                         atom_t.append(-1)
                     else:
                         atom_d.extend([float(atom.pn), float(atom.default_z)])
-                        atom_t.append(static.atom_types[_atype_key(atom.atom_type)])
+                        atom_t.append(static.atom_types[_atype_key(atom.atom_type, self._atype_memo)])
             phase_comp.append(cid)
         return mat_off
