@@ -100,3 +100,30 @@ def test_binding_errors():
         ph = syn.CONFIGS["c2"].truth().specimens[0].phases[0][0]
         ph.prob_model, ph.prob_params = "R2G2", [0.5]
         packing.prob_model_of(ph)
+
+
+def test_packing_caches_are_keyed_by_value():
+    """the serial drop-in calls repack a graph per trial: atom-type keys are memoised per packing call (by object),
+    wavelength tables cached across calls (by value) -- neither may change what is packed"""
+    mix, _ = syn.template("c2")
+    spec = mix.specimens[0]
+    g = spec.goniometer
+    a = packing.wavelength_tables(spec.range_theta, g.wavelength, g.wavelength_distribution)
+    b = packing.wavelength_tables(np.array(spec.range_theta), g.wavelength, list(g.wavelength_distribution))
+    assert all(u is v for u, v in zip(a, b)) and not a[1].flags.writeable            # one read-only entry
+    fresh = packing._wavelength_tables(spec.range_theta, g.wavelength, g.wavelength_distribution)
+    assert all(np.array_equal(u, v) for u, v in zip(a, fresh))
+    c = packing.wavelength_tables(spec.range_theta, g.wavelength * 1.001, g.wavelength_distribution)
+    assert not np.array_equal(a[2], c[2])
+    # equal-valued atom types held by different objects land on the same table row, a changed one on a new row
+    other = copy.deepcopy(mix)
+    atoms = [at for ph in packing.iter_phases(other.specimens[0]) for comp in ph.components
+             for at in list(comp.layer_atoms) + list(comp.interlayer_atoms) if at is not None and at.atom_type is not None]
+    atoms[0].atom_type = copy.deepcopy(atoms[0].atom_type)
+    types = packing.collect_atom_types(other.specimens)
+    assert types == packing.collect_atom_types(mix.specimens)
+    one = packing.BatchPack([other], packing.StaticPack(other.specimens, types))
+    two = packing.BatchPack([mix], packing.StaticPack(mix.specimens, types))
+    assert np.array_equal(one.atom_type, two.atom_type)
+    atoms[0].atom_type.debye = float(atoms[0].atom_type.debye) + 0.25
+    assert len(packing.collect_atom_types(other.specimens)) == len(types) + 1
