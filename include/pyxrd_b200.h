@@ -28,7 +28,7 @@ extern "C" {
 typedef struct pyxrd_ctx pyxrd_ctx;
 
 /* layout strides of the packed parameter tables */
-#define PYXRD_GONIO_STRIDE 12 /* wavelength, soller1, soller2, mcr_2theta, divergence_mode (0 FIXED, 1 AUTOMATIC, 2 other), divergence, has_absorption_correction, absorption, sample_surf_density, sample_length, radius, reserved */
+#define PYXRD_GONIO_STRIDE 12 /* wavelength, soller1, soller2, mcr_2theta, divergence_mode (0 FIXED, 1 AUTOMATIC, 2 other), divergence, has_absorption_correction, absorption, sample_surf_density, sample_length, radius, has_observations (0: the specimen's residual is 0.0, mixture.py:247-251) */
 #define PYXRD_ATYPE_STRIDE 12 /* par_a[5], par_b[5], par_c, debye */
 #define PYXRD_PHASE_I_STRIDE 8 /* G, rank, csds_minimum, csds_maximum, flags, comp_list_begin, matrix_offset, reserved */
 #define PYXRD_PHASE_D_STRIDE 8 /* sigma_star, csds_average, alpha_scale, alpha_offset, beta_scale, beta_offset, reserved x2 */
@@ -199,6 +199,13 @@ int pyxrd_set_stream(pyxrd_ctx *ctx, void *cuda_stream);
 int pyxrd_synchronize(pyxrd_ctx *ctx);
 /* number of kernels this context has launched so far */
 int64_t pyxrd_launch_count(const pyxrd_ctx *ctx);
+/* Explicit measurement / experiment switches of one context (the library reads nothing from the environment; the
+ * defaults are what the product runs).  Names: "use_structure" (1; 0 = treat structured transition matrices as dense),
+ * "series_mma" (1; 0 = CUDA-core series for the ranks that have an FP64 tensor-core kernel), "overlap_classes" (1; 0 =
+ * job classes one after the other), "optimizer_threads" (0 = by population size; 128 | 256), "host_chunks" (0 = by
+ * population size; candidate chunks of pyxrd_evaluate_host), "optimizer_delta0" (1e-2), "optimizer_shrink" (0.5),
+ * "optimizer_delta_min" (1e-7): weight-floor schedule of pyxrd_optimize relative to the mean observed intensity. */
+int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value);
 
 /* ---- upload -------------------------------------------------------------------- */
 /* Uploads the tables and runs the table kernels: sin(theta), stl = 2 sin(theta)/lambda

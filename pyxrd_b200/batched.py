@@ -99,10 +99,14 @@ def get_optimized_residuals(mixtures: Sequence, ctx: Optional[Context] = None, f
             mix.parsed = False
             mix.m, mix.n = mix.real_m, mix.real_n
             out[i] = cm.get_optimized_residual(mix)
-    if todo:
-        group = [mixtures[i] for i in todo]
+    # one device batch per value of o: the candidates of a batch share "background refined or not"
+    for free_bg in (True, False):
+        rows = [i for i in todo if (mixtures[i].o > 0) == free_bg]
+        if not rows:
+            continue
+        group = [mixtures[i] for i in rows]
         static, batch = pack_population(group)
-        refine_bg = group[0].o > 0 and bool(settings.get("BGSHIFT"))
+        refine_bg = free_bg and bool(settings.get("BGSHIFT"))
         with ctx.lock:
             ctx.set_static(static)
             ctx.set_batch(batch)
@@ -110,20 +114,19 @@ def get_optimized_residuals(mixtures: Sequence, ctx: Optional[Context] = None, f
             ctx.optimize(refine_bg=refine_bg, outer=outer, newton=newton)
             sol = ctx.read_solutions()
             res = ctx.read_opt_residuals()
-            ctx._resident_epoch = None
-            M, S = batch.M, batch.S
-            for row, i in enumerate(todo):
-                mix = mixtures[i]
-                fractions = np.around(sol[row, :M] / np.sum(sol[row, :M]), 6)
-                mix.fractions = fractions
-                mix.scales = np.array(sol[row, M:M + S]).round(6)
-                mix.bgshifts = np.array(sol[row, M + S:M + 2 * S]) if group[0].o > 0 else np.asarray(mix.bgshifts, float)
-                mix.residual = np.array([res[row, 0]])
-                mix.parsed = False            # phase intensities were not copied to the host
-                mix.m, mix.n = mix.real_m, mix.real_n
-                mix.calculated = False
-                mix.optimized = True
-                out[i] = mix.residual
+        M, S = batch.M, batch.S
+        for row, i in enumerate(rows):
+            mix = mixtures[i]
+            mix.fractions = np.around(sol[row, :M] / np.sum(sol[row, :M]), 6)
+            mix.scales = np.array(sol[row, M:M + S]).round(6)
+            mix.bgshifts = np.array(sol[row, M + S:M + 2 * S]) if free_bg else np.asarray(mix.bgshifts, float)
+            mix.residual = np.array([res[row, 0]])
+            mix.parsed = False            # phase intensities were not copied to the host
+            mix.m, mix.n = mix.real_m, mix.real_n
+            mix.calculated = False
+            mix.optimized = True
+            out[i] = mix.residual
+    if todo:
         if finalize:
             for i in todo:
                 cm.calculate_mixture(mixtures[i])

@@ -18,8 +18,6 @@ from .exceptions import wrap_exceptions
 
 logger = logging.getLogger(__name__)
 
-_epoch = [0]
-
 
 def _inspect_signature_has(func, name):
     import inspect
@@ -30,52 +28,80 @@ def _inspect_signature_has(func, name):
 
 
 # ---- solution vector handling (mixture.py:32-77): host bookkeeping on tiny vectors ------------
+# x = [free fractions | free scales | free bgshifts]; which entries of the mixture's arrays are free was decided by
+# parse_mixture (selected_*), m / n / o count them.
+def _split_solution(x, mixture):
+    """the three segments of x.  The reference addresses the background segment as x[-o:], which is the WHOLE vector
+    when o == 0 -- harmless there because no index receives it; here the empty case is an empty slice."""
+    x = np.asarray(x)
+    nf, ns, nb = int(mixture.m), int(mixture.n), int(mixture.o)
+    return x[:nf], x[nf:nf + ns], (x[x.size - nb:] if nb else x[:0])
+
+
+def _store(array, where, values):
+    """array[where[i]] = values[i], in place (the caller may hold a reference to the array, as with np.put)"""
+    where = np.asarray(where, dtype=np.intp).ravel()
+    if where.size:
+        array[where] = np.asarray(values)[:where.size]
+    return array
+
+
 def parse_solution(x, mixture):
-    fractions, scales, bgshifts = mixture.fractions, mixture.scales, mixture.bgshifts
-    scaled = x[:mixture.m] * (1.0 - mixture.sum_static_fractions) / np.sum(x[:mixture.m])
-    np.put(fractions, mixture.selected_fractions, scaled)
-    np.put(scales, mixture.selected_scales, x[mixture.m:mixture.m + mixture.n])
-    np.put(bgshifts, mixture.selected_bgshifts, x[-mixture.o:])
-    return fractions, scales, bgshifts
+    """mixture.py:32-48: x written into the mixture's own arrays (which are returned); the free fractions are rescaled
+    so that free + static fractions sum to one (0 / 0 -> nan for an all-zero proposal, as in the reference)."""
+    free_f, free_s, free_b = _split_solution(x, mixture)
+    # multiply first, divide second: the rounding of the reference's expression (mixture.py:40)
+    _store(mixture.fractions, mixture.selected_fractions, free_f * (1.0 - mixture.sum_static_fractions) / np.sum(free_f))
+    _store(mixture.scales, mixture.selected_scales, free_s)
+    _store(mixture.bgshifts, mixture.selected_bgshifts, free_b)
+    return mixture.fractions, mixture.scales, mixture.bgshifts
 
 
 def get_solution(mixture):
-    return np.concatenate((np.take(mixture.fractions, mixture.selected_fractions),
-                           np.take(mixture.scales, mixture.selected_scales),
-                           np.take(mixture.bgshifts, mixture.selected_bgshifts)))
+    """mixture.py:50-55"""
+    parts = [np.asarray(arr)[np.asarray(sel, dtype=np.intp)] for arr, sel in (
+        (mixture.fractions, mixture.selected_fractions), (mixture.scales, mixture.selected_scales),
+        (mixture.bgshifts, mixture.selected_bgshifts))]
+    return np.concatenate(parts)
 
 
 def set_solution(x, mixture):
+    """mixture.py:57-58"""
     mixture.fractions, mixture.scales, mixture.bgshifts = parse_solution(x, mixture)
 
 
 def get_zero_solution(mixture):
-    x0 = np.ones(shape=(mixture.m + mixture.n + mixture.o,))
-    x0[-mixture.o:] = 0.0       # NB: with o == 0 this zeroes everything first, as in the reference
-    x0[:mixture.m] = 1.0 / (1.0 - mixture.sum_static_fractions)
+    """mixture.py:60-68: starting point of the reference's L-BFGS-B call.  Quirk kept on purpose: the
+    reference zeroes the background segment with x0[-o:] = 0, which for o == 0 zeroes the whole vector, so without
+    free background shifts the scales start at 0 (and are lifted to their lower bound 1e-3 by the optimiser)."""
+    nf, ns, nb = int(mixture.m), int(mixture.n), int(mixture.o)
+    x0 = np.empty(nf + ns + nb)
+    x0[nf:nf + ns] = 1.0 if nb else 0.0
+    x0[nf + ns:] = 0.0
+    x0[:nf] = 1.0 / (1.0 - mixture.sum_static_fractions)
     return x0
 
 
 def get_bounds(mixture):
-    return ([(0., 1.)] * mixture.m) + ([(1e-3, None)] * mixture.n) + ([(0., None)] * mixture.o)
+    """mixture.py:73-77: fractions in [0, 1], scales >= 1e-3, background shifts >= 0"""
+    return [(0., 1.)] * int(mixture.m) + [(1e-3, None)] * int(mixture.n) + [(0., None)] * int(mixture.o)
 
 
 # ---- device residency -------------------------------------------------------------------
 def _make_resident(mixture, ctx, download):
     """Pack + upload the mixture and compute its phase intensities on ``ctx``.
 
-    ``mixture._b200_epoch`` (a plain int: survives pickling, is no device handle) remembers
-    which upload the context holds, so that later calls on the same parsed mixture reuse the
-    device-resident intensities instead of recomputing them."""
+    ``mixture._b200_epoch`` (a tuple of plain ints (pid, context, counter): survives pickling, is no device handle, and
+    never matches a context of another process) remembers which upload the context holds, so that later calls on
+    the same parsed mixture reuse the device-resident intensities instead of recomputing them.  The context forgets
+    the token whenever ANY call replaces its tables, batch or intensities (runtime.Context.invalidate_residency)."""
     specimens = mixture.specimens
     static = StaticPack(specimens, collect_atom_types(specimens), n_patterns=mixture.z)
     ctx.set_static(static)
     batch = BatchPack([mixture], static, bgshift_enabled=bool(settings.get("BGSHIFT")))
     ctx.set_batch(batch)
     ctx.compute_intensities()
-    _epoch[0] += 1
-    mixture._b200_epoch = _epoch[0]
-    ctx._resident_epoch = _epoch[0]
+    mixture._b200_epoch = ctx.new_resident_token()
     if download:
         corr = ctx.read_correction_flat()
         per_spec = ctx.split_per_specimen(ctx.read_intensities_flat(), (batch.M, static.Z))[0]
@@ -87,7 +113,8 @@ def _make_resident(mixture, ctx, download):
 
 
 def _ensure_resident(mixture, ctx):
-    if getattr(ctx, "_resident_epoch", None) != getattr(mixture, "_b200_epoch", -1):
+    token = getattr(mixture, "_b200_epoch", None)
+    if token is None or ctx._resident_token != token:
         _make_resident(mixture, ctx, download=False)
 
 
@@ -104,35 +131,45 @@ def _device_residuals(mixture, ctx, want_patterns):
 
 
 # ---- the public functions ----------------------------------------------------------------
+def _free_indices(mask):
+    """positions of the non-zero entries of a mask, as a flat index array"""
+    return np.flatnonzero(np.asarray(mask))
+
+
 def _parse_bookkeeping(mixture):
-    """the host half of parse_mixture (mixture.py:107-138): sanity checks, selected variables,
-    static fraction sum, pattern count"""
+    """the host half of parse_mixture (mixture.py:107-138): sanity checks (AssertionError, which the callers swallow),
+    the index sets of the free variables, the static fraction sum, the pattern count.  Conventions kept: m / n / o are
+    OVERWRITTEN with the numbers of free variables while real_m / real_n keep the sizes -- and real_o is set to n, not
+    o, as the reference does (mixture.py:119)."""
     mixture.parsed = False
-    assert mixture.n > 0, "Need at least 1 specimen to optimize phase fractions, scales and background."
-    assert mixture.n == len(mixture.specimens), "Invalid specimen count on mixture data object."
-    assert mixture.m > 0, "Need at least 1 phase in one of the specimen to optimize phase fractions, scales and background."
-    mixture.selected_fractions = np.asanyarray(np.nonzero(mixture.fractions_mask)).flatten()
-    mixture.selected_scales = np.asanyarray(np.nonzero(mixture.scales_mask)).flatten()
-    mixture.selected_bgshifts = np.asanyarray(np.nonzero(mixture.bgshifts_mask)).flatten()
-    mixture.real_m, mixture.real_n, mixture.real_o = mixture.m, mixture.n, mixture.n
+    n_specimens, n_phases = mixture.n, mixture.m
+    assert n_specimens > 0, "a mixture needs at least one specimen"
+    assert n_specimens == len(mixture.specimens), "mixture.n does not match the number of specimens"
+    assert n_phases > 0, "a mixture needs at least one phase"
+    mixture.real_m, mixture.real_n, mixture.real_o = n_phases, n_specimens, n_specimens
+    for name, mask in (("fractions", mixture.fractions_mask), ("scales", mixture.scales_mask),
+                       ("bgshifts", mixture.bgshifts_mask)):
+        setattr(mixture, "selected_" + name, _free_indices(mask))
     mixture.m = len(mixture.selected_fractions)
     mixture.n = len(mixture.selected_scales)
     mixture.o = len(mixture.selected_bgshifts)
-    sm = np.sum(mixture.fractions)
-    mixture.sum_static_fractions = sm - np.sum(np.take(mixture.fractions, mixture.selected_fractions))
-    if sm != 1.0 and mixture.sum_static_fractions < 0.0 or mixture.sum_static_fractions > 1.0:
-        mixture.fractions = mixture.fractions / sm
-        sm = 1.0
-    mixture.sum_static_fractions = sm - np.sum(np.take(mixture.fractions, mixture.selected_fractions))
-    mixture.z = 0
-    for specimen in mixture.specimens:
-        if specimen is not None:
-            mixture.z = len(specimen.z_list)
-            break
-    assert mixture.z > 0, "Need at least 1 pattern in one of the specimens to optimize phase fractions, scales and background."
-    for specimen in mixture.specimens:
-        if specimen is None:
-            logger.warning("parse_mixture reports: 'None found!'")
+
+    def static_share(total):
+        return total - np.sum(np.asarray(mixture.fractions)[mixture.selected_fractions])
+
+    total = np.sum(mixture.fractions)
+    static = static_share(total)
+    # fractions a user typed in need not sum to one: renormalise when the fixed ones would leave a negative share
+    # (and the total is not one) or claim more than everything -- the reference's condition, mixture.py:126
+    if (total != 1.0 and static < 0.0) or static > 1.0:
+        mixture.fractions = mixture.fractions / total
+        total = 1.0
+    mixture.sum_static_fractions = static_share(total)
+    present = [sp for sp in mixture.specimens if sp is not None]
+    mixture.z = len(present[0].z_list) if present else 0
+    assert mixture.z > 0, "a mixture needs at least one pattern in one of its specimens"
+    for _ in range(len(mixture.specimens) - len(present)):
+        logger.warning("parse_mixture reports: 'None found!'")
 
 
 def parse_mixture(mixture, force=False):

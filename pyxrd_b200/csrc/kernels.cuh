@@ -2071,7 +2071,8 @@ __global__ void k_residual_finish(StaticDev st, BatchDev bt, int k0, int k1, int
     for (int t = 0; t < ntiles; ++t) num += partial[(long long)i * ntiles + t];
     const double den = st.derived[s * 8 + 3];
     const int n = st.Z * st.spec_npts[s];
-    bt.residuals[(long long)k * (S + 1) + 1 + s] = (n > 0) ? num / den * 100.0 : 0.0;     // no observations -> 0.0 (mixture.py:247-251)
+    const bool has_obs = st.gonio[s * 12 + 11] != 0.0;                                    // no observations -> 0.0 (mixture.py:247-251)
+    bt.residuals[(long long)k * (S + 1) + 1 + s] = (n > 0 && has_obs) ? num / den * 100.0 : 0.0;
 }
 
 // ---------------------------------------------------------------------------------
@@ -2165,7 +2166,8 @@ __global__ void __launch_bounds__(256) k_residual_rpder(StaticDev st, BatchDev b
             num += __shfl_down_sync(0xffffffffu, num, o);
             den += __shfl_down_sync(0xffffffffu, den, o);
         }
-        if (threadIdx.x == 0) bt.residuals[(long long)k * (st.S + 1) + 1 + s] = (Z * X > 0) ? num / den * 100.0 : 0.0;
+        if (threadIdx.x == 0)
+            bt.residuals[(long long)k * (st.S + 1) + 1 + s] = (Z * X > 0 && st.gonio[s * 12 + 11] != 0.0) ? num / den * 100.0 : 0.0;
     }
 }
 

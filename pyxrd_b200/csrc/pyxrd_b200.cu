@@ -102,14 +102,18 @@ struct pyxrd_ctx {
     cudaStream_t copy_stream = nullptr;      // device -> host copies of finished candidate chunks (pyxrd_evaluate_host)
     cudaStream_t class_stream[3] = {};       // the job classes after the first run beside it (their tails overlap)
     cudaEvent_t fork_ev = nullptr, join_ev[3] = {};
-    bool overlap_classes = true;             // PYXRD_B200_OVERLAP=0: one class after the other
+    bool overlap_classes = true;             // pyxrd_set_option("overlap_classes", 0): one class after the other
     cudaEvent_t chunk_ev[16] = {};
     std::string error;
     int64_t launches = 0;
     int smem_optin = 0;
     int sm_count = 148;
-    bool use_structure = true;   // PYXRD_B200_STRUCTURE=0: ignore the transition structure of P (A/B measurements)
-    bool series_mma = true;   // PYXRD_B200_SERIES=dfma selects the CUDA-core series kernels (A/B measurements only)
+    // measurement / experiment options, set explicitly through pyxrd_set_option (nothing is read from the environment)
+    bool use_structure = true;   // "use_structure" 0: ignore the transition structure of P
+    bool series_mma = true;      // "series_mma" 0: CUDA-core series kernels for the ranks that have a DMMA kernel
+    int opt_tpb = 0;             // "optimizer_threads" 128 / 256: block size of k_mixture_optimize (0: by population size)
+    int host_chunks = 0;         // "host_chunks" n: candidate chunks of pyxrd_evaluate_host (0: by population size)
+    double opt_delta0 = 1e-2, opt_shrink = 0.5, opt_delta_min = 1e-7;   // weight-floor schedule of the optimiser
 
     // static
     bool have_static = false;
@@ -308,7 +312,7 @@ template <int MB>
 static int launch_optimize(pyxrd_ctx *ctx, const OptParams &op) {
     // one wave of 256-thread blocks (2 per SM) when the population fits it, else 128-thread blocks (4 per SM)
     int tpb = ctx->bt.K <= 2 * ctx->sm_count ? 256 : 128;
-    if (const char *e = getenv("PYXRD_B200_OPT_TPB")) tpb = atoi(e) == 128 ? 128 : 256;
+    if (ctx->opt_tpb) tpb = ctx->opt_tpb;
     if (tpb == 256)
         k_mixture_optimize<MB, 256><<<ctx->bt.K, 256, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
                                                                         ctx->d_optres.as<double>());
@@ -341,8 +345,6 @@ int pyxrd_create(int device, pyxrd_ctx **out) {
         return 3;
     }
     ctx->stream = ctx->own_stream;
-    if (const char *e = getenv("PYXRD_B200_SERIES")) ctx->series_mma = strcmp(e, "dfma") != 0;
-    if (const char *e = getenv("PYXRD_B200_STRUCTURE")) ctx->use_structure = atoi(e) != 0;
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
@@ -352,7 +354,6 @@ int pyxrd_create(int device, pyxrd_ctx **out) {
         cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
-    if (const char *e = getenv("PYXRD_B200_OVERLAP")) ctx->overlap_classes = atoi(e) != 0;
     {   // np.blackman(31) / np.blackman(31).sum()  (math_tools.py:93-98 with half_window_len = 15)
         double w[31], sum = 0.0;
         for (int i = 0; i < 31; ++i) {
@@ -408,6 +409,27 @@ int pyxrd_synchronize(pyxrd_ctx *ctx) {
 }
 
 int64_t pyxrd_launch_count(const pyxrd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value) {
+    if (!ctx || !name) return 1;
+    const std::string key(name);
+    if (key == "use_structure") ctx->use_structure = value != 0.0;
+    else if (key == "series_mma") ctx->series_mma = value != 0.0;
+    else if (key == "overlap_classes") ctx->overlap_classes = value != 0.0;
+    else if (key == "optimizer_threads") {
+        if (value != 0.0 && value != 128.0 && value != 256.0) return fail(ctx, "set_option: optimizer_threads is 0, 128 or 256");
+        ctx->opt_tpb = (int)value;
+    } else if (key == "host_chunks") {
+        if (value < 0.0 || value > 16.0) return fail(ctx, "set_option: host_chunks is 0 .. 16");
+        ctx->host_chunks = (int)value;
+    } else if (key == "optimizer_delta0" || key == "optimizer_shrink" || key == "optimizer_delta_min") {
+        if (!(value > 0.0) || (key == "optimizer_shrink" && value > 1.0)) return fail(ctx, "set_option: %s must be positive (shrink <= 1)", name);
+        (key == "optimizer_delta0" ? ctx->opt_delta0 : key == "optimizer_shrink" ? ctx->opt_shrink : ctx->opt_delta_min) = value;
+    } else {
+        return fail(ctx, "set_option: unknown option '%s'", name);
+    }
+    return 0;
+}
 
 int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
     if (!ctx || !d) return 1;
@@ -1001,13 +1023,9 @@ int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newt
     op.lm_iters = newton_iterations > 0 ? newton_iterations : 2;
     op.refine_bg = refine_bg ? 1 : 0;
     op.reserved = 0;
-    op.delta0 = 1e-2;
-    op.shrink = 0.5;
-    op.delta_min = 1e-7;
-    // experiment knobs of tools/opt_sweep.py (weight-floor schedule of the majorise-minimise iteration)
-    if (const char *e = getenv("PYXRD_B200_OPT_DELTA0")) op.delta0 = atof(e);
-    if (const char *e = getenv("PYXRD_B200_OPT_SHRINK")) op.shrink = atof(e);
-    if (const char *e = getenv("PYXRD_B200_OPT_DELTA_MIN")) op.delta_min = atof(e);
+    op.delta0 = ctx->opt_delta0;
+    op.shrink = ctx->opt_shrink;
+    op.delta_min = ctx->opt_delta_min;
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     int rc = 1;
     switch (M + 1) {
@@ -1080,7 +1098,7 @@ int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *re
     // the copy stream (the patterns are the bulk of the result: 8 B per point against ~2 kflop)
     int nchunks = 1;
     if (intensities_out && K >= 16) nchunks = std::min(8, K / 8);
-    if (const char *e = getenv("PYXRD_B200_CHUNKS")) nchunks = std::max(1, std::min(16, std::min(K, atoi(e))));
+    if (ctx->host_chunks > 0) nchunks = std::max(1, std::min(16, std::min(K, ctx->host_chunks)));
     for (int c = 0; c < nchunks; ++c) {
         const int k0 = (int)((long long)K * c / nchunks), k1 = (int)((long long)K * (c + 1) / nchunks);
         if (evaluate_range(ctx, k0, k1, 0, nchunks == 1)) return 1;

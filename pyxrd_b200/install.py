@@ -88,6 +88,9 @@ def _refiner_template(refiner):
         try:
             from .population import mixture_model_of, template_from_refiner
             template = template_from_refiner(refiner, mixture_model_of(refiner))
+            reason = template.optimiser_scope()
+            if reason:          # fixed fractions, auto_scales off, Rpder ...: the device optimiser would minimise
+                raise NotImplementedError(reason)     # another objective than get_optimized_residual
         except Exception as error:          # NotImplementedError: not expressible; anything else: stay safe
             logging.getLogger(__name__).info("pyxrd_b200: this refinement stays on the per-trial path (%s)", error)
             template = False

@@ -153,8 +153,9 @@ def _wavelength_tables(theta: np.ndarray, wavelength: float, distribution):
 
 
 def specimen_signature(spec):
-    """what a specimen contributes to the candidate-invariant tables, as a cheap comparable tuple (the abscissa by
-    size and end points, the goniometer row, the wavelength list): the candidates of one batch must agree on it"""
+    """the scalar part of what a specimen contributes to the candidate-invariant tables, as a cheap comparable tuple
+    (goniometer row, wavelength list, sizes); the arrays themselves -- abscissa, observed patterns, selected range --
+    are compared value by value in ``StaticPack.same_specimen``: the candidates of one batch must agree on all of it"""
     if spec is None:
         return None
     g = spec.goniometer
@@ -184,6 +185,7 @@ class StaticPack(object):
                     break
         self.Z = int(n_patterns)
         self.specimen_signatures = [specimen_signature(spec) for spec in specimens]
+        self._sources = [None] * S         # per specimen: ids of the arrays the tables were built from (identity shortcut)
         self.npts = np.zeros(S, dtype=np.int32)
         self.gonio = np.zeros((S, GONIO_STRIDE))
         self.nwl = np.zeros(S, dtype=np.int32)
@@ -201,6 +203,8 @@ class StaticPack(object):
                                   float(g.has_absorption_correction or 0.0), g.absorption,
                                   g.sample_surf_density, g.sample_length if g.sample_length is not None else 0.0,
                                   g.radius if g.radius is not None else 1.0]
+            # a specimen without observed data reports residual 0.0 (mixture.py:247-251), whatever its patterns are
+            self.gonio[s, 11] = 1.0 if np.size(spec.observed_intensity) > 0 else 0.0
             dist = list(g.wavelength_distribution or [])
             self.nwl[s] = len(dist)
             frac, idx, w_hi, w_lo = wavelength_tables(theta, g.wavelength, dist)
@@ -226,6 +230,8 @@ class StaticPack(object):
                 mask[sel] = True
                 sel = mask
             sels.append(sel.astype(np.uint8))
+            self._sources[s] = (id(spec.range_theta), id(spec.observed_intensity), id(spec.selected_range),
+                                spec.range_theta, spec.observed_intensity, spec.selected_range)   # keep them alive
 
         def cat(parts, dtype):
             return np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0), dtype=dtype)
@@ -246,10 +252,41 @@ class StaticPack(object):
             self.no_observations = set()
 
     def signature(self):
-        """cheap identity of the tables, to decide whether a resident copy can be reused"""
+        """identity of EVERYTHING pyxrd_set_static uploads, to decide whether a resident copy can be reused (the
+        gonio row only holds the primary wavelength: the interpolation tables of the wavelength list are part of it)"""
         return (self.S, self.Z, self.T, self.npts.tobytes(), self.gonio.tobytes(), self.theta.tobytes(),
-                self.wl_fraction.tobytes(), self.observed.tobytes(), self.selected.tobytes(),
+                self.nwl.tobytes(), self.wl_fraction.tobytes(), self.wl_index.tobytes(), self.wl_w_hi.tobytes(),
+                self.wl_w_lo.tobytes(), self.observed.tobytes(), self.selected.tobytes(),
                 self.atype_table.tobytes(), None if self.stl_override is None else self.stl_override.tobytes())
+
+    def same_specimen(self, s: int, spec) -> bool:
+        """does specimen ``spec`` of a candidate describe the same candidate-invariant tables as specimen ``s`` of this
+        pack: scalars by ``specimen_signature``, abscissa / observed patterns / selected range value by value (arrays
+        that ARE the ones the pack was built from are not compared again)"""
+        if specimen_signature(spec) != self.specimen_signatures[s]:
+            return False
+        if spec is None:
+            return True
+        src = self._sources[s]
+        lo, hi = int(self.offsets[s]), int(self.offsets[s + 1])
+        X = hi - lo
+        if src is None or id(spec.range_theta) != src[0]:
+            if not np.array_equal(np.asarray(spec.range_theta, dtype=float).ravel(), self.theta[lo:hi]):
+                return False
+        if src is None or id(spec.observed_intensity) != src[1]:
+            obs = np.asarray(spec.observed_intensity, dtype=float)
+            if obs.size and not np.array_equal(obs.reshape(X, -1).T.ravel(), self.observed[self.Z * lo:self.Z * hi]):
+                return False
+        if src is None or id(spec.selected_range) != src[2]:
+            sel = spec.selected_range
+            mask = np.ones(X, dtype=bool) if sel is None else np.asarray(sel)
+            if mask.dtype != np.bool_:
+                full = np.zeros(X, dtype=bool)
+                full[mask] = True
+                mask = full
+            if not np.array_equal(mask.astype(np.uint8), self.selected[lo:hi]):
+                return False
+        return True
 
 
 class BatchPack(object):
@@ -297,7 +334,7 @@ class BatchPack(object):
             phase_ids: Dict[int, int] = {}
             comp_ids: Dict[int, int] = {}
             for s, spec in enumerate(specimens):
-                if specimen_signature(spec) != static.specimen_signatures[s]:
+                if not static.same_specimen(s, spec):
                     raise ValueError("candidate %d, specimen %d: abscissa / goniometer / observations differ from the "
                                      "resident static tables (specimens are shared by the candidates of a batch)" % (k, s))
                 for z in range(Z):

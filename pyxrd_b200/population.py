@@ -197,7 +197,6 @@ class PopulationTemplate(object):
         with ctx.lock:
             ctx.set_static(self.static)
             ctx.set_residual_method(settings.get("RESIDUAL_METHOD"))
-            ctx._resident_epoch = None
             return ctx.evaluate_population(self.batch, self._x(x), self.bindings, self.csds_auto, self.csds_factor)
 
     def optimized_residuals(self, x, ctx: Optional[Context] = None, outer: int = 0, newton: int = 0,
@@ -205,10 +204,13 @@ class PopulationTemplate(object):
         """f64[K]: ``get_optimized_residual`` (mixture.py:268-276) of the K solutions -- phase patterns,
         then the device mixture optimiser; with ``want_solutions`` also f64[K, M+2S]"""
         ctx = ctx or default_context()
+        reason = self.optimiser_scope()
+        if reason:
+            raise ValueError("the device optimiser does not minimise what get_optimized_residual minimises for this "
+                             "mixture (%s): evaluate its trials one by one through calculations.mixture" % reason)
         refine_bg = self.mixture_refines_background()
         with ctx.lock:
             ctx.set_static(self.static)
-            ctx._resident_epoch = None
             res, sol = ctx.optimize_population(self.batch, self._x(x), self.bindings, self.csds_auto, self.csds_factor,
                                                refine_bg=refine_bg, outer=outer, newton=newton)
         return (res[:, 0], sol) if want_solutions else res[:, 0]
@@ -218,14 +220,38 @@ class PopulationTemplate(object):
         ctx = ctx or default_context()
         with ctx.lock:
             ctx.set_static(self.static)
-            ctx._resident_epoch = None
             ctx.set_population(self.batch, self._x(x), self.bindings, self.csds_auto, self.csds_factor)
             ctx.compute_intensities()
             return ctx.split_per_specimen(ctx.read_intensities_flat(), (self.batch.M, self.static.Z))
 
     def mixture_refines_background(self) -> bool:
         mask = getattr(self.mixture, "bgshifts_mask", None)
-        return bool(settings.get("BGSHIFT")) and mask is not None and bool(np.any(np.asarray(mask)))
+        return bool(settings.get("BGSHIFT")) and mask is not None and bool(np.all(np.asarray(mask)))
+
+    def optimiser_scope(self):
+        """None when ``pyxrd_optimize`` minimises exactly what ``get_optimized_residual`` minimises for the template's
+        mixture, else the reason as text.  The device optimiser varies ALL fractions and ALL scales (and all background
+        shifts or none) and minimises Rp: the reference's default masks (mixture/models/mixture.py:64-73).  A mixture
+        with a fixed fraction, ``auto_scales`` off, a partially fixed background, another ``RESIDUAL_METHOD``, more than
+        11 phases / 8 specimens or a specimen without observations has to stay on the per-trial path
+        (``batched._device_optimisable`` is the same test on a parsed mixture)."""
+        mix = self.mixture
+        if settings.get("RESIDUAL_METHOD") != "Rp":
+            return "RESIDUAL_METHOD is %r, the device optimiser minimises Rp" % (settings.get("RESIDUAL_METHOD"),)
+        M, S = self.batch.M, self.batch.S
+        if M > 11 or S > 8:
+            return "%d phases / %d specimens exceed the optimiser's 11 / 8" % (M, S)
+        for name, want in (("fractions_mask", M), ("scales_mask", S)):
+            mask = np.asarray(getattr(mix, name, np.ones(want))).ravel()
+            if mask.size != want or not np.all(mask):
+                return "%s fixes some entries" % name
+        bg = np.asarray(getattr(mix, "bgshifts_mask", np.zeros(S))).ravel()
+        if np.any(bg) and not np.all(bg):
+            return "bgshifts_mask fixes some background shifts and frees others"
+        for s, spec in enumerate(mix.specimens):
+            if spec is None or np.size(spec.observed_intensity) == 0:
+                return "specimen %d has no observations" % s
+        return None
 
     # -- writing one solution back into the DataObject graph --------------------------------------
     def apply(self, x, probabilities=None, ctx: Optional[Context] = None):

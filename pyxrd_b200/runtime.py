@@ -7,7 +7,9 @@ missing or no CUDA device is present, constructing a :class:`Context` raises.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import os
+import sys
 import threading
 from typing import Optional
 
@@ -59,7 +61,7 @@ class PopulationDesc(C.Structure):
 # every symbol include/pyxrd_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "pyxrd_create", "pyxrd_destroy", "pyxrd_last_error", "pyxrd_set_stream", "pyxrd_synchronize",
-    "pyxrd_launch_count", "pyxrd_set_static", "pyxrd_set_batch", "pyxrd_set_solution", "pyxrd_set_intensities",
+    "pyxrd_launch_count", "pyxrd_set_option", "pyxrd_set_static", "pyxrd_set_batch", "pyxrd_set_solution", "pyxrd_set_intensities",
     "pyxrd_compute_intensities", "pyxrd_compute_residuals", "pyxrd_compute_all", "pyxrd_set_residual_method", "pyxrd_optimize", "pyxrd_read_solutions",
     "pyxrd_read_opt_residuals", "pyxrd_intensity_count", "pyxrd_total_count",
     "pyxrd_read_intensities", "pyxrd_read_scaled", "pyxrd_read_totals", "pyxrd_read_residuals",
@@ -72,6 +74,9 @@ EXPORTS = [
 
 _lib = None
 _lib_lock = threading.Lock()
+_token_counter = itertools.count(1)
+# set in a child that was forked after its parent had initialised CUDA (os.register_at_fork below)
+_forked_after_cuda = False
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -104,6 +109,7 @@ def load_library():
         lib.pyxrd_synchronize.argtypes = [vp]
         lib.pyxrd_launch_count.argtypes = [vp]
         lib.pyxrd_launch_count.restype = C.c_int64
+        lib.pyxrd_set_option.argtypes = [vp, C.c_char_p, C.c_double]
         lib.pyxrd_set_static.argtypes = [vp, C.POINTER(StaticDesc)]
         lib.pyxrd_set_batch.argtypes = [vp, C.POINTER(BatchDesc)]
         lib.pyxrd_set_solution.argtypes = [vp, _f64p, _f64p, _f64p]
@@ -164,6 +170,11 @@ class Context(object):
     """One device context = one CUDA stream + resident tables / batch / results."""
 
     def __init__(self, device: int = 0):
+        if _forked_after_cuda:
+            raise DeviceError(
+                "this process was forked from a process that had already initialised CUDA; CUDA cannot be used in such "
+                "a child.  Evaluate trials in the parent through pyxrd_b200.provider.B200AsyncServerProvider (one "
+                "batched device call per generation) or start the workers with the 'spawn' start method")
         self._lib = load_library()
         self._h = C.c_void_p()
         rc = self._lib.pyxrd_create(int(device), C.byref(self._h))
@@ -177,6 +188,18 @@ class Context(object):
         self._static_sig = None
         self._batch: Optional[BatchPack] = None
         self._keep = []
+        # which parsed mixture the resident batch + intensities belong to (calculations/mixture.py); every call that
+        # replaces the static tables, the batch or its intensities clears it
+        self._resident_token = None
+
+    def new_resident_token(self):
+        """mark the resident batch as belonging to one caller-side object; unique across processes and contexts (the
+        token is stored on a picklable DataObject and may travel to another process)"""
+        self._resident_token = (os.getpid(), id(self), next(_token_counter))
+        return self._resident_token
+
+    def invalidate_residency(self):
+        self._resident_token = None
 
     # -- plumbing ---------------------------------------------------------------------
     def close(self):
@@ -205,6 +228,10 @@ class Context(object):
     def launch_count(self) -> int:
         return int(self._lib.pyxrd_launch_count(self._h))
 
+    def set_option(self, name: str, value: float):
+        """measurement / experiment switches (include/pyxrd_b200.h: pyxrd_set_option); nothing is read from the environment"""
+        self._check(self._lib.pyxrd_set_option(self._h, name.encode("ascii"), float(value)), "set_option")
+
     # -- upload -----------------------------------------------------------------------
     def set_static(self, static: StaticPack, force: bool = False):
         sig = static.signature()
@@ -216,6 +243,7 @@ class Context(object):
                        _p(static.wl_index, _i32p), _p(static.wl_w_hi, _f64p), _p(static.wl_w_lo, _f64p),
                        _p(static.observed, _f64p), _p(static.selected, _u8p), _p(static.atype_table, _f64p),
                        _p(static.stl_override, _f64p) if static.stl_override is not None else None)
+        self._resident_token = None
         self._check(self._lib.pyxrd_set_static(self._h, C.byref(d)), "set_static")
         self._static, self._static_sig, self._batch = static, sig, None
         return True
@@ -231,6 +259,7 @@ class Context(object):
                          _p(b.prob_params, _f64p) if getattr(b, "prob_params", None) is not None else None)
 
     def set_batch(self, batch: BatchPack):
+        self._resident_token = None
         d = self.batch_desc(batch)
         self._check(self._lib.pyxrd_set_batch(self._h, C.byref(d)), "set_batch")
         self._batch = batch
@@ -241,6 +270,7 @@ class Context(object):
         self._check(self._lib.pyxrd_set_solution(self._h, _p(f, _f64p), _p(s, _f64p), _p(g, _f64p)), "set_solution")
 
     def set_intensities(self, flat):
+        self._resident_token = None
         flat = _f64(flat).ravel()
         self._check(self._lib.pyxrd_set_intensities(self._h, _p(flat, _f64p), flat.size), "set_intensities")
 
@@ -285,6 +315,7 @@ class Context(object):
                       out_intensities=None):
         """one C-ABI call: upload K candidates, compute, return residuals [K, 1+S] (+ intensities).
         ``out_*`` may be preallocated (e.g. pinned) float64 arrays."""
+        self._resident_token = None
         d = self.batch_desc(batch)
         res = np.empty(batch.K * (batch.S + 1)) if out_residuals is None else out_residuals
         inten = out_intensities
@@ -299,6 +330,7 @@ class Context(object):
                       out_residuals=None, out_solutions=None):
         """one C-ABI call per generation: K candidates in (host), optimised residuals [K, 1+S] and
         solutions [K, M+2S] out (host)"""
+        self._resident_token = None
         d = self.batch_desc(batch)
         res = np.empty(batch.K * (batch.S + 1)) if out_residuals is None else out_residuals
         sol = np.empty(batch.K * (batch.M + 2 * batch.S)) if out_solutions is None else out_solutions
@@ -436,6 +468,7 @@ class Context(object):
 
     # -- populations from a template + binding table ----------------------------------------
     def _population_desc(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5):
+        self._resident_token = None               # every population call replaces the resident batch
         x = np.ascontiguousarray(x, dtype=np.float64)
         if x.ndim != 2:
             raise ValueError("x must be [K, d]")
@@ -554,6 +587,32 @@ def expand_population(template: BatchPack, x, bindings, csds_auto=None, csds_fac
 
 _contexts = {}
 _ctx_lock = threading.Lock()
+
+
+def _after_fork_in_child():
+    """CUDA state does not survive fork(): a child of a process that had initialised CUDA (through this library or
+    through torch) can neither use the parent's contexts nor create its own.  The inherited handles are dropped WITHOUT
+    calling into the CUDA runtime and the child is marked, so that the first attempt to compute raises a DeviceError
+    that says what to do instead (the reference evaluates trials in forked Pool workers, pyxrd_server.py:57-64)."""
+    global _forked_after_cuda, _ctx_lock
+    _ctx_lock = threading.Lock()
+    had_cuda = bool(_contexts)
+    torch = sys.modules.get("torch")
+    if torch is not None:
+        try:
+            had_cuda = had_cuda or bool(torch.cuda.is_initialized())
+        except Exception:
+            pass
+    for ctx in _contexts.values():
+        ctx._h = C.c_void_p()                     # never pyxrd_destroy() a handle of the parent in the child
+        ctx.lock = threading.RLock()
+    _contexts.clear()
+    if had_cuda:
+        _forked_after_cuda = True
+
+
+if hasattr(os, "register_at_fork"):
+    os.register_at_fork(after_in_child=_after_fork_in_child)
 
 
 def default_context(device: Optional[int] = None) -> Context:

@@ -1,0 +1,194 @@
+"""State, threading and process conventions of the drop-in functions on the device: residency of a
+parsed mixture across interleaved calls, two threads on one context, a child forked after CUDA was initialised, a
+specimen without observations in the batched calls, stale static tables."""
+import copy
+import multiprocessing as mp
+import threading
+
+import numpy as np
+import pytest
+
+from helpers import rel_err
+from oracle import pyxrd_oracle as orc
+from pyxrd_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def calc():
+    import pyxrd_b200.calculations as c
+    return c
+
+
+def _observed(mix, seed=1):
+    rng = np.random.default_rng(seed)
+    for spec in mix.specimens:
+        spec.observed_intensity = rng.uniform(20.0, 60.0, (spec.range_theta.size, 1))
+    return mix
+
+
+def test_interleaved_calls_do_not_reuse_foreign_device_state(calc):
+    """parse_mixture(mix) leaves the patterns resident; another entry point (get_intensity,
+    calculate_phase_intensities, a population call, another mixture) then replaces the context's batch.  The later
+    calculate_mixture / optimize_mixture of the first mixture must notice and recompute, not use foreign patterns."""
+    from pyxrd_b200.batched import population_residuals
+    mix = _observed(syn.CONFIGS["c4"].candidate(2024, 3))
+    ref = copy.deepcopy(mix)
+    orc.calculate_mixture(ref)
+    calc.mixture.parse_mixture(mix)
+    other = _observed(syn.CONFIGS["c4"].candidate(2024, 4), seed=1)        # same shapes (K, M, S agree), other patterns
+    spec = other.specimens[0]
+    phase = spec.phases[0][3]
+    stl = 2.0 * np.sin(spec.range_theta) / spec.goniometer.wavelength
+    calc.phases.get_intensity(spec.range_theta, stl, 2.3, 2.3, 0.0, phase)
+    calc.mixture.calculate_mixture(mix)
+    assert rel_err(mix.residuals, ref.residuals) < RTOL
+    for a, b in zip(mix.specimens, ref.specimens):
+        assert rel_err(a.total_intensity, b.total_intensity) < RTOL
+    # a whole other batch of the same shape in between
+    mix.calculated = False
+    population_residuals([other])
+    calc.mixture.calculate_mixture(mix)
+    assert rel_err(mix.residuals, ref.residuals) < RTOL
+    # specimen-level entry point in between, then the optimiser
+    mix.calculated = False
+    calc.specimen.calculate_phase_intensities(other.specimens[1])
+    calc.mixture.calculate_mixture(mix)
+    assert rel_err(mix.residuals, ref.residuals) < RTOL
+    # a parsed mixture that went through pickle (a worker of another process) never matches a resident token
+    import pickle
+    clone = pickle.loads(pickle.dumps(mix))
+    clone.calculated = False
+    calc.mixture.calculate_mixture(clone)
+    assert rel_err(clone.residuals, ref.residuals) < RTOL
+
+
+def test_two_threads_share_one_context(calc):
+    """the functions are called from the GUI thread and a refinement thread at once; the context
+    serialises them (per-context lock) and each caller gets its own results"""
+    mixes = [_observed(syn.CONFIGS[name].candidate(2024, i), seed=i) for i, name in enumerate(("c1", "c4", "c1", "c4"))]
+    refs = []
+    for m in mixes:
+        r = copy.deepcopy(m)
+        orc.calculate_mixture(r)
+        refs.append(r)
+    errors, worst = [], [0.0] * len(mixes)
+
+    def worker(i):
+        try:
+            for _ in range(6):
+                m = copy.deepcopy(mixes[i])
+                calc.mixture.calculate_mixture(m)
+                worst[i] = max(worst[i], rel_err(m.residuals, refs[i].residuals),
+                               max(rel_err(a.total_intensity, b.total_intensity) for a, b in zip(m.specimens, refs[i].specimens)))
+                calc.mixture.get_optimized_residual(copy.deepcopy(mixes[i]))
+        except Exception as err:        # pragma: no cover
+            errors.append(err)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(mixes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert max(worst) < RTOL, worst
+
+
+def _child(queue):
+    import pyxrd_b200.calculations as c
+    from pyxrd_b200.runtime import DeviceError
+    try:
+        c.mixture.calculate_mixture(_observed(syn.CONFIGS["c1"].truth()))
+        queue.put(("computed", ""))
+    except DeviceError as err:
+        queue.put(("DeviceError", str(err)))
+    except Exception as err:            # pragma: no cover
+        queue.put((type(err).__name__, str(err)))
+
+
+def test_fork_after_cuda_initialisation(calc):
+    """the reference's Pool workers are forked (pyxrd_server.py:57-64): a child forked after the parent touched CUDA
+    gets a DeviceError that names the provider / spawn, and the parent keeps working"""
+    calc.mixture.calculate_mixture(_observed(syn.CONFIGS["c1"].truth()))          # the parent has a context now
+    ctx = mp.get_context("fork")
+    queue = ctx.Queue()
+    proc = ctx.Process(target=_child, args=(queue,))
+    proc.start()
+    kind, text = queue.get(timeout=120)
+    proc.join(timeout=120)
+    assert kind == "DeviceError" and "forked" in text and "B200AsyncServerProvider" in text, (kind, text)
+    mix = _observed(syn.CONFIGS["c1"].truth())
+    ref = copy.deepcopy(mix)
+    orc.calculate_mixture(ref)
+    calc.mixture.calculate_mixture(mix)
+    assert rel_err(mix.residuals, ref.residuals) < RTOL
+
+
+def test_spawned_worker_computes(calc):
+    """... while a SPAWNED worker (fresh interpreter) creates its own context and computes"""
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    proc = ctx.Process(target=_child, args=(queue,))
+    proc.start()
+    kind, text = queue.get(timeout=300)
+    proc.join(timeout=120)
+    assert kind == "computed", (kind, text)
+
+
+def test_specimen_without_observations_in_the_batched_calls(calc):
+    """a specimen without observed data reports 0.0 (mixture.py:247-251) in every call that has
+    calculate_mixture semantics, the batched ones included (the device knows the specimen has no observations)"""
+    from pyxrd_b200.batched import population_residuals
+    from pyxrd_b200.population import PopulationTemplate
+    mixes = [_observed(syn.CONFIGS["c4"].candidate(2024, i)) for i in range(3)]
+    for m in mixes:
+        m.specimens[1].observed_intensity = np.zeros((0, 1))
+    res = population_residuals(mixes)
+    assert np.isfinite(res).all() and np.array_equal(res[:, 2], np.zeros(3))
+    for k, m in enumerate(mixes):
+        ref = copy.deepcopy(m)
+        orc.calculate_mixture(ref)
+        assert rel_err(res[k], ref.residuals) < RTOL
+    tmix, refs = syn.template("c4")
+    _observed(tmix)
+    tmix.specimens[0].observed_intensity = np.zeros((0, 1))
+    tmpl = PopulationTemplate(tmix, refs)
+    res = tmpl.residuals(syn.sample_solutions(refs, 5, 4))
+    assert np.isfinite(res).all() and np.array_equal(res[:, 1], np.zeros(4)) and np.all(res[:, 2] > 0.0)
+    assert np.allclose(res[:, 0], 0.5 * res[:, 2], rtol=1e-15)
+
+
+def test_static_tables_follow_a_changed_secondary_wavelength(calc):
+    """two goniometers that differ only in a SECONDARY wavelength of the distribution (same
+    primary wavelength, same fractions) must not share resident interpolation tables"""
+    mix = _observed(syn.CONFIGS["c2"].candidate(2024, 0))
+    calc.mixture.calculate_mixture(mix)
+    changed = copy.deepcopy(mix)
+    changed.parsed = changed.calculated = False
+    (w1, f1), (w2, f2) = changed.specimens[0].goniometer.wavelength_distribution
+    changed.specimens[0].goniometer.wavelength_distribution = [(w1, f1), (w2 * 1.004, f2)]
+    ref = copy.deepcopy(changed)
+    orc.calculate_mixture(ref)
+    calc.mixture.calculate_mixture(changed)
+    assert rel_err(changed.specimens[0].phase_intensities, ref.specimens[0].phase_intensities) < RTOL
+    assert rel_err(changed.residuals, ref.residuals) < RTOL
+    assert rel_err(changed.specimens[0].phase_intensities, mix.specimens[0].phase_intensities) > 1e-6
+
+
+def test_candidates_with_other_observations_are_refused(calc):
+    """... and candidates whose observed data / selected range differ from the batch's first candidate are refused
+    (same end points and sizes are not enough)"""
+    from pyxrd_b200.batched import pack_population
+    mixes = [_observed(syn.CONFIGS["c1"].candidate(2024, i)) for i in range(2)]
+    pack_population(mixes)
+    mixes[1].specimens[0].observed_intensity = mixes[1].specimens[0].observed_intensity * 1.01
+    with pytest.raises(ValueError):
+        pack_population(mixes)
+    mixes[1].specimens[0].observed_intensity = mixes[0].specimens[0].observed_intensity.copy()
+    sel = np.ones(mixes[1].specimens[0].range_theta.size, dtype=bool)
+    sel[100:200] = False
+    mixes[1].specimens[0].selected_range = sel
+    with pytest.raises(ValueError):
+        pack_population(mixes)

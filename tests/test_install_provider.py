@@ -11,6 +11,28 @@ from pyxrd_b200.provider import B200AsyncServer, B200AsyncServerProvider
 HAVE_REFERENCE = os.path.isdir("/root/reference/pyxrd")
 
 
+@pytest.fixture(scope="module")
+def reference_mixture():
+    """the mixture model of the reference's integration fixture inside its running (headless) model layer, with the
+    first two refinables left switched on; parsed once per module (a second parse of the same file in one process
+    collides in the reference's object pool)"""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import _live_models
+    _live_models.load()
+    import pyxrd.project.models  # noqa: F401
+    from pyxrd.file_parsers.json_parser import JSONParser
+    project = JSONParser.parse("/root/reference/test/test_mixture/test refinement.pyxrd")
+    mixture = project.mixtures[0]
+    n = 0
+    for node in mixture.refinement.refinables.iter_children():
+        r = node.object
+        if r.prop_descr is not None and r.refine:
+            n += 1
+            if n > 2:
+                r.refine = False
+    return mixture
+
+
 def get_optimized_residual(mixture):          # a stand-in with the reference's function name
     return ("single", mixture)
 
@@ -73,29 +95,16 @@ def test_install_rebinds_reference_modules():
 
 @pytest.mark.filterwarnings("ignore")
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="needs the reference tree (build container only)")
-def test_generations_of_a_reference_refinement_go_through_the_binding_table(monkeypatch):
+def test_generations_of_a_reference_refinement_go_through_the_binding_table(monkeypatch, reference_mixture):
     """install(generations=True) inside the live reference: its brute-force run (custom_brute.py:36-56) hands the whole
     grid to ONE PopulationTemplate call (table discovered from its own Refiner); the reference's bookkeeping
     (Refiner.update -> history) receives the values.  The device evaluation itself is replaced by a stand-in here (no
     GPU in the build container; its numerics are pinned by tests/test_gpu_population.py on binding.npz)."""
     import threading
     import numpy as np
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-    import _live_models
-    _live_models.load()
-    import pyxrd.project.models  # noqa: F401
-    from pyxrd.file_parsers.json_parser import JSONParser
     import pyxrd_b200.install as inst
     from pyxrd_b200 import population
-    project = JSONParser.parse("/root/reference/test/test_mixture/test refinement.pyxrd")
-    mixture = project.mixtures[0]
-    n = 0
-    for node in mixture.refinement.refinables.iter_children():
-        r = node.object
-        if r.prop_descr is not None and r.refine:
-            n += 1
-            if n > 2:
-                r.refine = False
+    mixture = reference_mixture
     calls, steepness = [], [1e-6]
 
     def stand_in(self, x, ctx=None, **kwargs):
@@ -132,3 +141,25 @@ def test_generations_of_a_reference_refinement_go_through_the_binding_table(monk
     assert len(calls) >= 2 and all(c.shape == (3, 2) for c in calls)
     b = tmpl.bounds()
     assert np.allclose(calls[-1][0], np.clip([7.0, 18.0], b[:, 0], b[:, 1]), atol=1e-2)     # the stand-in's minimum inside the ranges
+
+
+@pytest.mark.filterwarnings("ignore")
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="needs the reference tree (build container only)")
+def test_refinements_outside_the_optimiser_scope_keep_the_reference_loop(reference_mixture):
+    """with ``auto_scales`` off the reference zeroes scales_mask (mixture/models/mixture.py:64-68) and
+    get_optimized_residual keeps the scales fixed; the device optimiser would free them.  The install hooks must then
+    hand the generation back to the reference's own loop (``_refiner_template`` -> False)."""
+    import pyxrd_b200.install as inst
+    from pyxrd_b200 import population
+    mixture = reference_mixture
+    refiner = mixture.refinement.get_refiner()
+    template = inst._refiner_template(refiner)
+    assert isinstance(template, population.PopulationTemplate) and template.optimiser_scope() is None
+    mixture.auto_scales = False
+    refiner = mixture.refinement.get_refiner()
+    assert inst._refiner_template(refiner) is False
+    mixture.auto_scales = True
+    mixture.auto_bg = False                     # background fixed for every specimen: in scope, not refined
+    refiner = mixture.refinement.get_refiner()
+    template = inst._refiner_template(refiner)
+    assert isinstance(template, population.PopulationTemplate) and not template.mixture_refines_background()

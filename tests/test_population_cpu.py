@@ -127,3 +127,44 @@ def test_packing_caches_are_keyed_by_value():
     assert np.array_equal(one.atom_type, two.atom_type)
     atoms[0].atom_type.debye = float(atoms[0].atom_type.debye) + 0.25
     assert len(packing.collect_atom_types(other.specimens)) == len(types) + 1
+
+
+def test_optimiser_scope_follows_the_mixture_masks():
+    """the device optimiser frees every fraction and scale and minimises Rp.  A template whose mixture fixes
+    a fraction, switches auto_scales off (scales_mask zero, mixture/models/mixture.py:64-68), frees only part of the
+    background shifts or asks for another residual must refuse ``optimized_residuals`` -- the refinement then stays on the
+    per-trial path -- instead of silently minimising another objective."""
+    from pyxrd_b200 import settings
+    mix, refs = syn.template("c4")
+    rng = np.random.default_rng(3)
+    for spec in mix.specimens:
+        spec.observed_intensity = rng.uniform(20.0, 60.0, (spec.range_theta.size, 1))
+    tmpl = PopulationTemplate(mix, refs)
+    assert tmpl.optimiser_scope() is None and tmpl.mixture_refines_background()
+    x = syn.sample_solutions(refs, 1, 2)
+
+    def refused(fragment):
+        reason = tmpl.optimiser_scope()
+        assert reason and fragment in reason, reason
+        with pytest.raises(ValueError):          # raised before any device call
+            tmpl.optimized_residuals(x, ctx=object())
+
+    mix.fractions_mask = np.array([1, 1, 0, 1, 1, 1.0])
+    refused("fractions_mask")
+    mix.fractions_mask = np.ones(6)
+    mix.scales_mask = np.zeros(2)
+    refused("scales_mask")
+    mix.scales_mask = np.ones(2)
+    mix.bgshifts_mask = np.array([1.0, 0.0])
+    refused("bgshifts_mask")
+    assert not tmpl.mixture_refines_background()         # a partially fixed background is not "free"
+    mix.bgshifts_mask = np.zeros(2)
+    assert tmpl.optimiser_scope() is None and not tmpl.mixture_refines_background()
+    mix.bgshifts_mask = np.ones(2)
+    settings.RESIDUAL_METHOD = "Rpder"
+    try:
+        refused("Rpder")
+    finally:
+        settings.RESIDUAL_METHOD = "Rp"
+    mix.specimens[1].observed_intensity = np.zeros((0, 1))
+    refused("no observations")

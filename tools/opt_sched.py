@@ -17,10 +17,10 @@ syn.attach_observed(mixes, truth, calc_total)
 static, batch = pack_population(mixes)
 ctx = default_context(0)
 def run(outer, newton, **env):
-    for k in ("DELTA0", "SHRINK", "DELTA_MIN"):
-        os.environ.pop("PYXRD_B200_OPT_" + k, None)
-    for k, v in env.items():
-        os.environ["PYXRD_B200_OPT_" + k] = repr(v)
+    schedule = dict(DELTA0=1e-2, SHRINK=0.5, DELTA_MIN=1e-7)
+    schedule.update(env)
+    for k, v in schedule.items():
+        ctx.set_option("optimizer_" + k.lower(), v)
     ctx.optimize(refine_bg=True, outer=outer, newton=newton); ctx.synchronize()
     t0 = time.perf_counter()
     for _ in range(3):
