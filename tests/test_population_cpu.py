@@ -129,7 +129,7 @@ def test_packing_caches_are_keyed_by_value():
     assert len(packing.collect_atom_types(other.specimens)) == len(types) + 1
 
 
-def test_optimiser_scope_follows_the_mixture_masks():
+def test_optimiser_scope_follows_the_mixture_masks(monkeypatch):
     """the device optimiser frees every fraction and scale and minimises Rp.  A template whose mixture fixes
     a fraction, switches auto_scales off (scales_mask zero, mixture/models/mixture.py:64-68), frees only part of the
     background shifts or asks for another residual must refuse ``optimized_residuals`` -- the refinement then stays on the
@@ -161,10 +161,9 @@ def test_optimiser_scope_follows_the_mixture_masks():
     mix.bgshifts_mask = np.zeros(2)
     assert tmpl.optimiser_scope() is None and not tmpl.mixture_refines_background()
     mix.bgshifts_mask = np.ones(2)
-    settings.RESIDUAL_METHOD = "Rpder"
-    try:
-        refused("Rpder")
-    finally:
-        settings.RESIDUAL_METHOD = "Rp"
+    real_get = settings.get          # (inside a PyXRD process the reference's own settings module is consulted)
+    monkeypatch.setattr(settings, "get", lambda name: "Rpder" if name == "RESIDUAL_METHOD" else real_get(name))
+    refused("Rpder")
+    monkeypatch.setattr(settings, "get", real_get)
     mix.specimens[1].observed_intensity = np.zeros((0, 1))
     refused("no observations")
