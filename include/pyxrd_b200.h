@@ -179,6 +179,12 @@ const char *pyxrd_expand_error(void);   /* message of the last failed pyxrd_expa
  * (K * d * 8 bytes per generation instead of K parameter blocks), every candidate's slice of the batch arrays, its
  * job table and job lists are written by one kernel, then the batch prologue runs as after pyxrd_set_batch */
 int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *template_desc, const pyxrd_population_desc *pop);
+/* The next generation of the SAME refinement (same template, table, K and d as the resident population; refinement/
+ * refine_async_helper.py:16-23 evaluates generation after generation): only the solution vectors x[K][d] cross PCIe
+ * (NULL: keep the resident vectors), the expansion kernel and the batch prologue run again.  Fails -- and the caller
+ * falls back to pyxrd_set_population -- when no population is resident (any pyxrd_set_static / pyxrd_set_batch in
+ * between drops it). */
+int pyxrd_update_population(pyxrd_ctx *ctx, const double *x);
 /* set_population + compute_intensities + compute_residuals -> residuals [K][1+S] */
 int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *template_desc, const pyxrd_population_desc *pop,
                               double *residuals_out);
@@ -273,6 +279,9 @@ int pyxrd_read_correction(pyxrd_ctx *ctx, double *out, int64_t count); /* [sum X
 /* device addresses of the result buffers, for zero-copy consumers (NCCL gather) */
 int pyxrd_device_buffers(pyxrd_ctx *ctx, double **intensities_dev, double **totals_dev,
                          double **residuals_dev);
+
+/* device addresses of the optimiser's results (pyxrd_optimize): residuals [K][1+S], solutions [K][M+2S] */
+int pyxrd_device_results(pyxrd_ctx *ctx, double **opt_residuals_dev, double **solutions_dev);
 
 /* ---- one call, host buffers in and out (what a per-generation plugin call does) ---- */
 /* set_batch + compute_intensities + compute_residuals + read residuals [K][1+S];

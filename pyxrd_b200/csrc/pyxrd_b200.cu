@@ -148,6 +148,26 @@ struct pyxrd_ctx {
     int64_t int_count = 0, tot_count = 0;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_set[4] = {false, false, false, false};
+
+    // what pyxrd_update_population needs of the resident device-expanded population
+    struct Population {
+        bool valid = false;
+        ExpandDev e{};
+        int ncap0 = 2, acap = 1;                     // coefficient stride without the automatic maxima / atom stride
+        size_t x_off = 0;                            // offset of the solution vectors inside the staging blob
+        std::vector<int32_t> t_phase_i;              // template parameter blocks (CSDS range, flags)
+        std::vector<double> t_phase_d;
+        std::vector<int> t_job_pb;
+        std::vector<std::vector<int>> cls_jobs;      // template job ids of every class
+        std::vector<int> cls_cap0;                   // class coefficient caps of the template itself
+        std::vector<pyxrd_binding> bind;
+        std::vector<uint8_t> auto_max;
+        double factor = 2.5;
+        long long NJ = 0;
+        size_t njobids = 0;
+        int M = 0;
+        bool model_driven = false;
+    } pop;
 };
 
 namespace {
@@ -438,6 +458,7 @@ int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
     if (S <= 0 || Z <= 0 || T < 0) return fail(ctx, "set_static: need S > 0 and Z > 0 (S=%d Z=%d T=%d)", S, Z, T);
     ctx->have_static = false;
     ctx->have_batch = false;
+    ctx->pop.valid = false;
     ctx->h_npts.assign(d->spec_npts, d->spec_npts + S);
     ctx->h_nwl.assign(d->spec_nwl, d->spec_nwl + S);
     ctx->h_off.assign(S + 1, 0);
@@ -799,6 +820,7 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     ctx->have_batch = false;
     ctx->have_intensities = false;
     ctx->have_opt = false;
+    ctx->pop.valid = false;                  // the blob of a device-expanded population is overwritten
     const StaticDev &st = ctx->st;
     if (d->n_candidates <= 0 || d->n_phase_slots <= 0)
         return fail(ctx, "set_batch: need K > 0 and M > 0 (K=%d M=%d)", d->n_candidates, d->n_phase_slots);
@@ -1090,6 +1112,13 @@ int pyxrd_device_buffers(pyxrd_ctx *ctx, double **intensities_dev, double **tota
     return 0;
 }
 
+int pyxrd_device_results(pyxrd_ctx *ctx, double **opt_residuals_dev, double **solutions_dev) {
+    if (!ctx || !ctx->have_opt) return fail(ctx, "device_results: optimiser has not run");
+    if (opt_residuals_dev) *opt_residuals_dev = ctx->d_optres.as<double>();
+    if (solutions_dev) *solutions_dev = ctx->d_sol.as<double>();
+    return 0;
+}
+
 int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *residuals_out, double *intensities_out) {
     if (pyxrd_set_batch(ctx, desc)) return 1;
     const int K = ctx->bt.K;
@@ -1366,6 +1395,61 @@ void pyxrd_expanded_desc(const pyxrd_expanded *e, pyxrd_batch_desc *out) {
 
 void pyxrd_expanded_free(pyxrd_expanded *e) { delete e; }
 
+}  // extern "C"
+
+namespace {
+// The automatic CSDS maximum int(factor * average) depends on the bound average: its range over the solution vectors
+// x[K][D] sizes the coefficient table (*ncap) and the shared memory of each job class (the last binding of a slot wins,
+// as in the expansion).
+int population_caps(pyxrd_ctx *ctx, const double *x, int K, int D, int *ncap) {
+    pyxrd_ctx::Population &pp = ctx->pop;
+    const int NP = (int)(pp.t_phase_i.size() / PYXRD_PHASE_I_STRIDE), NB = (int)pp.bind.size();
+    std::vector<int> pmax(NP);
+    for (int p = 0; p < NP; ++p) pmax[p] = pp.t_phase_i[(size_t)p * PYXRD_PHASE_I_STRIDE + 3];
+    if (!pp.auto_max.empty())
+        for (int p = 0; p < NP; ++p) {
+            if (!pp.auto_max[p]) continue;
+            const pyxrd_binding *last = nullptr;
+            for (int b = 0; b < NB; ++b)
+                if (pp.bind[b].target == PYXRD_BIND_PHASE_D && pp.bind[b].index == p * PYXRD_PHASE_D_STRIDE + 1) last = &pp.bind[b];
+            int lo, hi;
+            if (!last) {
+                lo = hi = (int32_t)(pp.factor * pp.t_phase_d[(size_t)p * PYXRD_PHASE_D_STRIDE + 1]);
+            } else {
+                lo = 0x7fffffff; hi = -0x7fffffff;
+                for (int k = 0; k < K; ++k) {
+                    const double avg = last->scale * x[(size_t)k * D + last->param] + last->offset;
+                    const double mx = pp.factor * avg;
+                    if (!(mx > -1e9 && mx < 1e9)) return fail(ctx, "set_population: candidate %d: CSDS average %g of phase %d is not usable", k, avg, p);
+                    lo = std::min(lo, (int)mx);
+                    hi = std::max(hi, (int)mx);
+                }
+            }
+            pmax[p] = hi;
+            const int32_t *pi = pp.t_phase_i.data() + (size_t)p * PYXRD_PHASE_I_STRIDE;
+            if ((pi[4] & PYXRD_FLAG_VALID_PROBS) && !(pi[4] & PYXRD_FLAG_RAW_PATTERN) && lo < pi[2])
+                return fail(ctx, "set_batch: phase %d CSDS range [%d, %d] unsupported", p, pi[2], lo);
+        }
+    int cap = pp.ncap0;
+    for (size_t c = 0; c < ctx->classes.size(); ++c) {
+        RankClass &rc = ctx->classes[c];
+        rc.max_ntop_cap = pp.cls_cap0[c];
+        for (int j : pp.cls_jobs[c]) {
+            const int pb = pp.t_job_pb[j];
+            const int32_t *pi = pp.t_phase_i.data() + (size_t)pb * PYXRD_PHASE_I_STRIDE;
+            if (!(pi[4] & PYXRD_FLAG_RAW_PATTERN)) {
+                rc.max_ntop_cap = std::max(rc.max_ntop_cap, pmax[pb] + 1);
+                cap = std::max(cap, pmax[pb] + 2);
+            }
+        }
+    }
+    *ncap = cap;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
 int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop) {
     if (!ctx) return 1;
     if (!t || !pop) return fail(ctx, "set_population: null argument");
@@ -1404,34 +1488,20 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     std::vector<int> job_pb, job_spec, jobids;
     std::vector<long long> job_out;
     if (build_jobs(ctx, t, job_pb, job_spec, job_out, jobids)) return 1;
-    // the automatic CSDS maximum depends on the bound average: its range over the population sizes the coefficient
-    // table and the shared memory of each class (the last binding of a slot wins, as in the expansion)
-    std::vector<int> pmax(NP), pmin(NP);
-    for (int p = 0; p < NP; ++p) pmax[p] = pmin[p] = t->phase_i[(size_t)p * PYXRD_PHASE_I_STRIDE + 3];
-    if (pop->csds_auto_maximum)
-        for (int p = 0; p < NP; ++p) {
-            if (!pop->csds_auto_maximum[p]) continue;
-            const pyxrd_binding *last = nullptr;
-            for (int b = 0; b < NB; ++b)
-                if (pop->bindings[b].target == PYXRD_BIND_PHASE_D && pop->bindings[b].index == p * PYXRD_PHASE_D_STRIDE + 1) last = &pop->bindings[b];
-            int lo, hi;
-            if (!last) {
-                lo = hi = (int32_t)(pop->csds_factor * t->phase_d[(size_t)p * PYXRD_PHASE_D_STRIDE + 1]);
-            } else {
-                lo = 0x7fffffff; hi = -0x7fffffff;
-                for (int k = 0; k < K; ++k) {
-                    const double avg = last->scale * pop->x[(size_t)k * D + last->param] + last->offset;
-                    const double mx = pop->csds_factor * avg;
-                    if (!(mx > -1e9 && mx < 1e9)) return fail(ctx, "set_population: candidate %d: CSDS average %g of phase %d is not usable", k, avg, p);
-                    lo = std::min(lo, (int)mx);
-                    hi = std::max(hi, (int)mx);
-                }
-            }
-            pmin[p] = lo; pmax[p] = hi;
-            const int32_t *pi = t->phase_i + (size_t)p * PYXRD_PHASE_I_STRIDE;
-            if ((pi[4] & PYXRD_FLAG_VALID_PROBS) && !(pi[4] & PYXRD_FLAG_RAW_PATTERN) && lo < pi[2])
-                return fail(ctx, "set_batch: phase %d CSDS range [%d, %d] unsupported", p, pi[2], lo);
-        }
+    // remember the template side of the population: pyxrd_update_population re-expands it for new solution vectors
+    pyxrd_ctx::Population &pp = ctx->pop;
+    pp.valid = false;
+    pp.t_phase_i.assign(t->phase_i, t->phase_i + (size_t)NP * PYXRD_PHASE_I_STRIDE);
+    pp.t_phase_d.assign(t->phase_d, t->phase_d + (size_t)NP * PYXRD_PHASE_D_STRIDE);
+    pp.t_job_pb = job_pb;
+    pp.bind.assign(pop->bindings, pop->bindings + NB);
+    pp.auto_max.clear();
+    if (pop->csds_auto_maximum) pp.auto_max.assign(pop->csds_auto_maximum, pop->csds_auto_maximum + NP);
+    pp.factor = pop->csds_factor;
+    pp.ncap0 = ncap;
+    pp.acap = acap;
+    pp.cls_jobs.clear();
+    pp.cls_cap0.clear();
     const size_t JPC = job_pb.size();
     std::vector<int> cls_first, cls_n;
     {
@@ -1440,19 +1510,14 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
             cls_first.push_back((int)pos);
             cls_n.push_back((int)rc.jobs.size());
             pos += rc.jobs.size();
-            for (int j : rc.jobs) {
-                const int pb = job_pb[j];
-                const int32_t *pi = t->phase_i + (size_t)pb * PYXRD_PHASE_I_STRIDE;
-                if (!(pi[4] & PYXRD_FLAG_RAW_PATTERN)) {
-                    rc.max_ntop_cap = std::max(rc.max_ntop_cap, pmax[pb] + 1);
-                    ncap = std::max(ncap, pmax[pb] + 2);
-                }
-            }
+            pp.cls_jobs.push_back(rc.jobs);
+            pp.cls_cap0.push_back(rc.max_ntop_cap);
             rc.per_cand = rc.jobs.size();
             rc.uniform = true;
             rc.jobs.clear();
         }
     }
+    if (population_caps(ctx, pop->x, K, D, &ncap)) return 1;
     const int NCLS = (int)ctx->classes.size();
 
     BatchSizes z;
@@ -1522,7 +1587,49 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     e.bg = (double *)dp(P_BG); e.pmodel = model_driven ? (int *)dp(P_PMODEL) : nullptr; e.pparam = model_driven ? (double *)dp(P_PPARAM) : nullptr;
     k_expand_population<<<K, 128, 0, ctx->stream>>>(e);
     LAUNCH_CHECK("k_expand_population");
-    return bind_batch(ctx, z, L, ncap, acap);
+    if (bind_batch(ctx, z, L, ncap, acap)) return 1;
+    pp.e = e;
+    pp.x_off = parts[a_x].off;
+    pp.NJ = z.NJ;
+    pp.njobids = z.njobids;
+    pp.M = M;
+    pp.model_driven = model_driven;
+    pp.valid = true;
+    return 0;
+}
+
+int pyxrd_update_population(pyxrd_ctx *ctx, const double *x) {
+    if (!ctx) return 1;
+    pyxrd_ctx::Population &pp = ctx->pop;
+    if (!pp.valid || !ctx->have_static) return fail(ctx, "update_population: no resident population (call pyxrd_set_population first)");
+    CK(cudaSetDevice(ctx->device));
+    const ExpandDev &e = pp.e;
+    const int K = e.K, D = e.D;
+    ctx->have_batch = false;
+    ctx->have_intensities = false;
+    ctx->have_opt = false;
+    int ncap = pp.ncap0;
+    if (x) {
+        pp.valid = false;                              // stays invalid if anything below fails
+        if (population_caps(ctx, x, K, D, &ncap)) return 1;
+        const size_t bytes = sizeof(double) * (size_t)K * D;
+        CK(cudaStreamSynchronize(ctx->stream));        // the staging blob may still feed the previous copy
+        char *stage = static_cast<char *>(ctx->h_tmpl.ptr) + pp.x_off;
+        memcpy(stage, x, bytes);
+        CK(cudaMemcpyAsync(static_cast<char *>(ctx->d_tmpl.ptr) + pp.x_off, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        // same solution vectors: the caps of the resident population stand
+        ncap = ctx->bt.ncap;
+    }
+    BatchSizes z;
+    z.K = K; z.M = pp.M; z.NP = e.NP * K; z.NC = e.NC * K; z.NA = e.NA * K; z.NPC = e.NPC * K; z.NM = e.NM * K;
+    z.NJ = pp.NJ; z.njobids = pp.njobids; z.model_driven = pp.model_driven;
+    const BlobLayout L = plan_blob(z, ctx->st.S);
+    k_expand_population<<<K, 128, 0, ctx->stream>>>(e);
+    LAUNCH_CHECK("k_expand_population");
+    if (bind_batch(ctx, z, L, ncap, pp.acap)) return 1;
+    pp.valid = true;
+    return 0;
 }
 
 int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop, double *residuals_out) {

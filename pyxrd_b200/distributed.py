@@ -8,7 +8,7 @@ the CPU tests).  A single pattern / trial is never split across GPUs.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -52,60 +52,103 @@ def shard(items: Sequence, rank: int, world_size: int):
     return items[lo:hi]
 
 
+_pad_buffers = {}
+
+
 def gather_rows(local, n_total: int, world_size: int, group=None):
     """All-gather row blocks of unequal length: ``local`` is a torch tensor [k_rank, C] on the
-    device the process group communicates on; returns [n_total, C] on every rank."""
+    device the process group communicates on (on the GPU path: the zero-copy view of the library's residual buffer,
+    ``Context.residuals_tensor``); returns [n_total, C] on every rank.  Ranks hold ceil(n / ws) rows (the tail ranks
+    fewer): blocks are padded to that length in a reused staging buffer, one ``all_gather_into_tensor``.  The result
+    is a view of a reused buffer: copy it (``_to_host``) before the next gather."""
     import torch
     import torch.distributed as dist
     per = -(-int(n_total) // int(world_size)) if n_total > 0 else 0
     cols = local.shape[1]
-    padded = torch.zeros((per, cols), dtype=local.dtype, device=local.device)
-    padded[: local.shape[0]] = local
-    out = torch.empty((world_size * per, cols), dtype=local.dtype, device=local.device)
-    if world_size > 1:
-        dist.all_gather_into_tensor(out, padded, group=group)
+    if world_size <= 1:
+        return local[:n_total]
+    key = (per, cols, local.dtype, str(local.device), world_size)
+    bufs = _pad_buffers.get(key)
+    if bufs is None:
+        if len(_pad_buffers) > 16:
+            _pad_buffers.clear()
+        bufs = _pad_buffers[key] = (torch.zeros((per, cols), dtype=local.dtype, device=local.device),
+                                    torch.empty((world_size * per, cols), dtype=local.dtype, device=local.device))
+    padded, out = bufs
+    if local.shape[0] == per:
+        padded = local if local.is_contiguous() else local.contiguous()
     else:
-        out.copy_(padded)
+        padded[: local.shape[0]].copy_(local)
+    dist.all_gather_into_tensor(out, padded, group=group)
     return out[:n_total]
+
+
+def _to_host(t) -> np.ndarray:
+    """host copy of a gathered table (never a view of the reused gather buffer)"""
+    return (t.cpu() if t.is_cuda else t.clone()).numpy()
+
+
+def _as_rows(values, rows: int, device):
+    """(tensor [rows, C], squeeze): the rank's block as a 2-D torch tensor on ``device``; a torch tensor that already
+    lives on the device (zero-copy view of the library's result buffer) is used as it is"""
+    import torch
+    if isinstance(values, torch.Tensor):
+        t = values if values.dim() == 2 else values.reshape(rows, -1)
+        return (t if device is None or t.device == torch.device(device) else t.to(device)), False
+    values = np.asarray(values, dtype=np.float64)
+    squeeze = values.ndim == 1
+    t = torch.from_numpy(np.ascontiguousarray(values.reshape(rows, -1) if rows else values.reshape(0, max(values.shape[-1] if values.ndim == 2 else 1, 1))))
+    return (t.to(device) if device is not None else t), squeeze
 
 
 def evaluate_population_sharded(mixtures: Sequence, evaluate, device=None, group=None) -> np.ndarray:
     """Each rank evaluates its block of the population with ``evaluate(list) -> f64[k, 1+S]``
     (on the GPU path: ``pyxrd_b200.batched.population_residuals``) and all ranks receive the full
-    [K, 1+S] table, bit-identical to a single-rank evaluation of the same candidates."""
-    import torch
+    [K, 1+S] table, bit-identical to a single-rank evaluation of the same candidates.  ``evaluate`` may return a
+    torch tensor on ``device``: it is gathered as it is, without a trip through host memory."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     mine = shard(mixtures, rank, world)
     n_spec = len(mixtures[0].specimens)
-    res = np.asarray(evaluate(mine), dtype=np.float64).reshape(len(mine), 1 + n_spec) if len(mine) else \
-        np.zeros((0, 1 + n_spec))
-    t = torch.from_numpy(np.ascontiguousarray(res))
-    if device is not None:
-        t = t.to(device)
-    return gather_rows(t, len(mixtures), world, group).cpu().numpy()
+    values = evaluate(mine) if len(mine) else np.zeros((0, 1 + n_spec))
+    t, _ = _as_rows(values, len(mine), device)
+    return _to_host(gather_rows(t, len(mixtures), world, group))
 
 
-def evaluate_solutions_sharded(x, evaluate, device=None, group=None) -> np.ndarray:
-    """The template path over several GPUs: every rank evaluates its block of the solution matrix ``x`` f64[K, d] with
-    ``evaluate(x_block) -> f64[k] or f64[k, C]`` (on the GPU path ``PopulationTemplate.optimized_residuals`` /
-    ``.residuals`` of the rank's own template) and all ranks receive the values of all K solutions in order."""
+def evaluate_solutions_sharded(x, evaluate, device=None, group=None, columns: Optional[int] = None) -> np.ndarray:
+    """The template path over several GPUs (what ``RefineAsyncHelper.do_async_evaluation`` does with Pool tasks,
+    refinement/refine_async_helper.py:16-23, async_evaluatable.py:38-50): every rank evaluates its block of the solution
+    matrix ``x`` f64[K, d] with ``evaluate(x_block) -> f64[k] | f64[k, C]`` and all ranks receive the values of all K
+    solutions in order.  On the GPU path ``evaluate`` is ``lambda xb: template.residuals(xb, device=True)`` /
+    ``template.optimized_residuals(xb, device=True)`` of the rank's own template: the rank's rows are gathered straight
+    from the library's device buffer (NCCL over NVLink), one device -> host copy of the gathered table at the end.
+    ``columns``: C when known (saves the broadcast that tells empty tail ranks the column count)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     x = np.atleast_2d(np.asarray(x, dtype=np.float64))
     lo, hi = shard_bounds(len(x), world)[rank]
-    values = np.asarray(evaluate(x[lo:hi]), dtype=np.float64) if hi > lo else np.zeros(0)
-    cols = int(values.shape[1]) if values.ndim == 2 else 1
-    if world > 1:                                  # empty tail ranks learn the column count from rank 0
+    values = evaluate(x[lo:hi]) if hi > lo else np.zeros(0)
+    if isinstance(values, torch.Tensor):
+        cols, squeeze = (int(values.shape[1]) if values.dim() == 2 else 1), values.dim() == 1
+    else:
+        values = np.asarray(values, dtype=np.float64)
+        cols, squeeze = (int(values.shape[1]) if values.ndim == 2 else 1), values.ndim == 1
+    if columns is not None:
+        cols = int(columns)
+    elif world > 1:                                # empty tail ranks learn the column count from rank 0
         c = torch.tensor([cols], dtype=torch.int64, device=device if device is not None else "cpu")
         dist.broadcast(c, src=0, group=group)
         cols = int(c.item())
-    squeeze = values.ndim == 1 and cols == 1
-    t = torch.from_numpy(np.ascontiguousarray(values.reshape(hi - lo, cols)))
-    if device is not None:
-        t = t.to(device)
-    out = gather_rows(t, len(x), world, group).cpu().numpy()
-    return out[:, 0] if squeeze else out
+    if isinstance(values, torch.Tensor):
+        t = values.reshape(hi - lo, cols)
+        if device is not None and t.device != torch.device(device):
+            t = t.to(device)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(values.reshape(hi - lo, cols)))
+        if device is not None:
+            t = t.to(device)
+    out = _to_host(gather_rows(t, len(x), world, group))
+    return out[:, 0] if (squeeze and cols == 1) else out

@@ -17,6 +17,7 @@ DataObject that receives the value as a target of the same Refinable.
 """
 from __future__ import annotations
 
+import itertools
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -55,6 +56,9 @@ class Refinable(object):
         self.minimum, self.maximum = float(minimum), float(maximum)
 
 
+_serials = itertools.count(1)
+
+
 class PopulationTemplate(object):
     """Template candidate + resolved binding table."""
 
@@ -62,6 +66,7 @@ class PopulationTemplate(object):
                  csds_factor: Optional[float] = None, static: Optional[StaticPack] = None):
         self.mixture = mixture
         self.refinables = list(refinables)
+        self._serial = next(_serials)
         if static is None:
             types = collect_atom_types(mixture.specimens)
             z = 0
@@ -190,19 +195,32 @@ class PopulationTemplate(object):
         """host only: arrays of the expanded K-candidate batch (dict), see runtime.expand_population"""
         return expand_population(self.batch, self._x(x), self.bindings, self.csds_auto, self.csds_factor)
 
-    def residuals(self, x, ctx: Optional[Context] = None):
+    def _key(self):
+        """identity of what ``pyxrd_set_population`` uploads besides x: a later call with the same key and shape of x only
+        uploads the new solution vectors (``pyxrd_update_population``)"""
+        return (self._serial, id(self.batch), id(self.bindings), id(self.csds_auto), self.csds_factor)
+
+    def _load(self, ctx: Context, x):
+        if ctx.set_static(self.static):
+            pass                                  # fresh tables: nothing of an earlier population survives
+        ctx.load_population(self.batch, x, self.bindings, self.csds_auto, self.csds_factor, key=self._key())
+
+    def residuals(self, x, ctx: Optional[Context] = None, device: bool = False):
         """f64[K, 1+S]: ``calculate_mixture`` residuals (mixture.py:221-257) of the K solutions at the
-        template's fractions / scales / bgshifts (or the bound ones)"""
+        template's fractions / scales / bgshifts (or the bound ones).  ``device=True``: a zero-copy torch view of the
+        device buffer instead of a host array (no synchronisation; for the NCCL gather of ``distributed``)"""
         ctx = ctx or default_context()
         with ctx.lock:
-            ctx.set_static(self.static)
             ctx.set_residual_method(settings.get("RESIDUAL_METHOD"))
-            return ctx.evaluate_population(self.batch, self._x(x), self.bindings, self.csds_auto, self.csds_factor)
+            self._load(ctx, self._x(x))
+            ctx.compute_all(False)
+            return ctx.residuals_tensor() if device else ctx.read_residuals()
 
     def optimized_residuals(self, x, ctx: Optional[Context] = None, outer: int = 0, newton: int = 0,
-                            want_solutions: bool = False):
+                            want_solutions: bool = False, device: bool = False):
         """f64[K]: ``get_optimized_residual`` (mixture.py:268-276) of the K solutions -- phase patterns,
-        then the device mixture optimiser; with ``want_solutions`` also f64[K, M+2S]"""
+        then the device mixture optimiser; with ``want_solutions`` also f64[K, M+2S].  ``device=True``: the zero-copy
+        torch view f64[K, 1+S] of the optimiser's residual table on the device"""
         ctx = ctx or default_context()
         reason = self.optimiser_scope()
         if reason:
@@ -210,17 +228,20 @@ class PopulationTemplate(object):
                              "mixture (%s): evaluate its trials one by one through calculations.mixture" % reason)
         refine_bg = self.mixture_refines_background()
         with ctx.lock:
-            ctx.set_static(self.static)
-            res, sol = ctx.optimize_population(self.batch, self._x(x), self.bindings, self.csds_auto, self.csds_factor,
-                                               refine_bg=refine_bg, outer=outer, newton=newton)
+            self._load(ctx, self._x(x))
+            ctx.compute_intensities()
+            ctx.optimize(refine_bg=refine_bg, outer=outer, newton=newton)
+            if device:
+                return ctx.residuals_tensor(optimised=True)
+            res = ctx.read_opt_residuals()
+            sol = ctx.read_solutions() if want_solutions else None
         return (res[:, 0], sol) if want_solutions else res[:, 0]
 
     def phase_intensities(self, x, ctx: Optional[Context] = None):
         """list over candidates of list over specimens of f64[M, Z, X_s]"""
         ctx = ctx or default_context()
         with ctx.lock:
-            ctx.set_static(self.static)
-            ctx.set_population(self.batch, self._x(x), self.bindings, self.csds_auto, self.csds_factor)
+            self._load(ctx, self._x(x))
             ctx.compute_intensities()
             return ctx.split_per_specimen(ctx.read_intensities_flat(), (self.batch.M, self.static.Z))
 

@@ -68,7 +68,7 @@ EXPORTS = [
     "pyxrd_read_correction", "pyxrd_device_buffers", "pyxrd_evaluate_host", "pyxrd_optimize_host", "pyxrd_leaf_asf",
     "pyxrd_leaf_lpf", "pyxrd_leaf_csds", "pyxrd_leaf_component", "pyxrd_stage_times", "pyxrd_dfma_peak",
     "pyxrd_expand_population", "pyxrd_expanded_desc", "pyxrd_expanded_free", "pyxrd_expand_error",
-    "pyxrd_set_population", "pyxrd_evaluate_population", "pyxrd_optimize_population", "pyxrd_leaf_probabilities",
+    "pyxrd_set_population", "pyxrd_update_population", "pyxrd_device_results", "pyxrd_evaluate_population", "pyxrd_optimize_population", "pyxrd_leaf_probabilities",
     "pyxrd_leaf_statistic", "pyxrd_leaf_derive", "pyxrd_leaf_lorentz",
 ]
 
@@ -148,6 +148,8 @@ def load_library():
         lib.pyxrd_expand_error.argtypes = []
         lib.pyxrd_expand_error.restype = C.c_char_p
         lib.pyxrd_set_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc)]
+        lib.pyxrd_update_population.argtypes = [vp, _f64p]
+        lib.pyxrd_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         lib.pyxrd_evaluate_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc), _f64p]
         lib.pyxrd_optimize_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc), C.c_int, C.c_int,
                                                   C.c_int, _f64p, _f64p]
@@ -191,6 +193,8 @@ class Context(object):
         # which parsed mixture the resident batch + intensities belong to (calculations/mixture.py); every call that
         # replaces the static tables, the batch or its intensities clears it
         self._resident_token = None
+        # which population (template, table, K) is resident for pyxrd_update_population; cleared together with the token
+        self._population_key = None
 
     def new_resident_token(self):
         """mark the resident batch as belonging to one caller-side object; unique across processes and contexts (the
@@ -200,6 +204,7 @@ class Context(object):
 
     def invalidate_residency(self):
         self._resident_token = None
+        self._population_key = None
 
     # -- plumbing ---------------------------------------------------------------------
     def close(self):
@@ -220,6 +225,7 @@ class Context(object):
 
     def set_stream(self, cuda_stream_handle: Optional[int]):
         self._check(self._lib.pyxrd_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)), "set_stream")
+        self._stream_handle = int(cuda_stream_handle or 0)
 
     def synchronize(self):
         self._check(self._lib.pyxrd_synchronize(self._h), "synchronize")
@@ -243,7 +249,7 @@ class Context(object):
                        _p(static.wl_index, _i32p), _p(static.wl_w_hi, _f64p), _p(static.wl_w_lo, _f64p),
                        _p(static.observed, _f64p), _p(static.selected, _u8p), _p(static.atype_table, _f64p),
                        _p(static.stl_override, _f64p) if static.stl_override is not None else None)
-        self._resident_token = None
+        self.invalidate_residency()
         self._check(self._lib.pyxrd_set_static(self._h, C.byref(d)), "set_static")
         self._static, self._static_sig, self._batch = static, sig, None
         return True
@@ -259,7 +265,7 @@ class Context(object):
                          _p(b.prob_params, _f64p) if getattr(b, "prob_params", None) is not None else None)
 
     def set_batch(self, batch: BatchPack):
-        self._resident_token = None
+        self.invalidate_residency()
         d = self.batch_desc(batch)
         self._check(self._lib.pyxrd_set_batch(self._h, C.byref(d)), "set_batch")
         self._batch = batch
@@ -270,7 +276,7 @@ class Context(object):
         self._check(self._lib.pyxrd_set_solution(self._h, _p(f, _f64p), _p(s, _f64p), _p(g, _f64p)), "set_solution")
 
     def set_intensities(self, flat):
-        self._resident_token = None
+        self.invalidate_residency()
         flat = _f64(flat).ravel()
         self._check(self._lib.pyxrd_set_intensities(self._h, _p(flat, _f64p), flat.size), "set_intensities")
 
@@ -315,7 +321,7 @@ class Context(object):
                       out_intensities=None):
         """one C-ABI call: upload K candidates, compute, return residuals [K, 1+S] (+ intensities).
         ``out_*`` may be preallocated (e.g. pinned) float64 arrays."""
-        self._resident_token = None
+        self.invalidate_residency()
         d = self.batch_desc(batch)
         res = np.empty(batch.K * (batch.S + 1)) if out_residuals is None else out_residuals
         inten = out_intensities
@@ -330,7 +336,7 @@ class Context(object):
                       out_residuals=None, out_solutions=None):
         """one C-ABI call per generation: K candidates in (host), optimised residuals [K, 1+S] and
         solutions [K, M+2S] out (host)"""
-        self._resident_token = None
+        self.invalidate_residency()
         d = self.batch_desc(batch)
         res = np.empty(batch.K * (batch.S + 1)) if out_residuals is None else out_residuals
         sol = np.empty(batch.K * (batch.M + 2 * batch.S)) if out_solutions is None else out_solutions
@@ -468,7 +474,7 @@ class Context(object):
 
     # -- populations from a template + binding table ----------------------------------------
     def _population_desc(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5):
-        self._resident_token = None               # every population call replaces the resident batch
+        self.invalidate_residency()               # every population call replaces the resident batch
         x = np.ascontiguousarray(x, dtype=np.float64)
         if x.ndim != 2:
             raise ValueError("x must be [K, d]")
@@ -490,11 +496,46 @@ class Context(object):
         self._batch = _Shape(K, template.M, template.S, template.Z)
         return res.reshape(K, template.S + 1)
 
-    def set_population(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5):
+    def set_population(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5, key=None):
+        """upload template + solution vectors + table, expand on the device, run the batch prologue.  ``key``: any
+        hashable identity of (template, table); a later ``update_population`` of the same key and K re-uses the
+        resident template"""
         d = self.batch_desc(template)
         pop, keep = self._population_desc(template, x, bindings, csds_auto, csds_factor)
         self._check(self._lib.pyxrd_set_population(self._h, C.byref(d), C.byref(pop)), "set_population")
         self._batch = _Shape(keep[0].shape[0], template.M, template.S, template.Z)
+        self._population_key = None if key is None else (key, keep[0].shape)
+
+    def population_is_resident(self, key, shape) -> bool:
+        return key is not None and self._population_key == (key, tuple(shape))
+
+    def update_population(self, x=None):
+        """the next generation of the resident population: only x f64[K, d] is uploaded (None: the resident vectors
+        are expanded again)"""
+        if self._population_key is None and x is not None:
+            raise DeviceError("update_population: no resident population")
+        if x is not None:
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            if x.shape != self._population_key[1]:
+                raise ValueError("update_population: x is %r, the resident population is %r" % (x.shape, self._population_key[1]))
+        keep_key, keep_batch = self._population_key, self._batch
+        self._resident_token = None
+        try:
+            self._check(self._lib.pyxrd_update_population(self._h, _p(x, _f64p) if x is not None else None), "update_population")
+        except DeviceError:
+            self._population_key = None
+            raise
+        self._population_key, self._batch = keep_key, keep_batch
+
+    def load_population(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5, key=None):
+        """``update_population`` when (key, x.shape) is resident, else ``set_population``"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if self.population_is_resident(key, x.shape):
+            try:
+                return self.update_population(x)
+            except DeviceError:
+                pass                # e.g. dropped on the library side: upload everything again
+        self.set_population(template, x, bindings, csds_auto, csds_factor, key=key)
 
     def optimize_population(self, template: BatchPack, x, bindings, csds_auto=None, csds_factor=2.5,
                             refine_bg: bool = True, outer: int = 0, newton: int = 0):
@@ -516,11 +557,22 @@ class Context(object):
         self._check(self._lib.pyxrd_stage_times(self._h, _p(out, _f64p)), "stage_times")
         return dict(phase=out[0], wavelength=out[1], residual=out[2], prologue=out[3])
 
-    def residuals_tensor(self):
-        """zero-copy torch view f64[K, 1+S] of the device residual buffer (for the NCCL gather)"""
+    def device_results(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.pyxrd_device_results(self._h, C.byref(a), C.byref(b)), "device_results")
+        return a.value, b.value
+
+    def residuals_tensor(self, optimised: bool = False):
+        """zero-copy torch view f64[K, 1+S] of the device residual buffer (``optimised``: of the optimiser's residuals),
+        for the NCCL gather; valid until the next call that replaces the batch"""
         import torch
         b = self._batch
-        _, _, res = self.device_buffers()
+        res = self.device_results()[0] if optimised else self.device_buffers()[2]
+        # the library's kernels run on the context's stream; unless that IS torch's current stream, whatever torch does
+        # with the view (a collective, a copy) must not start before they finish
+        if getattr(self, "_stream_handle", 0) == 0 or \
+                torch.cuda.current_stream(self.device).cuda_stream != self._stream_handle:
+            self.synchronize()
 
         class _View(object):
             __cuda_array_interface__ = dict(shape=(b.K, b.S + 1), typestr="<f8", data=(int(res), False), version=3)

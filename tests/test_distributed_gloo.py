@@ -40,7 +40,12 @@ def _worker(rank, world, port, out_dir):
     x = np.arange(7 * 3, dtype=float).reshape(7, 3)                  # 7 solutions over 2 ranks: 4 + 3
     one = evaluate_solutions_sharded(x, lambda block: block.sum(axis=1) * 2.0)
     two = evaluate_solutions_sharded(x, lambda block: np.stack([block[:, 0], block[:, 2] - block[:, 1]], axis=1))
-    np.save(os.path.join(out_dir, "sol%d.npy" % rank), np.column_stack([one, two]))
+    # an evaluator that hands back a torch tensor (on the GPU path: the zero-copy view of the device buffer) is gathered
+    # as it is; `columns` saves the broadcast of the column count
+    import torch
+    three = evaluate_solutions_sharded(x, lambda block: torch.from_numpy(np.stack([block[:, 1], block[:, 0] * 0.5], axis=1)),
+                                       columns=2)
+    np.save(os.path.join(out_dir, "sol%d.npy" % rank), np.column_stack([one, two, three]))
     dist.destroy_process_group()
 
 
@@ -70,5 +75,5 @@ def test_two_rank_gather_equals_single_rank(tmp_path):
         want.append(m.residuals)
     assert np.array_equal(a, np.array(want, dtype=float))
     x = np.arange(7 * 3, dtype=float).reshape(7, 3)
-    want = np.column_stack([x.sum(axis=1) * 2.0, x[:, 0], x[:, 2] - x[:, 1]])
+    want = np.column_stack([x.sum(axis=1) * 2.0, x[:, 0], x[:, 2] - x[:, 1], x[:, 1], x[:, 0] * 0.5])
     assert np.array_equal(np.load(tmp_path / "sol0.npy"), want) and np.array_equal(np.load(tmp_path / "sol1.npy"), want)
