@@ -309,7 +309,7 @@ def measure_generation(env, name, per_gpu, optimise, verify=True):
                 ctx.compute_intensities()
                 ctx.optimize(refine_bg=refine_bg)
             else:
-                ctx.compute_all(False)
+                ctx.compute_all(residuals_only=True)
             if env.world > 1:
                 dist.all_gather_into_tensor(gathered, ctx.residuals_tensor(optimised=optimise))
 

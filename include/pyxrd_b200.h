@@ -241,11 +241,15 @@ int pyxrd_set_intensities(pyxrd_ctx *ctx, const double *intensities, int64_t cou
 int pyxrd_compute_intensities(pyxrd_ctx *ctx);
 /* Scale / sum / background and Rp per specimen (specimen.py:84-88,16-19,
  * statistics.py:22-27, mixture.py:222-257).  Result: residuals f64 [K][1+S]
- * ([k][0] = mean over specimens), totals f64 [K][S][Z][X_s]; with want_scaled != 0
- * also scaled_phase_intensities f64 [K][S][M][Z][X_s]. */
-int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled);
-/* pyxrd_compute_intensities + pyxrd_compute_residuals as one call (calculate_mixture for the resident batch) */
-int pyxrd_compute_all(pyxrd_ctx *ctx, int want_scaled);
+ * ([k][0] = mean over specimens), totals f64 [K][S][Z][X_s]; flags: PYXRD_WANT_SCALED
+ * also stores scaled_phase_intensities f64 [K][S][M][Z][X_s], PYXRD_RESIDUALS_ONLY skips the totals. */
+#define PYXRD_WANT_SCALED 1     /* also scaled_phase_intensities (calculate_mixture hands them back) */
+#define PYXRD_RESIDUALS_ONLY 2  /* the total patterns are summed on the fly but not stored (a refinement trial only
+                                 * needs residuals [K][1+S]); pyxrd_read_totals fails afterwards */
+int pyxrd_compute_residuals(pyxrd_ctx *ctx, int flags);
+/* pyxrd_compute_intensities + pyxrd_compute_residuals as one call (calculate_mixture for the resident batch); the last
+ * pass of the wavelength distribution runs inside the residual kernel (the patterns are not read a second time) */
+int pyxrd_compute_all(pyxrd_ctx *ctx, int flags);
 
 /* Which pattern residual pyxrd_compute_residuals / pyxrd_evaluate_host report (settings.py:27-32,
  * mixture.py:22-27,89): PYXRD_RESIDUAL_RP = statistics.py:22-27 (default), PYXRD_RESIDUAL_RPDER =

@@ -1996,15 +1996,22 @@ __global__ void __launch_bounds__(PX_WL_TPB) k_wavelength_pass(StaticDev st, Bat
 
 // ---------------------------------------------------------------------------------
 // mixture: total = scale * sum_p frac_p I_p + bg * C ; Rp = 100 sum|obs - total| / sum|obs|
-// 4 points in flight per thread
+// (specimen.py:84-88,16-19, statistics.py:22-27), optionally FUSED with the last pass of the wavelength distribution
+// (GATHER): the block forms I_p <- I_p + interp(f_j I_p) for every phase of its tile on the fly -- the same operations
+// in the same order as k_wavelength_pass -- writes the final pattern (dst) and feeds it straight into the sum, so the
+// patterns are not read a second time and the abscissa tables (index + two weights, 20 B per point) are fetched once
+// per point instead of once per point and phase.
+// grid (candidates, 1024-point tiles, S): a block owns one tile of one (candidate, specimen) for all Z patterns and M
+// phases, 4 points in flight per thread (one block per (candidate, specimen) looping over the whole pattern was
+// latency-bound: 91 us against 50 us for c2).  Its sum |obs - total| goes to partial[((k - k0) S + s) ntiles + tile];
+// k_residual_finish adds the tiles in order (deterministic).  want_totals = 0: the total pattern is only summed, not
+// stored (callers that want residuals only).
 // ---------------------------------------------------------------------------------
 #define PX_RES_TPB 256
 #define PX_RES_PPT 4
-// grid (candidates, 1024-point tiles, S): a block owns one tile of one (candidate, specimen) for all Z patterns and M
-// phases (a streaming pass like k_wavelength_pass; one block per (candidate, specimen) looping over the whole pattern
-// was latency-bound: 91 us against 50 us for c2).  Its sum |obs - total| goes to partial[((k - k0) S + s) ntiles + tile];
-// k_residual_finish adds the tiles in order (deterministic).
-__global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, BatchDev bt, int k0, int want_scaled,
+template <bool GATHER>
+__global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, BatchDev bt, int k0, int want_scaled, int want_totals,
+                                                                int pass, const double *__restrict__ src, double *__restrict__ dst,
                                                                 double *__restrict__ partial) {
     const int s = blockIdx.z, k = k0 + blockIdx.x, tile = blockIdx.y;       // candidates on x: grid.y / z stop at 65535
     const int X = st.spec_npts[s], Z = st.Z, M = bt.M;
@@ -2012,8 +2019,10 @@ __global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, B
     double num = 0.0;
     if (tile * (PX_RES_TPB * PX_RES_PPT) < X) {
         const long long soff = st.spec_off[s];
-        const double *I = bt.intensities + (long long)k * bt.cand_stride + (long long)M * Z * soff;
-        double *scaled = (want_scaled && bt.scaled) ? bt.scaled + (long long)k * bt.cand_stride + (long long)M * Z * soff : nullptr;
+        const long long cbase = (long long)k * bt.cand_stride + (long long)M * Z * soff;
+        const double *I = src + cbase;
+        double *O = GATHER ? dst + cbase : nullptr;
+        double *scaled = (want_scaled && bt.scaled) ? bt.scaled + cbase : nullptr;
         double *tot = bt.totals + ((long long)k * st.sumX + soff) * Z;
         const double *obs = st.observed + (long long)Z * soff;
         const unsigned char *sel = st.selected + soff;
@@ -2021,6 +2030,20 @@ __global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, B
         const double scale = bt.scales[k * st.S + s], bg = bt.bgshifts[k * st.S + s];
         const double *frac = bt.fractions + (long long)k * M;
         const long long pstride = (long long)Z * X;                   // phase stride inside [M][Z][X]
+        int hi[PX_RES_PPT];
+        double whi[PX_RES_PPT], wlo[PX_RES_PPT], f = 0.0;
+        if constexpr (GATHER) {
+            const bool active = pass < st.spec_nwl[s];
+            const long long off = st.wl_off[s] + (long long)pass * X;
+            f = active ? st.wl_fraction[st.wl_first[s] + pass] : 0.0;
+#pragma unroll
+            for (int u = 0; u < PX_RES_PPT; ++u) {
+                const int x = xb + u * PX_RES_TPB;
+                hi[u] = (active && x < X) ? __ldg(st.wl_index + off + x) : -1;
+                whi[u] = hi[u] >= 0 ? __ldg(st.wl_w_hi + off + x) : 0.0;
+                wlo[u] = hi[u] >= 0 ? __ldg(st.wl_w_lo + off + x) : 0.0;
+            }
+        }
         for (int z = 0; z < Z; ++z) {
             const double *Iz = I + (long long)z * X;
             double *Sz = scaled ? scaled + (long long)z * X : nullptr;
@@ -2033,6 +2056,20 @@ __global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, B
                 double iv[PX_RES_PPT];
 #pragma unroll
                 for (int u = 0; u < PX_RES_PPT; ++u) iv[u] = (xb + u * PX_RES_TPB < X) ? Ip[xb + u * PX_RES_TPB] : 0.0;
+                if constexpr (GATHER) {
+                    double hv[PX_RES_PPT], lv[PX_RES_PPT];
+#pragma unroll
+                    for (int u = 0; u < PX_RES_PPT; ++u) {
+                        hv[u] = hi[u] >= 0 ? Ip[hi[u]] : 0.0;
+                        lv[u] = hi[u] >= 0 ? Ip[hi[u] - 1] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < PX_RES_PPT; ++u) {
+                        if (hi[u] >= 0)             // the operations of k_wavelength_pass, in its order
+                            iv[u] = __dadd_rn(iv[u], __dadd_rn(__dmul_rn(whi[u], __dmul_rn(hv[u], f)), __dmul_rn(wlo[u], __dmul_rn(lv[u], f))));
+                        if (xb + u * PX_RES_TPB < X) O[(long long)z * X + p * pstride + xb + u * PX_RES_TPB] = iv[u];
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < PX_RES_PPT; ++u) {
                     const double v = __dmul_rn(__dmul_rn(fp, iv[u]), scale);
@@ -2045,7 +2082,7 @@ __global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, B
                 const int x = xb + u * PX_RES_TPB;
                 if (x >= X) continue;
                 const double t = __dadd_rn(acc[u], __dmul_rn(bg, corr[x]));
-                tot[(long long)z * X + x] = t;
+                if (want_totals) tot[(long long)z * X + x] = t;
                 if (sel[x]) num += fabs(obs[(long long)z * X + x] - t);
             }
         }

@@ -145,6 +145,7 @@ struct pyxrd_ctx {
     PinBuf h_res;
     DevBuf d_leaf_a, d_leaf_b, d_leaf_c, d_leaf_d, d_sol, d_optres;
     bool have_opt = false;
+    bool have_totals = false;
     int64_t int_count = 0, tot_count = 0;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_set[4] = {false, false, false, false};
@@ -820,6 +821,7 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     ctx->have_batch = false;
     ctx->have_intensities = false;
     ctx->have_opt = false;
+    ctx->have_totals = false;
     ctx->pop.valid = false;                  // the blob of a device-expanded population is overwritten
     const StaticDev &st = ctx->st;
     if (d->n_candidates <= 0 || d->n_phase_slots <= 0)
@@ -923,19 +925,23 @@ int phase_range(pyxrd_ctx *ctx, int k0, int k1, double *target, bool timed) {
     return 0;
 }
 
-int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
+// phase patterns + wavelength passes of the candidates [k0, k1).  fuse_last: the last pass of the wavelength
+// distribution is left to the residual kernel (k_mixture_residual<true>); *last_src then names the buffer it reads.
+int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed, bool fuse_last = false, const double **last_src = nullptr) {
     const StaticDev &st = ctx->st;
     double *bufs[2] = {ctx->d_int.as<double>(), ctx->d_int2.as<double>()};
     int cur = ctx->wl_passes & 1;                      // passes alternate cur -> 1 - cur and must end in 0
     const long long j0 = (long long)k0 * ctx->jobs_per_cand, j1 = (long long)k1 * ctx->jobs_per_cand;
     if (phase_range(ctx, k0, k1, bufs[cur], timed)) return 1;
+    const int separate = ctx->wl_passes - (fuse_last && ctx->wl_passes > 0 ? 1 : 0);
     if (j1 > j0 && st.maxX > 0)
-        for (int pass = 0; pass < ctx->wl_passes; ++pass) {
+        for (int pass = 0; pass < separate; ++pass) {
             dim3 grid((unsigned)(j1 - j0), (unsigned)((st.maxX + PX_WL_TPB * PX_WL_PPT - 1) / (PX_WL_TPB * PX_WL_PPT)));
             k_wavelength_pass<<<grid, PX_WL_TPB, 0, ctx->stream>>>(st, ctx->bt, (int)j0, pass, bufs[cur], bufs[1 - cur]);
             LAUNCH_CHECK("k_wavelength_pass");
             cur = 1 - cur;
         }
+    if (last_src) *last_src = bufs[cur];
     if (timed) {
         CK(cudaEventRecord(ctx->ev[3], ctx->stream));
         ctx->ev_set[0] = ctx->ev_set[1] = true;
@@ -943,9 +949,14 @@ int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed) {
     return 0;
 }
 
-// mixture totals + residuals of the candidates [k0, k1)
-int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed) {
+// mixture totals + residuals of the candidates [k0, k1).  flags: bit 0 = also the scaled phase patterns, bit 1 =
+// residuals only (the total patterns are summed but not stored).  gather_src != nullptr: the last wavelength pass is
+// taken on the fly from that buffer and the final patterns are written to d_int by the same kernel.
+int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const double *gather_src = nullptr) {
     BatchDev bt = ctx->bt;
+    const int want_scaled = flags & 1;
+    int want_totals = (flags & 2) ? 0 : 1;
+    if (ctx->residual_method == PYXRD_RESIDUAL_RPDER) want_totals = 1;      // k_residual_rpder reads the totals
     if (want_scaled) {
         CK(ctx->d_scaled.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
         bt.scaled = ctx->d_scaled.as<double>();
@@ -956,7 +967,12 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed)
         const int tile = PX_RES_TPB * PX_RES_PPT, ntiles = std::max(1, (ctx->st.maxX + tile - 1) / tile);
         CK(ctx->d_partial.ensure(sizeof(double) * (size_t)(k1 - k0) * ctx->st.S * ntiles));
         dim3 tgrid(k1 - k0, ntiles, ctx->st.S);
-        k_mixture_residual<<<tgrid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled, ctx->d_partial.as<double>());
+        if (gather_src)
+            k_mixture_residual<true><<<tgrid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled, want_totals, ctx->wl_passes - 1,
+                                                                            gather_src, ctx->d_int.as<double>(), ctx->d_partial.as<double>());
+        else
+            k_mixture_residual<false><<<tgrid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled, want_totals, 0,
+                                                                             ctx->d_int.as<double>(), nullptr, ctx->d_partial.as<double>());
         LAUNCH_CHECK("k_mixture_residual");
         k_residual_finish<<<((k1 - k0) * ctx->st.S + 127) / 128, 128, 0, ctx->stream>>>(ctx->st, bt, k0, k1, ntiles,
                                                                                       ctx->d_partial.as<double>());
@@ -982,6 +998,7 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed)
         k_mixture_mean<<<(k1 - k0 + 127) / 128, 128, 0, ctx->stream>>>(k0, k1, ctx->st.S, bt.residuals);
         LAUNCH_CHECK("k_mixture_mean");
     }
+    ctx->have_totals = want_totals != 0;
     if (timed) {
         CK(cudaEventRecord(ctx->ev[5], ctx->stream));
         ctx->ev_set[2] = true;
@@ -989,22 +1006,23 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed)
     return 0;
 }
 
-// patterns + residuals of the candidates [k0, k1) at the batch's solution.  (A single pass that composes the
-// wavelength entries per point and forms totals / residuals on the fly was measured: 0.23 ms against 0.21 ms for
-// the three streaming kernels on c2 -- three levels of dependent gathers per point -- and dropped.)
-int evaluate_range(pyxrd_ctx *ctx, int k0, int k1, int want_scaled, bool timed) {
-    if (intensities_range(ctx, k0, k1, timed)) return 1;
-    return residuals_range(ctx, k0, k1, want_scaled, timed);
+// patterns + residuals of the candidates [k0, k1) at the batch's solution: phase kernels, all wavelength passes but the
+// last as streaming kernels, the last one inside the residual kernel.  (A single pass that composes ALL the wavelength
+// entries per point was measured in round 1: three levels of dependent gathers per point, slower than the passes.)
+int evaluate_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed) {
+    const double *src = nullptr;
+    if (intensities_range(ctx, k0, k1, timed, true, &src)) return 1;
+    return residuals_range(ctx, k0, k1, flags, timed, ctx->wl_passes > 0 ? src : nullptr);
 }
 
 }  // namespace
 
 extern "C" {
 
-int pyxrd_compute_all(pyxrd_ctx *ctx, int want_scaled) {
+int pyxrd_compute_all(pyxrd_ctx *ctx, int flags) {
     if (!ctx || !ctx->have_batch) return fail(ctx, "compute_all: no resident batch");
     CK(cudaSetDevice(ctx->device));
-    if (evaluate_range(ctx, 0, ctx->bt.K, want_scaled, true)) return 1;
+    if (evaluate_range(ctx, 0, ctx->bt.K, flags, true)) return 1;
     ctx->have_intensities = true;
     return 0;
 }
@@ -1025,10 +1043,10 @@ int pyxrd_set_residual_method(pyxrd_ctx *ctx, int method) {
     return 0;
 }
 
-int pyxrd_compute_residuals(pyxrd_ctx *ctx, int want_scaled) {
+int pyxrd_compute_residuals(pyxrd_ctx *ctx, int flags) {
     if (!ctx || !ctx->have_batch || !ctx->have_intensities) return fail(ctx, "compute_residuals: intensities not computed");
     CK(cudaSetDevice(ctx->device));
-    return residuals_range(ctx, 0, ctx->bt.K, want_scaled, true);
+    return residuals_range(ctx, 0, ctx->bt.K, flags, true);
 }
 
 int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newton_iterations) {
@@ -1093,6 +1111,7 @@ int pyxrd_read_scaled(pyxrd_ctx *ctx, double *out, int64_t count) {
 }
 int pyxrd_read_totals(pyxrd_ctx *ctx, double *out, int64_t count) {
     if (!ctx || !ctx->have_batch) return fail(ctx, "read totals: no batch");
+    if (!ctx->have_totals) return fail(ctx, "read totals: the last residual call did not store them (PYXRD_RESIDUALS_ONLY)");
     return read_back(ctx, ctx->d_tot.ptr, out, count, ctx->tot_count, "totals");
 }
 int pyxrd_read_residuals(pyxrd_ctx *ctx, double *out, int64_t count) {
@@ -1130,7 +1149,7 @@ int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *re
     if (ctx->host_chunks > 0) nchunks = std::max(1, std::min(16, std::min(K, ctx->host_chunks)));
     for (int c = 0; c < nchunks; ++c) {
         const int k0 = (int)((long long)K * c / nchunks), k1 = (int)((long long)K * (c + 1) / nchunks);
-        if (evaluate_range(ctx, k0, k1, 0, nchunks == 1)) return 1;
+        if (evaluate_range(ctx, k0, k1, PYXRD_RESIDUALS_ONLY, nchunks == 1)) return 1;
         if (intensities_out && ctx->bt.cand_stride > 0) {
             CK(cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[c], 0));
@@ -1466,6 +1485,7 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     ctx->have_batch = false;
     ctx->have_intensities = false;
     ctx->have_opt = false;
+    ctx->have_totals = false;
     const int NP = t->n_phases, NC = t->n_components, NA = t->n_atoms, NPC = t->n_phase_comp, M = t->n_phase_slots;
     const int64_t NM = t->n_matrix;
     if ((int64_t)NP * K > 0x7fffffffLL || (int64_t)NA * K > 0x7fffffffLL || NM * K > 0x7fffffffLL)
@@ -1608,6 +1628,7 @@ int pyxrd_update_population(pyxrd_ctx *ctx, const double *x) {
     ctx->have_batch = false;
     ctx->have_intensities = false;
     ctx->have_opt = false;
+    ctx->have_totals = false;
     int ncap = pp.ncap0;
     if (x) {
         pp.valid = false;                              // stays invalid if anything below fails
@@ -1634,7 +1655,7 @@ int pyxrd_update_population(pyxrd_ctx *ctx, const double *x) {
 
 int pyxrd_evaluate_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_population_desc *pop, double *residuals_out) {
     if (pyxrd_set_population(ctx, t, pop)) return 1;
-    if (pyxrd_compute_all(ctx, 0)) return 1;
+    if (pyxrd_compute_all(ctx, PYXRD_RESIDUALS_ONLY)) return 1;
     return pyxrd_read_residuals(ctx, residuals_out, (int64_t)ctx->bt.K * (ctx->st.S + 1));
 }
 

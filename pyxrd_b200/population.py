@@ -213,7 +213,7 @@ class PopulationTemplate(object):
         with ctx.lock:
             ctx.set_residual_method(settings.get("RESIDUAL_METHOD"))
             self._load(ctx, self._x(x))
-            ctx.compute_all(False)
+            ctx.compute_all(residuals_only=True)
             return ctx.residuals_tensor() if device else ctx.read_residuals()
 
     def optimized_residuals(self, x, ctx: Optional[Context] = None, outer: int = 0, newton: int = 0,

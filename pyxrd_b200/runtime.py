@@ -298,12 +298,16 @@ class Context(object):
             self._check(self._lib.pyxrd_set_residual_method(self._h, code), "set_residual_method")
             self._residual_method = code
 
-    def compute_residuals(self, want_scaled: bool = False):
-        self._check(self._lib.pyxrd_compute_residuals(self._h, int(bool(want_scaled))), "compute_residuals")
+    def compute_residuals(self, want_scaled: bool = False, residuals_only: bool = False):
+        """``residuals_only``: the total patterns are not stored (PYXRD_RESIDUALS_ONLY)"""
+        flags = int(bool(want_scaled)) | (2 if residuals_only else 0)
+        self._check(self._lib.pyxrd_compute_residuals(self._h, flags), "compute_residuals")
 
-    def compute_all(self, want_scaled: bool = False):
-        """phase patterns + wavelength distribution + totals / residuals of the resident batch (fused pass)"""
-        self._check(self._lib.pyxrd_compute_all(self._h, int(bool(want_scaled))), "compute_all")
+    def compute_all(self, want_scaled: bool = False, residuals_only: bool = False):
+        """phase patterns + wavelength distribution + totals / residuals of the resident batch (the last wavelength
+        pass runs inside the residual kernel)"""
+        flags = int(bool(want_scaled)) | (2 if residuals_only else 0)
+        self._check(self._lib.pyxrd_compute_all(self._h, flags), "compute_all")
 
     def optimize(self, refine_bg: bool = True, outer: int = 0, newton: int = 0):
         """device optimiser over the resident batch (needs computed intensities)"""
