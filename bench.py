@@ -264,6 +264,11 @@ class Env(object):
         return (time.perf_counter() - t0) * 1e3
 
 
+def optimiser_threads(candidates, sm_count=148):
+    """block size k_mixture_optimize picks for a population of that size (pyxrd_b200.cu: launch_optimize)"""
+    return 256 if candidates <= 2 * sm_count else 128
+
+
 def observed_for(name, calc):
     """the 'observed' patterns of a configuration: its truth evaluated by the device path + noise (seed 1234)"""
     cfg = syn.CONFIGS[name]
@@ -328,9 +333,12 @@ def measure_generation(env, name, per_gpu, optimise, verify=True):
         e2e_ms = env.time_wall(step_e2e, args.steps, min(args.warmup, 2))
         check = None
         if verify and env.world > 1 and env.rank == 0:
-            # the gathered table equals a single-GPU evaluation of all K solutions, bit for bit
+            # the gathered table equals a single-GPU evaluation of all K solutions, bit for bit (same
+            # kernels: the optimiser's block size, which it otherwise picks by population size, is held at the shards')
+            ctx.set_option("optimizer_threads", optimiser_threads(per_gpu))
             alone = (tmpl.optimized_residuals(x_total, ctx=ctx, device=True) if optimise
                      else tmpl.residuals(x_total, ctx=ctx, device=True)).cpu().numpy()
+            ctx.set_option("optimizer_threads", 0)
             check = bool(np.array_equal(alone, table[0]))
             if not check:
                 raise AssertionError("%s: the gathered residual table differs from the single-GPU table" % name)
@@ -384,7 +392,9 @@ def measure_sweep(env, name="c5", totals=SWEEP_TOTALS, steps=2):
             ms = env.time_wall(step, steps, 1)
             check = None
             if env.world > 1 and env.rank == 0:
+                ctx.set_option("optimizer_threads", optimiser_threads(-(-total // env.world)))
                 alone = tmpl.optimized_residuals(x, ctx=ctx, device=True).cpu().numpy()
+                ctx.set_option("optimizer_threads", 0)
                 check = bool(np.array_equal(alone, table[0]))
                 if not check:
                     raise AssertionError("c5 sweep K=%d: gathered table differs from the single-GPU table" % total)
@@ -589,12 +599,12 @@ def run_b200(args, rank, world, local_rank):
     sampler.start()
     name = args.workload
     main = measure_generation(env, name, args.candidates or DEFAULT_CANDIDATES[name], optimise=False)
-    clocks = sampler.stop()
     trials = None
     if not args.no_trials:
         tw = args.trials_workload
         trials = measure_generation(env, tw, args.trials_candidates or DEFAULT_CANDIDATES[tw], optimise=True)
     sweep = None if args.no_sweep else measure_sweep(env)
+    clocks = sampler.stop()            # sampled over every timed region above (headline, trials, population sweep)
     download = configs = None
     if world == 1:
         download = measure_patterns_download(env, main)
