@@ -117,6 +117,14 @@ def population_work(tmpl, x):
     npt = t_pi.shape[0]
     t_struct = np.zeros(npt, dtype=int)
     t_exp = np.zeros(npt, dtype=int)
+    bound_layers = set()          # components with a refinable on one of their layer atoms (PYXRD_BIND_ATOM_D = 2)
+    for row in tmpl.bindings:
+        if int(row["target"]) == 2:
+            atom = int(row["index"]) // 2
+            for c in range(tmpl.batch.comp_i.shape[0]):
+                a0, nl = int(tmpl.batch.comp_i[c, 0]), int(tmpl.batch.comp_i[c, 1])
+                if a0 <= atom < a0 + nl:
+                    bound_layers.add(c)
     for p in range(npt):
         G, r = int(t_pi[p, 0]), int(t_pi[p, 1])
         if not (t_pi[p, 4] & 1) or (t_pi[p, 4] & 8) or G < 1:
@@ -127,14 +135,19 @@ def population_work(tmpl, x):
         else:
             off = int(t_pi[p, 6])
             t_struct[p] = structured_transitions(tmpl.batch.matrices[off + r * r: off + 2 * r * r].reshape(r, r), G)
-        # distinct planes of the phase (z after the interlayer stretch of the TEMPLATE; the count does not depend on x)
+        # complex exponentials the kernels evaluate for the phase: one per distinct plane (z after the interlayer stretch
+        # of the TEMPLATE; the count does not depend on x).  The layer planes of a component no refinable drives come from
+        # the layer table of the batch (k_layer_table: populations of >= 3 candidates) and cost no exponential here.
         zs = set()
         for c in tmpl.batch.phase_comp[t_pi[p, 5]: t_pi[p, 5] + G]:
             a0, nl, ni = (int(v) for v in tmpl.batch.comp_i[c, :3])
             d001, default_c, _, lattice_d = tmpl.batch.comp_d[c, :4]
             zf = (d001 - lattice_d) / (default_c - lattice_d)
+            tabulated = K >= 3 and c not in bound_layers
             for a in range(nl + ni):
                 z0 = tmpl.batch.atom_d[a0 + a, 1]
+                if a < nl and tabulated:
+                    continue
                 zs.add(float(z0) if a < nl else float(lattice_d + zf * (z0 - lattice_d)))
         t_exp[p] = len(zs)
     for p in range(NP):
@@ -654,7 +667,8 @@ def run_b200(args, rank, world, local_rank):
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                      "frac_executed": executed_tf / peak_tf if peak_tf else None,
                      "note": "frac: algorithmic count (one complex exponential per atom, SURVEY 8(d)); frac_executed: the "
-                             "exponentials the kernel evaluates (one per distinct plane of a phase)",
+                             "exponentials the kernel evaluates (one per distinct interlayer plane of a phase; the "
+                             "candidate-invariant layer stacks are read from the layer table of the batch)",
                      "peak_source": "DFMA microbenchmark pyxrd_dfma_peak measured in this run (MEASURED_PEAKS.json "
                                     "has no fp64 entry)",
                      "kernel_ms": phase_ms, "algorithmic_flops_per_launch": main["flops"],

@@ -208,7 +208,8 @@ int64_t pyxrd_launch_count(const pyxrd_ctx *ctx);
 /* Explicit measurement / experiment switches of one context (the library reads nothing from the environment; the
  * defaults are what the product runs).  Names: "use_structure" (1; 0 = treat structured transition matrices as dense),
  * "series_mma" (1; 0 = CUDA-core series for the ranks that have an FP64 tensor-core kernel), "overlap_classes" (1; 0 =
- * job classes one after the other), "optimizer_threads" (0 = by population size; 128 | 256), "host_chunks" (0 = by
+ * job classes one after the other), "layer_tables" (1; 0 = candidate-invariant layer stacks are evaluated inside the
+ * phase kernels instead of being tabulated once per batch), "optimizer_threads" (0 = by population size; 128 | 256), "host_chunks" (0 = by
  * population size; candidate chunks of pyxrd_evaluate_host), "optimizer_delta0" (1e-2), "optimizer_shrink" (0.5),
  * "optimizer_delta_min" (1e-7): weight-floor schedule of pyxrd_optimize relative to the mean observed intensity. */
 int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value);

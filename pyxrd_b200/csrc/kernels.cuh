@@ -105,6 +105,15 @@ struct BatchDev {
     double *atom_z;                  // [NA]   derived: stretched z
     int *atom_plane;                 // [NA]   derived: plane index within the component (runs of equal z)
     int *comp_nplanes;               // [NC]   derived
+    int *comp_ilplane;               // [NC]   derived: plane index of the first interlayer atom (= comp_nplanes without any)
+    // candidate-invariant layer stacks: the silicate layer of a component (atoms, contents, positions: calculate_z only
+    // moves INTERLAYER atoms, components.py:15-16,40-45) is the same for every candidate unless a refinable drives it;
+    // components with identical layer rows form a class whose part of the structure factor,
+    // sum_layer pn asf(s) exp(2 pi i z s), is tabulated once per batch per point (k_layer_table)
+    const int *comp_class;           // [NC]   class of the component's layer, -1: evaluated inside the phase kernels
+    const int *class_rep;            // [n_classes] a component of the class (its layer rows define the table)
+    int n_classes;
+    double2 *layer_tab;              // [n_classes][sumX] (+ PX_TABLE_PAD entries)
     double *phase_x;                 // [NP][4] derived: mean, abs_scale, ntop
     double *coef;                    // [NP][ncap] derived, index = power of Q
     const int *prob_model;           // [NP] PX_PROB_* (nullptr: every phase carries its W / P in the pool)
@@ -534,7 +543,7 @@ struct ExpandDev {
     int K, D, NB, NP, NC, NA, NPC, M, S, JPC, NCLS;
     long long NM, cand_stride;
     // template (one candidate)
-    const int *t_phase_i, *t_phase_comp, *t_comp_i, *t_atom_t, *t_job_pb, *t_job_spec, *t_jobids, *t_pmodel;
+    const int *t_phase_i, *t_phase_comp, *t_comp_i, *t_atom_t, *t_job_pb, *t_job_spec, *t_jobids, *t_pmodel, *t_comp_class;
     const long long *t_job_out;
     const double *t_phase_d, *t_matrices, *t_comp_d, *t_atom_d, *t_frac, *t_scales, *t_bg, *t_pparam;
     const int *cls_first, *cls_n;            // [NCLS] position / length of each class inside t_jobids
@@ -543,7 +552,7 @@ struct ExpandDev {
     const unsigned char *auto_max;           // [NP] or nullptr
     double factor;
     // destination (K candidates)
-    int *phase_i, *phase_comp, *comp_i, *atom_t, *job_pb, *job_spec, *jobids, *pmodel;
+    int *phase_i, *phase_comp, *comp_i, *atom_t, *job_pb, *job_spec, *jobids, *pmodel, *comp_class;
     long long *job_out;
     double *phase_d, *matrices, *comp_d, *atom_d, *frac, *scales, *bg, *pparam;
 };
@@ -561,6 +570,7 @@ __global__ void __launch_bounds__(128) k_expand_population(ExpandDev e) {
     for (long long i = t; i < e.NM; i += nt) e.matrices[(size_t)k * e.NM + i] = e.t_matrices[i];
     for (int i = t; i < e.NC * 8; i += nt) e.comp_d[(size_t)k * e.NC * 8 + i] = e.t_comp_d[i];
     for (int i = t; i < e.NC * 4; i += nt) e.comp_i[(size_t)k * e.NC * 4 + i] = e.t_comp_i[i] + ((i & 3) == 0 ? k * e.NA : 0);
+    for (int i = t; i < e.NC; i += nt) e.comp_class[(size_t)k * e.NC + i] = e.t_comp_class[i];
     for (int i = t; i < e.NA * 2; i += nt) e.atom_d[(size_t)k * e.NA * 2 + i] = e.t_atom_d[i];
     for (int i = t; i < e.NA; i += nt) e.atom_t[(size_t)k * e.NA + i] = e.t_atom_t[i];
     for (int i = t; i < e.M; i += nt) e.frac[(size_t)k * e.M + i] = e.t_frac[i];
@@ -755,11 +765,39 @@ __global__ void k_component_z(BatchDev bt) {
         const double z0 = bt.atom_d[(cc[0] + a) * 2 + 1];
         const double z = (a < cc[1]) ? z0 : __dadd_rn(lattice_d, __dmul_rn(zf, z0 - lattice_d));
         bt.atom_z[cc[0] + a] = z;
-        if (a == 0 || z != prev) ++plane;       // consecutive atoms at one z share a plane
+        if (a == 0 || a == cc[1] || z != prev) ++plane;       // consecutive atoms of one group at one z share a plane
+        if (a == cc[1]) bt.comp_ilplane[ci] = plane;
         bt.atom_plane[cc[0] + a] = plane;
         prev = z;
     }
     bt.comp_nplanes[ci] = plane + 1;
+    if (cc[2] == 0) bt.comp_ilplane[ci] = plane + 1;
+}
+
+// layer table of class blockIdx.y at point gx: (sum over the planes of the layer) (sum_a asf_a pn_a) exp(i (2 pi z) stl),
+// the arithmetic the phase kernels apply per plane (plane_term)
+__global__ void __launch_bounds__(128) k_layer_table(StaticDev st, BatchDev bt) {
+    const long long gx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cls = blockIdx.y;
+    if (gx >= st.sumX) return;
+    const int ci = bt.class_rep[cls];
+    const int a0 = bt.comp_i[ci * 4], nl = bt.comp_i[ci * 4 + 1];
+    const double stl = st.stl[gx];
+    double sr = 0.0, si = 0.0;
+    int a = 0;
+    while (a < nl) {
+        const double z = bt.atom_d[(a0 + a) * 2 + 1];
+        double f = 0.0;
+        for (; a < nl && bt.atom_d[(a0 + a) * 2 + 1] == z; ++a) {
+            const int t = bt.atom_type[a0 + a];
+            if (t >= 0) f = fma(__ldg(st.asf + (long long)t * st.sumX + gx), bt.atom_d[(a0 + a) * 2], f);
+        }
+        double sn, cs;
+        px_sincos(__dmul_rn(__dmul_rn(PX_TWO_PI, z), stl), sn, cs);
+        sr = fma(f, cs, sr);
+        si = fma(f, sn, si);
+    }
+    bt.layer_tab[(long long)cls * st.sumX + gx] = make_double2(sr, si);
 }
 
 #define PX_MAX_ATOMS 256     // atoms per phase (all components)
@@ -779,17 +817,18 @@ __global__ void __launch_bounds__(32) k_phase_planes(BatchDev bt) {
     for (int c = 0; c < G; ++c) {
         const int ci = bt.phase_comp[pi[5] + c];
         const int a0 = bt.comp_i[ci * 4], na = bt.comp_i[ci * 4 + 1] + bt.comp_i[ci * 4 + 2];
+        const int skip = bt.comp_class[ci] >= 0 ? bt.comp_ilplane[ci] : 0;    // tabulated layer: interlayer planes only
         for (int a = lane; a < na; a += 32) {
             const int pl = bt.atom_plane[a0 + a];
-            if (a == 0 || bt.atom_plane[a0 + a - 1] != pl) {
+            if (pl >= skip && (a == 0 || bt.atom_plane[a0 + a - 1] != pl)) {
                 int e = a + 1;
                 while (e < na && bt.atom_plane[a0 + e] == pl) ++e;
-                seg_z[nseg + pl] = bt.atom_z[a0 + a];
-                seg_info[nseg + pl] = (first_atom + a) | ((first_atom + e) << 9) | (c << 18);
+                seg_z[nseg + pl - skip] = bt.atom_z[a0 + a];
+                seg_info[nseg + pl - skip] = (first_atom + a) | ((first_atom + e) << 9) | (c << 18);
             }
         }
         first_atom += na;
-        nseg += bt.comp_nplanes[ci];
+        nseg += bt.comp_nplanes[ci] - skip;
     }
     __syncwarp();
     for (int j = lane; j < nseg; j += 32) {            // first segment at the same z
@@ -839,6 +878,8 @@ __global__ void k_leaf_csds(const double *pd, int nmin, int nmax, double *arr, d
 struct PhaseSmem {          // header living at the start of dynamic shared memory
     int comp_first[8];      // first plane (local index) of component c
     int comp_count[8];      // number of planes of component c
+    int comp_a0[8];         // first atom (local index) of the first listed plane of component c
+    long long comp_tab[8];  // offset of the component's layer class inside the layer table, -1: no table (all planes listed)
     double comp_d001[8];
     double comp_delta[8];
     double plane_arg[PX_MAX_ATOMS];  // (2 pi) * z of a plane = run of consecutive atoms with equal z
@@ -904,22 +945,27 @@ __device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int
     int first_atom = 0, first_plane = 0;
     for (int c = 0; c < G; ++c) {
         const int ci = bt.phase_comp[pi[5] + c];
-        const int a0 = bt.comp_i[ci * 4], na = bt.comp_i[ci * 4 + 1] + bt.comp_i[ci * 4 + 2];
-        const int np = bt.comp_nplanes[ci];
+        const int a0 = bt.comp_i[ci * 4], nl = bt.comp_i[ci * 4 + 1], na = nl + bt.comp_i[ci * 4 + 2];
+        const int cls = bt.comp_class[ci];
+        const int skip = cls >= 0 ? bt.comp_ilplane[ci] : 0;       // planes of a tabulated layer are not listed
+        const int np = bt.comp_nplanes[ci] - skip;
         if (threadIdx.x == 0) {
             ps->comp_first[c] = first_plane;
             ps->comp_count[c] = np;
+            ps->comp_a0[c] = first_atom + (cls >= 0 ? nl : 0);
+            ps->comp_tab[c] = cls >= 0 ? (long long)cls * sumX : -1LL;
             ps->comp_d001[c] = bt.comp_d[ci * 8 + 0];
             ps->comp_delta[c] = bt.comp_d[ci * 8 + 2];
         }
         for (int a = threadIdx.x; a < na; a += blockDim.x) {
             const int l = first_atom + a;
-            const int pl = bt.atom_plane[a0 + a];
+            const int pl = bt.atom_plane[a0 + a] - skip;
             const int t = bt.atom_type[a0 + a];         // None atom type -> contributes 0 (atoms.py:65-67)
             ps->atom_po[l] = make_double2(t >= 0 ? bt.atom_d[(a0 + a) * 2] : 0.0, __longlong_as_double(t >= 0 ? t * sumX : 0LL));
-            if (a == 0 || bt.atom_plane[a0 + a - 1] != pl)
+            if (pl < 0) continue;
+            if (a == 0 || bt.atom_plane[a0 + a - 1] - skip != pl)
                 ps->plane_arg[first_plane + pl] = __dmul_rn(PX_TWO_PI, bt.atom_z[a0 + a]);     // 2 * pi * atom.z
-            if (a == na - 1 || bt.atom_plane[a0 + a + 1] != pl) ps->plane_end[first_plane + pl] = l + 1;
+            if (a == na - 1 || bt.atom_plane[a0 + a + 1] - skip != pl) ps->plane_end[first_plane + pl] = l + 1;
         }
         first_atom += na;
         first_plane += np;
@@ -970,10 +1016,16 @@ __device__ __forceinline__ void phase_factor(double stl, double d001, double del
 // structure factor SF_c and phase factor phi_c of component c at one point
 // (atoms.py:40-67, components.py:18-54)
 __device__ __forceinline__ void component_factors(const PhaseSmem *ps, int c, double stl, const double *__restrict__ asf_col,
-                                                  long long sumX, double &ur, double &ui, double &pr, double &pi_) {
+                                                  const double2 *__restrict__ tab_col, long long sumX, double &ur, double &ui,
+                                                  double &pr, double &pi_) {
     double sr = 0.0, si = 0.0;
+    if (ps->comp_tab[c] >= 0) {                          // block-uniform: the tabulated layer stack
+        const double2 t = __ldg(tab_col + ps->comp_tab[c]);
+        sr = t.x;
+        si = t.y;
+    }
     const int p0 = ps->comp_first[c], p1 = p0 + ps->comp_count[c];
-    int a = (p0 == 0) ? 0 : ps->plane_end[p0 - 1];
+    int a = ps->comp_a0[c];
     for (int p = p0; p < p1; ++p) {
         const int end = ps->plane_end[p];
         double f = 0.0;
@@ -1024,13 +1076,20 @@ __device__ __forceinline__ void px_sincos_n(const double (&a)[N], double (&s)[N]
 // (same arithmetic per point as component_factors)
 template <int N>
 __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, const double (&stl)[N],
-                                                    const double *__restrict__ asf_col, int stride,
-                                                    double (&ur)[N], double (&ui)[N], double (&pr)[N], double (&pim)[N]) {
+                                                    const double *__restrict__ asf_col, const double2 *__restrict__ tab_col,
+                                                    int stride, double (&ur)[N], double (&ui)[N], double (&pr)[N],
+                                                    double (&pim)[N]) {
     double sr[N], si[N];
+    if (ps->comp_tab[c] >= 0) {                          // block-uniform: the tabulated layer stack
+        const double2 *tc = tab_col + ps->comp_tab[c];
 #pragma unroll
-    for (int k = 0; k < N; ++k) { sr[k] = 0.0; si[k] = 0.0; }
+        for (int k = 0; k < N; ++k) { const double2 t = __ldg(tc + k * stride); sr[k] = t.x; si[k] = t.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) { sr[k] = 0.0; si[k] = 0.0; }
+    }
     const int p0 = ps->comp_first[c], p1 = p0 + ps->comp_count[c];
-    int a = (p0 == 0) ? 0 : ps->plane_end[p0 - 1];
+    int a = ps->comp_a0[c];
     for (int p = p0; p < p1; ++p) {
         const int end = ps->plane_end[p];
         double f[N];
@@ -1074,12 +1133,19 @@ __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, 
 // DISTINCT plane of the phase (load_phase_lists<true>); per plane the arithmetic is that of component_factors_n
 template <int G, int N>
 __device__ __forceinline__ void phase_factors_n(const PhaseSmem *ps, const double (&stl)[N], const double *__restrict__ asf_col,
-                                                int stride, double (&ur)[G][N], double (&ui)[G][N], double (&pr)[G][N],
-                                                double (&pim)[G][N]) {
+                                                const double2 *__restrict__ tab_col, int stride, double (&ur)[G][N],
+                                                double (&ui)[G][N], double (&pr)[G][N], double (&pim)[G][N]) {
 #pragma unroll
-    for (int c = 0; c < G; ++c)
+    for (int c = 0; c < G; ++c) {
+        if (ps->comp_tab[c] >= 0) {                      // block-uniform: the tabulated layer stack of the component
+            const double2 *tc = tab_col + ps->comp_tab[c];
 #pragma unroll
-        for (int k = 0; k < N; ++k) { ur[c][k] = 0.0; ui[c][k] = 0.0; }
+            for (int k = 0; k < N; ++k) { const double2 t = __ldg(tc + k * stride); ur[c][k] = t.x; ui[c][k] = t.y; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) { ur[c][k] = 0.0; ui[c][k] = 0.0; }
+        }
+    }
     const int nu = ps->n_u;
     int sg = 0;
     for (int u = 0; u < nu; ++u) {
@@ -1214,10 +1280,10 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     for (int k = 0; k < PPT; ++k) stl[k] = st.stl[gx + k * TPB];
 
     double ur[G][PPT], ui[G][PPT], pr[G][PPT], pim[G][PPT], gr[G][PPT], gi[G][PPT];
-    if constexpr (DISTINCT) phase_factors_n<G, PPT>(ps, stl, st.asf + gx, TPB, ur, ui, pr, pim);
+    if constexpr (DISTINCT) phase_factors_n<G, PPT>(ps, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur, ui, pr, pim);
 #pragma unroll
     for (int c = 0; c < G; ++c) {
-        if constexpr (!DISTINCT) component_factors_n<PPT>(ps, c, stl, st.asf + gx, TPB, ur[c], ui[c], pr[c], pim[c]);
+        if constexpr (!DISTINCT) component_factors_n<PPT>(ps, c, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur[c], ui[c], pr[c], pim[c]);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             gr[c][k] = pr[c][k] * ur[c][k] + pim[c][k] * ui[c][k];          // g = phi * conj(u)
@@ -1519,7 +1585,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_staged(StaticDev st, BatchDev 
     double ur[G], ui[G], pr[G], pim[G], gr[G], gi[G];
 #pragma unroll
     for (int c = 0; c < G; ++c) {
-        component_factors(ps, c, stl, st.asf + gx, st.sumX, ur[c], ui[c], pr[c], pim[c]);
+        component_factors(ps, c, stl, st.asf + gx, bt.layer_tab + gx, st.sumX, ur[c], ui[c], pr[c], pim[c]);
         gr[c] = pr[c] * ur[c] + pim[c] * ui[c];
         gi[c] = pim[c] * ur[c] - pr[c] * ui[c];
     }
@@ -1674,7 +1740,7 @@ __global__ void __launch_bounds__(PX_TPB) k_phase_mma(StaticDev st, BatchDev bt,
 #pragma unroll
     for (int c = 0; c < G; ++c) {
         double a, b, f, g;
-        component_factors(ps, c, stl, st.asf + gx, st.sumX, a, b, f, g);
+        component_factors(ps, c, stl, st.asf + gx, bt.layer_tab + gx, st.sumX, a, b, f, g);
         sU[c * PX_TPB + threadIdx.x] = make_double2(a, b);
         sF[c * PX_TPB + threadIdx.x] = make_double2(f, g);
     }
@@ -1875,7 +1941,7 @@ __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, Batc
     const double stl = st.stl[gx];
     for (int c = 0; c < G; ++c) {
         double a, b, p, q;
-        component_factors(ps, c, stl, st.asf + gx, st.sumX, a, b, p, q);
+        component_factors(ps, c, stl, st.asf + gx, bt.layer_tab + gx, st.sumX, a, b, p, q);
         vu[c * PX_GEN_TPB + t] = make_double2(a, b);
         vp[c * PX_GEN_TPB + t] = make_double2(p, q);
     }

@@ -111,6 +111,7 @@ struct pyxrd_ctx {
     // measurement / experiment options, set explicitly through pyxrd_set_option (nothing is read from the environment)
     bool use_structure = true;   // "use_structure" 0: ignore the transition structure of P
     bool series_mma = true;      // "series_mma" 0: CUDA-core series kernels for the ranks that have a DMMA kernel
+    bool use_layer_tables = true;   // "layer_tables" 0: every layer stack is evaluated inside the phase kernels
     int opt_tpb = 0;             // "optimizer_threads" 128 / 256: block size of k_mixture_optimize (0: by population size)
     int host_chunks = 0;         // "host_chunks" n: candidate chunks of pyxrd_evaluate_host (0: by population size)
     double opt_delta0 = 1e-2, opt_shrink = 0.5, opt_delta_min = 1e-7;   // weight-floor schedule of the optimiser
@@ -136,6 +137,7 @@ struct pyxrd_ctx {
     PinBuf h_tmpl;
     const int *jobids_dev = nullptr;   // inside d_blob
     DevBuf d_ph_nu, d_ph_uz, d_ph_uend, d_ph_useg, d_partial;
+    DevBuf d_comp_ilp, d_layer_tab;
     DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_phase_valid, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
     int residual_method = PYXRD_RESIDUAL_RP;   // settings.RESIDUAL_METHOD (mixture.py:22-27,89)
     DevBuf d_selpos, d_selcount;
@@ -167,6 +169,7 @@ struct pyxrd_ctx {
         long long NJ = 0;
         size_t njobids = 0;
         int M = 0;
+        int n_layer_classes = 0;
         bool model_driven = false;
     } pop;
 };
@@ -398,7 +401,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob, &ctx->d_tmpl,
                       &ctx->d_partial, &ctx->d_ph_nu, &ctx->d_ph_uz, &ctx->d_ph_uend, &ctx->d_ph_useg, &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
-                      &ctx->d_res, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_leaf_d, &ctx->d_sol, &ctx->d_optres};
+                      &ctx->d_res, &ctx->d_comp_ilp, &ctx->d_layer_tab, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_leaf_d, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
     ctx->h_tmpl.release();
@@ -437,6 +440,7 @@ int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value) {
     if (key == "use_structure") ctx->use_structure = value != 0.0;
     else if (key == "series_mma") ctx->series_mma = value != 0.0;
     else if (key == "overlap_classes") ctx->overlap_classes = value != 0.0;
+    else if (key == "layer_tables") ctx->use_layer_tables = value != 0.0;
     else if (key == "optimizer_threads") {
         if (value != 0.0 && value != 128.0 && value != 256.0) return fail(ctx, "set_option: optimizer_threads is 0, 128 or 256");
         ctx->opt_tpb = (int)value;
@@ -565,7 +569,10 @@ namespace {
 
 // parts of the batch blob (one device allocation, identical layout for uploaded and device-expanded batches)
 enum { P_PHASE_I, P_PHASE_D, P_PHASE_COMP, P_MATRICES, P_COMP_D, P_COMP_I, P_ATOM_D, P_ATOM_T, P_JOB_PB, P_JOB_SPEC,
-       P_JOB_OUT, P_JOBIDS, P_FRAC, P_SCALES, P_BG, P_PMODEL, P_PPARAM, P_COUNT };
+       P_JOB_OUT, P_JOBIDS, P_FRAC, P_SCALES, P_BG, P_PMODEL, P_PPARAM, P_COMP_CLASS, P_CLASS_REP, P_COUNT };
+
+#define PX_MAX_LAYER_CLASSES 64
+#define PX_MIN_CLASS_MEMBERS 3     // a layer stack is tabulated when at least this many components of the batch share it
 
 struct BatchSizes {
     int K = 0, M = 0, NP = 0, NC = 0, NA = 0, NPC = 0;
@@ -573,6 +580,7 @@ struct BatchSizes {
     long long NJ = 0;
     size_t njobids = 0;
     bool model_driven = false;
+    int n_classes = 0;
 };
 
 struct BlobLayout {
@@ -587,7 +595,8 @@ BlobLayout plan_blob(const BatchSizes &z, int S) {
         sizeof(int32_t) * (size_t)z.NC * PYXRD_COMP_I_STRIDE, sizeof(double) * (size_t)z.NA * PYXRD_ATOM_D_STRIDE,
         sizeof(int32_t) * (size_t)z.NA, sizeof(int) * (size_t)z.NJ, sizeof(int) * (size_t)z.NJ, sizeof(long long) * (size_t)z.NJ,
         sizeof(int) * z.njobids, sizeof(double) * (size_t)z.K * z.M, sizeof(double) * (size_t)z.K * S, sizeof(double) * (size_t)z.K * S,
-        z.model_driven ? sizeof(int32_t) * (size_t)z.NP : 0, z.model_driven ? sizeof(double) * (size_t)z.NP * PYXRD_PROB_STRIDE : 0};
+        z.model_driven ? sizeof(int32_t) * (size_t)z.NP : 0, z.model_driven ? sizeof(double) * (size_t)z.NP * PYXRD_PROB_STRIDE : 0,
+        sizeof(int32_t) * (size_t)z.NC, sizeof(int32_t) * PX_MAX_LAYER_CLASSES};
     for (int i = 0; i < P_COUNT; ++i) {
         L.off[i] = L.total;
         L.bytes[i] = bytes[i];
@@ -637,6 +646,47 @@ int validate_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, int *ncap_out, int
     *ncap_out = ncap;
     *acap_out = acap;
     return 0;
+}
+
+// Layer classes of the components of a descriptor: components whose layer rows (atom type, content, position of every
+// layer atom, in packed order) are identical share a class.  `bound`: components a refinable drives (population
+// templates) never join a class; `weight`: how many components of the final batch every listed component stands for.
+// Classes with fewer than PX_MIN_CLASS_MEMBERS members (or beyond PX_MAX_LAYER_CLASSES) are dissolved (-1): their layers
+// are evaluated inside the phase kernels.  -> comp_class[NC], class_rep[n_classes]
+int layer_classes(const pyxrd_batch_desc *d, const std::vector<char> *bound, int weight, std::vector<int32_t> &comp_class,
+                  std::vector<int32_t> &class_rep) {
+    const int NC = d->n_components;
+    comp_class.assign((size_t)std::max(NC, 1), -1);
+    class_rep.clear();
+    std::map<std::string, int> seen;
+    std::vector<int> members;
+    std::string key;
+    for (int c = 0; c < NC; ++c) {
+        if (bound && (*bound)[c]) continue;
+        const int32_t *ci = d->comp_i + (size_t)c * PYXRD_COMP_I_STRIDE;
+        const int a0 = ci[0], nl = ci[1];
+        if (nl <= 0 || a0 < 0 || a0 + nl > d->n_atoms) continue;
+        key.assign(reinterpret_cast<const char *>(d->atom_d + (size_t)a0 * PYXRD_ATOM_D_STRIDE), sizeof(double) * PYXRD_ATOM_D_STRIDE * nl);
+        key.append(reinterpret_cast<const char *>(d->atom_type + a0), sizeof(int32_t) * nl);
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            if ((int)class_rep.size() >= PX_MAX_LAYER_CLASSES) continue;
+            it = seen.emplace(key, (int)class_rep.size()).first;
+            class_rep.push_back(c);
+            members.push_back(0);
+        }
+        comp_class[c] = it->second;
+        members[it->second] += weight;
+    }
+    // dissolve small classes, renumber the rest
+    std::vector<int> renumber(class_rep.size(), -1);
+    std::vector<int32_t> kept;
+    for (size_t i = 0; i < class_rep.size(); ++i)
+        if (members[i] >= PX_MIN_CLASS_MEMBERS) { renumber[i] = (int)kept.size(); kept.push_back(class_rep[i]); }
+    for (int c = 0; c < NC; ++c)
+        if (comp_class[c] >= 0) comp_class[c] = renumber[comp_class[c]];
+    class_rep.swap(kept);
+    return (int)class_rep.size();
 }
 
 // job tables [K][S][Z][M] of a descriptor and the job lists per (rank, G) class, heavy classes first
@@ -726,6 +776,14 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
     CK(ctx->d_atom_z.ensure(sizeof(double) * std::max(NA, 1)));
     CK(ctx->d_atom_plane.ensure(sizeof(int) * std::max(NA, 1)));
     CK(ctx->d_comp_np.ensure(sizeof(int) * std::max(NC, 1)));
+    CK(ctx->d_comp_ilp.ensure(sizeof(int) * std::max(NC, 1)));
+    {   // layer tables [n_classes][sumX] + the slack the multi-point threads of k_phase_small read past the end
+        const size_t bytes = sizeof(double2) * ((size_t)std::max(z.n_classes, 1) * (size_t)st.sumX + PX_TABLE_PAD);
+        if (bytes > ctx->d_layer_tab.cap) {
+            CK(ctx->d_layer_tab.ensure(bytes));
+            CK(cudaMemsetAsync(ctx->d_layer_tab.ptr, 0, ctx->d_layer_tab.cap, ctx->stream));
+        }
+    }
     CK(ctx->d_phase_x.ensure(sizeof(double) * 4 * std::max(NP, 1)));
     CK(ctx->d_phase_valid.ensure(sizeof(int) * std::max(NP, 1)));
     CK(ctx->d_coef.ensure(sizeof(double) * (size_t)ncap * std::max(NP, 1)));
@@ -759,6 +817,11 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
     bt.atom_z = ctx->d_atom_z.as<double>();
     bt.atom_plane = ctx->d_atom_plane.as<int>();
     bt.comp_nplanes = ctx->d_comp_np.as<int>();
+    bt.comp_ilplane = ctx->d_comp_ilp.as<int>();
+    bt.comp_class = reinterpret_cast<const int *>(dev(P_COMP_CLASS));
+    bt.class_rep = reinterpret_cast<const int *>(dev(P_CLASS_REP));
+    bt.n_classes = z.n_classes;
+    bt.layer_tab = ctx->d_layer_tab.as<double2>();
     bt.phase_x = ctx->d_phase_x.as<double>();
     bt.coef = ctx->d_coef.as<double>();
     bt.prob_model = z.model_driven ? reinterpret_cast<const int *>(dev(P_PMODEL)) : nullptr;
@@ -800,6 +863,11 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
         k_component_z<<<(NC + 63) / 64, 64, 0, ctx->stream>>>(bt);
         LAUNCH_CHECK("k_component_z");
     }
+    if (z.n_classes > 0 && st.sumX > 0) {
+        dim3 grid((unsigned)((st.sumX + 127) / 128), (unsigned)z.n_classes);
+        k_layer_table<<<grid, 128, 0, ctx->stream>>>(st, bt);
+        LAUNCH_CHECK("k_layer_table");
+    }
     if (NP > 0) {
         k_phase_planes<<<NP, 32, 0, ctx->stream>>>(bt);
         LAUNCH_CHECK("k_phase_planes");
@@ -836,11 +904,15 @@ int pyxrd_set_batch(pyxrd_ctx *ctx, const pyxrd_batch_desc *d) {
     z.K = d->n_candidates; z.M = d->n_phase_slots; z.NP = d->n_phases; z.NC = d->n_components; z.NA = d->n_atoms;
     z.NPC = d->n_phase_comp; z.NM = d->n_matrix; z.NJ = (long long)job_pb.size(); z.njobids = jobids.size();
     z.model_driven = d->prob_model && d->prob_params;
+    std::vector<int32_t> comp_class, class_rep;
+    z.n_classes = layer_classes(d, nullptr, ctx->use_layer_tables ? 1 : 0, comp_class, class_rep);
+    class_rep.resize(PX_MAX_LAYER_CLASSES, 0);
     const BlobLayout L = plan_blob(z, st.S);
     // ---- one pinned blob, one H2D copy ---------------------------------------------------
     const void *src[P_COUNT] = {d->phase_i, d->phase_d, d->phase_comp, d->matrices, d->comp_d, d->comp_i, d->atom_d, d->atom_type,
                                 job_pb.data(), job_spec.data(), job_out.data(), jobids.data(), d->fractions, d->scales, d->bgshifts,
-                                z.model_driven ? d->prob_model : nullptr, z.model_driven ? d->prob_params : nullptr};
+                                z.model_driven ? d->prob_model : nullptr, z.model_driven ? d->prob_params : nullptr,
+                                comp_class.data(), class_rep.data()};
     CK(cudaStreamSynchronize(ctx->stream));        // the pinned blob may still feed a previous copy
     CK(ctx->h_blob.ensure(L.total));
     CK(ctx->d_blob.ensure(L.total));
@@ -1539,8 +1611,24 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     }
     if (population_caps(ctx, pop->x, K, D, &ncap)) return 1;
     const int NCLS = (int)ctx->classes.size();
+    // layer classes of the template's components; a component whose layer atoms a refinable drives keeps its layer
+    // inside the phase kernels.  Every template component stands for K components of the population.
+    std::vector<char> bound_comp((size_t)std::max(NC, 1), 0);
+    for (int b = 0; b < NB; ++b) {
+        const pyxrd_binding &bd = pop->bindings[b];
+        if (bd.target != PYXRD_BIND_ATOM_D) continue;
+        const int atom = bd.index / PYXRD_ATOM_D_STRIDE;
+        for (int c = 0; c < NC; ++c) {
+            const int32_t *ci = t->comp_i + (size_t)c * PYXRD_COMP_I_STRIDE;
+            if (atom >= ci[0] && atom < ci[0] + ci[1]) bound_comp[c] = 1;
+        }
+    }
+    std::vector<int32_t> comp_class, class_rep;
+    const int n_layer_classes = layer_classes(t, &bound_comp, ctx->use_layer_tables ? K : 0, comp_class, class_rep);
+    class_rep.resize(PX_MAX_LAYER_CLASSES, 0);
 
     BatchSizes z;
+    z.n_classes = n_layer_classes;
     z.K = K; z.M = M; z.NP = NP * K; z.NC = NC * K; z.NA = NA * K; z.NPC = NPC * K; z.NM = NM * K;
     z.NJ = (long long)JPC * K; z.njobids = jobids.size() * (size_t)K; z.model_driven = model_driven;
     if (z.NJ > 0x7fffffffLL) return fail(ctx, "set_batch: too many patterns (%lld)", z.NJ);
@@ -1573,6 +1661,8 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     const int a_bg = add(t->bgshifts, sizeof(double) * (size_t)S);
     const int a_pmodel = add(model_driven ? t->prob_model : nullptr, sizeof(int32_t) * (size_t)NP);
     const int a_pparam = add(model_driven ? t->prob_params : nullptr, sizeof(double) * (size_t)NP * PYXRD_PROB_STRIDE);
+    const int a_comp_class = add(comp_class.data(), sizeof(int32_t) * (size_t)NC);
+    const int a_class_rep = add(class_rep.data(), sizeof(int32_t) * PX_MAX_LAYER_CLASSES);
     const int a_cls_first = add(cls_first.data(), sizeof(int) * (size_t)NCLS);
     const int a_cls_n = add(cls_n.data(), sizeof(int) * (size_t)NCLS);
     const int a_x = add(pop->x, sizeof(double) * (size_t)K * D);
@@ -1596,6 +1686,8 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     e.t_job_spec = (const int *)tp(a_job_spec); e.t_job_out = (const long long *)tp(a_job_out); e.t_jobids = (const int *)tp(a_jobids);
     e.t_frac = (const double *)tp(a_frac); e.t_scales = (const double *)tp(a_scales); e.t_bg = (const double *)tp(a_bg);
     e.t_pmodel = (const int *)tp(a_pmodel); e.t_pparam = (const double *)tp(a_pparam);
+    e.t_comp_class = (const int *)tp(a_comp_class);
+    e.comp_class = (int *)dp(P_COMP_CLASS);
     e.cls_first = (const int *)tp(a_cls_first); e.cls_n = (const int *)tp(a_cls_n);
     e.x = (const double *)tp(a_x); e.bind = (const pyxrd_binding *)tp(a_bind);
     e.auto_max = pop->csds_auto_maximum ? (const unsigned char *)tp(a_auto) : nullptr;
@@ -1605,9 +1697,12 @@ int pyxrd_set_population(pyxrd_ctx *ctx, const pyxrd_batch_desc *t, const pyxrd_
     e.atom_d = (double *)dp(P_ATOM_D); e.atom_t = (int *)dp(P_ATOM_T); e.job_pb = (int *)dp(P_JOB_PB); e.job_spec = (int *)dp(P_JOB_SPEC);
     e.job_out = (long long *)dp(P_JOB_OUT); e.jobids = (int *)dp(P_JOBIDS); e.frac = (double *)dp(P_FRAC); e.scales = (double *)dp(P_SCALES);
     e.bg = (double *)dp(P_BG); e.pmodel = model_driven ? (int *)dp(P_PMODEL) : nullptr; e.pparam = model_driven ? (double *)dp(P_PPARAM) : nullptr;
+    // the class representatives are components of candidate 0 (= the template's own indices)
+    CK(cudaMemcpyAsync(dp(P_CLASS_REP), tp(a_class_rep), sizeof(int32_t) * PX_MAX_LAYER_CLASSES, cudaMemcpyDeviceToDevice, ctx->stream));
     k_expand_population<<<K, 128, 0, ctx->stream>>>(e);
     LAUNCH_CHECK("k_expand_population");
     if (bind_batch(ctx, z, L, ncap, acap)) return 1;
+    pp.n_layer_classes = n_layer_classes;
     pp.e = e;
     pp.x_off = parts[a_x].off;
     pp.NJ = z.NJ;
@@ -1644,7 +1739,7 @@ int pyxrd_update_population(pyxrd_ctx *ctx, const double *x) {
     }
     BatchSizes z;
     z.K = K; z.M = pp.M; z.NP = e.NP * K; z.NC = e.NC * K; z.NA = e.NA * K; z.NPC = e.NPC * K; z.NM = e.NM * K;
-    z.NJ = pp.NJ; z.njobids = pp.njobids; z.model_driven = pp.model_driven;
+    z.NJ = pp.NJ; z.njobids = pp.njobids; z.model_driven = pp.model_driven; z.n_classes = pp.n_layer_classes;
     const BlobLayout L = plan_blob(z, ctx->st.S);
     k_expand_population<<<K, 128, 0, ctx->stream>>>(e);
     LAUNCH_CHECK("k_expand_population");

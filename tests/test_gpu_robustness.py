@@ -192,3 +192,45 @@ def test_candidates_with_other_observations_are_refused(calc):
     mixes[1].specimens[0].selected_range = sel
     with pytest.raises(ValueError):
         pack_population(mixes)
+
+
+def test_layer_tables_on_and_off_agree(calc):
+    """candidate-invariant layer stacks (components.py:15-16 only moves interlayer atoms) come from a table computed once
+    per batch; switched off ("layer_tables" 0) every layer is evaluated inside the phase kernels.  Both against the oracle
+    at 1e-9, against each other at 1e-12; a population whose refinable drives a LAYER atom keeps that component out of
+    the table and still matches graphs rebuilt per candidate."""
+    from oracle import pyxrd_oracle_models as om
+    from pyxrd_b200.batched import population_phase_intensities
+    from pyxrd_b200.population import PopulationTemplate, Refinable
+    from pyxrd_b200.runtime import default_context
+    ctx = default_context()
+    mixes = [_observed(syn.CONFIGS["c4"].candidate(2024, i)) for i in range(4)]
+    got = {}
+    for flag in (1, 0):
+        ctx.set_option("layer_tables", flag)
+        try:
+            got[flag] = population_phase_intensities([copy.deepcopy(m) for m in mixes])
+        finally:
+            ctx.set_option("layer_tables", 1)
+    for k, m in enumerate(mixes):
+        ref = copy.deepcopy(m)
+        orc.calculate_mixture(ref)
+        for s, spec in enumerate(ref.specimens):
+            assert rel_err(got[1][k][s], spec.phase_intensities) < RTOL
+            assert rel_err(got[0][k][s], spec.phase_intensities) < RTOL
+            assert rel_err(got[1][k][s], got[0][k][s]) < 1e-12
+    # a refinable on the content of a LAYER atom of one component, the other components keep their tables
+    tmix, refs = syn.template("c2")
+    _observed(tmix)
+    phase = tmix.specimens[0].phases[0][0]
+    refs = list(refs) + [Refinable("illite.Fe", [(phase.components[0].layer_atoms[7], "pn")], 0.1, 0.6)]
+    tmpl = PopulationTemplate(tmix, refs)
+    x = syn.sample_solutions(refs, 9, 5)
+    res = tmpl.residuals(x)
+    pats = tmpl.phase_intensities(x)
+    for k in range(len(x)):
+        tmpl.apply(x[k], probabilities=om.probabilities)
+        ref = copy.deepcopy(tmpl.mixture)
+        orc.calculate_mixture(ref)
+        assert rel_err(pats[k][0], ref.specimens[0].phase_intensities) < RTOL
+        assert rel_err(res[k], ref.residuals) < RTOL
