@@ -41,6 +41,41 @@ __constant__ double PX_SC[19] = {
     2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
     -0.5, 1.0};
 
+// erf(Q) and exp(-Q^2) of the Lorentz-polarisation factor as piecewise degree-7 polynomials (tools/make_lpf_table.py):
+// [i / 16, (i + 1) / 16) for i < 104, one 128-byte line of 8 (erf, exp) coefficient pairs per interval, tail entry = (1, 0)
+#define PX_LPF_TABLE_DECL __device__ __align__(128) const double PX_LPF_TAB
+#include "lpf_table.inc"
+
+// exp(a), a <= 0: a = n ln 2 + r, |r| <= ln 2 / 2; Taylor polynomial of degree 13 (remainder 4e-18), 2^n into the exponent
+__constant__ double PX_EX[18] = {
+    1.4426950408889634,         // log2(e)
+    6755399441055744.0,         // 1.5 * 2^52
+    -6.93147180369123816490e-01, -1.90821492927058770002e-10,      // -ln 2 in two parts (fdlibm)
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+
+template <int N>
+__device__ __forceinline__ void px_exp_neg_n(const double (&a)[N], double (&out)[N]) {
+    double r[N], p[N];
+    int n[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double ac = fmax(a[k], -700.0);                  // the result stays a normal number
+        const double t = fma(ac, PX_EX[0], PX_EX[1]);
+        n[k] = __double2loint(t);
+        const double nf = t - PX_EX[1];
+        r[k] = fma(nf, PX_EX[2], ac);
+        r[k] = fma(nf, PX_EX[3], r[k]);
+        p[k] = PX_EX[4];
+    }
+#pragma unroll
+    for (int j = 5; j <= 17; ++j)
+#pragma unroll
+        for (int k = 0; k < N; ++k) p[k] = fma(p[k], r[k], PX_EX[j]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = __hiloint2double(__double2hiint(p[k]) + (n[k] << 20), __double2loint(p[k]));
+}
+
 // sin and cos of a (|a| < 2^30 * pi/2): Cody-Waite reduction with FMAs, 13/14-degree minimax
 // polynomials; max error 1.6 ulp / 1.8e-16 absolute (checked against long-double libm on 2e7 points).
 __device__ __forceinline__ void px_sincos(double a, double &s, double &c) {
@@ -910,10 +945,42 @@ __device__ __forceinline__ void lpf_setup(PhaseSmem *ps, double sigma_star, cons
     ps->lpf_k2 = 1.0 / Ss2;
     ps->lpf_pol = derived_s[0];
 }
+// erf(Q) and exp(-Q^2) come from the interval tables above (absolute error 1.5e-16 / 3.7e-16); the N points of a thread
+// run in lock step, neighbouring points fall into the same or the next interval (one cache line per warp and step)
+template <int N>
+__device__ __forceinline__ void lpf_point_n(const PhaseSmem *ps, const double (&st)[N], const double (&inv_st)[N],
+                                            const double (&c2t2)[N], double (&out)[N]) {
+    const double2 *row[N];
+    double s[N], e[N], g[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double Q = fmin(ps->lpf_q * inv_st[k], (double)PX_LPF_INTERVALS / PX_LPF_WIDTH_INV);
+        const int i = min(__double2int_rz(Q * PX_LPF_WIDTH_INV), PX_LPF_INTERVALS);
+        s[k] = fma(Q, 2.0 * PX_LPF_WIDTH_INV, -(double)(2 * i + 1));
+        row[k] = reinterpret_cast<const double2 *>(PX_LPF_TAB) + i * (PX_LPF_DEGREE + 1);
+        const double2 c = __ldg(row[k]);
+        e[k] = c.x;
+        g[k] = c.y;
+    }
+#pragma unroll
+    for (int j = 1; j <= PX_LPF_DEGREE; ++j)
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const double2 c = __ldg(row[k] + j);
+            e[k] = fma(e[k], s[k], c.x);
+            g[k] = fma(g[k], s[k], c.y);
+        }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double T = e[k] * ps->lpf_k1 - (2.0 * st[k]) * (1.0 - g[k]) * ps->lpf_k2;
+        out[k] = T * (1.0 + ps->lpf_pol * c2t2[k]) * inv_st[k];
+    }
+}
 __device__ __forceinline__ double lpf_point(const PhaseSmem *ps, double st, double inv_st, double c2t2) {
-    const double Q = ps->lpf_q * inv_st;
-    const double T = erf(Q) * ps->lpf_k1 - (2.0 * st) * (1.0 - exp(-(Q * Q))) * ps->lpf_k2;
-    return T * (1.0 + ps->lpf_pol * c2t2) * inv_st;
+    const double a[1] = {st}, b[1] = {inv_st}, c[1] = {c2t2};
+    double out[1];
+    lpf_point_n<1>(ps, a, b, c, out);
+    return out[0];
 }
 
 // t_only: get_T (goniometer.py:20-25) instead of the whole factor
@@ -1004,9 +1071,11 @@ __device__ __forceinline__ void phase_factor(double stl, double d001, double del
     double sn, cs;
     px_sincos(__dmul_rn(A, d001), sn, cs);
     if (delta_c != 0.0) {                                   // block-uniform branch
-        const double e = exp(__dmul_rn(A, -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl)));
-        pr = e * cs;
-        pi_ = e * sn;
+        const double arg[1] = {__dmul_rn(A, -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl))};
+        double e[1];
+        px_exp_neg_n<1>(arg, e);
+        pr = e[0] * cs;
+        pi_ = e[0] * sn;
     } else {                                                // exp(-0.0) == 1 exactly
         pr = cs;
         pi_ = sn;
@@ -1115,17 +1184,17 @@ __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, 
     for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), d001);
     px_sincos_n<N>(ang, sn, cs);
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        ur[k] = sr[k];
-        ui[k] = si[k];
-        if (delta_c != 0.0) {                               // block-uniform branch
-            const double e = exp(__dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl[k])));
-            pr[k] = e * cs[k];
-            pim[k] = e * sn[k];
-        } else {
-            pr[k] = cs[k];
-            pim[k] = sn[k];
-        }
+    for (int k = 0; k < N; ++k) { ur[k] = sr[k]; ui[k] = si[k]; }
+    if (delta_c != 0.0) {                                   // block-uniform branch
+        double arg[N], e[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) arg[k] = __dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl[k]));
+        px_exp_neg_n<N>(arg, e);
+#pragma unroll
+        for (int k = 0; k < N; ++k) { pr[k] = e[k] * cs[k]; pim[k] = e[k] * sn[k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) { pr[k] = cs[k]; pim[k] = sn[k]; }
     }
 }
 
@@ -1182,16 +1251,16 @@ __device__ __forceinline__ void phase_factors_n(const PhaseSmem *ps, const doubl
 #pragma unroll
         for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), d001);
         px_sincos_n<N>(ang, sn, cs);
+        if (delta_c != 0.0) {                               // block-uniform branch
+            double arg[N], e[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            if (delta_c != 0.0) {                           // block-uniform branch
-                const double e = exp(__dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl[k])));
-                pr[c][k] = e * cs[k];
-                pim[c][k] = e * sn[k];
-            } else {
-                pr[c][k] = cs[k];
-                pim[c][k] = sn[k];
-            }
+            for (int k = 0; k < N; ++k) arg[k] = __dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), -__dmul_rn(__dmul_rn(PX_PI, delta_c), stl[k]));
+            px_exp_neg_n<N>(arg, e);
+#pragma unroll
+            for (int k = 0; k < N; ++k) { pr[c][k] = e[k] * cs[k]; pim[c][k] = e[k] * sn[k]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) { pr[c][k] = cs[k]; pim[c][k] = sn[k]; }
         }
     }
 }
@@ -1526,9 +1595,22 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     } else {
         trace(px_int<0>{});
     }
+    // absolute scale, LPF, machine correction (phases.py:158,81-95, specimen.py:57-62); padded tables: loads past X are safe
     double out[PPT];
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) out[k] = finish_point(tr[k], abs_scale, flags, ps, st, gx + k * TPB);   // padded tables: safe past X
+    for (int k = 0; k < PPT; ++k) out[k] = tr[k] * abs_scale;
+    if (flags & 2) {
+        double sn[PPT], isn[PPT], c2[PPT], lpf[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) { sn[k] = st.sin_t[gx + k * TPB]; isn[k] = st.inv_sin[gx + k * TPB]; c2[k] = st.c2t2[gx + k * TPB]; }
+        lpf_point_n<PPT>(ps, sn, isn, c2, lpf);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) out[k] = out[k] * lpf[k];
+    }
+    if (flags & 4) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) out[k] = out[k] * st.corr[gx + k * TPB];
+    }
 #pragma unroll
     for (int k = 0; k < PPT; ++k)
         if (x + k * TPB < X) bt.intensities[bt.job_out[job] + x + k * TPB] = out[k];
