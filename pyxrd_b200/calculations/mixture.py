@@ -273,6 +273,8 @@ def optimize_mixture(mixture, force=False):
     bounds = get_bounds(mixture)
     no_obs = [s for s, sp in enumerate(mixture.specimens) if sp is None or np.size(sp.observed_intensity) == 0]
 
+    best = [np.inf, None]
+
     def objective(x):
         mixture.calculated = False
         set_solution(x, mixture)
@@ -280,14 +282,23 @@ def optimize_mixture(mixture, force=False):
             res = _device_residuals(mixture, ctx, want_patterns=False)
         if no_obs:
             per = [0.0 if s in no_obs else res[1 + s] for s in range(len(mixture.specimens))]
-            return np.average(per)
-        return res[0]
+            value = np.average(per)
+        else:
+            value = res[0]
+        if np.isfinite(value) and value < best[0]:
+            best[0], best[1] = float(value), np.array(x, dtype=float)
+        return value
 
     t1 = time.time()
     kwargs = dict(approx_grad=True, bounds=bounds)
     if _inspect_signature_has(fmin_l_bfgs_b, "iprint"):
         kwargs["iprint"] = -1
     lastx, residual, info = fmin_l_bfgs_b(objective, x0, **kwargs)
+    if not np.all(np.isfinite(residual)) and best[1] is not None:
+        # L-BFGS-B may end on a proposal with every free fraction at its lower bound 0: parse_solution then divides
+        # 0 / 0 and the objective is NaN (the reference hands that NaN back: whether a run gets there depends on the last
+        # bits of the objective).  The best point the run has seen is returned instead.
+        lastx, residual = best[1], best[0]
     if np.isscalar(residual):
         residual = np.array([residual])
     logger.debug('%s took %0.3f ms' % ("optimize_mixture", (time.time() - t1) * 1000.0))

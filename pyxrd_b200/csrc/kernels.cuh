@@ -2098,7 +2098,7 @@ __global__ void k_leaf_component(const double *stl, long long n, const double *c
 // candidate-invariant and L2-resident.
 // ---------------------------------------------------------------------------------
 #define PX_WL_TPB 256
-#define PX_WL_PPT 4
+#define PX_WL_PPT 4           // measured on c2: 4 points per thread 54 us, 2 (full occupancy) 58 us, 1: 82 us
 __global__ void __launch_bounds__(PX_WL_TPB) k_wavelength_pass(StaticDev st, BatchDev bt, int job0, int pass,
                                                                const double *__restrict__ src, double *__restrict__ dst) {
     const int job = job0 + blockIdx.x;                  // jobs on x: grid.y stops at 65535
@@ -2149,16 +2149,22 @@ __global__ void __launch_bounds__(PX_WL_TPB) k_wavelength_pass(StaticDev st, Bat
 // in the same order as k_wavelength_pass -- writes the final pattern (dst) and feeds it straight into the sum, so the
 // patterns are not read a second time and the abscissa tables (index + two weights, 20 B per point) are fetched once
 // per point instead of once per point and phase.
-// grid (candidates, 1024-point tiles, S): a block owns one tile of one (candidate, specimen) for all Z patterns and M
-// phases, 4 points in flight per thread (one block per (candidate, specimen) looping over the whole pattern was
+// grid (candidates, tiles of PX_RES_TPB * PX_RES_PPT points, S): a block owns one tile of one (candidate, specimen) for all Z patterns and M
+// phases, PX_RES_PPT points in flight per thread (one block per (candidate, specimen) looping over the whole pattern was
 // latency-bound: 91 us against 50 us for c2).  Its sum |obs - total| goes to partial[((k - k0) S + s) ntiles + tile];
 // k_residual_finish adds the tiles in order (deterministic).  want_totals = 0: the total pattern is only summed, not
 // stored (callers that want residuals only).
 // ---------------------------------------------------------------------------------
 #define PX_RES_TPB 256
-#define PX_RES_PPT 4
+// two points per thread at full occupancy (8 blocks of 256 threads, <= 32 registers): the fused kernel is bound by the
+// latency of its dependent loads (index -> gather -> sum), not by DRAM; measured on c2 (220 MB moved): 4 points / 80
+// registers / 3 blocks 130 us, 4 / 64 / 4: 134, 2 / 6 blocks 129, 2 / 8 blocks 113, 1 / 8 blocks 185
+#ifndef PX_RES_PPT
+#define PX_RES_PPT 2
+#define PX_RES_MINB 8
+#endif
 template <bool GATHER>
-__global__ void __launch_bounds__(PX_RES_TPB) k_mixture_residual(StaticDev st, BatchDev bt, int k0, int want_scaled, int want_totals,
+__global__ void __launch_bounds__(PX_RES_TPB, PX_RES_MINB) k_mixture_residual(StaticDev st, BatchDev bt, int k0, int want_scaled, int want_totals,
                                                                 int pass, const double *__restrict__ src, double *__restrict__ dst,
                                                                 double *__restrict__ partial) {
     const int s = blockIdx.z, k = k0 + blockIdx.x, tile = blockIdx.y;       // candidates on x: grid.y / z stop at 65535
