@@ -1304,7 +1304,10 @@ __host__ __device__ constexpr int px_rot(int L, int s, int R, int G) {
 //  2  every row of P is the same vector w (Reichweite 0, R0models.py:80-83): Q^n = 1 (w o phi)^T q^(n-1) with the
 //     complex SCALAR q = sum_J w_J phi_J, so the series is a scalar Horner recurrence whatever G is:
 //     sum_n c_n Q^n b = 1 * (sum_J w_J phi_J b_J) * sum_n c_n q^(n-1).
-template <int R, int G, int PPT, int TPB, int MINB, int STRUCT = 0>
+//
+// A block walks TILES consecutive tiles of TPB * PPT points of its pattern: staging the phase's parameter block (lists,
+// matrices, coefficients, LPF constants: a chain of dependent global loads) is paid once per TILES tiles.
+template <int R, int G, int PPT, int TPB, int MINB, int STRUCT = 0, int TILES = 1>
 __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDev bt, const int *__restrict__ jobs) {
     constexpr int REPS = R / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1316,8 +1319,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     const int job = jobs[blockIdx.x];
     const int pb = bt.job_pb[job], s = bt.job_spec[job];
     const int X = st.spec_npts[s];
-    const int x0 = blockIdx.y * (TPB * PPT);
-    if (x0 >= X || phase_is_invalid(bt, pb, job, X, x0, TPB * PPT)) return;
+    const int xblock = blockIdx.y * (TPB * PPT * TILES);
+    if (xblock >= X || phase_is_invalid(bt, pb, job, X, xblock, TPB * PPT * TILES)) return;
     const int *pi = bt.phase_i + pb * 8;
     const double *px = bt.phase_x + pb * 4;
     const int ntop = (int)px[2];
@@ -1341,8 +1344,10 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     }
     __syncthreads();
 
+#pragma unroll 1
+    for (int x0 = xblock; x0 < xblock + TPB * PPT * TILES; x0 += TPB * PPT) {
     const int x = x0 + threadIdx.x;
-    if (x >= X) return;
+    if (x >= X) break;
     const long long gx = st.spec_off[s] + x;
     double stl[PPT];
 #pragma unroll
@@ -1614,6 +1619,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
 #pragma unroll
     for (int k = 0; k < PPT; ++k)
         if (x + k * TPB < X) bt.intensities[bt.job_out[job] + x + k * TPB] = out[k];
+    }
 }
 
 // ---- ranks 16 / 27: w in registers, the new vector staged through shared memory ----

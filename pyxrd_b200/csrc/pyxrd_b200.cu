@@ -235,13 +235,16 @@ int set_smem(pyxrd_ctx *ctx, K kernel, size_t bytes) {
     return 0;
 }
 
-template <int R, int G, int PPT, int TPB, int MINB = 0, int STRUCT = 0>
+#ifndef PX_SMALL_TILES
+#define PX_SMALL_TILES 4     // tiles per block of the one-warp kernels (ranks 1, 2)
+#endif
+template <int R, int G, int PPT, int TPB, int MINB = 0, int STRUCT = 0, int TILES = 1>
 int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     static_assert((PPT - 1) * TPB <= PX_TABLE_PAD, "table padding too small");
     const size_t smem = small_smem(R, G, rc.max_ntop_cap);
-    if (set_smem(ctx, k_phase_small<R, G, PPT, TPB, MINB, STRUCT>, smem)) return 1;
-    dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + TPB * PPT - 1) / (TPB * PPT)));
-    k_phase_small<R, G, PPT, TPB, MINB, STRUCT><<<grid, TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
+    if (set_smem(ctx, k_phase_small<R, G, PPT, TPB, MINB, STRUCT, TILES>, smem)) return 1;
+    dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + TPB * PPT * TILES - 1) / (TPB * PPT * TILES)));
+    k_phase_small<R, G, PPT, TPB, MINB, STRUCT, TILES><<<grid, TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
     LAUNCH_CHECK("k_phase_small");
     return 0;
 }
@@ -285,11 +288,11 @@ int launch_raw(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t 
 int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     if (rc.rank == 0 && rc.G == 0) return launch_raw(ctx, rc, jobs_dev, njobs, bt);
 #define SMALL(R_, G_, PPT_, TPB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_>(ctx, rc, jobs_dev, njobs, bt)
-#define SMALLB(R_, G_, PPT_, TPB_, MINB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_, MINB_>(ctx, rc, jobs_dev, njobs, bt)
+#define SMALLB(R_, G_, PPT_, TPB_, MINB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_, MINB_, 0, PX_SMALL_TILES>(ctx, rc, jobs_dev, njobs, bt)
 #define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev, njobs, bt)
     if (rc.structure == 2 && ctx->use_structure) {
         // Reichweite 0 with G components: a scalar series whatever G is
-        if (rc.rank == 2 && rc.G == 2) return launch_small<2, 2, 4, 32, 16, 2>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 2 && rc.G == 2) return launch_small<2, 2, 4, 32, 16, 2, PX_SMALL_TILES>(ctx, rc, jobs_dev, njobs, bt);
         if (rc.rank == 3 && rc.G == 3) return launch_small<3, 3, 2, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
         if (rc.rank == 4 && rc.G == 4) return launch_small<4, 4, 2, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
         if (rc.rank == 5 && rc.G == 5) return launch_small<5, 5, 1, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
