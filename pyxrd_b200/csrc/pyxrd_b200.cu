@@ -238,6 +238,9 @@ int set_smem(pyxrd_ctx *ctx, K kernel, size_t bytes) {
 #ifndef PX_SMALL_TILES
 #define PX_SMALL_TILES 4     // tiles per block of the one-warp kernels (ranks 1, 2)
 #endif
+#ifndef PX_WIDE_TILES
+#define PX_WIDE_TILES 1      // ... of the kernels with 64 / 128 threads per block
+#endif
 template <int R, int G, int PPT, int TPB, int MINB = 0, int STRUCT = 0, int TILES = 1>
 int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     static_assert((PPT - 1) * TPB <= PX_TABLE_PAD, "table padding too small");
@@ -287,28 +290,28 @@ int launch_raw(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t 
 
 int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     if (rc.rank == 0 && rc.G == 0) return launch_raw(ctx, rc, jobs_dev, njobs, bt);
-#define SMALL(R_, G_, PPT_, TPB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_>(ctx, rc, jobs_dev, njobs, bt)
+#define SMALL(R_, G_, PPT_, TPB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_, 0, 0, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt)
 #define SMALLB(R_, G_, PPT_, TPB_, MINB_) if (rc.rank == R_ && rc.G == G_) return launch_small<R_, G_, PPT_, TPB_, MINB_, 0, PX_SMALL_TILES>(ctx, rc, jobs_dev, njobs, bt)
 #define STAGED(R_, G_) if (rc.rank == R_ && rc.G == G_) return launch_staged<R_, G_>(ctx, rc, jobs_dev, njobs, bt)
     if (rc.structure == 2 && ctx->use_structure) {
         // Reichweite 0 with G components: a scalar series whatever G is
         if (rc.rank == 2 && rc.G == 2) return launch_small<2, 2, 4, 32, 16, 2, PX_SMALL_TILES>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 3 && rc.G == 3) return launch_small<3, 3, 2, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 4 && rc.G == 4) return launch_small<4, 4, 2, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 5 && rc.G == 5) return launch_small<5, 5, 1, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 6 && rc.G == 6) return launch_small<6, 6, 1, 128, 0, 2>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 3 && rc.G == 3) return launch_small<3, 3, 2, 128, 0, 2, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 4 && rc.G == 4) return launch_small<4, 4, 2, 128, 0, 2, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 5 && rc.G == 5) return launch_small<5, 5, 1, 128, 0, 2, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 6 && rc.G == 6) return launch_small<6, 6, 1, 128, 0, 2, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
     }
     if (rc.structure == 1 && ctx->use_structure) {
         // structured transition matrices (Reichweite >= 2 models): G instead of R multiply-adds per state
         // (shapes from sweeps on B200)
-        if (rc.rank == 4 && rc.G == 2) return launch_small<4, 2, 2, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 8 && rc.G == 2) return launch_small<8, 2, 2, 64, 8, 1>(ctx, rc, jobs_dev, njobs, bt);   // 3.64 ms on c5; 1 x 128: 4.02
-        if (rc.rank == 9 && rc.G == 3) return launch_small<9, 3, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 4 && rc.G == 2) return launch_small<4, 2, 2, 128, 0, 1, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 8 && rc.G == 2) return launch_small<8, 2, 2, 64, 8, 1, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);   // 3.64 ms on c5; 1 x 128: 4.02
+        if (rc.rank == 9 && rc.G == 3) return launch_small<9, 3, 1, 128, 0, 1, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
         // larger ranks: the in-place series needs the state vector once (254 registers at rank 27); c3s 1.52 ms per 256
         // candidates, 4.07 ms with the vector staged through shared memory, 7.89 ms with the dense DMMA kernel
-        if (rc.rank == 27 && rc.G == 3) return launch_small<27, 3, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 16 && rc.G == 2) return launch_small<16, 2, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
-        if (rc.rank == 16 && rc.G == 4) return launch_small<16, 4, 1, 128, 0, 1>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 27 && rc.G == 3) return launch_small<27, 3, 1, 128, 0, 1, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 16 && rc.G == 2) return launch_small<16, 2, 1, 128, 0, 1, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
+        if (rc.rank == 16 && rc.G == 4) return launch_small<16, 4, 1, 128, 0, 1, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
     }
     // (points per thread, threads per block, min blocks per SM) from sweeps on B200 (profiles/r1_summary.md)
     SMALLB(1, 1, 4, 32, 0); SMALLB(2, 2, 4, 32, 16); SMALLB(2, 1, 4, 32, 16);

@@ -335,3 +335,78 @@ def test_table_discovered_from_the_reference_model_layer(ctx):
         for s in range(len(pis[k])):
             for m in range(pis[k][s].shape[0]):
                 assert bool(pis[k][s][m].any()) == bool(g["valid_probs"][k][s][m])
+
+
+def test_deap_shaped_generation_end_to_end():
+    """A generation of a population method, evaluated the way the reference's DEAP runs ask for it
+    (refinement/methods/deap_cma.py:345-360 ``_ask`` -> ``RefineAsyncHelper.do_async_evaluation(toolbox.generate,
+    result_func=...)``, refine_async_helper.py:16-23, async_evaluatable.py:38-50) -- through the installed hook with a
+    REAL device evaluation of a 256-row population, and through the batching provider with the default evaluator.
+    No ``deap`` needed: the hook only sees an ``iter_func`` that yields individuals."""
+    import functools
+    import pyxrd_b200.calculations as calc
+    from pyxrd_b200 import install
+    from pyxrd_b200.provider import B200AsyncServer
+    tmix, refs = syn.template("c4")
+    truth = syn.CONFIGS["c4"].truth()
+
+    def calc_total(mix):
+        calc.mixture.calculate_mixture(mix)
+        return [np.array(s.total_intensity) for s in mix.specimens]
+
+    syn.attach_observed([tmix], truth, calc_total)
+    tmpl = PopulationTemplate(tmix, refs)
+    x = syn.sample_solutions(refs, 31, 256)
+
+    class Individual(list):                       # what deap's creator.Individual is: a list with a fitness slot
+        fitness = None
+
+    class Refiner(object):
+        def __init__(self):
+            self._b200_template = tmpl             # what install._refiner_template caches after discovering the table
+            self.seen = []
+
+        def update(self, solution, residual=None):
+            self.seen.append((list(solution), residual))
+
+    class Run(object):                            # the part of RefineCMAESRun the hook touches
+        def __init__(self):
+            self.refiner = Refiner()
+
+        def _user_cancelled(self):
+            return False
+
+    def must_not_run(*args, **kwargs):            # pragma: no cover
+        raise AssertionError("the reference's per-trial loop must not run")
+
+    hook = install._generation_evaluator(must_not_run)
+    run = Run()
+    reported = []
+
+    def result_f(*args):                          # deap_cma.py:349-351
+        run.refiner.update(*args)
+        reported.append(args)
+
+    population = hook(run, lambda: (Individual(row) for row in x), result_func=result_f)
+    assert len(population) == 256 and all(isinstance(ind, Individual) for ind in population)
+    assert len(reported) == 256 and len(run.refiner.seen) == 256
+    values = np.array([float(r[1][0]) for r in reported])
+    assert all(np.shape(r[1]) == (1,) for r in reported)                  # get_optimized_residual returns a 1-element array
+    assert np.array_equal(values, tmpl.optimized_residuals(x))            # the same launch sequence, deterministic
+    # a few rows against the oracle's get_optimized_residual on graphs rebuilt per candidate (optimiser contract)
+    for k in (0, 97, 255):
+        tmpl.apply(x[k], probabilities=om.probabilities)
+        ref = copy.deepcopy(tmpl.mixture)
+        want = float(orc.get_optimized_residual(ref)[0])
+        assert values[k] <= want * (1.0 + 5e-3), (k, values[k], want)
+        assert values[k] >= want * 0.5
+    # the provider route (settings.ASYNC_SERER_PROVIDERS): submit all trials, fetch all -> one device batch
+    server = B200AsyncServer()
+    graphs = []
+    for k in range(24):
+        tmpl.apply(x[k], probabilities=om.probabilities)
+        graphs.append(copy.deepcopy(tmpl.mixture))
+    results = [server.submit(functools.partial(calc.mixture.get_optimized_residual, g)) for g in graphs]
+    fetched = np.array([float(r.get()[0]) for r in results])
+    assert np.allclose(fetched, values[:24], rtol=1e-9, atol=0.0)         # packed graphs == template expansion
+    assert all(g.optimized for g in graphs)
