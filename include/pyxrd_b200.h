@@ -211,7 +211,9 @@ int64_t pyxrd_launch_count(const pyxrd_ctx *ctx);
  * job classes one after the other), "layer_tables" (1; 0 = candidate-invariant layer stacks are evaluated inside the
  * phase kernels instead of being tabulated once per batch), "optimizer_threads" (0 = by population size; 128 | 256), "host_chunks" (0 = by
  * population size; candidate chunks of pyxrd_evaluate_host), "optimizer_delta0" (1e-2), "optimizer_shrink" (0.5),
- * "optimizer_delta_min" (1e-7): weight-floor schedule of pyxrd_optimize relative to the mean observed intensity. */
+ * "optimizer_delta_min" (1e-7): weight-floor schedule of pyxrd_optimize relative to the mean observed intensity;
+ * "optimizer_newton_tol" (1e-5): relative decrease of the majoriser below which a pass takes no further Newton iteration;
+ * "optimizer_single_from" (0 = off): pass from which one Newton iteration is taken whatever the decrease. */
 int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value);
 
 /* ---- upload -------------------------------------------------------------------- */

@@ -2483,8 +2483,9 @@ struct OptParams {
     int outer;          // majorise-minimise iterations
     int lm_iters;       // Newton / LM iterations per majoriser
     int refine_bg;      // 0: bgshifts stay at the values of the batch
-    int reserved;
+    int single_from;    // from this majoriser on ONE Newton / LM iteration per majoriser (0: lm_iters throughout)
     double delta0, shrink, delta_min;   // weight floor relative to mean |obs|: delta0 * shrink^it >= delta_min
+    double newton_tol;                  // relative decrease of the majoriser below which no further Newton iteration is taken
 };
 
 #ifndef PX_OPT_NDAMP
@@ -2507,6 +2508,7 @@ struct OptSmem {
     double A[PX_OPT_MAXD * PX_OPT_LDA];
     double g[PX_OPT_MAXD], vn[PX_OPT_MAXD], invd[PX_OPT_MAXD];
     double lam;                     // Levenberg-Marquardt damping, carried from one majoriser to the next
+    double newton_tol;              // a Newton / LM iteration that lowers the majoriser by less than this (relative) is the last
     double cand_q[PX_OPT_NDAMP];                    // majoriser value each warp's damping reaches (register solver)
     double cand_v[PX_OPT_NDAMP][PX_OPT_MAXD];       // and its trial point
 #ifdef PX_OPT_PROFILE
@@ -2691,7 +2693,7 @@ __device__ __noinline__ void opt_inner_solve(OptSmem &sm, int M, int S, int MB, 
             if (lane == 0) sm.prof[5] += clock64() - tC;
 #endif
         }
-        if (!accepted || rel < 1e-13) break;
+        if (!accepted || rel < sm.newton_tol) break;
     }
     if (lane == 0) sm.lam = fmin(lam, 1e-3);            // never start a majoriser more damped than the first one
 }
@@ -2877,7 +2879,7 @@ __device__ __noinline__ void opt_inner_solve_reg(OptSmem &sm, int lm_iters, int 
             if (lane == 0 && warp == 0) sm.prof[5] += clock64() - tC;
 #endif
         }
-        if (!accepted || rel < 1e-13) break;
+        if (!accepted || rel < sm.newton_tol) break;
     }
     if (warp == 0) {
         if (lane < D) sm.v[lane] = vi;
@@ -3041,7 +3043,7 @@ __device__ __noinline__ void opt_inner_solve_scalar(OptSmem &sm, int lm_iters, i
                 for (int i = 0; i < PX_OPT_NDAMP; ++i) lam *= 5.0;
             }
         }
-        if (!accepted || rel < 1e-13) break;
+        if (!accepted || rel < sm.newton_tol) break;
     }
     if (lane == 0) {
 #pragma unroll
@@ -3115,6 +3117,23 @@ __device__ __forceinline__ void opt_store_reduced(const double (&acc)[N], int la
     }
 }
 
+// Asynchronous prefetch ring of the Gram pass (PX_OPT_ASYNC_MINMB <= MB): every thread copies the MB + 1 values of ITS
+// point of the tiles ahead with cp.async (global -> shared without passing through registers) and later reads back
+// exactly the slots it wrote, so no block barrier is involved and the L2 latency of the pattern reads is hidden behind
+// the arithmetic of the tiles in between -- with registers only for the one point being accumulated.
+#ifndef PX_OPT_ASYNC_MINMB
+#define PX_OPT_ASYNC_MINMB 99     // measured on c4 (MB = 7): 1.39 ms against 1.01 ms for the register path: off
+#endif
+// tiles in flight: four for the one-wave blocks of 256 threads (64 KB of ring at MB = 7, two blocks per SM), two where
+// four blocks of 128 threads share an SM or the mixture has many phases
+__host__ __device__ constexpr int opt_stages(int MB, int TPB) { return (TPB == 256 && MB <= 8) ? 4 : 2; }
+__host__ __device__ constexpr int opt_ring_doubles(int MB, int TPB) { return MB >= PX_OPT_ASYNC_MINMB ? opt_stages(MB, TPB) * (MB + 1) * TPB : 0; }
+__device__ __forceinline__ void px_cp_async8(double *dst_shared, const double *src_global) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+}
+__device__ __forceinline__ void px_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void px_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int MB, int TPB>
 __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev st, BatchDev bt, OptParams op,
                                                                  double *solutions, double *opt_residuals) {
@@ -3134,6 +3153,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
 #endif
     if (tid == 0) {
         sm.lam = 1e-3;
+        sm.newton_tol = op.newton_tol;
         for (int p = 0; p < M; ++p) { sm.v[p] = 1.0 / M; sm.lo[p] = 0.0; }             // mixture.py:60-68 start
         for (int s = 0; s < S; ++s) {
             sm.v[M + s] = 1.0; sm.lo[M + s] = 1e-12;
@@ -3191,7 +3211,59 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
                     }
                 }
             };
-            if constexpr (MB <= PX_OPT_PTR_MB) {
+            if constexpr (MB >= PX_OPT_ASYNC_MINMB) {
+                extern __shared__ __align__(16) double opt_ring[];      // [stage][MB + 1][TPB]
+                constexpr int PX_OPT_STAGES = opt_stages(MB, TPB);
+                const int npts = Z * X, ntile = (npts + TPB - 1) / TPB;
+                auto issue = [&](int tile) {                            // this thread's point of `tile` into its ring slots
+                    if (tile < ntile) {
+                        int i = tile * TPB + tid;
+                        if (i >= npts) i = npts - 1;                    // a legal address; the point is masked below
+                        const int z = i / X, x = i - z * X;
+                        double *slot = opt_ring + (size_t)(tile % PX_OPT_STAGES) * (MB + 1) * TPB + tid;
+#pragma unroll
+                        for (int p = 0; p < M; ++p) px_cp_async8(slot + p * TPB, I + ((long long)p * Z + z) * X + x);
+                        px_cp_async8(slot + M * TPB, corr + x);
+                        px_cp_async8(slot + MB * TPB, obs + (long long)z * X + x);
+                    }
+                    px_cp_async_commit();                               // (possibly empty: the group count stays in step)
+                };
+#pragma unroll
+                for (int t = 0; t < PX_OPT_STAGES - 1; ++t) issue(t);
+                for (int tile = 0; tile < ntile; ++tile) {
+                    issue(tile + PX_OPT_STAGES - 1);
+                    const int i = tile * TPB + tid;
+                    const bool live = i < npts && sel[i % X] != 0;      // (the mask byte is an ordinary cached load)
+                    px_cp_async_wait<PX_OPT_STAGES - 1>();
+                    const double *slot = opt_ring + (size_t)(tile % PX_OPT_STAGES) * (MB + 1) * TPB + tid;
+                    double phi[1][MB], o[1];
+                    bool on[1] = {live};
+#pragma unroll
+                    for (int p = 0; p < MB; ++p) phi[0][p] = slot[p * TPB];
+                    o[0] = slot[MB * TPB];
+                    // (PIF of the register paths is the array extent here: one point at a time)
+                    {
+                        if (on[0]) {
+                            double calc = 0.0;
+#pragma unroll
+                            for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[0][p], calc);
+                            const double r = o[0] - calc;
+                            double w;
+                            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(w) : "d"(fmax(fabs(r), delta)));
+                            acc[NACC - 1] += fabs(r);
+                            int e = 0;
+#pragma unroll
+                            for (int p = 0; p < MB; ++p) {
+                                const double wp = w * phi[0][p];
+                                acc[NG + p] = fma(wp, o[0], acc[NG + p]);
+#pragma unroll
+                                for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[0][q], acc[e]);
+                            }
+                        }
+                    }
+                }
+                px_cp_async_wait<0>();
+            } else if constexpr (MB <= PX_OPT_PTR_MB) {
                 // few phases: the pass is bound by instruction issue, not by the fp64 pipe.  Full groups of PIF points
                 // read at constant offsets from one running pointer per array (no index arithmetic per load); the
                 // ragged end of the pattern goes through the same body with clamped offsets.
@@ -3274,7 +3346,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
 #ifdef PX_OPT_PROFILE
         long long tN = clock64();
 #endif
-        opt_solve_dispatch<M>(sm, S, op.lm_iters, op.refine_bg, tid);
+        opt_solve_dispatch<M>(sm, S, (op.single_from > 0 && it >= op.single_from) ? 1 : op.lm_iters, op.refine_bg, tid);
         __syncthreads();
 #ifdef PX_OPT_PROFILE
         if (tid == 0) sm.prof[2] += clock64() - tN;

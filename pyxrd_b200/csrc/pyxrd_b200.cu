@@ -115,6 +115,11 @@ struct pyxrd_ctx {
     int opt_tpb = 0;             // "optimizer_threads" 128 / 256: block size of k_mixture_optimize (0: by population size)
     int host_chunks = 0;         // "host_chunks" n: candidate chunks of pyxrd_evaluate_host (0: by population size)
     double opt_delta0 = 1e-2, opt_shrink = 0.5, opt_delta_min = 1e-7;   // weight-floor schedule of the optimiser
+    int opt_single_from = 0;     // "optimizer_single_from": majoriser from which ONE Newton iteration is taken (0: never)
+    // "optimizer_newton_tol": a Newton iteration that lowers the majoriser by less than this (relative) is the last of
+    // its pass.  1e-5 keeps the excess over a long run on c4 AND on the ill-conditioned c5 (four similar phases) where
+    // 1e-13 had it, 14 % / 9 % faster; 1e-4 and fixed single iterations after the first passes lose c5 (tools/opt_switch.py)
+    double opt_newton_tol = 1e-5;
 
     // static
     bool have_static = false;
@@ -343,12 +348,17 @@ static int launch_optimize(pyxrd_ctx *ctx, const OptParams &op) {
     // one wave of 256-thread blocks (2 per SM) when the population fits it, else 128-thread blocks (4 per SM)
     int tpb = ctx->bt.K <= 2 * ctx->sm_count ? 256 : 128;
     if (ctx->opt_tpb) tpb = ctx->opt_tpb;
-    if (tpb == 256)
-        k_mixture_optimize<MB, 256><<<ctx->bt.K, 256, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
-                                                                        ctx->d_optres.as<double>());
-    else
-        k_mixture_optimize<MB, 128><<<ctx->bt.K, 128, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
-                                                                        ctx->d_optres.as<double>());
+    if (tpb == 256) {
+        const size_t ring = sizeof(double) * opt_ring_doubles(MB, 256);
+        if (ring) CK(cudaFuncSetAttribute(k_mixture_optimize<MB, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
+        k_mixture_optimize<MB, 256><<<ctx->bt.K, 256, ring, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
+                                                                           ctx->d_optres.as<double>());
+    } else {
+        const size_t ring = sizeof(double) * opt_ring_doubles(MB, 128);
+        if (ring) CK(cudaFuncSetAttribute(k_mixture_optimize<MB, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
+        k_mixture_optimize<MB, 128><<<ctx->bt.K, 128, ring, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
+                                                                           ctx->d_optres.as<double>());
+    }
     LAUNCH_CHECK("k_mixture_optimize");
     return 0;
 }
@@ -450,6 +460,10 @@ int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value) {
     else if (key == "optimizer_threads") {
         if (value != 0.0 && value != 128.0 && value != 256.0) return fail(ctx, "set_option: optimizer_threads is 0, 128 or 256");
         ctx->opt_tpb = (int)value;
+    } else if (key == "optimizer_newton_tol") {
+        ctx->opt_newton_tol = value;
+    } else if (key == "optimizer_single_from") {
+        ctx->opt_single_from = value > 0.0 ? (int)value : 0;
     } else if (key == "host_chunks") {
         if (value < 0.0 || value > 16.0) return fail(ctx, "set_option: host_chunks is 0 .. 16");
         ctx->host_chunks = (int)value;
@@ -1140,7 +1154,8 @@ int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newt
     op.outer = outer_iterations > 0 ? outer_iterations : 32;
     op.lm_iters = newton_iterations > 0 ? newton_iterations : 2;
     op.refine_bg = refine_bg ? 1 : 0;
-    op.reserved = 0;
+    op.single_from = ctx->opt_single_from;
+    op.newton_tol = ctx->opt_newton_tol;
     op.delta0 = ctx->opt_delta0;
     op.shrink = ctx->opt_shrink;
     op.delta_min = ctx->opt_delta_min;
