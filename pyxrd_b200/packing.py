@@ -253,7 +253,14 @@ class StaticPack(object):
 
     def signature(self):
         """identity of EVERYTHING pyxrd_set_static uploads, to decide whether a resident copy can be reused (the
-        gonio row only holds the primary wavelength: the interpolation tables of the wavelength list are part of it)"""
+        gonio row only holds the primary wavelength: the interpolation tables of the wavelength list are part of it).
+        Computed once: a pack is not modified after construction."""
+        sig = getattr(self, "_signature", None)
+        if sig is None:
+            sig = self._signature = self._compute_signature()
+        return sig
+
+    def _compute_signature(self):
         return (self.S, self.Z, self.T, self.npts.tobytes(), self.gonio.tobytes(), self.theta.tobytes(),
                 self.nwl.tobytes(), self.wl_fraction.tobytes(), self.wl_index.tobytes(), self.wl_w_hi.tobytes(),
                 self.wl_w_lo.tobytes(), self.observed.tobytes(), self.selected.tobytes(),

@@ -240,6 +240,8 @@ class Context(object):
 
     # -- upload -----------------------------------------------------------------------
     def set_static(self, static: StaticPack, force: bool = False):
+        if not force and static is self._static:          # the very pack that is resident
+            return False
         sig = static.signature()
         if not force and self._static_sig == sig:
             self._static = static
