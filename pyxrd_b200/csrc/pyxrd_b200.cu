@@ -788,7 +788,7 @@ int build_jobs(pyxrd_ctx *ctx, const pyxrd_batch_desc *d, std::vector<int> &job_
 }
 
 // derived buffers, the BatchDev view of the blob, and the per-candidate prologue kernels
-int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int ncap, int acap) {
+int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int ncap, int acap, bool keep_layer_tables = false) {
     const StaticDev &st = ctx->st;
     const int K = z.K, M = z.M, NP = z.NP, NC = z.NC, NA = z.NA, S = st.S, Z = st.Z;
     const long long cand_stride = (long long)M * Z * st.sumX;
@@ -873,24 +873,45 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
     }
 
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    // Two independent chains and one independent kernel, side by side (the kernels are small and latency-bound):
+    //   probabilities -> phase prologue (CSDS, absolute scale)          on the context's stream
+    //   interlayer z-stretch -> distinct planes of every phase          on an auxiliary stream
+    //   layer tables (only when the classes or the static tables changed)  on another one
+    cudaStream_t main_stream = ctx->stream;
+    const bool side = ctx->overlap_classes && NP > 0 && NC > 0;
+    const bool need_tables = z.n_classes > 0 && st.sumX > 0 && !keep_layer_tables;
+    if (side) {
+        CK(cudaEventRecord(ctx->fork_ev, main_stream));
+        CK(cudaStreamWaitEvent(ctx->class_stream[0], ctx->fork_ev, 0));
+        if (need_tables) CK(cudaStreamWaitEvent(ctx->class_stream[1], ctx->fork_ev, 0));
+    }
     if (NP > 0) {
-        k_probabilities<<<(NP + 31) / 32, 32, 0, ctx->stream>>>(bt);        // serial per phase: spread over the SMs
+        k_probabilities<<<(NP + 31) / 32, 32, 0, main_stream>>>(bt);        // serial per phase: spread over the SMs
         LAUNCH_CHECK("k_probabilities");
-        k_phase_prologue<<<(NP + PX_PROLOGUE_WARPS - 1) / PX_PROLOGUE_WARPS, 32 * PX_PROLOGUE_WARPS, 0, ctx->stream>>>(bt);
+        k_phase_prologue<<<(NP + PX_PROLOGUE_WARPS - 1) / PX_PROLOGUE_WARPS, 32 * PX_PROLOGUE_WARPS, 0, main_stream>>>(bt);
         LAUNCH_CHECK("k_phase_prologue");
     }
+    cudaStream_t z_stream = side ? ctx->class_stream[0] : main_stream;
     if (NC > 0) {
-        k_component_z<<<(NC + 63) / 64, 64, 0, ctx->stream>>>(bt);
+        k_component_z<<<(NC + 63) / 64, 64, 0, z_stream>>>(bt);
         LAUNCH_CHECK("k_component_z");
     }
-    if (z.n_classes > 0 && st.sumX > 0) {
+    if (NP > 0) {
+        k_phase_planes<<<NP, 32, 0, z_stream>>>(bt);
+        LAUNCH_CHECK("k_phase_planes");
+    }
+    if (need_tables) {
         dim3 grid((unsigned)((st.sumX + 127) / 128), (unsigned)z.n_classes);
-        k_layer_table<<<grid, 128, 0, ctx->stream>>>(st, bt);
+        k_layer_table<<<grid, 128, 0, side ? ctx->class_stream[1] : main_stream>>>(st, bt);
         LAUNCH_CHECK("k_layer_table");
     }
-    if (NP > 0) {
-        k_phase_planes<<<NP, 32, 0, ctx->stream>>>(bt);
-        LAUNCH_CHECK("k_phase_planes");
+    if (side) {
+        CK(cudaEventRecord(ctx->join_ev[0], ctx->class_stream[0]));
+        CK(cudaStreamWaitEvent(main_stream, ctx->join_ev[0], 0));
+        if (need_tables) {
+            CK(cudaEventRecord(ctx->join_ev[1], ctx->class_stream[1]));
+            CK(cudaStreamWaitEvent(main_stream, ctx->join_ev[1], 0));
+        }
     }
     CK(cudaEventRecord(ctx->ev[7], ctx->stream));
     ctx->ev_set[3] = true;
@@ -1764,7 +1785,8 @@ int pyxrd_update_population(pyxrd_ctx *ctx, const double *x) {
     const BlobLayout L = plan_blob(z, ctx->st.S);
     k_expand_population<<<K, 128, 0, ctx->stream>>>(e);
     LAUNCH_CHECK("k_expand_population");
-    if (bind_batch(ctx, z, L, ncap, pp.acap)) return 1;
+    // the layer tables depend on the template's unbound layer rows and the static tables only: still valid
+    if (bind_batch(ctx, z, L, ncap, pp.acap, true)) return 1;
     pp.valid = true;
     return 0;
 }
