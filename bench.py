@@ -447,12 +447,13 @@ def measure_packed_config(env, name, count, peak_tf):
 
 
 def config_row(name, count, points, flops, flops_exe, dev_ms, phase_ms, peak_tf, path):
-    row = {"workload": "%s: %s" % (name, syn.CONFIGS[name].description), "candidates": count, "path": path,
-           "value": points / (dev_ms * 1e-3), "unit": "pattern-pts/s", "ms_per_step": dev_ms, "kernel_ms": phase_ms,
-           "frac": flops / (phase_ms * 1e-3) * 1e-12 / peak_tf if phase_ms > 0 else None}
-    if flops_exe is not None:
-        row["frac_executed"] = flops_exe / (phase_ms * 1e-3) * 1e-12 / peak_tf if phase_ms > 0 else None
-    return row
+    alg = flops / (phase_ms * 1e-3) * 1e-12 / peak_tf if phase_ms > 0 else None
+    exe = flops_exe / (phase_ms * 1e-3) * 1e-12 / peak_tf if (phase_ms > 0 and flops_exe is not None) else None
+    # frac: executed count where the template path knows it; packed graphs (c3 / c3s: one plane per atom group, no shared
+    # planes worth mentioning next to a rank-27 series): the algorithmic count
+    return {"workload": "%s: %s" % (name, syn.CONFIGS[name].description), "candidates": count, "path": path,
+            "value": points / (dev_ms * 1e-3), "unit": "pattern-pts/s", "ms_per_step": dev_ms, "kernel_ms": phase_ms,
+            "frac": exe if exe is not None else alg, "frac_algorithmic": alg}
 
 
 # ---------------------------------------------------------------------------------------
@@ -499,8 +500,18 @@ def _cpu_candidate(name, seed, idx, optimised):
     return m
 
 
+def _single_threaded_blas():
+    """one BLAS / OpenMP thread per process: the reference's Pool runs one trial per worker (pyxrd_server.py:57-76), and
+    scipy's L-BFGS-B would otherwise start a thread team in every worker (16 workers x 16 threads on 16 cores: measured
+    no faster than ONE process)"""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+
+
 def _cpu_one(arg):
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
     name, seed, idx, optimised = arg
     calc_mix, opt_res, _ = cpu_functions()
     m = _cpu_candidate(name, seed, idx, optimised)
@@ -516,6 +527,7 @@ def cpu_sample(name, budget_s, processes, optimised=False):
     kind = cpu_functions()[2]
     pts = mixture_work(syn.CONFIGS[name].truth())[1]
     done = 0
+    _single_threaded_blas()
     if processes <= 1:
         _cpu_one((name, SEED, 0, optimised))            # imports, observed pattern
         t0 = time.perf_counter()
@@ -528,7 +540,7 @@ def cpu_sample(name, budget_s, processes, optimised=False):
     else:
         import multiprocessing as mp
         _cpu_candidate(name, SEED, 0, optimised)          # the observed pattern is computed once, before the fork
-        with mp.get_context("fork").Pool(processes) as pool:
+        with mp.get_context("fork").Pool(processes, initializer=_single_threaded_blas) as pool:
             pool.map(_cpu_one, [(name, SEED, i, optimised) for i in range(processes)])      # warm every worker
             t0 = time.perf_counter()
             pos = processes
@@ -663,16 +675,19 @@ def run_b200(args, rank, world, local_rank):
                 "evals_per_s": main["K"] * world / (main["e2e_ms"] * 1e-3), "refinables": main["d"],
                 "gather_matches_single_gpu": main["gather_matches_single_gpu"]},
         "gpu_launches": main["launches"],
-        "roofline": {"bound": "fp64", "kernel": "k_phase_* (phase-intensity kernels)", "achieved": achieved_tf,
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                     "frac_executed": executed_tf / peak_tf if peak_tf else None,
-                     "note": "frac: algorithmic count (one complex exponential per atom, SURVEY 8(d)); frac_executed: the "
-                             "exponentials the kernel evaluates (one per distinct interlayer plane of a phase; the "
-                             "candidate-invariant layer stacks are read from the layer table of the batch)",
+        "roofline": {"bound": "fp64", "kernel": "k_phase_* (phase-intensity kernels)", "achieved": executed_tf,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": executed_tf / peak_tf if peak_tf else None,
+                     "count": "flops the kernels execute (DESIGN.md section 3): series + (32 + 8) per complex exponential "
+                              "evaluated (one per distinct interlayer plane of a phase; candidate-invariant layer stacks "
+                              "are read from the layer table of the batch) + 2 per atom + 64 per component + 120 (LPF, "
+                              "corrections)",
+                     "algorithmic": {"achieved": achieved_tf, "frac": achieved_tf / peak_tf if peak_tf else None,
+                                     "count": "SURVEY 8(d): one complex exponential per ATOM (32 + 8 + 2 each); exceeds 1 "
+                                              "where the kernels no longer evaluate them"},
                      "peak_source": "DFMA microbenchmark pyxrd_dfma_peak measured in this run (MEASURED_PEAKS.json "
                                     "has no fp64 entry)",
-                     "kernel_ms": phase_ms, "algorithmic_flops_per_launch": main["flops"],
-                     "executed_flops_per_launch": main["flops_executed"], "traffic": traffic,
+                     "kernel_ms": phase_ms, "flops_per_launch": main["flops_executed"],
+                     "algorithmic_flops_per_launch": main["flops"], "traffic": traffic,
                      "hbm": {"achieved_gbs": 16.0 * main["points"] / (phase_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
                              "frac": 16.0 * main["points"] / (phase_ms * 1e-3) * 1e-9 / hbm_peak,
                              "peak_source": "of measured" if peaks else "of fallback"}},
@@ -691,7 +706,7 @@ def run_b200(args, rank, world, local_rank):
         opt_ms = t["stage"]["residual"]
         opt_flops = t["K"] * optimiser_flops(t["M"], t["selected_points"], passes)
         opt_tf = opt_flops / (opt_ms * 1e-3) * 1e-12 if opt_ms > 0 else 0.0
-        ph_tf = t["flops"] / (t["stage"]["phase"] * 1e-3) * 1e-12 if t["stage"]["phase"] > 0 else 0.0
+        ph_tf = t["flops_executed"] / (t["stage"]["phase"] * 1e-3) * 1e-12 if t["stage"]["phase"] > 0 else 0.0
         line["trials"] = {
             "metric": "refinement trial evals/s (get_optimized_residual semantics: all phase patterns of the trial + "
                       "optimisation of fractions / scales / background + residual)",
@@ -710,7 +725,7 @@ def run_b200(args, rank, world, local_rank):
                          "count": "%d Gram passes x selected points x (2 NG + 4 MB + 4), MB = M + 1, NG = MB (MB + 1) / 2; "
                                   "the kernel is one latency chain per candidate (DESIGN.md section 4)" % passes,
                          "phase": {"kernel": "k_phase_*", "achieved": ph_tf, "frac": ph_tf / peak_tf if peak_tf else None,
-                                   "kernel_ms": t["stage"]["phase"]}},
+                                   "kernel_ms": t["stage"]["phase"], "count": "executed flops, as the headline roofline"}},
             "optimiser": "device majorise-minimise (pyxrd_optimize), 32 reweightings x <= 2 Newton steps; contract: <= "
                          "reference L-BFGS-B optimum * (1 + 5e-3)",
             "gpu_launches": t["launches"], "pattern_pts_per_s": t["points"] * world / (t["dev_ms"] * 1e-3)}
