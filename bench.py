@@ -320,6 +320,12 @@ def measure_generation(env, name, per_gpu, optimise, verify=True):
     with torch.cuda.stream(env.stream), ctx.lock:
         tmpl._load(ctx, x_mine)
         gathered = torch.empty((env.world * per_gpu, S + 1), dtype=torch.float64, device="cuda")
+        # the exchange: one NCCL all_gather_into_tensor of the rows; --gather peer: this rank's rows stored into every
+        # rank's table over NVLink by the library's kernel + one barrier (distributed.PeerGather)
+        peer = None
+        if env.world > 1 and args.gather == "peer":
+            peer = distributed.peer_gather_for(ctx, per_gpu, S + 1, env.device)
+        gather_ctx = ctx if peer is not None else None
 
         def step_resident():
             ctx.update_population(None)            # expansion + per-candidate prologue from the resident x
@@ -328,7 +334,9 @@ def measure_generation(env, name, per_gpu, optimise, verify=True):
                 ctx.optimize(refine_bg=refine_bg)
             else:
                 ctx.compute_all(residuals_only=True)
-            if env.world > 1:
+            if peer is not None:
+                peer(ctx.residuals_tensor(optimised=optimise), per_gpu * env.world)
+            elif env.world > 1:
                 dist.all_gather_into_tensor(gathered, ctx.residuals_tensor(optimised=optimise))
 
         dev_ms, stage, launches = env.time_device(step_resident, args.steps, args.warmup,
@@ -338,10 +346,12 @@ def measure_generation(env, name, per_gpu, optimise, verify=True):
         def step_e2e():
             if optimise:
                 table[0] = distributed.evaluate_solutions_sharded(
-                    x_total, lambda xb: tmpl.optimized_residuals(xb, ctx=ctx, device=True), device=env.device, columns=S + 1)
+                    x_total, lambda xb: tmpl.optimized_residuals(xb, ctx=ctx, device=True), device=env.device, columns=S + 1,
+                    ctx=gather_ctx)
             else:
                 table[0] = distributed.evaluate_solutions_sharded(
-                    x_total, lambda xb: tmpl.residuals(xb, ctx=ctx, device=True), device=env.device, columns=S + 1)
+                    x_total, lambda xb: tmpl.residuals(xb, ctx=ctx, device=True), device=env.device, columns=S + 1,
+                    ctx=gather_ctx)
 
         e2e_ms = env.time_wall(step_e2e, args.steps, min(args.warmup, 2))
         check = None
@@ -363,7 +373,9 @@ def measure_generation(env, name, per_gpu, optimise, verify=True):
                 stage={k: v / args.steps for k, v in stage.items()}, launches=launches,
                 h2d=int(x_mine.nbytes), d2h=int(per_gpu * env.world * (S + 1) * 8), finite=bool(np.isfinite(table[0]).all()),
                 gather_matches_single_gpu=check, selected_points=sel_points, X=[int(v) for v in tmpl.static.npts],
-                residual_sample=float(table[0][0, 0]), tmpl=tmpl, x_mine=x_mine)
+                residual_sample=float(table[0][0, 0]), tmpl=tmpl, x_mine=x_mine,
+                gather=("none (one rank)" if env.world == 1 else "rows stored into every rank's table over NVLink by "
+                        "k_put_rows_to_peers + one symmetric-memory barrier" if peer is not None else "NCCL all_gather_into_tensor"))
 
 
 def measure_patterns_download(env, gen):
@@ -400,7 +412,8 @@ def measure_sweep(env, name="c5", totals=SWEEP_TOTALS, steps=2):
 
             def step():
                 table[0] = distributed.evaluate_solutions_sharded(
-                    x, lambda xb: tmpl.optimized_residuals(xb, ctx=ctx, device=True), device=env.device, columns=S + 1)
+                    x, lambda xb: tmpl.optimized_residuals(xb, ctx=ctx, device=True), device=env.device, columns=S + 1,
+                    ctx=ctx if (env.world > 1 and env.args.gather == "peer") else None)
 
             ms = env.time_wall(step, steps, 1)
             check = None
@@ -673,7 +686,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": total_pts / (main["e2e_ms"] * 1e-3), "unit": "pattern-pts/s", "h2d_bytes_per_step": main["h2d"],
                 "d2h_bytes_per_step": main["d2h"], "ms_per_step": main["e2e_ms"], "call": call,
                 "evals_per_s": main["K"] * world / (main["e2e_ms"] * 1e-3), "refinables": main["d"],
-                "gather_matches_single_gpu": main["gather_matches_single_gpu"]},
+                "gather_matches_single_gpu": main["gather_matches_single_gpu"], "gather": main["gather"]},
         "gpu_launches": main["launches"],
         "roofline": {"bound": "fp64", "kernel": "k_phase_* (phase-intensity kernels)", "achieved": executed_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": executed_tf / peak_tf if peak_tf else None,
@@ -766,6 +779,9 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[4] population sweep")
     ap.add_argument("--no-configs", action="store_true", help="skip the table of the other configurations (N = 1)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+                    help="exchange of the residual rows at N > 1: one NCCL all-gather (default), or the library's stores into "
+                         "peer memory + a symmetric-memory barrier (measured equal at 2 GPUs, 2 %% slower at 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

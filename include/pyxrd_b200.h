@@ -290,6 +290,15 @@ int pyxrd_device_buffers(pyxrd_ctx *ctx, double **intensities_dev, double **tota
 /* device addresses of the optimiser's results (pyxrd_optimize): residuals [K][1+S], solutions [K][M+2S] */
 int pyxrd_device_results(pyxrd_ctx *ctx, double **opt_residuals_dev, double **solutions_dev);
 
+/* The exchange step of the sharded path (refinement/async_evaluatable.py:38-50 collects the results of
+ * a generation's tasks): rows [0, n_rows) of the device table src_dev[n_rows][cols] (this rank's residual rows,
+ * pyxrd_device_buffers / pyxrd_device_results) are stored into the gathered table of EVERY rank at row dst_row0.
+ * peer_tables: n_peers (<= 16) DEVICE pointers, one per rank, this rank's own included -- the peers' tables mapped into
+ * this process over NVLink / NVSwitch by the caller (torch symmetric memory, CUDA IPC).  Plain stores + a system-scope
+ * fence on the context's stream; the caller's cross-GPU barrier orders them against the peers' reads. */
+int pyxrd_put_rows_to_peers(pyxrd_ctx *ctx, const double *src_dev, int64_t n_rows, int cols, void *const *peer_tables,
+                            int n_peers, int64_t dst_row0);
+
 /* ---- one call, host buffers in and out (what a per-generation plugin call does) ---- */
 /* set_batch + compute_intensities + compute_residuals + read residuals [K][1+S];
  * intensities_out may be NULL (a refinement trial only needs the residuals). */

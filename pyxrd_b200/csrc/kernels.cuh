@@ -2378,6 +2378,24 @@ __global__ void k_mixture_mean(int k0, int K, int S, double *residuals) {
 }
 
 // ---------------------------------------------------------------------------------
+// residual rows of this rank into the gathered table of EVERY rank of the box (the only exchange of the
+// path).  The peers' tables are mapped into this process over NVLink / NVSwitch (torch symmetric memory or CUDA IPC, the
+// caller's business); the kernel is plain stores to peer memory -- 8 B per element and peer, latency-bound -- followed by
+// a system-scope fence; the caller's cross-GPU barrier orders them against the peers' reads.
+// ---------------------------------------------------------------------------------
+#define PX_MAX_PEERS 16
+struct PeerTables { double *table[PX_MAX_PEERS]; int n; };
+__global__ void k_put_rows_to_peers(const double *__restrict__ src, long long count, long long dst0, PeerTables peers) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        const double v = src[i];
+#pragma unroll 1
+        for (int p = 0; p < peers.n; ++p) peers.table[p][dst0 + i] = v;
+    }
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------
 // FP64 FMA peak microbenchmark: 8 independent chains per thread
 // ---------------------------------------------------------------------------------
 __global__ void k_dfma_peak(double *out, int iters, double seed) {

@@ -1252,6 +1252,25 @@ int pyxrd_device_results(pyxrd_ctx *ctx, double **opt_residuals_dev, double **so
     return 0;
 }
 
+int pyxrd_put_rows_to_peers(pyxrd_ctx *ctx, const double *src_dev, int64_t n_rows, int cols, void *const *peer_tables,
+                            int n_peers, int64_t dst_row0) {
+    if (!ctx) return 1;
+    if (!src_dev || !peer_tables || n_rows < 0 || cols <= 0 || n_peers <= 0 || n_peers > PX_MAX_PEERS || dst_row0 < 0)
+        return fail(ctx, "put_rows_to_peers: bad arguments (rows %lld, cols %d, peers %d of at most %d)", (long long)n_rows, cols, n_peers, PX_MAX_PEERS);
+    CK(cudaSetDevice(ctx->device));
+    if (n_rows == 0) return 0;
+    PeerTables peers{};
+    peers.n = n_peers;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peer_tables[p]) return fail(ctx, "put_rows_to_peers: peer %d has no table", p);
+        peers.table[p] = static_cast<double *>(peer_tables[p]);
+    }
+    const long long count = (long long)n_rows * cols;
+    k_put_rows_to_peers<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(src_dev, count, (long long)dst_row0 * cols, peers);
+    LAUNCH_CHECK("k_put_rows_to_peers");
+    return 0;
+}
+
 int pyxrd_evaluate_host(pyxrd_ctx *ctx, const pyxrd_batch_desc *desc, double *residuals_out, double *intensities_out) {
     if (pyxrd_set_batch(ctx, desc)) return 1;
     const int K = ctx->bt.K;

@@ -53,6 +53,60 @@ def shard(items: Sequence, rank: int, world_size: int):
 
 
 _pad_buffers = {}
+_peer_gathers = {}
+
+
+class PeerGather(object):
+    """All-gather of residual rows by direct stores into peer memory (NVLink / NVSwitch) instead of a NCCL collective.
+
+    Every rank owns two gathered tables f64[world * per, cols] in torch symmetric memory (mapped into every process of the
+    box at rendezvous; two, used alternately, so that the stores of generation g + 1 never land in a table a peer is
+    still copying to its host for generation g).  A gather is: the library's kernel ``pyxrd_put_rows_to_peers`` stores
+    the rank's rows into the table of EVERY rank at the rank's row offset, then one cross-GPU barrier on the signal pads
+    (``_SymmetricMemory.barrier``).  Measured inside the bench step (c2, 2048 candidates per GPU, 32 KB of rows per rank):
+    2 GPUs 0.803 ms against 0.801 ms with the NCCL all-gather, 8 GPUs 0.825 against 0.808 -- the exchange is ~25 us of
+    latency either way, so NCCL stays the default and this path is an option (``ctx=`` of ``evaluate_solutions_sharded``,
+    ``bench.py --gather peer``); both give the single-GPU table bit for bit."""
+
+    def __init__(self, ctx, per: int, cols: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.ctx, self.per, self.cols = ctx, int(per), int(cols)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.tables, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty((self.world * self.per, self.cols), dtype=torch.float64, device=device)
+            t.zero_()
+            self.tables.append(t)
+            self.handles.append(symm_mem.rendezvous(t, self.group))
+        self.turn = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)
+
+    def __call__(self, local, n_total: int):
+        t, h = self.tables[self.turn], self.handles[self.turn]
+        self.turn ^= 1
+        if local.shape[0]:
+            src = local if local.is_contiguous() else local.contiguous()
+            self.ctx.put_rows_to_peers(src.data_ptr(), src.shape[0], self.cols, list(h.buffer_ptrs), self.rank * self.per)
+        if not self.ctx.stream_is_torch_current():
+            self.ctx.synchronize()                 # the stores run on the context's stream, the barrier on torch's
+        h.barrier(channel=0)
+        return t[:n_total]
+
+
+def peer_gather_for(ctx, per: int, cols: int, device, group=None):
+    """cached ``PeerGather`` of this shape, or None where symmetric memory is not available (CPU groups, gloo, a torch
+    without it, GPUs without peer access): the caller then uses the NCCL all-gather"""
+    key = (id(ctx), int(per), int(cols), str(device), id(group))
+    if key not in _peer_gathers:
+        try:
+            _peer_gathers[key] = PeerGather(ctx, per, cols, device, group)
+        except Exception:
+            _peer_gathers[key] = None
+    return _peer_gathers[key]
 
 
 def gather_rows(local, n_total: int, world_size: int, group=None):
@@ -116,14 +170,16 @@ def evaluate_population_sharded(mixtures: Sequence, evaluate, device=None, group
     return _to_host(gather_rows(t, len(mixtures), world, group))
 
 
-def evaluate_solutions_sharded(x, evaluate, device=None, group=None, columns: Optional[int] = None) -> np.ndarray:
+def evaluate_solutions_sharded(x, evaluate, device=None, group=None, columns: Optional[int] = None, ctx=None) -> np.ndarray:
     """The template path over several GPUs (what ``RefineAsyncHelper.do_async_evaluation`` does with Pool tasks,
     refinement/refine_async_helper.py:16-23, async_evaluatable.py:38-50): every rank evaluates its block of the solution
     matrix ``x`` f64[K, d] with ``evaluate(x_block) -> f64[k] | f64[k, C]`` and all ranks receive the values of all K
     solutions in order.  On the GPU path ``evaluate`` is ``lambda xb: template.residuals(xb, device=True)`` /
     ``template.optimized_residuals(xb, device=True)`` of the rank's own template: the rank's rows are gathered straight
     from the library's device buffer (NCCL over NVLink), one device -> host copy of the gathered table at the end.
-    ``columns``: C when known (saves the broadcast that tells empty tail ranks the column count)."""
+    ``columns``: C when known (saves the broadcast that tells empty tail ranks the column count).  ``ctx``: the library
+    context the rows come from -- with it (and ``columns``) the exchange is ``PeerGather``: the rank's rows are stored
+    straight into every rank's gathered table over NVLink by the library's own kernel, one barrier, no NCCL collective."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -150,5 +206,8 @@ def evaluate_solutions_sharded(x, evaluate, device=None, group=None, columns: Op
         t = torch.from_numpy(np.ascontiguousarray(values.reshape(hi - lo, cols)))
         if device is not None:
             t = t.to(device)
-    out = _to_host(gather_rows(t, len(x), world, group))
+    peer = None
+    if ctx is not None and columns is not None and world > 1 and t.is_cuda:
+        peer = peer_gather_for(ctx, -(-len(x) // world), cols, t.device, group)
+    out = _to_host(peer(t, len(x)) if peer is not None else gather_rows(t, len(x), world, group))
     return out[:, 0] if (squeeze and cols == 1) else out

@@ -68,7 +68,7 @@ EXPORTS = [
     "pyxrd_read_correction", "pyxrd_device_buffers", "pyxrd_evaluate_host", "pyxrd_optimize_host", "pyxrd_leaf_asf",
     "pyxrd_leaf_lpf", "pyxrd_leaf_csds", "pyxrd_leaf_component", "pyxrd_stage_times", "pyxrd_dfma_peak",
     "pyxrd_expand_population", "pyxrd_expanded_desc", "pyxrd_expanded_free", "pyxrd_expand_error",
-    "pyxrd_set_population", "pyxrd_update_population", "pyxrd_device_results", "pyxrd_evaluate_population", "pyxrd_optimize_population", "pyxrd_leaf_probabilities",
+    "pyxrd_set_population", "pyxrd_update_population", "pyxrd_device_results", "pyxrd_put_rows_to_peers", "pyxrd_evaluate_population", "pyxrd_optimize_population", "pyxrd_leaf_probabilities",
     "pyxrd_leaf_statistic", "pyxrd_leaf_derive", "pyxrd_leaf_lorentz",
 ]
 
@@ -150,6 +150,7 @@ def load_library():
         lib.pyxrd_set_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc)]
         lib.pyxrd_update_population.argtypes = [vp, _f64p]
         lib.pyxrd_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        lib.pyxrd_put_rows_to_peers.argtypes = [vp, vp, C.c_int64, C.c_int, C.POINTER(vp), C.c_int, C.c_int64]
         lib.pyxrd_evaluate_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc), _f64p]
         lib.pyxrd_optimize_population.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(PopulationDesc), C.c_int, C.c_int,
                                                   C.c_int, _f64p, _f64p]
@@ -567,6 +568,18 @@ class Context(object):
         a, b = C.c_void_p(), C.c_void_p()
         self._check(self._lib.pyxrd_device_results(self._h, C.byref(a), C.byref(b)), "device_results")
         return a.value, b.value
+
+    def put_rows_to_peers(self, src_ptr: int, n_rows: int, cols: int, peer_ptrs, dst_row0: int):
+        """this rank's rows (device pointer) into the gathered table of every rank (device pointers of the peers' tables,
+        mapped by the caller): stores over NVLink on the context's stream"""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._check(self._lib.pyxrd_put_rows_to_peers(self._h, C.c_void_p(int(src_ptr)), int(n_rows), int(cols), arr,
+                                                      len(peer_ptrs), int(dst_row0)), "put_rows_to_peers")
+
+    def stream_is_torch_current(self) -> bool:
+        import torch
+        return getattr(self, "_stream_handle", 0) != 0 and \
+            torch.cuda.current_stream(self.device).cuda_stream == self._stream_handle
 
     def residuals_tensor(self, optimised: bool = False):
         """zero-copy torch view f64[K, 1+S] of the device residual buffer (``optimised``: of the optimiser's residuals),
