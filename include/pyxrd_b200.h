@@ -340,6 +340,13 @@ int pyxrd_leaf_component(pyxrd_ctx *ctx, const double *stl, int64_t n, const dou
                          const double *atom_type_rows, const uint8_t *atom_has_type,
                          double *sf_out, double *phi_out, double *z_out);
 
+/* mmult (math_tools.py:16-17): out[x] = a[x] b[x], n_points complex rank x rank matrices (interleaved re / im, row
+ * major), with numpy's rounding of the reference's broadcast-and-sum (no FMA, contraction index ascending) */
+int pyxrd_leaf_mmult(pyxrd_ctx *ctx, const double *a, const double *b, int64_t n_points, int rank, double *out);
+/* get_Q_matrices (phases.py:41-46): out[n][x] = q[x]^(n+1), n = 0 .. n_max, by repeated mmult.  The phase kernels never
+ * form this stack ((N + 1) X r^2 complex numbers: 2.96 GB for BASELINE configs[2]); this is the reference's helper as such. */
+int pyxrd_leaf_matrix_powers(pyxrd_ctx *ctx, const double *q, int64_t n_points, int rank, int n_max, double *out);
+
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* CUDA-event durations (ms) of the most recent compute calls, on the context's stream:
  * ms_out[0] = phase-intensity kernels, [1] = wavelength kernel, [2] = mixture residual kernels,

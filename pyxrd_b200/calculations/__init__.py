@@ -6,5 +6,5 @@ the C-ABI (``pyxrd_b200.runtime``) and hands back host numpy arrays, exactly whe
 the reference would have put them.  Nothing in this package computes on the CPU
 and nothing imports ``oracle/``.
 """
-from . import atoms, components, CSDS, goniometer, phases, specimen, mixture, statistics, exceptions  # noqa: F401
+from . import atoms, components, CSDS, goniometer, math_tools, phases, specimen, mixture, statistics, exceptions  # noqa: F401
 from .. import data_objects  # noqa: F401

@@ -74,6 +74,15 @@ def get_structure_factors(range_stl, G, comp_list):
     return SF, PF
 
 
+def get_Q_matrices(Q, CSDS_max):
+    """phases.py:41-46: ``Qn[n] = Q ** (n + 1)`` for n = 0 .. CSDS_max by repeated ``mmult`` (math_tools.py:16-17),
+    complex128[CSDS_max + 1, X, r, r].  The batch path never forms this stack; this is the
+    reference's helper itself, on the device (``k_leaf_matrix_powers``, numpy's rounding of the products and sums)."""
+    ctx = default_context()
+    with ctx.lock:
+        return ctx.leaf_matrix_powers(Q, CSDS_max)
+
+
 def get_absolute_scale(components, CSDS_real_mean, W):
     """phases.py:48-66: a dozen scalar operations on model constants (inside the batch path the prologue kernel does
     them per phase, k_phase_prologue); first G diagonal entries of W, ``None`` components skipped, 0 if the mass is 0."""

@@ -2070,6 +2070,50 @@ __global__ void __launch_bounds__(PX_GEN_TPB) k_phase_generic(StaticDev st, Batc
     bt.intensities[bt.job_out[job] + x] = finish_point(tr, abs_scale, flags, ps, st, gx);
 }
 
+// mmult (math_tools.py:16-17): C[x] = A[x] B[x] for X complex r x r matrices, in the order numpy evaluates the
+// reference's broadcast-and-sum: every product on its own ((ar br - ai bi) + i (ar bi + ai br), no FMA -- numpy's SIMD
+// loops fuse one of the two products on some CPUs, so the last bit is not portable there either), summed over the
+// contraction index in ascending order starting from the first product.  get_Q_matrices (phases.py:41-46): Qn[0] = Q,
+// Qn[n] = mmult(Qn[n-1], Q); a thread owns one ROW of one point's matrix: row i of Q^(n+1) only needs row i of Q^n.
+__device__ __forceinline__ double2 px_cmul_np(double2 a, double2 b) {
+    return make_double2(__dadd_rn(__dmul_rn(a.x, b.x), -__dmul_rn(a.y, b.y)), __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+}
+__global__ void k_leaf_mmult(const double2 *__restrict__ A, const double2 *__restrict__ B, long long X, int r, double2 *__restrict__ Cout) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= X * r * r) return;
+    const long long x = t / (r * r);
+    const int i = (int)((t / r) % r), j = (int)(t % r);
+    const double2 *a = A + (x * r + i) * r, *b = B + x * r * r + j;
+    double2 acc = px_cmul_np(a[0], b[0]);
+    for (int k = 1; k < r; ++k) {
+        const double2 p = px_cmul_np(a[k], b[(long long)k * r]);
+        acc = make_double2(__dadd_rn(acc.x, p.x), __dadd_rn(acc.y, p.y));
+    }
+    Cout[t] = acc;
+}
+__global__ void k_leaf_matrix_powers(const double2 *__restrict__ Q, long long X, int r, int nmax, double2 *__restrict__ Qn) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= X * r) return;
+    const long long x = t / r;
+    const int i = (int)(t % r);
+    const double2 *q = Q + x * r * r;
+    const long long level = X * r * r;                     // doubles2 per power
+    double2 *row = Qn + (x * r + i) * r;                   // row i of Qn[0][x]
+    for (int j = 0; j < r; ++j) row[j] = q[i * r + j];
+    for (int n = 1; n <= nmax; ++n) {
+        const double2 *prev = row + (long long)(n - 1) * level;
+        double2 *next = row + (long long)n * level;
+        for (int j = 0; j < r; ++j) {
+            double2 acc = px_cmul_np(prev[0], q[j]);
+            for (int k = 1; k < r; ++k) {
+                const double2 p = px_cmul_np(prev[k], q[k * r + j]);
+                acc = make_double2(__dadd_rn(acc.x, p.x), __dadd_rn(acc.y, p.y));
+            }
+            next[j] = acc;
+        }
+    }
+}
+
 // one component on an arbitrary stl axis (leaf: components.get_factors / atoms.get_structure_factor)
 __global__ void k_leaf_component(const double *stl, long long n, const double *comp_d, int n_layer, int n_inter,
                                  const double *atom_d, const double *atype_rows, const unsigned char *has_type,

@@ -243,6 +243,10 @@ int set_smem(pyxrd_ctx *ctx, K kernel, size_t bytes) {
 #ifndef PX_SMALL_TILES
 #define PX_SMALL_TILES 4     // tiles per block of the one-warp kernels (ranks 1, 2)
 #endif
+#ifndef PX_S22_PPT
+#define PX_S22_PPT 4         // points per thread / blocks per SM of the rank-2, two-component kernel (c2)
+#define PX_S22_MINB 16
+#endif
 #ifndef PX_WIDE_TILES
 #define PX_WIDE_TILES 1      // ... of the kernels with 64 / 128 threads per block
 #endif
@@ -319,7 +323,7 @@ int launch_class(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_
         if (rc.rank == 16 && rc.G == 4) return launch_small<16, 4, 1, 128, 0, 1, PX_WIDE_TILES>(ctx, rc, jobs_dev, njobs, bt);
     }
     // (points per thread, threads per block, min blocks per SM) from sweeps on B200 (profiles/r1_summary.md)
-    SMALLB(1, 1, 4, 32, 0); SMALLB(2, 2, 4, 32, 16); SMALLB(2, 1, 4, 32, 16);
+    SMALLB(1, 1, 4, 32, 0); SMALLB(2, 2, PX_S22_PPT, 32, PX_S22_MINB); SMALLB(2, 1, 4, 32, 16);
     SMALL(3, 3, 2, 128); SMALL(4, 4, 2, 128);  // R0 / R1
     SMALL(5, 5, 1, 128); SMALL(6, 6, 1, 128);
     SMALL(3, 1, 2, 128); SMALL(4, 1, 2, 128);
@@ -1434,6 +1438,35 @@ int pyxrd_leaf_component(pyxrd_ctx *ctx, const double *stl, int64_t n, const dou
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int pyxrd_leaf_mmult(pyxrd_ctx *ctx, const double *a, const double *b, int64_t n_points, int rank, double *out) {
+    if (!ctx || !a || !b || !out || n_points < 0 || rank <= 0) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_points * rank * rank * 2;
+    if (n == 0) return 0;
+    if (upload(ctx, ctx->d_leaf_a, a, n)) return 1;
+    if (upload(ctx, ctx->d_leaf_b, b, n)) return 1;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * n));
+    const long long threads = (long long)n_points * rank * rank;
+    k_leaf_mmult<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_leaf_a.as<double2>(), ctx->d_leaf_b.as<double2>(),
+                                                                           (long long)n_points, rank, ctx->d_leaf_c.as<double2>());
+    LAUNCH_CHECK("k_leaf_mmult");
+    return read_back(ctx, ctx->d_leaf_c.ptr, out, (int64_t)n, (int64_t)n, "mmult");
+}
+
+int pyxrd_leaf_matrix_powers(pyxrd_ctx *ctx, const double *q, int64_t n_points, int rank, int n_max, double *out) {
+    if (!ctx || !q || !out || n_points < 0 || rank <= 0 || n_max < 0) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const size_t per = (size_t)n_points * rank * rank * 2, n = per * ((size_t)n_max + 1);
+    if (per == 0) return 0;
+    if (upload(ctx, ctx->d_leaf_a, q, per)) return 1;
+    CK(ctx->d_leaf_c.ensure(sizeof(double) * n));
+    const long long threads = (long long)n_points * rank;
+    k_leaf_matrix_powers<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_leaf_a.as<double2>(), (long long)n_points, rank,
+                                                                                   n_max, ctx->d_leaf_c.as<double2>());
+    LAUNCH_CHECK("k_leaf_matrix_powers");
+    return read_back(ctx, ctx->d_leaf_c.ptr, out, (int64_t)n, (int64_t)n, "matrix powers");
 }
 
 // ---- population from a template + binding table (host side: layout only) ------------------------

@@ -21,7 +21,9 @@ _TARGETS = {
     "pyxrd.calculations.CSDS": ("CSDS", ["calculate_distribution"]),
     "pyxrd.calculations.goniometer": ("goniometer", ["get_T", "get_lorentz_polarisation_factor",
                                                      "get_fixed_to_ads_correction_range"]),
-    "pyxrd.calculations.phases": ("phases", ["get_diffracted_intensity", "get_intensity", "get_structure_factors"]),
+    "pyxrd.calculations.phases": ("phases", ["get_diffracted_intensity", "get_intensity", "get_structure_factors",
+                                             "get_Q_matrices"]),
+    "pyxrd.calculations.math_tools": ("math_tools", ["mmult"]),
     "pyxrd.calculations.specimen": ("specimen", ["get_machine_correction_range", "calculate_phase_intensities",
                                                  "calculate_scaled_intensities"]),
     "pyxrd.calculations.statistics": ("statistics", ["R_squared", "Rp", "smooth_pattern", "derive", "Rpder", "Rpw", "Rpe",

@@ -69,7 +69,7 @@ EXPORTS = [
     "pyxrd_leaf_lpf", "pyxrd_leaf_csds", "pyxrd_leaf_component", "pyxrd_stage_times", "pyxrd_dfma_peak",
     "pyxrd_expand_population", "pyxrd_expanded_desc", "pyxrd_expanded_free", "pyxrd_expand_error",
     "pyxrd_set_population", "pyxrd_update_population", "pyxrd_device_results", "pyxrd_put_rows_to_peers", "pyxrd_evaluate_population", "pyxrd_optimize_population", "pyxrd_leaf_probabilities",
-    "pyxrd_leaf_statistic", "pyxrd_leaf_derive", "pyxrd_leaf_lorentz",
+    "pyxrd_leaf_statistic", "pyxrd_leaf_derive", "pyxrd_leaf_lorentz", "pyxrd_leaf_mmult", "pyxrd_leaf_matrix_powers",
 ]
 
 _lib = None
@@ -134,6 +134,8 @@ def load_library():
         lib.pyxrd_leaf_asf.argtypes = [vp, _f64p, C.c_int64, _f64p, _f64p]
         lib.pyxrd_leaf_statistic.argtypes = [vp, C.c_int, _f64p, _f64p, _f64p, C.c_int64, C.c_double, _f64p]
         lib.pyxrd_leaf_derive.argtypes = [vp, _f64p, C.c_int64, C.c_int, _f64p]
+        lib.pyxrd_leaf_mmult.argtypes = [vp, _f64p, _f64p, C.c_int64, C.c_int, _f64p]
+        lib.pyxrd_leaf_matrix_powers.argtypes = [vp, _f64p, C.c_int64, C.c_int, C.c_int, _f64p]
         lib.pyxrd_leaf_lorentz.argtypes = [vp, _f64p, C.c_int64, C.c_double, C.c_double, C.c_double, _f64p]
         lib.pyxrd_leaf_lpf.argtypes = [vp, _f64p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _f64p]
         lib.pyxrd_leaf_csds.argtypes = [vp, _f64p, C.c_int, C.c_int, _f64p, _f64p, _f64p]
@@ -422,6 +424,27 @@ class Context(object):
         out = np.empty_like(v)
         self._check(self._lib.pyxrd_leaf_derive(self._h, _p(v, _f64p), v.size, int(bool(smooth_only)), _p(out, _f64p)),
                     "leaf_derive")
+        return out
+
+    def leaf_mmult(self, A, B):
+        """math_tools.mmult: batched complex matrix product [X, r, r] x [X, r, r] -> complex128[X, r, r]"""
+        A = np.ascontiguousarray(A, dtype=np.complex128)
+        B = np.ascontiguousarray(B, dtype=np.complex128)
+        if A.ndim != 3 or A.shape != B.shape or A.shape[1] != A.shape[2]:
+            raise ValueError("operands could not be broadcast together with shapes %r %r" % (A.shape, B.shape))
+        out = np.empty_like(A)
+        self._check(self._lib.pyxrd_leaf_mmult(self._h, A.ctypes.data_as(_f64p), B.ctypes.data_as(_f64p), A.shape[0], A.shape[1],
+                                               out.ctypes.data_as(_f64p)), "leaf_mmult")
+        return out
+
+    def leaf_matrix_powers(self, Q, n_max: int):
+        """phases.get_Q_matrices: complex128[n_max + 1, X, r, r], entry n = Q^(n + 1)"""
+        Q = np.ascontiguousarray(Q, dtype=np.complex128)
+        if Q.ndim != 3 or Q.shape[1] != Q.shape[2]:
+            raise ValueError("Q must be [X, r, r], got %r" % (Q.shape,))
+        out = np.empty((int(n_max) + 1,) + Q.shape, dtype=np.complex128)
+        self._check(self._lib.pyxrd_leaf_matrix_powers(self._h, Q.ctypes.data_as(_f64p), Q.shape[0], Q.shape[1], int(n_max),
+                                                       out.ctypes.data_as(_f64p)), "leaf_matrix_powers")
         return out
 
     def leaf_lpf(self, theta, sigma_star, soller1, soller2, mcr_2theta):

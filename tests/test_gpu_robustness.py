@@ -234,3 +234,30 @@ def test_layer_tables_on_and_off_agree(calc):
         orc.calculate_mixture(ref)
         assert rel_err(pats[k][0], ref.specimens[0].phase_intensities) < RTOL
         assert rel_err(res[k], ref.residuals) < RTOL
+
+
+def test_mmult_and_q_matrices_match_numpy(calc):
+    """a7: ``mmult`` (math_tools.py:16-17) and ``get_Q_matrices`` (phases.py:41-46) as device leaves, against the
+    reference's own numpy expressions (restated here: broadcast-and-sum over the contraction index).  1e-13 of the
+    largest entry: numpy's complex product is not bit-portable (its SIMD loops fuse one of the two products)"""
+    rng = np.random.default_rng(8)
+
+    def np_mmult(A, B):
+        return np.sum(np.transpose(A, (0, 2, 1))[:, :, :, np.newaxis] * B[:, :, np.newaxis, :], -3)
+
+    for X, r in ((37, 1), (50, 2), (21, 3), (9, 8), (3, 27)):
+        A = rng.standard_normal((X, r, r)) + 1j * rng.standard_normal((X, r, r))
+        B = rng.standard_normal((X, r, r)) + 1j * rng.standard_normal((X, r, r))
+        want = np_mmult(A, B)
+        assert np.max(np.abs(calc.math_tools.mmult(A, B) - want)) <= 1e-13 * np.max(np.abs(want)), (X, r)
+        Q = 0.6 * A / r
+        want = np.zeros((6,) + Q.shape, dtype=complex)
+        want[0] = Q
+        for n in range(1, 6):
+            want[n] = np_mmult(want[n - 1], Q)
+        got = calc.phases.get_Q_matrices(Q, 5)
+        assert got.shape == want.shape, (X, r)
+        for n in range(6):
+            assert np.max(np.abs(got[n] - want[n])) <= 1e-13 * np.max(np.abs(want[n])), (X, r, n)
+    with pytest.raises(ValueError):
+        calc.math_tools.mmult(np.zeros((2, 3, 3)), np.zeros((2, 2, 2)))
