@@ -2548,6 +2548,7 @@ struct OptParams {
     int single_from;    // from this majoriser on ONE Newton / LM iteration per majoriser (0: lm_iters throughout)
     double delta0, shrink, delta_min;   // weight floor relative to mean |obs|: delta0 * shrink^it >= delta_min
     double newton_tol;                  // relative decrease of the majoriser below which no further Newton iteration is taken
+    int coarse_until, coarse_stride;    // passes before coarse_until visit every coarse_stride-th group of points
 };
 
 #ifndef PX_OPT_NDAMP
@@ -3243,6 +3244,10 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
 #pragma unroll
             for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
             const double delta = delta_rel * sm.mean_obs[s];
+            // coarse passes (optimizer_coarse_until / _stride): while the weight floor is still large a majoriser built
+            // from every stride-th group of points -- another group every pass -- moves the iterate as well as the full one
+            const int stride = (it < op.coarse_until && op.coarse_stride > 1) ? op.coarse_stride : 1;
+            const int g0 = stride > 1 ? it % stride : 0;
 #ifdef PX_OPT_PROFILE
             long long tG = clock64();
 #endif
@@ -3349,16 +3354,18 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
                     const double *Ix = I + (long long)z * X + tid, *ox = obs + (long long)z * X + tid;
                     const double *cx = corr + tid;
                     const unsigned char *sx = sel + tid;
-                    int left = X - tid;                     // points from this thread's position to the end
-                    for (; left > (PIF - 1) * TPB; left -= PIF * TPB, Ix += PIF * TPB, ox += PIF * TPB, cx += PIF * TPB,
-                                                   sx += PIF * TPB)
+                    // (coarse passes: every `stride`-th group of PIF * TPB points, starting at group `g0`)
+                    const int skip = g0 * PIF * TPB, hop = PIF * TPB * stride;
+                    int left = X - tid - skip;              // points from this thread's position to the end
+                    Ix += skip; ox += skip; cx += skip; sx += skip;
+                    for (; left > (PIF - 1) * TPB; left -= hop, Ix += hop, ox += hop, cx += hop, sx += hop)
                         group(std::true_type(), Ix, cx, ox, sx, left);
                     if (left > 0) group(std::false_type(), Ix, cx, ox, sx, left);
                 }
             } else {
                 // many phases: indexed loads (a running pointer per phase would cost the registers of the accumulators)
                 for (int z = 0; z < Z; ++z)
-                    for (int x0 = tid; x0 < X; x0 += PIF * TPB) {
+                    for (int x0 = tid + g0 * PIF * TPB; x0 < X; x0 += PIF * TPB * stride) {
                         double phi[PIF][MB], o[PIF];
                         bool on[PIF];
 #pragma unroll

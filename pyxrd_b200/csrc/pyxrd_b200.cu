@@ -120,6 +120,7 @@ struct pyxrd_ctx {
     // its pass.  1e-5 keeps the excess over a long run on c4 AND on the ill-conditioned c5 (four similar phases) where
     // 1e-13 had it, 14 % / 9 % faster; 1e-4 and fixed single iterations after the first passes lose c5 (tools/opt_switch.py)
     double opt_newton_tol = 1e-5;
+    int opt_coarse_until = 0, opt_coarse_stride = 1;   // "optimizer_coarse_until" / "optimizer_coarse_stride" (off)
 
     // static
     bool have_static = false;
@@ -464,6 +465,10 @@ int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value) {
     else if (key == "optimizer_threads") {
         if (value != 0.0 && value != 128.0 && value != 256.0) return fail(ctx, "set_option: optimizer_threads is 0, 128 or 256");
         ctx->opt_tpb = (int)value;
+    } else if (key == "optimizer_coarse_until") {
+        ctx->opt_coarse_until = value > 0.0 ? (int)value : 0;
+    } else if (key == "optimizer_coarse_stride") {
+        ctx->opt_coarse_stride = value >= 1.0 ? (int)value : 1;
     } else if (key == "optimizer_newton_tol") {
         ctx->opt_newton_tol = value;
     } else if (key == "optimizer_single_from") {
@@ -1181,6 +1186,8 @@ int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newt
     op.refine_bg = refine_bg ? 1 : 0;
     op.single_from = ctx->opt_single_from;
     op.newton_tol = ctx->opt_newton_tol;
+    op.coarse_until = std::min(ctx->opt_coarse_until, op.outer);
+    op.coarse_stride = ctx->opt_coarse_stride;
     op.delta0 = ctx->opt_delta0;
     op.shrink = ctx->opt_shrink;
     op.delta_min = ctx->opt_delta_min;

@@ -261,3 +261,54 @@ def test_mmult_and_q_matrices_match_numpy(calc):
             assert np.max(np.abs(got[n] - want[n])) <= 1e-13 * np.max(np.abs(want[n])), (X, r, n)
     with pytest.raises(ValueError):
         calc.math_tools.mmult(np.zeros((2, 3, 3)), np.zeros((2, 2, 2)))
+
+
+def test_generations_of_one_population_reuse_the_resident_template(calc):
+    """``pyxrd_update_population``: later generations of the same template only upload x.  Same results, bit for bit, as
+    a fresh upload; a changed population size, another template or any other call in between falls back to the full
+    upload; CSDS maxima beyond the first generation's (longer series, larger coefficient tables) are handled."""
+    from pyxrd_b200.population import PopulationTemplate
+    from pyxrd_b200.runtime import default_context
+    ctx = default_context()
+    tmix, refs = syn.template("c4")
+    _observed(tmix)
+    tmpl = PopulationTemplate(tmix, refs)
+    omix, orefs = syn.template("c4")
+    other = PopulationTemplate(_observed(omix), orefs)                  # same content, another template object
+    lo = np.array([r.minimum for r in refs])
+    hi = np.array([r.maximum for r in refs])
+    rng = np.random.default_rng(12)
+
+    def fresh(x, optimised):
+        ctx.invalidate_residency()
+        return tmpl.optimized_residuals(x) if optimised else tmpl.residuals(x)
+
+    x1 = lo + rng.uniform(0.0, 0.5, (6, lo.size)) * (hi - lo)          # small CSDS averages first
+    x2 = lo + rng.uniform(0.5, 1.0, (6, lo.size)) * (hi - lo)          # then larger ones: longer series than resident
+    first = tmpl.residuals(x1)
+    assert ctx.population_is_resident(tmpl._key(), x1.shape)
+    second = tmpl.residuals(x2)                                         # update path
+    assert ctx.population_is_resident(tmpl._key(), x2.shape)
+    assert np.array_equal(second, fresh(x2, False)) and np.array_equal(first, fresh(x1, False))
+    opt_a = tmpl.optimized_residuals(x1)                                # update path again (after the fresh uploads)
+    assert np.array_equal(opt_a, fresh(x1, True))
+    x3 = np.concatenate([x1, x2])                                       # another K: full upload
+    assert np.array_equal(tmpl.residuals(x3)[:6], first)
+    calc.mixture.calculate_mixture(_observed(syn.CONFIGS["c1"].truth()))   # a drop-in call in between drops the population
+    assert not ctx.population_is_resident(tmpl._key(), x3.shape)
+    assert np.array_equal(tmpl.residuals(x3)[6:], second)
+    assert np.array_equal(other.residuals(x3), tmpl.residuals(x3))      # templates do not share residency
+
+
+def test_layer_tables_with_none_atom_types(calc):
+    """a None atom type contributes nothing (atoms.py:65-67), also inside a tabulated layer stack"""
+    from pyxrd_b200.batched import population_phase_intensities
+    mixes = [_observed(syn.CONFIGS["c2"].candidate(2024, i)) for i in range(3)]
+    for m in mixes:
+        for comp in m.specimens[0].phases[0][0].components:
+            comp.layer_atoms[4].atom_type = None                        # the same layer position in every component
+    got = population_phase_intensities([copy.deepcopy(m) for m in mixes])
+    for k, m in enumerate(mixes):
+        ref = copy.deepcopy(m)
+        orc.calculate_mixture(ref)
+        assert rel_err(got[k][0], ref.specimens[0].phase_intensities) < RTOL

@@ -17,9 +17,11 @@ def calc_total(mix):
 syn.attach_observed(mixes, truth, calc_total)
 static, batch = pack_population(mixes)
 ctx = default_context(0)
-def run(outer, newton, single_from, tol=1e-13):
+def run(outer, newton, single_from, tol=1e-5, coarse=(0, 1)):
     ctx.set_option("optimizer_single_from", single_from)
     ctx.set_option("optimizer_newton_tol", tol)
+    ctx.set_option("optimizer_coarse_until", coarse[0])
+    ctx.set_option("optimizer_coarse_stride", coarse[1])
     ctx.optimize(refine_bg=True, outer=outer, newton=newton); ctx.synchronize()
     t0 = time.perf_counter()
     for _ in range(3):
@@ -31,10 +33,12 @@ with ctx.lock:
     ctx.set_batch(batch)
     ctx.compute_intensities()
     best, _ = run(96, 8, 0)
-    for outer, newton, sf, tol in [(32, 2, 0, 1e-13), (32, 2, 4, 1e-13), (32, 2, 0, 1e-6), (32, 2, 0, 1e-5), (32, 2, 0, 1e-4), (32, 2, 0, 1e-3), (32, 2, 0, 1e-2),
-                                  (32, 3, 0, 1e-4), (32, 3, 0, 1e-3), (32, 4, 0, 1e-3), (32, 4, 0, 1e-2)]:
-        r, dt = run(outer, newton, sf, tol)
+    for outer, coarse in [(32, (0, 1)), (32, (8, 2)), (32, (12, 2)), (32, (16, 2)), (32, (8, 4)), (32, (12, 4)), (32, (16, 4)), (32, (20, 4)),
+                          (32, (12, 8)), (32, (16, 8)), (36, (16, 4))]:
+        r, dt = run(outer, 2, 0, 1e-5, coarse)
         ex = r / np.minimum(best, r) - 1.0
-        print("outer %2d newton %d single from %2d tol %.0e: %.3f ms  excess max %.2e p99 %.2e mean %.2e (#>1e-3: %d)" % (outer, newton, sf, tol, dt * 1e3, ex.max(), np.quantile(ex, 0.99), ex.mean(), int((ex > 1e-3).sum())))
+        print("outer %2d coarse until %2d stride %d: %.3f ms  excess max %.2e p99 %.2e mean %.2e (#>1e-3: %d)" % (outer, coarse[0], coarse[1], dt * 1e3, ex.max(), np.quantile(ex, 0.99), ex.mean(), int((ex > 1e-3).sum())))
+    ctx.set_option("optimizer_coarse_until", 0)
+    ctx.set_option("optimizer_coarse_stride", 1)
     ctx.set_option("optimizer_single_from", 0)
     ctx.set_option("optimizer_newton_tol", 1e-5)
