@@ -288,18 +288,23 @@ __global__ void k_observed_norm(StaticDev st, double *derived) {
 #define PX_PROB_STRIDE 12
 #define PX_PROB_MAXSQ 81  // largest level matrix: rank 9 (R2G3)
 
+// G, R compile-time: every multi-index of a model's update() folds to a constant and the level matrices live in
+// registers (the first version kept them in 4.5 KB of local memory per thread behind run-time index arithmetic:
+// 51 us for c4's 1536 model-driven phases, 15 us for c2's 2048)
+template <int G_, int R_>
 struct ProbLevels {
-    int R, G, Rp;
-    double W[4][PX_PROB_MAXSQ];      // lW[0 .. Rp-1], lW[Rp] = W . P
-    double P[3][PX_PROB_MAXSQ];      // lP[0 .. Rp-1]
-    __device__ int ipow(int e) const { int v = 1; for (int i = 0; i < e; ++i) v *= G; return v; }
-    __device__ int wrank(int r) const { return ipow(r < Rp ? r + 1 : Rp); }
-    __device__ int prank(int r) const { return ipow(r + 1); }
-    __device__ void xy(const int *ind, int Rl, int &x, int &y) const {
+    static constexpr int G = G_, R = R_, Rp = R_ > 1 ? R_ : 1;
+    __host__ __device__ static constexpr int ipow(int e) { int v = 1; for (int i = 0; i < e; ++i) v *= G_; return v; }
+    static constexpr int SQ = ipow(Rp) * ipow(Rp);  // largest level matrix
+    double W[Rp + 1][SQ];            // lW[0 .. Rp-1], lW[Rp] = W . P
+    double P[Rp][SQ];                // lP[0 .. Rp-1]
+    __device__ __forceinline__ static constexpr int wrank(int r) { return ipow(r < Rp ? r + 1 : Rp); }
+    __device__ __forceinline__ static constexpr int prank(int r) { return ipow(r + 1); }
+    __device__ __forceinline__ static void xy(const int *ind, int Rl, int &x, int &y) {
         x = 0; y = 0;
         for (int i = 1; i <= Rl; ++i) { const int f = ipow(Rl - i); x += ind[i - 1] * f; y += ind[i] * f; }
     }
-    __device__ double &mW(const int *ind, int l) {             // base_models.py:263-281
+    __device__ __forceinline__ double &mW(const int *ind, int l) {             // base_models.py:263-281
         if (l == Rp + 1) {
             int x, y;
             xy(ind, l - 1 > 1 ? l - 1 : 1, x, y);
@@ -309,17 +314,17 @@ struct ProbLevels {
         for (int i = 0; i < l; ++i) x += ind[i] * ipow(l - (i + 1));
         return W[l - 1][x * wrank(l - 1) + x];
     }
-    __device__ double &mP(const int *ind, int l) {             // base_models.py:243-261
+    __device__ __forceinline__ double &mP(const int *ind, int l) {             // base_models.py:243-261
         int x, y;
         xy(ind, l - 1 > 1 ? l - 1 : 1, x, y);
         return P[l - 2][x * prank(l - 2) + y];
     }
-    __device__ double &W1(int a) { int i[1] = {a}; return mW(i, 1); }
-    __device__ double &W2(int a, int b) { int i[2] = {a, b}; return mW(i, 2); }
-    __device__ double &W3(int a, int b, int c) { int i[3] = {a, b, c}; return mW(i, 3); }
-    __device__ double &P2(int a, int b) { int i[2] = {a, b}; return mP(i, 2); }
-    __device__ double &P3(int a, int b, int c) { int i[3] = {a, b, c}; return mP(i, 3); }
-    __device__ double &P4(int a, int b, int c, int d) { int i[4] = {a, b, c, d}; return mP(i, 4); }
+    __device__ __forceinline__ double &W1(int a) { int i[1] = {a}; return mW(i, 1); }
+    __device__ __forceinline__ double &W2(int a, int b) { int i[2] = {a, b}; return mW(i, 2); }
+    __device__ __forceinline__ double &W3(int a, int b, int c) { int i[3] = {a, b, c}; return mW(i, 3); }
+    __device__ __forceinline__ double &P2(int a, int b) { int i[2] = {a, b}; return mP(i, 2); }
+    __device__ __forceinline__ double &P3(int a, int b, int c) { int i[3] = {a, b, c}; return mP(i, 3); }
+    __device__ __forceinline__ double &P4(int a, int b, int c, int d) { int i[4] = {a, b, c, d}; return mP(i, 4); }
 };
 
 __device__ __forceinline__ double pm_clamp(double v, double lo) { return fmin(fmax(v, lo), 1.0); }
@@ -331,37 +336,48 @@ __device__ __forceinline__ double pm_mul(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ double pm_div(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ double pm_ratio(double a, double b) { return b > 0.0 ? __ddiv_rn(a, b) : 0.0; }   // a / b if b > 0 else 0
 
-__device__ void prob_solve(ProbLevels &lv) {                    // base_models.py:142-162
-    const int G = lv.G;
-    for (int num = 1; num < lv.R; ++num) {
+template <class LV>
+__device__ __forceinline__ void prob_solve(LV &lv) {                    // base_models.py:142-162
+    constexpr int G = LV::G;
+#pragma unroll
+    for (int num = 1; num < LV::R; ++num) {
         int base[4];
-        for (int code = 0, n = lv.ipow(num); code < n; ++code) {
+#pragma unroll
+        for (int code = 0; code < LV::ipow(num); ++code) {
+#pragma unroll
             for (int i = 0, c = code; i < num; ++i) { base[num - i] = c % G; c /= G; }      // base[1..num]
             double acc = 0.0;
+#pragma unroll
             for (int i = 0; i < G; ++i) { base[0] = i; acc = __dadd_rn(acc, lv.mW(base, num + 1)); }
             lv.mW(base + 1, num) = acc;
         }
-        for (int code = 0, n = lv.ipow(num + 1); code < n; ++code) {
+#pragma unroll
+        for (int code = 0; code < LV::ipow(num + 1); ++code) {
+#pragma unroll
             for (int i = 0, c = code; i <= num; ++i) { base[num - i] = c % G; c /= G; }      // base[0..num]
             const double w = lv.mW(base, num);
             lv.mP(base, num + 1) = w > 0.0 ? __ddiv_rn(lv.mW(base, num + 1), w) : 0.0;
         }
     }
-    const int r = lv.wrank(lv.Rp);
-    const double *Wt = lv.W[lv.Rp - 1], *Pt = lv.P[lv.Rp - 1];
+    constexpr int r = LV::wrank(LV::Rp);
+#pragma unroll
     for (int i = 0; i < r; ++i)
+#pragma unroll
         for (int j = 0; j < r; ++j) {
             double acc = 0.0;
-            for (int k = 0; k < r; ++k) acc = fma(Wt[i * r + k], Pt[k * r + j], acc);
-            lv.W[lv.Rp][i * r + j] = acc;
+#pragma unroll
+            for (int k = 0; k < r; ++k) acc = fma(lv.W[LV::Rp - 1][i * r + k], lv.P[LV::Rp - 1][k * r + j], acc);
+            lv.W[LV::Rp][i * r + j] = acc;
         }
 }
 
-__device__ void prob_update(ProbLevels &lv, int model, const double *par) {
-    const int G = lv.G;
-    if (model == PX_PROB_R0) {
+template <int model, class LV>
+__device__ __forceinline__ void prob_update(LV &lv, const double *par) {
+    constexpr int G = LV::G;
+    if constexpr (model == PX_PROB_R0) {
         if (G > 1) {
             double run = 0.0;                                   // np.sum(np.diag(W)[0:i]), sequential
+#pragma unroll
             for (int i = 0; i < G - 1; ++i) {
                 const double F = pm_clamp(par[i], 0.0);
                 const double w = i > 0 ? __dmul_rn(F, pm_sub(1.0, run)) : F;
@@ -372,9 +388,11 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
         } else {
             lv.W1(0) = 1.0;
         }
+#pragma unroll
         for (int i = 0; i < G; ++i)
+#pragma unroll
             for (int j = 0; j < G; ++j) lv.P[0][i * G + j] = lv.W[0][j * G + j];
-    } else if (model == PX_PROB_R1G2) {
+    } else if constexpr (model == PX_PROB_R1G2) {
         const double W1 = pm_clamp(par[0], 0.0), Pxx = pm_clamp(par[1], 0.0);
         lv.W1(0) = W1;
         lv.W1(1) = pm_sub(1.0, W1);
@@ -389,7 +407,7 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
             lv.P2(0, 1) = pm_muldiv(lv.W1(1), lv.P2(1, 0), lv.W1(0));
             lv.P2(0, 0) = pm_sub(1.0, lv.P2(0, 1));
         }
-    } else if (model == PX_PROB_R2G2) {
+    } else if constexpr (model == PX_PROB_R2G2) {
         const double W1 = pm_clamp(par[0], 0.5), Pa = pm_clamp(par[1], 0.0), P21 = pm_clamp(par[2], 0.0),
                      Pb = pm_clamp(par[3], 0.0);
         lv.W1(0) = W1;
@@ -418,7 +436,7 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
         }
         lv.P3(0, 1, 0) = pm_sub(1.0, lv.P3(0, 1, 1));
         lv.P3(1, 1, 1) = pm_sub(1.0, lv.P3(1, 1, 0));
-    } else if (model == PX_PROB_R3G2) {
+    } else if constexpr (model == PX_PROB_R3G2) {
         const double W1 = pm_clamp(par[0], 2.0 / 3.0), Px = pm_clamp(par[1], 0.0);
         lv.W1(0) = W1;
         lv.W1(1) = pm_sub(1.0, W1);
@@ -435,6 +453,7 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
             lv.P4(0, 0, 0, 1) = pm_c01(pm_sub(1.0, lv.P4(0, 0, 0, 0)));
         }
         const int fixed[6][3] = {{0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}, {1, 1, 1}};
+#pragma unroll
         for (int t = 0; t < 6; ++t) {
             lv.P4(fixed[t][0], fixed[t][1], fixed[t][2], 0) = 1.0;
             lv.P4(fixed[t][0], fixed[t][1], fixed[t][2], 1) = 0.0;
@@ -443,7 +462,7 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
         lv.W3(1, 0, 1) = 0.0; lv.W3(1, 1, 0) = 0.0; lv.W3(1, 1, 1) = 0.0; lv.W3(0, 1, 1) = 0.0;
         const double wm = pm_c01(pm_sub(1.0, w0));
         lv.W3(1, 0, 0) = wm; lv.W3(0, 1, 0) = wm; lv.W3(0, 0, 1) = wm;
-    } else if (model == PX_PROB_R1G3) {
+    } else if constexpr (model == PX_PROB_R1G3) {
         const double W1 = pm_clamp(par[0], 0.0), Pxx = pm_clamp(par[1], 0.0), G1 = pm_clamp(par[2], 0.0),
                      G2 = pm_clamp(par[3], 0.0), G3 = pm_clamp(par[4], 0.0), G4 = pm_clamp(par[5], 0.0);
         lv.W1(0) = W1;
@@ -471,8 +490,9 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
         lv.P2(0, 2) = pm_mul(pm_sub(pm_sub(lv.W1(2), lv.W2(1, 2)), lv.W2(2, 2)), W0inv);
         if (lv.W1(0) > 0.5) lv.P2(0, 0) = pm_sub(pm_sub(1.0, lv.P2(0, 1)), lv.P2(0, 2));
         // R1models.py:405-407 rewrite the two-index weights, which solve() replaces by W . P anyway
-    } else if (model == PX_PROB_R1G4) {
+    } else if constexpr (model == PX_PROB_R1G4) {
         double q[12];
+#pragma unroll
         for (int i = 0; i < 12; ++i) q[i] = pm_clamp(par[i], 0.0);      // W1 P11_or_P22 R1 R2 G1 G2 G11 G12 G21 G22 G31 G32
         lv.W1(0) = q[0];
         lv.W1(1) = pm_mul(pm_sub(1.0, lv.W1(0)), q[2]);
@@ -488,23 +508,27 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
         }
         const double W1x = pm_mul(Wxx, q[4]), Wyx = pm_sub(Wxx, W1x), W2x = pm_mul(Wyx, q[5]), W3x = pm_sub(Wyx, W2x);
         const double Wix[3] = {W1x, W2x, W3x};
+#pragma unroll
         for (int i = 1; i < 4; ++i) {
             lv.W2(i, 1) = pm_mul(q[4 + 2 * i], Wix[i - 1]);
             lv.W2(i, 2) = pm_mul(q[5 + 2 * i], pm_sub(Wix[i - 1], lv.W2(i, 1)));
             lv.W2(i, 3) = pm_sub(pm_sub(Wix[i - 1], lv.W2(i, 1)), lv.W2(i, 2));
         }
+#pragma unroll
         for (int i = 1; i < 4; ++i) {
             lv.P2(i, 0) = 1.0;
+#pragma unroll
             for (int j = 1; j < 4; ++j) {
                 lv.P2(i, j) = pm_ratio(lv.W2(i, j), lv.W1(i));
                 lv.P2(i, 0) = pm_sub(lv.P2(i, 0), lv.P2(i, j));
             }
             lv.W2(i, 0) = pm_mul(lv.W1(i), lv.P2(i, 0));
         }
+#pragma unroll
         for (int j = 1; j < 4; ++j)
             lv.P2(0, j) = pm_mul(pm_sub(pm_sub(pm_sub(lv.W1(j), lv.W2(1, j)), lv.W2(2, j)), lv.W2(3, j)), W0inv);
         if (lv.W1(0) >= 0.5) lv.P2(0, 0) = pm_sub(pm_sub(pm_sub(1.0, lv.P2(0, 1)), lv.P2(0, 2)), lv.P2(0, 3));
-    } else if (model == PX_PROB_R2G3) {
+    } else if constexpr (model == PX_PROB_R2G3) {
         const double W1 = pm_clamp(par[0], 0.5), Pxx = pm_clamp(par[1], 0.0), G1 = pm_clamp(par[2], 0.0),
                      G2 = pm_clamp(par[3], 0.0), G3 = pm_clamp(par[4], 0.0), G4 = pm_clamp(par[5], 0.0);
         lv.W1(0) = W1;
@@ -534,36 +558,65 @@ __device__ void prob_update(ProbLevels &lv, int model, const double *par) {
         lv.W3(0, 0, 0) = pm_mul(lv.W2(0, 0), lv.P3(0, 0, 0));
         lv.W3(0, 0, 1) = pm_sub(pm_sub(lv.W2(0, 1), lv.W3(1, 0, 1)), lv.W3(2, 0, 1));
         lv.W3(0, 0, 2) = pm_sub(pm_sub(lv.W2(0, 2), lv.W3(1, 0, 2)), lv.W3(2, 0, 2));
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
             for (int j = 0; j < 3; ++j)
+#pragma unroll
                 for (int k = 0; k < 3; ++k) lv.P3(i, j, k) = pm_ratio(lv.W3(i, j, k), lv.W2(i, j));
     }
     prob_solve(lv);
 }
 
 // -> rank; W (diagonal matrix) and P written row-major, *valid = every entry of every level in [0, 1]
-__device__ int prob_evaluate(int model, int G, const double *par, double *Wout, double *Pout, int *valid) {
-    ProbLevels lv;
-    lv.G = G;
-    lv.R = model == PX_PROB_R0 ? 0 : (model == PX_PROB_R1G2 || model == PX_PROB_R1G3 || model == PX_PROB_R1G4) ? 1
-           : (model == PX_PROB_R2G2 || model == PX_PROB_R2G3) ? 2 : 3;
-    lv.Rp = lv.R > 1 ? lv.R : 1;
-    const int nsq = lv.wrank(lv.Rp) * lv.wrank(lv.Rp);          // the largest level matrix of this model
-    for (int r = 0; r <= lv.Rp; ++r)
-        for (int i = 0; i < nsq; ++i) lv.W[r][i] = 0.0;
-    for (int r = 0; r < lv.Rp; ++r)
-        for (int i = 0; i < nsq; ++i) lv.P[r][i] = 0.0;
-    prob_update(lv, model, par);
-    prob_update(lv, model, par);
+template <int model, int G, int R>
+__device__ __noinline__ int prob_evaluate_t(const double *par, double *Wout, double *Pout, int *valid) {
+    using LV = ProbLevels<G, R>;
+    LV lv;
+#pragma unroll
+    for (int r = 0; r <= LV::Rp; ++r)
+#pragma unroll
+        for (int i = 0; i < LV::SQ; ++i) lv.W[r][i] = 0.0;
+#pragma unroll
+    for (int r = 0; r < LV::Rp; ++r)
+#pragma unroll
+        for (int i = 0; i < LV::SQ; ++i) lv.P[r][i] = 0.0;
+    prob_update<model>(lv, par);
+    prob_update<model>(lv, par);
     bool ok = true;
-    for (int r = 0; r <= lv.Rp; ++r)
-        for (int i = 0, n = lv.wrank(r) * lv.wrank(r); i < n; ++i) ok = ok && !(lv.W[r][i] < 0.0 || lv.W[r][i] > 1.0);
-    for (int r = 0; r < lv.Rp; ++r)
-        for (int i = 0, n = lv.prank(r) * lv.prank(r); i < n; ++i) ok = ok && !(lv.P[r][i] < 0.0 || lv.P[r][i] > 1.0);
-    const int rank = lv.wrank(lv.Rp);
-    for (int i = 0; i < rank * rank; ++i) { Wout[i] = lv.W[lv.Rp - 1][i]; Pout[i] = lv.P[lv.Rp - 1][i]; }
+#pragma unroll
+    for (int r = 0; r <= LV::Rp; ++r)
+#pragma unroll
+        for (int i = 0; i < LV::wrank(r) * LV::wrank(r); ++i) ok = ok && !(lv.W[r][i] < 0.0 || lv.W[r][i] > 1.0);
+#pragma unroll
+    for (int r = 0; r < LV::Rp; ++r)
+#pragma unroll
+        for (int i = 0; i < LV::prank(r) * LV::prank(r); ++i) ok = ok && !(lv.P[r][i] < 0.0 || lv.P[r][i] > 1.0);
+    constexpr int rank = LV::wrank(LV::Rp);
+#pragma unroll
+    for (int i = 0; i < rank * rank; ++i) { Wout[i] = lv.W[LV::Rp - 1][i]; Pout[i] = lv.P[LV::Rp - 1][i]; }
     *valid = ok ? 1 : 0;
     return rank;
+}
+
+__device__ int prob_evaluate(int model, int G, const double *par, double *Wout, double *Pout, int *valid) {
+    switch (model) {
+        case PX_PROB_R0:
+            switch (G) {
+                case 1: return prob_evaluate_t<PX_PROB_R0, 1, 0>(par, Wout, Pout, valid);
+                case 2: return prob_evaluate_t<PX_PROB_R0, 2, 0>(par, Wout, Pout, valid);
+                case 3: return prob_evaluate_t<PX_PROB_R0, 3, 0>(par, Wout, Pout, valid);
+                case 4: return prob_evaluate_t<PX_PROB_R0, 4, 0>(par, Wout, Pout, valid);
+                case 5: return prob_evaluate_t<PX_PROB_R0, 5, 0>(par, Wout, Pout, valid);
+                default: return prob_evaluate_t<PX_PROB_R0, 6, 0>(par, Wout, Pout, valid);
+            }
+        case PX_PROB_R1G2: return prob_evaluate_t<PX_PROB_R1G2, 2, 1>(par, Wout, Pout, valid);
+        case PX_PROB_R2G2: return prob_evaluate_t<PX_PROB_R2G2, 2, 2>(par, Wout, Pout, valid);
+        case PX_PROB_R3G2: return prob_evaluate_t<PX_PROB_R3G2, 2, 3>(par, Wout, Pout, valid);
+        case PX_PROB_R1G3: return prob_evaluate_t<PX_PROB_R1G3, 3, 1>(par, Wout, Pout, valid);
+        case PX_PROB_R1G4: return prob_evaluate_t<PX_PROB_R1G4, 4, 1>(par, Wout, Pout, valid);
+        default: return prob_evaluate_t<PX_PROB_R2G3, 3, 2>(par, Wout, Pout, valid);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -2549,6 +2602,7 @@ struct OptParams {
     double delta0, shrink, delta_min;   // weight floor relative to mean |obs|: delta0 * shrink^it >= delta_min
     double newton_tol;                  // relative decrease of the majoriser below which no further Newton iteration is taken
     int coarse_until, coarse_stride;    // passes before coarse_until visit every coarse_stride-th group of points
+    int lane_solver;                    // 5 < D <= 12: dampings of the single-lane Levenberg-Marquardt solver (0: warp teams)
 };
 
 #ifndef PX_OPT_NDAMP
@@ -2572,6 +2626,7 @@ struct OptSmem {
     double g[PX_OPT_MAXD], vn[PX_OPT_MAXD], invd[PX_OPT_MAXD];
     double lam;                     // Levenberg-Marquardt damping, carried from one majoriser to the next
     double newton_tol;              // a Newton / LM iteration that lowers the majoriser by less than this (relative) is the last
+    int lane_solver;                // dampings of the single-lane solver (0: the warp-team solvers)
     double cand_q[PX_OPT_NDAMP];                    // majoriser value each warp's damping reaches (register solver)
     double cand_v[PX_OPT_NDAMP][PX_OPT_MAXD];       // and its trial point
 #ifdef PX_OPT_PROFILE
@@ -3115,6 +3170,156 @@ __device__ __noinline__ void opt_inner_solve_scalar(OptSmem &sm, int lm_iters, i
     }
 }
 
+// The same step for 5 < D <= 12 on single lanes of warp 0 (`optimizer_lane_solver` = number of dampings, each on its own
+// lane): the team version above pays ~10 k cycles per Levenberg-Marquardt round for D = 10 -- chains of shuffles, a named
+// barrier and a round trip through shared memory between four warps -- for ~600 floating-point operations.  Here a lane
+// carries the whole system: the Hessian is assembled once per iteration into shared memory (every lane computes the same
+// values, lane 0 stores), the left-looking Cholesky factor lives in the lane's registers / local memory (packed lower
+// triangle, static indices), the forward substitution runs inside the factorisation, and the majoriser value of the trial
+// point comes from the Gram matrices in shared memory (broadcast loads).  The chain per round is D reciprocal square
+// roots plus short fma chains; nothing waits on another warp.
+template <int M, int S, int ND>
+__device__ __noinline__ void opt_inner_solve_lane(OptSmem &sm, int lm_iters, int refine_bg, int lane) {
+    constexpr int MB = M + 1, D = M + 2 * S;
+    static_assert(ND == 4 || ND == 8 || ND == 16, "dampings side by side");
+    double v[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = sm.v[i];
+    double lam = sm.lam;
+    double *H = sm.H;                                           // [D][PX_OPT_LDA], lower triangle used
+    for (int it = 0; it < lm_iters; ++it) {
+        double g[D], qv = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) g[i] = 0.0;
+        __syncwarp();                                           // the previous iteration's reads of H are done
+        {
+            double c2[S];                                       // 2 w r^2 per specimen
+#pragma unroll
+            for (int s = 0; s < S; ++s) c2[s] = 2.0 * sm.wgt[s] * v[M + s] * v[M + s];
+#pragma unroll
+            for (int p = 0; p < M; ++p)
+#pragma unroll
+                for (int q = 0; q <= p; ++q) {
+                    double h = 0.0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) h = fma(c2[s], sm.B[s][p * MB + q], h);
+                    if (lane == 0) H[p * PX_OPT_LDA + q] = h;
+                }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const double *B = sm.B[s], *c = sm.c[s];
+            const double w = sm.wgt[s], r = v[M + s], b = v[M + S + s];
+            const int ir = M + s, ib = M + S + s;
+            double fBf = 0.0, Bcf = 0.0, cf = 0.0;
+#pragma unroll
+            for (int p = 0; p < M; ++p) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < M; ++q) t = fma(B[p * MB + q], v[q], t);
+                const double bm = B[p * MB + M], cl = c[p];
+                fBf = fma(v[p], t, fBf);
+                Bcf = fma(bm, v[p], Bcf);
+                cf = fma(cl, v[p], cf);
+                g[p] += w * (2.0 * r * r * t + 2.0 * r * b * bm - 2.0 * r * cl);
+                if (lane == 0) {
+                    H[ir * PX_OPT_LDA + p] = w * (4.0 * r * t + 2.0 * b * bm - 2.0 * cl);
+                    H[ib * PX_OPT_LDA + p] = 2.0 * w * r * bm;
+                }
+            }
+            const double BMM = B[M * MB + M], cM = c[M];
+            qv += w * (r * r * fBf + 2.0 * r * b * Bcf + BMM * b * b - 2.0 * r * cf - 2.0 * cM * b);
+            g[ir] = w * (2.0 * r * fBf + 2.0 * b * Bcf - 2.0 * cf);
+            g[ib] = w * (2.0 * r * Bcf + 2.0 * BMM * b - 2.0 * cM);
+            if (lane == 0) {
+                // rows of the scale / background variables: entries towards other specimens' variables are zero
+#pragma unroll
+                for (int j = M; j <= ib; ++j) { if (j < ir) H[ir * PX_OPT_LDA + j] = 0.0; if (j < ib) H[ib * PX_OPT_LDA + j] = 0.0; }
+                H[ir * PX_OPT_LDA + ir] = 2.0 * w * fBf;
+                H[ib * PX_OPT_LDA + ir] = 2.0 * w * Bcf;
+                H[ib * PX_OPT_LDA + ib] = 2.0 * w * BMM;
+            }
+        }
+        __syncwarp();
+        unsigned fr = 0u;                                       // bit i: variable i is free
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const bool fixed_bg = (!refine_bg && i >= M + S);
+            if (!fixed_bg && !(v[i] <= sm.lo[i] && g[i] > 0.0) && H[i * PX_OPT_LDA + i] > 0.0) fr |= 1u << i;
+        }
+        if (fr == 0u) break;
+        bool accepted = false;
+        double rel = 0.0;
+#pragma unroll 1
+        for (int round = 0; round < 4 && !accepted; ++round) {
+            const int wdx = lane & (ND - 1);
+            double lam_w = lam * 0.2;
+            for (int i = 0; i < wdx; ++i) lam_w *= 5.0;
+            double L[D * (D + 1) / 2], y[D];                    // packed lower triangle: (i, j) at i (i + 1) / 2 + j; diagonal = 1 / l_jj
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const bool fj = (fr >> j) & 1u;
+                const double hjj = fj ? H[j * PX_OPT_LDA + j] : 1.0;
+                double djj = hjj + (lam_w * fabs(hjj) + 1e-300), z = fj ? -g[j] : 0.0;
+#pragma unroll
+                for (int k = 0; k < j; ++k) {
+                    const double ljk = L[j * (j + 1) / 2 + k];
+                    djj = fma(-ljk, ljk, djj);
+                    z = fma(-ljk, y[k], z);
+                }
+                if (!(djj > 0.0)) ok = false;
+                const double inv = rsqrt(ok ? djj : 1.0);
+                L[j * (j + 1) / 2 + j] = inv;
+                y[j] = z * inv;                                 // L z = -g alongside
+#pragma unroll
+                for (int i = j + 1; i < D; ++i) {
+                    double a = (fj && ((fr >> i) & 1u)) ? H[i * PX_OPT_LDA + j] : 0.0;
+#pragma unroll
+                    for (int k = 0; k < j; ++k) a = fma(-L[i * (i + 1) / 2 + k], L[j * (j + 1) / 2 + k], a);
+                    L[i * (i + 1) / 2 + j] = a * inv;
+                }
+            }
+#pragma unroll
+            for (int j = D - 1; j >= 0; --j) {                  // L^T x = z
+                double z = y[j];
+#pragma unroll
+                for (int k = j + 1; k < D; ++k) z = fma(-L[k * (k + 1) / 2 + j], y[k], z);
+                y[j] = z * L[j * (j + 1) / 2 + j];
+            }
+            double vn[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) vn[i] = ((fr >> i) & 1u) ? fmax(sm.lo[i], v[i] + y[i]) : v[i];
+            const double qn = opt_q_scalar<M, S>(sm, vn);
+            double qb = (ok && qn < qv) ? qn : __longlong_as_double(0x7ff0000000000000LL);        // best of the ladder: lowest value, then lowest damping
+            int wb = wdx;
+#pragma unroll
+            for (int o = 1; o < ND; o <<= 1) {
+                const double q2 = __shfl_xor_sync(0xffffffffu, qb, o);
+                const int w2 = __shfl_xor_sync(0xffffffffu, wb, o);
+                if (q2 < qb || (q2 == qb && w2 < wb)) { qb = q2; wb = w2; }
+            }
+            if (qb < qv) {
+                accepted = true;
+                rel = (qv - qb) / fmax(fabs(qv), 1e-300);
+                const int src = (lane & ~(ND - 1)) | wb;
+#pragma unroll
+                for (int i = 0; i < D; ++i) v[i] = __shfl_sync(0xffffffffu, vn[i], src);
+                lam = fmax(__shfl_sync(0xffffffffu, lam_w, src), 1e-12);
+            } else {
+                for (int i = 0; i < ND; ++i) lam *= 5.0;
+            }
+        }
+        if (!accepted || rel < sm.newton_tol) break;
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) sm.v[i] = v[i];
+        sm.lam = fmin(lam, 1e-3);
+    }
+}
+
 // register version (PX_OPT_NDAMP warps of the block, one damping each) where the problem is small enough (S <= 3 and
 // D = M + 2 S <= 12), shared-memory version (warp 0) otherwise.  Each kernel instantiation (M fixed) compiles at most
 // three register solvers; D <= 5 goes to the single-thread scalar solver.  Called by every thread of the block.
@@ -3130,6 +3335,10 @@ __device__ __forceinline__ void opt_solve_dispatch(OptSmem &sm, int S, int lm_it
     if constexpr (M + 2 <= 5) { if (S == 1) { if (warp == 0) opt_inner_solve_scalar<M, 1>(sm, lm_iters, refine_bg, lane); return; } }
     if constexpr (M + 4 <= 5) { if (S == 2) { if (warp == 0) opt_inner_solve_scalar<M, 2>(sm, lm_iters, refine_bg, lane); return; } }
 #endif
+    if (sm.lane_solver) {                                       // block-uniform
+        if constexpr (PX_OPT_SCALAR_D < M + 2 && M + 2 <= 12) { if (S == 1) { if (warp == 0) { if (sm.lane_solver >= 8) opt_inner_solve_lane<M, 1, 8>(sm, lm_iters, refine_bg, lane); else opt_inner_solve_lane<M, 1, 4>(sm, lm_iters, refine_bg, lane); } return; } }
+        if constexpr (PX_OPT_SCALAR_D < M + 4 && M + 4 <= 12) { if (S == 2) { if (warp == 0) { if (sm.lane_solver >= 8) opt_inner_solve_lane<M, 2, 8>(sm, lm_iters, refine_bg, lane); else opt_inner_solve_lane<M, 2, 4>(sm, lm_iters, refine_bg, lane); } return; } }
+    }
     const bool team = warp < PX_OPT_NDAMP;
     if constexpr (PX_OPT_SCALAR_D < M + 2 && M + 2 <= 12) { if (S == 1) { if (team) opt_inner_solve_reg<M, 1>(sm, lm_iters, refine_bg, lane, warp); return; } }
     if constexpr (PX_OPT_SCALAR_D < M + 4 && M + 4 <= 12) { if (S == 2) { if (team) opt_inner_solve_reg<M, 2>(sm, lm_iters, refine_bg, lane, warp); return; } }
@@ -3217,6 +3426,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
     if (tid == 0) {
         sm.lam = 1e-3;
         sm.newton_tol = op.newton_tol;
+        sm.lane_solver = op.lane_solver;
         for (int p = 0; p < M; ++p) { sm.v[p] = 1.0 / M; sm.lo[p] = 0.0; }             // mixture.py:60-68 start
         for (int s = 0; s < S; ++s) {
             sm.v[M + s] = 1.0; sm.lo[M + s] = 1e-12;

@@ -121,6 +121,7 @@ struct pyxrd_ctx {
     // 1e-13 had it, 14 % / 9 % faster; 1e-4 and fixed single iterations after the first passes lose c5 (tools/opt_switch.py)
     double opt_newton_tol = 1e-5;
     int opt_coarse_until = 0, opt_coarse_stride = 1;   // "optimizer_coarse_until" / "optimizer_coarse_stride" (off)
+    int opt_lane_solver = 4;     // "optimizer_lane_solver": dampings of the single-lane solver for 5 < D <= 12 (0: warp teams)
 
     // static
     bool have_static = false;
@@ -471,6 +472,9 @@ int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value) {
         ctx->opt_coarse_stride = value >= 1.0 ? (int)value : 1;
     } else if (key == "optimizer_newton_tol") {
         ctx->opt_newton_tol = value;
+    } else if (key == "optimizer_lane_solver") {
+        if (value != 0.0 && value != 4.0 && value != 8.0) return fail(ctx, "set_option: optimizer_lane_solver is 0, 4 or 8");
+        ctx->opt_lane_solver = (int)value;
     } else if (key == "optimizer_single_from") {
         ctx->opt_single_from = value > 0.0 ? (int)value : 0;
     } else if (key == "host_chunks") {
@@ -1186,6 +1190,7 @@ int pyxrd_optimize(pyxrd_ctx *ctx, int refine_bg, int outer_iterations, int newt
     op.refine_bg = refine_bg ? 1 : 0;
     op.single_from = ctx->opt_single_from;
     op.newton_tol = ctx->opt_newton_tol;
+    op.lane_solver = ctx->opt_lane_solver;
     op.coarse_until = std::min(ctx->opt_coarse_until, op.outer);
     op.coarse_stride = ctx->opt_coarse_stride;
     op.delta0 = ctx->opt_delta0;
