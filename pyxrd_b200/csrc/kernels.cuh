@@ -3173,11 +3173,26 @@ __device__ __noinline__ void opt_inner_solve_scalar(OptSmem &sm, int lm_iters, i
 // The same step for 5 < D <= 12 on single lanes of warp 0 (`optimizer_lane_solver` = number of dampings, each on its own
 // lane): the team version above pays ~10 k cycles per Levenberg-Marquardt round for D = 10 -- chains of shuffles, a named
 // barrier and a round trip through shared memory between four warps -- for ~600 floating-point operations.  Here a lane
-// carries the whole system: the Hessian is assembled once per iteration into shared memory (every lane computes the same
-// values, lane 0 stores), the left-looking Cholesky factor lives in the lane's registers / local memory (packed lower
-// triangle, static indices), the forward substitution runs inside the factorisation, and the majoriser value of the trial
-// point comes from the Gram matrices in shared memory (broadcast loads).  The chain per round is D reciprocal square
-// roots plus short fma chains; nothing waits on another warp.
+// carries the whole system and uses its block structure: the scale and background of a specimen couple to the fractions
+// but not to another specimen's pair, so the damped Newton matrix is
+//     [ Hff  C_1  C_2 .. ]      Hff: M x M,  C_s = [u_s v_s]: M x 2,  D_s: 2 x 2
+//     [ C_1' D_1         ]
+//     [ C_2'      D_2    ]
+// and the pairs are eliminated in closed form (2 x 2 inverses): A = Hff - sum_s C_s D_s^-1 C_s' is the only matrix that
+// is factorised -- M instead of M + 2 S dependent pivots (reciprocal square roots), a triangle of M (M + 1) / 2 doubles
+// that stays in registers.  Variables that are not free (fixed background, held at a bound by the gradient) get identity
+// rows, exactly as in the other solvers; the matrix is positive definite iff every D_s and A are.  The Hessian blocks are
+// assembled once per iteration into shared memory (every lane computes the same values, lane 0 stores) and read back
+// with broadcast loads in the rounds.  First version of the lane solver (round 2, full D x D left-looking Cholesky with
+// the factor in local memory): ~9 k cycles per round on c4; this one: see DESIGN.md section 4.
+__device__ __forceinline__ double px_rcp_newton(double x) {        // 1 / x for x > 0: special-function seed + two Newton steps
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 template <int M, int S, int ND>
 __device__ __noinline__ void opt_inner_solve_lane(OptSmem &sm, int lm_iters, int refine_bg, int lane) {
     constexpr int MB = M + 1, D = M + 2 * S;
@@ -3186,9 +3201,9 @@ __device__ __noinline__ void opt_inner_solve_lane(OptSmem &sm, int lm_iters, int
 #pragma unroll
     for (int i = 0; i < D; ++i) v[i] = sm.v[i];
     double lam = sm.lam;
-    double *H = sm.H;                                           // [D][PX_OPT_LDA], lower triangle used
+    double *H = sm.H;                                           // rows 0 .. M-1: lower triangle of Hff; row M + s: u_s; row M + S + s: v_s
     for (int it = 0; it < lm_iters; ++it) {
-        double g[D], qv = 0.0;
+        double g[D], hrr[S], hrb[S], hbb[S], qv = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) g[i] = 0.0;
         __syncwarp();                                           // the previous iteration's reads of H are done
@@ -3214,9 +3229,13 @@ __device__ __noinline__ void opt_inner_solve_lane(OptSmem &sm, int lm_iters, int
             double fBf = 0.0, Bcf = 0.0, cf = 0.0;
 #pragma unroll
             for (int p = 0; p < M; ++p) {
-                double t = 0.0;
+                double t0 = 0.0, t1 = 0.0;                      // two partial sums: half the dependent chain
 #pragma unroll
-                for (int q = 0; q < M; ++q) t = fma(B[p * MB + q], v[q], t);
+                for (int q = 0; q < M; q += 2) {
+                    t0 = fma(B[p * MB + q], v[q], t0);
+                    if (q + 1 < M) t1 = fma(B[p * MB + q + 1], v[q + 1], t1);
+                }
+                const double t = t0 + t1;
                 const double bm = B[p * MB + M], cl = c[p];
                 fBf = fma(v[p], t, fBf);
                 Bcf = fma(bm, v[p], Bcf);
@@ -3231,21 +3250,19 @@ __device__ __noinline__ void opt_inner_solve_lane(OptSmem &sm, int lm_iters, int
             qv += w * (r * r * fBf + 2.0 * r * b * Bcf + BMM * b * b - 2.0 * r * cf - 2.0 * cM * b);
             g[ir] = w * (2.0 * r * fBf + 2.0 * b * Bcf - 2.0 * cf);
             g[ib] = w * (2.0 * r * Bcf + 2.0 * BMM * b - 2.0 * cM);
-            if (lane == 0) {
-                // rows of the scale / background variables: entries towards other specimens' variables are zero
-#pragma unroll
-                for (int j = M; j <= ib; ++j) { if (j < ir) H[ir * PX_OPT_LDA + j] = 0.0; if (j < ib) H[ib * PX_OPT_LDA + j] = 0.0; }
-                H[ir * PX_OPT_LDA + ir] = 2.0 * w * fBf;
-                H[ib * PX_OPT_LDA + ir] = 2.0 * w * Bcf;
-                H[ib * PX_OPT_LDA + ib] = 2.0 * w * BMM;
-            }
+            hrr[s] = 2.0 * w * fBf;
+            hrb[s] = 2.0 * w * Bcf;
+            hbb[s] = 2.0 * w * BMM;
         }
         __syncwarp();
         unsigned fr = 0u;                                       // bit i: variable i is free
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-            const bool fixed_bg = (!refine_bg && i >= M + S);
-            if (!fixed_bg && !(v[i] <= sm.lo[i] && g[i] > 0.0) && H[i * PX_OPT_LDA + i] > 0.0) fr |= 1u << i;
+        for (int p = 0; p < M; ++p)
+            if (!(v[p] <= sm.lo[p] && g[p] > 0.0) && H[p * PX_OPT_LDA + p] > 0.0) fr |= 1u << p;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            if (!(v[M + s] <= sm.lo[M + s] && g[M + s] > 0.0) && hrr[s] > 0.0) fr |= 1u << (M + s);
+            if (refine_bg && !(v[M + S + s] <= sm.lo[M + S + s] && g[M + S + s] > 0.0) && hbb[s] > 0.0) fr |= 1u << (M + S + s);
         }
         if (fr == 0u) break;
         bool accepted = false;
@@ -3253,43 +3270,96 @@ __device__ __noinline__ void opt_inner_solve_lane(OptSmem &sm, int lm_iters, int
 #pragma unroll 1
         for (int round = 0; round < 4 && !accepted; ++round) {
             const int wdx = lane & (ND - 1);
+#ifdef PX_OPT_PROFILE
+            if (lane == 0) sm.prof[6] += 1;
+#endif
             double lam_w = lam * 0.2;
             for (int i = 0; i < wdx; ++i) lam_w *= 5.0;
-            double L[D * (D + 1) / 2], y[D];                    // packed lower triangle: (i, j) at i (i + 1) / 2 + j; diagonal = 1 / l_jj
             bool ok = true;
+            // A = damped Hff (identity rows for fractions that are not free), rhs = -g_f
+            double A[M * (M + 1) / 2], y[M];                    // packed lower triangle: (i, j) at i (i + 1) / 2 + j
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                const bool fj = (fr >> j) & 1u;
-                const double hjj = fj ? H[j * PX_OPT_LDA + j] : 1.0;
-                double djj = hjj + (lam_w * fabs(hjj) + 1e-300), z = fj ? -g[j] : 0.0;
+            for (int p = 0; p < M; ++p) {
+                const bool fp = (fr >> p) & 1u;
 #pragma unroll
-                for (int k = 0; k < j; ++k) {
-                    const double ljk = L[j * (j + 1) / 2 + k];
-                    djj = fma(-ljk, ljk, djj);
-                    z = fma(-ljk, y[k], z);
+                for (int q = 0; q < p; ++q) A[p * (p + 1) / 2 + q] = (fp && ((fr >> q) & 1u)) ? H[p * PX_OPT_LDA + q] : 0.0;
+                const double hpp = fp ? H[p * PX_OPT_LDA + p] : 1.0;
+                A[p * (p + 1) / 2 + p] = hpp + (lam_w * fabs(hpp) + 1e-300);
+                y[p] = fp ? -g[p] : 0.0;
+            }
+            // eliminate the (scale, background) pair of every specimen
+            double i11[S], i12[S], i22[S], er[S], eb[S];        // D_s^-1 and D_s^-1 (g_r, g_b)
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const bool f_r = (fr >> (M + s)) & 1u, f_b = (fr >> (M + S + s)) & 1u;
+                const double h1 = f_r ? hrr[s] : 1.0, h2 = f_b ? hbb[s] : 1.0;
+                const double a = h1 + (lam_w * fabs(h1) + 1e-300), c = h2 + (lam_w * fabs(h2) + 1e-300);
+                const double bq = (f_r && f_b) ? hrb[s] : 0.0;
+                const double det = fma(a, c, -bq * bq);
+                if (!(det > 0.0)) ok = false;
+                const double idet = px_rcp_newton(ok ? det : 1.0);
+                i11[s] = c * idet; i12[s] = -bq * idet; i22[s] = a * idet;
+                const double gr = f_r ? g[M + s] : 0.0, gb = f_b ? g[M + S + s] : 0.0;
+                er[s] = fma(i11[s], gr, i12[s] * gb);
+                eb[s] = fma(i12[s], gr, i22[s] * gb);
+                double wu[M], wv[M], uu[M], vv[M];
+#pragma unroll
+                for (int p = 0; p < M; ++p) {
+                    const bool fp = (fr >> p) & 1u;
+                    uu[p] = (fp && f_r) ? H[(M + s) * PX_OPT_LDA + p] : 0.0;
+                    vv[p] = (fp && f_b) ? H[(M + S + s) * PX_OPT_LDA + p] : 0.0;
+                    wu[p] = fma(uu[p], i11[s], vv[p] * i12[s]);
+                    wv[p] = fma(uu[p], i12[s], vv[p] * i22[s]);
+                    y[p] = fma(wu[p], gr, fma(wv[p], gb, y[p]));
                 }
+#pragma unroll
+                for (int p = 0; p < M; ++p)
+#pragma unroll
+                    for (int q = 0; q <= p; ++q)
+                        A[p * (p + 1) / 2 + q] = fma(-wu[p], uu[q], fma(-wv[p], vv[q], A[p * (p + 1) / 2 + q]));
+            }
+            // right-looking Cholesky of A in place (diagonal <- 1 / l_jj), forward substitution alongside
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const double djj = A[j * (j + 1) / 2 + j];
                 if (!(djj > 0.0)) ok = false;
                 const double inv = rsqrt(ok ? djj : 1.0);
-                L[j * (j + 1) / 2 + j] = inv;
-                y[j] = z * inv;                                 // L z = -g alongside
+                A[j * (j + 1) / 2 + j] = inv;
+                y[j] *= inv;
 #pragma unroll
-                for (int i = j + 1; i < D; ++i) {
-                    double a = (fj && ((fr >> i) & 1u)) ? H[i * PX_OPT_LDA + j] : 0.0;
+                for (int i = j + 1; i < M; ++i) A[i * (i + 1) / 2 + j] *= inv;
 #pragma unroll
-                    for (int k = 0; k < j; ++k) a = fma(-L[i * (i + 1) / 2 + k], L[j * (j + 1) / 2 + k], a);
-                    L[i * (i + 1) / 2 + j] = a * inv;
+                for (int i = j + 1; i < M; ++i) {
+                    const double lij = A[i * (i + 1) / 2 + j];
+                    y[i] = fma(-lij, y[j], y[i]);
+#pragma unroll
+                    for (int k2 = j + 1; k2 <= i; ++k2) A[i * (i + 1) / 2 + k2] = fma(-lij, A[k2 * (k2 + 1) / 2 + j], A[i * (i + 1) / 2 + k2]);
                 }
             }
 #pragma unroll
-            for (int j = D - 1; j >= 0; --j) {                  // L^T x = z
+            for (int j = M - 1; j >= 0; --j) {                  // L^T x = z
                 double z = y[j];
 #pragma unroll
-                for (int k = j + 1; k < D; ++k) z = fma(-L[k * (k + 1) / 2 + j], y[k], z);
-                y[j] = z * L[j * (j + 1) / 2 + j];
+                for (int k2 = j + 1; k2 < M; ++k2) z = fma(-A[k2 * (k2 + 1) / 2 + j], y[k2], z);
+                y[j] = z * A[j * (j + 1) / 2 + j];
             }
             double vn[D];
 #pragma unroll
-            for (int i = 0; i < D; ++i) vn[i] = ((fr >> i) & 1u) ? fmax(sm.lo[i], v[i] + y[i]) : v[i];
+            for (int p = 0; p < M; ++p) vn[p] = ((fr >> p) & 1u) ? fmax(sm.lo[p], v[p] + y[p]) : v[p];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {                       // (dr, db) = -D^-1 (g_rb + C' df)
+                const bool f_r = (fr >> (M + s)) & 1u, f_b = (fr >> (M + S + s)) & 1u;
+                double cu = 0.0, cv = 0.0;
+#pragma unroll
+                for (int p = 0; p < M; ++p) {
+                    const bool fp = (fr >> p) & 1u;
+                    cu = fma((fp && f_r) ? H[(M + s) * PX_OPT_LDA + p] : 0.0, y[p], cu);
+                    cv = fma((fp && f_b) ? H[(M + S + s) * PX_OPT_LDA + p] : 0.0, y[p], cv);
+                }
+                const double dr = -(er[s] + fma(i11[s], cu, i12[s] * cv)), db = -(eb[s] + fma(i12[s], cu, i22[s] * cv));
+                vn[M + s] = f_r ? fmax(sm.lo[M + s], v[M + s] + dr) : v[M + s];
+                vn[M + S + s] = f_b ? fmax(sm.lo[M + S + s], v[M + S + s] + db) : v[M + S + s];
+            }
             const double qn = opt_q_scalar<M, S>(sm, vn);
             double qb = (ok && qn < qv) ? qn : __longlong_as_double(0x7ff0000000000000LL);        // best of the ladder: lowest value, then lowest damping
             int wb = wdx;
@@ -3389,23 +3459,14 @@ __device__ __forceinline__ void opt_store_reduced(const double (&acc)[N], int la
     }
 }
 
-// Asynchronous prefetch ring of the Gram pass (PX_OPT_ASYNC_MINMB <= MB): every thread copies the MB + 1 values of ITS
-// point of the tiles ahead with cp.async (global -> shared without passing through registers) and later reads back
-// exactly the slots it wrote, so no block barrier is involved and the L2 latency of the pattern reads is hidden behind
-// the arithmetic of the tiles in between -- with registers only for the one point being accumulated.
-#ifndef PX_OPT_ASYNC_MINMB
-#define PX_OPT_ASYNC_MINMB 99     // measured on c4 (MB = 7): 1.39 ms against 1.01 ms for the register path: off
-#endif
-// tiles in flight: four for the one-wave blocks of 256 threads (64 KB of ring at MB = 7, two blocks per SM), two where
-// four blocks of 128 threads share an SM or the mixture has many phases
-__host__ __device__ constexpr int opt_stages(int MB, int TPB) { return (TPB == 256 && MB <= 8) ? 4 : 2; }
-__host__ __device__ constexpr int opt_ring_doubles(int MB, int TPB) { return MB >= PX_OPT_ASYNC_MINMB ? opt_stages(MB, TPB) * (MB + 1) * TPB : 0; }
-__device__ __forceinline__ void px_cp_async8(double *dst_shared, const double *src_global) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
-}
-__device__ __forceinline__ void px_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void px_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
+// Gram pass: register loads, PIF points in flight per thread.  Three shared-memory feeds were built and measured in round
+// 2 and are NOT kept (numbers on c4, 256 candidates, B200): 8-byte cp.async per point in 256-point
+// tiles (1.39 ms against 1.01 ms: twice the LDGSTS instructions for the same bytes); cp.async.bulk + mbarrier ring, one 2 KB
+// row segment per copy (0.98 against 0.84 ms: a UBLKCP stalls the issuing warp ~136 cycles, 1090 cycles per 8-row tile
+// whoever issues it, with one or two CTAs per SM); 16-byte cp.async of point pairs in 512-point tiles (0.83 against 0.79 ms,
+// 0.96 with the two points of a pair interleaved: with 36 accumulators per thread at the 128-register cap the extra
+// pointers and the second point spill).  Cycle counters show why none helps: the pass is not waiting for L2 (wait on the
+// copies: 5 % of the pass), it is a chain of dependent instructions per warp at two to four warps per scheduler.
 template <int MB, int TPB>
 __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev st, BatchDev bt, OptParams op,
                                                                  double *solutions, double *opt_residuals) {
@@ -3437,8 +3498,9 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
         }
     }
     __syncthreads();
-    for (int it = 0; it <= op.outer; ++it) {
-        const double delta_rel = fmax(op.delta0 * pow(op.shrink, (double)it), op.delta_min);
+    double delta_pow = 1.0;                                 // shrink^it
+    for (int it = 0; it <= op.outer; ++it, delta_pow *= op.shrink) {
+        const double delta_rel = fmax(op.delta0 * delta_pow, op.delta_min);
         for (int s = 0; s < S; ++s) {
             const int X = st.spec_npts[s];
             const long long soff = st.spec_off[s];
@@ -3464,83 +3526,32 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_mixture_optimize(StaticDev s
             // PIF points in flight per thread: the loads of all of them are issued before the arithmetic (few phases
             // leave registers for more points: the pass is bound by the latency of these loads)
             constexpr int PIF = MB <= 2 ? 8 : MB <= 4 ? 4 : 2;
-            auto accumulate = [&](const double (&phi)[PIF][MB], const double (&o)[PIF], const bool (&on)[PIF]) {
+            auto one_point = [&](const double (&phi)[MB], const double o) {
+                double calc = 0.0;
 #pragma unroll
-                for (int u = 0; u < PIF; ++u) {
-                    if (!on[u]) continue;
-                    double calc = 0.0;
+                for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[p], calc);
+                const double r = o - calc;
+                // weight of the majoriser 1 / max(|r|, delta): the 20-bit reciprocal of the special-function unit
+                // is enough (any positive weight majorises, the objective itself is summed exactly) and keeps
+                // the division's Newton steps off the fp64 pipe
+                double w;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(w) : "d"(fmax(fabs(r), delta)));
+                acc[NACC - 1] += fabs(r);
+                int e = 0;
 #pragma unroll
-                    for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[u][p], calc);
-                    const double r = o[u] - calc;
-                    // weight of the majoriser 1 / max(|r|, delta): the 20-bit reciprocal of the special-function unit
-                    // is enough (any positive weight majorises, the objective itself is summed exactly) and keeps
-                    // the division's Newton steps off the fp64 pipe
-                    double w;
-                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(w) : "d"(fmax(fabs(r), delta)));
-                    acc[NACC - 1] += fabs(r);
-                    int e = 0;
+                for (int p = 0; p < MB; ++p) {
+                    const double wp = w * phi[p];
+                    acc[NG + p] = fma(wp, o, acc[NG + p]);
 #pragma unroll
-                    for (int p = 0; p < MB; ++p) {
-                        const double wp = w * phi[u][p];
-                        acc[NG + p] = fma(wp, o[u], acc[NG + p]);
-#pragma unroll
-                        for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[u][q], acc[e]);
-                    }
+                    for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[q], acc[e]);
                 }
             };
-            if constexpr (MB >= PX_OPT_ASYNC_MINMB) {
-                extern __shared__ __align__(16) double opt_ring[];      // [stage][MB + 1][TPB]
-                constexpr int PX_OPT_STAGES = opt_stages(MB, TPB);
-                const int npts = Z * X, ntile = (npts + TPB - 1) / TPB;
-                auto issue = [&](int tile) {                            // this thread's point of `tile` into its ring slots
-                    if (tile < ntile) {
-                        int i = tile * TPB + tid;
-                        if (i >= npts) i = npts - 1;                    // a legal address; the point is masked below
-                        const int z = i / X, x = i - z * X;
-                        double *slot = opt_ring + (size_t)(tile % PX_OPT_STAGES) * (MB + 1) * TPB + tid;
+            auto accumulate = [&](const double (&phi)[PIF][MB], const double (&o)[PIF], const bool (&on)[PIF]) {
 #pragma unroll
-                        for (int p = 0; p < M; ++p) px_cp_async8(slot + p * TPB, I + ((long long)p * Z + z) * X + x);
-                        px_cp_async8(slot + M * TPB, corr + x);
-                        px_cp_async8(slot + MB * TPB, obs + (long long)z * X + x);
-                    }
-                    px_cp_async_commit();                               // (possibly empty: the group count stays in step)
-                };
-#pragma unroll
-                for (int t = 0; t < PX_OPT_STAGES - 1; ++t) issue(t);
-                for (int tile = 0; tile < ntile; ++tile) {
-                    issue(tile + PX_OPT_STAGES - 1);
-                    const int i = tile * TPB + tid;
-                    const bool live = i < npts && sel[i % X] != 0;      // (the mask byte is an ordinary cached load)
-                    px_cp_async_wait<PX_OPT_STAGES - 1>();
-                    const double *slot = opt_ring + (size_t)(tile % PX_OPT_STAGES) * (MB + 1) * TPB + tid;
-                    double phi[1][MB], o[1];
-                    bool on[1] = {live};
-#pragma unroll
-                    for (int p = 0; p < MB; ++p) phi[0][p] = slot[p * TPB];
-                    o[0] = slot[MB * TPB];
-                    // (PIF of the register paths is the array extent here: one point at a time)
-                    {
-                        if (on[0]) {
-                            double calc = 0.0;
-#pragma unroll
-                            for (int p = 0; p < MB; ++p) calc = fma(theta[p], phi[0][p], calc);
-                            const double r = o[0] - calc;
-                            double w;
-                            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(w) : "d"(fmax(fabs(r), delta)));
-                            acc[NACC - 1] += fabs(r);
-                            int e = 0;
-#pragma unroll
-                            for (int p = 0; p < MB; ++p) {
-                                const double wp = w * phi[0][p];
-                                acc[NG + p] = fma(wp, o[0], acc[NG + p]);
-#pragma unroll
-                                for (int q = p; q < MB; ++q, ++e) acc[e] = fma(wp, phi[0][q], acc[e]);
-                            }
-                        }
-                    }
-                }
-                px_cp_async_wait<0>();
-            } else if constexpr (MB <= PX_OPT_PTR_MB) {
+                for (int u = 0; u < PIF; ++u)
+                    if (on[u]) one_point(phi[u], o[u]);
+            };
+            if constexpr (MB <= PX_OPT_PTR_MB) {
                 // few phases: the pass is bound by instruction issue, not by the fp64 pipe.  Full groups of PIF points
                 // read at constant offsets from one running pointer per array (no index arithmetic per load); the
                 // ragged end of the pattern goes through the same body with clamped offsets.

@@ -355,14 +355,10 @@ static int launch_optimize(pyxrd_ctx *ctx, const OptParams &op) {
     int tpb = ctx->bt.K <= 2 * ctx->sm_count ? 256 : 128;
     if (ctx->opt_tpb) tpb = ctx->opt_tpb;
     if (tpb == 256) {
-        const size_t ring = sizeof(double) * opt_ring_doubles(MB, 256);
-        if (ring) CK(cudaFuncSetAttribute(k_mixture_optimize<MB, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
-        k_mixture_optimize<MB, 256><<<ctx->bt.K, 256, ring, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
+        k_mixture_optimize<MB, 256><<<ctx->bt.K, 256, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
                                                                            ctx->d_optres.as<double>());
     } else {
-        const size_t ring = sizeof(double) * opt_ring_doubles(MB, 128);
-        if (ring) CK(cudaFuncSetAttribute(k_mixture_optimize<MB, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
-        k_mixture_optimize<MB, 128><<<ctx->bt.K, 128, ring, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
+        k_mixture_optimize<MB, 128><<<ctx->bt.K, 128, 0, ctx->stream>>>(ctx->st, ctx->bt, op, ctx->d_sol.as<double>(),
                                                                            ctx->d_optres.as<double>());
     }
     LAUNCH_CHECK("k_mixture_optimize");

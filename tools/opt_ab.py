@@ -18,8 +18,7 @@ from pyxrd_b200.runtime import default_context  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "c4"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 variants = [json.loads(a) for a in sys.argv[3:]] or [{}]
-DEFAULTS = {"optimizer_lane_solver": 4, "optimizer_threads": 0, "optimizer_newton_tol": 1e-5, "optimizer_single_from": 0,
-            "optimizer_gram_tma": 1}
+DEFAULTS = {"optimizer_lane_solver": 4, "optimizer_threads": 0, "optimizer_newton_tol": 1e-5, "optimizer_single_from": 0}
 cfg = syn.CONFIGS[name]
 truth, mixes = cfg.truth(), cfg.population(2024, K)
 
@@ -54,7 +53,7 @@ with ctx.lock:
     ctx.set_static(static, force=True)
     ctx.set_batch(batch)
     ctx.compute_intensities()
-    best, _ = run(96, 8, {"optimizer_lane_solver": 0, "optimizer_newton_tol": 1e-13, "optimizer_gram_tma": 0}, reps=1)
+    best, _ = run(96, 8, {"optimizer_lane_solver": 0, "optimizer_newton_tol": 1e-13}, reps=1)
     for options in variants:
         r, dt = run(32, 2, options)
         best = np.minimum(best, r)

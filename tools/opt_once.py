@@ -1,4 +1,4 @@
-"""one optimiser call on a bench population (argv: candidates, configuration name; default 256 c4) (profiling aid: build with -DPX_OPT_PROFILE for cycle counters)"""
+"""one optimiser call on a bench population (argv: candidates, configuration name, JSON dict of pyxrd_set_option keys; default 256 c4) (profiling aid: build with -DPX_OPT_PROFILE for cycle counters)"""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,6 +15,10 @@ def calc_total(mix):
 syn.attach_observed(mixes, truth, calc_total)
 static, batch = pack_population(mixes)
 ctx = default_context(0)
+if len(sys.argv) > 3:
+    import json
+    for key, value in json.loads(sys.argv[3]).items():
+        ctx.set_option(key, value)
 with ctx.lock:
     ctx.set_static(static, force=True)
     ctx.set_batch(batch)
