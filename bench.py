@@ -227,6 +227,9 @@ class Env(object):
         self.rank, self.world, self.local_rank = rank, world, local_rank
         from pyxrd_b200.runtime import default_context
         self.ctx = default_context(local_rank)
+        for item in getattr(args, "option", []):
+            key, _, value = item.partition("=")
+            self.ctx.set_option(key, float(value))
         self.stream = torch.cuda.Stream()
         self.ctx.set_stream(self.stream.cuda_stream)
         self.device = torch.device("cuda", local_rank)
@@ -779,6 +782,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[4] population sweep")
     ap.add_argument("--no-configs", action="store_true", help="skip the table of the other configurations (N = 1)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
+                    help="pyxrd_set_option applied to the context before the measurements (experiments; repeatable)")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
                     help="exchange of the residual rows at N > 1: one NCCL all-gather (default), or the library's stores into "
                          "peer memory + a symmetric-memory barrier (measured equal at 2 GPUs, 2 %% slower at 8)")

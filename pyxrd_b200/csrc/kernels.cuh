@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <type_traits>
 
 #define PX_TPB 128          // threads (= 2-theta points) per block in the phase kernels
@@ -156,6 +157,12 @@ struct BatchDev {
     int *phase_valid;                // [NP]   derived: valid_probs (host flag, or the device model's verdict)
     // derived by k_phase_planes: planes of a phase that sit at the same z in several components, listed once
     int acap;                        // row stride of the three tables = most atoms of any phase
+    // phase images (k_phase_image): everything k_phase_small stages per block, laid out once per generation so that
+    // the staging is ONE round of independent loads instead of a chain of six dependent ones (+ three divisions):
+    //   [PX_IMG_HDR header words][plane_arg AE][atom_po 2 AE][plane_end AE / 2][useg AE / 2][P R^2][WG G R] ... [coef ncap]
+    double *phase_img;               // [NP][img_stride]
+    int img_stride, img_ae, img_mcap;   // words per image; acap rounded up to even; words reserved for P and WG
+    int img_ncopy;                   // coefficients a block copies (set per launch: the launch's shared-memory capacity)
     int *ph_nu;                      // [NP]        number of distinct planes
     double *ph_uz;                   // [NP][acap]  z of distinct plane u
     int *ph_uend;                    // [NP][acap]  one past the last segment of distinct plane u
@@ -963,21 +970,27 @@ __global__ void k_leaf_csds(const double *pd, int nmin, int nmax, double *arr, d
 // phase kernels: shared-memory staging of one phase parameter block
 // ---------------------------------------------------------------------------------
 
+#define PX_IMG_HDR 74        // 8-byte words of the header block of PhaseSmem = first words of a phase image
 struct PhaseSmem {          // header living at the start of dynamic shared memory
+    // ---- header block: PX_IMG_HDR words, copied verbatim from the phase image (k_phase_image) by k_phase_small ----
+    double px[4];           // mean, absolute scale, ntop, phase flags (phase_x + phase_i[4])
+    double lpf_all[8][4];   // per specimen: lpf_q, lpf_k1, lpf_k2, lpf_pol (lpf_consts)
+    double comp_d001[8];
+    double comp_delta[8];
+    long long comp_tab[8];  // offset of the component's layer class inside the layer table, -1: no table (all planes listed)
     int comp_first[8];      // first plane (local index) of component c
     int comp_count[8];      // number of planes of component c
     int comp_a0[8];         // first atom (local index) of the first listed plane of component c
-    long long comp_tab[8];  // offset of the component's layer class inside the layer table, -1: no table (all planes listed)
-    double comp_d001[8];
-    double comp_delta[8];
+    int n_atoms, n_u, pad[2];
+    // ---- per block ----
+    double lpf_q, lpf_k1, lpf_k2, lpf_pol;   // Lorentz-polarisation constants of this (phase, specimen), see lpf_point
     double plane_arg[PX_MAX_ATOMS];  // (2 pi) * z of a plane = run of consecutive atoms with equal z
     int plane_end[PX_MAX_ATOMS];     // one past the last atom (local index) of the plane
     double2 atom_po[PX_MAX_ATOMS];   // .x = pn (0 for a None atom type), .y = bit pattern of the ASF-table offset type * sumX
     int useg[PX_MAX_ATOMS];          // distinct-plane mode (k_phase_small): plane_arg / plane_end describe DISTINCT planes of the
                                      // whole phase, plane_end[u] = one past the last entry of useg that belongs to plane u
-    int n_atoms, n_u, pad[2];
-    double lpf_q, lpf_k1, lpf_k2, lpf_pol;   // Lorentz-polarisation constants of this (phase, specimen), see lpf_point
 };
+static_assert(offsetof(PhaseSmem, lpf_q) == PX_IMG_HDR * 8, "header block of PhaseSmem and PX_IMG_HDR disagree");
 
 // Lorentz-polarisation factor for one point (goniometer.py:20-34)
 __device__ __forceinline__ double lpf_value(double st, double c2t2, double sigma_star, double Ss, double Ss2, double pol) {
@@ -991,12 +1004,15 @@ __device__ __forceinline__ double lpf_value(double st, double c2t2, double sigma
 // multiplications by reciprocals taken once per block, and 1 / sin(theta) is a static table
 // (differs from lpf_value by rounding only, ~2 ulp).
 //   Q = lpf_q / st, lpf_q = S / (sqrt8 sigma);  T = erf(Q) lpf_k1 - 2 st (1 - exp(-Q^2)) lpf_k2
-__device__ __forceinline__ void lpf_setup(PhaseSmem *ps, double sigma_star, const double *derived_s) {
+__device__ __forceinline__ void lpf_consts(double sigma_star, const double *derived_s, double *out4) {
     const double sig = fmax(sigma_star, 1e-18), Ss = derived_s[1], Ss2 = derived_s[2];
-    ps->lpf_q = Ss / (PX_SQRT8 * sig);
-    ps->lpf_k1 = PX_SQRT2PI / ((2.0 * sig) * Ss);
-    ps->lpf_k2 = 1.0 / Ss2;
-    ps->lpf_pol = derived_s[0];
+    out4[0] = Ss / (PX_SQRT8 * sig);
+    out4[1] = PX_SQRT2PI / ((2.0 * sig) * Ss);
+    out4[2] = 1.0 / Ss2;
+    out4[3] = derived_s[0];
+}
+__device__ __forceinline__ void lpf_setup(PhaseSmem *ps, double sigma_star, const double *derived_s) {
+    lpf_consts(sigma_star, derived_s, &ps->lpf_q);
 }
 // erf(Q) and exp(-Q^2) come from the interval tables above (absolute error 1.5e-16 / 3.7e-16); the N points of a thread
 // run in lock step, neighbouring points fall into the same or the next interval (one cache line per warp and step)
@@ -1335,6 +1351,65 @@ __device__ __forceinline__ bool phase_is_invalid(const BatchDev &bt, int pb, int
     return true;
 }
 
+// ---------------------------------------------------------------------------------
+// phase images: warp per phase, once per generation (after the prologue kernels).  The block runs the staging code the
+// phase kernels run per block (load_phase_lists: job -> phase -> component list -> components -> atoms, a chain of six
+// dependent global loads; the Lorentz-polarisation constants with three divisions; WG from W) ONCE and lays the result
+// out contiguously (BatchDev::phase_img).  A block of k_phase_small then fills its shared memory with one round of
+// independent loads.  ncu on c2 before this: 20 % of the warps' time went into the staging code of a block (long
+// scoreboard on the chain, math-pipe throttle on the divisions) for 4 % of the executed instructions.
+// ---------------------------------------------------------------------------------
+// Two parts, each at the end of the prologue chain it depends on (they run side by side on two streams):
+//   PART 0  lists, components, Lorentz-polarisation constants   after k_component_z -> k_phase_planes
+//   PART 1  mean / absolute scale / ntop / flags, P, WG, coefficients   after k_probabilities -> k_phase_prologue
+template <int PART>
+__global__ void __launch_bounds__(32) k_phase_image(StaticDev st, BatchDev bt) {
+    const int pb = blockIdx.x, lane = threadIdx.x;
+    const int *pi = bt.phase_i + pb * 8;
+    if (!(pi[4] & 1) || (pi[4] & 8)) return;                 // no components / raw pattern: no phase kernel reads an image
+    const int G = pi[0], R = pi[1];
+    double *img = bt.phase_img + (long long)pb * bt.img_stride;
+    const int AE = bt.img_ae;
+    double *pa = img + PX_IMG_HDR;
+    if constexpr (PART == 0) {
+        __shared__ PhaseSmem ps;
+        if (G > 1) load_phase_lists<true>(bt, pb, G, &ps, st.sumX, st.derived);
+        else load_phase_lists<false>(bt, pb, G, &ps, st.sumX, st.derived);
+        if (lane < st.S && lane < 8) lpf_consts(bt.phase_d[pb * 8], st.derived + lane * 8, ps.lpf_all[lane]);
+        __syncwarp();
+        for (int i = 4 + lane; i < PX_IMG_HDR; i += 32) img[i] = reinterpret_cast<const double *>(&ps)[i];
+        double2 *po = reinterpret_cast<double2 *>(pa + AE);
+        int *pe = reinterpret_cast<int *>(pa + 3 * AE), *us = pe + AE;
+        const int na = ps.n_atoms;
+        for (int i = lane; i < AE; i += 32) {                // (entries past the phase's counts are never read: zeros)
+            const bool in = i < na;
+            pa[i] = in ? ps.plane_arg[i] : 0.0;
+            po[i] = in ? ps.atom_po[i] : make_double2(0.0, 0.0);
+            pe[i] = in ? ps.plane_end[i] : 0;
+            us[i] = (in && G > 1) ? ps.useg[i] : 0;
+        }
+    } else {
+        if (lane < 3) img[lane] = bt.phase_x[pb * 4 + lane];
+        if (lane == 3) img[3] = (double)pi[4];
+        double *mat = pa + 4 * AE;
+        if (R * R + G * R <= bt.img_mcap) {
+            const double *W = bt.matrices + pi[6];
+            const double *P = W + R * R;
+            const int REPS = R / G;
+            for (int i = lane; i < R * R; i += 32) mat[i] = P[i];
+            for (int i = lane; i < G * R; i += 32) {         // WG[c][K] = sum_{J in c} W[J][K]
+                const int c = i / R, K = i % R;
+                double acc = 0.0;
+                for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
+                mat[R * R + i] = acc;
+            }
+        }
+        double *cf = mat + bt.img_mcap;
+        const double *coef = bt.coef + (long long)pb * bt.ncap;
+        for (int i = lane; i < bt.ncap; i += 32) cf[i] = coef[i];
+    }
+}
+
 // helpers of the in-place structured series (k_phase_small, STRUCT = 1): states are digit strings (i1 .. iD) in base
 // G, R = G^D; px_rotl moves the leading digit to the end, px_rot applies it s times
 template <int V> struct px_int { static constexpr int value = V; };
@@ -1374,28 +1449,33 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     const int X = st.spec_npts[s];
     const int xblock = blockIdx.y * (TPB * PPT * TILES);
     if (xblock >= X || phase_is_invalid(bt, pb, job, X, xblock, TPB * PPT * TILES)) return;
-    const int *pi = bt.phase_i + pb * 8;
-    const double *px = bt.phase_x + pb * 4;
-    const int ntop = (int)px[2];
-    const double mean = px[0], abs_scale = px[1];
-    const int flags = pi[4];
-
     constexpr bool DISTINCT = G > 1;        // one component: nothing to share between components
-    load_phase_lists<DISTINCT>(bt, pb, G, ps, st.sumX, st.derived + s * 8);
     {
-        const double *W = bt.matrices + pi[6];
-        const double *P = W + R * R;
-        for (int i = threadIdx.x; i < R * R; i += TPB) sP[i] = P[i];
-        for (int i = threadIdx.x; i < G * R; i += TPB) {          // WG[c][K] = sum_{J in c} W[J][K]
-            const int c = i / R, K = i % R;
-            double acc = 0.0;
-            for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
-            sWG[i] = acc;
+        // staging from the phase image (k_phase_image): one round of independent loads
+        const double *img = bt.phase_img + (long long)pb * bt.img_stride;
+        const int AE = bt.img_ae;
+        double *hdr = reinterpret_cast<double *>(ps);
+        for (int i = threadIdx.x; i < PX_IMG_HDR; i += TPB) hdr[i] = img[i];
+        if (threadIdx.x < 4) (&ps->lpf_q)[threadIdx.x] = img[4 + 4 * s + threadIdx.x];       // lpf_all[s]
+        const double *pa = img + PX_IMG_HDR;
+        const double2 *po = reinterpret_cast<const double2 *>(pa + AE);
+        const int *pe = reinterpret_cast<const int *>(pa + 3 * AE), *us = pe + AE;
+        for (int i = threadIdx.x; i < AE; i += TPB) {
+            ps->plane_arg[i] = pa[i];
+            ps->atom_po[i] = po[i];
+            ps->plane_end[i] = pe[i];
+            if constexpr (DISTINCT) ps->useg[i] = us[i];
         }
-        const double *coef = bt.coef + (long long)pb * bt.ncap;
-        for (int i = threadIdx.x; i <= ntop; i += TPB) sCoef[i] = coef[i];
+        const double *mat = pa + 4 * AE;
+        for (int i = threadIdx.x; i < R * R; i += TPB) sP[i] = mat[i];
+        for (int i = threadIdx.x; i < G * R; i += TPB) sWG[i] = mat[R * R + i];
+        const double *cf = mat + bt.img_mcap;
+        for (int i = threadIdx.x; i < bt.img_ncopy; i += TPB) sCoef[i] = cf[i];
     }
     __syncthreads();
+    const int ntop = (int)ps->px[2];
+    const double mean = ps->px[0], abs_scale = ps->px[1];
+    const int flags = (int)ps->px[3];
 
 #pragma unroll 1
     for (int x0 = xblock; x0 < xblock + TPB * PPT * TILES; x0 += TPB * PPT) {

@@ -143,7 +143,7 @@ struct pyxrd_ctx {
     DevBuf d_tmpl;           // template candidate + solution vectors + binding table of a device-expanded population
     PinBuf h_tmpl;
     const int *jobids_dev = nullptr;   // inside d_blob
-    DevBuf d_ph_nu, d_ph_uz, d_ph_uend, d_ph_useg, d_partial;
+    DevBuf d_ph_nu, d_ph_uz, d_ph_uend, d_ph_useg, d_partial, d_phase_img;
     DevBuf d_comp_ilp, d_layer_tab;
     DevBuf d_atom_z, d_atom_plane, d_comp_np, d_phase_x, d_phase_valid, d_coef, d_int, d_int2, d_scaled, d_tot, d_res;
     int residual_method = PYXRD_RESIDUAL_RP;   // settings.RESIDUAL_METHOD (mixture.py:22-27,89)
@@ -258,7 +258,9 @@ int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_
     const size_t smem = small_smem(R, G, rc.max_ntop_cap);
     if (set_smem(ctx, k_phase_small<R, G, PPT, TPB, MINB, STRUCT, TILES>, smem)) return 1;
     dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + TPB * PPT * TILES - 1) / (TPB * PPT * TILES)));
-    k_phase_small<R, G, PPT, TPB, MINB, STRUCT, TILES><<<grid, TPB, smem, ctx->stream>>>(ctx->st, bt, jobs_dev);
+    BatchDev b2 = bt;
+    b2.img_ncopy = std::min(bt.ncap, rc.max_ntop_cap + 2);      // what the launch's shared memory holds
+    k_phase_small<R, G, PPT, TPB, MINB, STRUCT, TILES><<<grid, TPB, smem, ctx->stream>>>(ctx->st, b2, jobs_dev);
     LAUNCH_CHECK("k_phase_small");
     return 0;
 }
@@ -418,7 +420,7 @@ void pyxrd_destroy(pyxrd_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_npts, &ctx->d_off, &ctx->d_gonio, &ctx->d_derived, &ctx->d_theta, &ctx->d_sin, &ctx->d_invsin, &ctx->d_stl,
                       &ctx->d_c2t2, &ctx->d_corr, &ctx->d_asf, &ctx->d_nwl, &ctx->d_wlfirst, &ctx->d_wloff, &ctx->d_wlfrac,
                       &ctx->d_wlidx, &ctx->d_wlhi, &ctx->d_wllo, &ctx->d_obs, &ctx->d_sel, &ctx->d_atypes, &ctx->d_stlov, &ctx->d_blob, &ctx->d_tmpl,
-                      &ctx->d_partial, &ctx->d_ph_nu, &ctx->d_ph_uz, &ctx->d_ph_uend, &ctx->d_ph_useg, &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
+                      &ctx->d_partial, &ctx->d_phase_img, &ctx->d_ph_nu, &ctx->d_ph_uz, &ctx->d_ph_uend, &ctx->d_ph_useg, &ctx->d_atom_z, &ctx->d_atom_plane, &ctx->d_comp_np, &ctx->d_phase_x, &ctx->d_phase_valid, &ctx->d_coef, &ctx->d_int, &ctx->d_scaled, &ctx->d_tot,
                       &ctx->d_res, &ctx->d_comp_ilp, &ctx->d_layer_tab, &ctx->d_int2, &ctx->d_selpos, &ctx->d_selcount, &ctx->d_leaf_a, &ctx->d_leaf_b, &ctx->d_leaf_c, &ctx->d_leaf_d, &ctx->d_sol, &ctx->d_optres};
     for (DevBuf *b : bufs) b->release();
     ctx->h_blob.release();
@@ -861,6 +863,17 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
     bt.ph_uz = ctx->d_ph_uz.as<double>();
     bt.ph_uend = ctx->d_ph_uend.as<int>();
     bt.ph_useg = ctx->d_ph_useg.as<int>();
+    {
+        // phase images (k_phase_image): capacities of this batch
+        int mcap = 2;
+        for (const RankClass &rc : ctx->classes) mcap = std::max(mcap, rc.rank * rc.rank + rc.G * rc.rank);
+        bt.img_ae = (acap + 1) & ~1;
+        bt.img_mcap = (mcap + 1) & ~1;
+        bt.img_stride = PX_IMG_HDR + 4 * bt.img_ae + bt.img_mcap + ((bt.ncap + 1) & ~1);
+        bt.img_ncopy = 0;
+        CK(ctx->d_phase_img.ensure(sizeof(double) * (size_t)bt.img_stride * std::max(NP, 1)));
+        bt.phase_img = ctx->d_phase_img.as<double>();
+    }
     bt.job_pb = reinterpret_cast<const int *>(dev(P_JOB_PB));
     bt.job_spec = reinterpret_cast<const int *>(dev(P_JOB_SPEC));
     bt.job_out = reinterpret_cast<const long long *>(dev(P_JOB_OUT));
@@ -899,6 +912,8 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
         LAUNCH_CHECK("k_probabilities");
         k_phase_prologue<<<(NP + PX_PROLOGUE_WARPS - 1) / PX_PROLOGUE_WARPS, 32 * PX_PROLOGUE_WARPS, 0, main_stream>>>(bt);
         LAUNCH_CHECK("k_phase_prologue");
+        k_phase_image<1><<<NP, 32, 0, main_stream>>>(st, bt);
+        LAUNCH_CHECK("k_phase_image");
     }
     cudaStream_t z_stream = side ? ctx->class_stream[0] : main_stream;
     if (NC > 0) {
@@ -908,6 +923,8 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
     if (NP > 0) {
         k_phase_planes<<<NP, 32, 0, z_stream>>>(bt);
         LAUNCH_CHECK("k_phase_planes");
+        k_phase_image<0><<<NP, 32, 0, z_stream>>>(st, bt);
+        LAUNCH_CHECK("k_phase_image");
     }
     if (need_tables) {
         dim3 grid((unsigned)((st.sumX + 127) / 128), (unsigned)z.n_classes);
