@@ -251,7 +251,10 @@ int pyxrd_compute_intensities(pyxrd_ctx *ctx);
                                  * needs residuals [K][1+S]); pyxrd_read_totals fails afterwards */
 int pyxrd_compute_residuals(pyxrd_ctx *ctx, int flags);
 /* pyxrd_compute_intensities + pyxrd_compute_residuals as one call (calculate_mixture for the resident batch); the last
- * pass of the wavelength distribution runs inside the residual kernel (the patterns are not read a second time) */
+ * pass of the wavelength distribution runs inside the residual kernel (the patterns are not read a second time); where
+ * the gathers of the distribution stay within 128 points (K-alpha doublets) ALL passes run inside it.  With
+ * PYXRD_RESIDUALS_ONLY alone (Rp) that kernel does not store the final phase patterns either: afterwards
+ * pyxrd_read_intensities / pyxrd_compute_residuals / pyxrd_optimize fail until the patterns are computed again. */
 int pyxrd_compute_all(pyxrd_ctx *ctx, int flags);
 
 /* Which pattern residual pyxrd_compute_residuals / pyxrd_evaluate_host report (settings.py:27-32,

@@ -2435,6 +2435,184 @@ __global__ void __launch_bounds__(PX_RES_TPB, PX_RES_MINB) k_mixture_residual(St
     }
 }
 
+// ---------------------------------------------------------------------------------
+// ALL passes of the wavelength distribution + mixture + residual in one kernel (pyxrd_compute_all where the gathers of
+// the distribution stay local).  A gather of pass j reaches at most r-_j points down and r+_j points up (Cu K-alpha2
+// against K-alpha1 on the c2 grid: 21 points down), so the final value of a point depends on the raw pattern inside a
+// window of HL = sum r-_j points below and HR = sum r+_j points above it (the host takes the reaches from the abscissa
+// tables, pyxrd_set_static).  A block stages the raw pattern of its tile + halo in shared memory once per (z, phase),
+// runs the passes between two shared buffers -- the operations of k_wavelength_pass / k_mixture_residual<true> in their
+// order, bit for bit the same patterns -- and feeds the tile straight into the mixture sum.  The patterns cross HBM once
+// (read, + halo) instead of four times (pass: read + write, residual: read + write); with PYXRD_RESIDUALS_ONLY nothing is
+// written but the tile sums.  c2 (2048 candidates): wavelength + residual 168 -> see DESIGN.md section 3.
+// ---------------------------------------------------------------------------------
+#define PX_FUSE_TPB 256
+#define PX_FUSE_T 512                  // points of a tile
+#define PX_FUSE_HMAX 128               // HL + HR the shared buffers hold; wider distributions keep the pass kernels
+#define PX_FUSE_SLOTS ((PX_FUSE_T + PX_FUSE_HMAX + PX_FUSE_TPB - 1) / PX_FUSE_TPB)
+#define PX_FUSE_MAXPASS 4
+#ifndef PX_FUSE_MINB
+#define PX_FUSE_MINB 4
+#endif
+#ifndef PX_FUSE_CPB
+#define PX_FUSE_CPB 8                  // candidates a block walks for its tile (grid.x = ceil(candidates / PX_FUSE_CPB))
+#endif
+// A block owns one tile of one specimen for PX_FUSE_CPB consecutive candidates: the abscissa tables of the tile (index of
+// the upper neighbour and the two weights, per pass) are candidate-invariant and fetched once into registers; the raw
+// pattern of the NEXT (candidate, z, phase) is prefetched into registers while the current one goes through the passes
+// in shared memory, so that no global latency sits between the stages of a pattern.
+template <int NPASS>
+__global__ void __launch_bounds__(PX_FUSE_TPB, PX_FUSE_MINB) k_patterns_residual(StaticDev st, BatchDev bt, int k0, int k1, int want_scaled, int want_totals,
+                                                                  int HL, int HR, const double *__restrict__ src, double *__restrict__ dst,
+                                                                  double *__restrict__ partial) {
+    constexpr int NOUT = PX_FUSE_T / PX_FUSE_TPB, NBUF = PX_FUSE_SLOTS * PX_FUSE_TPB;    // every slot of every thread has a buffer entry
+    const int s = blockIdx.z, tile = blockIdx.y, tid = threadIdx.x;
+    const int kb = k0 + blockIdx.x * PX_FUSE_CPB, ke = min(k1, kb + PX_FUSE_CPB);
+    const int X = st.spec_npts[s], Z = st.Z, M = bt.M, S = st.S;
+    const int x0 = tile * PX_FUSE_T;
+    __shared__ double bufR[NBUF], bufA[NPASS > 1 ? NBUF : 1], bufB[NPASS > 2 ? NBUF : 1];
+    __shared__ double red[32];
+    if (x0 >= X) {                                              // (specimens shorter than the longest one)
+        if (tid == 0)
+            for (int k = kb; k < ke; ++k) partial[((long long)(k - k0) * S + s) * gridDim.y + tile] = 0.0;
+        return;
+    }
+    const int W = PX_FUSE_T + HL + HR, y0 = x0 - HL;
+    const long long soff = st.spec_off[s];
+    const long long pstride = (long long)Z * X;
+    const int nwl = st.spec_nwl[s];
+    const long long off0 = st.wl_off[s];
+    const double *wf = st.wl_fraction + st.wl_first[s];
+    // Tables of a pass at a buffer position: index of the upper neighbour INSIDE the buffer and the two weights.  No
+    // neighbour (outside the pattern, fill value, a margin position nobody reads): index 1 with weights 0 -- the pass is
+    // then v + (0 a + 0 b) = v without a branch (the same value as the pass kernels give; the sign of a zero may differ).
+    auto table = [&](int j, int y, int &g, double &wh, double &wl) {
+        g = 1; wh = 0.0; wl = 0.0;
+        if (j < nwl && y >= 0 && y < X) {
+            const long long off = off0 + (long long)j * X + y;
+            const int hi = __ldg(st.wl_index + off);
+            if (hi >= 0 && hi - 1 >= y0 && hi < y0 + W) { g = hi - y0; wh = __ldg(st.wl_w_hi + off); wl = __ldg(st.wl_w_lo + off); }
+        }
+    };
+    int g0[PX_FUSE_SLOTS], gL[NOUT];
+    double wh0[PX_FUSE_SLOTS], wl0[PX_FUSE_SLOTS], whL[NOUT], wlL[NOUT];
+    unsigned in_mask = 0u;                                      // bit u: buffer position tid + u TPB lies inside the pattern
+#pragma unroll
+    for (int u = 0; u < PX_FUSE_SLOTS; ++u) {
+        const int b = tid + u * PX_FUSE_TPB, y = y0 + b;
+        table(0, b < W ? y : -1, g0[u], wh0[u], wl0[u]);
+        if (b < W && y >= 0 && y < X) in_mask |= 1u << u;
+    }
+    // tile points of this thread: observed, background, mask (candidate-invariant when Z == 1; else read per z below)
+    double corr_x[NOUT];
+    bool live[NOUT], inside[NOUT];
+#pragma unroll
+    for (int u = 0; u < NOUT; ++u) {
+        const int x = x0 + tid + u * PX_FUSE_TPB;
+        inside[u] = x < X;
+        table(NPASS - 1, inside[u] ? x : -1, gL[u], whL[u], wlL[u]);
+        corr_x[u] = inside[u] ? st.corr[soff + x] : 0.0;
+        live[u] = inside[u] && st.selected[soff + x] != 0;
+    }
+    const double *obs = st.observed + (long long)Z * soff + x0 + tid;
+    const double f0 = 0 < nwl ? wf[0] : 0.0, fL = NPASS - 1 < nwl ? wf[NPASS - 1] : 0.0;
+    // the patterns this block walks: candidates kb .. ke-1, per candidate z, then phase; the raw values of the NEXT pattern
+    // are prefetched into registers while the current one goes through the passes (pointer arithmetic without divisions)
+    const long long spec_base = (long long)M * Z * soff;
+    double raw[PX_FUSE_SLOTS];
+    auto prefetch = [&](const double *pat) {                    // pat: the pattern's point y0 + tid
+#pragma unroll
+        for (int u = 0; u < PX_FUSE_SLOTS; ++u) raw[u] = ((in_mask >> u) & 1u) ? pat[u * PX_FUSE_TPB] : 0.0;
+    };
+    const double *pat_next = src + (long long)kb * bt.cand_stride + spec_base + y0 + tid;
+    prefetch(pat_next);
+    for (int k = kb; k < ke; ++k) {
+        const long long cbase = (long long)k * bt.cand_stride + spec_base + x0 + tid;
+        double *O = dst ? dst + cbase : nullptr;
+        double *scaled = (want_scaled && bt.scaled) ? bt.scaled + cbase : nullptr;
+        double *tot = bt.totals + ((long long)k * st.sumX + soff) * Z + x0 + tid;
+        const double scale = bt.scales[k * S + s], bg = bt.bgshifts[k * S + s];
+        const double *frac = bt.fractions + (long long)k * M;
+        double num = 0.0;
+        for (int z = 0; z < Z; ++z) {
+            double acc[NOUT];
+#pragma unroll
+            for (int u = 0; u < NOUT; ++u) acc[u] = 0.0;
+            for (int p = 0; p < M; ++p) {
+                const double fp = frac[p];
+#pragma unroll
+                for (int u = 0; u < PX_FUSE_SLOTS; ++u) bufR[tid + u * PX_FUSE_TPB] = raw[u];
+                __syncthreads();
+                // next pattern of the sequence: next phase, else the first phase of the next z, else the next candidate
+                const bool more = p + 1 < M || z + 1 < Z || k + 1 < ke;
+                if (p + 1 < M) pat_next += pstride;
+                else if (z + 1 < Z) pat_next += X - (long long)(M - 1) * pstride;
+                else pat_next += bt.cand_stride - (long long)(Z - 1) * X - (long long)(M - 1) * pstride;
+                if (more) prefetch(pat_next);
+                const double *cur = bufR;
+                if constexpr (NPASS > 1) {
+#pragma unroll
+                    for (int u = 0; u < PX_FUSE_SLOTS; ++u) {   // first pass (operations of k_wavelength_pass, in its order)
+                        const int b = tid + u * PX_FUSE_TPB;
+                        const double add = __dadd_rn(__dmul_rn(wh0[u], __dmul_rn(bufR[g0[u]], f0)), __dmul_rn(wl0[u], __dmul_rn(bufR[g0[u] - 1], f0)));
+                        bufA[b] = __dadd_rn(bufR[b], add);
+                    }
+                    __syncthreads();
+                    cur = bufA;
+                    double *nxt = bufB;
+#pragma unroll
+                    for (int j = 1; j + 1 < NPASS; ++j) {       // middle passes: tables on the fly
+                        const double f = j < nwl ? wf[j] : 0.0;
+                        double *out = nxt;
+#pragma unroll
+                        for (int u = 0; u < PX_FUSE_SLOTS; ++u) {
+                            const int b = tid + u * PX_FUSE_TPB;
+                            int g; double wh, wl;
+                            table(j, b < W ? y0 + b : -1, g, wh, wl);
+                            const double add = __dadd_rn(__dmul_rn(wh, __dmul_rn(cur[g], f)), __dmul_rn(wl, __dmul_rn(cur[g - 1], f)));
+                            out[b] = __dadd_rn(cur[b], add);
+                        }
+                        __syncthreads();
+                        nxt = const_cast<double *>(cur); cur = out;
+                    }
+                }
+                double iv[NOUT];
+#pragma unroll
+                for (int u = 0; u < NOUT; ++u) {                // last pass, tile points only
+                    const double add = __dadd_rn(__dmul_rn(whL[u], __dmul_rn(cur[gL[u]], fL)), __dmul_rn(wlL[u], __dmul_rn(cur[gL[u] - 1], fL)));
+                    iv[u] = __dadd_rn(cur[HL + tid + u * PX_FUSE_TPB], add);
+                }
+                const long long poff = (long long)z * X + p * pstride;
+#pragma unroll
+                for (int u = 0; u < NOUT; ++u) {
+                    if (O && inside[u]) O[poff + u * PX_FUSE_TPB] = iv[u];
+                    const double v = __dmul_rn(__dmul_rn(fp, iv[u]), scale);
+                    if (scaled && inside[u]) scaled[poff + u * PX_FUSE_TPB] = v;
+                    acc[u] = __dadd_rn(acc[u], v);
+                }
+                if (NPASS == 1) __syncthreads();                // (bufR is read by the single pass and rewritten by the next pattern)
+            }
+#pragma unroll
+            for (int u = 0; u < NOUT; ++u) {
+                const double t = __dadd_rn(acc[u], __dmul_rn(bg, corr_x[u]));
+                if (want_totals && inside[u]) tot[(long long)z * X + u * PX_FUSE_TPB] = t;
+                const double o = inside[u] ? obs[(long long)z * X + u * PX_FUSE_TPB] : 0.0;
+                if (live[u]) num += fabs(o - t);
+            }
+        }
+        // tile sum of this candidate (the reduction of k_mixture_residual)
+        for (int o = 16; o > 0; o >>= 1) num += __shfl_down_sync(0xffffffffu, num, o);
+        if ((tid & 31) == 0) red[tid >> 5] = num;
+        __syncthreads();
+        if (tid < 32) {
+            num = tid < (PX_FUSE_TPB >> 5) ? red[tid] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) num += __shfl_down_sync(0xffffffffu, num, o);
+            if (tid == 0) partial[((long long)(k - k0) * S + s) * gridDim.y + tile] = num;
+        }
+        __syncthreads();                                        // red[] is rewritten by the next candidate
+    }
+}
+
 // residual of every (candidate, specimen) from the tile sums, in tile order
 __global__ void k_residual_finish(StaticDev st, BatchDev bt, int k0, int k1, int ntiles, const double *__restrict__ partial) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

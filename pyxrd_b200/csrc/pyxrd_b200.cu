@@ -150,6 +150,8 @@ struct pyxrd_ctx {
     DevBuf d_selpos, d_selcount;
     std::vector<int> h_selcount;
     int wl_passes = 0;       // longest wavelength list of the specimens = number of ping-pong passes
+    int wl_halo_l = 0, wl_halo_r = 0;   // how far below / above a point the passes of the distribution reach in total (k_patterns_residual)
+    bool fuse_patterns = true;          // "fuse_patterns": pyxrd_compute_all runs all passes + residual in one kernel where the reach allows
     int jobs_per_cand = 0;
     PinBuf h_res;
     DevBuf d_leaf_a, d_leaf_b, d_leaf_c, d_leaf_d, d_sol, d_optres;
@@ -460,6 +462,7 @@ int pyxrd_set_option(pyxrd_ctx *ctx, const char *name, double value) {
     if (key == "use_structure") ctx->use_structure = value != 0.0;
     else if (key == "series_mma") ctx->series_mma = value != 0.0;
     else if (key == "overlap_classes") ctx->overlap_classes = value != 0.0;
+    else if (key == "fuse_patterns") ctx->fuse_patterns = value != 0.0;
     else if (key == "layer_tables") ctx->use_layer_tables = value != 0.0;
     else if (key == "optimizer_threads") {
         if (value != 0.0 && value != 128.0 && value != 256.0) return fail(ctx, "set_option: optimizer_threads is 0, 128 or 256");
@@ -512,6 +515,24 @@ int pyxrd_set_static(pyxrd_ctx *ctx, const pyxrd_static_desc *d) {
         wl_pts += (long long)d->spec_nwl[s] * d->spec_npts[s];
     }
     const long long sumX = ctx->h_off[S];
+    {
+        // reach of the gathers of every pass of the wavelength distribution (k_patterns_residual): pass j of specimen s
+        // reads at most r-_j points below and r+_j above the point it writes; the passes add up
+        ctx->wl_halo_l = ctx->wl_halo_r = 0;
+        for (int s = 0; s < S; ++s) {
+            const int X = d->spec_npts[s];
+            long long below = 0, above = 0;
+            for (int j = 0; j < d->spec_nwl[s]; ++j) {
+                const int32_t *idx = d->wl_index + wloff[s] + (long long)j * X;
+                int lo = 0, hi = 0;
+                for (int x = 0; x < X; ++x)
+                    if (idx[x] >= 0) { lo = std::max(lo, x - (idx[x] - 1)); hi = std::max(hi, idx[x] - x); }
+                below += lo; above += hi;
+            }
+            ctx->wl_halo_l = (int)std::max<long long>(ctx->wl_halo_l, std::min<long long>(below, 1 << 20));
+            ctx->wl_halo_r = (int)std::max<long long>(ctx->wl_halo_r, std::min<long long>(above, 1 << 20));
+        }
+    }
     if (upload(ctx, ctx->d_npts, d->spec_npts, S)) return 1;
     if (upload(ctx, ctx->d_off, ctx->h_off.data(), S + 1)) return 1;
     if (upload(ctx, ctx->d_gonio, d->spec_gonio, (size_t)S * PYXRD_GONIO_STRIDE)) return 1;
@@ -1091,7 +1112,8 @@ int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed, bool fuse_last
 // mixture totals + residuals of the candidates [k0, k1).  flags: bit 0 = also the scaled phase patterns, bit 1 =
 // residuals only (the total patterns are summed but not stored).  gather_src != nullptr: the last wavelength pass is
 // taken on the fly from that buffer and the final patterns are written to d_int by the same kernel.
-int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const double *gather_src = nullptr) {
+int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const double *gather_src = nullptr,
+                    bool store_patterns = true, bool all_passes = false) {
     BatchDev bt = ctx->bt;
     const int want_scaled = flags & 1;
     int want_totals = (flags & 2) ? 0 : 1;
@@ -1106,7 +1128,20 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const
         const int tile = PX_RES_TPB * PX_RES_PPT, ntiles = std::max(1, (ctx->st.maxX + tile - 1) / tile);
         CK(ctx->d_partial.ensure(sizeof(double) * (size_t)(k1 - k0) * ctx->st.S * ntiles));
         dim3 tgrid(k1 - k0, ntiles, ctx->st.S);
-        if (gather_src)
+        if (all_passes) {
+            static_assert(PX_FUSE_T == PX_RES_TPB * PX_RES_PPT, "the two residual kernels share the tile sums");
+            double *dst = store_patterns ? ctx->d_int.as<double>() : nullptr;
+            const int HL = ctx->wl_halo_l, HR = ctx->wl_halo_r;
+            dim3 fgrid((k1 - k0 + PX_FUSE_CPB - 1) / PX_FUSE_CPB, ntiles, ctx->st.S);
+#define PX_FUSED(N_) k_patterns_residual<N_><<<fgrid, PX_FUSE_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, k1, want_scaled, want_totals, HL, HR, gather_src, dst, ctx->d_partial.as<double>())
+            switch (ctx->wl_passes) {
+                case 1: PX_FUSED(1); break;
+                case 2: PX_FUSED(2); break;
+                case 3: PX_FUSED(3); break;
+                default: PX_FUSED(4); break;
+            }
+#undef PX_FUSED
+        } else if (gather_src)
             k_mixture_residual<true><<<tgrid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled, want_totals, ctx->wl_passes - 1,
                                                                             gather_src, ctx->d_int.as<double>(), ctx->d_partial.as<double>());
         else
@@ -1148,8 +1183,19 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const
 // patterns + residuals of the candidates [k0, k1) at the batch's solution: phase kernels, all wavelength passes but the
 // last as streaming kernels, the last one inside the residual kernel.  (A single pass that composes ALL the wavelength
 // entries per point was measured in round 1: three levels of dependent gathers per point, slower than the passes.)
-int evaluate_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed) {
+int evaluate_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, bool store_patterns = true) {
     const double *src = nullptr;
+    const bool fused = ctx->fuse_patterns && ctx->wl_passes >= 1 && ctx->wl_passes <= PX_FUSE_MAXPASS &&
+                       ctx->wl_halo_l + ctx->wl_halo_r <= PX_FUSE_HMAX;
+    if (fused) {
+        // raw phase patterns into the second buffer; k_patterns_residual takes every pass of the distribution from there
+        if (phase_range(ctx, k0, k1, ctx->d_int2.as<double>(), timed)) return 1;
+        if (timed) {
+            CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+            ctx->ev_set[0] = ctx->ev_set[1] = true;
+        }
+        return residuals_range(ctx, k0, k1, flags, timed, ctx->d_int2.as<double>(), store_patterns, true);
+    }
     if (intensities_range(ctx, k0, k1, timed, true, &src)) return 1;
     return residuals_range(ctx, k0, k1, flags, timed, ctx->wl_passes > 0 ? src : nullptr);
 }
@@ -1161,8 +1207,13 @@ extern "C" {
 int pyxrd_compute_all(pyxrd_ctx *ctx, int flags) {
     if (!ctx || !ctx->have_batch) return fail(ctx, "compute_all: no resident batch");
     CK(cudaSetDevice(ctx->device));
-    if (evaluate_range(ctx, 0, ctx->bt.K, flags, true)) return 1;
-    ctx->have_intensities = true;
+    // residuals only (no totals, no scaled patterns, Rp): nobody reads the final phase patterns; the fused kernel does not
+    // store them and the pattern buffer is marked as not computed
+    const bool store = !((flags & PYXRD_RESIDUALS_ONLY) && !(flags & PYXRD_WANT_SCALED) && ctx->residual_method == PYXRD_RESIDUAL_RP);
+    if (evaluate_range(ctx, 0, ctx->bt.K, flags, true, store)) return 1;
+    const bool fused = ctx->fuse_patterns && ctx->wl_passes >= 1 && ctx->wl_passes <= PX_FUSE_MAXPASS &&
+                       ctx->wl_halo_l + ctx->wl_halo_r <= PX_FUSE_HMAX;
+    ctx->have_intensities = store || !fused;
     return 0;
 }
 
