@@ -312,3 +312,53 @@ def test_layer_tables_with_none_atom_types(calc):
         ref = copy.deepcopy(m)
         orc.calculate_mixture(ref)
         assert rel_err(got[k][0], ref.specimens[0].phase_intensities) < RTOL
+
+
+def test_all_wavelength_passes_inside_the_residual_kernel(calc):
+    """pyxrd_compute_all takes every pass of the wavelength distribution inside the residual kernel where the gathers
+    stay local (k_patterns_residual): same patterns / totals / residuals, bit for bit, as the pass kernels
+    ("fuse_patterns" 0); a residuals-only call does not store the final patterns and says so; a distribution with a
+    far-away line (Cu K-beta: the gathers reach thousands of points) keeps the pass kernels and still matches the oracle
+    (specimen.py:64-74)."""
+    from pyxrd_b200.batched import pack_population
+    from pyxrd_b200.runtime import DeviceError, default_context
+    ctx = default_context()
+    mixes = [_observed(syn.CONFIGS["c4"].candidate(2024, i)) for i in range(11)]      # 11: a block's last group is ragged
+    mixes[3].specimens[1].phases[0][1] = None
+    static, batch = pack_population(mixes)
+    got = {}
+    with ctx.lock:
+        for flag in (1, 0):
+            ctx.set_option("fuse_patterns", flag)
+            try:
+                ctx.set_static(static, force=True)
+                ctx.set_batch(batch)
+                ctx.compute_all(True)
+                got[flag] = [ctx.read_intensities_flat(), ctx.read_totals_flat(), ctx.read_scaled_flat(), ctx.read_residuals()]
+                ctx.set_batch(batch)
+                ctx.compute_all(residuals_only=True)
+                got[flag].append(ctx.read_residuals())
+                if flag:
+                    with pytest.raises(DeviceError):
+                        ctx.read_intensities_flat()          # the final patterns were not stored
+            finally:
+                ctx.set_option("fuse_patterns", 1)
+    for a, b in zip(got[1], got[0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got[1][3], got[1][4])
+    for k in (0, 3, 10):
+        ref = copy.deepcopy(mixes[k])
+        orc.calculate_mixture(ref)
+        assert rel_err(got[1][3][k], ref.residuals) < RTOL
+    # K-beta in the list: no halo holds that gather
+    wide = [_observed(syn.CONFIGS["c2"].candidate(7, i)) for i in range(3)]
+    for m in wide:
+        for spec in m.specimens:
+            spec.goniometer.wavelength_distribution = [(syn.CU_KA1, 0.9), (0.1392218, 0.1)]
+    res = calc.mixture.calculate_mixture
+    for m in wide:
+        ref = copy.deepcopy(m)
+        orc.calculate_mixture(ref)
+        res(m)
+        assert rel_err(m.residuals, ref.residuals) < RTOL
+        assert rel_err(m.specimens[0].phase_intensities, ref.specimens[0].phase_intensities) < RTOL
