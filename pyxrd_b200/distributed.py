@@ -137,9 +137,25 @@ def gather_rows(local, n_total: int, world_size: int, group=None):
     return out[:n_total]
 
 
+_pinned = {}        # (shape, dtype) -> reused pinned host buffer of _to_host
+
+
 def _to_host(t) -> np.ndarray:
-    """host copy of a gathered table (never a view of the reused gather buffer)"""
-    return (t.cpu() if t.is_cuda else t.clone()).numpy()
+    """host copy of a gathered table (never a view of the reused gather buffer).  Device tables go through a reused
+    PINNED staging buffer (one asynchronous copy + one stream synchronisation: a pageable ``.cpu()`` costs an allocation
+    and a staged copy per generation)"""
+    if not t.is_cuda:
+        return t.clone().numpy()
+    import torch
+    key = (tuple(t.shape), t.dtype)
+    buf = _pinned.get(key)
+    if buf is None:
+        if len(_pinned) > 16:
+            _pinned.clear()
+        buf = _pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return buf.numpy().copy()
 
 
 def _as_rows(values, rows: int, device):
