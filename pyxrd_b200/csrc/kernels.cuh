@@ -2455,19 +2455,19 @@ __global__ void __launch_bounds__(PX_RES_TPB, PX_RES_MINB) k_mixture_residual(St
 #define PX_FUSE_MINB 4
 #endif
 #ifndef PX_FUSE_CPB
-#define PX_FUSE_CPB 8                  // candidates a block walks for its tile (grid.x = ceil(candidates / PX_FUSE_CPB))
-#endif
+#define PX_FUSE_CPB 8                  // candidates a block walks for its tile at most (grid.x = ceil(candidates / cpb); the host
+#endif                                 // takes fewer where the population is too small to fill the machine with blocks)
 // A block owns one tile of one specimen for PX_FUSE_CPB consecutive candidates: the abscissa tables of the tile (index of
 // the upper neighbour and the two weights, per pass) are candidate-invariant and fetched once into registers; the raw
 // pattern of the NEXT (candidate, z, phase) is prefetched into registers while the current one goes through the passes
 // in shared memory, so that no global latency sits between the stages of a pattern.
 template <int NPASS>
-__global__ void __launch_bounds__(PX_FUSE_TPB, PX_FUSE_MINB) k_patterns_residual(StaticDev st, BatchDev bt, int k0, int k1, int want_scaled, int want_totals,
+__global__ void __launch_bounds__(PX_FUSE_TPB, PX_FUSE_MINB) k_patterns_residual(StaticDev st, BatchDev bt, int k0, int k1, int cpb, int want_scaled, int want_totals,
                                                                   int HL, int HR, const double *__restrict__ src, double *__restrict__ dst,
                                                                   double *__restrict__ partial) {
     constexpr int NOUT = PX_FUSE_T / PX_FUSE_TPB, NBUF = PX_FUSE_SLOTS * PX_FUSE_TPB;    // every slot of every thread has a buffer entry
     const int s = blockIdx.z, tile = blockIdx.y, tid = threadIdx.x;
-    const int kb = k0 + blockIdx.x * PX_FUSE_CPB, ke = min(k1, kb + PX_FUSE_CPB);
+    const int kb = k0 + blockIdx.x * cpb, ke = min(k1, kb + cpb);
     const int X = st.spec_npts[s], Z = st.Z, M = bt.M, S = st.S;
     const int x0 = tile * PX_FUSE_T;
     __shared__ double bufR[NBUF], bufA[NPASS > 1 ? NBUF : 1], bufB[NPASS > 2 ? NBUF : 1];

@@ -1138,8 +1138,11 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const
             static_assert(PX_FUSE_T == PX_RES_TPB * PX_RES_PPT, "the two residual kernels share the tile sums");
             double *dst = store_patterns ? ctx->d_int.as<double>() : nullptr;
             const int HL = ctx->wl_halo_l, HR = ctx->wl_halo_r;
-            dim3 fgrid((k1 - k0 + PX_FUSE_CPB - 1) / PX_FUSE_CPB, ntiles, ctx->st.S);
-#define PX_FUSED(N_) k_patterns_residual<N_><<<fgrid, PX_FUSE_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, k1, want_scaled, want_totals, HL, HR, gather_src, dst, ctx->d_partial.as<double>())
+            // candidates per block: up to PX_FUSE_CPB, fewer where that would leave SMs without blocks (two waves of 4)
+            const long long tiles_total = (long long)(k1 - k0) * ntiles * ctx->st.S;
+            const int cpb = (int)std::max<long long>(1, std::min<long long>(PX_FUSE_CPB, tiles_total / (8LL * ctx->sm_count)));
+            dim3 fgrid((k1 - k0 + cpb - 1) / cpb, ntiles, ctx->st.S);
+#define PX_FUSED(N_) k_patterns_residual<N_><<<fgrid, PX_FUSE_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, k1, cpb, want_scaled, want_totals, HL, HR, gather_src, dst, ctx->d_partial.as<double>())
             switch (ctx->wl_passes) {
                 case 1: PX_FUSED(1); break;
                 case 2: PX_FUSED(2); break;
