@@ -1093,9 +1093,27 @@ int phase_range(pyxrd_ctx *ctx, int k0, int k1, double *target, bool timed) {
 
 // phase patterns + wavelength passes of the candidates [k0, k1).  fuse_last: the last pass of the wavelength
 // distribution is left to the residual kernel (k_mixture_residual<true>); *last_src then names the buffer it reads.
+int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const double *gather_src, bool store_patterns, bool all_passes,
+                    bool patterns_only);
+bool patterns_fusable(const pyxrd_ctx *ctx) {
+    return ctx->fuse_patterns && ctx->wl_passes >= 1 && ctx->wl_passes <= PX_FUSE_MAXPASS && ctx->wl_halo_l + ctx->wl_halo_r <= PX_FUSE_HMAX;
+}
+
 int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed, bool fuse_last = false, const double **last_src = nullptr) {
     const StaticDev &st = ctx->st;
     double *bufs[2] = {ctx->d_int.as<double>(), ctx->d_int2.as<double>()};
+    if (!fuse_last && ctx->wl_passes >= 2 && patterns_fusable(ctx)) {
+        // all passes in ONE kernel (k_patterns_residual storing the patterns; its tile sums are scratch): one read and
+        // one write of the patterns instead of one per pass
+        if (phase_range(ctx, k0, k1, bufs[1], timed)) return 1;
+        if (residuals_range(ctx, k0, k1, PYXRD_RESIDUALS_ONLY, false, bufs[1], true, true, true)) return 1;
+        if (last_src) *last_src = bufs[0];
+        if (timed) {
+            CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+            ctx->ev_set[0] = ctx->ev_set[1] = true;
+        }
+        return 0;
+    }
     int cur = ctx->wl_passes & 1;                      // passes alternate cur -> 1 - cur and must end in 0
     const long long j0 = (long long)k0 * ctx->jobs_per_cand, j1 = (long long)k1 * ctx->jobs_per_cand;
     if (phase_range(ctx, k0, k1, bufs[cur], timed)) return 1;
@@ -1119,11 +1137,12 @@ int intensities_range(pyxrd_ctx *ctx, int k0, int k1, bool timed, bool fuse_last
 // residuals only (the total patterns are summed but not stored).  gather_src != nullptr: the last wavelength pass is
 // taken on the fly from that buffer and the final patterns are written to d_int by the same kernel.
 int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const double *gather_src = nullptr,
-                    bool store_patterns = true, bool all_passes = false) {
+                    bool store_patterns = true, bool all_passes = false, bool patterns_only = false) {
     BatchDev bt = ctx->bt;
     const int want_scaled = flags & 1;
     int want_totals = (flags & 2) ? 0 : 1;
     if (ctx->residual_method == PYXRD_RESIDUAL_RPDER) want_totals = 1;      // k_residual_rpder reads the totals
+    if (patterns_only) want_totals = 0;
     if (want_scaled) {
         CK(ctx->d_scaled.ensure(sizeof(double) * std::max<int64_t>(ctx->int_count, 1)));
         bt.scaled = ctx->d_scaled.as<double>();
@@ -1157,6 +1176,7 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const
             k_mixture_residual<false><<<tgrid, PX_RES_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, want_scaled, want_totals, 0,
                                                                              ctx->d_int.as<double>(), nullptr, ctx->d_partial.as<double>());
         LAUNCH_CHECK("k_mixture_residual");
+        if (patterns_only) return 0;            // (intensities_range: the kernel was run for the patterns it stores)
         k_residual_finish<<<((k1 - k0) * ctx->st.S + 127) / 128, 128, 0, ctx->stream>>>(ctx->st, bt, k0, k1, ntiles,
                                                                                       ctx->d_partial.as<double>());
         LAUNCH_CHECK("k_residual_finish");
@@ -1194,8 +1214,7 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const
 // entries per point was measured in round 1: three levels of dependent gathers per point, slower than the passes.)
 int evaluate_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, bool store_patterns = true) {
     const double *src = nullptr;
-    const bool fused = ctx->fuse_patterns && ctx->wl_passes >= 1 && ctx->wl_passes <= PX_FUSE_MAXPASS &&
-                       ctx->wl_halo_l + ctx->wl_halo_r <= PX_FUSE_HMAX;
+    const bool fused = patterns_fusable(ctx);
     if (fused) {
         // raw phase patterns into the second buffer; k_patterns_residual takes every pass of the distribution from there
         if (phase_range(ctx, k0, k1, ctx->d_int2.as<double>(), timed)) return 1;
@@ -1220,9 +1239,7 @@ int pyxrd_compute_all(pyxrd_ctx *ctx, int flags) {
     // store them and the pattern buffer is marked as not computed
     const bool store = !((flags & PYXRD_RESIDUALS_ONLY) && !(flags & PYXRD_WANT_SCALED) && ctx->residual_method == PYXRD_RESIDUAL_RP);
     if (evaluate_range(ctx, 0, ctx->bt.K, flags, true, store)) return 1;
-    const bool fused = ctx->fuse_patterns && ctx->wl_passes >= 1 && ctx->wl_passes <= PX_FUSE_MAXPASS &&
-                       ctx->wl_halo_l + ctx->wl_halo_r <= PX_FUSE_HMAX;
-    ctx->have_intensities = store || !fused;
+    ctx->have_intensities = store || !patterns_fusable(ctx);
     return 0;
 }
 
