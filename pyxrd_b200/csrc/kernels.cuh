@@ -2461,7 +2461,7 @@ __global__ void __launch_bounds__(PX_RES_TPB, PX_RES_MINB) k_mixture_residual(St
 // the upper neighbour and the two weights, per pass) are candidate-invariant and fetched once into registers; the raw
 // pattern of the NEXT (candidate, z, phase) is prefetched into registers while the current one goes through the passes
 // in shared memory, so that no global latency sits between the stages of a pattern.
-template <int NPASS>
+template <int NPASS, bool STORE>         // STORE = false: residuals only, nothing but the tile sums is written
 __global__ void __launch_bounds__(PX_FUSE_TPB, PX_FUSE_MINB) k_patterns_residual(StaticDev st, BatchDev bt, int k0, int k1, int cpb, int want_scaled, int want_totals,
                                                                   int HL, int HR, const double *__restrict__ src, double *__restrict__ dst,
                                                                   double *__restrict__ partial) {
@@ -2528,9 +2528,9 @@ __global__ void __launch_bounds__(PX_FUSE_TPB, PX_FUSE_MINB) k_patterns_residual
     prefetch(pat_next);
     for (int k = kb; k < ke; ++k) {
         const long long cbase = (long long)k * bt.cand_stride + spec_base + x0 + tid;
-        double *O = dst ? dst + cbase : nullptr;
-        double *scaled = (want_scaled && bt.scaled) ? bt.scaled + cbase : nullptr;
-        double *tot = bt.totals + ((long long)k * st.sumX + soff) * Z + x0 + tid;
+        double *O = (STORE && dst) ? dst + cbase : nullptr;
+        double *scaled = (STORE && want_scaled && bt.scaled) ? bt.scaled + cbase : nullptr;
+        double *tot = STORE ? bt.totals + ((long long)k * st.sumX + soff) * Z + x0 + tid : nullptr;
         const double scale = bt.scales[k * S + s], bg = bt.bgshifts[k * S + s];
         const double *frac = bt.fractions + (long long)k * M;
         double num = 0.0;
@@ -2585,9 +2585,9 @@ __global__ void __launch_bounds__(PX_FUSE_TPB, PX_FUSE_MINB) k_patterns_residual
                 const long long poff = (long long)z * X + p * pstride;
 #pragma unroll
                 for (int u = 0; u < NOUT; ++u) {
-                    if (O && inside[u]) O[poff + u * PX_FUSE_TPB] = iv[u];
+                    if (STORE && O && inside[u]) O[poff + u * PX_FUSE_TPB] = iv[u];
                     const double v = __dmul_rn(__dmul_rn(fp, iv[u]), scale);
-                    if (scaled && inside[u]) scaled[poff + u * PX_FUSE_TPB] = v;
+                    if (STORE && scaled && inside[u]) scaled[poff + u * PX_FUSE_TPB] = v;
                     acc[u] = __dadd_rn(acc[u], v);
                 }
                 if (NPASS == 1) __syncthreads();                // (bufR is read by the single pass and rewritten by the next pattern)
@@ -2595,7 +2595,7 @@ __global__ void __launch_bounds__(PX_FUSE_TPB, PX_FUSE_MINB) k_patterns_residual
 #pragma unroll
             for (int u = 0; u < NOUT; ++u) {
                 const double t = __dadd_rn(acc[u], __dmul_rn(bg, corr_x[u]));
-                if (want_totals && inside[u]) tot[(long long)z * X + u * PX_FUSE_TPB] = t;
+                if (STORE && want_totals && inside[u]) tot[(long long)z * X + u * PX_FUSE_TPB] = t;
                 const double o = inside[u] ? obs[(long long)z * X + u * PX_FUSE_TPB] : 0.0;
                 if (live[u]) num += fabs(o - t);
             }

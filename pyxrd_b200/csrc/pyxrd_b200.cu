@@ -1161,7 +1161,9 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const
             const long long tiles_total = (long long)(k1 - k0) * ntiles * ctx->st.S;
             const int cpb = (int)std::max<long long>(1, std::min<long long>(PX_FUSE_CPB, tiles_total / (8LL * ctx->sm_count)));
             dim3 fgrid((k1 - k0 + cpb - 1) / cpb, ntiles, ctx->st.S);
-#define PX_FUSED(N_) k_patterns_residual<N_><<<fgrid, PX_FUSE_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, k1, cpb, want_scaled, want_totals, HL, HR, gather_src, dst, ctx->d_partial.as<double>())
+            const bool stores = dst || want_scaled || want_totals;
+#define PX_FUSED(N_) do { if (stores) k_patterns_residual<N_, true><<<fgrid, PX_FUSE_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, k1, cpb, want_scaled, want_totals, HL, HR, gather_src, dst, ctx->d_partial.as<double>()); \
+                          else k_patterns_residual<N_, false><<<fgrid, PX_FUSE_TPB, 0, ctx->stream>>>(ctx->st, bt, k0, k1, cpb, 0, 0, HL, HR, gather_src, nullptr, ctx->d_partial.as<double>()); } while (0)
             switch (ctx->wl_passes) {
                 case 1: PX_FUSED(1); break;
                 case 2: PX_FUSED(2); break;
