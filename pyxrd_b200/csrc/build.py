@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["pyxrd_b200.cu"]
-DEPENDS = ["pyxrd_b200.cu", "kernels.cuh", "lpf_table.inc", os.path.join("..", "..", "include", "pyxrd_b200.h")]
+DEPENDS = ["pyxrd_b200.cu", "kernels.cuh", "lpf_table.inc", "sincos_table.inc", os.path.join("..", "..", "include", "pyxrd_b200.h")]
 OUTPUT = os.path.join(HERE, "libpyxrd_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]

@@ -29,23 +29,21 @@
 #define PX_SQRT2PI 2.5066282746310002      // math.sqrt(2 * pi)
 #define PX_SQRT8 2.8284271247461903        // math.sqrt(8)
 
-// sin/cos coefficients live in constant memory so that ptxas keeps them in (uniform) registers
-// across the atom loop instead of re-materialising every 64-bit immediate with two UMOVs
-// (measured: 25 % of all issued instructions of the first version of k_phase_small).
-__constant__ double PX_SC[19] = {
-    0.63661977236758138,        // 2/pi
-    6755399441055744.0,         // 1.5 * 2^52: round-to-nearest-integer magic
-    -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33,    // -pi/2 in three parts
-    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,    // sin minimax, |r| <= pi/4
-    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
-    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,   // cos minimax
-    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
-    -0.5, 1.0};
+// (constants of the phase kernels live in constant memory so that ptxas keeps them in uniform registers across the
+// atom loop instead of re-materialising every 64-bit immediate with two UMOVs: 25 % of all issued instructions of the
+// first version of k_phase_small)
 
 // erf(Q) and exp(-Q^2) of the Lorentz-polarisation factor as piecewise degree-7 polynomials (tools/make_lpf_table.py):
 // [i / 16, (i + 1) / 16) for i < 104, one 128-byte line of 8 (erf, exp) coefficient pairs per interval, tail entry = (1, 0)
 #define PX_LPF_TABLE_DECL __device__ __align__(128) const double PX_LPF_TAB
 #include "lpf_table.inc"
+
+// table-assisted sine / cosine of k_phase_small (tools/make_sincos_table.py): reduction constants PX_ST, table PX_SCT
+#define PX_SCT_N 128
+#ifndef PX_SCT_SMEM
+#define PX_SCT_SMEM true       // k_phase_small reads its own copy of the table in shared memory (false: the global one)
+#endif
+#include "sincos_table.inc"
 
 // exp(a), a <= 0: a = n ln 2 + r, |r| <= ln 2 / 2; Taylor polynomial of degree 13 (remainder 4e-18), 2^n into the exponent
 __constant__ double PX_EX[18] = {
@@ -77,34 +75,19 @@ __device__ __forceinline__ void px_exp_neg_n(const double (&a)[N], double (&out)
     for (int k = 0; k < N; ++k) out[k] = __hiloint2double(__double2hiint(p[k]) + (n[k] << 20), __double2loint(p[k]));
 }
 
-// sin and cos of a (|a| < 2^30 * pi/2): Cody-Waite reduction with FMAs, 13/14-degree minimax
-// polynomials; max error 1.6 ulp / 1.8e-16 absolute (checked against long-double libm on 2e7 points).
+// sin and cos of a (|a| < 2^20): two-part Cody-Waite reduction with FMAs to |r| <= pi / 128 around a table entry
 __device__ __forceinline__ void px_sincos(double a, double &s, double &c) {
-    const double t = fma(a, PX_SC[0], PX_SC[1]);
-    const double q = t - PX_SC[1];
-    const int n = __double2loint(t);
-    double r = fma(q, PX_SC[2], a);
-    r = fma(q, PX_SC[3], r);
-    r = fma(q, PX_SC[4], r);
+    // table-assisted (see px_sincos_n): a = k h + r, h = pi / 64, (S, C) = (sin, cos)(k h) from PX_SCT
+    const double t = fma(a, PX_ST[0], PX_ST[1]);
+    const double q = t - PX_ST[1];
+    const double2 sc = __ldg(reinterpret_cast<const double2 *>(PX_SCT) + (__double2loint(t) & (PX_SCT_N - 1)));
+    double r = fma(q, PX_ST[2], a);
+    r = fma(q, PX_ST[3], r);
     const double r2 = r * r;
-    double ps = PX_SC[5];
-    ps = fma(ps, r2, PX_SC[6]);
-    ps = fma(ps, r2, PX_SC[7]);
-    ps = fma(ps, r2, PX_SC[8]);
-    ps = fma(ps, r2, PX_SC[9]);
-    ps = fma(ps, r2, PX_SC[10]);
-    const double sn = fma(r * r2, ps, r);
-    double pc = PX_SC[11];
-    pc = fma(pc, r2, PX_SC[12]);
-    pc = fma(pc, r2, PX_SC[13]);
-    pc = fma(pc, r2, PX_SC[14]);
-    pc = fma(pc, r2, PX_SC[15]);
-    pc = fma(pc, r2, PX_SC[16]);
-    const double cs = fma(r2 * r2, pc, fma(r2, PX_SC[17], PX_SC[18]));
-    const double S = (n & 1) ? cs : sn, C = (n & 1) ? sn : cs;
-    // quadrant signs by flipping the sign bit of the high word
-    s = __hiloint2double(__double2hiint(S) ^ ((n & 2) << 30), __double2loint(S));
-    c = __hiloint2double(__double2hiint(C) ^ (((n + 1) & 2) << 30), __double2loint(C));
+    const double ps = fma(fma(r2, PX_ST[4], PX_ST[5]), r2, PX_ST[6]), pc = fma(fma(r2, PX_ST[7], PX_ST[8]), r2, PX_ST[9]);
+    const double sr = fma(r * r2, ps, r), cm1 = r2 * pc;
+    s = fma(sc.y, sr, fma(sc.x, cm1, sc.x));
+    c = fma(-sc.x, sr, fma(sc.y, cm1, sc.y));
 }
 
 struct StaticDev {
@@ -163,6 +146,7 @@ struct BatchDev {
     double *phase_img;               // [NP][img_stride]
     int img_stride, img_ae, img_mcap;   // words per image; acap rounded up to even; words reserved for P and WG
     int img_ncopy;                   // coefficients a block copies (set per launch: the launch's shared-memory capacity)
+    int img_sct_off;                 // byte offset of the sine / cosine table inside the block's dynamic shared memory (per launch)
     int *ph_nu;                      // [NP]        number of distinct planes
     double *ph_uz;                   // [NP][acap]  z of distinct plane u
     int *ph_uend;                    // [NP][acap]  one past the last segment of distinct plane u
@@ -1178,45 +1162,59 @@ __device__ __forceinline__ void component_factors(const PhaseSmem *ps, int c, do
     phase_factor(stl, ps->comp_d001[c], ps->comp_delta[c], pr, pi_);
 }
 
-// N independent arguments in lock step: every coefficient is fetched once for N FMAs and the N
-// dependent chains interleave (DFMA latency is 8.5 cycles, tools/microbench.cu)
-template <int N>
-__device__ __forceinline__ void px_sincos_n(const double (&a)[N], double (&s)[N], double (&c)[N]) {
-    double q[N], r[N], r2[N], ps[N], pc[N];
+// sin and cos of N independent arguments in lock step (every constant is fetched once for N FMAs, the N dependent chains
+// interleave: DFMA latency is 8.5 cycles, tools/microbench.cu), table-assisted: a = k h + r, h = pi / 64,
+// (S, C) = (sin, cos)(k h) from the 128-entry table PX_SCT (tools/make_sincos_table.py),
+//   sin a = S + (S (cos r - 1) + C sin r),  cos a = C + (C (cos r - 1) - S sin r),  |r| <= pi / 128:
+// degree-7 / degree-6 Taylor polynomials are exact to 1e-20 / 4e-18 there.  17 FP64 + 4 other instructions per argument;
+// the quadrant reduction with degree-13 / 14 minimax polynomials it replaces took 21 + 13 (quadrant selection, sign
+// flips).  Worst absolute error 1.6e-16 on |a| <= 200 (the generator's report; the polynomial version: 1.7e-16).
+// SMEM: the table is the caller's copy in shared memory (k_phase_small), else the global one through the read-only path.
+// px_sincos (scalar) performs the same operations in the same order: every kernel gets bit-identical values.
+template <int N, bool SMEM = false>
+__device__ __forceinline__ void px_sincos_n(const double (&a)[N], double (&s)[N], double (&c)[N], const double2 *__restrict__ smem_tab = nullptr) {
+    double q[N], r[N];
     int n[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const double t = fma(a[k], PX_SC[0], PX_SC[1]);
-        q[k] = t - PX_SC[1];
-        n[k] = __double2loint(t);
+        const double t = fma(a[k], PX_ST[0], PX_ST[1]);
+        q[k] = t - PX_ST[1];
+        n[k] = __double2loint(t) & (PX_SCT_N - 1);
     }
-#pragma unroll
-    for (int k = 0; k < N; ++k) r[k] = fma(q[k], PX_SC[2], a[k]);
-#pragma unroll
-    for (int k = 0; k < N; ++k) r[k] = fma(q[k], PX_SC[3], r[k]);
-#pragma unroll
-    for (int k = 0; k < N; ++k) { r[k] = fma(q[k], PX_SC[4], r[k]); r2[k] = r[k] * r[k]; ps[k] = PX_SC[5]; pc[k] = PX_SC[11]; }
-#pragma unroll
-    for (int j = 6; j <= 10; ++j)
-#pragma unroll
-        for (int k = 0; k < N; ++k) { ps[k] = fma(ps[k], r2[k], PX_SC[j]); pc[k] = fma(pc[k], r2[k], PX_SC[j + 6]); }
+    double2 sc[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const double sn = fma(r[k] * r2[k], ps[k], r[k]);
-        const double cs = fma(r2[k] * r2[k], pc[k], fma(r2[k], PX_SC[17], PX_SC[18]));
-        const double S = (n[k] & 1) ? cs : sn, C = (n[k] & 1) ? sn : cs;
-        s[k] = __hiloint2double(__double2hiint(S) ^ ((n[k] & 2) << 30), __double2loint(S));
-        c[k] = __hiloint2double(__double2hiint(C) ^ (((n[k] + 1) & 2) << 30), __double2loint(C));
+        if constexpr (SMEM) sc[k] = smem_tab[n[k]];
+        else sc[k] = __ldg(reinterpret_cast<const double2 *>(PX_SCT) + n[k]);
     }
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = fma(q[k], PX_ST[2], a[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = fma(q[k], PX_ST[3], r[k]);
+    double r2[N], ps[N], pc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { r2[k] = r[k] * r[k]; ps[k] = fma(r2[k], PX_ST[4], PX_ST[5]); pc[k] = fma(r2[k], PX_ST[7], PX_ST[8]); }
+#pragma unroll
+    for (int k = 0; k < N; ++k) { ps[k] = fma(ps[k], r2[k], PX_ST[6]); pc[k] = fma(pc[k], r2[k], PX_ST[9]); }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double sr = fma(r[k] * r2[k], ps[k], r[k]), cm1 = r2[k] * pc[k];
+        s[k] = fma(sc[k].y, sr, fma(sc[k].x, cm1, sc[k].x));
+        c[k] = fma(-sc[k].x, sr, fma(sc[k].y, cm1, sc[k].y));
+    }
+}
+template <int N, bool TAB>
+__device__ __forceinline__ void px_sincos_sel(const double2 *__restrict__ tab, const double (&a)[N], double (&s)[N], double (&c)[N]) {
+    px_sincos_n<N, TAB>(a, s, c, tab);
 }
 
 // structure factor and phase factor of component c at the N points gx0 + k * stride of one thread
 // (same arithmetic per point as component_factors)
-template <int N>
+template <int N, bool TAB = false>
 __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, const double (&stl)[N],
                                                     const double *__restrict__ asf_col, const double2 *__restrict__ tab_col,
                                                     int stride, double (&ur)[N], double (&ui)[N], double (&pr)[N],
-                                                    double (&pim)[N]) {
+                                                    double (&pim)[N], const double2 *__restrict__ sct = nullptr) {
     double sr[N], si[N];
     if (ps->comp_tab[c] >= 0) {                          // block-uniform: the tabulated layer stack
         const double2 *tc = tab_col + ps->comp_tab[c];
@@ -1243,7 +1241,7 @@ __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, 
         double ang[N], sn[N], cs[N];
 #pragma unroll
         for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(arg, stl[k]);
-        px_sincos_n<N>(ang, sn, cs);
+        px_sincos_sel<N, TAB>(sct, ang, sn, cs);
 #pragma unroll
         for (int k = 0; k < N; ++k) { sr[k] = fma(f[k], cs[k], sr[k]); si[k] = fma(f[k], sn[k], si[k]); }
     }
@@ -1251,7 +1249,7 @@ __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, 
     double ang[N], sn[N], cs[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), d001);
-    px_sincos_n<N>(ang, sn, cs);
+    px_sincos_sel<N, TAB>(sct, ang, sn, cs);
 #pragma unroll
     for (int k = 0; k < N; ++k) { ur[k] = sr[k]; ui[k] = si[k]; }
     if (delta_c != 0.0) {                                   // block-uniform branch
@@ -1269,10 +1267,11 @@ __device__ __forceinline__ void component_factors_n(const PhaseSmem *ps, int c, 
 
 // structure factors and phase factors of ALL G components at the N points of one thread, one complex exponential per
 // DISTINCT plane of the phase (load_phase_lists<true>); per plane the arithmetic is that of component_factors_n
-template <int G, int N>
+template <int G, int N, bool TAB = false>
 __device__ __forceinline__ void phase_factors_n(const PhaseSmem *ps, const double (&stl)[N], const double *__restrict__ asf_col,
                                                 const double2 *__restrict__ tab_col, int stride, double (&ur)[G][N],
-                                                double (&ui)[G][N], double (&pr)[G][N], double (&pim)[G][N]) {
+                                                double (&ui)[G][N], double (&pr)[G][N], double (&pim)[G][N],
+                                                const double2 *__restrict__ sct = nullptr) {
 #pragma unroll
     for (int c = 0; c < G; ++c) {
         if (ps->comp_tab[c] >= 0) {                      // block-uniform: the tabulated layer stack of the component
@@ -1291,7 +1290,7 @@ __device__ __forceinline__ void phase_factors_n(const PhaseSmem *ps, const doubl
         double ang[N], sn[N], cs[N];
 #pragma unroll
         for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(arg, stl[k]);
-        px_sincos_n<N>(ang, sn, cs);
+        px_sincos_sel<N, TAB>(sct, ang, sn, cs);
         const int sg_end = ps->plane_end[u];
         for (; sg < sg_end; ++sg) {
             const int info = ps->useg[sg];
@@ -1319,7 +1318,7 @@ __device__ __forceinline__ void phase_factors_n(const PhaseSmem *ps, const doubl
         double ang[N], sn[N], cs[N];
 #pragma unroll
         for (int k = 0; k < N; ++k) ang[k] = __dmul_rn(__dmul_rn(PX_TWO_PI, stl[k]), d001);
-        px_sincos_n<N>(ang, sn, cs);
+        px_sincos_sel<N, TAB>(sct, ang, sn, cs);
         if (delta_c != 0.0) {                               // block-uniform branch
             double arg[N], e[N];
 #pragma unroll
@@ -1443,6 +1442,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     double *sP = reinterpret_cast<double *>(smem_raw + sizeof(PhaseSmem));   // [R][R]
     double *sWG = sP + R * R;                                               // [G][R]
     double *sCoef = sWG + G * R;                                            // [ntop+1]
+    double2 *sSct = reinterpret_cast<double2 *>(smem_raw + bt.img_sct_off);   // [PX_SCT_N] (sin, cos)(k pi / 64), px_sincos_tab_n
 
     const int job = jobs[blockIdx.x];
     const int pb = bt.job_pb[job], s = bt.job_spec[job];
@@ -1471,6 +1471,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
         for (int i = threadIdx.x; i < G * R; i += TPB) sWG[i] = mat[R * R + i];
         const double *cf = mat + bt.img_mcap;
         for (int i = threadIdx.x; i < bt.img_ncopy; i += TPB) sCoef[i] = cf[i];
+        if (PX_SCT_SMEM)
+            for (int i = threadIdx.x; i < PX_SCT_N; i += TPB) sSct[i] = reinterpret_cast<const double2 *>(PX_SCT)[i];
     }
     __syncthreads();
     const int ntop = (int)ps->px[2];
@@ -1487,10 +1489,10 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     for (int k = 0; k < PPT; ++k) stl[k] = st.stl[gx + k * TPB];
 
     double ur[G][PPT], ui[G][PPT], pr[G][PPT], pim[G][PPT], gr[G][PPT], gi[G][PPT];
-    if constexpr (DISTINCT) phase_factors_n<G, PPT>(ps, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur, ui, pr, pim);
+    if constexpr (DISTINCT) phase_factors_n<G, PPT, PX_SCT_SMEM>(ps, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur, ui, pr, pim, sSct);
 #pragma unroll
     for (int c = 0; c < G; ++c) {
-        if constexpr (!DISTINCT) component_factors_n<PPT>(ps, c, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur[c], ui[c], pr[c], pim[c]);
+        if constexpr (!DISTINCT) component_factors_n<PPT, PX_SCT_SMEM>(ps, c, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur[c], ui[c], pr[c], pim[c], sSct);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             gr[c][k] = pr[c][k] * ur[c][k] + pim[c][k] * ui[c][k];          // g = phi * conj(u)

@@ -218,9 +218,11 @@ int upload(pyxrd_ctx *ctx, DevBuf &buf, const T *src, size_t n) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-size_t small_smem(int R, int G, int ntop_cap) {
-    return sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + ntop_cap + 2);
+// PhaseSmem, P, WG, coefficients, then (16-byte aligned) the sine / cosine table of px_sincos_tab_n
+size_t small_sct_offset(int R, int G, int ntop_cap) {
+    return align_up(sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + ntop_cap + 2), 16);
 }
+size_t small_smem(int R, int G, int ntop_cap) { return small_sct_offset(R, G, ntop_cap) + sizeof(double2) * PX_SCT_N; }
 size_t staged_smem(int R, int G, int ntop_cap) {
     const int RB = (R + 3) / 4;
     return sizeof(PhaseSmem) + sizeof(double) * (size_t)(RB * R * 4 + G * R + (G * R & 1)) +
@@ -262,6 +264,7 @@ int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_
     dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + TPB * PPT * TILES - 1) / (TPB * PPT * TILES)));
     BatchDev b2 = bt;
     b2.img_ncopy = std::min(bt.ncap, rc.max_ntop_cap + 2);      // what the launch's shared memory holds
+    b2.img_sct_off = (int)small_sct_offset(R, G, rc.max_ntop_cap);
     k_phase_small<R, G, PPT, TPB, MINB, STRUCT, TILES><<<grid, TPB, smem, ctx->stream>>>(ctx->st, b2, jobs_dev);
     LAUNCH_CHECK("k_phase_small");
     return 0;
