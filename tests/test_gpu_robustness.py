@@ -362,3 +362,40 @@ def test_all_wavelength_passes_inside_the_residual_kernel(calc):
         res(m)
         assert rel_err(m.residuals, ref.residuals) < RTOL
         assert rel_err(m.specimens[0].phase_intensities, ref.specimens[0].phase_intensities) < RTOL
+
+
+@pytest.mark.parametrize("lines", [1, 3, 4, 5])
+def test_fused_passes_for_every_list_length(calc, lines):
+    """k_patterns_residual is instantiated per number of passes (1 .. 4; five entries keep the pass kernels): a list of
+    ``lines`` close wavelengths, fused against the pass kernels bit for bit (compute_all and compute_intensities) and against
+    the oracle (specimen.py:64-74)."""
+    from pyxrd_b200.batched import pack_population
+    from pyxrd_b200.runtime import default_context
+    ctx = default_context()
+    dist = [(0.1544426, 0.60), (0.153475, 0.25), (0.15406, 0.08), (0.15411, 0.04), (0.15390, 0.03)][:lines]
+    mixes = [_observed(syn.CONFIGS["c2"].candidate(11, i)) for i in range(5)]
+    for m in mixes:
+        for spec in m.specimens:
+            spec.goniometer.wavelength_distribution = list(dist)
+    static, batch = pack_population(mixes)
+    got = {}
+    with ctx.lock:
+        for flag in (1, 0):
+            ctx.set_option("fuse_patterns", flag)
+            try:
+                ctx.set_static(static, force=True)
+                ctx.set_batch(batch)
+                ctx.compute_all()
+                got[flag] = [ctx.read_intensities_flat(), ctx.read_totals_flat(), ctx.read_residuals()]
+                ctx.set_batch(batch)
+                ctx.compute_intensities()
+                got[flag].append(ctx.read_intensities_flat())
+            finally:
+                ctx.set_option("fuse_patterns", 1)
+    for a, b in zip(got[1], got[0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got[1][0], got[1][3])
+    for k in (0, 4):
+        ref = copy.deepcopy(mixes[k])
+        orc.calculate_mixture(ref)
+        assert rel_err(got[1][2][k], ref.residuals) < RTOL
