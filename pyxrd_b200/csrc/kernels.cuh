@@ -2446,7 +2446,8 @@ __global__ void __launch_bounds__(PX_RES_TPB, PX_RES_MINB) k_mixture_residual(St
 // runs the passes between two shared buffers -- the operations of k_wavelength_pass / k_mixture_residual<true> in their
 // order, bit for bit the same patterns -- and feeds the tile straight into the mixture sum.  The patterns cross HBM once
 // (read, + halo) instead of four times (pass: read + write, residual: read + write); with PYXRD_RESIDUALS_ONLY nothing is
-// written but the tile sums.  c2 (2048 candidates): wavelength + residual 168 -> see DESIGN.md section 3.
+// written but the tile sums.  c2 (2048 candidates): wavelength pass + residual kernel 168 us -> 121 us, bound by instruction
+// issue (measured: 4 blocks per SM at 64 registers beat 6 at 40 with spills; 8 candidates per block = 16 = 4).
 // ---------------------------------------------------------------------------------
 #define PX_FUSE_TPB 256
 #define PX_FUSE_T 512                  // points of a tile
@@ -2454,7 +2455,7 @@ __global__ void __launch_bounds__(PX_RES_TPB, PX_RES_MINB) k_mixture_residual(St
 #define PX_FUSE_SLOTS ((PX_FUSE_T + PX_FUSE_HMAX + PX_FUSE_TPB - 1) / PX_FUSE_TPB)
 #define PX_FUSE_MAXPASS 4
 #ifndef PX_FUSE_MINB
-#define PX_FUSE_MINB 4
+#define PX_FUSE_MINB 4                 // blocks per SM the register allocation aims at
 #endif
 #ifndef PX_FUSE_CPB
 #define PX_FUSE_CPB 8                  // candidates a block walks for its tile at most (grid.x = ceil(candidates / cpb); the host
