@@ -399,3 +399,45 @@ def test_fused_passes_for_every_list_length(calc, lines):
         ref = copy.deepcopy(mixes[k])
         orc.calculate_mixture(ref)
         assert rel_err(got[1][2][k], ref.residuals) < RTOL
+
+
+def test_fused_passes_on_ragged_shapes(calc):
+    """the tile + halo bookkeeping of k_patterns_residual on awkward shapes: pattern lengths around the tile size and below
+    the halo, a coarse grid (gathers that reach further), an exclusion window, two patterns per specimen (Z = 2) with a
+    None phase in one of them -- fused against the pass kernels bit for bit, and against the oracle"""
+    from pyxrd_b200.batched import pack_population
+    from pyxrd_b200.runtime import default_context
+    ctx = default_context()
+
+    def reshaped(npoints, lo, hi, seed):
+        out = []
+        for i in range(3):
+            m = syn.CONFIGS["c4"].candidate(seed, i)
+            for si, spec in enumerate(m.specimens):
+                theta = np.radians(np.linspace(lo, hi, npoints + 7 * si) / 2.0)
+                new = syn.make_specimen(theta, spec.phases[0], spec.goniometer, exclusion=(12.0, 12.6) if si == 0 else None)
+                new.goniometer.wavelength_distribution = list(syn.CU_PAIR)
+                m.specimens[si] = new
+            out.append(_observed(m, seed=seed))
+        return out
+
+    cases = [reshaped(511, 3.0, 45.0, 3), reshaped(513, 3.0, 45.0, 4), reshaped(1030, 20.0, 110.0, 5), reshaped(40, 5.0, 30.0, 6),
+             [syn.z2_case(), syn.z2_case()]]
+    for mixes in cases:
+        static, batch = pack_population(mixes)
+        got = {}
+        with ctx.lock:
+            for flag in (1, 0):
+                ctx.set_option("fuse_patterns", flag)
+                try:
+                    ctx.set_static(static, force=True)
+                    ctx.set_batch(batch)
+                    ctx.compute_all()
+                    got[flag] = [ctx.read_intensities_flat(), ctx.read_totals_flat(), ctx.read_residuals()]
+                finally:
+                    ctx.set_option("fuse_patterns", 1)
+        for a, b in zip(got[1], got[0]):
+            assert np.array_equal(a, b)
+        ref = copy.deepcopy(mixes[0])
+        orc.calculate_mixture(ref)
+        assert rel_err(got[1][2][0], ref.residuals) < RTOL
