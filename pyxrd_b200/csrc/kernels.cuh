@@ -2630,6 +2630,27 @@ __global__ void k_residual_finish(StaticDev st, BatchDev bt, int k0, int k1, int
     bt.residuals[(long long)k * (S + 1) + 1 + s] = (n > 0 && has_obs) ? num / den * 100.0 : 0.0;
 }
 
+// k_residual_finish + k_mixture_mean in one launch (Rp: nothing runs between them): thread per candidate, the tile sums of
+// its specimens in tile order, then the mean over the specimens -- the operations of the two kernels in their order
+__global__ void k_residual_finish_mean(StaticDev st, BatchDev bt, int k0, int k1, int ntiles, const double *__restrict__ partial) {
+    const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const int S = st.S;
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const double *pk = partial + ((long long)(k - k0) * S + s) * ntiles;
+        double num = 0.0;
+        for (int t = 0; t < ntiles; ++t) num += pk[t];
+        const double den = st.derived[s * 8 + 3];
+        const int n = st.Z * st.spec_npts[s];
+        const bool has_obs = st.gonio[s * 12 + 11] != 0.0;                                    // no observations -> 0.0 (mixture.py:247-251)
+        const double r = (n > 0 && has_obs) ? num / den * 100.0 : 0.0;
+        bt.residuals[(long long)k * (S + 1) + 1 + s] = r;
+        acc += r;
+    }
+    bt.residuals[(long long)k * (S + 1)] = acc / S;                                           // np.average(residuals[1:])
+}
+
 // ---------------------------------------------------------------------------------
 // Rpder (settings.RESIDUAL_METHOD = "Rpder", statistics.py:29-48, math_tools.py:46-99):
 //   Rp(gradient(smooth(exp, 15)), gradient(smooth(calc, 15))) on the CLIPPED patterns, i.e. the

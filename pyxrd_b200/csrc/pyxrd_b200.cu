@@ -1182,6 +1182,16 @@ int residuals_range(pyxrd_ctx *ctx, int k0, int k1, int flags, bool timed, const
                                                                              ctx->d_int.as<double>(), nullptr, ctx->d_partial.as<double>());
         LAUNCH_CHECK("k_mixture_residual");
         if (patterns_only) return 0;            // (intensities_range: the kernel was run for the patterns it stores)
+        if (ctx->residual_method == PYXRD_RESIDUAL_RP) {
+            k_residual_finish_mean<<<(k1 - k0 + 127) / 128, 128, 0, ctx->stream>>>(ctx->st, bt, k0, k1, ntiles, ctx->d_partial.as<double>());
+            LAUNCH_CHECK("k_residual_finish_mean");
+            ctx->have_totals = want_totals != 0;
+            if (timed) {
+                CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+                ctx->ev_set[2] = true;
+            }
+            return 0;
+        }
         k_residual_finish<<<((k1 - k0) * ctx->st.S + 127) / 128, 128, 0, ctx->stream>>>(ctx->st, bt, k0, k1, ntiles,
                                                                                       ctx->d_partial.as<double>());
         LAUNCH_CHECK("k_residual_finish");
