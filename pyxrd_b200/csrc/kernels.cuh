@@ -24,6 +24,7 @@
 #define PX_TPB 128          // threads (= 2-theta points) per block in the phase kernels
 #define PX_GEN_TPB 64       // generic-rank fallback
 #define PX_TABLE_PAD 1024    // doubles of slack after every per-point table (multi-point threads read past a pattern end)
+#define PX_IMG_HDR 74        // 8-byte words of the header block of PhaseSmem = first words of a phase image
 #define PX_TWO_PI 6.283185307179586        // python: 2 * math.pi
 #define PX_PI 3.141592653589793
 #define PX_SQRT2PI 2.5066282746310002      // math.sqrt(2 * pi)
@@ -138,9 +139,9 @@ struct BatchDev {
     const int *prob_model;           // [NP] PX_PROB_* (nullptr: every phase carries its W / P in the pool)
     const double *prob_params;       // [NP][PX_PROB_STRIDE] probability parameters of the model
     int *phase_valid;                // [NP]   derived: valid_probs (host flag, or the device model's verdict)
-    // derived by k_phase_planes: planes of a phase that sit at the same z in several components, listed once
+    // derived by px_planes_phase (k_phase_planes_image): planes of a phase that sit at the same z in several components, listed once
     int acap;                        // row stride of the three tables = most atoms of any phase
-    // phase images (k_phase_image): everything k_phase_small stages per block, laid out once per generation so that
+    // phase images (k_phase_prologue / k_phase_planes_image): everything k_phase_small stages per block, laid out once per generation so that
     // the staging is ONE round of independent loads instead of a chain of six dependent ones (+ three divisions):
     //   [PX_IMG_HDR header words][plane_arg AE][atom_po 2 AE][plane_end AE / 2][useg AE / 2][P R^2][WG G R] ... [coef ncap]
     double *phase_img;               // [NP][img_stride]
@@ -766,6 +767,33 @@ __global__ void k_leaf_probabilities(int model, int G, const double *par, double
 // the lanes; the sums are then taken by lane 0 in the order csds_series takes them, so both give the same bits.
 #define PX_PROLOGUE_WARPS 4
 #define PX_PROLOGUE_QCAP 512      // layer counts staged per warp; longer distributions take the serial path
+// coefficient half of the phase image (see k_phase_planes_image for the other half and the layout): mean / absolute
+// scale / ntop / flags, P, WG, coefficients -- by the warp that has just computed them
+__device__ __forceinline__ void px_image_coef(const BatchDev &bt, const int pb, const int lane) {
+    const int *pi = bt.phase_i + pb * 8;
+    if (!(pi[4] & 1) || (pi[4] & 8)) return;                 // no components / raw pattern: no phase kernel reads an image
+    const int G = pi[0], R = pi[1];
+    double *img = bt.phase_img + (long long)pb * bt.img_stride;
+    if (lane < 3) img[lane] = bt.phase_x[pb * 4 + lane];
+    if (lane == 3) img[3] = (double)pi[4];
+    double *mat = img + PX_IMG_HDR + 4 * bt.img_ae;
+    if (R * R + G * R <= bt.img_mcap) {
+        const double *W = bt.matrices + pi[6];
+        const double *P = W + R * R;
+        const int REPS = R / G;
+        for (int i = lane; i < R * R; i += 32) mat[i] = P[i];
+        for (int i = lane; i < G * R; i += 32) {             // WG[c][K] = sum_{J in c} W[J][K]
+            const int c = i / R, K = i % R;
+            double acc = 0.0;
+            for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
+            mat[R * R + i] = acc;
+        }
+    }
+    double *cf = mat + bt.img_mcap;
+    const double *coef = bt.coef + (long long)pb * bt.ncap;
+    for (int i = lane; i < bt.ncap; i += 32) cf[i] = coef[i];
+}
+
 __global__ void __launch_bounds__(32 * PX_PROLOGUE_WARPS) k_phase_prologue(BatchDev bt) {
     __shared__ double sq[PX_PROLOGUE_WARPS][PX_PROLOGUE_QCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -814,26 +842,27 @@ __global__ void __launch_bounds__(32 * PX_PROLOGUE_WARPS) k_phase_prologue(Batch
             }
         }
     }
-    if (lane != 0) return;
-    // absolute scale, phases.py:48-66 (first G diagonal entries of W)
-    const double *W = bt.matrices + pi[6];
-    double vol = 0.0, d001 = 0.0, dens = 0.0;
-    for (int i = 0; i < G; ++i) {
-        const double *cd = bt.comp_d + bt.phase_comp[pi[5] + i] * 8;
-        const double w = W[i * r + i];
-        vol += cd[4] * w;
-        d001 += cd[0] * w;
-        dens += cd[5] * w / cd[4];
+    if (lane == 0) {
+        // absolute scale, phases.py:48-66 (first G diagonal entries of W)
+        const double *W = bt.matrices + pi[6];
+        double vol = 0.0, d001 = 0.0, dens = 0.0;
+        for (int i = 0; i < G; ++i) {
+            const double *cd = bt.comp_d + bt.phase_comp[pi[5] + i] * 8;
+            const double w = W[i * r + i];
+            vol += cd[4] * w;
+            d001 += cd[0] * w;
+            dens += cd[5] * w / cd[4];
+        }
+        const double mass = mean * (vol * vol) * dens;
+        px[0] = mean;
+        px[1] = (mass != 0.0) ? d001 / mass : 0.0;
+        px[2] = (double)ntop;
     }
-    const double mass = mean * (vol * vol) * dens;
-    px[0] = mean;
-    px[1] = (mass != 0.0) ? d001 / mass : 0.0;
-    px[2] = (double)ntop;
+    __syncwarp();
+    px_image_coef(bt, pb, lane);                             // (coefficients and phase_x were written by this warp)
 }
 
-__global__ void k_component_z(BatchDev bt) {
-    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= bt.NC) return;
+__device__ __forceinline__ void px_component_z(const BatchDev &bt, const int ci) {
     const double *cd = bt.comp_d + ci * 8;
     const int *cc = bt.comp_i + ci * 4;
     const double lattice_d = cd[3];
@@ -884,10 +913,13 @@ __global__ void __launch_bounds__(128) k_layer_table(StaticDev st, BatchDev bt) 
 // warp per phase: planes (runs of atoms with equal z inside a component) that occur at the same z in several
 // components of the phase -- the shared silicate layer of a mixed-layer phase -- are listed once, so that the phase
 // kernels evaluate exp(2 pi i z stl) once per DISTINCT plane.  Segment = (component, atom range) of one plane.
-__global__ void __launch_bounds__(32) k_phase_planes(BatchDev bt) {
-    const int pb = blockIdx.x, lane = threadIdx.x;
-    __shared__ double seg_z[PX_MAX_ATOMS];
-    __shared__ int seg_info[PX_MAX_ATOMS], seg_first[PX_MAX_ATOMS], seg_u[PX_MAX_ATOMS];
+struct PlanesSmem {
+    double seg_z[PX_MAX_ATOMS];
+    int seg_info[PX_MAX_ATOMS], seg_first[PX_MAX_ATOMS], seg_u[PX_MAX_ATOMS];
+};
+__device__ __forceinline__ void px_planes_phase(const BatchDev &bt, const int pb, const int lane, PlanesSmem *sm) {
+    double *seg_z = sm->seg_z;
+    int *seg_info = sm->seg_info, *seg_first = sm->seg_first, *seg_u = sm->seg_u;
     const int *pi = bt.phase_i + pb * 8;
     int *nu_out = bt.ph_nu + pb;
     if (!(pi[4] & 1) || (pi[4] & 8)) { if (lane == 0) *nu_out = 0; return; }
@@ -954,9 +986,8 @@ __global__ void k_leaf_csds(const double *pd, int nmin, int nmax, double *arr, d
 // phase kernels: shared-memory staging of one phase parameter block
 // ---------------------------------------------------------------------------------
 
-#define PX_IMG_HDR 74        // 8-byte words of the header block of PhaseSmem = first words of a phase image
 struct PhaseSmem {          // header living at the start of dynamic shared memory
-    // ---- header block: PX_IMG_HDR words, copied verbatim from the phase image (k_phase_image) by k_phase_small ----
+    // ---- header block: PX_IMG_HDR words, copied verbatim from the phase image (k_phase_planes_image) by k_phase_small ----
     double px[4];           // mean, absolute scale, ntop, phase flags (phase_x + phase_i[4])
     double lpf_all[8][4];   // per specimen: lpf_q, lpf_k1, lpf_k2, lpf_pol (lpf_consts)
     double comp_d001[8];
@@ -1095,7 +1126,7 @@ __device__ __forceinline__ void load_phase_lists(const BatchDev &bt, int pb, int
         lpf_setup(ps, bt.phase_d[pb * 8], derived_s);
     }
     if constexpr (DISTINCT) {
-        // plane_arg / plane_end written above are replaced by the distinct-plane tables of k_phase_planes (the writes
+        // plane_arg / plane_end written above are replaced by the distinct-plane tables of px_planes_phase (the writes
         // above and below touch the same addresses from different threads: order them)
         __syncthreads();
         const int nu = bt.ph_nu[pb];
@@ -1358,54 +1389,54 @@ __device__ __forceinline__ bool phase_is_invalid(const BatchDev &bt, int pb, int
 // independent loads.  ncu on c2 before this: 20 % of the warps' time went into the staging code of a block (long
 // scoreboard on the chain, math-pipe throttle on the divisions) for 4 % of the executed instructions.
 // ---------------------------------------------------------------------------------
-// Two parts, each at the end of the prologue chain it depends on (they run side by side on two streams):
-//   PART 0  lists, components, Lorentz-polarisation constants   after k_component_z -> k_phase_planes
-//   PART 1  mean / absolute scale / ntop / flags, P, WG, coefficients   after k_probabilities -> k_phase_prologue
-template <int PART>
-__global__ void __launch_bounds__(32) k_phase_image(StaticDev st, BatchDev bt) {
+// The image is written in two halves, each by the warp at the end of the prologue chain it depends on (the chains run side
+// by side on two streams):
+//   k_phase_prologue       mean / absolute scale / ntop / flags, P, WG, coefficients (px_image_coef)
+//   k_phase_planes_image   z-stretch of the phase's components -> distinct planes -> lists, components,
+//                          Lorentz-polarisation constants
+// k_phase_planes_image is the whole second chain in one launch, warp per phase: lane c stretches component c of the phase
+// (a component that several phases share is stretched by each of them: the same values to the same places), then the warp
+// takes the distinct planes and stages the lists exactly as a phase-kernel block would.  Three launches, each a latency
+// chain of its own, became one (c2: 9 + 8 + 12 us under ncu -> see DESIGN.md).
+union PlanesImageSmem {
+    PlanesSmem planes;
+    PhaseSmem phase;
+};
+// thread per component: the z-stretch as a launch of its own, for batches whose phases share components (each phase
+// stretching them again inside k_phase_planes_image costs more than the launch: c4, six phases over shared components)
+__global__ void k_component_z(BatchDev bt) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci < bt.NC) px_component_z(bt, ci);
+}
+__global__ void __launch_bounds__(32) k_phase_planes_image(StaticDev st, BatchDev bt, int stretch) {
+    __shared__ PlanesImageSmem sm;
     const int pb = blockIdx.x, lane = threadIdx.x;
     const int *pi = bt.phase_i + pb * 8;
+    const int G = pi[0];
+    if (stretch && (pi[4] & 1) && !(pi[4] & 8))
+        for (int c = lane; c < G; c += 32) px_component_z(bt, bt.phase_comp[pi[5] + c]);
+    __syncwarp();
+    px_planes_phase(bt, pb, lane, &sm.planes);
+    __syncwarp();
     if (!(pi[4] & 1) || (pi[4] & 8)) return;                 // no components / raw pattern: no phase kernel reads an image
-    const int G = pi[0], R = pi[1];
     double *img = bt.phase_img + (long long)pb * bt.img_stride;
     const int AE = bt.img_ae;
     double *pa = img + PX_IMG_HDR;
-    if constexpr (PART == 0) {
-        __shared__ PhaseSmem ps;
-        if (G > 1) load_phase_lists<true>(bt, pb, G, &ps, st.sumX, st.derived);
-        else load_phase_lists<false>(bt, pb, G, &ps, st.sumX, st.derived);
-        if (lane < st.S && lane < 8) lpf_consts(bt.phase_d[pb * 8], st.derived + lane * 8, ps.lpf_all[lane]);
-        __syncwarp();
-        for (int i = 4 + lane; i < PX_IMG_HDR; i += 32) img[i] = reinterpret_cast<const double *>(&ps)[i];
-        double2 *po = reinterpret_cast<double2 *>(pa + AE);
-        int *pe = reinterpret_cast<int *>(pa + 3 * AE), *us = pe + AE;
-        const int na = ps.n_atoms;
-        for (int i = lane; i < AE; i += 32) {                // (entries past the phase's counts are never read: zeros)
-            const bool in = i < na;
-            pa[i] = in ? ps.plane_arg[i] : 0.0;
-            po[i] = in ? ps.atom_po[i] : make_double2(0.0, 0.0);
-            pe[i] = in ? ps.plane_end[i] : 0;
-            us[i] = (in && G > 1) ? ps.useg[i] : 0;
-        }
-    } else {
-        if (lane < 3) img[lane] = bt.phase_x[pb * 4 + lane];
-        if (lane == 3) img[3] = (double)pi[4];
-        double *mat = pa + 4 * AE;
-        if (R * R + G * R <= bt.img_mcap) {
-            const double *W = bt.matrices + pi[6];
-            const double *P = W + R * R;
-            const int REPS = R / G;
-            for (int i = lane; i < R * R; i += 32) mat[i] = P[i];
-            for (int i = lane; i < G * R; i += 32) {         // WG[c][K] = sum_{J in c} W[J][K]
-                const int c = i / R, K = i % R;
-                double acc = 0.0;
-                for (int J = c * REPS; J < (c + 1) * REPS; ++J) acc += W[J * R + K];
-                mat[R * R + i] = acc;
-            }
-        }
-        double *cf = mat + bt.img_mcap;
-        const double *coef = bt.coef + (long long)pb * bt.ncap;
-        for (int i = lane; i < bt.ncap; i += 32) cf[i] = coef[i];
+    PhaseSmem &ps = sm.phase;
+    if (G > 1) load_phase_lists<true>(bt, pb, G, &ps, st.sumX, st.derived);
+    else load_phase_lists<false>(bt, pb, G, &ps, st.sumX, st.derived);
+    if (lane < st.S && lane < 8) lpf_consts(bt.phase_d[pb * 8], st.derived + lane * 8, ps.lpf_all[lane]);
+    __syncwarp();
+    for (int i = 4 + lane; i < PX_IMG_HDR; i += 32) img[i] = reinterpret_cast<const double *>(&ps)[i];
+    double2 *po = reinterpret_cast<double2 *>(pa + AE);
+    int *pe = reinterpret_cast<int *>(pa + 3 * AE), *us = pe + AE;
+    const int na = ps.n_atoms;
+    for (int i = lane; i < AE; i += 32) {                    // (entries past the phase's counts are never read: zeros)
+        const bool in = i < na;
+        pa[i] = in ? ps.plane_arg[i] : 0.0;
+        po[i] = in ? ps.atom_po[i] : make_double2(0.0, 0.0);
+        pe[i] = in ? ps.plane_end[i] : 0;
+        us[i] = (in && G > 1) ? ps.useg[i] : 0;
     }
 }
 
@@ -1451,7 +1482,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     if (xblock >= X || phase_is_invalid(bt, pb, job, X, xblock, TPB * PPT * TILES)) return;
     constexpr bool DISTINCT = G > 1;        // one component: nothing to share between components
     {
-        // staging from the phase image (k_phase_image): one round of independent loads
+        // staging from the phase image (k_phase_prologue + k_phase_planes_image): one round of independent loads
         const double *img = bt.phase_img + (long long)pb * bt.img_stride;
         const int AE = bt.img_ae;
         double *hdr = reinterpret_cast<double *>(ps);

@@ -926,11 +926,11 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
 
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
     // Two independent chains and one independent kernel, side by side (the kernels are small and latency-bound):
-    //   probabilities -> phase prologue (CSDS, absolute scale)          on the context's stream
-    //   interlayer z-stretch -> distinct planes of every phase          on an auxiliary stream
+    //   probabilities -> phase prologue (CSDS, absolute scale, coefficient half of the phase images)   on the context's stream
+    //   interlayer z-stretch -> distinct planes -> list half of the phase images (one kernel)          on an auxiliary stream
     //   layer tables (only when the classes or the static tables changed)  on another one
     cudaStream_t main_stream = ctx->stream;
-    const bool side = ctx->overlap_classes && NP > 0 && NC > 0;
+    const bool side = ctx->overlap_classes && NP > 0;
     const bool need_tables = z.n_classes > 0 && st.sumX > 0 && !keep_layer_tables;
     if (side) {
         CK(cudaEventRecord(ctx->fork_ev, main_stream));
@@ -942,19 +942,17 @@ int bind_batch(pyxrd_ctx *ctx, const BatchSizes &z, const BlobLayout &L, int nca
         LAUNCH_CHECK("k_probabilities");
         k_phase_prologue<<<(NP + PX_PROLOGUE_WARPS - 1) / PX_PROLOGUE_WARPS, 32 * PX_PROLOGUE_WARPS, 0, main_stream>>>(bt);
         LAUNCH_CHECK("k_phase_prologue");
-        k_phase_image<1><<<NP, 32, 0, main_stream>>>(st, bt);
-        LAUNCH_CHECK("k_phase_image");
     }
     cudaStream_t z_stream = side ? ctx->class_stream[0] : main_stream;
-    if (NC > 0) {
-        k_component_z<<<(NC + 63) / 64, 64, 0, z_stream>>>(bt);
-        LAUNCH_CHECK("k_component_z");
-    }
     if (NP > 0) {
-        k_phase_planes<<<NP, 32, 0, z_stream>>>(bt);
-        LAUNCH_CHECK("k_phase_planes");
-        k_phase_image<0><<<NP, 32, 0, z_stream>>>(st, bt);
-        LAUNCH_CHECK("k_phase_image");
+        // components referenced by several phases are stretched once, by a launch of their own
+        const bool shared_components = z.NPC > z.NC;
+        if (shared_components && NC > 0) {
+            k_component_z<<<(NC + 63) / 64, 64, 0, z_stream>>>(bt);
+            LAUNCH_CHECK("k_component_z");
+        }
+        k_phase_planes_image<<<NP, 32, 0, z_stream>>>(st, bt, shared_components ? 0 : 1);   // (z-stretch ->) distinct planes -> list half of the images
+        LAUNCH_CHECK("k_phase_planes_image");
     }
     if (need_tables) {
         dim3 grid((unsigned)((st.sumX + 127) / 128), (unsigned)z.n_classes);
