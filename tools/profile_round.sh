@@ -12,6 +12,6 @@ capture() {   # name, kernel regex, skip, count, extra bench flags
 }
 capture small22 k_phase_small 2 1 --no-trials
 capture optimize k_mixture_optimize 1 1 ""
-capture prologue "k_expand_population|k_phase_planes|k_phase_prologue|k_probabilities|k_phase_image" 6 6 --no-trials
-capture stream "k_wavelength_pass|k_mixture_residual|k_patterns_residual" 2 2 --no-trials
+capture prologue "k_expand_population|k_phase_planes_image|k_phase_prologue|k_probabilities" 4 4 --no-trials
+capture stream "k_wavelength_pass|k_mixture_residual|k_patterns_residual|k_residual_finish_mean" 2 2 --no-trials
 ls -la gpurun_out/${TAG}_*
