@@ -1473,7 +1473,11 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     double *sP = reinterpret_cast<double *>(smem_raw + sizeof(PhaseSmem));   // [R][R]
     double *sWG = sP + R * R;                                               // [G][R]
     double *sCoef = sWG + G * R;                                            // [ntop+1]
-    double2 *sSct = reinterpret_cast<double2 *>(smem_raw + bt.img_sct_off);   // [PX_SCT_N] (sin, cos)(k pi / 64), px_sincos_tab_n
+    // the sine / cosine table: a copy in shared memory for the instantiations that are at their register limit anyway
+    // (MINB > 0: the c2 kernel, 16 blocks per SM), the global table through the read-only path for the others -- their
+    // occupancy is limited by shared memory, and 2 KB more per block would cost blocks (c1: 25 -> 20 per SM)
+    constexpr bool SCT_SMEM = PX_SCT_SMEM && MINB > 0;
+    double2 *sSct = reinterpret_cast<double2 *>(smem_raw + bt.img_sct_off);   // [PX_SCT_N] (sin, cos)(k pi / 64), px_sincos_n
 
     const int job = jobs[blockIdx.x];
     const int pb = bt.job_pb[job], s = bt.job_spec[job];
@@ -1502,7 +1506,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
         for (int i = threadIdx.x; i < G * R; i += TPB) sWG[i] = mat[R * R + i];
         const double *cf = mat + bt.img_mcap;
         for (int i = threadIdx.x; i < bt.img_ncopy; i += TPB) sCoef[i] = cf[i];
-        if (PX_SCT_SMEM)
+        if constexpr (SCT_SMEM)
             for (int i = threadIdx.x; i < PX_SCT_N; i += TPB) sSct[i] = reinterpret_cast<const double2 *>(PX_SCT)[i];
     }
     __syncthreads();
@@ -1520,10 +1524,10 @@ __global__ void __launch_bounds__(TPB, MINB) k_phase_small(StaticDev st, BatchDe
     for (int k = 0; k < PPT; ++k) stl[k] = st.stl[gx + k * TPB];
 
     double ur[G][PPT], ui[G][PPT], pr[G][PPT], pim[G][PPT], gr[G][PPT], gi[G][PPT];
-    if constexpr (DISTINCT) phase_factors_n<G, PPT, PX_SCT_SMEM>(ps, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur, ui, pr, pim, sSct);
+    if constexpr (DISTINCT) phase_factors_n<G, PPT, SCT_SMEM>(ps, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur, ui, pr, pim, sSct);
 #pragma unroll
     for (int c = 0; c < G; ++c) {
-        if constexpr (!DISTINCT) component_factors_n<PPT, PX_SCT_SMEM>(ps, c, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur[c], ui[c], pr[c], pim[c], sSct);
+        if constexpr (!DISTINCT) component_factors_n<PPT, SCT_SMEM>(ps, c, stl, st.asf + gx, bt.layer_tab + gx, TPB, ur[c], ui[c], pr[c], pim[c], sSct);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             gr[c][k] = pr[c][k] * ur[c][k] + pim[c][k] * ui[c][k];          // g = phi * conj(u)

@@ -222,7 +222,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 size_t small_sct_offset(int R, int G, int ntop_cap) {
     return align_up(sizeof(PhaseSmem) + sizeof(double) * (size_t)(R * R + G * R + ntop_cap + 2), 16);
 }
-size_t small_smem(int R, int G, int ntop_cap) { return small_sct_offset(R, G, ntop_cap) + sizeof(double2) * PX_SCT_N; }
+size_t small_smem(int R, int G, int ntop_cap, bool table) { return small_sct_offset(R, G, ntop_cap) + (table ? sizeof(double2) * PX_SCT_N : 0); }
 size_t staged_smem(int R, int G, int ntop_cap) {
     const int RB = (R + 3) / 4;
     return sizeof(PhaseSmem) + sizeof(double) * (size_t)(RB * R * 4 + G * R + (G * R & 1)) +
@@ -259,7 +259,7 @@ int set_smem(pyxrd_ctx *ctx, K kernel, size_t bytes) {
 template <int R, int G, int PPT, int TPB, int MINB = 0, int STRUCT = 0, int TILES = 1>
 int launch_small(pyxrd_ctx *ctx, const RankClass &rc, const int *jobs_dev, size_t njobs, const BatchDev &bt) {
     static_assert((PPT - 1) * TPB <= PX_TABLE_PAD, "table padding too small");
-    const size_t smem = small_smem(R, G, rc.max_ntop_cap);
+    const size_t smem = small_smem(R, G, rc.max_ntop_cap, PX_SCT_SMEM && MINB > 0);
     if (set_smem(ctx, k_phase_small<R, G, PPT, TPB, MINB, STRUCT, TILES>, smem)) return 1;
     dim3 grid((unsigned)njobs, (unsigned)((rc.max_x + TPB * PPT * TILES - 1) / (TPB * PPT * TILES)));
     BatchDev b2 = bt;
